@@ -1,0 +1,185 @@
+/*
+ * pasero_b200 — C ABI of the B200-native kernels behind Pasero's speech-translation training step.
+ *
+ * The reference (naver/pasero) is pure Python and has no FFI of its own; its extension surface is the
+ * Python model/task registry (pasero/config.py:91-135). These entry points are what the Python host
+ * layer (pasero_b200/*.py, mirroring pasero.models / pasero.tasks / pasero.training) binds with ctypes;
+ * each declaration cites the reference code whose work it takes over.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pb200_last_error_string() describes the
+ *     last failure on the calling thread. Nothing throws, nothing aborts.
+ *   - the caller owns every buffer, including workspaces (sizes from pb200_*_workspace_bytes); the
+ *     library never allocates or frees device memory.
+ *   - all work is asynchronous and ordered on `stream` (a cudaStream_t passed as void*); no host
+ *     synchronisation, no global mutable state apart from read-only tables => CUDA-graph capturable.
+ *   - device = the CUDA context current on the calling thread. Pointers are device pointers unless
+ *     stated otherwise, 16-byte aligned, row-major, bf16 for activations/weights, fp32/fp64 statistics.
+ *   - there is no CPU fallback: without a GPU every compute entry point fails with a CUDA error.
+ */
+#ifndef PASERO_B200_H
+#define PASERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+int32_t pb200_abi_version(void);
+const char* pb200_last_error_string(void);
+/* number of SMs of the current device (148 on B200); <= 0 when no device is usable */
+int32_t pb200_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Audio frontend — fused log-mel fbank (+ utterance CMVN).
+ * Oracle: torchaudio.compliance.kaldi.fbank(wave * 2**15, num_mel_bins=80, sample_frequency=16000)
+ * (kaldi.py:514-646) followed by per-utterance mean/variance normalisation; the reference itself only
+ * consumes pre-extracted features (pasero/files.py:103-192, pasero/tasks/speech_translation.py:42-86).
+ *   pcm            fp32 samples of all utterances, concatenated
+ *   sample_offsets int64[batch+1] start of each utterance in `pcm` (device)
+ *   frame_offsets  int64[batch+1] start row of each utterance in `feats` (device);
+ *                  frames(b) = 1 + (samples(b) - 400) / 160  (pb200_fbank_num_frames)
+ *   max_frames     host-side upper bound on frames per utterance (grid sizing)
+ *   pcm_scale      multiplier applied to samples on load (32768 for [-1,1) floats)
+ *   feats          fp32 [total_frames, 80] out; normalised in place when cmvn != 0
+ *   feats_bf16_padded  optional bf16 [batch, padded_frames, 80]: features of utterance b at rows
+ *                  [front_pad, front_pad + frames(b)), zeros elsewhere (conv subsampler input layout)
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_fbank_init(void);
+int64_t pb200_fbank_num_frames(int64_t num_samples);
+size_t pb200_fbank_workspace_bytes(int32_t batch);
+int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets, const int64_t* frame_offsets, int32_t batch,
+                     int32_t max_frames, float pcm_scale, int32_t cmvn, float* feats, void* feats_bf16_padded,
+                     int32_t padded_frames, int32_t front_pad, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05/TMEM with TMA-fed operands:  C[z] = epilogue(alpha * op(A[z]) op(B[z])^T)
+ * op(A) is [m x k], op(B) is [n x k]. An operand is "K-major" when its reduction dimension is the
+ * contiguous one (x_mn_major = 0: stored [rows = m|n][cols = k]) and "MN-major" otherwise
+ * (x_mn_major = 1: stored [rows = k][cols = m|n]). ld* = elements between stored rows (may be smaller
+ * than the row length: overlapping rows express the strided-conv im2col view without materialising it).
+ * Takes over nn.Linear / nn.Conv1d / Embedding.projection of the reference
+ * (pasero/models/modules.py:610-615, 737, 829-834, 935-947; transformer.py:999-1019, 1224-1244).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pb200_gemm_params {
+    const void* a;
+    const void* b;
+    void* c;
+    int64_t m, n, k;
+    int64_t batch;            /* number of z slices (>= 1) */
+    int64_t lda, ldb, ldc;
+    int64_t a_batch_stride, b_batch_stride, c_batch_stride; /* elements; 0 = operand shared by all z */
+    int32_t a_mn_major, b_mn_major;
+    int32_t reduce_batch;     /* 1: C = sum_z op(A[z]) op(B[z])^T (weight gradients over utterances) */
+    const void* bias;         /* bf16 [n] or NULL */
+    const void* residual;     /* bf16, C layout, added after the activation, or NULL */
+    const void* relu_mask;    /* bf16, C layout: result zeroed where mask <= 0 (ReLU backward), or NULL */
+    int32_t act;              /* 0 none, 1 ReLU, 2 GELU (erf) */
+    int32_t out_fp32;         /* 0: C is bf16, 1: C is fp32 */
+    int32_t accumulate;       /* 1: C += result */
+    float alpha;
+    int32_t split_k;          /* 0 = choose automatically, >= 1 = force */
+    int32_t tile_n;           /* 0 = choose automatically, 128 or 256 = force */
+    void* workspace;          /* fp32 split-K partials; may be NULL when split_k == 1 */
+    size_t workspace_bytes;
+} pb200_gemm_params;
+
+size_t pb200_gemm_workspace_bytes(int64_t m, int64_t n, int64_t batch, int32_t max_splits);
+int pb200_gemm_bf16(const pb200_gemm_params* params, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-head attention, head_dim 64, length-masked (kv_len) and/or causal; replaces
+ * MultiheadAttention.forward's SDPA / flash-attn call (pasero/models/modules.py:648-734).
+ * q/k/v rows are tokens ([B*L, ld]), head h occupies columns [h*64, h*64+64) from the given pointer.
+ * lse: fp32 [B, H, Lq] (written by fwd, read by bwd); delta: fp32 [B, H, Lq] scratch written by bwd.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pb200_attn_params {
+    const void* q; const void* k; const void* v;
+    void* o;
+    float* lse;
+    const int32_t* kv_len;    /* int32 [B] valid key count per batch element, or NULL */
+    int64_t ldq, ldk, ldv, ldo;
+    int32_t B, H, Lq, Lk, head_dim;
+    int32_t causal;
+    float scale;              /* 1/sqrt(head_dim) when `scaled` */
+    /* backward only */
+    const void* dout; int64_t lddo;
+    float* delta;
+    void* dq; void* dk; void* dv;
+    int64_t lddq, lddk, lddv;
+} pb200_attn_params;
+
+int pb200_attention_fwd(const pb200_attn_params* params, void* stream);
+int pb200_attention_bwd(const pb200_attn_params* params, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * sum = residual + dropout(x);  y = LayerNorm(sum) * gamma + beta   (gamma == NULL: no LayerNorm)
+ * (pasero/models/transformer.py:1043-1054, 1073-1086, 1322-1339, 1389-1409). Dropout mask =
+ * Philox(seed, offset, element / 8); backward regenerates it.
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta, int64_t M,
+                             int64_t D, float eps, float p, uint64_t seed, uint64_t offset, void* sum_out, void* y_out,
+                             float* mean_out, float* rstd_out, void* stream);
+size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
+int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
+                             const float* mean, const float* rstd, int64_t M, int64_t D, float p, uint64_t seed,
+                             uint64_t offset, void* dresidual, void* dx, void* dgamma, void* dbeta, int32_t accumulate,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* column sums of a bf16 [M, N] matrix -> bf16 [N] (bias gradients) */
+size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);
+int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out, int32_t accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding epilogue: out[r] = dropout(bf16(bf16(src_row * scale) + pos[r % L])), src_row = src[ids[r]]
+ * when ids != NULL else src[r]   (pasero/models/transformer.py:739-744, 874-878; modules.py:415-457,916-933)
+ * Backward: dx (no ids) or fp32 atomics into dtable[ids[r]] (rows == padding_idx skipped).
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_embed_fwd(const int64_t* ids, const void* src, const void* pos, int64_t M, int64_t D, int64_t L, float scale,
+                    float p, uint64_t seed, uint64_t offset, int64_t num_embeddings, void* out, void* stream);
+int pb200_embed_bwd(const void* dy, const int64_t* ids, int64_t M, int64_t D, float scale, float p, uint64_t seed,
+                    uint64_t offset, int64_t padding_idx, int64_t num_embeddings, void* dx, float* dtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv subsampler pieces (pasero/models/modules.py:774-834): GLU over channels writing the next conv's
+ * zero-padded input layout, its backward, the col2im gather of the strided-conv input gradient, and the
+ * zero-padding copy of the first conv's input.
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_glu_fwd(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
+int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t C, void* din, void* stream);
+int pb200_gelu_bwd(const void* dy, const void* pre, int64_t n, void* dx, void* stream);
+int pb200_col2im(const void* dcol, int32_t B, int32_t Tin, int32_t Tout, int32_t C, int32_t KW, int32_t stride,
+                 void* dx, void* stream);
+int pb200_pad_rows(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
+int pb200_f32_to_bf16(const float* in, int64_t n, void* out, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Label-smoothed cross-entropy over bf16 logits [B*T, V] (row stride ld), targets int64 read as
+ * target[b * target_stride0 + t]; rows whose target == padding_idx contribute nothing. Overwrites the
+ * logits with d loss / d logits (bf16) when write_grad != 0. stats (fp64): [0] += loss (nats, summed),
+ * [1] += nll (nats, summed), [2] += number of non-pad targets.  (pasero/models/transformer.py:323-380)
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T, int64_t V,
+                        int64_t ld, int64_t padding_idx, float label_smoothing, float grad_scale, int32_t write_grad,
+                        double* stats, float* row_loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer over the flat arenas (pasero/training.py:455-487; pasero/optimization.py:56-149, 390-427).
+ *   hyper fp32[16] (device): [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] 1-beta1^t
+ *        [6] sqrt(1-beta2^t) [7] clip_norm [8] dp_size [9] 1-beta1 [10] 1-beta2 [11] lr/(1-beta1^t)
+ *        [12] weight_decay*lr
+ *   stats fp64[8] (device): [2] num_tokens (gradient divisor), [4] squared gradient norm (in/out)
+ * ---------------------------------------------------------------------------------------------- */
+int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* stream);
+int pb200_adam_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
+                    const double* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASERO_B200_H */

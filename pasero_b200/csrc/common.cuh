@@ -1,0 +1,124 @@
+// pasero_b200 — shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace pb200 {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (C-ABI: every entry point returns 0 or a non-zero code; the text of the last
+// failure on this thread is available from pb200_last_error_string())
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define PB_CHECK(cond, ...)                                  \
+    do {                                                     \
+        if (!(cond)) {                                       \
+            ::pb200::set_error(__VA_ARGS__);                 \
+            return 1;                                        \
+        }                                                    \
+    } while (0)
+
+#define PB_CUDA(expr)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::pb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                               __FILE__, __LINE__);                                       \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define PB_LAUNCH_CHECK()                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = cudaPeekAtLastError();                                           \
+        if (_e != cudaSuccess) {                                                          \
+            ::pb200::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),\
+                               __FILE__, __LINE__);                                       \
+            return 3;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ float bf16_to_f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f_to_bf16(float x) { return __float2bfloat16_rn(x); }
+// round an fp32 value to bf16 precision and come back (emulates the reference's bf16 in-place ops)
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    bf162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+    bf162 h = *reinterpret_cast<bf162*>(&v);
+    return __bfloat1622float2(h);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG. Dropout masks are a pure function of (seed, offset, element
+// index) so the backward kernels regenerate them instead of storing a mask tensor.
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t key0, key1;
+    __device__ __forceinline__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t counter, uint64_t stream) const {
+        uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
+        uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+        uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+// keep-mask for 8 consecutive elements starting at element index `idx8*8`.
+// Each 32-bit Philox word yields two 16-bit uniforms; keep iff u16 >= p*65536.
+__device__ __forceinline__ uint32_t dropout_keep8(const Philox& rng, uint64_t offset, uint64_t idx8,
+                                                  uint32_t thresh16) {
+    uint4 r = rng(idx8, offset);
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m |= ((w[i] & 0xffffu) >= thresh16 ? 1u : 0u) << (2 * i);
+        m |= ((w[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
+    float t = p * 65536.0f;
+    return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : (uint32_t)(t + 0.5f));
+}
+
+}  // namespace pb200

@@ -1,0 +1,505 @@
+// pasero_b200 — persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   C[z] = epilogue( alpha * op(A[z]) * op(B[z])^T )        op(A): [M x K], op(B): [N x K]
+//
+// TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages operand tiles in shared memory, one elected thread
+// issues tcgen05.mma (128 x BN x 16, bf16 in, fp32 accumulate) into a double-buffered TMEM
+// accumulator, and four epilogue warps drain TMEM with tcgen05.ld while the next tile's main loop
+// is already running. Both operands may be K-major (reduction dim contiguous) or MN-major, so the
+// same kernel serves forward (X W^T), dgrad (dY W) and wgrad (dY^T X) without transposes.
+//
+// Replaces the cuBLASLt / cuDNN calls behind nn.Linear / nn.Conv1d / Embedding.projection in the
+// reference (pasero/models/modules.py:610-615,737,829-834,935-947; transformer.py:999-1019).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/pasero_b200.h"
+
+#include <mutex>
+
+namespace pb200 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 256;
+
+struct GemmDev {
+    int M, N;
+    int Z;               // batches iterated as independent output problems (1 when reduce_batch)
+    int kb_per;          // k-blocks per batch slice = ceil(K / BK)
+    int total_kb;        // k-blocks in the whole reduction (kb_per * Zred)
+    int kb_per_split;    // k-blocks handled by one split
+    int splits;
+    int m_blks, n_blks;
+    int reduce_batch;
+    int a_batched, b_batched;
+    // epilogue
+    void* c;
+    long long ldc, c_batch_stride;
+    const bf16* bias;
+    const bf16* residual;
+    const bf16* relu_mask;
+    int act, out_fp32, accumulate;
+    float alpha;
+    float* partial;      // split-K partials [split][Z][M][N] fp32
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 128) ? 6 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const GemmDev p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tma);
+        ptx::prefetch_tmap(&tmb);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full[i], 1);
+            ptx::mbar_init(&tmem_empty[i], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int tiles_per_z = p.m_blks * p.n_blks * p.splits;
+    const int total_tiles = p.Z * tiles_per_z;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int r = tile;
+                const int split = r % p.splits; r /= p.splits;
+                const int n_blk = r % p.n_blks; r /= p.n_blks;
+                const int m_blk = r % p.m_blks; r /= p.m_blks;
+                const int z = r;
+                const int m0 = m_blk * BM, n0 = n_blk * BN;
+                const int kb_begin = split * p.kb_per_split;
+                const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    const int zk = p.reduce_batch ? (kb / p.kb_per) : z;
+                    const int k0 = (kb % p.kb_per) * BK;
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    const int za = p.a_batched ? zk : 0;
+                    const int zb = p.b_batched ? zk : 0;
+                    if (!A_MN) {
+                        ptx::tma_load_3d(&tma, &full_bar[stage], sa, k0, m0, za);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            ptx::tma_load_3d(&tma, &full_bar[stage], sa + j * (BK * 128), m0 + j * 64, k0, za);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_3d(&tmb, &full_bar[stage], sb, k0, n0, zb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            ptx::tma_load_3d(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, k0, zb);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                const int split = tile % p.splits;
+                const int kb_begin = split * p.kb_per_split;
+                const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: 8-row groups 1024 B apart, advance 32 B per UMMA_K inside the 128 B row.
+                        // MN-major: 64-element column blocks (BK*128 B apart, LBO), 8-k-row groups 1024 B
+                        // apart (SBO), advance 16 k-rows = 2048 B per UMMA_K.
+                        const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                                    : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                                    : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps (TMEM -> registers -> global) =====================
+        const int ew = warp & 3;  // TMEM lane quarter this warp may access
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            int r = tile;
+            const int split = r % p.splits; r /= p.splits;
+            const int n_blk = r % p.n_blks; r /= p.n_blks;
+            const int m_blk = r % p.m_blks; r /= p.m_blks;
+            const int z = r;
+            const int n0 = n_blk * BN;
+            const int row = m_blk * BM + ew * 32 + lane;
+            const bool row_ok = row < p.M;
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int kb_begin = split * p.kb_per_split;
+            const bool empty_range = kb_begin >= p.total_kb;
+
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+                ptx::tmem_ld_32x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (!row_ok || col0 >= p.N) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = empty_range ? 0.f : __uint_as_float(v[j]);
+
+                if (p.splits > 1) {
+                    float* dst = p.partial + (((long long)split * p.Z + z) * p.M + row) * (long long)p.N + col0;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (col0 + g * 4 < p.N)
+                            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                    continue;
+                }
+                const long long coff = (long long)z * p.c_batch_stride + (long long)row * p.ldc + col0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {  // groups of 8 columns
+                    if (col0 + g * 8 >= p.N) break;
+                    float* x = f + g * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] *= p.alpha;
+                    if (p.bias) {
+                        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + g * 8));
+                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 b2 = unpack_bf16x2(bw[j]);
+                            x[2 * j] += b2.x; x[2 * j + 1] += b2.y;
+                        }
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+                    }
+                    if (p.relu_mask) {
+                        const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + coff + g * 8));
+                        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 m2 = unpack_bf16x2(mw[j]);
+                            if (!(m2.x > 0.f)) x[2 * j] = 0.f;
+                            if (!(m2.y > 0.f)) x[2 * j + 1] = 0.f;
+                        }
+                    }
+                    if (p.residual) {
+                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + coff + g * 8));
+                        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r2 = unpack_bf16x2(rw[j]);
+                            x[2 * j] += r2.x; x[2 * j + 1] += r2.y;
+                        }
+                    }
+                    if (p.out_fp32) {
+                        float* dst = reinterpret_cast<float*>(p.c) + coff + g * 8;
+                        if (p.accumulate) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(dst);
+                            const float4 o1 = *reinterpret_cast<const float4*>(dst + 4);
+                            x[0] += o0.x; x[1] += o0.y; x[2] += o0.z; x[3] += o0.w;
+                            x[4] += o1.x; x[5] += o1.y; x[6] += o1.z; x[7] += o1.w;
+                        }
+                        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                    } else {
+                        bf16* dst = reinterpret_cast<bf16*>(p.c) + coff + g * 8;
+                        if (p.accumulate) {
+                            const uint4 ov = *reinterpret_cast<const uint4*>(dst);
+                            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 o2 = unpack_bf16x2(ow[j]);
+                                x[2 * j] += o2.x; x[2 * j + 1] += o2.y;
+                            }
+                        }
+                        uint4 ov;
+                        ov.x = pack_bf16x2(x[0], x[1]); ov.y = pack_bf16x2(x[2], x[3]);
+                        ov.z = pack_bf16x2(x[4], x[5]); ov.w = pack_bf16x2(x[6], x[7]);
+                        *reinterpret_cast<uint4*>(dst) = ov;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-K reduction: out = alpha * sum_s partial[s] (+bias) (+ old out) ; bf16 or fp32 out
+// ------------------------------------------------------------------------------------------------
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long zmn, int M, int N,
+                                     void* out, long long ldc, long long c_batch_stride, int out_fp32,
+                                     int accumulate, float alpha, const float* __restrict__ extra_fp32) {
+    const long long n4 = zmn / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < splits; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (long long)k * zmn + e));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        s.x *= alpha; s.y *= alpha; s.z *= alpha; s.w *= alpha;
+        if (extra_fp32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(extra_fp32 + e));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const int col = (int)(e % N);
+        const long long rz = e / N;
+        const int row = (int)(rz % M);
+        const long long z = rz / M;
+        const long long off = z * c_batch_stride + (long long)row * ldc + col;
+        if (out_fp32) {
+            float* dst = reinterpret_cast<float*>(out) + off;
+            if (accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst) = s;
+        } else {
+            bf16* dst = reinterpret_cast<bf16*>(out) + off;
+            if (accumulate) {
+                const uint2 o = *reinterpret_cast<const uint2*>(dst);
+                const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
+                s.x += a.x; s.y += a.y; s.z += b.x; s.w += b.y;
+            }
+            uint2 o;
+            o.x = pack_bf16x2(s.x, s.y); o.y = pack_bf16x2(s.z, s.w);
+            *reinterpret_cast<uint2*>(dst) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// Tensor map over a bf16 matrix stored as `rows` x `cols` (cols contiguous), `ld` elements between
+// rows, `batch` slices `batch_stride` elements apart; box = box_cols x box_rows x 1, SWIZZLE_128B.
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+                     long long batch, long long batch_stride, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    PB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    PB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm operand pointer must be 16-byte aligned");
+    PB_CHECK(ld % 8 == 0, "gemm operand leading dimension (%lld) must be a multiple of 8 elements", ld);
+    PB_CHECK(batch <= 1 || batch_stride % 8 == 0, "gemm operand batch stride (%lld) must be a multiple of 8", batch_stride);
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+    long long bs = (batch > 1 && batch_stride > 0) ? batch_stride : rows * ld;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld batch=%lld bstride=%lld box=%dx%d",
+             (int)r, rows, cols, ld, batch, bs, box_cols, box_rows);
+    return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid, cudaStream_t stream) {
+    auto kern = gemm_kernel<BN, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, d);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" size_t pb200_gemm_workspace_bytes(int64_t m, int64_t n, int64_t batch, int32_t max_splits) {
+    if (max_splits < 1) max_splits = 1;
+    return (size_t)max_splits * (size_t)(batch > 0 ? batch : 1) * (size_t)m * (size_t)n * sizeof(float);
+}
+
+extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PB_CHECK(q != nullptr, "null params");
+    PB_CHECK(q->m > 0 && q->n > 0 && q->k > 0, "gemm dims must be positive (m=%lld n=%lld k=%lld)",
+             (long long)q->m, (long long)q->n, (long long)q->k);
+    PB_CHECK(q->n % 8 == 0, "gemm N (%lld) must be a multiple of 8", (long long)q->n);
+    PB_CHECK(q->ldc % 8 == 0, "gemm ldc must be a multiple of 8");
+    const long long Zall = q->batch > 0 ? q->batch : 1;
+    const bool a_mn = q->a_mn_major != 0, b_mn = q->b_mn_major != 0;
+
+    // tile width: wide tiles when N is large enough to keep >= ~1 wave of CTAs busy
+    const long long m_blks = (q->m + BM - 1) / BM;
+    const long long Zout = q->reduce_batch ? 1 : Zall;
+    int bn = 128;
+    if (q->n >= 256 && q->tile_n != 128) {
+        const long long tiles256 = Zout * m_blks * ((q->n + 255) / 256);
+        if (tiles256 >= 2LL * num_sms() || q->tile_n == 256) bn = 256;
+    }
+    const long long n_blks = (q->n + bn - 1) / bn;
+    const long long kb_per = (q->k + BK - 1) / BK;
+    const long long total_kb = kb_per * (q->reduce_batch ? Zall : 1);
+    const long long out_tiles = Zout * m_blks * n_blks;
+
+    long long splits = q->split_k;
+    if (splits <= 0) {
+        splits = 1;
+        if (out_tiles * 2 <= num_sms()) splits = num_sms() / out_tiles;
+    }
+    if (splits > total_kb) splits = total_kb;
+    if (splits > 1) {
+        const size_t per_split = (size_t)Zout * q->m * q->n * sizeof(float);
+        const long long fit = q->workspace ? (long long)(q->workspace_bytes / per_split) : 0;
+        if (splits > fit) splits = fit;
+        if (splits < 1) splits = 1;
+    }
+    long long kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per_split - 1) / kb_per_split;
+    if (splits > 1) {
+        PB_CHECK(q->relu_mask == nullptr && q->residual == nullptr && q->act == 0 && q->bias == nullptr,
+                 "split-K path supports only alpha/accumulate epilogues");
+    }
+
+    CUtensorMap ta, tb;
+    int rc;
+    if (!a_mn) rc = make_tmap(&ta, q->a, q->m, q->k, q->lda, Zall, q->a_batch_stride, BK, BM);
+    else rc = make_tmap(&ta, q->a, q->k, q->m, q->lda, Zall, q->a_batch_stride, 64, BK);
+    if (rc) return rc;
+    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn);
+    else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zall, q->b_batch_stride, 64, BK);
+    if (rc) return rc;
+
+    GemmDev d;
+    d.M = (int)q->m; d.N = (int)q->n; d.Z = (int)Zout;
+    d.kb_per = (int)kb_per; d.total_kb = (int)total_kb; d.kb_per_split = (int)kb_per_split; d.splits = (int)splits;
+    d.m_blks = (int)m_blks; d.n_blks = (int)n_blks;
+    d.reduce_batch = q->reduce_batch ? 1 : 0;
+    d.a_batched = (Zall > 1 && q->a_batch_stride != 0) ? 1 : 0;
+    d.b_batched = (Zall > 1 && q->b_batch_stride != 0) ? 1 : 0;
+    d.c = q->c; d.ldc = q->ldc; d.c_batch_stride = q->c_batch_stride;
+    d.bias = reinterpret_cast<const bf16*>(q->bias);
+    d.residual = reinterpret_cast<const bf16*>(q->residual);
+    d.relu_mask = reinterpret_cast<const bf16*>(q->relu_mask);
+    d.act = q->act; d.out_fp32 = q->out_fp32; d.accumulate = q->accumulate; d.alpha = q->alpha;
+    d.partial = reinterpret_cast<float*>(q->workspace);
+
+    const long long total_tiles = out_tiles * splits;
+    const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+
+#define PB_DISPATCH(BN_)                                                                         \
+    do {                                                                                         \
+        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false>(ta, tb, d, grid, stream);        \
+        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true>(ta, tb, d, grid, stream);     \
+        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false>(ta, tb, d, grid, stream);     \
+        else rc = launch_gemm<BN_, true, true>(ta, tb, d, grid, stream);                         \
+    } while (0)
+    if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
+#undef PB_DISPATCH
+    if (rc) return rc;
+
+    if (splits > 1) {
+        const long long zmn = Zout * q->m * q->n;
+        const int threads = 256;
+        long long blocks = (zmn / 4 + threads - 1) / threads;
+        if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+        splitk_reduce_kernel<<<(int)blocks, threads, 0, stream>>>(d.partial, (int)splits, zmn, d.M, d.N, q->c, q->ldc,
+                                                                 q->c_batch_stride, q->out_fp32, q->accumulate,
+                                                                 q->alpha, nullptr);
+        PB_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -1,0 +1,128 @@
+// pasero_b200 — fused label-smoothed cross-entropy over bf16 logits.
+//
+// One CTA per target position streams the row of logits twice (second pass hits L1/L2): online
+// max / sum-exp / sum-of-logits in fp32, then overwrites the logits in place with
+// d(loss)/d(logits) = g * (softmax - (1-eps) onehot - eps/V) in bf16. Neither an fp32 copy of the
+// logits nor the softmax probabilities are ever materialised (the reference makes an fp32 copy and two
+// log-softmax passes: pasero/models/transformer.py:355-372). Returns both the smoothed loss and the
+// plain NLL (the reference's second no-grad pass) plus the non-pad target count, accumulated in fp64.
+#include "common.cuh"
+#include "../../include/pasero_b200.h"
+
+namespace pb200 {
+
+static constexpr int CE_THREADS = 256;
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = (threadIdx.x < CE_THREADS / 32) ? red[threadIdx.x] : 0.f;
+    if (warp == 0) { r = warp_sum(r); if (lane == 0) red[0] = r; }
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = (threadIdx.x < CE_THREADS / 32) ? red[threadIdx.x] : -INFINITY;
+    if (warp == 0) { r = warp_max(r); if (lane == 0) red[0] = r; }
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// stats (fp64): [0] += sum loss (nats), [1] += sum nll (nats), [2] += #non-pad targets
+__global__ void __launch_bounds__(CE_THREADS)
+ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, long long target_stride0,
+             int T, int V, long long ld, long long padding_idx, float eps, float grad_scale, int write_grad,
+             double* __restrict__ stats, float* __restrict__ row_loss) {
+    __shared__ float red[CE_THREADS / 32];
+    const long long row = blockIdx.x;
+    // targets may be a strided [B, T] view (decoder_input[:, 1:]); row = b * T + t
+    const long long tgt = target[(row / T) * target_stride0 + (row % T)];
+    bf16* x = logits + row * ld;
+    const int v8 = V >> 3;
+    if (tgt == padding_idx) {
+        if (write_grad)
+            for (int i = threadIdx.x; i < v8; i += CE_THREADS) reinterpret_cast<uint4*>(x)[i] = make_uint4(0, 0, 0, 0);
+        if (row_loss && threadIdx.x == 0) row_loss[row] = 0.f;
+        return;
+    }
+    float mx = -INFINITY, sx = 0.f;
+    for (int i = threadIdx.x; i < v8; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            mx = fmaxf(mx, fmaxf(f.x, f.y));
+            sx += f.x + f.y;
+        }
+    }
+    mx = block_reduce_max(mx, red);
+    sx = block_reduce_sum(sx, red);
+    float se = 0.f;
+    for (int i = threadIdx.x; i < v8; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            se += __expf(f.x - mx) + __expf(f.y - mx);
+        }
+    }
+    se = block_reduce_sum(se, red);
+    const float lse = mx + logf(se);
+    const float xt = bf16_to_f(x[tgt]);
+    const float nll = lse - xt;
+    const float smooth = lse - sx / V;
+    const float loss = (1.f - eps) * nll + eps * smooth;
+    __syncthreads();  // everyone has read x[tgt] before the row is overwritten
+    if (threadIdx.x == 0) {
+        atomicAdd(&stats[0], (double)loss);
+        atomicAdd(&stats[1], (double)nll);
+        atomicAdd(&stats[2], 1.0);
+        if (row_loss) row_loss[row] = loss;
+    }
+    if (!write_grad) return;
+    const float uni = eps / V;
+    for (int i = threadIdx.x; i < v8; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            const int c = i * 8 + 2 * j;
+            float g0 = __expf(f.x - lse) - uni, g1 = __expf(f.y - lse) - uni;
+            if (c == tgt) g0 -= (1.f - eps);
+            if (c + 1 == tgt) g1 -= (1.f - eps);
+            o[j] = pack_bf16x2(g0 * grad_scale, g1 * grad_scale);
+        }
+        reinterpret_cast<uint4*>(x)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
+                                   int64_t V, int64_t ld, int64_t padding_idx, float label_smoothing, float grad_scale,
+                                   int32_t write_grad, double* stats, float* row_loss, void* stream_) {
+    if (B * T == 0) return 0;
+    PB_CHECK(V % 8 == 0 && ld % 8 == 0, "cross-entropy: V (%lld) and ld must be multiples of 8", (long long)V);
+    PB_CHECK(stats != nullptr, "cross-entropy: stats buffer required");
+    ls_ce_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
+        (bf16*)logits, (const long long*)target, target_stride0, (int)T, (int)V, ld, padding_idx, label_smoothing,
+        grad_scale, write_grad, stats, row_loss);
+    PB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,349 @@
+// pasero_b200 — fused dropout + residual + LayerNorm (forward / backward), bf16 I/O, fp32 math.
+//
+//   sum = residual + dropout(x)            (bf16, saved for backward — same rounding as the reference)
+//   y   = LayerNorm(sum) * gamma + beta    (optional)
+//
+// Replaces the three ATen kernels per sub-block of the reference's `residual + self.dropout(x)` followed
+// by `nn.LayerNorm` (pasero/models/transformer.py:1043-1054, 1073-1086, 1322-1339). Dropout masks come
+// from Philox(seed, offset, element/8) and are regenerated in backward.
+#include "common.cuh"
+#include "../../include/pasero_b200.h"
+
+namespace pb200 {
+
+static constexpr int LN_WARPS = 4;
+
+template <int NCH>  // NCH = ceil(D / 256): chunks of 8 elements per lane
+__global__ void __launch_bounds__(LN_WARPS * 32)
+dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual,
+                          const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int M, int D, float eps,
+                          float p, uint64_t seed, uint64_t offset, bf16* __restrict__ sum_out,
+                          bf16* __restrict__ y_out, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const Philox rng(seed);
+    const uint32_t thresh = dropout_thresh16(p);
+    const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < D) {
+            const long long e = (long long)row * D + col;
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + e));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t keep = 0xffu;
+            if (p > 0.f) keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+            uint32_t rw[4] = {0, 0, 0, 0};
+            if (residual) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + e));
+                rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
+            }
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 a = unpack_bf16x2(xw[j]);
+                if (p > 0.f) {  // dropout output is a bf16 tensor in the reference
+                    a.x = ((keep >> (2 * j)) & 1) ? round_bf16(a.x * keep_scale) : 0.f;
+                    a.y = ((keep >> (2 * j + 1)) & 1) ? round_bf16(a.y * keep_scale) : 0.f;
+                }
+                const float2 r = unpack_bf16x2(rw[j]);
+                ow[j] = pack_bf16x2(a.x + r.x, a.y + r.y);
+                const float2 o = unpack_bf16x2(ow[j]);
+                v[c][2 * j] = o.x; v[c][2 * j + 1] = o.y;
+                s += o.x + o.y;
+            }
+            if (sum_out) *reinterpret_cast<uint4*>(sum_out + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+        }
+    }
+    if (!gamma) return;
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < D) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < D) {
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + col));
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+            uint32_t bw[4] = {0, 0, 0, 0};
+            if (beta) {
+                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + col));
+                bw[0] = bv.x; bw[1] = bv.y; bw[2] = bv.z; bw[3] = bv.w;
+            }
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 g = unpack_bf16x2(gw[j]);
+                const float2 b = unpack_bf16x2(bw[j]);
+                ow[j] = pack_bf16x2((v[c][2 * j] - mean) * rstd * g.x + b.x, (v[c][2 * j + 1] - mean) * rstd * g.y + b.y);
+            }
+            *reinterpret_cast<uint4*>(y_out + (long long)row * D + col) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+    }
+}
+
+// backward: dsum = LN'(dy) (or dy when no LN) [+ dsum_extra]; dx = dropout'(dsum).
+// dgamma / dbeta partial sums per CTA -> partial[blockIdx][2][D] (fp32), reduced by reduce_partials.
+template <int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dsum_extra,
+                          const bf16* __restrict__ sum, const bf16* __restrict__ gamma,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D, float p,
+                          uint64_t seed, uint64_t offset, bf16* __restrict__ dresidual, bf16* __restrict__ dx,
+                          float* __restrict__ partial) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Philox rng(seed);
+    const uint32_t thresh = dropout_thresh16(p);
+    const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    float dg[NCH][8], db[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
+
+    for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+        float g[NCH][8];   // dy * gamma  (or dy)
+        float xh[NCH][8];  // normalised input
+        float s1 = 0.f, s2 = 0.f;
+        const float mu = gamma ? mean[row] : 0.f, rs = gamma ? rstd[row] : 1.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < D) {
+                const long long e = (long long)row * D + col;
+                const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + e));
+                const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+                if (gamma) {
+                    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sum + e));
+                    const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+                    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + col));
+                    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 d = unpack_bf16x2(dw[j]);
+                        const float2 sx = unpack_bf16x2(sw[j]);
+                        const float2 gm = unpack_bf16x2(gw[j]);
+                        const float x0 = (sx.x - mu) * rs, x1 = (sx.y - mu) * rs;
+                        xh[c][2 * j] = x0; xh[c][2 * j + 1] = x1;
+                        dg[c][2 * j] += d.x * x0; dg[c][2 * j + 1] += d.y * x1;
+                        db[c][2 * j] += d.x; db[c][2 * j + 1] += d.y;
+                        g[c][2 * j] = d.x * gm.x; g[c][2 * j + 1] = d.y * gm.y;
+                        s1 += g[c][2 * j] + g[c][2 * j + 1];
+                        s2 += g[c][2 * j] * x0 + g[c][2 * j + 1] * x1;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 d = unpack_bf16x2(dw[j]);
+                        g[c][2 * j] = d.x; g[c][2 * j + 1] = d.y;
+                    }
+                }
+            }
+        }
+        if (gamma) { s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D; }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < D) {
+                const long long e = (long long)row * D + col;
+                float ds[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ds[j] = gamma ? rs * (g[c][j] - s1 - xh[c][j] * s2) : g[c][j];
+                if (dsum_extra) {
+                    const uint4 ev = __ldg(reinterpret_cast<const uint4*>(dsum_extra + e));
+                    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 x2 = unpack_bf16x2(ew[j]);
+                        ds[2 * j] += x2.x; ds[2 * j + 1] += x2.y;
+                    }
+                }
+                uint32_t ow[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ow[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
+                if (dresidual) *reinterpret_cast<uint4*>(dresidual + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                if (dx && (dx != dresidual || p > 0.f)) {
+                    if (p > 0.f) {
+                        const uint32_t keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r = unpack_bf16x2(ow[j]);  // gradient reaching dropout is bf16
+                            const float a = ((keep >> (2 * j)) & 1) ? r.x * keep_scale : 0.f;
+                            const float b = ((keep >> (2 * j + 1)) & 1) ? r.y * keep_scale : 0.f;
+                            ow[j] = pack_bf16x2(a, b);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(dx + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            }
+        }
+    }
+    if (!gamma || !partial) return;
+    // reduce dgamma/dbeta over the CTA's warps, then one partial row per CTA
+    __shared__ float red[LN_WARPS][2][NCH * 256];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[warp][0][c * 256 + lane * 8 + j] = dg[c][j];
+            red[warp][1][c * 256 + lane * 8 + j] = db[c][j];
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+        const int which = i / D, col = i % D;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) a += red[w][which][col];
+        partial[((long long)blockIdx.x * 2 + which) * D + col] = a;
+    }
+}
+
+// out[n] (bf16) = (accumulate ? out[n] : 0) + sum_p partial[p * stride + n]
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int P, long long stride, int N,
+                                       bf16* __restrict__ out, int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float a = 0.f;
+    for (int p = 0; p < P; ++p) a += partial[(long long)p * stride + n];
+    if (accumulate) a += bf16_to_f(out[n]);
+    out[n] = f_to_bf16(a);
+}
+
+// column sums of a bf16 [M, N] matrix (bias gradients): partial[split][N]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, int M, int N, long long ld, float* __restrict__ partial) {
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;   // 32 column groups of 8, 8 row lanes
+    const int col = blockIdx.x * 256 + cg * 8;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col < N) {
+        for (int r = blockIdx.y * 8 + rl; r < M; r += gridDim.y * 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + col));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(w[j]);
+                a[2 * j] += f.x; a[2 * j + 1] += f.y;
+            }
+        }
+    }
+    __shared__ float red[8][256];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = a[j];
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (blockIdx.x * 256 + c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][c];
+        partial[(long long)blockIdx.y * N + blockIdx.x * 256 + c] = s;
+    }
+}
+
+static int ln_bwd_grid(int M) {
+    int g = (M + LN_WARPS - 1) / LN_WARPS;
+    const int cap = 4 * num_sms();
+    return g < cap ? g : cap;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D) {
+    return (size_t)ln_bwd_grid((int)M) * 2 * (size_t)D * sizeof(float);
+}
+
+extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
+                                        int64_t M, int64_t D, float eps, float p, uint64_t seed, uint64_t offset,
+                                        void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (M == 0) return 0;
+    PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported (multiple of 8, <= 1024)", (long long)D);
+    PB_CHECK(gamma == nullptr || y_out != nullptr, "y_out required with LayerNorm");
+    PB_CHECK(gamma != nullptr || sum_out != nullptr, "sum_out required without LayerNorm");
+    PB_CHECK(p >= 0.f && p < 1.f, "dropout p out of range");
+    const int nch = (int)((D + 255) / 256);
+    const int grid = (int)((M + LN_WARPS - 1) / LN_WARPS);
+#define PB_LN_FWD(N_)                                                                                         \
+    dropout_add_ln_fwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                         \
+        (const bf16*)x, (const bf16*)residual, (const bf16*)gamma, (const bf16*)beta, (int)M, (int)D, eps, p,  \
+        seed, offset, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out)
+    switch (nch) { case 1: PB_LN_FWD(1); break; case 2: PB_LN_FWD(2); break; case 3: PB_LN_FWD(3); break; default: PB_LN_FWD(4); }
+#undef PB_LN_FWD
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
+                                        const float* mean, const float* rstd, int64_t M, int64_t D, float p,
+                                        uint64_t seed, uint64_t offset, void* dresidual, void* dx, void* dgamma,
+                                        void* dbeta, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                        void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (M == 0) return 0;
+    PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported", (long long)D);
+    const int grid = ln_bwd_grid((int)M);
+    float* partial = nullptr;
+    if (gamma && (dgamma || dbeta)) {
+        PB_CHECK(workspace && workspace_bytes >= pb200_ln_bwd_workspace_bytes(M, D), "LN backward workspace too small");
+        partial = reinterpret_cast<float*>(workspace);
+    }
+    const int nch = (int)((D + 255) / 256);
+#define PB_LN_BWD(N_)                                                                                        \
+    dropout_add_ln_bwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                        \
+        (const bf16*)dy, (const bf16*)dsum_extra, (const bf16*)sum, (const bf16*)gamma, mean, rstd, (int)M,   \
+        (int)D, p, seed, offset, (bf16*)dresidual, (bf16*)dx, partial)
+    switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
+#undef PB_LN_BWD
+    PB_LAUNCH_CHECK();
+    if (partial) {
+        const int threads = 256, blocks = (int)((D + threads - 1) / threads);
+        if (dgamma) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial, grid, 2 * D, (int)D, (bf16*)dgamma, accumulate);
+        if (dbeta) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial + D, grid, 2 * D, (int)D, (bf16*)dbeta, accumulate);
+        PB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N) {
+    long long splits = (M + 255) / 256;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    return (size_t)splits * (size_t)N * sizeof(float);
+}
+
+extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out, int32_t accumulate,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PB_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
+    if (N == 0) return 0;
+    long long splits = (M + 255) / 256;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    PB_CHECK(workspace && workspace_bytes >= pb200_colsum_workspace_bytes(M, N), "colsum workspace too small");
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)splits);
+    colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, (int)M, (int)N, ld, (float*)workspace);
+    PB_LAUNCH_CHECK();
+    reduce_partials_kernel<<<(int)((N + 255) / 256), 256, 0, stream>>>((const float*)workspace, (int)splits, N, (int)N,
+                                                                       (bf16*)out, accumulate);
+    PB_LAUNCH_CHECK();
+    return 0;
+}

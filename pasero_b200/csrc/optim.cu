@@ -1,0 +1,127 @@
+// pasero_b200 — fused gradient rescale + global-norm clip + Adam over the flat parameter arena.
+//
+// Semantics follow Trainer.train_step / clip_grad_norm_ / Adam.step of the reference
+// (pasero/training.py:455-487, pasero/optimization.py:56-149, 390-427), including its bf16 rounding
+// points: grads are bf16; `grad.mul_(dp_size / num_tokens)` and `grad.mul_(clip_coef)` each round to
+// bf16; moments and the update are fp32; the parameter is rounded back to bf16.
+// All step scalars live in device memory so the whole optimizer is CUDA-graph replayable and needs no
+// host synchronisation (the reference does ~10 launches x 353 tensors and two host syncs).
+//
+//   hyper (fp32[16]): [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1 - beta1^t
+//                     [6] sqrt(1 - beta2^t)  [7] clip_norm  [8] grad multiplier numerator (dp_size)
+//                     [9] 1 - beta1  [10] 1 - beta2  [11] lr / (1 - beta1^t)  [12] weight_decay * lr
+//                     (derived scalars are computed by the host in fp64, like the reference's Python floats)
+//   stats (fp64[8]) : [2] num_tokens (divisor; <=0 -> 1)   [4] out: sum of squares of the scaled grads
+#include "common.cuh"
+#include "../../include/pasero_b200.h"
+
+namespace pb200 {
+
+__device__ __forceinline__ float grad_coeff(const float* hyper, const double* stats) {
+    const double nt = stats[2];
+    return (float)((double)hyper[8] / (nt > 0.0 ? nt : 1.0));
+}
+
+__global__ void __launch_bounds__(256)
+grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __restrict__ hyper,
+                   double* __restrict__ stats) {
+    const float coeff = grad_coeff(hyper, stats);
+    float acc = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(grad) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            const float a = round_bf16(f.x * coeff), b = round_bf16(f.y * coeff);
+            acc += a * a + b * b;
+        }
+    }
+    __shared__ double red[8];
+    double d = warp_sum_d((double)acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomicAdd(&stats[4], t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __restrict__ exp_avg,
+            float* __restrict__ exp_avg_sq, long long n8, const float* __restrict__ hyper,
+            const double* __restrict__ stats) {
+    const float beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3];
+    const float bc2_sqrt = hyper[6], clip = hyper[7];
+    const float omb1 = hyper[9], omb2 = hyper[10], step_size = hyper[11], wd_lr = hyper[12];
+    const float coeff = grad_coeff(hyper, stats);
+    float clip_coef = 1.0f;
+    if (clip > 0.f) {
+        const float total_norm = (float)sqrt(stats[4]);
+        clip_coef = fminf(clip / (total_norm + 1e-6f), 1.0f);
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(grad) + i);
+        const uint4 pv = reinterpret_cast<const uint4*>(param)[i];
+        float4 m0 = reinterpret_cast<const float4*>(exp_avg)[2 * i], m1 = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
+        float4 v0 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i], v1 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, pw[4] = {pv.x, pv.y, pv.z, pv.w};
+        float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float g[8], p[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 gf = unpack_bf16x2(gw[j]);
+            const float2 pf = unpack_bf16x2(pw[j]);
+            g[2 * j] = gf.x; g[2 * j + 1] = gf.y; p[2 * j] = pf.x; p[2 * j + 1] = pf.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float gj = round_bf16(g[j] * coeff);
+            if (clip > 0.f) gj = round_bf16(gj * clip_coef);
+            m[j] = m[j] * beta1 + gj * omb1;
+            v[j] = v[j] * beta2 + gj * gj * omb2;
+            const float denom = sqrtf(v[j]) / bc2_sqrt + eps;
+            float pj = p[j];
+            if (wd_lr != 0.f) pj += pj * (-wd_lr);
+            pj += -step_size * (m[j] / denom);
+            p[j] = pj;
+        }
+        uint4 po;
+        po.x = pack_bf16x2(p[0], p[1]); po.y = pack_bf16x2(p[2], p[3]);
+        po.z = pack_bf16x2(p[4], p[5]); po.w = pack_bf16x2(p[6], p[7]);
+        reinterpret_cast<uint4*>(param)[i] = po;
+        reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(m[0], m[1], m[2], m[3]);
+        reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(m[4], m[5], m[6], m[7]);
+        reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(exp_avg_sq)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+// Sum of squares of bf16(grad * dp_size / num_tokens) accumulated into stats[4] (caller zeroes it).
+extern "C" int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* stream_) {
+    if (n == 0) return 0;
+    PB_CHECK(n % 8 == 0, "gradient arena length (%lld) must be a multiple of 8", (long long)n);
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+    grad_sqnorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)grad, n / 8, hyper, stats);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pb200_adam_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               const float* hyper, const double* stats, void* stream_) {
+    if (n == 0) return 0;
+    PB_CHECK(n % 8 == 0, "parameter arena length (%lld) must be a multiple of 8", (long long)n);
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq, n / 8,
+                                                               hyper, stats);
+    PB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,254 @@
+"""Raw tensor-level wrappers over the C ABI (no autograd). Each function checks shapes/dtypes on the
+host, allocates outputs/workspaces with torch (device memory plumbing) and launches on torch's current
+stream. Autograd-aware ops live in `pasero_b200.ops`."""
+import math
+from ctypes import byref
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import AttnParams, GemmParams, check, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _ws(nbytes: int, device) -> Optional[Tensor]:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------------
+def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: int, ldb: int, ldc: int,
+             batch: int = 1, a_batch_stride: int = 0, b_batch_stride: int = 0, c_batch_stride: int = 0,
+             a_mn_major: bool = False, b_mn_major: bool = False, reduce_batch: bool = False,
+             bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, relu_mask: Optional[Tensor] = None,
+             act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0) -> Tensor:
+    lib = _lib.load()
+    p = GemmParams()
+    p.a, p.b, p.c = a_ptr, b_ptr, c.data_ptr()
+    p.m, p.n, p.k, p.batch = m, n, k, batch
+    p.lda, p.ldb, p.ldc = lda, ldb, ldc
+    p.a_batch_stride, p.b_batch_stride, p.c_batch_stride = a_batch_stride, b_batch_stride, c_batch_stride
+    p.a_mn_major, p.b_mn_major, p.reduce_batch = int(a_mn_major), int(b_mn_major), int(reduce_batch)
+    p.bias, p.residual, p.relu_mask = ptr(bias), ptr(residual), ptr(relu_mask)
+    p.act, p.out_fp32, p.accumulate, p.alpha = act, int(c.dtype == torch.float32), int(accumulate), alpha
+    p.split_k, p.tile_n = split_k, tile_n
+    ws = None
+    plain = bias is None and residual is None and relu_mask is None and act == 0
+    if split_k != 1 and plain:
+        zout = 1 if reduce_batch else batch
+        tiles = zout * math.ceil(m / 128) * math.ceil(n / 128)
+        sms = lib.pb200_num_sms()
+        max_splits = split_k if split_k > 1 else (sms // tiles if tiles * 2 <= sms else 1)
+        if max_splits > 1:
+            ws = _ws(lib.pb200_gemm_workspace_bytes(m, n, zout, max_splits), c.device)
+    if ws is None:
+        p.split_k = 1
+    p.workspace, p.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
+    check(lib.pb200_gemm_bf16(byref(p), stream_ptr()))
+    return c
+
+
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0,
+               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0) -> Tensor:
+    """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual)"""
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    y = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    return gemm_raw(x.data_ptr(), w.data_ptr(), y, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, act=act,
+                    residual=residual, split_k=1, tile_n=tile_n)
+
+
+def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                 accumulate: bool = False) -> Tensor:
+    """dx[M, K] = dy[M, N] @ w[N, K]  (optionally masked by relu_mask > 0)"""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = out if out is not None else torch.empty(M, K, dtype=BF16, device=dy.device)
+    return gemm_raw(dy.data_ptr(), w.data_ptr(), dx, M, K, N, lda=N, ldb=K, ldc=K, b_mn_major=True,
+                    relu_mask=relu_mask, accumulate=accumulate, split_k=1)
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """dw[N, K] = dy[M, N]^T @ x[M, K]"""
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = out if out is not None else torch.empty(N, K, dtype=BF16, device=dy.device)
+    return gemm_raw(dy.data_ptr(), x.data_ptr(), dw, N, K, M, lda=N, ldb=K, ldc=K, a_mn_major=True, b_mn_major=True,
+                    accumulate=accumulate)
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, kv_len: Optional[Tensor],
+                  causal: bool, scale: float):
+    """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection)."""
+    lib = _lib.load()
+    o = torch.empty(B * Lq, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
+    p = AttnParams()
+    p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
+    p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.causal, p.scale = B, H, Lq, Lk, 64, int(causal), scale
+    check(lib.pb200_attention_fwd(byref(p), stream_ptr()))
+    return o, lse
+
+
+def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, B: int, H: int, Lq: int,
+                  Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor):
+    lib = _lib.load()
+    delta = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
+    p = AttnParams()
+    p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
+    p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.causal, p.scale = B, H, Lq, Lk, 64, int(causal), scale
+    p.dout, p.lddo, p.delta = dout.data_ptr(), dout.stride(0), delta.data_ptr()
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.lddq, p.lddk, p.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    check(lib.pb200_attention_bwd(byref(p), stream_ptr()))
+    return dq, dk, dv
+
+
+# --------------------------------------------------------------------------------------------------
+# dropout + residual + LayerNorm
+# --------------------------------------------------------------------------------------------------
+def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
+                       eps: float, p: float, seed: int, offset: int, need_sum: bool = True):
+    lib = _lib.load()
+    M, D = x.shape
+    dev = x.device
+    has_ln = gamma is not None
+    plain = residual is None and p == 0.0
+    sum_out = None if (has_ln and (plain or not need_sum)) else torch.empty(M, D, dtype=BF16, device=dev)
+    y = torch.empty(M, D, dtype=BF16, device=dev) if has_ln else None
+    mean = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
+    rstd = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
+    check(lib.pb200_dropout_add_ln_fwd(x.data_ptr(), ptr(residual), ptr(gamma), ptr(beta), M, D, eps, p, seed, offset,
+                                       ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), stream_ptr()))
+    if sum_out is None:
+        sum_out = x  # LN of x alone: the saved pre-norm input is x itself
+    return (y if has_ln else sum_out), sum_out, mean, rstd
+
+
+def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
+                       mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
+                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False):
+    lib = _lib.load()
+    M, D = dy.shape
+    dev = dy.device
+    dx = torch.empty(M, D, dtype=BF16, device=dev)
+    dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
+    ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if gamma is not None else None
+    check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
+                                       p, seed, offset, ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
+                                       int(accumulate), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
+    return dx, dres
+
+
+def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    lib = _lib.load()
+    M, N = x.shape
+    out = out if out is not None else torch.empty(N, dtype=BF16, device=x.device)
+    ws = _ws(lib.pb200_colsum_workspace_bytes(M, N), x.device)
+    check(lib.pb200_colsum_bf16(x.data_ptr(), M, N, x.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(),
+                                ws.numel(), stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# embedding epilogue, conv-subsampler pieces
+# --------------------------------------------------------------------------------------------------
+def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int, D: int, L: int, scale: float,
+              p: float, seed: int, offset: int) -> Tensor:
+    lib = _lib.load()
+    out = torch.empty(M, D, dtype=BF16, device=src.device)
+    check(lib.pb200_embed_fwd(ptr(ids), src.data_ptr(), ptr(pos), M, D, L, scale, p, seed, offset,
+                              src.shape[0] if ids is not None else 0, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p: float, seed: int, offset: int,
+              padding_idx: int = -1, dtable: Optional[Tensor] = None) -> Optional[Tensor]:
+    lib = _lib.load()
+    dx = torch.empty(M, D, dtype=BF16, device=dy.device) if ids is None else None
+    check(lib.pb200_embed_bwd(dy.data_ptr(), ptr(ids), M, D, scale, p, seed, offset, padding_idx,
+                              dtable.shape[0] if dtable is not None else 0, ptr(dx), ptr(dtable), stream_ptr()))
+    return dx
+
+
+def glu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
+    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    check(_lib.load().pb200_glu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    return out
+
+
+def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
+    din = torch.empty(M, 2 * C, dtype=BF16, device=x.device)
+    check(_lib.load().pb200_glu_bwd(dy.data_ptr(), x.data_ptr(), M, C, din.data_ptr(), stream_ptr()))
+    return din
+
+
+def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
+    dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
+    check(_lib.load().pb200_col2im(dcol.data_ptr(), B, Tin, Tout, C, KW, stride, dx.data_ptr(), stream_ptr()))
+    return dx
+
+
+def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
+    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    check(_lib.load().pb200_pad_rows(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    return out
+
+
+def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
+    check(_lib.load().pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# loss, optimizer, frontend
+# --------------------------------------------------------------------------------------------------
+def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smoothing: float, stats: Tensor,
+                  write_grad: bool = True, grad_scale: float = 1.0, row_loss: Optional[Tensor] = None) -> None:
+    """logits [B*T, V] bf16 (overwritten with the gradient), target [B, T] int64 (may be a strided view)."""
+    B, T = target.shape
+    assert target.stride(1) == 1 and target.dtype == torch.int64
+    V = logits.shape[1]
+    check(_lib.load().pb200_ls_ce_fwd_bwd(logits.data_ptr(), target.data_ptr(), target.stride(0), B, T, V,
+                                          logits.stride(0), padding_idx, label_smoothing, grad_scale, int(write_grad),
+                                          stats.data_ptr(), ptr(row_loss), stream_ptr()))
+
+
+def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
+    check(_lib.load().pb200_grad_sqnorm(grad.data_ptr(), grad.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor) -> None:
+    check(_lib.load().pb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                      param.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
+
+
+def fbank_num_frames(num_samples: int) -> int:
+    return int(_lib.load().pb200_fbank_num_frames(num_samples))
+
+
+def fbank_cmvn(pcm: Tensor, sample_offsets: Tensor, frame_offsets: Tensor, batch: int, max_frames: int,
+               total_frames: int, pcm_scale: float = 32768.0, cmvn: bool = True, padded_frames: int = 0,
+               front_pad: int = 0):
+    """pcm fp32 [total_samples]; offsets int64 [batch+1] on device. Returns (feats fp32 [total_frames, 80],
+    bf16 padded [batch, padded_frames, 80] or None)."""
+    lib = _lib.load()
+    dev = pcm.device
+    assert pcm.dtype == torch.float32 and pcm.is_contiguous()
+    feats = torch.empty(total_frames, 80, dtype=torch.float32, device=dev)
+    padded = torch.empty(batch, padded_frames, 80, dtype=BF16, device=dev) if padded_frames > 0 else None
+    ws = _ws(lib.pb200_fbank_workspace_bytes(batch), dev)
+    check(lib.pb200_fbank_cmvn(pcm.data_ptr(), sample_offsets.data_ptr(), frame_offsets.data_ptr(), batch, max_frames,
+                               pcm_scale, int(cmvn), feats.data_ptr(), ptr(padded), padded_frames, front_pad,
+                               ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
+    return feats, padded

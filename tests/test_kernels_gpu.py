@@ -1,0 +1,327 @@
+"""Kernel-level numerics: every C-ABI compute entry point against a plain PyTorch fp32 restatement of the
+same op on the same seeded inputs (the model-level parity against the oracle lives in test_parity_gpu.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _k():
+    from pasero_b200 import kernels
+    return kernels
+
+
+def _rand(*shape, scale=1.0, seed=0, dtype=BF16):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device='cuda') * scale).to(dtype)
+
+
+def _close(got, want, atol, rtol, name=''):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = (err > tol)
+    assert not bad.any(), f'{name}: {int(bad.sum())}/{bad.numel()} off, max err {err.max().item():.4g} ' \
+                          f'(ref max {want.abs().max().item():.4g})'
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 136, 200), (1000, 512, 512), (4096, 2048, 512), (257, 8032, 512)])
+@pytest.mark.parametrize('tile_n', [128, 256])
+def test_gemm_forward(M, N, K, tile_n):
+    k = _k()
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3)
+    y = k.linear_fwd(x, w, b, tile_n=tile_n)
+    ref = x.float() @ w.float().T + b.float()
+    _close(y, ref, 2e-2, 1e-2, 'linear_fwd')
+
+
+def test_gemm_epilogues():
+    k = _k()
+    M, N, K = 513, 384, 256
+    x, w, b, r = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    ref = x.float() @ w.float().T + b.float()
+    _close(k.linear_fwd(x, w, b, act=1), ref.relu(), 2e-2, 1e-2, 'relu')
+    _close(k.linear_fwd(x, w, b, act=2), F.gelu(ref), 2e-2, 1e-2, 'gelu')
+    _close(k.linear_fwd(x, w, b, residual=r), ref + r.float(), 2e-2, 1e-2, 'residual')
+    _close(k.linear_fwd(x, w, None, out_dtype=torch.float32), x.float() @ w.float().T, 1e-3, 1e-3, 'fp32 out')
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 136, 200), (2048, 512, 2048), (16000, 512, 512)])
+def test_gemm_dgrad_wgrad(M, N, K):
+    k = _k()
+    x, w, dy = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(M, N, seed=5)
+    dx = k.linear_dgrad(dy, w)
+    _close(dx, dy.float() @ w.float(), 3e-2, 1e-2, 'dgrad')
+    h = _rand(M, K, seed=6)
+    dxm = k.linear_dgrad(dy, w, relu_mask=h)
+    _close(dxm, (dy.float() @ w.float()) * (h.float() > 0), 3e-2, 1e-2, 'dgrad+relu mask')
+    dw = k.linear_wgrad(dy, x)
+    ref = dy.float().T @ x.float()
+    _close(dw, ref, 2e-2 * math.sqrt(M / 256), 1e-2, 'wgrad')
+    dw2 = k.linear_wgrad(dy, x, out=dw.clone(), accumulate=True)
+    _close(dw2, 2 * ref, 4e-2 * math.sqrt(M / 256), 2e-2, 'wgrad accumulate')
+
+
+def test_gemm_conv_view():
+    """strided conv1d (k=5, s=2, p=2) as a GEMM over an overlapping-row view of the zero-padded input"""
+    k = _k()
+    B, T, C, N, KW = 3, 101, 80, 256, 5
+    x = _rand(B, T, C, seed=1)
+    w = _rand(N, C, KW, scale=(C * KW) ** -0.5, seed=2)
+    bias = _rand(N, seed=3)
+    Tout = 1 + (T + 2 * (KW // 2) - KW) // 2
+    Tp = T + 4 + (T % 2)
+    xp = k.pad_rows(x, B, T, C, Tp, 2)
+    w2 = w.permute(0, 2, 1).contiguous().view(N, KW * C)      # [N, tap*C + c]
+    y = torch.empty(B, Tout, N, dtype=BF16, device='cuda')
+    k.gemm_raw(xp.data_ptr(), w2.data_ptr(), y, Tout, N, KW * C, lda=2 * C, ldb=KW * C, ldc=N, batch=B,
+               a_batch_stride=Tp * C, b_batch_stride=0, c_batch_stride=Tout * N, bias=bias, split_k=1)
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias.float(), stride=2, padding=2).transpose(1, 2)
+    _close(y, ref, 3e-2, 1e-2, 'conv fwd')
+    # weight gradient: reduce over (batch, time) with both operands MN-major
+    dy = _rand(B, Tout, N, seed=4)
+    dw = torch.empty(N, KW * C, dtype=BF16, device='cuda')
+    k.gemm_raw(dy.data_ptr(), xp.data_ptr(), dw, N, KW * C, Tout, lda=N, ldb=2 * C, ldc=KW * C, batch=B,
+               a_batch_stride=Tout * N, b_batch_stride=Tp * C, a_mn_major=True, b_mn_major=True, reduce_batch=True)
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    F.conv1d(xr, wr, None, stride=2, padding=2).backward(dy.float().transpose(1, 2))
+    _close(dw.view(N, KW, C).permute(0, 2, 1), wr.grad, 5e-2, 2e-2, 'conv wgrad')
+    # input gradient: dcol = dy @ w2, then col2im
+    dcol = torch.empty(B * Tout, KW * C, dtype=BF16, device='cuda')
+    k.gemm_raw(dy.data_ptr(), w2.data_ptr(), dcol, B * Tout, KW * C, N, lda=N, ldb=KW * C, ldc=KW * C, b_mn_major=True,
+               split_k=1)
+    dx = k.col2im(dcol, B, T, Tout, C, KW, 2)
+    _close(dx.view(B, T, C), xr.grad.transpose(1, 2), 5e-2, 2e-2, 'conv dgrad')
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, kv_len, causal, scale):
+    B, H, Lq, Lk = q.shape[0], q.shape[1], q.shape[2], k.shape[2]
+    s = (q @ k.transpose(-1, -2)) * scale
+    if kv_len is not None:
+        mask = torch.arange(Lk, device=q.device)[None, :] >= kv_len[:, None]
+        s = s.masked_fill(mask[:, None, None, :], float('-inf'))
+    if causal:
+        cm = torch.ones(Lq, Lk, dtype=torch.bool, device=q.device).triu(1 + Lk - Lq)
+        s = s.masked_fill(cm, float('-inf'))
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize('B,H,Lq,Lk,causal,masked', [
+    (2, 2, 64, 64, False, False), (3, 8, 250, 250, False, True), (3, 8, 48, 250, False, True),
+    (4, 8, 48, 48, True, False), (2, 4, 130, 130, True, False), (2, 2, 1, 77, False, True)])
+def test_attention(B, H, Lq, Lk, causal, masked):
+    k = _k()
+    D = H * 64
+    q2, kv2 = _rand(B * Lq, D, seed=1), _rand(B * Lk, 2 * D, seed=2)
+    k2, v2 = kv2[:, :D], kv2[:, D:]
+    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32) if masked else None
+    if masked:
+        kv_len[0] = Lk
+    scale = 1 / 8
+    o, lse = k.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
+
+    def heads(t, L):
+        return t.float().reshape(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    qr, kr, vr = heads(q2, Lq), heads(k2, Lk), heads(v2, Lk)
+    ref = _attn_ref(qr, kr, vr, kv_len, causal, scale)
+    _close(o.view(B, Lq, H, 64).transpose(1, 2), ref, 2e-2, 2e-2, 'attn fwd')
+    do = _rand(B * Lq, D, seed=3)
+    ref.backward(do.float().view(B, Lq, H, 64).transpose(1, 2))
+    dq = torch.empty_like(q2)
+    dkv = torch.empty_like(kv2)
+    k.attention_bwd(do, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+    _close(dq.view(B, Lq, H, 64).transpose(1, 2), qr.grad, 3e-2, 3e-2, 'dq')
+    _close(dkv[:, :D].reshape(B, Lk, H, 64).transpose(1, 2), kr.grad, 3e-2, 3e-2, 'dk')
+    _close(dkv[:, D:].reshape(B, Lk, H, 64).transpose(1, 2), vr.grad, 3e-2, 3e-2, 'dv')
+
+
+# ---------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize('M,D', [(1000, 512), (77, 128), (300, 768), (129, 1024)])
+def test_dropout_add_ln(M, D):
+    k = _k()
+    x, r = _rand(M, D, seed=1), _rand(M, D, seed=2)
+    g, b = (1 + 0.1 * _rand(D, seed=3).float()).to(BF16), _rand(D, scale=0.1, seed=4)
+    y, s, mean, rstd = k.dropout_add_ln_fwd(x, r, g, b, 1e-5, 0.0, 0, 0)
+    sr = (x.float() + r.float()).to(BF16)
+    assert torch.equal(s, sr)
+    xs = sr.float().requires_grad_(True)
+    gr, br = g.float().requires_grad_(True), b.float().requires_grad_(True)
+    ref = F.layer_norm(xs, (D,), gr, br, 1e-5)
+    _close(y, ref, 2e-2, 1e-2, 'ln fwd')
+    dy = _rand(M, D, seed=5)
+    ref.backward(dy.float())
+    dg, db = torch.empty(D, dtype=BF16, device='cuda'), torch.empty(D, dtype=BF16, device='cuda')
+    dx, dres = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, 0.0, 0, 0, True, dg, db)
+    assert dres is dx
+    _close(dx, xs.grad, 2e-2, 2e-2, 'ln dx')
+    _close(dg, gr.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dgamma')
+    _close(db, br.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dbeta')
+
+
+def test_dropout_mask_consistency():
+    k = _k()
+    M, D, p = 512, 512, 0.1
+    x = torch.ones(M, D, dtype=BF16, device='cuda')
+    r = torch.zeros(M, D, dtype=BF16, device='cuda')
+    s, _, _, _ = k.dropout_add_ln_fwd(x, r, None, None, 1e-5, p, 1234, 7)
+    keep = s.float() > 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert torch.allclose(s.float()[keep], torch.tensor(1 / (1 - p)).to(BF16).float())
+    # backward regenerates the same mask
+    dy = torch.ones(M, D, dtype=BF16, device='cuda')
+    dx, dres = k.dropout_add_ln_bwd(dy, None, None, None, None, None, p, 1234, 7, True)
+    assert torch.equal(dx.float() > 0, keep)
+    assert torch.equal(dres, dy)
+    # a different offset gives a different mask
+    s2, _, _, _ = k.dropout_add_ln_fwd(x, r, None, None, 1e-5, p, 1234, 8)
+    assert not torch.equal(s2, s)
+
+
+def test_colsum():
+    k = _k()
+    x = _rand(3001, 1024, seed=1)
+    _close(k.colsum(x), x.float().sum(0), 0.5, 2e-2, 'colsum')
+
+
+# ---------------------------------------------------------------------------------------------- embed / glu
+def test_embed():
+    k = _k()
+    V, D, B, T = 1000, 512, 5, 37
+    table = _rand(V, D, scale=D ** -0.5, seed=1)
+    pos = _rand(T, D, seed=2)
+    ids = torch.randint(0, V, (B, T), device='cuda')
+    ids[:, -3:] = 1
+    scale = math.sqrt(D)
+    out = k.embed_fwd(ids.view(-1), table, pos, B * T, D, T, scale, 0.0, 0, 0)
+    e = table[ids]
+    e = e * scale
+    e = e + pos[None]
+    assert torch.equal(out.view(B, T, D), e)
+    dy = _rand(B * T, D, seed=3)
+    dtab = torch.zeros(V, D, dtype=torch.float32, device='cuda')
+    k.embed_bwd(dy, ids.view(-1), B * T, D, scale, 0.0, 0, 0, padding_idx=1, dtable=dtab)
+    ref = torch.zeros(V, D, device='cuda')
+    g = (dy.float() * scale).to(BF16).float()
+    g[(ids.view(-1) == 1)] = 0
+    ref.index_add_(0, ids.view(-1), g)
+    _close(dtab, ref, 1e-3, 1e-3, 'embed bwd')
+    # feature path (no gather)
+    x = _rand(B * T, D, seed=4)
+    out2 = k.embed_fwd(None, x, pos, B * T, D, T, scale, 0.0, 0, 0)
+    assert torch.equal(out2.view(B, T, D), (x.view(B, T, D) * scale) + pos[None])
+    dx = k.embed_bwd(dy, None, B * T, D, scale, 0.0, 0, 0)
+    assert torch.equal(dx, (dy.float() * scale).to(BF16))
+
+
+def test_glu():
+    k = _k()
+    B, T, C = 3, 50, 512
+    x = _rand(B * T, 2 * C, seed=1)
+    out = k.glu_fwd(x, B, T, C, T + 5, 2)
+    xr = x.float().requires_grad_(True)
+    ref = F.glu(xr, dim=1)
+    _close(out[:, 2:2 + T].reshape(B * T, C), ref, 1e-2, 1e-2, 'glu')
+    assert out[:, :2].abs().sum() == 0 and out[:, 2 + T:].abs().sum() == 0
+    dy = _rand(B * T, C, seed=2)
+    ref.backward(dy.float())
+    _close(k.glu_bwd(dy, x, B * T, C), xr.grad, 1e-2, 1e-2, 'glu bwd')
+
+
+# ---------------------------------------------------------------------------------------------- loss / optimizer
+@pytest.mark.parametrize('V', [8032, 1000])
+def test_ls_ce(V):
+    k = _k()
+    B, T, eps = 7, 48, 0.1
+    logits = _rand(B * T, V, scale=2.0, seed=1)
+    dec = torch.randint(4, V, (B, T + 1), device='cuda')
+    dec[:, -5:] = 1
+    dec[0, :] = 1
+    target = dec[:, 1:]
+    lr = logits.float().requires_grad_(True)
+    ref = F.cross_entropy(lr, target.reshape(-1), ignore_index=1, reduction='sum', label_smoothing=eps)
+    nll = F.cross_entropy(lr.detach(), target.reshape(-1), ignore_index=1, reduction='sum')
+    ref.backward()
+    stats = torch.zeros(8, dtype=torch.float64, device='cuda')
+    k.ls_ce_fwd_bwd(logits, target, 1, eps, stats)
+    assert abs(stats[0].item() - ref.item()) / ref.item() < 1e-5
+    assert abs(stats[1].item() - nll.item()) / nll.item() < 1e-5
+    assert stats[2].item() == (target != 1).sum().item()
+    _close(logits, lr.grad, 2e-3, 1e-2, 'ce grad')
+
+
+def test_adam_and_clip():
+    k = _k()
+    n = 8 * 1000 + 8
+    p0 = _rand(n, scale=0.1, seed=1)
+    g = _rand(n, scale=3.0, seed=2)
+    m0 = _rand(n, scale=0.01, seed=3, dtype=torch.float32)
+    v0 = _rand(n, scale=0.01, seed=4, dtype=torch.float32).abs()
+    lr, b1, b2, eps, wd, step, clip, ntok = 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, 3072.0
+    # reference (pasero/training.py:462-477 + optimization.py:65-149), fp32 on GPU
+    gr = g.clone()
+    gr.mul_(1.0 / ntok)
+    norm = torch.norm(gr.float())
+    gr.mul_((clip / (norm + 1e-6)).clamp_(max=1))
+    gf = gr.float()
+    m, v, pf = m0.clone(), v0.clone(), p0.float()
+    m.mul_(b1).add_(gf, alpha=1 - b1)
+    v.mul_(b2).addcmul_(gf, gf, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    pf.add_(pf, alpha=-wd * lr)
+    pf.addcdiv_(m, denom, value=-(lr / bc1))
+    hyper = torch.tensor([lr, b1, b2, eps, wd, bc1, math.sqrt(bc2), clip, 1.0, 1 - b1, 1 - b2, lr / bc1, wd * lr, 0, 0, 0],
+                         dtype=torch.float32, device='cuda')
+    stats = torch.zeros(8, dtype=torch.float64, device='cuda')
+    stats[2] = ntok
+    p, m1, v1 = p0.clone(), m0.clone(), v0.clone()
+    k.grad_sqnorm(g, hyper, stats)
+    assert abs(math.sqrt(stats[4].item()) - norm.item()) / norm.item() < 1e-5
+    k.adam_step(p, g, m1, v1, hyper, stats)
+    _close(m1, m, 1e-7, 1e-5, 'exp_avg')
+    _close(v1, v, 1e-9, 1e-5, 'exp_avg_sq')
+    assert (p.float() - pf.to(BF16).float()).abs().max() <= 2 ** -8 * p0.float().abs().max()
+    assert (p != pf.to(BF16)).float().mean() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- fbank
+@pytest.mark.parametrize('lengths', [[160000, 160000], [400, 16000, 48123, 5000], [399, 8000]])
+def test_fbank_vs_torchaudio(lengths):
+    torchaudio = pytest.importorskip('torchaudio')
+    k = _k()
+    g = torch.Generator().manual_seed(1234)
+    waves = [(torch.rand(n, generator=g) - 0.5) for n in lengths]
+    frames = [k.fbank_num_frames(n) for n in lengths]
+    so = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int64, device='cuda')
+    fo = torch.tensor([0] + list(torch.tensor(frames).cumsum(0)), dtype=torch.int64, device='cuda')
+    pcm = torch.cat(waves).cuda()
+    raw, _ = k.fbank_cmvn(pcm, so, fo, len(lengths), max(frames), sum(frames), cmvn=False)
+    norm, padded = k.fbank_cmvn(pcm, so, fo, len(lengths), max(frames), sum(frames), cmvn=True,
+                                padded_frames=max(frames) + 4, front_pad=2)
+    for i, (w, f) in enumerate(zip(waves, frames)):
+        if f == 0:
+            continue
+        ref = torchaudio.compliance.kaldi.fbank((w * 2 ** 15)[None], num_mel_bins=80, sample_frequency=16000.0)
+        got = raw[int(fo[i]):int(fo[i + 1])].cpu()
+        assert ref.shape == got.shape
+        assert (got - ref).abs().max() < 1e-4, (got - ref).abs().max()
+        x = ref.double()
+        mean = x.mean(0)
+        var = (x * x).mean(0) - mean * mean
+        cm = ((x - mean) / var.clamp_min(1e-10).sqrt()).float()
+        gotn = norm[int(fo[i]):int(fo[i + 1])].cpu()
+        if f > 1:
+            assert (gotn - cm).abs().max() < 1e-4 * max(1.0, (1 / var.clamp_min(1e-10).sqrt()).max().item() / 10), \
+                (gotn - cm).abs().max()
+        pb = padded[i].float().cpu()
+        assert pb[:2].abs().sum() == 0 and pb[2 + f:].abs().sum() == 0
+        assert (pb[2:2 + f] - gotn).abs().max() < 0.05
