@@ -77,22 +77,22 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2*
 }
 
 struct FbankSmem {
-    float samples[SAMPLES_PER_CTA + 8];
-    float window[WIN];
-    float2 w256[NC];
-    float2 w512[NC + 1];
-    float mel_w[MAX_MEL_TAPS];
+    alignas(16) float samples[SAMPLES_PER_CTA + 8];
+    alignas(16) float out[FR_PER_CTA][NMEL];
+    alignas(16) float2 buf[FB_WARPS][2][NC];
+    alignas(16) float window[WIN];
+    alignas(16) float2 w256[NC];
+    alignas(16) float2 w512[NC + 1];
+    alignas(16) float mel_w[MAX_MEL_TAPS];
+    alignas(16) float power[FB_WARPS][NC + 8];
     int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
-    float2 buf[FB_WARPS][2][NC];
-    float power[FB_WARPS][NC + 8];
-    float out[FR_PER_CTA][NMEL];
 };
 
 __global__ void __launch_bounds__(FB_THREADS)
 fbank_kernel(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
              const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
              float pcm_scale) {
-    extern __shared__ uint8_t fb_smem_raw[];
+    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
     FbankSmem& s = *reinterpret_cast<FbankSmem*>(fb_smem_raw);
     const int b = blockIdx.y;
     const long long s0 = sample_off[b];
