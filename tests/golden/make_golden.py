@@ -1,0 +1,226 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference (naver/pasero,
+imported from /root/reference) and torchaudio in the build container. Run once, commit the outputs:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so its own outputs on seeded inputs
+are the pin. Two import stubs (tests/golden/_stubs: sacrebleu, stopes) and one harness-side shim (torch's
+LRScheduler no longer accepts the positional `verbose` the reference passes, pasero/optimization.py:38) are
+needed to import it; no reference file is modified or copied.
+"""
+import json
+import os
+import shutil
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('PASERO_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+from tests.golden import synth  # noqa: E402  (seeded synthetic inputs shared with the tests)
+
+
+def import_reference():
+    warnings.filterwarnings('ignore')
+    sys.path.insert(0, os.path.join(HERE, '_stubs'))
+    sys.path.insert(0, REF)
+    orig = torch.optim.lr_scheduler.LRScheduler.__init__
+
+    def init(self, optimizer, last_epoch=-1, verbose=None):
+        orig(self, optimizer, last_epoch)
+    torch.optim.lr_scheduler.LRScheduler.__init__ = init
+    import pasero.tasks, pasero.datasets, pasero.models  # noqa: F401,E401  (fills the registries, cli/train.py:28-33)
+    import pasero
+    return pasero
+
+
+def make_task_and_model(pasero, tmp, extra=()):
+    from pasero.config import TrainingConfig, get_task_class, get_architecture
+    dict_path = os.path.join(tmp, 'dict.txt')
+    with open(dict_path, 'w') as f:
+        for i in range(synth.TINY['vocab_size'] - 4):
+            f.write(f'tok{i} 1\n')
+    shutil.copy(os.path.join(REF, 'examples/TED/de-en/bpecodes'), os.path.join(tmp, 'bpecodes'))
+    t = synth.TINY
+    args = ['--task', 'speech_translation', '--arch', 'transformer',
+            '--encoder-layers', str(t['encoder_layers']), '--decoder-layers', str(t['decoder_layers']),
+            '--embed-dim', str(t['embed_dim']), '--encoder-ffn-dim', str(t['ffn_dim']), '--decoder-ffn-dim', str(t['ffn_dim']),
+            '--encoder-attention-heads', str(t['heads']), '--decoder-attention-heads', str(t['heads']),
+            '--input-dim', '80', '--conv-input-dim', '80', '--conv-channels', str(t['conv_channels']),
+            '--conv-kernel-sizes', '5', '5', '--data-dir', tmp, '--dict', 'dict.txt', '--tokenizer-path', 'bpecodes',
+            '--source-lang', 'de', '--target-lang', 'en', '--model-dir', os.path.join(tmp, 'model'),
+            '--encoder-max-len', '3000', '--batch-size', '64000', '--dropout', '0', '--label-smoothing', '0.1',
+            '--metrics', '--early-stopping-metric', 'nll_loss', '--max-steps', '1000', '--valid-interval', '1000',
+            '--dataset-type', 'simple', '--dtype', 'float32', '--lr', str(synth.TRAIN['lr']),
+            '--warmup', str(synth.TRAIN['warmup']), '--seed', '1234'] + list(extra)
+    cfg = TrainingConfig(*args)
+    task = get_task_class(cfg.task)(cfg.data_dir, cfg.task_cfg)
+    task.setup_for_model(cfg.model_cfg)
+    cfg.dp_size, cfg.dp_rank, cfg.dp_local_size, cfg.dp_local_rank, cfg.start_rank = 1, 0, 1, 0, 0  # utils.setup_distributed
+    torch.manual_seed(1234)
+    model = get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)
+    # seeded, reference-independent weights (bf16-representable), so the fixtures need not carry them
+    sd = synth.tiny_state_dict()
+    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == synth.tiny_param_shapes()
+    missing = model.load_state_dict(sd, strict=False)
+    assert all('_float_tensor' in k for k in missing.missing_keys) and not missing.unexpected_keys, missing
+    return cfg, task, model
+
+
+def golden_fbank(out):
+    import torchaudio
+    res = {}
+    for name, n in synth.FBANK_CASES.items():
+        w = synth.waveform(name, n)
+        wt = torch.from_numpy(w)
+        ref32 = torchaudio.compliance.kaldi.fbank((wt * 2 ** 15)[None], num_mel_bins=80, sample_frequency=16000.0)
+        ref64 = torchaudio.compliance.kaldi.fbank((wt.double() * 2 ** 15)[None], num_mel_bins=80, sample_frequency=16000.0)
+        res[f'{name}_f32'] = ref32.numpy().astype(np.float32)
+        res[f'{name}_f64'] = ref64.numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(out, 'fbank_torchaudio.npz'), **res)
+    print('fbank goldens:', {k: v.shape for k, v in res.items()})
+
+
+def golden_batching(pasero, task, out):
+    from pasero import utils, datasets
+    res = {}
+    # docstring known-answer vectors of the reference (utils.py:797-813, :253, :265)
+    sizes = [1000, 2000, 4000, 500, 1000, 1000]
+    kat = utils.build_batches([0, 1, 2, 3, 4, 5], sizes.__getitem__, 4000, 1, 2)
+    assert kat == [[0, 1], [2], [3, 4], [5]], kat
+    assert utils.mask_to_len(torch.tensor([[0, 1, 0, 1, 0], [1, 1, 0, 0, 0]]).bool()).tolist() == [4, 2]
+    assert utils.len_to_mask(torch.tensor([0, 3, 1])).long().tolist() == [[1, 1, 1], [0, 0, 0], [0, 1, 1]]
+    samples = synth.batching_samples()
+    combos = []
+    for bs in (4000, 40000):
+        for mult in (None, 8):
+            for lines in (None, 50):
+                task.cfg.batch_size_multiple = mult
+                task.cfg.lines_per_batch = lines
+                ds = types.SimpleNamespace(batch_by=[], task=task, shuffle=True, batch_size=bs)
+                np.random.seed(synth.BATCHING_SEED)
+                batches = datasets.TrainingDataset.buffered_batching(ds, list(samples))
+                flat = np.array([s['index'] for b in batches for s in b], dtype=np.int64)
+                sizes_ = np.array([len(b) for b in batches], dtype=np.int64)
+                key = f'bs{bs}_m{mult or 0}_l{lines or 0}'
+                res[key + '_flat'], res[key + '_sizes'] = flat, sizes_
+                combos.append((key, len(batches), int(flat.size)))
+    task.cfg.batch_size_multiple = None
+    task.cfg.lines_per_batch = None
+    # collated tensors of one small batch (float16 features -> model dtype, padding values, lengths, prompt length)
+    np.random.seed(synth.BATCHING_SEED)
+    small = task.build_batches(list(samples[:64]), shuffle=True, batch_size=4000)[3]
+    col = task.collate(small, padding_idx=task.padding_idx, dtype=torch.float32, model_type='encoder_decoder')
+    res['collate_indices_in'] = np.array([s['index'] for s in small], dtype=np.int64)
+    for k in ('decoder_input', 'prompt_mask', 'prompt_length', 'indices', 'encoder_input_length'):
+        res['collate_' + k] = col[k].numpy()
+    res['collate_encoder_input_sum'] = col['encoder_input'].double().sum(dim=(1, 2)).numpy()
+    res['collate_encoder_input_shape'] = np.array(col['encoder_input'].shape)
+    np.savez_compressed(os.path.join(out, 'batching.npz'), **res)
+    print('batching goldens:', combos)
+
+
+def golden_model(pasero, cfg, task, model, out):
+    model.train()
+    batch = synth.model_batch()
+    names = ['enc_0', f"enc_{synth.TINY['encoder_layers'] - 1}", 'dec_0', f"dec_{synth.TINY['decoder_layers'] - 1}"]
+    enc_out, enc_mask, enc_layers = model.encoder(batch['encoder_input'].clone(), batch['encoder_input_length'], return_layers=names)
+    logits, dec_layers = model.decoder(enc_out, enc_mask, batch['decoder_input'][:, :-1], return_layers=names)
+    loss, logs = model(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    model.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    torch.save({
+        'tiny': synth.TINY, 'state_dict_keys': sorted(model.state_dict().keys()),
+        'loss': loss.item(), 'logs': logs, 'encoder_out': enc_out.detach(), 'encoder_mask': enc_mask,
+        'logits': logits.detach(),
+        'layers': {k: v.detach() for k, v in {**enc_layers, **dec_layers}.items()},
+        'grads': {k: synth.summarize_grad(v) for k, v in grads.items()},
+        'param_names': [k for k, _ in model.named_parameters()],
+    }, os.path.join(out, 'st_tiny_model.pt'))
+    print('model golden: loss', loss.item(), logs, 'params', sum(p.numel() for p in model.parameters()))
+
+
+def golden_training_curve(pasero, cfg, task, model, out):
+    """200 optimizer steps through the reference Trainer.train_step; per-step logs captured by wrapping Metrics.update."""
+    from pasero.training import Trainer
+    from pasero import utils
+    os.makedirs(cfg.model_dir, exist_ok=True)
+    metrics = utils.Metrics()
+    rows = []
+    current = {}
+    orig_update = metrics.update
+
+    def update(name, value, *a, **kw):
+        current[name] = value
+        return orig_update(name, value, *a, **kw)
+    metrics.update = update
+    trainer = Trainer(cfg, task, model, metrics, None)
+    batches = synth.train_batches()
+
+    def it():
+        i = 0
+        while True:
+            b = batches[i % len(batches)]
+            yield {k: (v.clone() if torch.is_tensor(v) else dict(v)) for k, v in b.items()}
+            i += 1
+    iterator = it()
+    for step in range(synth.TRAIN['steps']):
+        current.clear()
+        trainer.train_step(iterator)
+        rows.append({k: float(current[k]) for k in ('loss', 'nll_loss', 'num_tokens', 'num_lines', 'gnorm', 'lr')})
+        if step == 2:
+            sd3 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            opt3 = {n: {kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in trainer.optimizer.state[p].items()}
+                    for n, p in model.named_parameters() if p in trainer.optimizer.state}
+            trainer.save()
+            files = sorted(os.listdir(cfg.model_dir))
+            layout = {}
+            for fn in files:
+                path = os.path.join(cfg.model_dir, fn)
+                if fn.endswith('.bin') and not os.path.islink(path):
+                    ck = torch.load(path, map_location='cpu', weights_only=False)
+                    layout[fn] = {k: (sorted(v.keys()) if isinstance(v, dict) else type(v).__name__) for k, v in ck.items()}
+                    if fn.startswith('optimizer'):
+                        st = ck['optimizer']['state']
+                        first = next(iter(st))
+                        layout[fn]['optimizer.state.first_key'] = str(first)
+                        layout[fn]['optimizer.state.entry_keys'] = sorted(st[first].keys())
+                        layout[fn]['optimizer.keys'] = sorted(ck['optimizer'].keys())
+                elif os.path.islink(path):
+                    layout[fn] = 'symlink -> ' + os.readlink(path)
+            with open(os.path.join(out, 'checkpoint_layout.json'), 'w') as f:
+                json.dump(layout, f, indent=1, default=str)
+    torch.save({
+        'train': synth.TRAIN, 'curve': rows,
+        'state_dict_step3': {k: synth.summarize_grad(v) for k, v in sd3.items() if v.is_floating_point() and v.numel() > 1},
+        'optimizer_step3': {n: {'step': s['step'], 'exp_avg_sum': s['exp_avg'].double().sum().item(),
+                                'exp_avg_sq_sum': s['exp_avg_sq'].double().sum().item()} for n, s in opt3.items()},
+        'state_dict_final_checksum': {k: v.double().sum().item() for k, v in model.state_dict().items()},
+    }, os.path.join(out, 'st_tiny_train.pt'))
+    print('training golden: first', rows[0], 'last', rows[-1])
+
+
+def main():
+    out = HERE
+    pasero = import_reference()
+    golden_fbank(out)
+    tmp = tempfile.mkdtemp()
+    try:
+        cfg, task, model = make_task_and_model(pasero, tmp)
+        golden_batching(pasero, task, out)
+        golden_model(pasero, cfg, task, model, out)
+        cfg2, task2, model2 = make_task_and_model(pasero, tmp)
+        golden_training_curve(pasero, cfg2, task2, model2, out)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == '__main__':
+    main()

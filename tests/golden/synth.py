@@ -1,0 +1,132 @@
+"""Seeded synthetic inputs shared by tests/golden/make_golden.py (which feeds them to the reference) and the
+tests (which feed them to the oracle and to the CUDA path). numpy.random.RandomState only: reproducible
+everywhere."""
+import math
+
+import numpy as np
+import torch
+
+TINY = dict(vocab_size=200, encoder_layers=2, decoder_layers=2, embed_dim=128, ffn_dim=256, heads=2,
+            conv_channels=256)
+TRAIN = dict(lr=2e-3, warmup=20, steps=200, clip_norm=1.0, label_smoothing=0.1)
+FBANK_CASES = {'noise': 8000, 'tone': 12000, 'single_frame': 400}
+BATCHING_SEED = 7
+PAD, EOS, BOS = 1, 2, 2
+
+
+def waveform(name: str, n: int) -> np.ndarray:
+    """float32 PCM in [-1, 1)."""
+    rng = np.random.RandomState(1234)
+    if name == 'tone':
+        t = np.arange(n) / 16000.0
+        w = 0.3 * np.sin(2 * math.pi * 440 * t) * np.exp(-t) + 0.01 * rng.randn(n)
+    else:
+        w = rng.rand(n) - 0.5
+    return w.astype(np.float32)
+
+
+def batching_samples(n: int = 5000, real_features: int = 64) -> list:
+    """SURVEY.md §8d batching parity set: F ~ clip(lognormal(6.3, 0.6), 100, 3000), T+1 ~ clip(round(F/20)+U{0..8}, 3, 256)."""
+    rng = np.random.RandomState(BATCHING_SEED)
+    F = np.clip(rng.lognormal(6.3, 0.6, n), 100, 3000).astype(np.int64)
+    T1 = np.clip(np.round(F / 20).astype(np.int64) + rng.randint(0, 9, n), 3, 256)
+    zero = np.zeros((1, 80), dtype=np.float16)
+    samples = []
+    for i in range(n):
+        if i < real_features:
+            feats = rng.randn(int(F[i]), 80).astype(np.float16)
+        else:
+            feats = np.broadcast_to(zero, (int(F[i]), 80))  # only len/ndim/dtype matter for bucketing
+        dec = np.concatenate([[BOS], rng.randint(4, TINY['vocab_size'], int(T1[i]) - 2), [EOS]]).astype(np.int64)
+        pm = np.zeros_like(dec, dtype=bool)
+        pm[:1] = True
+        samples.append({'encoder_input': feats, 'decoder_input': dec, 'prompt_mask': pm,
+                        'meta': {'source_lang': 'de', 'target_lang': 'en'}})
+    return samples
+
+
+def _batch(rng, frames, dec_lens) -> dict:
+    B, Fm, Tm = len(frames), max(frames), max(dec_lens)
+    x = torch.zeros(B, Fm, 80)
+    dec = torch.full((B, Tm), PAD, dtype=torch.int64)
+    pm = torch.zeros(B, Tm, dtype=torch.bool)
+    for b, (f, t) in enumerate(zip(frames, dec_lens)):
+        x[b, :f] = torch.from_numpy(rng.randn(f, 80).astype(np.float32)).to(torch.bfloat16).float()
+        dec[b, :t] = torch.from_numpy(np.concatenate([[BOS], rng.randint(4, TINY['vocab_size'], t - 2), [EOS]]))
+        pm[b, 0] = True
+    return {'encoder_input': x, 'encoder_input_length': torch.tensor(frames), 'decoder_input': dec, 'prompt_mask': pm,
+            'prompt_length': torch.ones(B, dtype=torch.int64), 'indices': torch.arange(B),
+            'meta': {'source_lang': 'de', 'target_lang': 'en'}}
+
+
+def model_batch() -> dict:
+    return _batch(np.random.RandomState(11), [93, 61, 40, 77], [9, 12, 5, 7])
+
+
+def train_batches() -> list:
+    rng = np.random.RandomState(12)
+    return [_batch(rng, [120, 100, 90, 64], [10, 9, 12, 6]), _batch(rng, [57, 50, 41], [7, 6, 8]),
+            _batch(rng, [200, 180], [14, 15]), _batch(rng, [80, 80, 75, 60, 33], [8, 9, 7, 11, 5])]
+
+
+def tiny_param_shapes() -> dict:
+    """Parameter names/shapes of the tiny ST model in the reference's state_dict naming."""
+    t = TINY
+    d, f, c, v = t['embed_dim'], t['ffn_dim'], t['conv_channels'], t['vocab_size']
+    shapes = {
+        'encoder.subsample.conv_layers.0.weight': (c, 80, 5), 'encoder.subsample.conv_layers.0.bias': (c,),
+        'encoder.subsample.conv_layers.1.weight': (2 * d, c // 2, 5), 'encoder.subsample.conv_layers.1.bias': (2 * d,),
+    }
+
+    def attn(prefix):
+        for p in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+            shapes[f'{prefix}.{p}.weight'] = (d, d)
+            shapes[f'{prefix}.{p}.bias'] = (d,)
+
+    def ln(prefix):
+        shapes[f'{prefix}.weight'] = (d,)
+        shapes[f'{prefix}.bias'] = (d,)
+
+    def ffn(prefix):
+        shapes[f'{prefix}.fc1.weight'] = (f, d)
+        shapes[f'{prefix}.fc1.bias'] = (f,)
+        shapes[f'{prefix}.fc2.weight'] = (d, f)
+        shapes[f'{prefix}.fc2.bias'] = (d,)
+
+    for i in range(t['encoder_layers']):
+        p = f'encoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm')
+    shapes['decoder.embed_tokens.weight'] = (v, d)
+    for i in range(t['decoder_layers']):
+        p = f'decoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm')
+        attn(p + '.encoder_attn'); ln(p + '.encoder_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm')
+    return shapes
+
+
+def tiny_state_dict() -> dict:
+    """Seeded, reference-independent weights (bf16-representable fp32) for the tiny model."""
+    rng = np.random.RandomState(99)
+    sd = {}
+    for name, shape in tiny_param_shapes().items():
+        if 'layer_norm' in name:
+            w = (1.0 + 0.1 * rng.randn(*shape)) if name.endswith('weight') else 0.05 * rng.randn(*shape)
+        elif name.endswith('bias'):
+            w = 0.02 * rng.randn(*shape)
+        elif name == 'decoder.embed_tokens.weight':
+            w = rng.randn(*shape) * shape[1] ** -0.5
+            w[PAD] = 0
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            w = rng.randn(*shape) * fan_in ** -0.5
+        sd[name] = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+    return sd
+
+
+def summarize_grad(g: torch.Tensor) -> dict:
+    """Compact but discriminating digest of a gradient tensor (full tensor when small)."""
+    g = g.detach().float()
+    if g.numel() <= 4096:
+        return {'full': g.clone()}
+    g2 = g.reshape(g.shape[0], -1)
+    return {'rows': g2[:4].clone(), 'row_sum': g2.sum(1), 'col_sum': g2.sum(0), 'abs_sum': g2.abs().sum()}
