@@ -8,7 +8,7 @@ import torch
 
 TINY = dict(vocab_size=200, encoder_layers=2, decoder_layers=2, embed_dim=128, ffn_dim=256, heads=2,
             conv_channels=256)
-TRAIN = dict(lr=2e-3, warmup=20, steps=200, clip_norm=1.0, label_smoothing=0.1)
+TRAIN = dict(lr=2e-4, warmup=50, steps=200, clip_norm=1.0, label_smoothing=0.1)
 FBANK_CASES = {'noise': 8000, 'tone': 12000, 'single_frame': 400}
 BATCHING_SEED = 7
 PAD, EOS, BOS = 1, 2, 2
@@ -63,10 +63,22 @@ def model_batch() -> dict:
     return _batch(np.random.RandomState(11), [93, 61, 40, 77], [9, 12, 5, 7])
 
 
-def train_batches() -> list:
+def train_batches(n: int = 16) -> list:
+    """Zipf-distributed target tokens: learnable (unigram statistics) but not memorisable within 200 steps, so the
+    loss curve is smooth and two correct implementations stay within a fraction of a percent of each other."""
     rng = np.random.RandomState(12)
-    return [_batch(rng, [120, 100, 90, 64], [10, 9, 12, 6]), _batch(rng, [57, 50, 41], [7, 6, 8]),
-            _batch(rng, [200, 180], [14, 15]), _batch(rng, [80, 80, 75, 60, 33], [8, 9, 7, 11, 5])]
+    probs = 1.0 / np.arange(1, TINY['vocab_size'] - 3)
+    probs /= probs.sum()
+    out = []
+    for _ in range(n):
+        B = int(rng.randint(3, 7))
+        frames = sorted((int(f) for f in rng.randint(40, 200, B)), reverse=True)
+        dec_lens = [int(t) for t in rng.randint(5, 16, B)]
+        b = _batch(rng, frames, dec_lens)
+        for i, t in enumerate(dec_lens):
+            b['decoder_input'][i, 1:t - 1] = torch.from_numpy(4 + rng.choice(len(probs), t - 2, p=probs))
+        out.append(b)
+    return out
 
 
 def tiny_param_shapes() -> dict:
