@@ -119,16 +119,17 @@ int pb200_attention_bwd(const pb200_attn_params* params, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * sum = residual + dropout(x);  y = LayerNorm(sum) * gamma + beta   (gamma == NULL: no LayerNorm)
  * (pasero/models/transformer.py:1043-1054, 1073-1086, 1322-1339, 1389-1409). Dropout mask =
- * Philox(seed, offset, element / 8); backward regenerates it.
+ * Philox(seed, offset + (*offset_base << 12), element / 8); backward regenerates it. offset_base (device int64,
+ * may be NULL) lets a captured CUDA graph draw fresh masks on every replay.
  * ---------------------------------------------------------------------------------------------- */
 int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta, int64_t M,
-                             int64_t D, float eps, float p, uint64_t seed, uint64_t offset, void* sum_out, void* y_out,
-                             float* mean_out, float* rstd_out, void* stream);
+                             int64_t D, float eps, float p, uint64_t seed, uint64_t offset, const int64_t* offset_base,
+                             void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* stream);
 size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
 int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                              const float* mean, const float* rstd, int64_t M, int64_t D, float p, uint64_t seed,
-                             uint64_t offset, void* dresidual, void* dx, void* dgamma, void* dbeta, int32_t accumulate,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx, void* dgamma, void* dbeta,
+                             int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* column sums of a bf16 [M, N] matrix -> bf16 [N] (bias gradients) */
 size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);
@@ -141,9 +142,11 @@ int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out
  * Backward: dx (no ids) or fp32 atomics into dtable[ids[r]] (rows == padding_idx skipped).
  * ---------------------------------------------------------------------------------------------- */
 int pb200_embed_fwd(const int64_t* ids, const void* src, const void* pos, int64_t M, int64_t D, int64_t L, float scale,
-                    float p, uint64_t seed, uint64_t offset, int64_t num_embeddings, void* out, void* stream);
+                    float p, uint64_t seed, uint64_t offset, const int64_t* offset_base, int64_t num_embeddings, void* out,
+                    void* stream);
 int pb200_embed_bwd(const void* dy, const int64_t* ids, int64_t M, int64_t D, float scale, float p, uint64_t seed,
-                    uint64_t offset, int64_t padding_idx, int64_t num_embeddings, void* dx, float* dtable, void* stream);
+                    uint64_t offset, const int64_t* offset_base, int64_t padding_idx, int64_t num_embeddings, void* dx,
+                    float* dtable, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv subsampler pieces (pasero/models/modules.py:774-834): GLU over channels writing the next conv's

@@ -1,0 +1,164 @@
+"""Configuration surface of the ST training path, mirroring the reference's flat YAML / CLI option names
+(pasero/config.py: TransformerConfig :1054-1319, TrainingConfig :1469-1868, TranslationTaskConfig :1871-2090,
+DistributedConfig :500-546). Only the options this path reads are typed here; anything else found in a
+reference YAML is kept in `extra` (and rejected if it switches on a subsystem that is out of scope).
+"""
+from dataclasses import dataclass, field, fields
+from typing import Optional
+
+import yaml
+
+
+@dataclass
+class TransformerConfig:
+    # architecture (defaults = the reference's `transformer` arch: Transformer Base, post-norm, ReLU, sinusoidal)
+    embed_dim: int = 512
+    encoder_layers: int = 6
+    decoder_layers: int = 6
+    encoder_attention_heads: int = 8
+    decoder_attention_heads: int = 8
+    encoder_ffn_dim: int = 2048
+    decoder_ffn_dim: int = 2048
+    dropout: float = 0.1
+    attention_dropout: float = 0.0
+    activation_dropout: float = 0.0
+    embed_dropout: Optional[float] = None
+    decoder_dropout: Optional[float] = None
+    label_smoothing: Optional[float] = None        # task-dependent default: 0.1 for (speech_)translation
+    activation_fn: str = 'relu'
+    encoder_prenorm: bool = False
+    decoder_prenorm: bool = False
+    scale_embed: bool = True
+    scale_attn: bool = True
+    shared_embeddings: bool = True
+    tied_output_projection: bool = True
+    input_dim: Optional[int] = None
+    conv_input_dim: Optional[int] = None
+    conv_channels: Optional[int] = None
+    conv_kernel_sizes: Optional[tuple] = None
+    conv_strides: Optional[tuple] = None
+    conv_activation: str = 'glu'
+    encoder_positional_encoding: str = 'sinusoidal'
+    decoder_positional_encoding: str = 'sinusoidal'
+    positional_encoding_shift: int = 2
+    encoder_max_len: int = 256
+    decoder_max_len: Optional[int] = None          # task-dependent default: 256 for (speech_)translation
+    norm_eps: float = 1e-5
+    prompt_loss: float = 1.0
+    model_type: str = 'encoder_decoder'
+
+    def finalize(self, task: str = 'speech_translation') -> 'TransformerConfig':
+        if self.label_smoothing is None:
+            self.label_smoothing = 0.1 if task in ('translation', 'speech_translation') else 0.0
+        if self.decoder_max_len is None:
+            self.decoder_max_len = 256
+        if self.conv_kernel_sizes is not None:
+            self.conv_kernel_sizes = tuple(self.conv_kernel_sizes)
+            self.conv_strides = tuple(self.conv_strides) if self.conv_strides else tuple(2 for _ in self.conv_kernel_sizes)
+        unsupported = []
+        if self.attention_dropout:
+            unsupported.append('attention_dropout > 0')
+        if self.activation_dropout:
+            unsupported.append('activation_dropout > 0')
+        if self.activation_fn != 'relu':
+            unsupported.append(f'activation_fn={self.activation_fn}')
+        if self.conv_activation != 'glu':
+            unsupported.append(f'conv_activation={self.conv_activation}')
+        if self.encoder_positional_encoding != 'sinusoidal' or self.decoder_positional_encoding != 'sinusoidal':
+            unsupported.append('non-sinusoidal positions')
+        if not self.tied_output_projection:
+            unsupported.append('untied output projection')
+        if self.prompt_loss != 1.0:
+            unsupported.append('prompt_loss != 1')
+        if self.model_type != 'encoder_decoder':
+            unsupported.append(f'model_type={self.model_type}')
+        if self.embed_dim % self.encoder_attention_heads or self.embed_dim // self.encoder_attention_heads != 64 or \
+                self.embed_dim // self.decoder_attention_heads != 64:
+            unsupported.append('head_dim != 64')
+        if unsupported:
+            raise NotImplementedError('pasero_b200 (round 1) does not cover: ' + ', '.join(unsupported))
+        return self
+
+
+@dataclass
+class DistributedConfig:
+    dp_size: int = 1
+    tp_size: int = 1
+    dp_rank: int = 0
+    tp_rank: int = 0
+    dtype: str = 'bfloat16'
+    seed: Optional[int] = None
+    sequence_parallel: bool = True
+
+
+@dataclass
+class TrainingConfig(DistributedConfig):
+    task: str = 'speech_translation'
+    arch: str = 'transformer'
+    model_dir: str = 'models/pasero_b200'
+    lr: float = 0.0005
+    adam_betas: tuple = (0.9, 0.999)
+    adam_eps: float = 1e-8
+    warmup: int = 4000
+    init_lr: float = 0.0
+    min_lr: float = 0.0
+    weight_decay: float = 0.0
+    clip_norm: float = 1.0
+    virtual_dp_size: int = 1
+    max_steps: int = 1000
+    log_interval: int = 100
+    valid_interval: int = 1000
+    save_interval: Optional[int] = None
+    # task / data options of the ST path (TranslationTaskConfig / dataset configs)
+    batch_size: int = 4000
+    batch_size_multiple: Optional[int] = None
+    lines_per_batch: Optional[int] = None
+    max_source_len: Optional[int] = None
+    max_target_len: Optional[int] = None
+    buffer_size: int = 5000
+    bucket_bytes: int = 25 * 2 ** 20      # gradient allreduce bucket (torch DDP default: 25 MB)
+    cuda_graphs: bool = False              # capture forward+backward+optimizer per batch shape
+    model_cfg: TransformerConfig = field(default_factory=TransformerConfig)
+    extra: dict = field(default_factory=dict)
+
+    OUT_OF_SCOPE = ('fsdp', 'flat_fp16', 'amp', 'lora_rank', 'moe_', 'checkpoint_activations')
+
+    @classmethod
+    def from_dict(cls, opts: dict) -> 'TrainingConfig':
+        opts = {k.replace('-', '_'): v for k, v in opts.items()}
+        model_fields = {f.name for f in fields(TransformerConfig)}
+        train_fields = {f.name for f in fields(cls)} - {'model_cfg', 'extra'}
+        cfg = cls()
+        for k, v in opts.items():
+            if k in model_fields:
+                setattr(cfg.model_cfg, k, v)
+            elif k in train_fields:
+                setattr(cfg, k, tuple(v) if isinstance(v, list) else v)
+            else:
+                cfg.extra[k] = v
+        for k, v in cfg.extra.items():
+            if v and any(k.startswith(p) for p in cls.OUT_OF_SCOPE):
+                raise NotImplementedError(f'option {k}={v!r} selects a subsystem outside the ST data-parallel path')
+        if cfg.tp_size != 1:
+            raise NotImplementedError('tensor parallelism is out of scope (pasero/training.py:180-183)')
+        if cfg.dtype != 'bfloat16':
+            raise NotImplementedError('the sm_100a kernels compute in bfloat16 (dtype: bfloat16)')
+        cfg.model_cfg.finalize(cfg.task)
+        cfg.save_interval = cfg.save_interval or cfg.valid_interval
+        cfg.max_source_len = cfg.max_source_len or cfg.model_cfg.encoder_max_len
+        cfg.max_target_len = cfg.max_target_len or cfg.model_cfg.decoder_max_len
+        return cfg
+
+    @classmethod
+    def from_yaml(cls, path: str, **overrides) -> 'TrainingConfig':
+        with open(path) as f:
+            opts = yaml.safe_load(f) or {}
+        opts.update(overrides)
+        return cls.from_dict(opts)
+
+    def as_dict(self) -> dict:
+        """Flat dict in the reference's `cfg.as_dict()` style (stored under 'args' in checkpoints)."""
+        out = {f.name: getattr(self, f.name) for f in fields(self) if f.name not in ('model_cfg', 'extra')}
+        out.update({f.name: getattr(self.model_cfg, f.name) for f in fields(self.model_cfg)})
+        out.update(self.extra)
+        return out

@@ -13,7 +13,9 @@ namespace pb200 {
 // out[r, :] = dropout( bf16( bf16(src_row * scale) + pos[r % L, :] ) ),  src_row = table[ids[r]] or x[r]
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const bf16* __restrict__ src,
                                  const bf16* __restrict__ pos, long long M, int D, int L, float scale, float p,
-                                 uint64_t seed, uint64_t offset, long long num_embeddings, bf16* __restrict__ out) {
+                                 uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
+                                 long long num_embeddings, bf16* __restrict__ out) {
+    if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
     const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -57,8 +59,10 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const bf16* 
 
 // dsrc = bf16( bf16(dy * mask / (1-p)) * scale ); with ids: scatter-add (fp32 atomics) into dtable
 __global__ void embed_bwd_kernel(const bf16* __restrict__ dy, const long long* __restrict__ ids, long long M, int D,
-                                 float scale, float p, uint64_t seed, uint64_t offset, long long padding_idx,
-                                 long long num_embeddings, bf16* __restrict__ dx, float* __restrict__ dtable) {
+                                 float scale, float p, uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
+                                 long long padding_idx, long long num_embeddings, bf16* __restrict__ dx,
+                                 float* __restrict__ dtable) {
+    if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
     const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -256,28 +260,28 @@ static int ew_grid(long long work_items, int threads = 256) {
 using namespace pb200;
 
 extern "C" int pb200_embed_fwd(const int64_t* ids, const void* src, const void* pos, int64_t M, int64_t D, int64_t L,
-                               float scale, float p, uint64_t seed, uint64_t offset, int64_t num_embeddings, void* out,
-                               void* stream_) {
+                               float scale, float p, uint64_t seed, uint64_t offset, const int64_t* offset_base,
+                               int64_t num_embeddings, void* out, void* stream_) {
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0, "embed: D must be a multiple of 8");
     PB_CHECK(L > 0, "embed: L must be positive");
     embed_fwd_kernel<<<ew_grid(M * (D / 8)), 256, 0, (cudaStream_t)stream_>>>(
         (const long long*)ids, (const bf16*)src, (const bf16*)pos, M, (int)D, (int)L, scale, p, seed, offset,
-        num_embeddings, (bf16*)out);
+        (const long long*)offset_base, num_embeddings, (bf16*)out);
     PB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int pb200_embed_bwd(const void* dy, const int64_t* ids, int64_t M, int64_t D, float scale, float p,
-                               uint64_t seed, uint64_t offset, int64_t padding_idx, int64_t num_embeddings, void* dx,
-                               float* dtable, void* stream_) {
+                               uint64_t seed, uint64_t offset, const int64_t* offset_base, int64_t padding_idx,
+                               int64_t num_embeddings, void* dx, float* dtable, void* stream_) {
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0, "embed: D must be a multiple of 8");
     PB_CHECK((ids != nullptr) == (dtable != nullptr), "embed_bwd: ids and dtable go together");
     PB_CHECK(ids != nullptr || dx != nullptr, "embed_bwd: dx required without ids");
     embed_bwd_kernel<<<ew_grid(M * (D / 8)), 256, 0, (cudaStream_t)stream_>>>(
-        (const bf16*)dy, (const long long*)ids, M, (int)D, scale, p, seed, offset, padding_idx, num_embeddings,
-        (bf16*)dx, dtable);
+        (const bf16*)dy, (const long long*)ids, M, (int)D, scale, p, seed, offset, (const long long*)offset_base, padding_idx,
+        num_embeddings, (bf16*)dx, dtable);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -17,8 +17,10 @@ template <int NCH>  // NCH = ceil(D / 256): chunks of 8 elements per lane
 __global__ void __launch_bounds__(LN_WARPS * 32)
 dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual,
                           const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int M, int D, float eps,
-                          float p, uint64_t seed, uint64_t offset, bf16* __restrict__ sum_out,
-                          bf16* __restrict__ y_out, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                          float p, uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
+                          bf16* __restrict__ sum_out, bf16* __restrict__ y_out, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out) {
+    if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -107,8 +109,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dsum_extra,
                           const bf16* __restrict__ sum, const bf16* __restrict__ gamma,
                           const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D, float p,
-                          uint64_t seed, uint64_t offset, bf16* __restrict__ dresidual, bf16* __restrict__ dx,
-                          float* __restrict__ partial) {
+                          uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
+                          bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial) {
+    if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
@@ -273,7 +276,8 @@ extern "C" size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D) {
 
 extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
                                         int64_t M, int64_t D, float eps, float p, uint64_t seed, uint64_t offset,
-                                        void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* stream_) {
+                                        const int64_t* offset_base, void* sum_out, void* y_out, float* mean_out,
+                                        float* rstd_out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported (multiple of 8, <= 1024)", (long long)D);
@@ -285,7 +289,7 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
 #define PB_LN_FWD(N_)                                                                                         \
     dropout_add_ln_fwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                         \
         (const bf16*)x, (const bf16*)residual, (const bf16*)gamma, (const bf16*)beta, (int)M, (int)D, eps, p,  \
-        seed, offset, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out)
+        seed, offset, (const long long*)offset_base, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out)
     switch (nch) { case 1: PB_LN_FWD(1); break; case 2: PB_LN_FWD(2); break; case 3: PB_LN_FWD(3); break; default: PB_LN_FWD(4); }
 #undef PB_LN_FWD
     PB_LAUNCH_CHECK();
@@ -294,9 +298,9 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
 
 extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                                         const float* mean, const float* rstd, int64_t M, int64_t D, float p,
-                                        uint64_t seed, uint64_t offset, void* dresidual, void* dx, void* dgamma,
-                                        void* dbeta, int32_t accumulate, void* workspace, size_t workspace_bytes,
-                                        void* stream_) {
+                                        uint64_t seed, uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx,
+                                        void* dgamma, void* dbeta, int32_t accumulate, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported", (long long)D);
@@ -310,7 +314,7 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
 #define PB_LN_BWD(N_)                                                                                        \
     dropout_add_ln_bwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                        \
         (const bf16*)dy, (const bf16*)dsum_extra, (const bf16*)sum, (const bf16*)gamma, mean, rstd, (int)M,   \
-        (int)D, p, seed, offset, (bf16*)dresidual, (bf16*)dx, partial)
+        (int)D, p, seed, offset, (const long long*)offset_base, (bf16*)dresidual, (bf16*)dx, partial)
     switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();

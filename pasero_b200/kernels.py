@@ -13,6 +13,10 @@ from ._lib import AttnParams, GemmParams, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
 
+# device int64 scalar added (<< 12) to every dropout offset; set by the Trainer when it captures CUDA graphs so that
+# replays draw fresh masks. None -> offsets are used as given.
+RNG_OFFSET_BASE: Optional[Tensor] = None
+
 
 def _ws(nbytes: int, device) -> Optional[Tensor]:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device) if nbytes > 0 else None
@@ -129,7 +133,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     mean = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     rstd = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     check(lib.pb200_dropout_add_ln_fwd(x.data_ptr(), ptr(residual), ptr(gamma), ptr(beta), M, D, eps, p, seed, offset,
-                                       ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), stream_ptr()))
+                                       ptr(RNG_OFFSET_BASE), ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), stream_ptr()))
     if sum_out is None:
         sum_out = x  # LN of x alone: the saved pre-norm input is x itself
     return (y if has_ln else sum_out), sum_out, mean, rstd
@@ -145,7 +149,7 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
     dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
     ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if gamma is not None else None
     check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
-                                       p, seed, offset, ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
+                                       p, seed, offset, ptr(RNG_OFFSET_BASE), ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
                                        int(accumulate), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
     return dx, dres
 
@@ -168,7 +172,7 @@ def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int,
     lib = _lib.load()
     out = torch.empty(M, D, dtype=BF16, device=src.device)
     check(lib.pb200_embed_fwd(ptr(ids), src.data_ptr(), ptr(pos), M, D, L, scale, p, seed, offset,
-                              src.shape[0] if ids is not None else 0, out.data_ptr(), stream_ptr()))
+                              ptr(RNG_OFFSET_BASE), src.shape[0] if ids is not None else 0, out.data_ptr(), stream_ptr()))
     return out
 
 
@@ -176,7 +180,7 @@ def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p
               padding_idx: int = -1, dtable: Optional[Tensor] = None) -> Optional[Tensor]:
     lib = _lib.load()
     dx = torch.empty(M, D, dtype=BF16, device=dy.device) if ids is None else None
-    check(lib.pb200_embed_bwd(dy.data_ptr(), ptr(ids), M, D, scale, p, seed, offset, padding_idx,
+    check(lib.pb200_embed_bwd(dy.data_ptr(), ptr(ids), M, D, scale, p, seed, offset, ptr(RNG_OFFSET_BASE), padding_idx,
                               dtable.shape[0] if dtable is not None else 0, ptr(dx), ptr(dtable), stream_ptr()))
     return dx
 

@@ -1,0 +1,289 @@
+"""Autograd-aware fused ops of the ST training step. Every forward/backward here is a handful of C-ABI kernel
+launches (pasero_b200.kernels); torch only provides device memory, the autograd graph and the stream.
+
+Dropout masks are Philox(seed, offset): `DropoutState` hands out a fresh offset per call so that backward can
+regenerate the same mask without storing it.
+"""
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import kernels as K
+
+BF16 = torch.bfloat16
+
+
+class DropoutState:
+    """Process-wide Philox (seed, running offset). One offset per dropout site per forward."""
+    seed = 0
+    offset = 0
+
+    @classmethod
+    def reseed(cls, seed: int) -> None:
+        cls.seed, cls.offset = int(seed) & (2 ** 63 - 1), 0
+
+    @classmethod
+    def next(cls) -> tuple:
+        cls.offset += 1
+        return cls.seed, cls.offset
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b   (x: [M, K] bf16, W: [N, K])"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return K.linear_fwd(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        dx = K.linear_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
+        dw = K.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        db = K.colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+class FFNFn(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 (pasero/models/transformer.py:999-1019); ReLU fused in the fc1 epilogue, its
+    backward mask fused in the fc2 dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _c(x)
+        h = K.linear_fwd(x, w1, b1, act=1)
+        y = K.linear_fwd(h, w2, b2)
+        ctx.save_for_backward(x, w1, w2, h)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, h = ctx.saved_tensors
+        dy = _c(dy)
+        dh = K.linear_dgrad(dy, w2, relu_mask=h)
+        dw2 = K.linear_wgrad(dy, h)
+        db2 = K.colsum(dy)
+        dx = K.linear_dgrad(dh, w1)
+        dw1 = K.linear_wgrad(dh, x)
+        db1 = K.colsum(dh)
+        return dx, dw1, db1, dw2, db2
+
+
+class AttentionFn(torch.autograd.Function):
+    """Multi-head attention block with fused projections (pasero/models/modules.py:579-739, training path).
+
+    in_w: [3D, D] rows ordered (k, v, q) — the reference's parameter creation order — in_b: [3D];
+    self-attention: one GEMM produces k|v|q; cross-attention: q from `query`, k|v from `key` in one GEMM.
+    """
+
+    @staticmethod
+    def forward(ctx, query, key, in_w, in_b, out_w, out_b, kv_len, B, Lq, Lk, H, causal, scale):
+        D = H * 64
+        query = _c(query)
+        self_attn = key is None
+        if self_attn:
+            kvq = K.linear_fwd(query, in_w, in_b)                       # [B*L, 3D]
+            k2, v2, q2 = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
+            key_c = None
+        else:
+            key_c = _c(key)
+            kv = K.linear_fwd(key_c, in_w[:2 * D], in_b[:2 * D])         # [B*Lk, 2D]
+            q2 = K.linear_fwd(query, in_w[2 * D:], in_b[2 * D:])         # [B*Lq, D]
+            k2, v2 = kv[:, :D], kv[:, D:]
+            kvq = None
+        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
+        y = K.linear_fwd(o, out_w, out_b)
+        ctx.save_for_backward(query, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len)
+        ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        query, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len = ctx.saved_tensors
+        B, Lq, Lk, H, causal, scale, self_attn = ctx.dims
+        D = H * 64
+        dy = _c(dy)
+        d_o = K.linear_dgrad(dy, out_w)
+        d_out_w = K.linear_wgrad(dy, o)
+        d_out_b = K.colsum(dy)
+        d_in_w = torch.empty_like(in_w)
+        d_in_b = torch.empty(3 * D, dtype=BF16, device=dy.device)
+        if self_attn:
+            dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
+                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
+            dquery = K.linear_dgrad(dkvq, in_w)
+            K.linear_wgrad(dkvq, query, out=d_in_w)
+            K.colsum(dkvq, out=d_in_b)
+            dkey = None
+        else:
+            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            dquery = K.linear_dgrad(dq, in_w[2 * D:])
+            dkey = K.linear_dgrad(dkv, in_w[:2 * D])
+            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D])
+            K.linear_wgrad(dq, query, out=d_in_w[2 * D:])
+            K.colsum(dkv, out=d_in_b[:2 * D])
+            K.colsum(dq, out=d_in_b[2 * D:])
+        return dquery, dkey, d_in_w, d_in_b, d_out_w, d_out_b, None, None, None, None, None, None, None
+
+
+class DropoutAddLNFn(torch.autograd.Function):
+    """y = LayerNorm(residual + dropout(x)) (gamma given) or residual + dropout(x) (gamma None)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, p, eps):
+        x = _c(x)
+        residual = _c(residual) if residual is not None else None
+        seed, offset = DropoutState.next() if p > 0 else (0, 0)
+        y, s, mean, rstd = K.dropout_add_ln_fwd(x, residual, gamma, beta, eps, p, seed, offset)
+        ctx.save_for_backward(s if gamma is not None else None, gamma, mean, rstd)
+        ctx.cfg = (p, seed, offset, residual is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, gamma, mean, rstd = ctx.saved_tensors
+        p, seed, offset, has_res, has_beta = ctx.cfg
+        dy = _c(dy)
+        D = dy.shape[1]
+        dgamma = torch.empty(D, dtype=BF16, device=dy.device) if gamma is not None else None
+        dbeta = torch.empty(D, dtype=BF16, device=dy.device) if (gamma is not None and has_beta) else None
+        dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, has_res, dgamma, dbeta)
+        return dx, dres, dgamma, dbeta, None, None
+
+
+class EmbedFn(torch.autograd.Function):
+    """dropout(bf16(bf16(src * scale) + pos)): src = table[ids] (decoder tokens) or a feature matrix (encoder)."""
+
+    @staticmethod
+    def forward(ctx, src, ids, pos, scale, p, L, padding_idx):
+        seed, offset = DropoutState.next() if p > 0 else (0, 0)
+        M = ids.numel() if ids is not None else src.shape[0]
+        D = src.shape[1]
+        ids_flat = _c(ids).view(-1) if ids is not None else None
+        out = K.embed_fwd(ids_flat, _c(src), pos, M, D, L, scale, p, seed, offset)
+        ctx.save_for_backward(ids_flat)
+        ctx.cfg = (M, D, scale, p, seed, offset, padding_idx, src.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids_flat,) = ctx.saved_tensors
+        M, D, scale, p, seed, offset, padding_idx, rows = ctx.cfg
+        dy = _c(dy)
+        if ids_flat is None:
+            return K.embed_bwd(dy, None, M, D, scale, p, seed, offset), None, None, None, None, None, None
+        dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
+        K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
+        dtable = torch.empty(rows, D, dtype=BF16, device=dy.device)
+        K.f32_to_bf16(dtable32, dtable)
+        return dtable, None, None, None, None, None, None
+
+
+class ConvGLUFn(torch.autograd.Function):
+    """One layer of the conv subsampler: Conv1d(kernel KW, stride, padding KW//2) + GLU over channels
+    (pasero/models/modules.py:829-834) as a TMA-described implicit GEMM over the zero-padded [B, Tp, C] input
+    (row t of batch b = the KW*C contiguous elements starting at padded frame t*stride) with a fused bias epilogue,
+    then GLU written into the next layer's padded layout.
+
+    weight: [Cout, KW * Cin] in tap-major order (w[o, tap * Cin + c] = conv.weight[o, c, tap]).
+    """
+
+    @staticmethod
+    def forward(ctx, xp, weight, bias, B, Tin, Cin, KW, stride, out_Tp, out_front_pad, need_input_grad):
+        Tp = xp.shape[1]
+        Cout = weight.shape[0]
+        Tout = 1 + (Tin + 2 * (KW // 2) - KW) // stride
+        pre = torch.empty(B * Tout, Cout, dtype=BF16, device=xp.device)
+        K.gemm_raw(xp.data_ptr(), weight.data_ptr(), pre, Tout, Cout, KW * Cin, lda=stride * Cin, ldb=KW * Cin, ldc=Cout,
+                   batch=B, a_batch_stride=Tp * Cin, b_batch_stride=0, c_batch_stride=Tout * Cout, bias=bias, split_k=1)
+        out = K.glu_fwd(pre, B, Tout, Cout // 2, out_Tp, out_front_pad)
+        ctx.save_for_backward(xp, weight, pre)
+        ctx.dims = (B, Tin, Cin, KW, stride, Tout, Tp, out_Tp, out_front_pad, need_input_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, weight, pre = ctx.saved_tensors
+        B, Tin, Cin, KW, stride, Tout, Tp, out_Tp, out_front_pad, need_input_grad = ctx.dims
+        Cout = weight.shape[0]
+        # gradient w.r.t. the GLU output rows (drop the padding rows of the padded layout)
+        dy = _c(dout[:, out_front_pad:out_front_pad + Tout]).view(B * Tout, Cout // 2)
+        dpre = K.glu_bwd(dy, pre, B * Tout, Cout // 2)
+        dw = torch.empty_like(weight)
+        K.gemm_raw(dpre.data_ptr(), xp.data_ptr(), dw, Cout, KW * Cin, Tout, lda=Cout, ldb=stride * Cin, ldc=KW * Cin, batch=B,
+                   a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True)
+        db = K.colsum(dpre)
+        dxp = None
+        if need_input_grad:
+            dcol = torch.empty(B * Tout, KW * Cin, dtype=BF16, device=dout.device)
+            K.gemm_raw(dpre.data_ptr(), weight.data_ptr(), dcol, B * Tout, KW * Cin, Cout, lda=Cout, ldb=KW * Cin,
+                       ldc=KW * Cin, b_mn_major=True, split_k=1)
+            dx = K.col2im(dcol, B, Tin, Tout, Cin, KW, stride)            # [B*Tin, Cin]
+            front = KW // 2
+            dxp = torch.zeros_like(xp)
+            dxp[:, front:front + Tin] = dx.view(B, Tin, Cin)
+        return dxp, dw, db, None, None, None, None, None, None, None, None
+
+
+class ProjCEFn(torch.autograd.Function):
+    """Tied output projection + label-smoothed cross-entropy (pasero/models/modules.py:935-947,
+    transformer.py:323-380). The logits are produced once in bf16 and overwritten in place by their gradient in the
+    same pass that computes the loss; no fp32 copy, no softmax tensor.
+    Returns the summed loss (fp32 0-dim); `stats` (fp64[8], device) receives loss / nll / token count."""
+
+    unit_loss_grad = False   # Trainer sets this when the loss is the root of backward (grad_output == 1)
+
+    @staticmethod
+    def forward(ctx, x, table, target, padding_idx, label_smoothing, stats):
+        x = _c(x)
+        logits = K.linear_fwd(x, table, None)
+        before = stats[0].clone()
+        K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True)
+        ctx.save_for_backward(x, table, logits)
+        return (stats[0] - before).float()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, table, dlogits = ctx.saved_tensors
+        dx = K.linear_dgrad(dlogits, table)
+        dtable = K.linear_wgrad(dlogits, x)
+        if not ProjCEFn.unit_loss_grad:
+            dx = dx * dloss.to(dx.dtype)
+            dtable = dtable * dloss.to(dtable.dtype)
+        return dx, dtable, None, None, None, None
+
+
+# functional front-ends ------------------------------------------------------------------------------
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    shape = x.shape
+    y = LinearFn.apply(x.reshape(-1, shape[-1]), weight, bias)
+    return y.view(*shape[:-1], weight.shape[0])
+
+
+def ffn(x: Tensor, w1, b1, w2, b2) -> Tensor:
+    shape = x.shape
+    return FFNFn.apply(x.reshape(-1, shape[-1]), w1, b1, w2, b2).view(shape)
+
+
+def dropout_add_ln(x: Tensor, residual: Optional[Tensor], gamma, beta, p: float, eps: float) -> Tensor:
+    shape = x.shape
+    r2 = residual.reshape(-1, shape[-1]) if residual is not None else None
+    return DropoutAddLNFn.apply(x.reshape(-1, shape[-1]), r2, gamma, beta, float(p), float(eps)).view(shape)
+
+
+def attention_scale(head_dim: int, scaled: bool = True) -> float:
+    return 1.0 / math.sqrt(head_dim) if scaled else 1.0

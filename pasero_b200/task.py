@@ -1,0 +1,269 @@
+"""Host-side feature/batch contract of the speech-translation task (integer work, bit-exact with the reference):
+Dictionary ids, NumpyFile feature container, sample binarisation, length bucketing and collation.
+
+Mirrors pasero/preprocessing.py:45-236 (Dictionary), pasero/files.py:103-192 (NumpyFile),
+pasero/tasks/speech_translation.py:42-86 (preprocess), pasero/tasks/task.py:531-610 (collate, build_batches),
+pasero/utils.py:709-736, 783-843 (tokens_as_tensor, build_batches), pasero/datasets.py:708-730 (buffered_batching).
+The numpy global RNG is consumed in the same order as the reference, so seeded runs produce identical batches.
+"""
+import collections
+import os
+import pickle
+from typing import Callable, Iterable, Optional
+
+import numpy as np
+import torch
+from torch.nn.utils.rnn import pad_sequence
+
+from .config import TrainingConfig
+from .modules import mask_to_len
+
+SEP, PAD, EOS, UNK, BOS = '<sep>', '<pad>', '</s>', '<unk>', '<s>'
+
+
+class Dictionary:
+    """fairseq-style dictionary file ("token count" per line) -> ids; specials sep=0, pad=1, eos=2, unk=3 are
+    prepended when the file has none (pasero/preprocessing.py:125-150); bos falls back to eos."""
+
+    def __init__(self, path: Optional[str] = None, tokens: Optional[list] = None):
+        if tokens is None:
+            tokens = []
+            with open(path, encoding='utf-8') as f:
+                for line in f:
+                    line = line.rstrip('\n')
+                    if line:
+                        tokens.append(line.split(' ')[0])
+        token_set = set(tokens)
+        if EOS not in token_set:
+            for t in (SEP, BOS, PAD, EOS, UNK):
+                assert t not in token_set, 'dictionary has a partial set of special tokens'
+            tokens = [SEP, PAD, EOS, UNK] + tokens
+        self.tokens = tokens
+        self.indices = {w: i for i, w in enumerate(tokens)}
+        self.eos_idx = self.indices.get(EOS)
+        self.padding_idx = self.indices.get(PAD, self.indices.get(UNK))
+        self.bos_idx = self.indices.get(BOS, self.eos_idx)
+        self.unk_idx = self.indices.get(UNK, self.padding_idx)
+        self.sep_idx = self.indices.get(SEP, self.bos_idx)
+
+    def __len__(self):
+        return len(self.tokens)
+
+    def idx(self, token: str) -> int:
+        return self.indices.get(token, self.unk_idx)
+
+    def to_indices(self, tokens: list, max_len: Optional[int] = None, append_eos: bool = True,
+                   prepend_bos: bool = False, truncate_left: bool = False) -> np.ndarray:
+        ids = [self.idx(t) for t in tokens]
+        if max_len is not None:
+            max_len = max_len - int(append_eos) - int(prepend_bos)
+            ids = ids[-max_len:] if truncate_left else ids[:max_len]
+        if prepend_bos:
+            ids.insert(0, self.bos_idx)
+        if append_eos:
+            ids.append(self.eos_idx)
+        return np.array(ids, dtype=np.int64)
+
+
+class NumpyFile:
+    """Feature container of the reference (pasero/files.py:103-192): a pickled header
+    {'positions', 'lengths', 'dim', 'dtype'} followed by the raw rows of every utterance."""
+
+    def __init__(self, path: str):
+        self._path = path
+        self._file = open(path, 'rb')
+        header = pickle.load(self._file)
+        self._dim = int(header['dim'])
+        self._dtype = np.dtype(header['dtype'])
+        self._itemsize = self._dim * self._dtype.itemsize
+        pos_len = [(p, n) for p, n in zip(header['positions'], header['lengths']) if p > 0]  # skip empty slots
+        self._positions = np.array([p for p, _ in pos_len], dtype=np.int64)
+        self._lengths = np.array([n for _, n in pos_len], dtype=np.int64)
+        self._index = 0
+
+    @classmethod
+    def build(cls, path: str, features: Iterable[np.ndarray], dtype: str = 'float16', num_feats: Optional[int] = None):
+        def write_header(file, positions, lengths, dim):
+            pickle.dump({'positions': positions, 'lengths': lengths, 'dim': np.array(dim, dtype=np.int64), 'dtype': dtype}, file)
+        if num_feats is None:
+            num_feats = len(features)
+        d = os.path.dirname(path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        with open(path, 'wb') as file:
+            dim = 0
+            positions = np.zeros(num_feats, dtype=np.int64)
+            lengths = np.zeros(num_feats, dtype=np.int64)
+            write_header(file, positions, lengths, dim)
+            for i, x in enumerate(features):
+                x = x.astype(dtype)
+                positions[i] = file.tell()
+                lengths[i] = x.shape[0]
+                dim = x.shape[1]
+                file.write(x.tobytes())
+            file.seek(0)
+            write_header(file, positions, lengths, dim)
+        return cls(path)
+
+    def __len__(self):
+        return len(self._positions)
+
+    def get_positions(self):
+        return np.arange(len(self._positions)), self._lengths
+
+    def seek(self, index: int):
+        self._index = index
+        self._file.seek(self._positions[index])
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> np.ndarray:
+        if self._index >= len(self._positions):
+            raise StopIteration
+        self._file.seek(self._positions[self._index])
+        length = int(self._lengths[self._index])
+        x = np.frombuffer(self._file.read(length * self._itemsize), dtype=self._dtype).copy()
+        if self._dim > 1:
+            x = x.reshape(length, self._dim)
+        self._index += 1
+        return x
+
+    def close(self):
+        self._file.close()
+
+
+def tokens_as_tensor(token_list: list, padding_idx: int, dtype: Optional[torch.dtype] = None):
+    """pasero/utils.py:709-736: right-pad float -> 0.0 (cast to dtype), bool -> False, int -> padding_idx (int64)."""
+    token_list = [torch.as_tensor(tokens) for tokens in token_list]
+    if token_list[0].is_floating_point():
+        tokens = pad_sequence(token_list, batch_first=True, padding_value=0.0).to(dtype)
+    elif token_list[0].dtype is torch.bool:
+        tokens = pad_sequence(token_list, batch_first=True, padding_value=False).bool()
+    else:
+        tokens = pad_sequence(token_list, batch_first=True, padding_value=padding_idx).long()
+    lengths = torch.LongTensor(list(map(len, token_list)))
+    return tokens, lengths
+
+
+def build_batches(indices, size_fn: Callable, batch_size: int, batch_size_multiple: Optional[int] = None,
+                  max_lines: Optional[int] = None) -> list:
+    """pasero/utils.py:783-843 — greedy packing of length-sorted indices under a padded-size budget."""
+    batch_size_multiple = batch_size_multiple or 1
+    batches, batch, lengths = [], [], []
+    max_len = 0
+    for idx in indices:
+        size = size_fn(idx)
+        if size > batch_size:
+            continue
+        lengths.append(size)
+        max_len = max(max_len, size)
+        if (max_lines and len(batch) >= max_lines) or max_len * (len(batch) + 1) > batch_size:
+            multiple_len = max(batch_size_multiple * (len(batch) // batch_size_multiple), len(batch) % batch_size_multiple)
+            batches.append(batch[:multiple_len])
+            batch = batch[multiple_len:]
+            lengths = lengths[multiple_len:]
+            max_len = max(lengths) if lengths else 0
+        batch.append(idx)
+    if batch:
+        batches.append(batch)
+    return batches
+
+
+class SpeechTranslationTask:
+    """The slice of pasero.tasks.SpeechTranslationTask the training step needs."""
+
+    model_type = 'encoder_decoder'
+    find_unused_parameters = False
+    encoder_num_embeddings = 0
+
+    def __init__(self, cfg: TrainingConfig, dictionary: Dictionary, target_tags: tuple = ()):
+        self.cfg = cfg
+        self.dictionary = dictionary
+        self.target_tags = tuple(target_tags)
+        self.prepend_bos = True
+        self.max_source_len = cfg.max_source_len
+        self.max_target_len = cfg.max_target_len
+        self.min_len_ratio = self.max_len_ratio = None
+
+    @property
+    def padding_idx(self) -> int:
+        return self.dictionary.padding_idx
+
+    @property
+    def eos_idx(self) -> int:
+        return self.dictionary.eos_idx
+
+    @property
+    def decoder_num_embeddings(self) -> int:
+        return len(self.dictionary)
+
+    def should_skip(self, source_len: int, target_len: int) -> bool:
+        ratio = source_len / max(1, target_len)
+        return bool(source_len == 0 or source_len > self.max_source_len or target_len > self.max_target_len or
+                    self.min_len_ratio and ratio < self.min_len_ratio or self.max_len_ratio and ratio > self.max_len_ratio)
+
+    def preprocess(self, sample: dict, truncate: bool = False, tokenize: bool = False, append_eos: bool = False) -> dict:
+        """pasero/tasks/speech_translation.py:42-86 with pre-tokenised targets (BPE itself is CPU string work that
+        stays with the reference's tokenizers): features pass through, target -> ids with BOS/EOS, prompt mask."""
+        if tokenize:
+            raise NotImplementedError('subword tokenisation is outside the hot path; pass BPE-split targets')
+        source, target, meta = sample['source'], sample['target'], sample.get('meta', {})
+        source_cutoff = self.max_source_len if truncate else None
+        target_cutoff = self.max_target_len if truncate else None
+        tags = list(self.target_tags)
+        encoder_input = source[:source_cutoff]
+        target_tok = tags + (target.split() if target is not None else [])
+        decoder_input = self.dictionary.to_indices(target_tok, max_len=target_cutoff, prepend_bos=self.prepend_bos,
+                                                   append_eos=append_eos)
+        prompt_mask = np.zeros_like(decoder_input, dtype=bool)
+        prompt_mask[:len(tags) + int(self.prepend_bos)] = True
+        if self.should_skip(len(encoder_input), len(decoder_input)):
+            assert not truncate
+            return {}
+        return {'encoder_input': encoder_input, 'decoder_input': decoder_input, 'prompt_mask': prompt_mask, 'meta': meta}
+
+    def build_batches(self, data: list, shuffle: bool = True, sort: bool = True, batch_size: Optional[int] = None) -> list:
+        """pasero/tasks/task.py:573-610"""
+        encoder_length = np.array([len(sample['encoder_input']) for sample in data])
+        decoder_length = np.array([len(sample['decoder_input']) for sample in data])
+        length = np.maximum(encoder_length, decoder_length)
+        indices = np.random.permutation(len(data)) if shuffle else np.arange(len(data))
+        if sort:
+            indices = indices[np.argsort(decoder_length[indices], kind='stable')]
+            indices = indices[np.argsort(encoder_length[indices], kind='stable')]
+        batch_indices = build_batches(indices, length.__getitem__, batch_size or self.cfg.batch_size,
+                                      self.cfg.batch_size_multiple, self.cfg.lines_per_batch)
+        return [[{**data[i], 'index': i} for i in idx] for idx in batch_indices]
+
+    def buffered_batching(self, buffer: list, batch_by=(), shuffle: bool = True, batch_size: Optional[int] = None) -> list:
+        """pasero/datasets.py:708-730"""
+        groups = collections.defaultdict(list)
+        for sample in buffer:
+            key = tuple(sample['meta'].get(k) for k in batch_by)
+            if sample.get('encoder_input') is not None:
+                key = key + (sample['encoder_input'].ndim, sample['encoder_input'].dtype)
+            groups[key].append(sample)
+        batches = []
+        for group in groups.values():
+            batches += self.build_batches(group, shuffle=shuffle, batch_size=batch_size)
+        if shuffle:
+            np.random.shuffle(batches)
+        return batches
+
+    @classmethod
+    def collate(cls, batch: list, padding_idx: int, dtype: torch.dtype, model_type: str = 'encoder_decoder'):
+        """pasero/tasks/task.py:531-571 + pasero/tasks/translation.py:876-899"""
+        if not batch:
+            return None
+        decoder_input, _ = tokens_as_tensor([s['decoder_input'] for s in batch], padding_idx, dtype)
+        indices = torch.tensor([s['index'] for s in batch])
+        prompt_mask, _ = tokens_as_tensor([s['prompt_mask'] for s in batch], padding_idx, dtype)
+        prompt_length = mask_to_len(prompt_mask)
+        meta = batch[0]['meta']
+        meta = {k: v for k, v in meta.items() if all(s['meta'].get(k) == v for s in batch[1:])}
+        batched = {'decoder_input': decoder_input, 'meta': meta, 'prompt_mask': prompt_mask, 'prompt_length': prompt_length,
+                   'indices': indices}
+        encoder_input, encoder_input_length = tokens_as_tensor([s['encoder_input'] for s in batch], padding_idx, dtype)
+        batched.update({'encoder_input': encoder_input, 'encoder_input_length': encoder_input_length})
+        return batched

@@ -1,0 +1,426 @@
+"""The training step of the ST path: B200-native counterpart of pasero/training.py (Trainer.train_step :324-517,
+checkpoint I/O :613-939) and pasero/optimization.py (Adam :56-149, LRScheduler :21-52, clip_grad_norm_ :390-427).
+
+Design (B200-first, one process per GPU):
+  * every parameter, gradient and Adam moment lives in ONE flat arena (bf16 params/grads, fp32 moments); the
+    nn.Parameters are views, so the optimizer is two kernel launches (grad-norm, clip+Adam) instead of ~10 x 353;
+  * data parallelism = bucketed bf16 allreduce (sum) of slices of the gradient arena over NCCL on a side stream,
+    launched from post-accumulate hooks in reverse-layer order so it overlaps the rest of backward; the loss /
+    token-count scalars ride in one fp64 allreduce; no all_gather_object, no per-step host synchronisation
+    (the reference syncs >= 5 times per micro-batch);
+  * the whole step (forward, backward, clip, Adam) can be captured in a CUDA graph per batch shape; step scalars
+    (lr, bias corrections, dropout offsets) live in device memory and are refreshed before each replay.
+"""
+import math
+import os
+import time
+from collections import defaultdict
+from typing import Iterator, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import kernels as K
+from . import ops
+from .config import TrainingConfig
+
+BF16 = torch.bfloat16
+ALIGN = 8  # elements: every parameter starts on a 16-byte boundary (TMA / 128-bit loads)
+
+
+class LRScheduler:
+    """pasero/optimization.py:21-52: linear warmup init_lr -> lr, then lr * sqrt(warmup / step); warmup == 0 means
+    linear decay to min_lr over max_steps. `last_epoch` counts completed scheduler steps, like torch's."""
+
+    def __init__(self, cfg: TrainingConfig):
+        assert cfg.init_lr >= 0 and cfg.warmup >= 0 and cfg.init_lr <= cfg.lr and cfg.max_steps > 0
+        self.warmup, self.max_steps = cfg.warmup, cfg.max_steps
+        self.max_lr, self.min_lr, self.init_lr = cfg.lr, cfg.min_lr, cfg.init_lr
+        self.last_epoch = 0
+
+    def lr_at(self, step: int) -> float:
+        if self.warmup == 0:
+            lr = self.max_lr - step * (self.max_lr - self.min_lr) / self.max_steps
+        elif step < self.warmup:
+            lr = self.init_lr + step * (self.max_lr - self.init_lr) / self.warmup
+        else:
+            lr = self.max_lr * math.sqrt(self.warmup / step)
+        return max(lr, self.min_lr)
+
+    def get_last_lr(self) -> list:
+        return [self.lr_at(self.last_epoch)]
+
+    def step(self) -> None:
+        self.last_epoch += 1
+
+    def state_dict(self) -> dict:
+        return {'last_epoch': self.last_epoch, 'warmup': self.warmup, 'max_steps': self.max_steps, 'max_lr': self.max_lr,
+                'min_lr': self.min_lr, 'init_lr': self.init_lr, '_step_count': self.last_epoch + 1,
+                '_last_lr': self.get_last_lr()}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.last_epoch = state['last_epoch']
+
+
+class ParamArena:
+    """Flat storage for parameters (bf16), gradients (bf16) and Adam moments (fp32); parameters become views."""
+
+    def __init__(self, model: torch.nn.Module, device):
+        self.params, self.names, self.offsets = [], [], []
+        seen = set()
+        off = 0
+        for name, p in model.named_parameters():
+            if not p.requires_grad or id(p) in seen:
+                continue
+            seen.add(id(p))
+            self.params.append(p)
+            self.names.append(name)
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.param = torch.zeros(off, dtype=BF16, device=device)
+        self.grad = torch.zeros(off, dtype=BF16, device=device)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.param[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def view(self, flat: Tensor, i: int) -> Tensor:
+        p, o = self.params[i], self.offsets[i]
+        return flat[o:o + p.numel()].view(p.shape)
+
+    def rebind_grads(self) -> None:
+        for i, p in enumerate(self.params):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + self.offsets[i] * 2:
+                p.grad = self.view(self.grad, i)
+
+
+class GradBuckets:
+    """Bucketed allreduce of the gradient arena, overlapped with backward (replaces torch DDP's reducer,
+    pasero/training.py:243-250). Buckets are contiguous arena slices of ~bucket_bytes, filled back to front."""
+
+    def __init__(self, arena: ParamArena, bucket_bytes: int, group=None):
+        self.arena, self.group = arena, group
+        self.stream = torch.cuda.Stream()
+        self.buckets = []           # (start, end) element ranges, in the order they become ready
+        self.param_bucket = {}
+        n = len(arena.params)
+        end_i = n
+        while end_i > 0:
+            start_i = end_i
+            size = 0
+            while start_i > 0 and (size == 0 or size + arena.params[start_i - 1].numel() * 2 <= bucket_bytes):
+                start_i -= 1
+                size += arena.params[start_i].numel() * 2
+            lo = arena.offsets[start_i]
+            hi = arena.offsets[end_i] if end_i < n else arena.numel
+            b = len(self.buckets)
+            self.buckets.append((lo, hi))
+            for i in range(start_i, end_i):
+                self.param_bucket[i] = b
+            end_i = start_i
+        self.pending = [0] * len(self.buckets)
+        self.sizes = [0] * len(self.buckets)
+        for i, b in self.param_bucket.items():
+            self.sizes[b] += 1
+        self.enabled = True
+        self.handles = []
+        for i, p in enumerate(arena.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i: int):
+        def hook(param):
+            if not self.enabled:
+                return
+            b = self.param_bucket[i]
+            self.pending[b] += 1
+            if self.pending[b] == self.sizes[b]:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: int) -> None:
+        lo, hi = self.buckets[b]
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        self.pending[b] = -1
+
+    def start_step(self, sync: bool) -> None:
+        self.enabled = sync
+        self.pending = [0] * len(self.buckets)
+
+    def finish(self, stats: Optional[Tensor] = None) -> None:
+        """Flush buckets whose hooks never fired (unused parameters), reduce the step scalars, rejoin the stream."""
+        for b in range(len(self.buckets)):
+            if self.pending[b] != -1:
+                self._launch(b)
+        if stats is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class Trainer:
+    def __init__(self, cfg: TrainingConfig, task, model, metrics=None, status_mp=None, device: Optional[str] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('pasero_b200.Trainer needs a CUDA device: the sm_100a kernels have no CPU fallback')
+        self.cfg, self.task, self.model = cfg, task, model
+        self.device = torch.device(device or f'cuda:{torch.cuda.current_device()}')
+        self.dtype = BF16
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.dp_size = dist.get_world_size() if self.distributed else 1
+        cfg.dp_size = self.dp_size
+        self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)
+        model.to(self.dtype)
+        model.to(self.device)
+        self.arena = ParamArena(model, self.device)
+        self.param_names = list(self.arena.names)
+        if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
+            dist.broadcast(self.arena.param, src=0)
+        self.buckets = GradBuckets(self.arena, cfg.bucket_bytes) if self.distributed else None
+        self.scheduler = LRScheduler(cfg)
+        self.optimizer_steps = 0     # Adam's state['step']
+        self.steps = 0
+        self.metrics = metrics if metrics is not None else defaultdict(list)
+        self.hyper = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.stats = model.stats_buffer(self.device)
+        self._stats_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+        self.rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
+        model.defer_logs = True
+        ops.ProjCEFn.unit_loss_grad = True
+        ops.DropoutState.reseed(cfg.seed if cfg.seed is not None else int(time.time()))
+        self._graphs = {}
+        self.saved = True
+
+    # ------------------------------------------------------------------ step pieces
+    def _write_hyper(self) -> None:
+        cfg = self.cfg
+        lr = self.scheduler.get_last_lr()[0]
+        b1, b2 = cfg.adam_betas
+        t = self.optimizer_steps + 1
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, cfg.adam_eps, cfg.weight_decay
+        h[5], h[6], h[7], h[8] = bc1, math.sqrt(bc2), cfg.clip_norm, 1.0
+        h[9], h[10], h[11], h[12] = 1 - b1, 1 - b2, lr / bc1, cfg.weight_decay * lr
+        self.hyper.copy_(h, non_blocking=True)
+
+    def move_to_device(self, batch: dict) -> dict:
+        """utils.move_to_device(batch, 'cuda', dtype) (pasero/utils.py:691-702): float tensors are cast to bf16."""
+        out = {}
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                v = v.to(self.device, non_blocking=True)
+                if v.is_floating_point():
+                    v = v.to(self.dtype)
+            out[k] = v
+        return out
+
+    def _forward_backward(self, batch: dict):
+        loss, logs = self.model(**batch)
+        loss.backward()
+        return logs
+
+    def _optimizer_kernels(self) -> None:
+        K.grad_sqnorm(self.arena.grad, self.hyper, self.stats)
+        K.adam_step(self.arena.param, self.arena.grad, self.arena.exp_avg, self.arena.exp_avg_sq, self.hyper, self.stats)
+
+    # ------------------------------------------------------------------ the step
+    def train_step(self, batch_iterator: Iterator[dict]) -> dict:
+        """One optimizer update over `update_freq` micro-batches (pasero/training.py:324-517). Returns the step's
+        logs: loss / nll_loss in bits (summed over all ranks' tokens), num_tokens, num_lines, gnorm, lr."""
+        self.model.train()
+        self.stats.zero_()
+        self.arena.grad.zero_()
+        self.arena.rebind_grads()
+        for batch_id in range(self.update_freq):
+            batch = next(batch_iterator)
+            batch = self.move_to_device(batch)
+            batch.setdefault('meta', {})
+            batch['meta']['step'] = self.steps
+            last = batch_id == self.update_freq - 1
+            if self.buckets is not None:
+                self.buckets.start_step(sync=last)   # no_sync() on all but the last micro-batch (training.py:407)
+            self._forward_backward(batch)
+        if self.buckets is not None:
+            self.buckets.finish(self.stats)
+        self._write_hyper()
+        self._optimizer_kernels()
+        return self._finish_step()
+
+    def _finish_step(self) -> dict:
+        self.scheduler.step()
+        self.optimizer_steps += 1
+        self.steps += 1
+        self.saved = False
+        self._stats_host.copy_(self.stats, non_blocking=True)
+        self._stats_event = torch.cuda.Event()
+        self._stats_event.record()
+        self._pending_lr = self.scheduler.get_last_lr()[0]
+        return LazyLogs(self)
+
+    def read_logs(self) -> dict:
+        """Synchronises on the step's single deferred D2H copy and returns python numbers."""
+        self._stats_event.synchronize()
+        s = self._stats_host.tolist()
+        logs = {'loss': s[0] / math.log(2), 'nll_loss': s[1] / math.log(2), 'num_tokens': int(s[2]), 'num_lines': int(s[3]),
+                'gnorm': math.sqrt(max(s[4], 0.0)), 'lr': self._pending_lr, 'loss_scale': 1.0}
+        return logs
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def train_step_graphed(self, batch: dict) -> 'LazyLogs':
+        """Same update as train_step for update_freq == 1, with forward + backward + clip + Adam replayed from a CUDA
+        graph keyed on the batch shape. Inputs are copied into static buffers; step scalars are refreshed in device
+        memory before the replay; dropout offsets advance through `rng_base`."""
+        assert self.update_freq == 1 and self.buckets is None, 'graph capture covers the single-GPU, update_freq=1 step'
+        tensors = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(tensors.items()))
+        key = key + tuple(sorted((k, v) for k, v in batch.items() if isinstance(v, (int, tuple))))
+        self.model.train()
+        if key not in self._graphs:
+            static = {}
+            for k, v in tensors.items():
+                dt = self.dtype if v.is_floating_point() else v.dtype
+                static[k] = torch.empty(v.shape, dtype=dt, device=self.device)
+            extras = {k: v for k, v in batch.items() if not torch.is_tensor(v)}
+            K.RNG_OFFSET_BASE = self.rng_base
+            ops.DropoutState.offset = 0
+            self._write_hyper()
+            snapshot = [self.arena.param.clone(), self.arena.exp_avg.clone(), self.arena.exp_avg_sq.clone()]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):   # warm-up outside capture (lazy inits, workspace sizes)
+                for k, v in tensors.items():
+                    static[k].copy_(v)
+                self._graph_body(static, extras)
+            torch.cuda.current_stream().wait_stream(side)
+            self.arena.param.copy_(snapshot[0]); self.arena.exp_avg.copy_(snapshot[1]); self.arena.exp_avg_sq.copy_(snapshot[2])
+            graph = torch.cuda.CUDAGraph()
+            ops.DropoutState.offset = 0
+            with torch.cuda.graph(graph):
+                self._graph_body(static, extras)
+            self._graphs[key] = (graph, static)
+        graph, static = self._graphs[key]
+        for k, v in tensors.items():
+            static[k].copy_(v, non_blocking=True)
+        self._write_hyper()
+        graph.replay()
+        self.rng_base += 1
+        return self._finish_step()
+
+    def _graph_body(self, static: dict, extras: dict) -> None:
+        self.stats.zero_()
+        self.arena.grad.zero_()
+        self.arena.rebind_grads()
+        batch = dict(static)
+        batch.update(extras)
+        self._forward_backward(batch)
+        self._optimizer_kernels()
+
+    # ------------------------------------------------------------------ checkpoints (reference layout)
+    def _named_state(self, flat: Tensor) -> dict:
+        """View a flat arena (moments) through the model's state_dict hooks -> tensors keyed by reference names."""
+        saved = [p.data for p in self.arena.params]
+        try:
+            for i, p in enumerate(self.arena.params):
+                p.data = self.arena.view(flat, i)
+            return {k: v.detach().clone().cpu() for k, v in self.model.state_dict().items() if v.is_floating_point() and v.numel() > 1}
+        finally:
+            for p, d in zip(self.arena.params, saved):
+                p.data = d
+
+    def _load_named_state(self, flat: Tensor, state: dict) -> None:
+        saved = [p.data for p in self.arena.params]
+        try:
+            for i, p in enumerate(self.arena.params):
+                p.data = self.arena.view(flat, i)
+            self.model.load_state_dict({k: v for k, v in state.items()}, strict=False)
+        finally:
+            for p, d in zip(self.arena.params, saved):
+                p.data = d
+
+    def model_state_dict(self) -> dict:
+        return {k: v.detach().clone().cpu() for k, v in self.model.state_dict().items()}
+
+    def optimizer_state_dict(self) -> dict:
+        """{'state': {param_name: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} — the reference keys
+        optimizer state by parameter *name* (pasero/training.py:899-906)."""
+        m, v = self._named_state(self.arena.exp_avg), self._named_state(self.arena.exp_avg_sq)
+        names = [k for k in m if not k.endswith('_float_tensor')]
+        state = {k: {'step': self.optimizer_steps, 'exp_avg': m[k], 'exp_avg_sq': v[k]} for k in names}
+        group = {'lr': self.scheduler.get_last_lr()[0], 'betas': tuple(self.cfg.adam_betas), 'eps': self.cfg.adam_eps,
+                 'weight_decay': self.cfg.weight_decay, 'amsgrad': False, 'params': names}
+        return {'state': state, 'param_groups': [group]}
+
+    def save(self, model_dir: Optional[str] = None) -> None:
+        """model_{steps}.bin / optimizer_{steps}.bin / metrics_{steps}.bin + model_last.bin symlink
+        (pasero/training.py:736-780, 878-939)."""
+        model_dir = model_dir or self.cfg.model_dir
+        if self.distributed and dist.get_rank() != 0:
+            return
+        os.makedirs(model_dir, exist_ok=True)
+        args = self.cfg.as_dict()
+        torch.save({'args': args, 'model': self.model_state_dict(), 'steps': self.steps},
+                   os.path.join(model_dir, f'model_{self.steps}.bin'))
+        torch.save({'args': args, 'optimizer': self.optimizer_state_dict(), 'scheduler': self.scheduler.state_dict(),
+                    'scaler': {}, 'steps': self.steps}, os.path.join(model_dir, f'optimizer_{self.steps}.bin'))
+        torch.save({'args': args, 'metrics': dict(self.metrics) if isinstance(self.metrics, dict) else {},
+                    'last_valid': 0, 'best_score': None, 'patience': None, 'steps': self.steps},
+                   os.path.join(model_dir, f'metrics_{self.steps}.bin'))
+        link = os.path.join(model_dir, 'model_last.bin')
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink(f'model_{self.steps}.bin', link)
+        self.saved = True
+
+    def load(self, model_dir: str, steps: Optional[int] = None, load_train_state: bool = True) -> None:
+        if steps is None:
+            target = os.readlink(os.path.join(model_dir, 'model_last.bin'))
+            steps = int(target[len('model_'):-len('.bin')])
+        ckpt = torch.load(os.path.join(model_dir, f'model_{steps}.bin'), map_location='cpu', weights_only=False)
+        self.model.load_state_dict(ckpt['model'], strict=False)
+        self.steps = ckpt.get('steps', 0)
+        opt_path = os.path.join(model_dir, f'optimizer_{steps}.bin')
+        if load_train_state and os.path.exists(opt_path):
+            opt = torch.load(opt_path, map_location='cpu', weights_only=False)
+            state = opt['optimizer']['state']
+            self._load_named_state(self.arena.exp_avg, {k: v['exp_avg'] for k, v in state.items()})
+            self._load_named_state(self.arena.exp_avg_sq, {k: v['exp_avg_sq'] for k, v in state.items()})
+            self.optimizer_steps = next(iter(state.values()))['step'] if state else 0
+            self.scheduler.load_state_dict(opt['scheduler'])
+
+
+class LazyLogs(dict):
+    """Step logs whose values are fetched from the deferred D2H copy on first access (no sync inside the step)."""
+
+    def __init__(self, trainer: Trainer):
+        super().__init__()
+        self._trainer, self._loaded = trainer, False
+
+    def _load(self):
+        if not self._loaded:
+            self._loaded = True
+            super().update(self._trainer.read_logs())
+
+    def __getitem__(self, k):
+        self._load()
+        return super().__getitem__(k)
+
+    def items(self):
+        self._load()
+        return super().items()
+
+    def keys(self):
+        self._load()
+        return super().keys()
+
+    def __repr__(self):
+        self._load()
+        return super().__repr__()

@@ -1,0 +1,289 @@
+"""The reference's encoder-decoder Transformer for the speech-translation task (pasero/models/transformer.py),
+re-built on the sm_100a kernels. Same constructor contract `(cfg, dist_cfg, task)`, same
+`forward(**batch) -> (loss, logs)`, `encoder(...)` / `decoder(...)` / `compute_loss(...)` entry points and
+state_dict keys, so it drops in behind the reference's model registry for this path.
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import modules, ops
+from .config import DistributedConfig, TransformerConfig
+from .modules import len_to_mask
+
+BF16 = torch.bfloat16
+
+
+def defined(*args):
+    return next((x for x in args if x is not None), None)
+
+
+class TransformerEncoderLayer(nn.Module):
+    """pasero/models/transformer.py:913-1099"""
+
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int):
+        super().__init__()
+        self.cfg, self.layer_id = cfg, layer_id
+        self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.encoder_attention_heads, dropout=cfg.attention_dropout,
+                                                    scaled=cfg.scale_attn)
+        self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
+        self.fc1 = modules.Linear(cfg.embed_dim, cfg.encoder_ffn_dim)
+        self.fc2 = modules.Linear(cfg.encoder_ffn_dim, cfg.embed_dim)
+        self.final_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
+        self.prenorm = cfg.encoder_prenorm
+        self.dropout_p = cfg.dropout
+        self.name = f'enc_{layer_id}'
+
+    def forward(self, x: Tensor, padding_mask: Optional[Tensor], /, return_layers=(), key_lengths: Optional[Tensor] = None):
+        p = self.dropout_p if self.training else 0.0
+        eps = self.cfg.norm_eps
+        ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        residual = x
+        if self.prenorm:
+            x = ops.dropout_add_ln(x, None, ln1.weight, ln1.bias, 0.0, eps)
+        x, _ = self.self_attn(x, x, x, attn_mask=padding_mask, key_lengths=key_lengths)
+        if self.prenorm:
+            x = ops.dropout_add_ln(x, residual, None, None, p, eps)
+        else:
+            x = ops.dropout_add_ln(x, residual, ln1.weight, ln1.bias, p, eps)
+        residual = x
+        if self.prenorm:
+            x = ops.dropout_add_ln(x, None, ln2.weight, ln2.bias, 0.0, eps)
+        x = ops.ffn(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+        if self.prenorm:
+            x = ops.dropout_add_ln(x, residual, None, None, p, eps)
+        else:
+            x = ops.dropout_add_ln(x, residual, ln2.weight, ln2.bias, p, eps)
+        return x, ({self.name: x} if self.name in return_layers else {})
+
+
+class TransformerDecoderLayer(nn.Module):
+    """pasero/models/transformer.py:1102-1417"""
+
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int):
+        super().__init__()
+        self.cfg, self.layer_id = cfg, layer_id
+        self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.decoder_attention_heads, dropout=cfg.attention_dropout,
+                                                    causal=True, scaled=cfg.scale_attn)
+        self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
+        self.encoder_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.decoder_attention_heads,
+                                                       dropout=cfg.attention_dropout, scaled=cfg.scale_attn)
+        self.encoder_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
+        self.fc1 = modules.Linear(cfg.embed_dim, cfg.decoder_ffn_dim)
+        self.fc2 = modules.Linear(cfg.decoder_ffn_dim, cfg.embed_dim)
+        self.final_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
+        self.prenorm = cfg.decoder_prenorm
+        self.dropout_p = defined(cfg.decoder_dropout, cfg.dropout)
+        self.name = f'dec_{layer_id}'
+
+    def _block(self, x, ln, fn, p, eps):
+        residual = x
+        if self.prenorm:
+            x = ops.dropout_add_ln(x, None, ln.weight, ln.bias, 0.0, eps)
+        x = fn(x)
+        if self.prenorm:
+            return ops.dropout_add_ln(x, residual, None, None, p, eps)
+        return ops.dropout_add_ln(x, residual, ln.weight, ln.bias, p, eps)
+
+    def forward(self, x: Tensor, encoder_out: Tensor, encoder_mask: Optional[Tensor], padding_mask: Optional[Tensor], /,
+                return_layers=(), state=None, encoder_lengths: Optional[Tensor] = None, **kwargs):
+        if state is not None:
+            raise NotImplementedError('incremental decoding is outside the training path')
+        p = self.dropout_p if self.training else 0.0
+        eps = self.cfg.norm_eps
+        x = self._block(x, self.self_attn_layer_norm, lambda h: self.self_attn(h, h, h)[0], p, eps)
+        x = self._block(x, self.encoder_attn_layer_norm,
+                        lambda h: self.encoder_attn(h, encoder_out, encoder_out, attn_mask=encoder_mask,
+                                                    key_lengths=encoder_lengths)[0], p, eps)
+        x = self._block(x, self.final_layer_norm,
+                        lambda h: ops.ffn(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias), p, eps)
+        return x, ({self.name: x} if self.name in return_layers else {})
+
+
+class TransformerEncoder(nn.Module):
+    """pasero/models/transformer.py:610-765 (speech features: conv subsampler + sinusoidal positions)."""
+
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task=None, embed=None):
+        super().__init__()
+        self.cfg = cfg
+        self.embed_tokens = None  # SpeechTranslationTask.encoder_num_embeddings == 0 (speech_translation.py:29-31)
+        input_dim = cfg.input_dim or cfg.embed_dim
+        if not cfg.conv_kernel_sizes:
+            raise NotImplementedError('the ST path expects a conv subsampler (conv_kernel_sizes)')
+        conv_input_dim = cfg.conv_input_dim or input_dim
+        if conv_input_dim != input_dim:
+            raise NotImplementedError('in_linear (input_dim != conv_input_dim) is a "next" row of SURVEY.md §8f')
+        self.subsample = modules.ConvolutionSubsampler(conv_input_dim, cfg.conv_channels or conv_input_dim, cfg.embed_dim,
+                                                       cfg.conv_kernel_sizes, cfg.conv_strides, cfg.conv_activation)
+        encoder_max_len = int(self.subsample.get_new_length(torch.tensor(cfg.encoder_max_len)))
+        self.embed_positions = modules.SinusoidalPositionalEmbedding(encoder_max_len, cfg.embed_dim,
+                                                                     shift=cfg.positional_encoding_shift)
+        self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
+        self.dropout_p = defined(cfg.embed_dropout, cfg.dropout)
+        self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, dist_cfg, i) for i in range(cfg.encoder_layers)])
+        self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.encoder_prenorm else None
+
+    def forward(self, encoder_input: Tensor, encoder_input_length: Tensor, return_layers=(), meta: dict = {},
+                padded_layout: Optional[tuple] = None, **kwargs):
+        """encoder_input (B, S, 80) bf16 features (or, with padded_layout=(frames,), the zero-padded layout written
+        by the fbank kernel). Returns (encoder_out (B, S', D), padding_mask (B, S') bool True = pad, layer_outputs)."""
+        return_layers = return_layers or ()
+        if encoder_input.ndim != 3:
+            raise NotImplementedError('text encoder inputs are outside the ST path')
+        x = encoder_input
+        if x.dtype != BF16:
+            x = x.to(BF16)
+        if padded_layout is not None:
+            x, length = self.subsample.forward_padded(x, padded_layout[0], encoder_input_length)
+        else:
+            x, length = self.subsample(x, encoder_input_length)
+        B = encoder_input.shape[0]
+        D = self.cfg.embed_dim
+        S = x.numel() // (B * D)
+        p = self.dropout_p if self.training else 0.0
+        pos = self.embed_positions.table(S)
+        x = ops.EmbedFn.apply(x.reshape(B * S, D), None, pos, float(self.embed_scale), float(p), S, -1).view(B, S, D)
+        padding_mask = len_to_mask(length, size=S)
+        key_lengths = length.clamp(max=S).to(torch.int32)
+        layer_outputs = {}
+        for layer in self.layers:
+            x, out = layer(x, padding_mask, return_layers=return_layers, key_lengths=key_lengths)
+            layer_outputs.update(out)
+        if self.layer_norm is not None:
+            x = ops.dropout_add_ln(x, None, self.layer_norm.weight, self.layer_norm.bias, 0.0, self.cfg.norm_eps)
+        self._last_lengths = key_lengths
+        return x, padding_mask, layer_outputs
+
+
+class TransformerDecoder(nn.Module):
+    """pasero/models/transformer.py:767-910"""
+
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task=None, embed=None):
+        super().__init__()
+        self.cfg = cfg
+        self.padding_idx = task.padding_idx
+        self.embed_tokens = embed if embed is not None else modules.Embedding(task.decoder_num_embeddings, cfg.embed_dim,
+                                                                              self.padding_idx)
+        self.embed_positions = modules.SinusoidalPositionalEmbedding(cfg.decoder_max_len, cfg.embed_dim,
+                                                                     shift=cfg.positional_encoding_shift)
+        self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
+        self.dropout_p = defined(cfg.embed_dropout, cfg.decoder_dropout, cfg.dropout)
+        self.layers = nn.ModuleList([TransformerDecoderLayer(cfg, dist_cfg, i) for i in range(cfg.decoder_layers)])
+        self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.decoder_prenorm else None
+        self.output_projection = None  # tied (cfg.tied_output_projection)
+
+    def features(self, encoder_out, encoder_mask, decoder_input, return_layers=(), encoder_lengths=None):
+        B, T = decoder_input.shape
+        D = self.cfg.embed_dim
+        p = self.dropout_p if self.training else 0.0
+        pos = self.embed_positions.table(T)
+        x = ops.EmbedFn.apply(self.embed_tokens.weight, decoder_input, pos, float(self.embed_scale), float(p), T,
+                              self.padding_idx).view(B, T, D)
+        layer_outputs = {}
+        for layer in self.layers:
+            x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths)
+            layer_outputs.update(out)
+        if self.layer_norm is not None:
+            x = ops.dropout_add_ln(x, None, self.layer_norm.weight, self.layer_norm.bias, 0.0, self.cfg.norm_eps)
+        return x, layer_outputs
+
+    def forward(self, encoder_out: Tensor, encoder_mask: Tensor, decoder_input: Tensor, prompt_mask=None, state=None,
+                return_layers=(), meta: dict = {}, encoder_lengths=None, **kwargs):
+        """Returns (logits (B, T, V), layer_outputs)"""
+        if state is not None:
+            raise NotImplementedError('incremental decoding is outside the training path')
+        x, layer_outputs = self.features(encoder_out, encoder_mask, decoder_input, return_layers or (), encoder_lengths)
+        return self.embed_tokens.projection(x), layer_outputs
+
+
+class Transformer(nn.Module):
+    """pasero/models/transformer.py:106-608 (`register_model('transformer')`), ST path."""
+
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task):
+        super().__init__()
+        self.cfg, self.dist_cfg, self.task = cfg, dist_cfg, task
+        self.find_unused_parameters = False
+        self.batch_by = None
+        self.encoder = self.build_encoder()
+        self.decoder = self.build_decoder(embed=None)
+        self.defer_logs = False   # True: logs hold device scalars (no host sync inside forward)
+        self._stats = None
+
+    shard_count, shard_id, is_sharded = 1, 0, False
+
+    @property
+    def padding_idx(self) -> int:
+        return self.task.padding_idx
+
+    @property
+    def total_param_count(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    def build_encoder(self, embed=None):
+        return TransformerEncoder(self.cfg, self.dist_cfg, task=self.task, embed=embed)
+
+    def build_decoder(self, embed=None):
+        return TransformerDecoder(self.cfg, self.dist_cfg, task=self.task, embed=embed)
+
+    def set_ddp_params_and_buffers_to_ignore(self) -> None:
+        pass
+
+    def stats_buffer(self, device) -> Tensor:
+        """fp64[8] device accumulator shared with the optimizer kernels: loss, nll, num_tokens, num_lines, gnorm^2."""
+        if self._stats is None or self._stats.device != device:
+            self._stats = torch.zeros(8, dtype=torch.float64, device=device)
+        return self._stats
+
+    def forward(self, encoder_input: Tensor = None, encoder_input_length: Tensor = None, decoder_input: Tensor = None,
+                prompt_mask: Optional[Tensor] = None, **kwargs):
+        """Returns (loss, logs) like the reference (transformer.py:227-283): summed label-smoothed CE and
+        {'loss', 'nll_loss'} in bits, 'num_tokens', 'num_lines'."""
+        target = decoder_input[:, 1:]
+        dec_in = decoder_input[:, :-1]
+        enc_kwargs = {k: v for k, v in kwargs.items() if k in ('return_layers', 'meta', 'padded_layout')}
+        encoder_out, encoder_mask, _ = self.encoder(encoder_input, encoder_input_length, **enc_kwargs)
+        x, _ = self.decoder.features(encoder_out, encoder_mask, dec_in, (), self.encoder._last_lengths)
+        return self.compute_loss(x, target, {}, fused=True)
+
+    def compute_loss(self, logits_or_features: Tensor, target: Tensor, layer_outputs: dict, *args, fused: bool = False, **kwargs):
+        """With fused=True the first argument holds decoder features (B, T, D) and the tied projection runs inside
+        the loss op; otherwise it holds logits (B, T, V) as in the reference (transformer.py:323-380)."""
+        B, T = target.shape
+        dev = target.device
+        stats = self.stats_buffer(dev)
+        before = stats[:3].clone()
+        eps = float(self.cfg.label_smoothing or 0.0)
+        if fused:
+            x = logits_or_features.reshape(B * T, -1)
+            loss = ops.ProjCEFn.apply(x, self.decoder.embed_tokens.weight, target, self.padding_idx, eps, stats)
+        else:
+            loss = LogitsCEFn.apply(logits_or_features.reshape(B * T, -1), target, self.padding_idx, eps, stats)
+        delta = stats[:3] - before
+        stats[3] += B
+        if self.defer_logs:
+            logs = {'loss': delta[0] / math.log(2), 'nll_loss': delta[1] / math.log(2), 'num_tokens': delta[2], 'num_lines': B}
+        else:
+            d = delta.tolist()
+            logs = {'loss': d[0] / math.log(2), 'nll_loss': d[1] / math.log(2), 'num_tokens': int(d[2]), 'num_lines': B}
+        return loss, logs
+
+
+class LogitsCEFn(torch.autograd.Function):
+    """Label-smoothed CE on materialised logits (reference-style compute_loss entry point)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, padding_idx, label_smoothing, stats):
+        from . import kernels as K
+        grad = logits.detach().clone().contiguous()
+        before = stats[0].clone()
+        K.ls_ce_fwd_bwd(grad, target, padding_idx, label_smoothing, stats, write_grad=True)
+        ctx.save_for_backward(grad)
+        return (stats[0] - before).float()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss.to(grad.dtype), None, None, None, None

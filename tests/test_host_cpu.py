@@ -1,0 +1,163 @@
+"""CPU-side checks of the host layer: batch contract bit-exact against the reference's golden vectors, config
+surface, state_dict key layout, and that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from pasero_b200 import TrainingConfig, build_model
+from pasero_b200.task import Dictionary, NumpyFile, SpeechTranslationTask, build_batches
+from pasero_b200.modules import len_to_mask, mask_to_len
+from tests.golden import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def tiny_training_cfg(**kw) -> TrainingConfig:
+    t = synth.TINY
+    opts = dict(encoder_layers=t['encoder_layers'], decoder_layers=t['decoder_layers'], embed_dim=t['embed_dim'],
+                encoder_ffn_dim=t['ffn_dim'], decoder_ffn_dim=t['ffn_dim'], encoder_attention_heads=t['heads'],
+                decoder_attention_heads=t['heads'], input_dim=80, conv_input_dim=80, conv_channels=t['conv_channels'],
+                conv_kernel_sizes=[5, 5], encoder_max_len=3000, batch_size=64000, dropout=0.0, label_smoothing=0.1,
+                dtype='bfloat16', lr=synth.TRAIN['lr'], warmup=synth.TRAIN['warmup'], max_steps=1000)
+    opts.update(kw)
+    return TrainingConfig.from_dict(opts)
+
+
+def tiny_task(cfg=None) -> SpeechTranslationTask:
+    cfg = cfg or tiny_training_cfg()
+    d = Dictionary(tokens=[f'tok{i}' for i in range(synth.TINY['vocab_size'] - 4)])
+    return SpeechTranslationTask(cfg, d)
+
+
+def test_library_exports_every_declared_symbol():
+    from pasero_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'pasero_b200.h')).read()
+    declared = set(re.findall(r'\b(pb200_\w+)\s*\(', header))
+    declared.discard('pb200_gemm_params')
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pb200_abi_version() == 1
+    assert lib.pb200_fbank_num_frames(160000) == 998 and lib.pb200_fbank_num_frames(399) == 0
+
+
+def test_no_cpu_fallback():
+    """Compute entry points must fail loudly without a GPU rather than fall back."""
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from pasero_b200 import frontend
+    with pytest.raises(RuntimeError):
+        frontend.fbank_batch(torch.zeros(1, 16000))
+    from pasero_b200.training import Trainer
+    cfg = tiny_training_cfg()
+    with pytest.raises(RuntimeError):
+        Trainer(cfg, tiny_task(cfg), build_model(cfg, tiny_task(cfg)))
+
+
+def test_dictionary_ids():
+    d = Dictionary(os.path.join(GOLD, '..', '..', 'tests', 'golden', 'dict_small.txt')) if False else \
+        Dictionary(tokens=['a', 'b', 'c'])
+    assert (d.padding_idx, d.eos_idx, d.unk_idx, d.bos_idx, d.sep_idx) == (1, 2, 3, 2, 0)
+    assert len(d) == 7
+    assert d.to_indices(['a', 'zzz', 'c'], append_eos=True, prepend_bos=True).tolist() == [2, 4, 3, 6, 2]
+    assert d.to_indices(['a', 'b', 'c'], max_len=3, append_eos=True, prepend_bos=True).tolist() == [2, 4, 2]
+
+
+def test_build_batches_docstring_vectors():
+    sizes = [1000, 2000, 4000, 500, 1000, 1000]
+    assert build_batches([0, 1, 2, 3, 4, 5], sizes.__getitem__, 4000, 1, 2) == [[0, 1], [2], [3, 4], [5]]
+    assert mask_to_len(torch.tensor([[0, 1, 0, 1, 0], [1, 1, 0, 0, 0]]).bool()).tolist() == [4, 2]
+    assert len_to_mask(torch.tensor([0, 3, 1])).long().tolist() == [[1, 1, 1], [0, 0, 0], [0, 1, 1]]
+
+
+@pytest.mark.parametrize('bs', [4000, 40000])
+@pytest.mark.parametrize('mult', [None, 8])
+@pytest.mark.parametrize('lines', [None, 50])
+def test_bucketing_bit_exact_with_reference(bs, mult, lines):
+    g = np.load(os.path.join(GOLD, 'batching.npz'))
+    cfg = tiny_training_cfg(batch_size_multiple=mult, lines_per_batch=lines)
+    task = tiny_task(cfg)
+    np.random.seed(synth.BATCHING_SEED)
+    batches = task.buffered_batching(list(synth.batching_samples()), batch_size=bs)
+    key = f'bs{bs}_m{mult or 0}_l{lines or 0}'
+    assert np.array_equal(np.array([s['index'] for b in batches for s in b]), g[key + '_flat'])
+    assert np.array_equal(np.array([len(b) for b in batches]), g[key + '_sizes'])
+
+
+def test_collate_bit_exact_with_reference():
+    g = np.load(os.path.join(GOLD, 'batching.npz'))
+    task = tiny_task()
+    np.random.seed(synth.BATCHING_SEED)
+    small = task.build_batches(list(synth.batching_samples()[:64]), shuffle=True, batch_size=4000)[3]
+    col = task.collate(small, padding_idx=task.padding_idx, dtype=torch.float32)
+    for k in ('decoder_input', 'prompt_mask', 'prompt_length', 'indices', 'encoder_input_length'):
+        assert np.array_equal(col[k].numpy(), g['collate_' + k]), k
+    assert np.array_equal(col['encoder_input'].double().sum(dim=(1, 2)).numpy(), g['collate_encoder_input_sum'])
+    assert task.collate([], 1, torch.float32) is None
+
+
+def test_preprocess_and_skip():
+    cfg = tiny_training_cfg(max_source_len=100, max_target_len=6)
+    task = tiny_task(cfg)
+    feats = np.zeros((50, 80), dtype=np.float16)
+    s = task.preprocess({'source': feats, 'target': 'tok1 tok2 nope', 'meta': {}}, append_eos=True)
+    assert s['decoder_input'].tolist() == [2, 5, 6, 3, 2] and s['prompt_mask'].tolist() == [True, False, False, False, False]
+    assert task.preprocess({'source': np.zeros((101, 80), np.float16), 'target': 'tok1', 'meta': {}}, append_eos=True) == {}
+    assert task.preprocess({'source': feats, 'target': 'tok1 ' * 6, 'meta': {}}, append_eos=True) == {}
+    t = task.preprocess({'source': np.zeros((300, 80), np.float16), 'target': 'tok1 ' * 9, 'meta': {}}, truncate=True, append_eos=True)
+    assert len(t['encoder_input']) == 100 and len(t['decoder_input']) == 6 and t['decoder_input'][-1] == 2
+
+
+def test_numpy_file_roundtrip(tmp_path):
+    rng = np.random.RandomState(0)
+    feats = [rng.randn(n, 80).astype(np.float32) for n in (5, 17, 1)]
+    f = NumpyFile.build(str(tmp_path / 'train.npy'), feats, dtype='float16')
+    assert len(f) == 3 and f.get_positions()[1].tolist() == [5, 17, 1]
+    for got, want in zip(f, feats):
+        assert got.dtype == np.float16 and np.array_equal(got, want.astype(np.float16))
+    f.seek(1)
+    assert next(f).shape == (17, 80)
+
+
+def test_state_dict_keys_match_reference():
+    import json
+    gold = torch.load(os.path.join(GOLD, 'st_tiny_model.pt'), weights_only=False)
+    cfg = tiny_training_cfg()
+    model = build_model(cfg, tiny_task(cfg))
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == gold['state_dict_keys']
+    shapes = synth.tiny_param_shapes()
+    for k, shape in shapes.items():
+        assert tuple(sd[k].shape) == shape, k
+    # loading a reference-format state dict fills the fused / tap-major storage
+    ref_sd = synth.tiny_state_dict()
+    missing = model.load_state_dict(ref_sd, strict=False)
+    assert not missing.unexpected_keys
+    sd2 = model.state_dict()
+    for k, v in ref_sd.items():
+        assert torch.equal(sd2[k].float(), v), k
+    attn = model.encoder.layers[0].self_attn
+    D = cfg.model_cfg.embed_dim
+    assert torch.equal(attn.in_proj_weight[2 * D:].detach(), ref_sd['encoder.layers.0.self_attn.q_proj.weight'])
+    layout = json.load(open(os.path.join(GOLD, 'checkpoint_layout.json')))
+    assert sorted(layout['model_3.bin']['model']) == sorted(sd.keys())
+
+
+def test_config_surface():
+    cfg = TrainingConfig.from_dict({'task': 'speech_translation', 'arch': 'transformer', 'encoder_layers': 12,
+                                    'input_dim': 80, 'conv_input_dim': 80, 'conv_channels': 1024, 'conv_kernel_sizes': [5, 5],
+                                    'encoder_max_len': 3000, 'dtype': 'bfloat16', 'batch_size': 64000, 'dict': 'de-en/dict.txt',
+                                    'source_lang': 'de', 'metrics': [], 'max_steps': 200, 'valid_interval': 100})
+    m = cfg.model_cfg
+    assert (m.encoder_layers, m.decoder_layers, m.embed_dim, m.label_smoothing, m.decoder_max_len) == (12, 6, 512, 0.1, 256)
+    assert m.conv_strides == (2, 2) and cfg.extra['dict'] == 'de-en/dict.txt' and cfg.max_source_len == 3000
+    with pytest.raises(NotImplementedError):
+        TrainingConfig.from_dict({'dtype': 'bfloat16', 'fsdp': True})
+    with pytest.raises(NotImplementedError):
+        TrainingConfig.from_dict({'dtype': 'float16'})
+    assert cfg.as_dict()['encoder_layers'] == 12
