@@ -373,6 +373,14 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
                      long long batch, long long batch_stride, int box_cols, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     PB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    // The driver-level encode needs a context current on THIS thread. PyTorch's autograd worker threads skip
+    // cudaSetDevice when the target is device 0 (the runtime default), so nothing has bound the primary context
+    // yet when backward's first op is a GEMM; a runtime call binds it (once per thread).
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        PB_CUDA(cudaFree(nullptr));
+        ctx_bound = true;
+    }
     PB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm operand pointer must be 16-byte aligned");
     PB_CHECK(ld % 8 == 0, "gemm operand leading dimension (%lld) must be a multiple of 8 elements", ld);
     PB_CHECK(batch <= 1 || batch_stride % 8 == 0, "gemm operand batch stride (%lld) must be a multiple of 8", batch_stride);
