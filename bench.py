@@ -1,0 +1,334 @@
+"""Headline benchmark: target tokens/s of the speech-translation training step (BASELINE.json config 2:
+IWSLT2023-style ST, 80-bin log-mel fbank + conv subsampler + 12/6-layer Transformer, synthetic 16 kHz audio).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                      (the reference's algorithm on the host CPU cores)
+
+A step = one pass of the hot path over one batch: PCM -> fused fbank+CMVN -> conv subsampler -> 12-layer encoder ->
+6-layer decoder -> tied projection + label-smoothed CE -> backward -> (gradient allreduce) -> clip + Adam.
+Per GPU: B = 64 utterances of 10 s (160 000 samples, 998 frames -> 250 encoder positions), 49-token decoder inputs
+(48 targets) => 3 072 target tokens per GPU per step; weak scaling over GPUs.
+Prints ONE JSON line (see the task contract for the keys).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_PER_GPU, N_SAMPLES, T_DEC, VOCAB = 64, 160000, 49, 8032
+METRIC = 'target tokens/sec/box (ST train step: fbank + 12/6 Transformer, fwd+bwd+Adam)'
+
+
+def st_config(**kw):
+    from pasero_b200 import TrainingConfig
+    opts = dict(task='speech_translation', arch='transformer', encoder_layers=12, decoder_layers=6, input_dim=80,
+                conv_input_dim=80, conv_channels=1024, conv_kernel_sizes=[5, 5], encoder_max_len=3000, dtype='bfloat16',
+                batch_size=64000, label_smoothing=0.1, dropout=0.1, lr=0.0005, warmup=4000, max_steps=100000, seed=1234)
+    opts.update(kw)
+    return TrainingConfig.from_dict(opts)
+
+
+def synthetic_batch(rank: int, batch: int):
+    rng = np.random.RandomState(1234 + rank)
+    pcm = (rng.rand(batch, N_SAMPLES).astype(np.float32) - 0.5)
+    dec = rng.randint(4, VOCAB, size=(batch, T_DEC)).astype(np.int64)
+    dec[:, 0] = 2
+    dec[:, -1] = 2
+    return torch.from_numpy(pcm), torch.from_numpy(dec)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def oracle_step_factory(batch: int, threads: int):
+    """The reference's algorithm (oracle port: numpy fbank+CMVN, torch-CPU fp32 model, Adam) on the host cores."""
+    from oracle import fbank as of
+    from oracle import model as om
+    from oracle import optim as oo
+    torch.set_num_threads(threads)
+    cfg = om.STConfig(encoder_layers=12, decoder_layers=6, vocab_size=VOCAB)
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    d, f, c = cfg.embed_dim, cfg.encoder_ffn_dim, cfg.conv_channels
+
+    def w(*shape):
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+        return (torch.randn(*shape, generator=g) * fan_in ** -0.5).requires_grad_(True)
+    sd['encoder.subsample.conv_layers.0.weight'], sd['encoder.subsample.conv_layers.0.bias'] = w(c, 80, 5), w(c)
+    sd['encoder.subsample.conv_layers.1.weight'], sd['encoder.subsample.conv_layers.1.bias'] = w(2 * d, c // 2, 5), w(2 * d)
+
+    def block(p, cross):
+        names = ['self_attn'] + (['encoder_attn'] if cross else [])
+        for a in names:
+            for proj in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+                sd[f'{p}.{a}.{proj}.weight'], sd[f'{p}.{a}.{proj}.bias'] = w(d, d), w(d)
+            sd[f'{p}.{a}_layer_norm.weight'] = torch.ones(d, requires_grad=True)
+            sd[f'{p}.{a}_layer_norm.bias'] = torch.zeros(d, requires_grad=True)
+        sd[f'{p}.fc1.weight'], sd[f'{p}.fc1.bias'], sd[f'{p}.fc2.weight'], sd[f'{p}.fc2.bias'] = w(f, d), w(f), w(d, f), w(d)
+        sd[f'{p}.final_layer_norm.weight'] = torch.ones(d, requires_grad=True)
+        sd[f'{p}.final_layer_norm.bias'] = torch.zeros(d, requires_grad=True)
+    for i in range(cfg.encoder_layers):
+        block(f'encoder.layers.{i}', False)
+    sd['decoder.embed_tokens.weight'] = w(VOCAB, d)
+    for i in range(cfg.decoder_layers):
+        block(f'decoder.layers.{i}', True)
+    pcm, dec = synthetic_batch(0, batch)
+    state, hp = {}, dict(lr=0.0005, warmup=4000, max_steps=100000, clip_norm=1.0)
+    counter = [0]
+
+    def step():
+        feats = np.stack([of.fbank_cmvn(pcm[b].numpy(), cmvn=True) for b in range(batch)])
+        b = {'encoder_input': torch.from_numpy(feats), 'encoder_input_length': torch.full((batch,), feats.shape[1]),
+             'decoder_input': dec}
+        logs = oo.train_step(cfg, sd, [b], state, counter[0], hp, om.forward)
+        counter[0] += 1
+        return logs['num_tokens']
+    return step
+
+
+def time_oracle(batch: int, steps: int, warmup: int, threads: int):
+    step = oracle_step_factory(batch, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    tokens = 0
+    for _ in range(steps):
+        tokens += step()
+    dt = time.perf_counter() - t0
+    return tokens / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 4
+    value, ms = time_oracle(batch, max(1, args.steps), max(0, args.warmup), threads)
+    sample = f'{batch} utterances x 10 s (of the {B_PER_GPU}-utterance step), {args.steps} steps after {args.warmup} warm-up'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': 0, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {'workload': 'BASELINE configs[1]: IWSLT2023-style ST, 80-bin fbank + conv subsampler (k=5,5) + 12/6-layer '
+                        'Transformer d=512 ffn=2048 h=8, V=8032, dropout 0.1, label smoothing 0.1',
+            'utterances_per_gpu': B_PER_GPU, 'samples_per_utterance': N_SAMPLES, 'frames': 998, 'encoder_len': 250,
+            'target_len': T_DEC - 1, 'global_batch_utterances': B_PER_GPU * max(1, n_gpus),
+            'parallelism': f'dp{max(1, n_gpus)}', 'l2_policy': 'per-step working set (>1 GB of activations) exceeds the 126 MB L2'}
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from pasero_b200 import build_model, frontend
+    from pasero_b200 import kernels as K
+    from pasero_b200.task import Dictionary, SpeechTranslationTask
+    from pasero_b200.training import Trainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == max(1, args.gpus), f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    W = max(3, args.warmup)
+
+    cfg = st_config()
+    task = SpeechTranslationTask(cfg, Dictionary(tokens=[f't{i}' for i in range(VOCAB - 4)]))
+    torch.manual_seed(1234)
+    model = build_model(cfg, task)
+    trainer = Trainer(cfg, task, model)
+    sub = model.encoder.subsample
+
+    pcm_host, dec_host = synthetic_batch(rank, B_PER_GPU)
+    pcm_host, dec_host = pcm_host.pin_memory(), dec_host.pin_memory()
+    plan = frontend.FbankPlan([N_SAMPLES] * B_PER_GPU, dev)
+    F = plan.max_frames
+    rows, front = sub.padded_rows(F, 0)
+    tokens_per_step = B_PER_GPU * (T_DEC - 1) * world
+    pcm_dev = pcm_host.to(dev).reshape(-1).contiguous()
+    dec_dev = dec_host.to(dev)
+    use_graph = not args.no_graph
+
+    def step(pcm_flat, dec):
+        _, padded = frontend.fbank(pcm_flat, plan, cmvn=True, padded_frames=rows, front_pad=front)
+        batch = {'encoder_input': padded, 'encoder_input_length': plan.frames_tensor, 'decoder_input': dec,
+                 'padded_layout': (F,), 'meta': {}}
+        if use_graph:
+            return trainer.train_step_graphed(batch)
+        return trainer.train_step(iter([batch]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`) ----
+    for _ in range(W):
+        logs = step(pcm_dev, dec_dev)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        logs = step(pcm_dev, dec_dev)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clock_info = clocks.stop() if clocks else None
+    last = dict(logs.items())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    value = tokens_per_step / (ms_per_step / 1e3)
+
+    # ---- end-to-end through the public API with host buffers (`e2e`) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss_sink = 0.0
+    for _ in range(args.steps):
+        pcm_d = pcm_host.to(dev, non_blocking=True).reshape(-1)
+        dec_d = dec_host.to(dev, non_blocking=True)
+        lg = step(pcm_d, dec_d)
+        loss_sink += lg['loss']          # device -> host read of the step's result (syncs on this step)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = tokens_per_step / (t.item() / args.steps / 1e3)
+    h2d = pcm_host.numel() * 4 + dec_host.numel() * 8
+    d2h = 8 * 8
+
+    # ---- dominant kernel roofline: the tcgen05 GEMM, all launches of one step timed with CUDA events ----
+    roofline, gemm_share, launches = None, None, None
+    if rank == 0:
+        roofline, gemm_share, launches = gemm_roofline(trainer, frontend, plan, rows, front, F, pcm_dev, dec_dev, ms_per_step)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, cms = time_oracle(4, 5, 1, threads)
+        cpu = {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
+               'sample': '5 steps over 4 utterances x 10 s (192 target tokens each) after 1 warm-up step; oracle port '
+                         '(numpy fbank+CMVN, torch-CPU fp32 model, Adam)', 'ms_per_step': cms}
+
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic', 'config': workload_config(world),
+            'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': (launches + 2) * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline, 'cpu_baseline': cpu,
+            'gemm_share_of_step': gemm_share, 'cuda_graph': use_graph,
+            'last_step_logs': {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in last.items()},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_roofline(trainer, frontend, plan, rows, front, F, pcm_dev, dec_dev, ms_per_step):
+    """One instrumented eager step: CUDA events around every pb200_gemm_bf16 launch on the launching stream."""
+    from pasero_b200 import kernels as K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('bf16_tflops_sustained')
+    peak_kind = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+    if peak is None:
+        peak, peak_kind = 1400.0, 'fallback (B200_PROFILING.md, sustained)'
+    K.PROFILE = []
+    _, padded = frontend.fbank(pcm_dev, plan, cmvn=True, padded_frames=rows, front_pad=front)
+    batch = {'encoder_input': padded, 'encoder_input_length': plan.frames_tensor, 'decoder_input': dec_dev,
+             'padded_layout': (F,), 'meta': {}}
+    K.COUNT = {'launches': 0}
+    trainer.train_step(iter([batch]))
+    torch.cuda.synchronize()
+    prof, K.PROFILE = K.PROFILE, None
+    launches = K.COUNT['launches']
+    K.COUNT = None
+    flops = sum(f for f, _, _ in prof)
+    ms = sum(s.elapsed_time(e) for _, s, e in prof)
+    achieved = flops / (ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': 'pb200::gemm_kernel (tcgen05, all instantiations of one step)',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'launches_timed': len(prof), 'gemm_ms_per_step': ms, 'algorithmic_gflop_per_step': flops / 1e9,
+                'peak_source': peak_kind}
+    return roofline, ms / ms_per_step, launches
+
+
+if __name__ == '__main__':
+    main()

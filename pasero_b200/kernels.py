@@ -17,6 +17,16 @@ BF16 = torch.bfloat16
 # replays draw fresh masks. None -> offsets are used as given.
 RNG_OFFSET_BASE: Optional[Tensor] = None
 
+# Instrumentation used by bench.py: PROFILE (list) receives (flops, start_event, end_event) per GEMM launch; COUNT
+# ({'launches': n}) counts kernel launches issued through this module. Both None in normal operation.
+PROFILE = None
+COUNT = None
+
+
+def _count(n: int) -> None:
+    if COUNT is not None:
+        COUNT['launches'] += n
+
 
 def _ws(nbytes: int, device) -> Optional[Tensor]:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device) if nbytes > 0 else None
@@ -52,6 +62,14 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     if ws is None:
         p.split_k = 1
     p.workspace, p.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
+    _count(1 if ws is None else 2)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.pb200_gemm_bf16(byref(p), stream_ptr()))
+        e1.record()
+        PROFILE.append((2.0 * m * n * k * (batch if batch > 0 else 1), e0, e1))
+        return c
     check(lib.pb200_gemm_bf16(byref(p), stream_ptr()))
     return c
 
@@ -99,6 +117,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: 
     p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
     p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     p.B, p.H, p.Lq, p.Lk, p.head_dim, p.causal, p.scale = B, H, Lq, Lk, 64, int(causal), scale
+    _count(1)
     check(lib.pb200_attention_fwd(byref(p), stream_ptr()))
     return o, lse
 
@@ -114,6 +133,7 @@ def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse:
     p.dout, p.lddo, p.delta = dout.data_ptr(), dout.stride(0), delta.data_ptr()
     p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     p.lddq, p.lddk, p.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    _count(3)
     check(lib.pb200_attention_bwd(byref(p), stream_ptr()))
     return dq, dk, dv
 
@@ -132,6 +152,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     y = torch.empty(M, D, dtype=BF16, device=dev) if has_ln else None
     mean = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     rstd = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
+    _count(1)
     check(lib.pb200_dropout_add_ln_fwd(x.data_ptr(), ptr(residual), ptr(gamma), ptr(beta), M, D, eps, p, seed, offset,
                                        ptr(RNG_OFFSET_BASE), ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), stream_ptr()))
     if sum_out is None:
@@ -148,6 +169,7 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
     dx = torch.empty(M, D, dtype=BF16, device=dev)
     dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
     ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if gamma is not None else None
+    _count(3)
     check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
                                        p, seed, offset, ptr(RNG_OFFSET_BASE), ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
                                        int(accumulate), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
@@ -159,6 +181,7 @@ def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) ->
     M, N = x.shape
     out = out if out is not None else torch.empty(N, dtype=BF16, device=x.device)
     ws = _ws(lib.pb200_colsum_workspace_bytes(M, N), x.device)
+    _count(2)
     check(lib.pb200_colsum_bf16(x.data_ptr(), M, N, x.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(),
                                 ws.numel(), stream_ptr()))
     return out
@@ -171,6 +194,7 @@ def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int,
               p: float, seed: int, offset: int) -> Tensor:
     lib = _lib.load()
     out = torch.empty(M, D, dtype=BF16, device=src.device)
+    _count(1)
     check(lib.pb200_embed_fwd(ptr(ids), src.data_ptr(), ptr(pos), M, D, L, scale, p, seed, offset,
                               ptr(RNG_OFFSET_BASE), src.shape[0] if ids is not None else 0, out.data_ptr(), stream_ptr()))
     return out
@@ -180,6 +204,7 @@ def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p
               padding_idx: int = -1, dtable: Optional[Tensor] = None) -> Optional[Tensor]:
     lib = _lib.load()
     dx = torch.empty(M, D, dtype=BF16, device=dy.device) if ids is None else None
+    _count(1)
     check(lib.pb200_embed_bwd(dy.data_ptr(), ptr(ids), M, D, scale, p, seed, offset, ptr(RNG_OFFSET_BASE), padding_idx,
                               dtable.shape[0] if dtable is not None else 0, ptr(dx), ptr(dtable), stream_ptr()))
     return dx
@@ -187,29 +212,34 @@ def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p
 
 def glu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
     out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    _count(1)
     check(_lib.load().pb200_glu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
 
 def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
     din = torch.empty(M, 2 * C, dtype=BF16, device=x.device)
+    _count(1)
     check(_lib.load().pb200_glu_bwd(dy.data_ptr(), x.data_ptr(), M, C, din.data_ptr(), stream_ptr()))
     return din
 
 
 def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
     dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
+    _count(1)
     check(_lib.load().pb200_col2im(dcol.data_ptr(), B, Tin, Tout, C, KW, stride, dx.data_ptr(), stream_ptr()))
     return dx
 
 
 def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
     out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    _count(1)
     check(_lib.load().pb200_pad_rows(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
 
 def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
+    _count(1)
     check(_lib.load().pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))
     return out
 
@@ -223,16 +253,19 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
     B, T = target.shape
     assert target.stride(1) == 1 and target.dtype == torch.int64
     V = logits.shape[1]
+    _count(1)
     check(_lib.load().pb200_ls_ce_fwd_bwd(logits.data_ptr(), target.data_ptr(), target.stride(0), B, T, V,
                                           logits.stride(0), padding_idx, label_smoothing, grad_scale, int(write_grad),
                                           stats.data_ptr(), ptr(row_loss), stream_ptr()))
 
 
 def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
+    _count(1)
     check(_lib.load().pb200_grad_sqnorm(grad.data_ptr(), grad.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor) -> None:
+    _count(1)
     check(_lib.load().pb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                       param.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
 
@@ -252,6 +285,7 @@ def fbank_cmvn(pcm: Tensor, sample_offsets: Tensor, frame_offsets: Tensor, batch
     feats = torch.empty(total_frames, 80, dtype=torch.float32, device=dev)
     padded = torch.empty(batch, padded_frames, 80, dtype=BF16, device=dev) if padded_frames > 0 else None
     ws = _ws(lib.pb200_fbank_workspace_bytes(batch), dev)
+    _count(2)
     check(lib.pb200_fbank_cmvn(pcm.data_ptr(), sample_offsets.data_ptr(), frame_offsets.data_ptr(), batch, max_frames,
                                pcm_scale, int(cmvn), feats.data_ptr(), ptr(padded), padded_frames, front_pad,
                                ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))

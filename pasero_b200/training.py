@@ -106,7 +106,8 @@ class GradBuckets:
 
     def __init__(self, arena: ParamArena, bucket_bytes: int, group=None):
         self.arena, self.group = arena, group
-        self.stream = torch.cuda.Stream()
+        self.cuda = arena.grad.is_cuda
+        self.stream = torch.cuda.Stream() if self.cuda else None   # CPU tensors (gloo tests): same logic, no streams
         self.buckets = []           # (start, end) element ranges, in the order they become ready
         self.param_bucket = {}
         n = len(arena.params)
@@ -129,7 +130,7 @@ class GradBuckets:
         for i, b in self.param_bucket.items():
             self.sizes[b] += 1
         self.enabled = True
-        self.handles = []
+        self.launch_order = []
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
@@ -145,14 +146,24 @@ class GradBuckets:
 
     def _launch(self, b: int) -> None:
         lo, hi = self.buckets[b]
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        else:
             dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         self.pending[b] = -1
+        self.launch_order.append(b)
 
     def start_step(self, sync: bool) -> None:
         self.enabled = sync
         self.pending = [0] * len(self.buckets)
+        self.launch_order = []
+
+    def allreduce_all(self, stats: Optional[Tensor] = None) -> None:
+        """Non-overlapped variant used between CUDA-graph segments: every bucket, then the step scalars."""
+        self.pending = [0] * len(self.buckets)
+        self.finish(stats)
 
     def finish(self, stats: Optional[Tensor] = None) -> None:
         """Flush buckets whose hooks never fired (unused parameters), reduce the step scalars, rejoin the stream."""
@@ -160,10 +171,14 @@ class GradBuckets:
             if self.pending[b] != -1:
                 self._launch(b)
         if stats is not None:
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
+            if self.cuda:
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+            else:
                 dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class Trainer:
@@ -279,7 +294,7 @@ class Trainer:
         """Same update as train_step for update_freq == 1, with forward + backward + clip + Adam replayed from a CUDA
         graph keyed on the batch shape. Inputs are copied into static buffers; step scalars are refreshed in device
         memory before the replay; dropout offsets advance through `rng_base`."""
-        assert self.update_freq == 1 and self.buckets is None, 'graph capture covers the single-GPU, update_freq=1 step'
+        assert self.update_freq == 1, 'graph capture covers the update_freq=1 step'
         tensors = {k: v for k, v in batch.items() if torch.is_tensor(v)}
         key = tuple((k, tuple(v.shape)) for k, v in sorted(tensors.items()))
         key = key + tuple(sorted((k, v) for k, v in batch.items() if isinstance(v, (int, tuple))))
@@ -293,15 +308,15 @@ class Trainer:
             K.RNG_OFFSET_BASE = self.rng_base
             ops.DropoutState.offset = 0
             self._write_hyper()
-            snapshot = [self.arena.param.clone(), self.arena.exp_avg.clone(), self.arena.exp_avg_sq.clone()]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
+            if self.buckets is not None:
+                self.buckets.start_step(sync=False)   # the allreduce runs between the two graph segments
             with torch.cuda.stream(side):   # warm-up outside capture (lazy inits, workspace sizes)
                 for k, v in tensors.items():
                     static[k].copy_(v)
                 self._graph_body(static, extras)
             torch.cuda.current_stream().wait_stream(side)
-            self.arena.param.copy_(snapshot[0]); self.arena.exp_avg.copy_(snapshot[1]); self.arena.exp_avg_sq.copy_(snapshot[2])
             graph = torch.cuda.CUDAGraph()
             ops.DropoutState.offset = 0
             with torch.cuda.graph(graph):
@@ -313,6 +328,9 @@ class Trainer:
         self._write_hyper()
         graph.replay()
         self.rng_base += 1
+        if self.buckets is not None:
+            self.buckets.allreduce_all(self.stats)
+        self._optimizer_kernels()
         return self._finish_step()
 
     def _graph_body(self, static: dict, extras: dict) -> None:
@@ -322,7 +340,6 @@ class Trainer:
         batch = dict(static)
         batch.update(extras)
         self._forward_backward(batch)
-        self._optimizer_kernels()
 
     # ------------------------------------------------------------------ checkpoints (reference layout)
     def _named_state(self, flat: Tensor) -> dict:
