@@ -15,6 +15,7 @@
 #include "../../include/pasero_b200.h"
 
 #include <mutex>
+#include <string.h>
 
 namespace pb200 {
 
@@ -39,6 +40,7 @@ struct GemmDev {
     const bf16* residual;
     const bf16* relu_mask;
     int act, out_fp32, accumulate;
+    int tma_store;       // bf16 output staged through shared memory and written with TMA
     float alpha;
     float* partial;      // split-K partials [split][Z][M][N] fp32
 };
@@ -50,19 +52,23 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_BUF_BYTES = 32 * 128;                 // 32 rows x 64 bf16, SWIZZLE_128B
+    static constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
+            const __grid_constant__ CUtensorMap tmc, const GemmDev p) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -74,6 +80,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tma);
         ptx::prefetch_tmap(&tmb);
+        if (p.tma_store) ptx::prefetch_tmap(&tmc);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -199,6 +206,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 
+            if (p.tma_store) {
+                // bf16 output: 64-column slabs -> swizzled smem (this warp's 32 rows) -> TMA store. The TMA clips
+                // rows >= M and columns >= N, so no store masks are needed; two staging buffers per warp.
+                const long long coff_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
+#pragma unroll 1
+                for (int c64 = 0; c64 < BN / 64; ++c64) {
+                    const int col0 = n0 + c64 * 64;
+                    if (col0 >= p.N) break;   // warp-uniform
+                    uint8_t* buf = epi_smem + (ew * 2 + (c64 & 1)) * Cfg::EPI_BUF_BYTES;
+                    if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last used this buffer has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
+                        ptx::tmem_ld_wait();
+                        const int colh = col0 + half * 32;
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]) * p.alpha;
+                            const int col = colh + g8 * 8;
+                            const bool col_ok = col < p.N;
+                            if (p.bias && col_ok) {
+                                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 b2 = unpack_bf16x2(bw[j]);
+                                    x[2 * j] += b2.x; x[2 * j + 1] += b2.y;
+                                }
+                            }
+                            if (p.act == 1) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+                            } else if (p.act == 2) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+                            }
+                            if (p.relu_mask && row_ok && col_ok) {
+                                const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + coff_row + col));
+                                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 m2 = unpack_bf16x2(mw[j]);
+                                    if (!(m2.x > 0.f)) x[2 * j] = 0.f;
+                                    if (!(m2.y > 0.f)) x[2 * j + 1] = 0.f;
+                                }
+                            }
+                            if (p.residual && row_ok && col_ok) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + coff_row + col));
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 r2 = unpack_bf16x2(rw[j]);
+                                    x[2 * j] += r2.x; x[2 * j + 1] += r2.y;
+                                }
+                            }
+                            uint4 ov;
+                            ov.x = pack_bf16x2(x[0], x[1]); ov.y = pack_bf16x2(x[2], x[3]);
+                            ov.z = pack_bf16x2(x[4], x[5]); ov.w = pack_bf16x2(x[6], x[7]);
+                            const int chunk = half * 4 + g8;   // 16-byte chunk inside the 128-byte row
+                            *reinterpret_cast<uint4*>(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = ov;
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_3d(&tmc, buf, col0, m_blk * BM + ew * 32, z);
+                        ptx::tma_store_commit();
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
+
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -294,6 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         }
     }
 
+    if (warp >= 4 && lane == 0 && p.tma_store) ptx::tma_store_wait<0>();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -399,14 +485,15 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d, int grid,
+                       cudaStream_t stream) {
     auto kern = gemm_kernel<BN, A_MN, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, d);
+    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, tc, d);
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -462,8 +549,16 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
                  "split-K path supports only alpha/accumulate epilogues");
     }
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc;
     int rc;
+    const bool tma_store = !q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 &&
+                           (reinterpret_cast<uintptr_t>(q->c) & 15) == 0;
+    if (tma_store) {
+        rc = make_tmap(&tc, q->c, q->m, q->n, q->ldc, Zout, q->c_batch_stride, 64, 32);
+        if (rc) return rc;
+    } else {
+        memset(&tc, 0, sizeof(tc));
+    }
     if (!a_mn) rc = make_tmap(&ta, q->a, q->m, q->k, q->lda, Zall, q->a_batch_stride, BK, BM);
     else rc = make_tmap(&ta, q->a, q->k, q->m, q->lda, Zall, q->a_batch_stride, 64, BK);
     if (rc) return rc;
@@ -483,6 +578,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     d.residual = reinterpret_cast<const bf16*>(q->residual);
     d.relu_mask = reinterpret_cast<const bf16*>(q->relu_mask);
     d.act = q->act; d.out_fp32 = q->out_fp32; d.accumulate = q->accumulate; d.alpha = q->alpha;
+    d.tma_store = tma_store ? 1 : 0;
     d.partial = reinterpret_cast<float*>(q->workspace);
 
     const long long total_tiles = out_tiles * splits;
@@ -490,10 +586,10 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
 
 #define PB_DISPATCH(BN_)                                                                         \
     do {                                                                                         \
-        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false>(ta, tb, d, grid, stream);        \
-        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true>(ta, tb, d, grid, stream);     \
-        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false>(ta, tb, d, grid, stream);     \
-        else rc = launch_gemm<BN_, true, true>(ta, tb, d, grid, stream);                         \
+        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false>(ta, tb, tc, d, grid, stream);        \
+        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true>(ta, tb, tc, d, grid, stream);     \
+        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false>(ta, tb, tc, d, grid, stream);     \
+        else rc = launch_gemm<BN_, true, true>(ta, tb, tc, d, grid, stream);                         \
     } while (0)
     if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
 #undef PB_DISPATCH

@@ -220,14 +220,32 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
 }
 
 // out[n] (bf16) = (accumulate ? out[n] : 0) + sum_p partial[p * stride + n]
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int P, long long stride, int N,
-                                       bf16* __restrict__ out, int accumulate) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// block = 32 columns x 8 partial-row lanes: coalesced 128-byte reads, tree-free smem reduce over the 8 lanes.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int P, long long stride, int N,
+                       bf16* __restrict__ out, int accumulate) {
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
     float a = 0.f;
-    for (int p = 0; p < P; ++p) a += partial[(long long)p * stride + n];
-    if (accumulate) a += bf16_to_f(out[n]);
-    out[n] = f_to_bf16(a);
+    if (n < N) {
+        int p = py;
+        for (; p + 24 < P; p += 32) {   // 4 independent loads in flight
+            const float v0 = partial[(long long)p * stride + n], v1 = partial[(long long)(p + 8) * stride + n];
+            const float v2 = partial[(long long)(p + 16) * stride + n], v3 = partial[(long long)(p + 24) * stride + n];
+            a += (v0 + v1) + (v2 + v3);
+        }
+        for (; p < P; p += 8) a += partial[(long long)p * stride + n];
+    }
+    __shared__ float red[8][33];
+    red[py][cx] = a;
+    __syncthreads();
+    if (py == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][cx];
+        if (accumulate) s += bf16_to_f(out[n]);
+        out[n] = f_to_bf16(s);
+    }
 }
 
 // column sums of a bf16 [M, N] matrix (bias gradients): partial[split][N]
@@ -262,8 +280,18 @@ colsum_kernel(const bf16* __restrict__ x, int M, int N, long long ld, float* __r
 
 static int ln_bwd_grid(int M) {
     int g = (M + LN_WARPS - 1) / LN_WARPS;
-    const int cap = 4 * num_sms();
+    const int cap = 2 * num_sms();
     return g < cap ? g : cap;
+}
+
+static int colsum_splits(long long M, long long N) {
+    const long long col_blocks = (N + 255) / 256;
+    long long splits = (4LL * num_sms() + col_blocks - 1) / col_blocks;
+    const long long max_splits = (M + 15) / 16;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 1024) splits = 1024;
+    if (splits < 1) splits = 1;
+    return (int)splits;
 }
 
 }  // namespace pb200
@@ -319,7 +347,7 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();
     if (partial) {
-        const int threads = 256, blocks = (int)((D + threads - 1) / threads);
+        const int threads = 256, blocks = (int)((D + 31) / 32);
         if (dgamma) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial, grid, 2 * D, (int)D, (bf16*)dgamma, accumulate);
         if (dbeta) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial + D, grid, 2 * D, (int)D, (bf16*)dbeta, accumulate);
         PB_LAUNCH_CHECK();
@@ -328,10 +356,7 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
 }
 
 extern "C" size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N) {
-    long long splits = (M + 255) / 256;
-    if (splits > 64) splits = 64;
-    if (splits < 1) splits = 1;
-    return (size_t)splits * (size_t)N * sizeof(float);
+    return (size_t)colsum_splits(M, N) * (size_t)N * sizeof(float);
 }
 
 extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out, int32_t accumulate,
@@ -339,14 +364,12 @@ extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PB_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
     if (N == 0) return 0;
-    long long splits = (M + 255) / 256;
-    if (splits > 64) splits = 64;
-    if (splits < 1) splits = 1;
+    const long long splits = colsum_splits(M, N);
     PB_CHECK(workspace && workspace_bytes >= pb200_colsum_workspace_bytes(M, N), "colsum workspace too small");
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)splits);
     colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, (int)M, (int)N, ld, (float*)workspace);
     PB_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(int)((N + 255) / 256), 256, 0, stream>>>((const float*)workspace, (int)splits, N, (int)N,
+    reduce_partials_kernel<<<(int)((N + 31) / 32), 256, 0, stream>>>((const float*)workspace, (int)splits, N, (int)N,
                                                                        (bf16*)out, accumulate);
     PB_LAUNCH_CHECK();
     return 0;
