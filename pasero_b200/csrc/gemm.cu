@@ -59,7 +59,11 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, bool A_MN, bool B_MN>
+// EPI selects the epilogue at compile time (the generic one carries ~2500 SASS instructions per 64 columns when every
+// option is a run-time flag, which made the kernel epilogue-bound):
+//   -1 generic direct-store path (fp32 out, accumulate, split-K partials, alpha, GELU, residual)
+//    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask      -> staged in smem, written by TMA
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
             const __grid_constant__ CUtensorMap tmc, const GemmDev p) {
@@ -80,7 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tma);
         ptx::prefetch_tmap(&tmb);
-        if (p.tma_store) ptx::prefetch_tmap(&tmc);
+        if (EPI >= 0) ptx::prefetch_tmap(&tmc);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -206,10 +210,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 
-            if (p.tma_store) {
+            if constexpr (EPI >= 0) {
                 // bf16 output: 64-column slabs -> swizzled smem (this warp's 32 rows) -> TMA store. The TMA clips
                 // rows >= M and columns >= N, so no store masks are needed; two staging buffers per warp.
                 const long long coff_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
+                // bias for the whole tile: lane l keeps columns [n0 + 8l, n0 + 8l + 8); broadcast by shuffle later, so
+                // no global-load latency sits between the TMEM reads and the stores
+                uint4 bias_reg = make_uint4(0, 0, 0, 0);
+                if ((EPI == 1 || EPI == 2) && lane * 8 < BN && n0 + lane * 8 < p.N)
+                    bias_reg = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + lane * 8));
 #pragma unroll 1
                 for (int c64 = 0; c64 < BN / 64; ++c64) {
                     const int col0 = n0 + c64 * 64;
@@ -219,50 +228,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                     __syncwarp();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
+                        const int colh = col0 + half * 32;
+                        // auxiliary operands of this 32-column slab are requested before the TMEM read is waited on
+                        uint4 aux_m[4];
+                        if constexpr (EPI == 3) {
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) {
+                                aux_m[g8] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                                if (row_ok && colh + g8 * 8 < p.N)
+                                    aux_m[g8] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + coff_row + colh + g8 * 8));
+                            }
+                        }
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
                         ptx::tmem_ld_wait();
-                        const int colh = col0 + half * 32;
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
                             float x[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]) * p.alpha;
-                            const int col = colh + g8 * 8;
-                            const bool col_ok = col < p.N;
-                            if (p.bias && col_ok) {
-                                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]);
+                            if constexpr (EPI == 1 || EPI == 2) {
+                                const int src = c64 * 8 + half * 4 + g8;
+                                const uint32_t bw[4] = {__shfl_sync(0xffffffffu, bias_reg.x, src), __shfl_sync(0xffffffffu, bias_reg.y, src),
+                                                        __shfl_sync(0xffffffffu, bias_reg.z, src), __shfl_sync(0xffffffffu, bias_reg.w, src)};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float2 b2 = unpack_bf16x2(bw[j]);
                                     x[2 * j] += b2.x; x[2 * j + 1] += b2.y;
                                 }
                             }
-                            if (p.act == 1) {
+                            if constexpr (EPI == 2) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
-                            } else if (p.act == 2) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
                             }
-                            if (p.relu_mask && row_ok && col_ok) {
-                                const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + coff_row + col));
-                                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+                            if constexpr (EPI == 3) {
+                                const uint32_t mw[4] = {aux_m[g8].x, aux_m[g8].y, aux_m[g8].z, aux_m[g8].w};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 m2 = unpack_bf16x2(mw[j]);
-                                    if (!(m2.x > 0.f)) x[2 * j] = 0.f;
-                                    if (!(m2.y > 0.f)) x[2 * j + 1] = 0.f;
-                                }
-                            }
-                            if (p.residual && row_ok && col_ok) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + coff_row + col));
-                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 r2 = unpack_bf16x2(rw[j]);
-                                    x[2 * j] += r2.x; x[2 * j + 1] += r2.y;
+                                for (int j = 0; j < 4; ++j) {   // bf16 > 0  <=>  sign bit clear and not +0
+                                    if ((int)(mw[j] << 16) <= 0) x[2 * j] = 0.f;
+                                    if ((int)(mw[j] & 0xffff0000u) <= 0) x[2 * j + 1] = 0.f;
                                 }
                             }
                             uint4 ov;
@@ -282,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&tmem_empty[acc]);
                 continue;
-            }
+            } else {
 
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -376,10 +380,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
 
-    if (warp >= 4 && lane == 0 && p.tma_store) ptx::tma_store_wait<0>();
+    if (EPI >= 0 && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -484,10 +489,10 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d, int grid,
                        cudaStream_t stream) {
-    auto kern = gemm_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
@@ -520,10 +525,12 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     // tile width: wide tiles when N is large enough to keep >= ~1 wave of CTAs busy
     const long long m_blks = (q->m + BM - 1) / BM;
     const long long Zout = q->reduce_batch ? 1 : Zall;
+    // 128 x 256 tiles halve the A re-reads and the per-tile overheads; fall back to 128 x 128 only when the wide
+    // tiling would leave most SMs without a tile
     int bn = 128;
     if (q->n >= 256 && q->tile_n != 128) {
         const long long tiles256 = Zout * m_blks * ((q->n + 255) / 256);
-        if (tiles256 >= 2LL * num_sms() || q->tile_n == 256) bn = 256;
+        if (tiles256 * 2 >= num_sms() || q->tile_n == 256) bn = 256;
     }
     const long long n_blks = (q->n + bn - 1) / bn;
     const long long kb_per = (q->k + BK - 1) / BK;
@@ -533,7 +540,17 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     long long splits = q->split_k;
     if (splits <= 0) {
         splits = 1;
-        if (out_tiles * 2 <= num_sms()) splits = num_sms() / out_tiles;
+        if (out_tiles * 2 <= num_sms()) {
+            // choose the split count that fills whole waves of SMs (each split keeps >= 8 k-blocks)
+            double best = 0.0;
+            const long long max_s = total_kb / 8 > 0 ? (total_kb / 8 < 32 ? total_kb / 8 : 32) : 1;
+            for (long long s = 1; s <= max_s; ++s) {
+                const long long t = out_tiles * s;
+                const long long waves = (t + num_sms() - 1) / num_sms();
+                const double eff = (double)t / (double)(waves * num_sms()) - 0.01 * (double)s;  // mild bias to fewer splits
+                if (eff > best) { best = eff; splits = s; }
+            }
+        }
     }
     if (splits > total_kb) splits = total_kb;
     if (splits > 1) {
@@ -551,8 +568,14 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
 
     CUtensorMap ta, tb, tc;
     int rc;
-    const bool tma_store = !q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 &&
-                           (reinterpret_cast<uintptr_t>(q->c) & 15) == 0;
+    int epi = -1;
+    if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
+        (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && q->residual == nullptr && (q->act == 0 || q->act == 1)) {
+        if (q->relu_mask) { if (!q->bias && q->act == 0) epi = 3; }
+        else if (q->bias) epi = q->act == 1 ? 2 : 1;
+        else if (q->act == 0) epi = 0;
+    }
+    const bool tma_store = epi >= 0;
     if (tma_store) {
         rc = make_tmap(&tc, q->c, q->m, q->n, q->ldc, Zout, q->c_batch_stride, 64, 32);
         if (rc) return rc;
@@ -584,14 +607,25 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     const long long total_tiles = out_tiles * splits;
     const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
 
-#define PB_DISPATCH(BN_)                                                                         \
-    do {                                                                                         \
-        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false>(ta, tb, tc, d, grid, stream);        \
-        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true>(ta, tb, tc, d, grid, stream);     \
-        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false>(ta, tb, tc, d, grid, stream);     \
-        else rc = launch_gemm<BN_, true, true>(ta, tb, tc, d, grid, stream);                         \
+#define PB_DISPATCH2(BN_, EPI_)                                                                          \
+    do {                                                                                                 \
+        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false, EPI_>(ta, tb, tc, d, grid, stream);      \
+        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true, EPI_>(ta, tb, tc, d, grid, stream);   \
+        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false, EPI_>(ta, tb, tc, d, grid, stream);   \
+        else rc = launch_gemm<BN_, true, true, EPI_>(ta, tb, tc, d, grid, stream);                       \
+    } while (0)
+#define PB_DISPATCH(BN_)                                          \
+    do {                                                          \
+        switch (epi) {                                            \
+            case 0: PB_DISPATCH2(BN_, 0); break;                  \
+            case 1: PB_DISPATCH2(BN_, 1); break;                  \
+            case 2: PB_DISPATCH2(BN_, 2); break;                  \
+            case 3: PB_DISPATCH2(BN_, 3); break;                  \
+            default: PB_DISPATCH2(BN_, -1); break;                \
+        }                                                         \
     } while (0)
     if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
+#undef PB_DISPATCH2
 #undef PB_DISPATCH
     if (rc) return rc;
 

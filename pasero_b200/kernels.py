@@ -54,9 +54,9 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     plain = bias is None and residual is None and relu_mask is None and act == 0
     if split_k != 1 and plain:
         zout = 1 if reduce_batch else batch
-        tiles = zout * math.ceil(m / 128) * math.ceil(n / 128)
+        tiles = zout * math.ceil(m / 128) * math.ceil(n / 256 if n >= 256 else n / 128)
         sms = lib.pb200_num_sms()
-        max_splits = split_k if split_k > 1 else (sms // tiles if tiles * 2 <= sms else 1)
+        max_splits = split_k if split_k > 1 else (32 if tiles * 2 <= sms else 1)
         if max_splits > 1:
             ws = _ws(lib.pb200_gemm_workspace_bytes(m, n, zout, max_splits), c.device)
     if ws is None:
