@@ -84,6 +84,7 @@ typedef struct pb200_gemm_params {
     float alpha;
     int32_t split_k;          /* 0 = choose automatically, >= 1 = force */
     int32_t tile_n;           /* 0 = choose automatically, 128 or 256 = force */
+    int32_t cluster_m;        /* 0 = choose automatically; 1, 2 or 4 CTAs per cluster sharing the B tile by TMA multicast */
     void* workspace;          /* fp32 split-K partials; may be NULL when split_k == 1 */
     size_t workspace_bytes;
 } pb200_gemm_params;

@@ -63,7 +63,12 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // option is a run-time flag, which made the kernel epilogue-bound):
 //   -1 generic direct-store path (fp32 out, accumulate, split-K partials, alpha, GELU, residual)
 //    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask      -> staged in smem, written by TMA
-template <int BN, bool A_MN, bool B_MN, int EPI>
+//    4 split-K: fp32 partial tile TMA-reduce-added (+=, performed in L2) into one fp32 accumulation buffer
+// CL > 1: thread-block clusters of CL CTAs along M. The CTAs of a cluster work on CL consecutive m-blocks of the same
+// n-block, so they need the same B tile: each CTA fetches 1/CL of it and TMA-multicasts that slice into every CTA's
+// shared memory, cutting the L2 -> SM operand traffic of these weight-small GEMMs (B re-read once per m-block) by
+// up to (1 - 1/CL) of the B share.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
             const __grid_constant__ CUtensorMap tmc, const GemmDev p) {
@@ -80,6 +85,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int cta_rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+    const int cluster_id = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int num_clusters = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tma);
@@ -89,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], CL);   // every CTA of the cluster releases the stage
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
@@ -102,23 +111,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int tiles_per_z = p.m_blks * p.n_blks * p.splits;
-    const int total_tiles = p.Z * tiles_per_z;
+    const int m_groups = (p.m_blks + CL - 1) / CL;
+    const int total_tiles = p.Z * m_groups * p.n_blks * p.splits;   // cluster-level tiles
 
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
                 int r = tile;
                 const int split = r % p.splits; r /= p.splits;
                 const int n_blk = r % p.n_blks; r /= p.n_blks;
-                const int m_blk = r % p.m_blks; r /= p.m_blks;
+                const int m_blk = (r % m_groups) * CL + cta_rank; r /= m_groups;
                 const int z = r;
                 const int m0 = m_blk * BM, n0 = n_blk * BN;
                 const int kb_begin = split * p.kb_per_split;
@@ -139,12 +148,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                         for (int j = 0; j < BM / 64; ++j)
                             ptx::tma_load_3d(&tma, &full_bar[stage], sa + j * (BK * 128), m0 + j * 64, k0, za);
                     }
-                    if (!B_MN) {
-                        ptx::tma_load_3d(&tmb, &full_bar[stage], sb, k0, n0, zb);
-                    } else {
+                    if (CL == 1) {
+                        if (!B_MN) {
+                            ptx::tma_load_3d(&tmb, &full_bar[stage], sb, k0, n0, zb);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            ptx::tma_load_3d(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, k0, zb);
+                            for (int j = 0; j < BN / 64; ++j)
+                                ptx::tma_load_3d(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, k0, zb);
+                        }
+                    } else if (!B_MN) {   // this CTA's BN/CL rows of the B tile, multicast to the whole cluster
+                        constexpr int ROWS = BN / CL;
+                        ptx::tma_load_3d_mc(&tmb, &full_bar[stage], sb + cta_rank * ROWS * 128, k0, n0 + cta_rank * ROWS, zb, MC_MASK);
+                    } else {              // this CTA's share of the 64-column boxes
+                        constexpr int PER = (BN / 64) / CL;
+#pragma unroll
+                        for (int jj = 0; jj < PER; ++jj) {
+                            const int j = cta_rank * PER + jj;
+                            ptx::tma_load_3d_mc(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, k0, zb, MC_MASK);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -157,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++local) {
                 const int split = tile % p.splits;
                 const int kb_begin = split * p.kb_per_split;
                 const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
@@ -182,7 +203,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                                                     : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
                         ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot (in every CTA of the cluster: peers multicast into it) when these MMAs retire
+                    if (CL > 1) ptx::umma_commit_mc(&empty_bar[stage], MC_MASK); else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
@@ -192,11 +214,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
         const int ew = warp & 3;  // TMEM lane quarter this warp may access
         int local = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++local) {
             int r = tile;
             const int split = r % p.splits; r /= p.splits;
             const int n_blk = r % p.n_blks; r /= p.n_blks;
-            const int m_blk = r % p.m_blks; r /= p.m_blks;
+            const int m_blk = (r % m_groups) * CL + cta_rank; r /= m_groups;
             const int z = r;
             const int n0 = n_blk * BN;
             const int row = m_blk * BM + ew * 32 + lane;
@@ -210,7 +232,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 
-            if constexpr (EPI >= 0) {
+            if constexpr (EPI == 4) {
+                // split-K partial: 32-column fp32 slabs -> swizzled smem -> TMA reduce-add into the fp32 accumulator
+#pragma unroll 1
+                for (int c32 = 0; c32 < BN / 32; ++c32) {
+                    const int col0 = n0 + c32 * 32;
+                    if (col0 >= p.N) break;   // warp-uniform
+                    uint8_t* buf = epi_smem + (ew * 2 + (c32 & 1)) * Cfg::EPI_BUF_BYTES;
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)   // 8 x 16-byte chunks (4 floats) per 128-byte row
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                            empty_range ? make_uint4(0, 0, 0, 0) : make_uint4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_reduce_add_3d(&tmc, buf, col0, m_blk * BM + ew * 32, z);
+                        ptx::tma_store_commit();
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tmem_empty[acc]);
+                continue;
+            } else if constexpr (EPI >= 0) {
                 // bf16 output: 64-column slabs -> swizzled smem (this warp's 32 rows) -> TMA store. The TMA clips
                 // rows >= M and columns >= N, so no store masks are needed; two staging buffers per warp.
                 const long long coff_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
@@ -386,7 +434,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 
     if (EPI >= 0 && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // no CTA leaves while peers may still signal its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -461,7 +509,7 @@ static EncodeTiledFn get_encode_fn() {
 // Tensor map over a bf16 matrix stored as `rows` x `cols` (cols contiguous), `ld` elements between
 // rows, `batch` slices `batch_stride` elements apart; box = box_cols x box_rows x 1, SWIZZLE_128B.
 static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
-                     long long batch, long long batch_stride, int box_cols, int box_rows) {
+                     long long batch, long long batch_stride, int box_cols, int box_rows, bool fp32 = false) {
     EncodeTiledFn enc = get_encode_fn();
     PB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     // The driver-level encode needs a context current on THIS thread. PyTorch's autograd worker threads skip
@@ -473,14 +521,15 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
         ctx_bound = true;
     }
     PB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm operand pointer must be 16-byte aligned");
-    PB_CHECK(ld % 8 == 0, "gemm operand leading dimension (%lld) must be a multiple of 8 elements", ld);
+    PB_CHECK(ld % (fp32 ? 4 : 8) == 0, "gemm operand leading dimension (%lld) must be a multiple of 16 bytes", ld);
     PB_CHECK(batch <= 1 || batch_stride % 8 == 0, "gemm operand batch stride (%lld) must be a multiple of 8", batch_stride);
+    const int esz = fp32 ? 4 : 2;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
     long long bs = (batch > 1 && batch_stride > 0) ? batch_stride : rows * ld;
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)bs * esz};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS,
@@ -489,16 +538,26 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d, int grid,
                        cudaStream_t stream) {
-    auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+    auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, tc, d);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, d));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -508,8 +567,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 using namespace pb200;
 
 extern "C" size_t pb200_gemm_workspace_bytes(int64_t m, int64_t n, int64_t batch, int32_t max_splits) {
-    if (max_splits < 1) max_splits = 1;
-    return (size_t)max_splits * (size_t)(batch > 0 ? batch : 1) * (size_t)m * (size_t)n * sizeof(float);
+    (void)max_splits;   // split-K partials are reduce-added into a single fp32 [batch, m, n] buffer
+    return (size_t)(batch > 0 ? batch : 1) * (size_t)m * (size_t)n * sizeof(float);
 }
 
 extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
@@ -530,7 +589,9 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     int bn = 128;
     if (q->n >= 256 && q->tile_n != 128) {
         const long long tiles256 = Zout * m_blks * ((q->n + 255) / 256);
-        if (tiles256 * 2 >= num_sms() || q->tile_n == 256) bn = 256;
+        const long long kb_all = ((q->k + BK - 1) / BK) * (q->reduce_batch ? Zall : 1);
+        const bool can_split = q->split_k != 1 && kb_all >= 32 && q->workspace != nullptr;   // split-K fills the SMs instead
+        if (tiles256 * 2 >= num_sms() || can_split || q->tile_n == 256) bn = 256;
     }
     const long long n_blks = (q->n + bn - 1) / bn;
     const long long kb_per = (q->k + BK - 1) / BK;
@@ -553,11 +614,9 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         }
     }
     if (splits > total_kb) splits = total_kb;
-    if (splits > 1) {
-        const size_t per_split = (size_t)Zout * q->m * q->n * sizeof(float);
-        const long long fit = q->workspace ? (long long)(q->workspace_bytes / per_split) : 0;
-        if (splits > fit) splits = fit;
-        if (splits < 1) splits = 1;
+    if (splits > 1) {   // partial tiles are reduce-added into ONE fp32 buffer
+        const size_t need = (size_t)Zout * q->m * q->n * sizeof(float);
+        if (!q->workspace || q->workspace_bytes < need) splits = 1;
     }
     long long kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per_split - 1) / kb_per_split;
@@ -569,14 +628,19 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     CUtensorMap ta, tb, tc;
     int rc;
     int epi = -1;
-    if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
+    if (splits > 1) epi = 4;
+    else if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
         (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && q->residual == nullptr && (q->act == 0 || q->act == 1)) {
         if (q->relu_mask) { if (!q->bias && q->act == 0) epi = 3; }
         else if (q->bias) epi = q->act == 1 ? 2 : 1;
         else if (q->act == 0) epi = 0;
     }
     const bool tma_store = epi >= 0;
-    if (tma_store) {
+    if (epi == 4) {
+        PB_CUDA(cudaMemsetAsync(q->workspace, 0, (size_t)Zout * q->m * q->n * sizeof(float), stream));
+        rc = make_tmap(&tc, q->workspace, q->m, q->n, q->n, Zout, (long long)q->m * q->n, 32, 32, /*fp32=*/true);
+        if (rc) return rc;
+    } else if (tma_store) {
         rc = make_tmap(&tc, q->c, q->m, q->n, q->ldc, Zout, q->c_batch_stride, 64, 32);
         if (rc) return rc;
     } else {
@@ -585,7 +649,12 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     if (!a_mn) rc = make_tmap(&ta, q->a, q->m, q->k, q->lda, Zall, q->a_batch_stride, BK, BM);
     else rc = make_tmap(&ta, q->a, q->k, q->m, q->lda, Zall, q->a_batch_stride, 64, BK);
     if (rc) return rc;
-    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn);
+    // cluster size along M (B-tile multicast); 2 keeps every SM usable (4-CTA clusters strand SMs on this part)
+    int cl = q->cluster_m > 0 ? q->cluster_m : 2;
+    if (m_blks < 2) cl = 1;
+    if (cl == 4 && b_mn && bn == 128) cl = 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn / cl);
     else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zall, q->b_batch_stride, 64, BK);
     if (rc) return rc;
 
@@ -604,15 +673,23 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     d.tma_store = tma_store ? 1 : 0;
     d.partial = reinterpret_cast<float*>(q->workspace);
 
-    const long long total_tiles = out_tiles * splits;
-    const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+    const long long m_groups = (m_blks + cl - 1) / cl;
+    const long long cluster_tiles = Zout * m_groups * n_blks * splits;
+    const long long max_clusters = num_sms() / cl;
+    const int grid = (int)((cluster_tiles < max_clusters ? cluster_tiles : max_clusters) * cl);
 
-#define PB_DISPATCH2(BN_, EPI_)                                                                          \
-    do {                                                                                                 \
-        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false, EPI_>(ta, tb, tc, d, grid, stream);      \
-        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true, EPI_>(ta, tb, tc, d, grid, stream);   \
-        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false, EPI_>(ta, tb, tc, d, grid, stream);   \
-        else rc = launch_gemm<BN_, true, true, EPI_>(ta, tb, tc, d, grid, stream);                       \
+#define PB_DISPATCH3(BN_, EPI_, CL_)                                                                         \
+    do {                                                                                                      \
+        if (!a_mn && !b_mn) rc = launch_gemm<BN_, false, false, EPI_, CL_>(ta, tb, tc, d, grid, stream);      \
+        else if (!a_mn && b_mn) rc = launch_gemm<BN_, false, true, EPI_, CL_>(ta, tb, tc, d, grid, stream);   \
+        else if (a_mn && !b_mn) rc = launch_gemm<BN_, true, false, EPI_, CL_>(ta, tb, tc, d, grid, stream);   \
+        else rc = launch_gemm<BN_, true, true, EPI_, CL_>(ta, tb, tc, d, grid, stream);                       \
+    } while (0)
+#define PB_DISPATCH2(BN_, EPI_)                                   \
+    do {                                                          \
+        if (cl == 1) PB_DISPATCH3(BN_, EPI_, 1);                  \
+        else if (cl == 2) PB_DISPATCH3(BN_, EPI_, 2);             \
+        else PB_DISPATCH3(BN_, EPI_, 4);                          \
     } while (0)
 #define PB_DISPATCH(BN_)                                          \
     do {                                                          \
@@ -621,10 +698,12 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
             case 1: PB_DISPATCH2(BN_, 1); break;                  \
             case 2: PB_DISPATCH2(BN_, 2); break;                  \
             case 3: PB_DISPATCH2(BN_, 3); break;                  \
+            case 4: PB_DISPATCH2(BN_, 4); break;                  \
             default: PB_DISPATCH2(BN_, -1); break;                \
         }                                                         \
     } while (0)
     if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
+#undef PB_DISPATCH3
 #undef PB_DISPATCH2
 #undef PB_DISPATCH
     if (rc) return rc;
@@ -634,7 +713,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         const int threads = 256;
         long long blocks = (zmn / 4 + threads - 1) / threads;
         if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
-        splitk_reduce_kernel<<<(int)blocks, threads, 0, stream>>>(d.partial, (int)splits, zmn, d.M, d.N, q->c, q->ldc,
+        splitk_reduce_kernel<<<(int)blocks, threads, 0, stream>>>(d.partial, 1, zmn, d.M, d.N, q->c, q->ldc,
                                                                  q->c_batch_stride, q->out_fp32, q->accumulate,
                                                                  q->alpha, nullptr);
         PB_LAUNCH_CHECK();

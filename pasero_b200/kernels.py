@@ -39,7 +39,8 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
              batch: int = 1, a_batch_stride: int = 0, b_batch_stride: int = 0, c_batch_stride: int = 0,
              a_mn_major: bool = False, b_mn_major: bool = False, reduce_batch: bool = False,
              bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, relu_mask: Optional[Tensor] = None,
-             act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0) -> Tensor:
+             act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0,
+             cluster_m: int = 0) -> Tensor:
     lib = _lib.load()
     p = GemmParams()
     p.a, p.b, p.c = a_ptr, b_ptr, c.data_ptr()
@@ -49,16 +50,15 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     p.a_mn_major, p.b_mn_major, p.reduce_batch = int(a_mn_major), int(b_mn_major), int(reduce_batch)
     p.bias, p.residual, p.relu_mask = ptr(bias), ptr(residual), ptr(relu_mask)
     p.act, p.out_fp32, p.accumulate, p.alpha = act, int(c.dtype == torch.float32), int(accumulate), alpha
-    p.split_k, p.tile_n = split_k, tile_n
+    p.split_k, p.tile_n, p.cluster_m = split_k, tile_n, cluster_m
     ws = None
     plain = bias is None and residual is None and relu_mask is None and act == 0
     if split_k != 1 and plain:
         zout = 1 if reduce_batch else batch
         tiles = zout * math.ceil(m / 128) * math.ceil(n / 256 if n >= 256 else n / 128)
         sms = lib.pb200_num_sms()
-        max_splits = split_k if split_k > 1 else (32 if tiles * 2 <= sms else 1)
-        if max_splits > 1:
-            ws = _ws(lib.pb200_gemm_workspace_bytes(m, n, zout, max_splits), c.device)
+        if split_k > 1 or tiles * 2 <= sms:
+            ws = _ws(lib.pb200_gemm_workspace_bytes(m, n, zout, 1), c.device)
     if ws is None:
         p.split_k = 1
     p.workspace, p.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
@@ -75,14 +75,14 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
 
 
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0,
-               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0) -> Tensor:
+               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0, cluster_m: int = 0) -> Tensor:
     """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual)"""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
     y = torch.empty(M, N, dtype=out_dtype, device=x.device)
     return gemm_raw(x.data_ptr(), w.data_ptr(), y, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, act=act,
-                    residual=residual, split_k=1, tile_n=tile_n)
+                    residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m)
 
 
 def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out: Optional[Tensor] = None,

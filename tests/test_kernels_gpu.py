@@ -33,10 +33,11 @@ def _close(got, want, atol, rtol, name=''):
 # ---------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 136, 200), (1000, 512, 512), (4096, 2048, 512), (257, 8032, 512)])
 @pytest.mark.parametrize('tile_n', [128, 256])
-def test_gemm_forward(M, N, K, tile_n):
+@pytest.mark.parametrize('cluster_m', [1, 2, 4])
+def test_gemm_forward(M, N, K, tile_n, cluster_m):
     k = _k()
     x, w, b = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3)
-    y = k.linear_fwd(x, w, b, tile_n=tile_n)
+    y = k.linear_fwd(x, w, b, tile_n=tile_n, cluster_m=cluster_m)
     ref = x.float() @ w.float().T + b.float()
     _close(y, ref, 2e-2, 1e-2, 'linear_fwd')
 

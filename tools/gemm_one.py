@@ -1,14 +1,22 @@
-"""Runs one GEMM shape a few times (for ncu)."""
+"""Runs one GEMM shape a few times (for ncu): mode fwd|dgrad|wgrad."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pasero_b200 import kernels as k
-M, N, K = [int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (16000, 2048, 512))]
-tn = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+mode = sys.argv[1]
+M, N, K = [int(x) for x in sys.argv[2:5]]
 x = torch.randn(M, K, device='cuda').to(torch.bfloat16)
 w = torch.randn(N, K, device='cuda').to(torch.bfloat16)
 b = torch.randn(N, device='cuda').to(torch.bfloat16)
+dy = torch.randn(M, N, device='cuda').to(torch.bfloat16)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 for _ in range(6):
-    y = k.linear_fwd(x, w, b, act=1, tile_n=tn)
+    flush.zero_()
+    if mode == 'fwd':
+        y = k.linear_fwd(x, w, b, act=1)
+    elif mode == 'dgrad':
+        y = k.linear_dgrad(dy, w)
+    else:
+        y = k.linear_wgrad(dy, x)
 torch.cuda.synchronize()
 print('ok', float(y.float().abs().mean()))
