@@ -34,6 +34,55 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class DirectGrads:
+    """Trainer-installed sink for parameter gradients. When active, the backward kernels write each weight / bias
+    gradient straight into its slice of the flat gradient arena (overwrite on the first write of an optimizer step,
+    accumulate afterwards: tied embeddings, gradient-accumulation micro-batches) and the autograd Functions return None
+    for parameters, so no AccumulateGrad `+=` kernels run and the arena needs no per-step zeroing. `on_ready(param)`
+    is called once a parameter's gradient for this micro-batch is complete (drives the allreduce buckets)."""
+
+    active: Optional['DirectGrads'] = None
+
+    def __init__(self, views: dict, on_ready=None):
+        self.views = views            # id(param) -> arena view
+        self.written = set()
+        self.on_ready = on_ready
+
+    def start_step(self) -> None:
+        self.written.clear()
+
+    def sink(self, param) -> tuple:
+        """(out tensor, accumulate flag) for this parameter, or (None, False) when not managed."""
+        view = self.views.get(id(param))
+        if view is None:
+            return None, False
+        acc = id(param) in self.written
+        self.written.add(id(param))
+        return view, acc
+
+    def ready(self, *params) -> None:
+        if self.on_ready is not None:
+            for p in params:
+                if p is not None and id(p) in self.views:
+                    self.on_ready(p)
+
+
+def _sink(param):
+    d = DirectGrads.active
+    return d.sink(param) if (d is not None and param is not None) else (None, False)
+
+
+def _ready(*params):
+    d = DirectGrads.active
+    if d is not None:
+        d.ready(*params)
+
+
+def _ret(grad, out):
+    """Gradient to hand back to autograd: None when it already went into the arena."""
+    return None if out is not None else grad
+
+
 # --------------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     """y = x @ W^T + b   (x: [M, K] bf16, W: [N, K])"""
@@ -42,16 +91,23 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         x = _c(x)
         ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)
         return K.linear_fwd(x, weight, bias)
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
+        w_param, b_param = ctx.params
         dy = _c(dy)
         dx = K.linear_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
-        dw = K.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
-        db = K.colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            out, acc = _sink(w_param)
+            dw = _ret(K.linear_wgrad(dy, x, out=out, accumulate=acc), out)
+        if b_param is not None and ctx.needs_input_grad[2]:
+            out, acc = _sink(b_param)
+            db = _ret(K.colsum(dy, out=out, accumulate=acc), out)
+        _ready(w_param, b_param)
         return dx, dw, db
 
 
@@ -65,18 +121,22 @@ class FFNFn(torch.autograd.Function):
         h = K.linear_fwd(x, w1, b1, act=1)
         y = K.linear_fwd(h, w2, b2)
         ctx.save_for_backward(x, w1, w2, h)
+        ctx.params = (w1, b1, w2, b2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w1, w2, h = ctx.saved_tensors
+        p_w1, p_b1, p_w2, p_b2 = ctx.params
         dy = _c(dy)
         dh = K.linear_dgrad(dy, w2, relu_mask=h)
-        dw2 = K.linear_wgrad(dy, h)
-        db2 = K.colsum(dy)
+        o, a = _sink(p_w2); dw2 = _ret(K.linear_wgrad(dy, h, out=o, accumulate=a), o)
+        o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
+        _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1)
-        dw1 = K.linear_wgrad(dh, x)
-        db1 = K.colsum(dh)
+        o, a = _sink(p_w1); dw1 = _ret(K.linear_wgrad(dh, x, out=o, accumulate=a), o)
+        o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
+        _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2
 
 
@@ -106,6 +166,7 @@ class AttentionFn(torch.autograd.Function):
         y = K.linear_fwd(o, out_w, out_b)
         ctx.save_for_backward(query, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len)
         ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn)
+        ctx.params = (in_w, in_b, out_w, out_b)
         return y
 
     @staticmethod
@@ -113,19 +174,23 @@ class AttentionFn(torch.autograd.Function):
         query, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len = ctx.saved_tensors
         B, Lq, Lk, H, causal, scale, self_attn = ctx.dims
         D = H * 64
+        p_in_w, p_in_b, p_out_w, p_out_b = ctx.params
         dy = _c(dy)
         d_o = K.linear_dgrad(dy, out_w)
-        d_out_w = K.linear_wgrad(dy, o)
-        d_out_b = K.colsum(dy)
-        d_in_w = torch.empty_like(in_w)
-        d_in_b = torch.empty(3 * D, dtype=BF16, device=dy.device)
+        so, a = _sink(p_out_w); d_out_w = _ret(K.linear_wgrad(dy, o, out=so, accumulate=a), so)
+        so, a = _sink(p_out_b); d_out_b = _ret(K.colsum(dy, out=so, accumulate=a), so)
+        _ready(p_out_w, p_out_b)
+        sink_w, acc_w = _sink(p_in_w)
+        sink_b, acc_b = _sink(p_in_b)
+        d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
+        d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
             dquery = K.linear_dgrad(dkvq, in_w)
-            K.linear_wgrad(dkvq, query, out=d_in_w)
-            K.colsum(dkvq, out=d_in_b)
+            K.linear_wgrad(dkvq, query, out=d_in_w, accumulate=acc_w)
+            K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
             dkey = None
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
@@ -133,11 +198,13 @@ class AttentionFn(torch.autograd.Function):
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
             dquery = K.linear_dgrad(dq, in_w[2 * D:])
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
-            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D])
-            K.linear_wgrad(dq, query, out=d_in_w[2 * D:])
-            K.colsum(dkv, out=d_in_b[:2 * D])
-            K.colsum(dq, out=d_in_b[2 * D:])
-        return dquery, dkey, d_in_w, d_in_b, d_out_w, d_out_b, None, None, None, None, None, None, None
+            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
+            K.linear_wgrad(dq, query, out=d_in_w[2 * D:], accumulate=acc_w)
+            K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
+        _ready(p_in_w, p_in_b)
+        return (dquery, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b,
+                None, None, None, None, None, None, None)
 
 
 class DropoutAddLNFn(torch.autograd.Function):
@@ -151,6 +218,7 @@ class DropoutAddLNFn(torch.autograd.Function):
         y, s, mean, rstd = K.dropout_add_ln_fwd(x, residual, gamma, beta, eps, p, seed, offset)
         ctx.save_for_backward(s if gamma is not None else None, gamma, mean, rstd)
         ctx.cfg = (p, seed, offset, residual is not None, beta is not None)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -159,10 +227,15 @@ class DropoutAddLNFn(torch.autograd.Function):
         p, seed, offset, has_res, has_beta = ctx.cfg
         dy = _c(dy)
         D = dy.shape[1]
-        dgamma = torch.empty(D, dtype=BF16, device=dy.device) if gamma is not None else None
-        dbeta = torch.empty(D, dtype=BF16, device=dy.device) if (gamma is not None and has_beta) else None
-        dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, has_res, dgamma, dbeta)
-        return dx, dres, dgamma, dbeta, None, None
+        p_gamma, p_beta = ctx.params
+        sg, ag = _sink(p_gamma)
+        sb, ab = _sink(p_beta)
+        dgamma = sg if sg is not None else (torch.empty(D, dtype=BF16, device=dy.device) if gamma is not None else None)
+        dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if (gamma is not None and has_beta) else None)
+        dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, has_res, dgamma, dbeta,
+                                        accumulate=ag or ab)
+        _ready(p_gamma, p_beta)
+        return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), None, None
 
 
 class EmbedFn(torch.autograd.Function):
@@ -177,6 +250,7 @@ class EmbedFn(torch.autograd.Function):
         out = K.embed_fwd(ids_flat, _c(src), pos, M, D, L, scale, p, seed, offset)
         ctx.save_for_backward(ids_flat)
         ctx.cfg = (M, D, scale, p, seed, offset, padding_idx, src.shape[0])
+        ctx.table = src if ids is not None else None
         return out
 
     @staticmethod
@@ -188,9 +262,11 @@ class EmbedFn(torch.autograd.Function):
             return K.embed_bwd(dy, None, M, D, scale, p, seed, offset), None, None, None, None, None, None
         dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
         K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
-        dtable = torch.empty(rows, D, dtype=BF16, device=dy.device)
-        K.f32_to_bf16(dtable32, dtable)
-        return dtable, None, None, None, None, None, None
+        so, acc = _sink(ctx.table)
+        dtable = so if so is not None else torch.empty(rows, D, dtype=BF16, device=dy.device)
+        K.f32_to_bf16(dtable32, dtable, accumulate=acc)
+        _ready(ctx.table)
+        return _ret(dtable, so), None, None, None, None, None, None
 
 
 class ConvGLUFn(torch.autograd.Function):
@@ -213,6 +289,7 @@ class ConvGLUFn(torch.autograd.Function):
         out = K.glu_fwd(pre, B, Tout, Cout // 2, out_Tp, out_front_pad)
         ctx.save_for_backward(xp, weight, pre)
         ctx.dims = (B, Tin, Cin, KW, stride, Tout, Tp, out_Tp, out_front_pad, need_input_grad)
+        ctx.params = (weight, bias)
         return out
 
     @staticmethod
@@ -223,10 +300,16 @@ class ConvGLUFn(torch.autograd.Function):
         # gradient w.r.t. the GLU output rows (drop the padding rows of the padded layout)
         dy = _c(dout[:, out_front_pad:out_front_pad + Tout]).view(B * Tout, Cout // 2)
         dpre = K.glu_bwd(dy, pre, B * Tout, Cout // 2)
-        dw = torch.empty_like(weight)
+        p_w, p_b = ctx.params
+        so_w, acc_w = _sink(p_w)
+        dw = so_w if so_w is not None else torch.empty_like(weight)
         K.gemm_raw(dpre.data_ptr(), xp.data_ptr(), dw, Cout, KW * Cin, Tout, lda=Cout, ldb=stride * Cin, ldc=KW * Cin, batch=B,
-                   a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True)
-        db = K.colsum(dpre)
+                   a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True,
+                   accumulate=acc_w)
+        so_b, acc_b = _sink(p_b)
+        db = K.colsum(dpre, out=so_b, accumulate=acc_b)
+        _ready(p_w, p_b)
+        dw, db = _ret(dw, so_w), _ret(db, so_b)
         dxp = None
         if need_input_grad:
             dcol = torch.empty(B * Tout, KW * Cin, dtype=BF16, device=dout.device)
@@ -254,16 +337,19 @@ class ProjCEFn(torch.autograd.Function):
         before = stats[0].clone()
         K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True)
         ctx.save_for_backward(x, table, logits)
+        ctx.table = table
         return (stats[0] - before).float()
 
     @staticmethod
     def backward(ctx, dloss):
         x, table, dlogits = ctx.saved_tensors
         dx = K.linear_dgrad(dlogits, table)
-        dtable = K.linear_wgrad(dlogits, x)
-        if not ProjCEFn.unit_loss_grad:
+        if ProjCEFn.unit_loss_grad:
+            so, acc = _sink(ctx.table)
+            dtable = _ret(K.linear_wgrad(dlogits, x, out=so, accumulate=acc), so)
+        else:
+            dtable = K.linear_wgrad(dlogits, x) * dloss.to(BF16)
             dx = dx * dloss.to(dx.dtype)
-            dtable = dtable * dloss.to(dtable.dtype)
         return dx, dtable, None, None, None, None
 
 

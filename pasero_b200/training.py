@@ -131,18 +131,19 @@ class GradBuckets:
             self.sizes[b] += 1
         self.enabled = True
         self.launch_order = []
-        for i, p in enumerate(arena.params):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
+        for i, p in enumerate(arena.params):   # plain-autograd path (DirectGrads calls param_ready itself)
+            p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i))
 
-    def _make_hook(self, i: int):
-        def hook(param):
-            if not self.enabled:
-                return
-            b = self.param_bucket[i]
-            self.pending[b] += 1
-            if self.pending[b] == self.sizes[b]:
-                self._launch(b)
-        return hook
+    def param_ready(self, i: int) -> None:
+        """Parameter i's gradient for this micro-batch is complete; launch its bucket when it is the last one."""
+        if not self.enabled:
+            return
+        b = self.param_bucket[i]
+        if self.pending[b] < 0:
+            return
+        self.pending[b] += 1
+        if self.pending[b] == self.sizes[b]:
+            self._launch(b)
 
     def _launch(self, b: int) -> None:
         lo, hi = self.buckets[b]
@@ -199,6 +200,12 @@ class Trainer:
         if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.arena.param, src=0)
         self.buckets = GradBuckets(self.arena, cfg.bucket_bytes) if self.distributed else None
+        # parameter gradients go straight into the arena (no AccumulateGrad adds, no per-step memset)
+        index = {id(p): i for i, p in enumerate(self.arena.params)}
+        on_ready = (lambda p: self.buckets.param_ready(index[id(p)])) if self.buckets is not None else None
+        self.direct = ops.DirectGrads({id(p): self.arena.view(self.arena.grad, i) for i, p in enumerate(self.arena.params)},
+                                      on_ready)
+        ops.DirectGrads.active = self.direct
         self.scheduler = LRScheduler(cfg)
         self.optimizer_steps = 0     # Adam's state['step']
         self.steps = 0
@@ -253,8 +260,8 @@ class Trainer:
         logs: loss / nll_loss in bits (summed over all ranks' tokens), num_tokens, num_lines, gnorm, lr."""
         self.model.train()
         self.stats.zero_()
-        self.arena.grad.zero_()
-        self.arena.rebind_grads()
+        ops.DirectGrads.active = self.direct
+        self.direct.start_step()
         for batch_id in range(self.update_freq):
             batch = next(batch_iterator)
             batch = self.move_to_device(batch)
@@ -335,8 +342,8 @@ class Trainer:
 
     def _graph_body(self, static: dict, extras: dict) -> None:
         self.stats.zero_()
-        self.arena.grad.zero_()
-        self.arena.rebind_grads()
+        ops.DirectGrads.active = self.direct
+        self.direct.start_step()
         batch = dict(static)
         batch.update(extras)
         self._forward_backward(batch)
