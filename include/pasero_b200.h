@@ -177,9 +177,12 @@ int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stri
  *   hyper fp32[16] (device): [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] 1-beta1^t
  *        [6] sqrt(1-beta2^t) [7] clip_norm [8] dp_size [9] 1-beta1 [10] 1-beta2 [11] lr/(1-beta1^t)
  *        [12] weight_decay*lr
- *   stats fp64[8] (device): [2] num_tokens (gradient divisor), [4] squared gradient norm (in/out)
+ *   stats fp64[8] (device): [2] num_tokens (gradient divisor), [4] squared gradient norm (out; reduced in a fixed
+ *        order so that data-parallel replicas stay bit-identical). The sqnorm workspace is zero-initialised once.
  * ---------------------------------------------------------------------------------------------- */
-int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* stream);
+size_t pb200_grad_sqnorm_workspace_bytes(void);
+int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* workspace,
+                      size_t workspace_bytes, void* stream);
 int pb200_adam_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
                     const double* stats, void* stream);
 

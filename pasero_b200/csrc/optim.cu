@@ -22,9 +22,12 @@ __device__ __forceinline__ float grad_coeff(const float* hyper, const double* st
     return (float)((double)hyper[8] / (nt > 0.0 ? nt : 1.0));
 }
 
+// Deterministic two-phase reduction: every block writes its partial sum, the last block to finish (atomic ticket)
+// adds the partials in index order. Data-parallel replicas therefore compute bit-identical norms from their
+// bit-identical (allreduced) gradients and never drift apart.
 __global__ void __launch_bounds__(256)
 grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __restrict__ hyper,
-                   double* __restrict__ stats) {
+                   double* __restrict__ stats, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
     const float coeff = grad_coeff(hyper, stats);
     float acc = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -38,13 +41,24 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
         }
     }
     __shared__ double red[8];
+    __shared__ bool is_last;
     double d = warp_sum_d((double)acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < 8; ++i) t += red[i];
-        atomicAdd(&stats[4], t);
+        partials[blockIdx.x] = t;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(partials)[i];
+        stats[4] = t;
+        *ticket = 0;
     }
 }
 
@@ -103,13 +117,20 @@ adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __re
 
 using namespace pb200;
 
-// Sum of squares of bf16(grad * dp_size / num_tokens) accumulated into stats[4] (caller zeroes it).
-extern "C" int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* stream_) {
+extern "C" size_t pb200_grad_sqnorm_workspace_bytes(void) { return (size_t)(4 * num_sms() + 2) * sizeof(double); }
+
+// stats[4] = sum of squares of bf16(grad * dp_size / num_tokens); workspace must be zero-initialised once (the
+// kernel leaves it ready for the next call).
+extern "C" int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
     if (n == 0) return 0;
     PB_CHECK(n % 8 == 0, "gradient arena length (%lld) must be a multiple of 8", (long long)n);
+    PB_CHECK(workspace && workspace_bytes >= pb200_grad_sqnorm_workspace_bytes(), "grad_sqnorm workspace too small");
     long long blocks = (n / 8 + 255) / 256;
     if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
-    grad_sqnorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)grad, n / 8, hyper, stats);
+    double* partials = reinterpret_cast<double*>(workspace) + 1;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
+    grad_sqnorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)grad, n / 8, hyper, stats, partials, ticket);
     PB_LAUNCH_CHECK();
     return 0;
 }

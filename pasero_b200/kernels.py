@@ -259,9 +259,17 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
                                           stats.data_ptr(), ptr(row_loss), stream_ptr()))
 
 
+_SQNORM_WS = {}
+
+
 def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
+    lib = _lib.load()
+    ws = _SQNORM_WS.get(grad.device)
+    if ws is None:   # persistent, zero-initialised once (the kernel re-arms its ticket)
+        ws = _SQNORM_WS[grad.device] = torch.zeros(lib.pb200_grad_sqnorm_workspace_bytes(), dtype=torch.uint8, device=grad.device)
     _count(1)
-    check(_lib.load().pb200_grad_sqnorm(grad.data_ptr(), grad.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
+    check(lib.pb200_grad_sqnorm(grad.data_ptr(), grad.numel(), hyper.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                stream_ptr()))
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor) -> None:

@@ -183,13 +183,14 @@ class GradBuckets:
 
 
 class Trainer:
-    def __init__(self, cfg: TrainingConfig, task, model, metrics=None, status_mp=None, device: Optional[str] = None):
+    def __init__(self, cfg: TrainingConfig, task, model, metrics=None, status_mp=None, device: Optional[str] = None,
+                 data_parallel: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError('pasero_b200.Trainer needs a CUDA device: the sm_100a kernels have no CPU fallback')
         self.cfg, self.task, self.model = cfg, task, model
         self.device = torch.device(device or f'cuda:{torch.cuda.current_device()}')
         self.dtype = BF16
-        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.distributed = data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dp_size = dist.get_world_size() if self.distributed else 1
         cfg.dp_size = self.dp_size
         self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)

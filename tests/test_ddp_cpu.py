@@ -1,0 +1,86 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: bucket partition of the gradient arena, the
+ready-order driven launches, sum-allreduce semantics with the 1/num_tokens normalisation, and unused-parameter
+flushing. The CUDA kernels are not involved: gradients are filled by hand."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pasero_b200.training import GradBuckets, ParamArena
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+class Tiny(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(64, 96)
+        self.b = torch.nn.Linear(96, 40)
+        self.c = torch.nn.Linear(40, 8)
+        self.unused = torch.nn.Parameter(torch.zeros(24))
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = Tiny().to(torch.bfloat16)
+        arena = ParamArena(model, 'cpu')
+        buckets = GradBuckets(arena, bucket_bytes=8 * 1024)
+        # partition: contiguous, covers the arena, built back to front
+        spans = sorted(buckets.buckets)
+        assert spans[0][0] == 0 and spans[-1][1] == arena.numel
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+        assert buckets.buckets[0][1] == arena.numel and len(buckets.buckets) >= 3
+        # every offset is 16-byte aligned
+        assert all(o % 8 == 0 for o in arena.offsets)
+        # fill rank-dependent grads, fire the hooks in backward (reverse) order, skip the unused parameter
+        buckets.start_step(sync=True)
+        for i in reversed(range(len(arena.params))):
+            if arena.names[i] == 'unused':
+                continue
+            arena.view(arena.grad, i).fill_(float(rank + 1))
+            buckets.param_ready(i)
+        stats = torch.tensor([10.0 * (rank + 1), 5.0, 100.0 + rank, 4.0, 0, 0, 0, 0], dtype=torch.float64)
+        launched_before_finish = list(buckets.launch_order)
+        buckets.finish(stats)
+        expect = float(sum(r + 1 for r in range(world)))
+        for i, name in enumerate(arena.names):
+            g = arena.view(arena.grad, i).float()
+            want = 0.0 if name == 'unused' else expect
+            assert torch.all(g == want), (name, g.unique())
+        assert stats[:4].tolist() == [10.0 * 3, 10.0, 201.0, 8.0]
+        # buckets complete in reverse-layer order (the last bucket holds the last parameters)
+        assert launched_before_finish == sorted(launched_before_finish)
+        # no_sync micro-batch: nothing is reduced
+        buckets.start_step(sync=False)
+        arena.grad.fill_(float(rank))
+        for i in range(len(arena.params)):
+            buckets.param_ready(i)
+        assert buckets.launch_order == [] and torch.all(arena.grad.float() == rank)
+        q.put((rank, 'ok'))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: 'ok', 1: 'ok'}, results
