@@ -131,8 +131,9 @@ class GradBuckets:
             self.sizes[b] += 1
         self.enabled = True
         self.launch_order = []
-        for i, p in enumerate(arena.params):   # plain-autograd path (DirectGrads calls param_ready itself)
-            p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i))
+        self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
+        for i, p in enumerate(arena.params):
+            p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i) if self.use_autograd_hooks else None)
 
     def param_ready(self, i: int) -> None:
         """Parameter i's gradient for this micro-batch is complete; launch its bucket when it is the last one."""
@@ -207,6 +208,8 @@ class Trainer:
         self.direct = ops.DirectGrads({id(p): self.arena.view(self.arena.grad, i) for i, p in enumerate(self.arena.params)},
                                       on_ready)
         ops.DirectGrads.active = self.direct
+        if self.buckets is not None:
+            self.buckets.use_autograd_hooks = False
         self.scheduler = LRScheduler(cfg)
         self.optimizer_steps = 0     # Adam's state['step']
         self.steps = 0
