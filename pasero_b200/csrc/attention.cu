@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "../../include/pasero_b200.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace pb200 {
 
 static constexpr int HD = 64;      // head dim
@@ -394,6 +397,24 @@ static AttnParams to_dev(const pb200_attn_params* q) {
     return p;
 }
 
+// tcgen05 path (attention_tc.cu)
+bool attn_tc_supported(const pb200_attn_params* q, bool backward);
+int attn_fwd_tc(const pb200_attn_params* q, cudaStream_t stream, bool p_in_tmem);
+int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream);
+
+// PB200_ATTN selects the kernel family for experiments: "hmma" forces the mma.sync kernels, "tc_ss" the tcgen05
+// forward with P staged in shared memory; default = tcgen05 (P kept in TMEM) whenever the shape fits.
+static int attn_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("PB200_ATTN");
+        mode = 0;
+        if (e && !strcmp(e, "hmma")) mode = 1;
+        else if (e && !strcmp(e, "tc_ss")) mode = 2;
+    }
+    return mode;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -402,6 +423,7 @@ extern "C" int pb200_attention_fwd(const pb200_attn_params* q, void* stream_) {
     if (int rc = check_attn(q)) return rc;
     if (q->B == 0 || q->Lq == 0) return 0;
     PB_CHECK(q->q && q->k && q->v && q->o, "attention_fwd: null tensor");
+    if (attn_mode() != 1 && attn_tc_supported(q, false)) return attn_fwd_tc(q, (cudaStream_t)stream_, attn_mode() != 2);
     const AttnParams p = to_dev(q);
     dim3 grid((p.Lq + BLK - 1) / BLK, p.H, p.B);
     attn_fwd_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream_>>>(p);
@@ -415,6 +437,7 @@ extern "C" int pb200_attention_bwd(const pb200_attn_params* q, void* stream_) {
     PB_CHECK(q->q && q->k && q->v && q->o && q->dout && q->lse && q->delta && q->dq && q->dk && q->dv,
              "attention_bwd: null tensor");
     PB_CHECK(q->lddo % 8 == 0 && q->lddq % 8 == 0 && q->lddk % 8 == 0 && q->lddv % 8 == 0, "attention strides must be multiples of 8");
+    if (attn_mode() != 1 && attn_tc_supported(q, true)) return attn_bwd_tc(q, (cudaStream_t)stream_);
     const AttnParams p = to_dev(q);
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long warps = (long long)p.B * p.H * p.Lq;

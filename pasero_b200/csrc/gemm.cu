@@ -12,6 +12,7 @@
 // reference (pasero/models/modules.py:610-615,737,829-834,935-947; transformer.py:999-1019).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 #include "../../include/pasero_b200.h"
 
 #include <mutex>
@@ -508,8 +509,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // Tensor map over a bf16 matrix stored as `rows` x `cols` (cols contiguous), `ld` elements between
 // rows, `batch` slices `batch_stride` elements apart; box = box_cols x box_rows x 1, SWIZZLE_128B.
-static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
-                     long long batch, long long batch_stride, int box_cols, int box_rows, bool fp32 = false) {
+int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+              long long batch, long long batch_stride, int box_cols, int box_rows, bool fp32) {
     EncodeTiledFn enc = get_encode_fn();
     PB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     // The driver-level encode needs a context current on THIS thread. PyTorch's autograd worker threads skip

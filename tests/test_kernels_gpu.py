@@ -117,7 +117,10 @@ def _attn_ref(q, k, v, kv_len, causal, scale):
 
 @pytest.mark.parametrize('B,H,Lq,Lk,causal,masked', [
     (2, 2, 64, 64, False, False), (3, 8, 250, 250, False, True), (3, 8, 48, 250, False, True),
-    (4, 8, 48, 48, True, False), (2, 4, 130, 130, True, False), (2, 2, 1, 77, False, True)])
+    (4, 8, 48, 48, True, False), (2, 4, 130, 130, True, False), (2, 2, 1, 77, False, True),
+    (2, 2, 200, 256, False, True), (2, 3, 256, 256, True, False), (2, 2, 17, 33, False, True),
+    (1, 2, 300, 200, False, True),      # tcgen05 forward, mma.sync backward (Lq > 256)
+    (2, 2, 100, 300, False, True), (1, 2, 320, 320, True, False)])   # Lk > 256: online-softmax mma.sync kernels
 def test_attention(B, H, Lq, Lk, causal, masked):
     k = _k()
     D = H * 64

@@ -14,13 +14,17 @@ _flush = None
 
 
 def timeit(fn, iters=20, warmup=5, flush=True):
+    """Median device time of fn() over `iters` launches. The GPU is kept busy (a long spin kernel) while the host
+    enqueues every iteration, so the events bracket the kernels themselves and not the host's launch path; a 256 MB
+    write between iterations evicts the 126 MB L2."""
     global _flush
     if _flush is None:
         _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    ts = []
+    torch.cuda._sleep(int(0.05 * 1.9e9))
+    evs = []
     for _ in range(iters):
         if flush:
             _flush.zero_()
@@ -28,15 +32,38 @@ def timeit(fn, iters=20, warmup=5, flush=True):
         s.record()
         fn()
         e.record()
-        torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
-    ts.sort()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in evs)
     return ts[len(ts) // 2]
+
+
+def attn(out, dev):
+    # attention
+    for (Bq, H, Lq, Lk, causal) in [(64, 8, 250, 250, False), (64, 8, 48, 48, True), (64, 8, 48, 250, False)]:
+        q = torch.randn(Bq * Lq, H * 64, device=dev).to(BF16)
+        kv = torch.randn(Bq * Lk, 2 * H * 64, device=dev).to(BF16)
+        kl = torch.full((Bq,), Lk, device=dev, dtype=torch.int32)
+        fl = 4.0 * Bq * H * Lq * Lk * 64 * (0.5 if causal else 1)
+        t = timeit(lambda: k.attention_fwd(q, kv[:, :H * 64], kv[:, H * 64:], Bq, H, Lq, Lk, None if causal else kl, causal, 0.125))
+        out[f'attn fwd {Bq}x{H}x{Lq}x{Lk}'] = (t, fl / t / 1e9)
+        o, lse = k.attention_fwd(q, kv[:, :H * 64], kv[:, H * 64:], Bq, H, Lq, Lk, None if causal else kl, causal, 0.125)
+        do = torch.randn_like(o)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        t = timeit(lambda: k.attention_bwd(do, q, kv[:, :H * 64], kv[:, H * 64:], o, lse, Bq, H, Lq, Lk, None if causal else kl,
+                                           causal, 0.125, dq, dkv[:, :H * 64], dkv[:, H * 64:]))
+        out[f'attn bwd {Bq}x{H}x{Lq}x{Lk}'] = (t, 2.5 * fl / t / 1e9)
+    for name, (t, rate) in out.items():
+        if name.startswith('attn'):
+            print(f'{name:40s} {t * 1000:10.1f} us   {rate:10.1f} TFLOP/s')
 
 
 def main():
     out = {}
     dev = 'cuda'
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == 'attn':
+        return attn(out, dev)
     # GEMM shapes of config 2 (M = 64 * 250 = 16000 encoder rows)
     for (M, N, K) in [(16000, 512, 512), (16000, 1536, 512), (16000, 2048, 512), (16000, 512, 2048), (31936, 1024, 400),
                       (16000, 1024, 2560), (3072, 8032, 512), (8192, 8192, 8192)]:
@@ -65,20 +92,7 @@ def main():
     out['fbank+cmvn 64x160000'] = (t, nbytes / t / 1e6)
     t = timeit(lambda: k.fbank_cmvn(pcm, so, fo, B, F, B * F, cmvn=False))
     out['fbank raw 64x160000'] = (t, nbytes / t / 1e6)
-    # attention
-    for (Bq, H, Lq, Lk, causal) in [(64, 8, 250, 250, False), (64, 8, 48, 48, True), (64, 8, 48, 250, False)]:
-        q = torch.randn(Bq * Lq, H * 64, device=dev).to(BF16)
-        kv = torch.randn(Bq * Lk, 2 * H * 64, device=dev).to(BF16)
-        kl = torch.full((Bq,), Lk, device=dev, dtype=torch.int32)
-        fl = 4.0 * Bq * H * Lq * Lk * 64 * (0.5 if causal else 1)
-        t = timeit(lambda: k.attention_fwd(q, kv[:, :H * 64], kv[:, H * 64:], Bq, H, Lq, Lk, None if causal else kl, causal, 0.125))
-        out[f'attn fwd {Bq}x{H}x{Lq}x{Lk}'] = (t, fl / t / 1e9)
-        o, lse = k.attention_fwd(q, kv[:, :H * 64], kv[:, H * 64:], Bq, H, Lq, Lk, None if causal else kl, causal, 0.125)
-        do = torch.randn_like(o)
-        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
-        t = timeit(lambda: k.attention_bwd(do, q, kv[:, :H * 64], kv[:, H * 64:], o, lse, Bq, H, Lq, Lk, None if causal else kl,
-                                           causal, 0.125, dq, dkv[:, :H * 64], dkv[:, H * 64:]))
-        out[f'attn bwd {Bq}x{H}x{Lq}x{Lk}'] = (t, 2.5 * fl / t / 1e9)
+    attn(out, dev)
     # LN, CE
     M, D = 16000, 512
     x, r = torch.randn(M, D, device=dev).to(BF16), torch.randn(M, D, device=dev).to(BF16)
