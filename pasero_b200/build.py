@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, 'libpasero_b200.so')
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v',
-]
+] + os.environ.get('PB200_NVCC_EXTRA', '').split()
 
 
 def _nvcc() -> str:

@@ -25,7 +25,7 @@
 namespace pb200 {
 
 static constexpr float LOG2E_F = 1.4426950408889634f;
-static constexpr int TC_THREADS = 160;   // 4 softmax/epilogue warps + 1 TMA/MMA warp
+static constexpr int TC_THREADS = 288;   // 8 softmax/epilogue warps + 1 TMA/MMA warp
 
 struct AttnTcDev {
     bf16* o; float* lse; const int* kv_len;
@@ -40,6 +40,15 @@ struct AttnTcDev {
     long long lddq, lddk, lddv;
 };
 
+// Optional in-kernel timeline (build with -DPB_ATTN_TIMING): per CTA 16 slots of clock64() at the phase boundaries of
+// the MMA warp (slots 0-7) and of softmax warp 0 (slots 8-13), slot 14 = %globaltimer at entry, slot 15 = SM id.
+#ifdef PB_ATTN_TIMING
+__device__ long long g_attn_t[4096 * 16];
+#define TSTAMP(slot) do { if (lane == 0 && cta_lin < 4096) g_attn_t[cta_lin * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TSTAMP(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint64_t kdesc(const uint8_t* base, int k16) {           // K-major operand, k-step of 16
     return ptx::make_smem_desc_sw128(ptx::smem_u32(base) + k16 * 32, 16, 1024);
 }
@@ -47,18 +56,41 @@ __device__ __forceinline__ uint64_t mndesc(const uint8_t* base, int k16, uint32_
     return ptx::make_smem_desc_sw128(ptx::smem_u32(base) + k16 * 2048, lbo, 1024);
 }
 
+// The single MMA-issuing thread is latency-bound on its own instruction stream (measured: ~100 cycles per tcgen05.mma
+// with descriptors rebuilt inside a rolled loop), so the issue loops below are unrolled and carry each descriptor as a
+// loop-invariant hi word plus a lo word that takes one 32-bit add per k-step (the 14-bit start-address field counts
+// 16-byte units and cannot carry: shared-memory addresses stay below 256 KB).
+__device__ __forceinline__ uint32_t lo32(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t hi32(uint64_t d) { return (uint32_t)(d >> 32); }
+// 16-byte units from the start of a K-major operand (64-column blocks of 16 KB = 128 rows x 128 B) to k-step kk
+__device__ __forceinline__ constexpr uint32_t kstep16(int kk) { return (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2); }
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
+// Eight softmax warps: warps w and w + 4 own the same 32 TMEM lanes (query rows) and split the key columns in two
+// halves, so that every scheduler has two (four with two CTAs per SM) warps to issue from.
+// TMEM columns (P in TMEM): S [0,256); after the softmax: P(keys 0..127) [0,64) | O_even [64,128) | P(keys 128..255)
+// [128,192) | O_odd [192,256) — each warp writes its packed P over S columns it has itself already consumed.
+// TMEM columns (P in shared memory): S [0,256) | O_even [256,320) | O_odd [320,384).
+// O = P V is accumulated in two halves (even / odd 16-key steps): back-to-back tcgen05.mma into ONE accumulator
+// serialise on its ~100-cycle latency when N is only 64 (measured), two accumulators keep the pipe busy.
 template <bool P_TMEM>
 struct FwdCfg {
     static constexpr int Q_BYTES = 128 * 128, KV_BYTES = 256 * 128, P_BYTES = P_TMEM ? 0 : 128 * 512;
-    static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + P_BYTES + 1024 /*align*/ + 64 /*barriers*/;
+    static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + P_BYTES + 2 * 2 * 128 * 4 + 1024 /*align*/ + 64 /*barriers*/;
     static constexpr int TMEM_COLS = P_TMEM ? 256 : 512;
-    static constexpr int O_COL = P_TMEM ? 128 : 256;
+    static constexpr int O_COL = P_TMEM ? 64 : 256;
+    static constexpr int O2_COL = P_TMEM ? 192 : 320;
 };
 
-template <bool P_TMEM>
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool P_TMEM, bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, P_TMEM ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const AttnTcDev p) {
@@ -69,7 +101,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     uint8_t* sK = sQ + Cfg::Q_BYTES;
     uint8_t* sV = sK + Cfg::KV_BYTES;
     uint8_t* sP = sV + Cfg::KV_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+    float* sMax = reinterpret_cast<float*>(sP + Cfg::P_BYTES);   // [2][128] per column half
+    float* sSum = sMax + 256;                                    // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);
     uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_o = bars + 3;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
@@ -77,14 +111,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
     const int coff = p.Lk - p.Lq;   // causal: key j visible to query i iff j <= i + coff
-    int kv_hi = p.causal ? min(kvlen, q0 + 128 + coff) : kvlen;
+    int kv_hi = CAUSAL ? min(kvlen, q0 + 128 + coff) : kvlen;
     kv_hi = max(kv_hi, 1);
     const int n1 = min(((kv_hi + 15) >> 4) << 4, p.kv_box);   // keys covered by the MMAs (multiple of 16)
+#ifdef PB_ATTN_TIMING
+    const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (warp == 8 && lane == 0 && cta_lin < 4096) {
+        unsigned long long gt; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_t[cta_lin * 16 + 14] = (long long)gt; g_attn_t[cta_lin * 16 + 15] = smid;
+    }
+    if (warp == 8) TSTAMP(0);
+#endif
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             ptx::prefetch_tmap(&tmq); ptx::prefetch_tmap(&tmk); ptx::prefetch_tmap(&tmv);
-            ptx::mbar_init(bar_load, 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 128); ptx::mbar_init(bar_o, 1);
+            ptx::mbar_init(bar_load, 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_o, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -95,69 +139,111 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + Cfg::O_COL;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + Cfg::O_COL, tmem_o2 = tmem_base + Cfg::O2_COL;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
+            TSTAMP(1);
             ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)(128 + 2 * p.kv_box) * 128u);
             ptx::tma_load_3d(&tmq, bar_load, sQ, h * 64, q0, b);
             ptx::tma_load_3d(&tmk, bar_load, sK, h * 64, 0, b);
             ptx::tma_load_3d(&tmv, bar_load, sV, h * 64, 0, b);
             ptx::mbar_wait(bar_load, 0);
             ptx::tc_fence_after();
+            TSTAMP(2);
             const uint32_t idesc1 = ptx::make_idesc_bf16(128, n1, false, false);
+            const uint64_t qd = kdesc(sQ, 0), kd = kdesc(sK, 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem_s, kdesc(sQ, k), kdesc(sK, k), idesc1, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_lh(tmem_s, lo32(qd) + 2 * k, hi32(qd), lo32(kd) + 2 * k, hi32(kd), idesc1, k > 0 ? 1u : 0u);
             ptx::umma_commit(bar_s);
+            TSTAMP(3);
             ptx::mbar_wait(bar_p, 0);
             ptx::tc_fence_after();
+            TSTAMP(4);
             const uint32_t idesc2 = ptx::make_idesc_bf16(128, 64, false, true);
             const int ksteps = n1 >> 4;
-            for (int kk = 0; kk < ksteps; ++kk) {
-                const uint64_t bd = mndesc(sV, kk, 8192);
-                if (P_TMEM) ptx::umma_bf16_ts(tmem_o, tmem_s + kk * 8, bd, idesc2, kk > 0 ? 1u : 0u);
-                else ptx::umma_bf16(tmem_o, kdesc(sP + (kk >> 2) * 16384, kk & 3), bd, idesc2, kk > 0 ? 1u : 0u);
+            const uint64_t vd = mndesc(sV, 0, 8192), pd = kdesc(sP, 0);
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                if (kk < ksteps) {
+                    // packed P of keys [0,128) sits at columns [0,64), of keys [128,256) at columns [128,192)
+                    const uint32_t acc = (kk & 1) ? tmem_o2 : tmem_o;
+                    if (P_TMEM) ptx::umma_bf16_ts_lh(acc, tmem_s + (kk >> 3) * 128 + (kk & 7) * 8, lo32(vd) + 128 * kk, hi32(vd), idesc2, kk > 1 ? 1u : 0u);
+                    else ptx::umma_bf16_lh(acc, lo32(pd) + kstep16(kk), hi32(pd), lo32(vd) + 128 * kk, hi32(vd), idesc2, kk > 1 ? 1u : 0u);
+                }
             }
             ptx::umma_commit(bar_o);
+            TSTAMP(5);
         }
     } else {
-        const int row = warp * 32 + lane;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
         const int qrow = q0 + row;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        const int lim = p.causal ? min(kvlen, qrow + coff + 1) : kvlen;   // keys [0, lim) are visible to this row
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const int lim = CAUSAL ? min(kvlen, qrow + coff + 1) : kvlen;   // keys [0, lim) are visible to this row
+        const int lim_lo = CAUSAL ? __shfl_sync(0xffffffffu, lim, 0) : lim;   // smallest lim of this warp's rows
         const float sl2 = p.scale * LOG2E_F;
         const int nch = (n1 + 31) >> 5;
+        const int c_begin = half * 4, c_end = min(nch, half * 4 + 4);   // this warp's 32-key chunks
+        if (warp == 0) TSTAMP(8);
         ptx::mbar_wait(bar_s, 0);
         ptx::tc_fence_after();
+        if (warp == 0) TSTAMP(9);
         float m = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
             ptx::tmem_ld_wait();
+            if (c * 32 + 32 <= lim_lo) {   // warp-uniform: whole chunk visible to every row
+                float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < lim) m = fmaxf(m, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(v[j])); m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[j + 2])); m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                }
+                m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < lim) m = fmaxf(m, __uint_as_float(v[j]));
+            }
         }
+        sMax[half * 128 + row] = m;
+        ptx::bar_sync(1, 256);
+        if (warp == 0) TSTAMP(10);
+        m = fmaxf(m, sMax[(half ^ 1) * 128 + row]);
         const float m_use = (m == -INFINITY) ? 0.f : m;
         const float msc = m_use * sl2;
-        float sum = 0.f;
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
             ptx::tmem_ld_wait();
             uint32_t pk[16];
+            if (c * 32 + 32 <= lim_lo) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = c * 32 + 2 * j;
-                const float p0 = col < lim ? exp2f(fmaf(__uint_as_float(v[2 * j]), sl2, -msc)) : 0.f;
-                const float p1 = col + 1 < lim ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc)) : 0.f;
-                sum += p0 + p1;
-                pk[j] = pack_bf16x2(p0, p1);
+                for (int j = 0; j < 16; ++j) {
+                    const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc));
+                    const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc));
+                    sum0 += p0; sum1 += p1;
+                    pk[j] = pack_bf16x2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c * 32 + 2 * j;
+                    const float p0 = col < lim ? ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc)) : 0.f;
+                    const float p1 = col + 1 < lim ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc)) : 0.f;
+                    sum0 += p0; sum1 += p1;
+                    pk[j] = pack_bf16x2(p0, p1);
+                }
             }
             if (P_TMEM) {
-                ptx::tmem_st_32x16(tmem_s + lane_base + c * 16, pk);   // in place: columns already consumed above
+                // in place, inside the S columns this warp has already consumed (chunk c -> 16 columns)
+                ptx::tmem_st_32x16(tmem_s + lane_base + half * 128 + (c - c_begin) * 16, pk);
             } else {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -167,39 +253,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
             }
         }
+        const float psum = sum0 + sum1;
+        sSum[half * 128 + row] = psum;
         if (P_TMEM) ptx::tmem_st_wait(); else ptx::fence_proxy_async();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar_p);
+        if (warp == 0) TSTAMP(11);
+        ptx::bar_sync(1, 256);
+        const float sum = psum + sSum[(half ^ 1) * 128 + row];
 
         ptx::mbar_wait(bar_o, 0);
         ptx::tc_fence_after();
+        if (warp == 0) TSTAMP(12);
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        bf16* orow = p.o + ((long long)b * p.Lq + qrow) * p.ldo + h * 64;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
+        bf16* orow = p.o + ((long long)b * p.Lq + qrow) * p.ldo + h * 64 + half * 32;   // this warp: 32 of the 64 columns
+        {
+            uint32_t v[32], w[32];
             ptx::tmem_ld_32x32(tmem_o + lane_base + half * 32, v);
+            if (n1 > 16) ptx::tmem_ld_32x32(tmem_o2 + lane_base + half * 32, w);   // warp-uniform: odd steps exist
             ptx::tmem_ld_wait();
             if (qrow < p.Lq) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + (n1 > 16 ? __uint_as_float(w[j]) : 0.f)) * inv;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 ov;
-                    ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
-                    ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
-                    ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
-                    ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + half * 32 + g * 8) = ov;
+                    ov.x = pack_bf16x2(f[8 * g], f[8 * g + 1]); ov.y = pack_bf16x2(f[8 * g + 2], f[8 * g + 3]);
+                    ov.z = pack_bf16x2(f[8 * g + 4], f[8 * g + 5]); ov.w = pack_bf16x2(f[8 * g + 6], f[8 * g + 7]);
+                    *reinterpret_cast<uint4*>(orow + g * 8) = ov;
                 }
             }
         }
-        if (p.lse && qrow < p.Lq)
+        if (half == 0 && p.lse && qrow < p.Lq)
             p.lse[((long long)b * p.H + h) * p.Lq + qrow] = sum > 0.f ? m_use * p.scale + logf(sum) : -INFINITY;
         ptx::tc_fence_before();
+        if (warp == 0) TSTAMP(13);
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        TSTAMP(6);
     }
 }
 
@@ -213,6 +308,7 @@ struct BwdCfg {
     // TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ chunk i [384 + 64 i, ...)
 };
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
@@ -228,19 +324,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     float* sLse = reinterpret_cast<float*>(sdST + BwdCfg::PT);
     float* sDelta = sLse + 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
-    uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_acc = bars + 3;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_acc = bars + 3, *bar_load2 = bars + 4;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
     const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
     const int coff = p.Lk - p.Lq;
     const int ni = (p.q_box + 127) >> 7, nj = (p.kv_box + 127) >> 7;
+#ifdef PB_ATTN_TIMING
+    const int cta_lin = blockIdx.x + gridDim.x * blockIdx.y;
+    if (warp == 8 && lane == 0 && cta_lin < 4096) {
+        unsigned long long gt; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_t[cta_lin * 16 + 14] = (long long)gt; g_attn_t[cta_lin * 16 + 15] = smid;
+    }
+    if (warp == 8) TSTAMP(0);
+#endif
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             ptx::prefetch_tmap(&tmq); ptx::prefetch_tmap(&tmk); ptx::prefetch_tmap(&tmv); ptx::prefetch_tmap(&tmdo);
-            ptx::mbar_init(bar_load, 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 128); ptx::mbar_init(bar_acc, 1);
+            ptx::mbar_init(bar_load, 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_acc, 1);
+            ptx::mbar_init(bar_load2, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -254,15 +361,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                    t_dq = tmem_base + 384;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)(2 * p.q_box + 2 * p.kv_box) * 128u);
+            // K and Q first: the S^T chain of the first iteration starts while V and dO are still in flight
+            ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)(p.q_box + p.kv_box) * 128u);
             ptx::tma_load_3d(&tmk, bar_load, sK, h * 64, 0, b);
             ptx::tma_load_3d(&tmq, bar_load, sQ, h * 64, 0, b);
-            ptx::tma_load_3d(&tmv, bar_load, sV, h * 64, 0, b);
-            ptx::tma_load_3d(&tmdo, bar_load, sdO, h * 64, 0, b);
+            ptx::mbar_arrive_expect_tx(bar_load2, (uint32_t)(p.q_box + p.kv_box) * 128u);
+            ptx::tma_load_3d(&tmv, bar_load2, sV, h * 64, 0, b);
+            ptx::tma_load_3d(&tmdo, bar_load2, sdO, h * 64, 0, b);
+            TSTAMP(1);
             ptx::mbar_wait(bar_load, 0);
             ptx::tc_fence_after();
+            TSTAMP(2);
             const uint32_t idesc_cd = ptx::make_idesc_bf16(128, 64, false, true);
             const uint32_t idesc_e = ptx::make_idesc_bf16(128, 64, true, true);
             int it = 0;
@@ -271,36 +382,64 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 for (int i = 0; i < ni; ++i, ++it) {
                     const int nq = min(128, p.q_box - 128 * i);     // query columns of this chunk inside the box
                     const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
+                    // S^T = K_j Q_i^T and dP^T = V_j dO_i^T. Independent chains are interleaved step by step: consecutive
+                    // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
+                    const uint64_t kd = kdesc(sK + j * 16384, 0), qd = kdesc(sQ + i * 16384, 0);
+                    const uint64_t vd = kdesc(sV + j * 16384, 0), dod = kdesc(sdO + i * 16384, 0);
+                    if (it == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // S^T = K_j Q_i^T
-                        ptx::umma_bf16(t_s, kdesc(sK + j * 16384, k), kdesc(sQ + i * 16384, k), idesc_ab, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                        ptx::mbar_wait(bar_load2, 0);
+                        ptx::tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // dP^T = V_j dO_i^T
-                        ptx::umma_bf16(t_dp, kdesc(sV + j * 16384, k), kdesc(sdO + i * 16384, k), idesc_ab, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                            ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                        }
+                    }
                     ptx::umma_commit(bar_s);
+                    if (it == 0) TSTAMP(3);
                     ptx::mbar_wait(bar_p, it & 1);
                     ptx::tc_fence_after();
-                    const int qsteps = nq >> 4;
-                    for (int kk = 0; kk < qsteps; ++kk)   // dV_j += P^T dO_i
-                        ptx::umma_bf16(t_dv, kdesc(sPT + (kk >> 2) * 16384, kk & 3), mndesc(sdO + i * 16384, kk, 8192), idesc_cd,
-                                       (i > 0 || kk > 0) ? 1u : 0u);
-                    for (int kk = 0; kk < qsteps; ++kk)   // dK_j += dS^T Q_i
-                        ptx::umma_bf16(t_dk, kdesc(sdST + (kk >> 2) * 16384, kk & 3), mndesc(sQ + i * 16384, kk, 8192), idesc_cd,
-                                       (i > 0 || kk > 0) ? 1u : 0u);
-                    const int ksteps = kc >> 4;
-                    for (int kk = 0; kk < ksteps; ++kk)   // dQ_i += dS K_j   (A = dS^T read MN-major)
-                        ptx::umma_bf16(t_dq + 64 * i, mndesc(sdST, kk, 16384), mndesc(sK + j * 16384, kk, 8192), idesc_e,
-                                       (j > 0 || kk > 0) ? 1u : 0u);
+                    if (it == 0) TSTAMP(4);
+                    const int qsteps = nq >> 4, ksteps = kc >> 4;
+                    const uint64_t ptd = kdesc(sPT, 0), dstd = kdesc(sdST, 0), dst_mn = mndesc(sdST, 0, 16384);
+                    const uint64_t do_mn = mndesc(sdO + i * 16384, 0, 8192), q_mn = mndesc(sQ + i * 16384, 0, 8192);
+                    const uint64_t k_mn = mndesc(sK + j * 16384, 0, 8192);
+                    const uint32_t acc_i = i > 0 ? 1u : 0u, acc_j = j > 0 ? 1u : 0u;
+                    const uint32_t t_dqi = t_dq + 64 * i;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {   // the three chains interleaved
+                        if (kk < qsteps) {
+                            // dV_j += P^T dO_i ; dK_j += dS^T Q_i
+                            ptx::umma_bf16_lh(t_dv, lo32(ptd) + kstep16(kk), hi32(ptd), lo32(do_mn) + 128 * kk, hi32(do_mn), idesc_cd,
+                                              kk > 0 ? 1u : acc_i);
+                            ptx::umma_bf16_lh(t_dk, lo32(dstd) + kstep16(kk), hi32(dstd), lo32(q_mn) + 128 * kk, hi32(q_mn), idesc_cd,
+                                              kk > 0 ? 1u : acc_i);
+                        }
+                        if (kk < ksteps)   // dQ_i += dS K_j   (A = dS^T read MN-major)
+                            ptx::umma_bf16_lh(t_dqi, lo32(dst_mn) + 128 * kk, hi32(dst_mn), lo32(k_mn) + 128 * kk, hi32(k_mn), idesc_e,
+                                              kk > 0 ? 1u : acc_j);
+                    }
                     ptx::umma_commit(bar_acc);
+                    if (it == 0) TSTAMP(5);
                 }
             }
+            TSTAMP(6);
         }
     } else {
-        const int t = warp * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        // warps w and w + 4 own the same 32 key rows (TMEM lanes) and split the query columns / output columns
+        const int quarter = warp & 3, half = warp >> 2;
+        const int t = quarter * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        // log-sum-exp (in log2 units) and delta = rowsum(dO o O) of every query row, while the TMA loads are in flight
-        for (int r = t; r < 256; r += 128) {
+        {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the TMA loads fly
+            const int r = threadIdx.x;   // 0..255
             float l2 = INFINITY, dl = 0.f;
             if (r < p.Lq) {
                 l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + r] * LOG2E_F;
@@ -319,72 +458,84 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             }
             sLse[r] = l2; sDelta[r] = dl;
         }
-        ptx::bar_sync(1, 128);
+        ptx::bar_sync(1, 256);
+        if (warp == 0) TSTAMP(8);
 
         int it = 0;
         for (int j = 0; j < nj; ++j) {
             const int key = 128 * j + t;
+            const bool rowok = key < kvlen;
             for (int i = 0; i < ni; ++i, ++it) {
                 const int nq = min(128, p.q_box - 128 * i);
                 const int nch = (nq + 31) >> 5;
                 ptx::mbar_wait(bar_s, it & 1);
                 ptx::tc_fence_after();
+                if (warp == 0 && it == 0) TSTAMP(9);
+                if (warp == 0 && it == 1) TSTAMP(11);
 #pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
+                for (int c = half; c < nch; c += 2) {
                     uint32_t s[32], dp[32];
                     ptx::tmem_ld_32x32(t_s + lane_base + c * 32, s);
                     ptx::tmem_ld_32x32(t_dp + lane_base + c * 32, dp);
                     ptx::tmem_ld_wait();
-                    uint32_t pk[16], dk_[16];
                     const int qb = 128 * i + c * 32;
+                    const float4* l4 = reinterpret_cast<const float4*>(sLse + qb);
+                    const float4* d4 = reinterpret_cast<const float4*>(sDelta + qb);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float pv[2], ds[2];
+                    for (int g = 0; g < 4; ++g) {   // 8 queries = one 16-byte chunk of P^T and of dS^T
+                        const float4 la = l4[2 * g], lb = l4[2 * g + 1], da = d4[2 * g], db = d4[2 * g + 1];
+                        const float lv[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+                        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                        float pe[8], ds[8];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int q = qb + 2 * e + u;
-                            const bool ok = key < kvlen && q < p.Lq && (!p.causal || key <= q + coff);
-                            const float pe = exp2f(fmaf(__uint_as_float(s[2 * e + u]), sl2, -sLse[q]));
-                            pv[u] = ok ? pe : 0.f;
-                            ds[u] = ok ? pe * (__uint_as_float(dp[2 * e + u]) - sDelta[q]) : 0.f;
+                        for (int e = 0; e < 8; ++e) {
+                            pe[e] = ex2(fmaf(__uint_as_float(s[8 * g + e]), sl2, -lv[e]));
+                            ds[e] = pe[e] * (__uint_as_float(dp[8 * g + e]) - dv[e]);
+                            if (CAUSAL) {
+                                const bool ok = key <= qb + 8 * g + e + coff;
+                                pe[e] = ok ? pe[e] : 0.f;
+                                ds[e] = ok ? ds[e] : 0.f;
+                            }
                         }
-                        pk[e] = pack_bf16x2(pv[0], pv[1]);
-                        dk_[e] = pack_bf16x2(ds[0], ds[1]);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int c8 = c * 4 + g;   // 16-byte chunk (8 queries) of this key row
+                        uint4 pw, dw;
+                        pw.x = pack_bf16x2(pe[0], pe[1]); pw.y = pack_bf16x2(pe[2], pe[3]);
+                        pw.z = pack_bf16x2(pe[4], pe[5]); pw.w = pack_bf16x2(pe[6], pe[7]);
+                        dw.x = pack_bf16x2(ds[0], ds[1]); dw.y = pack_bf16x2(ds[2], ds[3]);
+                        dw.z = pack_bf16x2(ds[4], ds[5]); dw.w = pack_bf16x2(ds[6], ds[7]);
+                        if (!rowok) { pw = make_uint4(0, 0, 0, 0); dw = make_uint4(0, 0, 0, 0); }   // masked / unloaded key row
+                        const int c8 = c * 4 + g;
                         const int off = (c8 >> 3) * 16384 + t * 128 + (((c8 & 7) ^ (t & 7)) << 4);
-                        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                        *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk_[4 * g], dk_[4 * g + 1], dk_[4 * g + 2], dk_[4 * g + 3]);
+                        *reinterpret_cast<uint4*>(sPT + off) = pw;
+                        *reinterpret_cast<uint4*>(sdST + off) = dw;
                     }
                 }
                 ptx::fence_proxy_async();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(bar_p);
+                if (warp == 0 && it == 0) TSTAMP(10);
+                if (warp == 0 && it == 1) TSTAMP(12);
                 if (i == ni - 1) {   // dV_j and dK_j are complete once this iteration's MMAs retire
                     ptx::mbar_wait(bar_acc, it & 1);
                     ptx::tc_fence_after();
+                    // half 0 drains dV, half 1 drains dK (64 columns each)
+                    bf16* dst = half == 0 ? p.dv + ((long long)b * p.Lk + key) * p.lddv + h * 64
+                                          : p.dk + ((long long)b * p.Lk + key) * p.lddk + h * 64;
+                    const float mul = half == 0 ? 1.0f : p.scale;
+                    const uint32_t src = (half == 0 ? t_dv : t_dk) + lane_base;
 #pragma unroll
-                    for (int which = 0; which < 2; ++which) {
-                        bf16* dst = which == 0 ? p.dv + ((long long)b * p.Lk + key) * p.lddv + h * 64
-                                               : p.dk + ((long long)b * p.Lk + key) * p.lddk + h * 64;
-                        const float mul = which == 0 ? 1.0f : p.scale;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(src + hh * 32, v);
+                        ptx::tmem_ld_wait();
+                        if (key < p.Lk) {
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint32_t v[32];
-                            ptx::tmem_ld_32x32((which == 0 ? t_dv : t_dk) + lane_base + half * 32, v);
-                            ptx::tmem_ld_wait();
-                            if (key < p.Lk) {
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    uint4 ov;
-                                    ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * mul, __uint_as_float(v[8 * g + 1]) * mul);
-                                    ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * mul, __uint_as_float(v[8 * g + 3]) * mul);
-                                    ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * mul, __uint_as_float(v[8 * g + 5]) * mul);
-                                    ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * mul, __uint_as_float(v[8 * g + 7]) * mul);
-                                    *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = ov;
-                                }
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 ov;
+                                ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * mul, __uint_as_float(v[8 * g + 1]) * mul);
+                                ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * mul, __uint_as_float(v[8 * g + 3]) * mul);
+                                ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * mul, __uint_as_float(v[8 * g + 5]) * mul);
+                                ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * mul, __uint_as_float(v[8 * g + 7]) * mul);
+                                *reinterpret_cast<uint4*>(dst + hh * 32 + g * 8) = ov;
                             }
                         }
                     }
@@ -392,34 +543,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
             }
         }
-        // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs)
+        // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs); each warp drains
+        // 32 of the 64 columns of its rows
         for (int i = 0; i < ni; ++i) {
             const int qrow = 128 * i + t;
-            bf16* dst = p.dq + ((long long)b * p.Lq + qrow) * p.lddq + h * 64;
+            bf16* dst = p.dq + ((long long)b * p.Lq + qrow) * p.lddq + h * 64 + half * 32;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
+            ptx::tmem_ld_wait();
+            if (qrow < p.Lq) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
-                ptx::tmem_ld_wait();
-                if (qrow < p.Lq) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 ov;
-                        ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * p.scale, __uint_as_float(v[8 * g + 1]) * p.scale);
-                        ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * p.scale, __uint_as_float(v[8 * g + 3]) * p.scale);
-                        ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * p.scale, __uint_as_float(v[8 * g + 5]) * p.scale);
-                        ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * p.scale, __uint_as_float(v[8 * g + 7]) * p.scale);
-                        *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = ov;
-                    }
+                for (int g = 0; g < 4; ++g) {
+                    uint4 ov;
+                    ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * p.scale, __uint_as_float(v[8 * g + 1]) * p.scale);
+                    ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * p.scale, __uint_as_float(v[8 * g + 3]) * p.scale);
+                    ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * p.scale, __uint_as_float(v[8 * g + 5]) * p.scale);
+                    ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * p.scale, __uint_as_float(v[8 * g + 7]) * p.scale);
+                    *reinterpret_cast<uint4*>(dst + g * 8) = ov;
                 }
             }
         }
         ptx::tc_fence_before();
+        if (warp == 0) TSTAMP(13);
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
+        TSTAMP(7);
     }
 }
 
@@ -443,10 +594,10 @@ static AttnTcDev tc_dev(const pb200_attn_params* q) {
     return p;
 }
 
-template <bool P_TMEM>
+template <bool P_TMEM, bool CAUSAL>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcDev& p,
                       cudaStream_t stream) {
-    auto kern = attn_fwd_tc_kernel<P_TMEM>;
+    auto kern = attn_fwd_tc_kernel<P_TMEM, CAUSAL>;
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<P_TMEM>::SMEM_BYTES));
@@ -465,7 +616,8 @@ int attn_fwd_tc(const pb200_attn_params* q, cudaStream_t stream, bool p_in_tmem)
     if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, 128)) return rc;
     if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, p.kv_box)) return rc;
     if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, p.kv_box)) return rc;
-    return p_in_tmem ? launch_fwd<true>(tq, tk, tv, p, stream) : launch_fwd<false>(tq, tk, tv, p, stream);
+    if (p.causal) return p_in_tmem ? launch_fwd<true, true>(tq, tk, tv, p, stream) : launch_fwd<false, true>(tq, tk, tv, p, stream);
+    return p_in_tmem ? launch_fwd<true, false>(tq, tk, tv, p, stream) : launch_fwd<false, false>(tq, tk, tv, p, stream);
 }
 
 int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
@@ -481,13 +633,23 @@ int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
     if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, p.kv_box)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid(p.H, p.B);
-    attn_bwd_tc_kernel<<<grid, TC_THREADS, BwdCfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+    if (p.causal) attn_bwd_tc_kernel<true><<<grid, TC_THREADS, BwdCfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+    else attn_bwd_tc_kernel<false><<<grid, TC_THREADS, BwdCfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
     PB_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace pb200
+
+#ifdef PB_ATTN_TIMING
+extern "C" int pb200_debug_attn_timing(long long* host_out, int n_ctas) {
+    if (n_ctas > 4096) n_ctas = 4096;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(host_out, pb200::g_attn_t, sizeof(long long) * 16 * n_ctas);
+}
+#endif
