@@ -127,10 +127,13 @@ int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* ga
                              int64_t D, float eps, float p, uint64_t seed, uint64_t offset, const int64_t* offset_base,
                              void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* stream);
 size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
+/* backward: dx / dresidual, dgamma, dbeta and (optional) dbias_lin = column sums of dx, i.e. the bias gradient of the
+ * Linear whose output was `x` (saves a separate pass over dx). accumulate: bit 0 = add into dgamma/dbeta, bit 1 = add
+ * into dbias_lin. */
 int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                              const float* mean, const float* rstd, int64_t M, int64_t D, float p, uint64_t seed,
                              uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx, void* dgamma, void* dbeta,
-                             int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+                             void* dbias_lin, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* column sums of a bf16 [M, N] matrix -> bf16 [N] (bias gradients) */
 size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);

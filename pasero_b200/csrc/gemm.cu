@@ -63,7 +63,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // EPI selects the epilogue at compile time (the generic one carries ~2500 SASS instructions per 64 columns when every
 // option is a run-time flag, which made the kernel epilogue-bound):
 //   -1 generic direct-store path (fp32 out, accumulate, split-K partials, alpha, GELU, residual)
-//    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask      -> staged in smem, written by TMA
+//    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask   5 +residual (bf16, C layout)   -> staged in smem, written by TMA
 //    4 split-K: fp32 partial tile TMA-reduce-added (+=, performed in L2) into one fp32 accumulation buffer
 // CL > 1: thread-block clusters of CL CTAs along M. The CTAs of a cluster work on CL consecutive m-blocks of the same
 // n-block, so they need the same B tile: each CTA fetches 1/CL of it and TMA-multicasts that slice into every CTA's
@@ -280,12 +280,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                         const int colh = col0 + half * 32;
                         // auxiliary operands of this 32-column slab are requested before the TMEM read is waited on
                         uint4 aux_m[4];
-                        if constexpr (EPI == 3) {
+                        if constexpr (EPI == 3 || EPI == 5) {
+                            const bf16* aux = EPI == 3 ? p.relu_mask : p.residual;
+                            const uint32_t fill = EPI == 3 ? 0x3f803f80u : 0u;
 #pragma unroll
                             for (int g8 = 0; g8 < 4; ++g8) {
-                                aux_m[g8] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                                aux_m[g8] = make_uint4(fill, fill, fill, fill);
                                 if (row_ok && colh + g8 * 8 < p.N)
-                                    aux_m[g8] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + coff_row + colh + g8 * 8));
+                                    aux_m[g8] = __ldg(reinterpret_cast<const uint4*>(aux + coff_row + colh + g8 * 8));
                             }
                         }
                         uint32_t v[32];
@@ -316,6 +318,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                                 for (int j = 0; j < 4; ++j) {   // bf16 > 0  <=>  sign bit clear and not +0
                                     if ((int)(mw[j] << 16) <= 0) x[2 * j] = 0.f;
                                     if ((int)(mw[j] & 0xffff0000u) <= 0) x[2 * j + 1] = 0.f;
+                                }
+                            }
+                            if constexpr (EPI == 5) {   // bf16(result) + residual, rounded again: what `a + b` on two bf16 tensors gives
+                                const uint32_t rw[4] = {aux_m[g8].x, aux_m[g8].y, aux_m[g8].z, aux_m[g8].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 r2 = unpack_bf16x2(rw[j]);
+                                    x[2 * j] = round_bf16(x[2 * j]) + r2.x; x[2 * j + 1] = round_bf16(x[2 * j + 1]) + r2.y;
                                 }
                             }
                             uint4 ov;
@@ -631,8 +641,9 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     int epi = -1;
     if (splits > 1) epi = 4;
     else if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
-        (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && q->residual == nullptr && (q->act == 0 || q->act == 1)) {
-        if (q->relu_mask) { if (!q->bias && q->act == 0) epi = 3; }
+        (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && (q->act == 0 || q->act == 1)) {
+        if (q->residual) { if (!q->relu_mask && !q->bias && q->act == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) epi = 5; }
+        else if (q->relu_mask) { if (!q->bias && q->act == 0) epi = 3; }
         else if (q->bias) epi = q->act == 1 ? 2 : 1;
         else if (q->act == 0) epi = 0;
     }
@@ -700,6 +711,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
             case 2: PB_DISPATCH2(BN_, 2); break;                  \
             case 3: PB_DISPATCH2(BN_, 3); break;                  \
             case 4: PB_DISPATCH2(BN_, 4); break;                  \
+            case 5: PB_DISPATCH2(BN_, 5); break;                  \
             default: PB_DISPATCH2(BN_, -1); break;                \
         }                                                         \
     } while (0)

@@ -103,73 +103,105 @@ dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ r
 }
 
 // backward: dsum = LN'(dy) (or dy when no LN) [+ dsum_extra]; dx = dropout'(dsum).
-// dgamma / dbeta partial sums per CTA -> partial[blockIdx][2][D] (fp32), reduced by reduce_partials.
+// Column sums needed by the parameter gradients are accumulated on the way: dgamma = sum dy * xhat, dbeta = sum dy and
+// (optionally) dlin = sum dx, the bias gradient of the Linear whose output fed this block (it would otherwise cost a
+// separate pass over dx). One partial row [3][D] per CTA -> partial[blockIdx], reduced by reduce_partials_multi.
+// One warp per row, 8 warps per CTA, the next row's operands are requested before the current row is processed so
+// that enough bytes are in flight per SM to cover HBM latency.
+static constexpr int LNB_WARPS = 8;
+
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LNB_WARPS * 32, NCH <= 2 ? 2 : 1)
 dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dsum_extra,
                           const bf16* __restrict__ sum, const bf16* __restrict__ gamma,
                           const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D, float p,
                           uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
-                          bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial) {
+                          bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial, int want_lin) {
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
     const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-    float dg[NCH][8], db[NCH][8];
+    float dg[NCH][8], db[NCH][8], dl[NCH][8];
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
+        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; dl[c][j] = 0.f; }
+    float gm[NCH][8];   // gamma of this lane's columns
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = c * 256 + lane * 8;
+        uint4 gv = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        if (gamma && col < D) gv = __ldg(reinterpret_cast<const uint4*>(gamma + col));
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 g2 = unpack_bf16x2(gw[j]); gm[c][2 * j] = g2.x; gm[c][2 * j + 1] = g2.y; }
+    }
 
-    for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-        float g[NCH][8];   // dy * gamma  (or dy)
-        float xh[NCH][8];  // normalised input
-        float s1 = 0.f, s2 = 0.f;
-        const float mu = gamma ? mean[row] : 0.f, rs = gamma ? rstd[row] : 1.f;
+    const int stride = gridDim.x * LNB_WARPS;
+    int row = blockIdx.x * LNB_WARPS + warp;
+    uint4 nd[NCH], ns[NCH];
+    float nmu = 0.f, nrs = 1.f;
+    auto fetch = [&](int r) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = c * 256 + lane * 8;
-            if (col < D) {
-                const long long e = (long long)row * D + col;
-                const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + e));
-                const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
-                if (gamma) {
-                    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sum + e));
-                    const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
-                    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + col));
-                    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 d = unpack_bf16x2(dw[j]);
-                        const float2 sx = unpack_bf16x2(sw[j]);
-                        const float2 gm = unpack_bf16x2(gw[j]);
-                        const float x0 = (sx.x - mu) * rs, x1 = (sx.y - mu) * rs;
-                        xh[c][2 * j] = x0; xh[c][2 * j + 1] = x1;
-                        dg[c][2 * j] += d.x * x0; dg[c][2 * j + 1] += d.y * x1;
-                        db[c][2 * j] += d.x; db[c][2 * j + 1] += d.y;
-                        g[c][2 * j] = d.x * gm.x; g[c][2 * j + 1] = d.y * gm.y;
-                        s1 += g[c][2 * j] + g[c][2 * j + 1];
-                        s2 += g[c][2 * j] * x0 + g[c][2 * j + 1] * x1;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 d = unpack_bf16x2(dw[j]);
-                        g[c][2 * j] = d.x; g[c][2 * j + 1] = d.y;
-                    }
-                }
+            nd[c] = make_uint4(0, 0, 0, 0); ns[c] = make_uint4(0, 0, 0, 0);
+            if (r < M && col < D) {
+                const long long e = (long long)r * D + col;
+                nd[c] = __ldg(reinterpret_cast<const uint4*>(dy + e));
+                if (gamma) ns[c] = __ldg(reinterpret_cast<const uint4*>(sum + e));
             }
         }
-        if (gamma) { s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D; }
+        if (gamma && r < M) { nmu = mean[r]; nrs = rstd[r]; }
+    };
+    fetch(row);
+    for (; row < M; row += stride) {
+        uint4 cd[NCH], cs[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cs[c] = ns[c]; }
+        const float mu = nmu, rs = nrs;
+        fetch(row + stride);
+        float s1 = 0.f, s2 = 0.f;
+        if (gamma) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const uint32_t dw[4] = {cd[c].x, cd[c].y, cd[c].z, cd[c].w};
+                const uint32_t sw[4] = {cs[c].x, cs[c].y, cs[c].z, cs[c].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 d = unpack_bf16x2(dw[j]);
+                    const float2 sx = unpack_bf16x2(sw[j]);
+                    const float x0 = (sx.x - mu) * rs, x1 = (sx.y - mu) * rs;
+                    dg[c][2 * j] += d.x * x0; dg[c][2 * j + 1] += d.y * x1;
+                    db[c][2 * j] += d.x; db[c][2 * j + 1] += d.y;
+                    const float g0 = d.x * gm[c][2 * j], g1 = d.y * gm[c][2 * j + 1];
+                    s1 += g0 + g1;
+                    s2 += g0 * x0 + g1 * x1;
+                }
+            }
+            s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
+        }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = c * 256 + lane * 8;
             if (col < D) {
                 const long long e = (long long)row * D + col;
+                const uint32_t dw[4] = {cd[c].x, cd[c].y, cd[c].z, cd[c].w};
+                const uint32_t sw[4] = {cs[c].x, cs[c].y, cs[c].z, cs[c].w};
                 float ds[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ds[j] = gamma ? rs * (g[c][j] - s1 - xh[c][j] * s2) : g[c][j];
+                for (int j = 0; j < 4; ++j) {
+                    const float2 d = unpack_bf16x2(dw[j]);
+                    if (gamma) {
+                        const float2 sx = unpack_bf16x2(sw[j]);
+                        const float x0 = (sx.x - mu) * rs, x1 = (sx.y - mu) * rs;
+                        ds[2 * j] = rs * (d.x * gm[c][2 * j] - s1 - x0 * s2);
+                        ds[2 * j + 1] = rs * (d.y * gm[c][2 * j + 1] - s1 - x1 * s2);
+                    } else {
+                        ds[2 * j] = d.x; ds[2 * j + 1] = d.y;
+                    }
+                }
                 if (dsum_extra) {
                     const uint4 ev = __ldg(reinterpret_cast<const uint4*>(dsum_extra + e));
                     const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
@@ -183,39 +215,46 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) ow[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
                 if (dresidual) *reinterpret_cast<uint4*>(dresidual + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                if (dx && (dx != dresidual || p > 0.f)) {
-                    if (p > 0.f) {
-                        const uint32_t keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+                if (p > 0.f) {
+                    const uint32_t keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 r = unpack_bf16x2(ow[j]);  // gradient reaching dropout is bf16
-                            const float a = ((keep >> (2 * j)) & 1) ? r.x * keep_scale : 0.f;
-                            const float b = ((keep >> (2 * j + 1)) & 1) ? r.y * keep_scale : 0.f;
-                            ow[j] = pack_bf16x2(a, b);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 r = unpack_bf16x2(ow[j]);  // gradient reaching dropout is bf16
+                        const float a = ((keep >> (2 * j)) & 1) ? r.x * keep_scale : 0.f;
+                        const float b = ((keep >> (2 * j + 1)) & 1) ? r.y * keep_scale : 0.f;
+                        ow[j] = pack_bf16x2(a, b);
                     }
-                    *reinterpret_cast<uint4*>(dx + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+                if (dx && (dx != dresidual || p > 0.f)) *reinterpret_cast<uint4*>(dx + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                if (want_lin) {   // column sums of dx exactly as stored (bf16)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 r = unpack_bf16x2(ow[j]);
+                        dl[c][2 * j] += r.x; dl[c][2 * j + 1] += r.y;
+                    }
                 }
             }
         }
     }
-    if (!gamma || !partial) return;
-    // reduce dgamma/dbeta over the CTA's warps, then one partial row per CTA
-    __shared__ float red[LN_WARPS][2][NCH * 256];
+    if (!partial) return;
+    // CTA-level sum in a fixed warp order (deterministic), then one partial row per CTA
+    __shared__ float red[3][NCH * 256];
+    for (int w = 0; w < LNB_WARPS; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            red[warp][0][c * 256 + lane * 8 + j] = dg[c][j];
-            red[warp][1][c * 256 + lane * 8 + j] = db[c][j];
+                for (int j = 0; j < 8; ++j) {
+                    const int i = c * 256 + lane * 8 + j;
+                    if (w == 0) { red[0][i] = dg[c][j]; red[1][i] = db[c][j]; red[2][i] = dl[c][j]; }
+                    else { red[0][i] += dg[c][j]; red[1][i] += db[c][j]; red[2][i] += dl[c][j]; }
+                }
         }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
         const int which = i / D, col = i % D;
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) a += red[w][which][col];
-        partial[((long long)blockIdx.x * 2 + which) * D + col] = a;
+        partial[((long long)blockIdx.x * 3 + which) * D + col] = red[which][col];
     }
 }
 
@@ -244,6 +283,37 @@ reduce_partials_kernel(const float* __restrict__ partial, int P, long long strid
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += red[r][cx];
         if (accumulate) s += bf16_to_f(out[n]);
+        out[n] = f_to_bf16(s);
+    }
+}
+
+// up to 3 vectors in one launch (blockIdx.y selects): out_k[n] = (acc_k ? out_k[n] : 0) + sum_p partial[p*stride + k*N + n]
+struct ReduceOut3 { bf16* out[3]; int accumulate[3]; };
+__global__ void __launch_bounds__(256)
+reduce_partials_multi_kernel(const float* __restrict__ partial, int P, long long stride, int N, ReduceOut3 o) {
+    bf16* out = o.out[blockIdx.y];
+    if (!out) return;
+    const float* src = partial + (long long)blockIdx.y * N;
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
+    float a = 0.f;
+    if (n < N) {
+        int q = py;
+        for (; q + 24 < P; q += 32) {
+            const float v0 = src[(long long)q * stride + n], v1 = src[(long long)(q + 8) * stride + n];
+            const float v2 = src[(long long)(q + 16) * stride + n], v3 = src[(long long)(q + 24) * stride + n];
+            a += (v0 + v1) + (v2 + v3);
+        }
+        for (; q < P; q += 8) a += src[(long long)q * stride + n];
+    }
+    __shared__ float red[8][33];
+    red[py][cx] = a;
+    __syncthreads();
+    if (py == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][cx];
+        if (o.accumulate[blockIdx.y]) s += bf16_to_f(out[n]);
         out[n] = f_to_bf16(s);
     }
 }
@@ -279,7 +349,7 @@ colsum_kernel(const bf16* __restrict__ x, int M, int N, long long ld, float* __r
 }
 
 static int ln_bwd_grid(int M) {
-    int g = (M + LN_WARPS - 1) / LN_WARPS;
+    int g = (M + LNB_WARPS - 1) / LNB_WARPS;
     const int cap = 2 * num_sms();
     return g < cap ? g : cap;
 }
@@ -299,7 +369,7 @@ static int colsum_splits(long long M, long long N) {
 using namespace pb200;
 
 extern "C" size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D) {
-    return (size_t)ln_bwd_grid((int)M) * 2 * (size_t)D * sizeof(float);
+    return (size_t)ln_bwd_grid((int)M) * 3 * (size_t)D * sizeof(float);
 }
 
 extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
@@ -327,29 +397,32 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
 extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                                         const float* mean, const float* rstd, int64_t M, int64_t D, float p,
                                         uint64_t seed, uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx,
-                                        void* dgamma, void* dbeta, int32_t accumulate, void* workspace,
+                                        void* dgamma, void* dbeta, void* dbias_lin, int32_t accumulate, void* workspace,
                                         size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported", (long long)D);
     const int grid = ln_bwd_grid((int)M);
     float* partial = nullptr;
-    if (gamma && (dgamma || dbeta)) {
+    if ((gamma && (dgamma || dbeta)) || dbias_lin) {
         PB_CHECK(workspace && workspace_bytes >= pb200_ln_bwd_workspace_bytes(M, D), "LN backward workspace too small");
         partial = reinterpret_cast<float*>(workspace);
     }
     const int nch = (int)((D + 255) / 256);
 #define PB_LN_BWD(N_)                                                                                        \
-    dropout_add_ln_bwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                        \
+    dropout_add_ln_bwd_kernel<N_><<<grid, LNB_WARPS * 32, 0, stream>>>(                                       \
         (const bf16*)dy, (const bf16*)dsum_extra, (const bf16*)sum, (const bf16*)gamma, mean, rstd, (int)M,   \
-        (int)D, p, seed, offset, (const long long*)offset_base, (bf16*)dresidual, (bf16*)dx, partial)
+        (int)D, p, seed, offset, (const long long*)offset_base, (bf16*)dresidual, (bf16*)dx, partial,          \
+        dbias_lin != nullptr ? 1 : 0)
     switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();
     if (partial) {
-        const int threads = 256, blocks = (int)((D + 31) / 32);
-        if (dgamma) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial, grid, 2 * D, (int)D, (bf16*)dgamma, accumulate);
-        if (dbeta) reduce_partials_kernel<<<blocks, threads, 0, stream>>>(partial + D, grid, 2 * D, (int)D, (bf16*)dbeta, accumulate);
+        ReduceOut3 o;
+        o.out[0] = gamma ? (bf16*)dgamma : nullptr; o.out[1] = gamma ? (bf16*)dbeta : nullptr; o.out[2] = (bf16*)dbias_lin;
+        o.accumulate[0] = o.accumulate[1] = accumulate & 1; o.accumulate[2] = (accumulate >> 1) & 1;
+        dim3 rgrid((unsigned)((D + 31) / 32), 3);
+        reduce_partials_multi_kernel<<<rgrid, 256, 0, stream>>>(partial, grid, 3 * D, (int)D, o);
         PB_LAUNCH_CHECK();
     }
     return 0;

@@ -86,13 +86,15 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0
 
 
 def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out: Optional[Tensor] = None,
-                 accumulate: bool = False) -> Tensor:
-    """dx[M, K] = dy[M, N] @ w[N, K]  (optionally masked by relu_mask > 0)"""
+                 accumulate: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+    """dx[M, K] = dy[M, N] @ w[N, K]  (optionally masked by relu_mask > 0, or + residual[M, K] in the epilogue:
+    the gradient of the skip connection joins the sub-block's input gradient without a separate add kernel)"""
     M, N = dy.shape
     K = w.shape[1]
     dx = out if out is not None else torch.empty(M, K, dtype=BF16, device=dy.device)
+    assert residual is None or (residual.shape == dx.shape and residual.is_contiguous())
     return gemm_raw(dy.data_ptr(), w.data_ptr(), dx, M, K, N, lda=N, ldb=K, ldc=K, b_mn_major=True,
-                    relu_mask=relu_mask, accumulate=accumulate, split_k=1)
+                    relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1)
 
 
 def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
@@ -162,17 +164,21 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
 
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
-                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False):
+                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False,
+                       dbias_lin: Optional[Tensor] = None, accumulate_lin: bool = False):
+    """dbias_lin (bf16 [D], optional) receives the column sums of dx = the bias gradient of the Linear that produced x."""
     lib = _lib.load()
     M, D = dy.shape
     dev = dy.device
     dx = torch.empty(M, D, dtype=BF16, device=dev)
     dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
-    ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if gamma is not None else None
-    _count(3)
+    need_ws = (gamma is not None and (dgamma is not None or dbeta is not None)) or dbias_lin is not None
+    ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if need_ws else None
+    _count(2 if need_ws else 1)
     check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
                                        p, seed, offset, ptr(RNG_OFFSET_BASE), ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
-                                       int(accumulate), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
+                                       ptr(dbias_lin), int(accumulate) | (int(accumulate_lin) << 1), ptr(ws),
+                                       ws.numel() if ws is not None else 0, stream_ptr()))
     return dx, dres
 
 

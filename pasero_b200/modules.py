@@ -128,6 +128,15 @@ class MultiheadAttention(nn.Module):
                 elif strict:
                     missing_keys.append(key)
 
+    @staticmethod
+    def key_lengths_of(attn_mask: Optional[Tensor]) -> Optional[Tensor]:
+        """(B, S) bool key-padding mask (True = masked, padding at the end of each row) -> int32 (B,) key counts"""
+        if attn_mask is None:
+            return None
+        if attn_mask.dim() != 2:
+            raise NotImplementedError('only (B, S) key-padding masks are supported')
+        return (~attn_mask).sum(dim=1).to(torch.int32)
+
     def forward(self, query: Tensor, key: Tensor, value: Tensor, attn_mask: Optional[Tensor] = None,
                 state: Optional[dict] = None, return_attn: bool = False, key_lengths: Optional[Tensor] = None):
         """query (B, T, D); key/value (B, S, D), value must be the same tensor as key (as everywhere on the ST path).

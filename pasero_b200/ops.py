@@ -207,6 +207,122 @@ class AttentionFn(torch.autograd.Function):
                 None, None, None, None, None, None, None)
 
 
+def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias):
+    """Shared backward of `LN(residual + dropout(x))`: returns (dx, dresidual, dgamma, dbeta, dlin_bias) with the
+    parameter gradients routed through DirectGrads when active (None is returned for those)."""
+    p_gamma, p_beta = params
+    D = dy.shape[1]
+    sg, ag = _sink(p_gamma)
+    sb, ab = _sink(p_beta)
+    sl, al = _sink(lin_bias)
+    dgamma = sg if sg is not None else torch.empty(D, dtype=BF16, device=dy.device)
+    dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
+    dlin = sl if sl is not None else (torch.empty(D, dtype=BF16, device=dy.device) if lin_bias is not None else None)
+    dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
+                                    accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al)
+    return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
+
+
+class AttnSublayerFn(torch.autograd.Function):
+    """Post-norm attention sub-block in one autograd node: LN(x + dropout(MHA(x, key))) (pasero/models/transformer.py
+    :1021-1054, 1246-1289). Compared with AttentionFn followed by DropoutAddLNFn, the backward gets the out-projection
+    bias gradient from the LayerNorm-backward pass and adds the skip-connection gradient in the epilogue of the last
+    dgrad GEMM (no column-sum pass over dy, no separate add kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps):
+        D = H * 64
+        x = _c(x)
+        self_attn = key is None
+        if self_attn:
+            kvq = K.linear_fwd(x, in_w, in_b)
+            k2, v2, q2 = kvq[:, :D], kvq[:, D:2 * D], kvq[:, 2 * D:]
+            key_c = None
+        else:
+            key_c = _c(key)
+            kv = K.linear_fwd(key_c, in_w[:2 * D], in_b[:2 * D])
+            q2 = K.linear_fwd(x, in_w[2 * D:], in_b[2 * D:])
+            k2, v2 = kv[:, :D], kv[:, D:]
+        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
+        y = K.linear_fwd(o, out_w, out_b)
+        seed, offset = DropoutState.next() if p > 0 else (0, 0)
+        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset)
+        ctx.save_for_backward(x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd)
+        ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset)
+        ctx.params = (in_w, in_b, out_w, out_b, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd = ctx.saved_tensors
+        B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset = ctx.dims
+        D = H * 64
+        p_in_w, p_in_b, p_out_w, p_out_b, p_gamma, p_beta = ctx.params
+        dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b)
+        _ready(p_gamma, p_beta)
+        d_o = K.linear_dgrad(dy, out_w)
+        so, a = _sink(p_out_w); d_out_w = _ret(K.linear_wgrad(dy, o, out=so, accumulate=a), so)
+        _ready(p_out_w, p_out_b)
+        sink_w, acc_w = _sink(p_in_w)
+        sink_b, acc_b = _sink(p_in_b)
+        d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
+        d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
+        if self_attn:
+            dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
+                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
+            dx = K.linear_dgrad(dkvq, in_w, residual=dres)
+            K.linear_wgrad(dkvq, x, out=d_in_w, accumulate=acc_w)
+            K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+            dkey = None
+        else:
+            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            dx = K.linear_dgrad(dq, in_w[2 * D:], residual=dres)
+            dkey = K.linear_dgrad(dkv, in_w[:2 * D])
+            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
+            K.linear_wgrad(dq, x, out=d_in_w[2 * D:], accumulate=acc_w)
+            K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
+        _ready(p_in_w, p_in_b)
+        return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta,
+                None, None, None, None, None, None, None, None, None)
+
+
+class FFNSublayerFn(torch.autograd.Function):
+    """Post-norm feed-forward sub-block in one autograd node: LN(x + dropout(fc2(relu(fc1(x))))) (pasero/models/
+    transformer.py:999-1019, 1073-1086); same backward fusions as AttnSublayerFn."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, p, eps):
+        x = _c(x)
+        h = K.linear_fwd(x, w1, b1, act=1)
+        y = K.linear_fwd(h, w2, b2)
+        seed, offset = DropoutState.next() if p > 0 else (0, 0)
+        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset)
+        ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd)
+        ctx.cfg = (p, seed, offset)
+        ctx.params = (w1, b1, w2, b2, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1, w2, h, s, gamma, mean, rstd = ctx.saved_tensors
+        p, seed, offset = ctx.cfg
+        p_w1, p_b1, p_w2, p_b2, p_gamma, p_beta = ctx.params
+        dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2)
+        _ready(p_gamma, p_beta)
+        dh = K.linear_dgrad(dy, w2, relu_mask=h)
+        o, a = _sink(p_w2); dw2 = _ret(K.linear_wgrad(dy, h, out=o, accumulate=a), o)
+        _ready(p_w2, p_b2)
+        dx = K.linear_dgrad(dh, w1, residual=dres)
+        o, a = _sink(p_w1); dw1 = _ret(K.linear_wgrad(dh, x, out=o, accumulate=a), o)
+        o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
+        _ready(p_w1, p_b1)
+        return dx, dw1, db1, dw2, db2, dgamma, dbeta, None, None
+
+
 class DropoutAddLNFn(torch.autograd.Function):
     """y = LayerNorm(residual + dropout(x)) (gamma given) or residual + dropout(x) (gamma None)."""
 
@@ -369,6 +485,23 @@ def dropout_add_ln(x: Tensor, residual: Optional[Tensor], gamma, beta, p: float,
     shape = x.shape
     r2 = residual.reshape(-1, shape[-1]) if residual is not None else None
     return DropoutAddLNFn.apply(x.reshape(-1, shape[-1]), r2, gamma, beta, float(p), float(eps)).view(shape)
+
+
+def attn_sublayer(x: Tensor, key: Optional[Tensor], attn, ln, kv_len, causal: bool, p: float, eps: float) -> Tensor:
+    """LN(x + dropout(attn(x, key, key))) for a `modules.MultiheadAttention` + nn.LayerNorm pair (post-norm)."""
+    B, T, D = x.shape
+    S = T if key is None else key.shape[1]
+    out = AttnSublayerFn.apply(x.reshape(B * T, D), None if key is None else key.reshape(B * S, D), attn.in_proj_weight,
+                               attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias, ln.weight, ln.bias, kv_len,
+                               B, T, S, attn.num_heads, causal, attention_scale(attn.head_dim, attn.scaled), float(p), float(eps))
+    return out.view(B, T, D)
+
+
+def ffn_sublayer(x: Tensor, fc1, fc2, ln, p: float, eps: float) -> Tensor:
+    shape = x.shape
+    out = FFNSublayerFn.apply(x.reshape(-1, shape[-1]), fc1.weight, fc1.bias, fc2.weight, fc2.bias, ln.weight, ln.bias,
+                              float(p), float(eps))
+    return out.view(shape)
 
 
 def attention_scale(head_dim: int, scaled: bool = True) -> float:

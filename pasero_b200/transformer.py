@@ -41,6 +41,11 @@ class TransformerEncoderLayer(nn.Module):
         p = self.dropout_p if self.training else 0.0
         eps = self.cfg.norm_eps
         ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        if not self.prenorm:   # post-norm (the ST default): each sub-block is one fused autograd node
+            x = ops.attn_sublayer(x, None, self.self_attn, ln1, key_lengths if key_lengths is not None else
+                                  self.self_attn.key_lengths_of(padding_mask), False, p, eps)
+            x = ops.ffn_sublayer(x, self.fc1, self.fc2, ln2, p, eps)
+            return x, ({self.name: x} if self.name in return_layers else {})
         residual = x
         if self.prenorm:
             x = ops.dropout_add_ln(x, None, ln1.weight, ln1.bias, 0.0, eps)
@@ -94,6 +99,12 @@ class TransformerDecoderLayer(nn.Module):
             raise NotImplementedError('incremental decoding is outside the training path')
         p = self.dropout_p if self.training else 0.0
         eps = self.cfg.norm_eps
+        if not self.prenorm:
+            x = ops.attn_sublayer(x, None, self.self_attn, self.self_attn_layer_norm, None, True, p, eps)
+            enc_len = encoder_lengths if encoder_lengths is not None else self.encoder_attn.key_lengths_of(encoder_mask)
+            x = ops.attn_sublayer(x, encoder_out, self.encoder_attn, self.encoder_attn_layer_norm, enc_len, False, p, eps)
+            x = ops.ffn_sublayer(x, self.fc1, self.fc2, self.final_layer_norm, p, eps)
+            return x, ({self.name: x} if self.name in return_layers else {})
         x = self._block(x, self.self_attn_layer_norm, lambda h: self.self_attn(h, h, h)[0], p, eps)
         x = self._block(x, self.encoder_attn_layer_norm,
                         lambda h: self.encoder_attn(h, encoder_out, encoder_out, attn_mask=encoder_mask,

@@ -62,6 +62,8 @@ def test_gemm_dgrad_wgrad(M, N, K):
     h = _rand(M, K, seed=6)
     dxm = k.linear_dgrad(dy, w, relu_mask=h)
     _close(dxm, (dy.float() @ w.float()) * (h.float() > 0), 3e-2, 1e-2, 'dgrad+relu mask')
+    dxr = k.linear_dgrad(dy, w, residual=h)     # skip-connection gradient added in the TMA-store epilogue
+    _close(dxr, (dy.float() @ w.float()).to(BF16).float() + h.float(), 3e-2, 1e-2, 'dgrad+residual')
     dw = k.linear_wgrad(dy, x)
     ref = dy.float().T @ x.float()
     _close(dw, ref, 2e-2 * math.sqrt(M / 256), 1e-2, 'wgrad')
@@ -168,6 +170,16 @@ def test_dropout_add_ln(M, D):
     _close(dx, xs.grad, 2e-2, 2e-2, 'ln dx')
     _close(dg, gr.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dgamma')
     _close(db, br.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dbeta')
+    # fused bias gradient of the preceding Linear: column sums of dx; accumulate flags are independent
+    dl = torch.ones(D, dtype=BF16, device='cuda')
+    dg2, db2 = dg.clone(), db.clone()
+    dx2, _ = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, 0.0, 0, 0, True, dg2, db2, accumulate=True, dbias_lin=dl)
+    assert torch.equal(dx2, dx)
+    _close(dl, dx.float().sum(0), 0.05 * math.sqrt(M / 100), 2e-2, 'ln dbias_lin')
+    _close(dg2, 2 * gr.grad, 0.1 * math.sqrt(M / 100), 3e-2, 'ln dgamma accumulate')
+    dl2 = dl.clone()
+    k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, 0.0, 0, 0, True, None, None, dbias_lin=dl2, accumulate_lin=True)
+    _close(dl2, 2 * dx.float().sum(0), 0.1 * math.sqrt(M / 100), 3e-2, 'ln dbias_lin accumulate')
 
 
 def test_dropout_mask_consistency():
