@@ -46,11 +46,15 @@ struct GemmDev {
     float* partial;      // split-K partials [split][Z][M][N] fp32
 };
 
-template <int BN>
+// PAIR: the CTA pair of a 2-CTA cluster works as one tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128
+// rows of A and only HALF of the B tile (the tensor core reads the other half from the peer's shared memory), which cuts
+// the L2 -> SM operand traffic per output tile by a third. The K = 512 GEMMs of this model are bound by exactly that
+// traffic (ncu: ~10 TB/s of TMA loads, the chip-wide L2 limit, with the tensor pipe ~50 % busy).
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 128) ? 6 : 4;
+    static constexpr int STAGES = PAIR ? 6 : ((BN == 128) ? 6 : 4);
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int EPI_BUF_BYTES = 32 * 128;                 // 32 rows x 64 bf16, SWIZZLE_128B
@@ -65,7 +69,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 //   -1 generic direct-store path (fp32 out, accumulate, split-K partials, alpha, GELU, residual)
 //    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask   5 +residual (bf16, C layout)   -> staged in smem, written by TMA
 //    4 split-K: fp32 partial tile TMA-reduce-added (+=, performed in L2) into one fp32 accumulation buffer
-// CL > 1: thread-block clusters of CL CTAs along M. The CTAs of a cluster work on CL consecutive m-blocks of the same
+// CL == 2: CTA pair (see GemmCfg). CL == 4: thread-block clusters of CL CTAs along M with TMA multicast of B: The CTAs of a cluster work on CL consecutive m-blocks of the same
 // n-block, so they need the same B tile: each CTA fetches 1/CL of it and TMA-multicasts that slice into every CTA's
 // shared memory, cutting the L2 -> SM operand traffic of these weight-small GEMMs (B re-read once per m-block) by
 // up to (1 - 1/CL) of the B share.
@@ -73,7 +77,8 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
             const __grid_constant__ CUtensorMap tmc, const GemmDev p) {
-    using Cfg = GemmCfg<BN>;
+    constexpr bool PAIR = (CL == 2);
+    using Cfg = GemmCfg<BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,18 +103,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], CL);   // every CTA of the cluster releases the stage
+            // PAIR: the leader's full barrier collects one arrival per CTA (+ the bytes of both CTAs' loads); one
+            // multicast commit of the pair's MMAs releases the stage in both CTAs
+            ptx::mbar_init(&full_bar[i], PAIR ? 2 : 1);
+            ptx::mbar_init(&empty_bar[i], PAIR ? 1 : CL);   // multicast clusters: every CTA releases the stage
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], 128);
+            ptx::mbar_init(&tmem_empty[i], PAIR ? 8 : 128);   // PAIR: one arrival per epilogue warp of both CTAs (leader's barrier)
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_2sm(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before any remote arrive
@@ -135,13 +142,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     const int zk = p.reduce_batch ? (kb / p.kb_per) : z;
                     const int k0 = (kb % p.kb_per) * BK;
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     const int za = p.a_batched ? zk : 0;
                     const int zb = p.b_batched ? zk : 0;
+                    if constexpr (PAIR) {
+                        // both CTAs' bytes are credited to the leader's barrier
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        if (!A_MN) {
+                            ptx::tma_load_3d_2sm(&tma, &full_bar[stage], sa, k0, m0, za);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                ptx::tma_load_3d_2sm(&tma, &full_bar[stage], sa + j * (BK * 128), m0 + j * 64, k0, za);
+                        }
+                        if (!B_MN) {   // this CTA's BN/2 rows of the B tile
+                            ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sb, k0, n0 + cta_rank * (BN / 2), zb);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j)
+                                ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + cta_rank * (BN / 2) + j * 64, k0, zb);
+                        }
+                        if (cta_rank != 0) ptx::mbar_arrive_remote(&full_bar[stage], 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (!A_MN) {
                         ptx::tma_load_3d(&tma, &full_bar[stage], sa, k0, m0, za);
                     } else {
@@ -173,9 +201,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+        // ===================== MMA issuer (one thread; the leader CTA's in PAIR mode) =====================
+        if (lane == 0 && (!PAIR || cta_rank == 0)) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -202,18 +230,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                                                     : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                     : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        if (PAIR) ptx::umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        else ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
-                    // frees the smem slot (in every CTA of the cluster: peers multicast into it) when these MMAs retire
-                    if (CL > 1) ptx::umma_commit_mc(&empty_bar[stage], MC_MASK); else ptx::umma_commit(&empty_bar[stage]);
+                    // frees the smem slot (in every CTA of the cluster: peers multicast into it / the pair's MMA read it)
+                    // when these MMAs retire
+                    if (PAIR) ptx::umma_commit_2sm_mc(&empty_bar[stage], MC_MASK);
+                    else if (CL > 1) ptx::umma_commit_mc(&empty_bar[stage], MC_MASK);
+                    else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (of both CTAs in PAIR mode)
+                if (PAIR) ptx::umma_commit_2sm_mc(&tmem_full[acc], MC_MASK); else ptx::umma_commit(&tmem_full[acc]);
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
         const int ew = warp & 3;  // TMEM lane quarter this warp may access
+        // hands the accumulator buffer back to the MMA issuer (PAIR: one arrival per warp on the leader CTA's barrier)
+        auto release_accumulator = [&](uint64_t* bar) {
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(bar, 0);
+            } else {
+                ptx::mbar_arrive(bar);
+            }
+        };
         int local = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++local) {
             int r = tile;
@@ -257,7 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                     }
                 }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
+                release_accumulator(&tmem_empty[acc]);
                 continue;
             } else if constexpr (EPI >= 0) {
                 // bf16 output: 64-column slabs -> swizzled smem (this warp's 32 rows) -> TMA store. The TMA clips
@@ -343,7 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                     }
                 }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
+                release_accumulator(&tmem_empty[acc]);
                 continue;
             } else {
 
@@ -438,7 +480,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 }
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tmem_empty[acc]);
+            release_accumulator(&tmem_empty[acc]);
             }
         }
     }
@@ -448,7 +490,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // no CTA leaves while peers may still signal its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -555,13 +597,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL == 2>::SMEM_BYTES));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = GemmCfg<BN, CL == 2>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -217,7 +217,8 @@ class Trainer:
         self.hyper = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._hyper_host = torch.zeros(16, dtype=torch.float32).pin_memory()
         self.stats = model.stats_buffer(self.device)
-        self._stats_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+        # ring of pinned host buffers: the logs of a step can be read after later steps were enqueued (pipelined loops)
+        self._stats_ring = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(4)]
         self.rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
         model.defer_logs = True
         ops.ProjCEFn.unit_loss_grad = True
@@ -286,18 +287,19 @@ class Trainer:
         self.optimizer_steps += 1
         self.steps += 1
         self.saved = False
-        self._stats_host.copy_(self.stats, non_blocking=True)
-        self._stats_event = torch.cuda.Event()
-        self._stats_event.record()
-        self._pending_lr = self.scheduler.get_last_lr()[0]
-        return LazyLogs(self)
+        host = self._stats_ring[self.steps % len(self._stats_ring)]
+        host.copy_(self.stats, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        return LazyLogs(self, host, event, self.scheduler.get_last_lr()[0])
 
-    def read_logs(self) -> dict:
+    @staticmethod
+    def read_logs(host: Tensor, event, lr: float) -> dict:
         """Synchronises on the step's single deferred D2H copy and returns python numbers."""
-        self._stats_event.synchronize()
-        s = self._stats_host.tolist()
+        event.synchronize()
+        s = host.tolist()
         logs = {'loss': s[0] / math.log(2), 'nll_loss': s[1] / math.log(2), 'num_tokens': int(s[2]), 'num_lines': int(s[3]),
-                'gnorm': math.sqrt(max(s[4], 0.0)), 'lr': self._pending_lr, 'loss_scale': 1.0}
+                'gnorm': math.sqrt(max(s[4], 0.0)), 'lr': lr, 'loss_scale': 1.0}
         return logs
 
     # ------------------------------------------------------------------ CUDA-graph path
@@ -425,17 +427,78 @@ class Trainer:
             self.scheduler.load_state_dict(opt['scheduler'])
 
 
+class DevicePrefetcher:
+    """Device-resident batches from an iterator of host batches (dicts / tuples / lists of pinned tensors): the
+    host->device copies of batch i+1 are issued on a side stream while step i computes, which is the job the
+    DataLoader's pinned-memory prefetch + `utils.move_to_device` do in the reference (pasero/training.py:367-381,
+    pasero/utils.py:691-702). Non-tensor entries pass through unchanged."""
+
+    def __init__(self, batches, device, transform=None):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.transform = transform
+        self.stream = torch.cuda.Stream(self.device)
+        self._next = None
+        self._fetch()
+
+    def _to_device(self, x):
+        if torch.is_tensor(x):
+            return x.to(self.device, non_blocking=True)
+        if isinstance(x, dict):
+            return {k: self._to_device(v) for k, v in x.items()}
+        if isinstance(x, (tuple, list)):
+            return type(x)(self._to_device(v) for v in x)
+        return x
+
+    def _record(self, x, stream):
+        if torch.is_tensor(x):
+            x.record_stream(stream)
+        elif isinstance(x, dict):
+            for v in x.values():
+                self._record(v, stream)
+        elif isinstance(x, (tuple, list)):
+            for v in x:
+                self._record(v, stream)
+
+    def _fetch(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            dev = self._to_device(host)
+            if self.transform is not None:
+                dev = self.transform(dev)
+            event = torch.cuda.Event()
+            event.record(self.stream)
+        self._next = (dev, event)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        dev, event = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(event)
+        self._record(dev, cur)
+        self._fetch()
+        return dev
+
+
 class LazyLogs(dict):
     """Step logs whose values are fetched from the deferred D2H copy on first access (no sync inside the step)."""
 
-    def __init__(self, trainer: Trainer):
+    def __init__(self, trainer: Trainer, host: Tensor, event, lr: float):
         super().__init__()
-        self._trainer, self._loaded = trainer, False
+        self._src, self._loaded = (host, event, lr), False
 
     def _load(self):
-        if not self._loaded:
+        if not self._loaded:   # must happen before the ring slot is reused (4 steps later)
             self._loaded = True
-            super().update(self._trainer.read_logs())
+            super().update(Trainer.read_logs(*self._src))
 
     def __getitem__(self, k):
         self._load()

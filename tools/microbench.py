@@ -64,6 +64,7 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None
     if only == 'attn':
         return attn(out, dev)
+    gemm_only = only == 'gemm'
     # GEMM shapes of config 2 (M = 64 * 250 = 16000 encoder rows)
     for (M, N, K) in [(16000, 512, 512), (16000, 1536, 512), (16000, 2048, 512), (16000, 512, 2048), (31936, 1024, 400),
                       (16000, 1024, 2560), (3072, 8032, 512), (8192, 8192, 8192)]:
@@ -81,6 +82,10 @@ def main():
         out[f'dgrad {M}x{N}x{K}'] = (t, fl / t / 1e9)
         t = timeit(lambda: k.linear_wgrad(dy, x))
         out[f'wgrad {M}x{N}x{K}'] = (t, fl / t / 1e9)
+    if gemm_only:
+        for name, (t, rate) in out.items():
+            print(f'{name:40s} {t * 1000:10.1f} us   {rate:10.1f} TFLOP/s')
+        return
     # fbank
     B, N = 64, 160000
     pcm = (torch.rand(B * N, device=dev) - 0.5)
