@@ -56,7 +56,7 @@ class ClockSampler:
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -257,11 +257,14 @@ def main():
     # pinned-memory DataLoader prefetch does); every step's logs are read back to the host (one step late, so that the
     # read does not drain the queue).
     from pasero_b200.training import DevicePrefetcher
+    copy_stream = torch.cuda.Stream(dev)
+    for pcm_d, dec_d in DevicePrefetcher(((pcm_host, dec_host) for _ in range(W)), dev, stream=copy_stream):   # warm-up
+        step(pcm_d.reshape(-1), dec_d)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss_sink, prev = 0.0, None
-    for pcm_d, dec_d in DevicePrefetcher(((pcm_host, dec_host) for _ in range(args.steps)), dev):
+    for pcm_d, dec_d in DevicePrefetcher(((pcm_host, dec_host) for _ in range(args.steps)), dev, stream=copy_stream):
         lg = step(pcm_d.reshape(-1), dec_d)
         if prev is not None:
             loss_sink += prev['loss']    # device -> host read of the previous step's result
@@ -278,7 +281,7 @@ def main():
 
     # ---- dominant kernel roofline: the tcgen05 GEMM, all launches of one step timed with CUDA events ----
     # (every rank runs the instrumented step: it contains the gradient allreduce)
-    roofline, gemm_share, launches = gemm_roofline(trainer, frontend, plan, rows, front, F, pcm_dev, dec_dev, ms_per_step)
+    roofline, gemm_share, launches = gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -294,7 +297,7 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic', 'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': (launches + 2) * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline, 'cpu_baseline': cpu,
+            'gpu_launches': launches * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline, 'cpu_baseline': cpu,
             'gemm_share_of_step': gemm_share, 'cuda_graph': use_graph,
             'last_step_logs': {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in last.items()},
         }
@@ -303,8 +306,11 @@ def main():
         dist.destroy_process_group()
 
 
-def gemm_roofline(trainer, frontend, plan, rows, front, F, pcm_dev, dec_dev, ms_per_step):
-    """One instrumented eager step: CUDA events around every pb200_gemm_bf16 launch on the launching stream."""
+def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
+    """Live timing of the dominant kernel inside the real step: the CUDA graph of the step is re-captured with an
+    external-event record node before and after every pb200_gemm_bf16 launch, replayed, and the event pairs of the last
+    replay are read back. (Events around eager launches over-count: each bracket then also holds the host's launch
+    latency.) Split-K launches are timed with their memset and reduction kernels; FLOPs are the algorithmic 2*M*N*K."""
     from pasero_b200 import kernels as K
     peaks = {}
     try:
@@ -315,26 +321,41 @@ def gemm_roofline(trainer, frontend, plan, rows, front, F, pcm_dev, dec_dev, ms_
     peak_kind = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
     if peak is None:
         peak, peak_kind = 1400.0, 'fallback (B200_PROFILING.md, sustained)'
-    K.PROFILE = []
-    # keep the GPU busy while the host enqueues the eager step, so that the events bracket back-to-back kernels and
-    # not the host's launch latency
-    torch.cuda._sleep(int(0.08 * 1.9e9))
-    _, padded = frontend.fbank(pcm_dev, plan, cmvn=True, padded_frames=rows, front_pad=front)
-    batch = {'encoder_input': padded, 'encoder_input_length': plan.frames_tensor, 'decoder_input': dec_dev,
-             'padded_layout': (F,), 'meta': {}}
-    K.COUNT = {'launches': 0}
-    trainer.train_step(iter([batch]))
-    torch.cuda.synchronize()
-    prof, K.PROFILE = K.PROFILE, None
-    launches = K.COUNT['launches']
-    K.COUNT = None
-    flops = sum(f for f, _, _ in prof)
-    ms = sum(s.elapsed_time(e) for _, s, e in prof)
+    saved = dict(trainer._graphs)
+    trainer._graphs.clear()
+    K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = [], True, {'launches': 0}
+    try:
+        step(pcm_dev, dec_dev)            # warm-up pass + capture (both go through the instrumented wrappers)
+        if trainer._graphs:
+            prof = K.PROFILE[len(K.PROFILE) // 2:]   # the event pairs recorded during capture = the graph's nodes
+            # one call = fbank + CMVN (2), warm-up body and captured body (N each), grad-norm + Adam (2)
+            launches = (K.COUNT['launches'] - 4) // 2 + 4
+        else:                                        # --no-graph: plain events around eager launches
+            prof, launches = K.PROFILE, K.COUNT['launches']
+        K.PROFILE, K.COUNT = None, None
+        for _ in range(3):
+            step(pcm_dev, dec_dev)        # replays: every event node is re-recorded
+        torch.cuda.synchronize()
+        flops = sum(f for f, _, _ in prof)
+        ms = sum(s.elapsed_time(e) for _, s, e in prof)
+        if os.environ.get('BENCH_GEMM_DUMP'):   # per-shape table on stderr
+            groups = {}
+            for (f, s_, e_), tag in zip(prof, K.PROFILE_TAGS[len(K.PROFILE_TAGS) - len(prof):]):
+                g = groups.setdefault(tag, [0, 0.0, f])
+                g[0] += 1
+                g[1] += s_.elapsed_time(e_)
+            for tag, (n, t, f) in sorted(groups.items(), key=lambda x: -x[1][1]):
+                sys.stderr.write(f'{tag:60s} n={n:3d} total {t * 1e3:8.1f} us  avg {t / n * 1e3:7.1f} us  {f * n / t / 1e9:7.1f} TFLOP/s\n')
+    finally:
+        K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = None, False, None
+        trainer._graphs.clear()
+        trainer._graphs.update(saved)
     achieved = flops / (ms / 1e3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'pb200::gemm_kernel (tcgen05, all instantiations of one step)',
+    roofline = {'bound': 'tensor', 'kernel': 'pb200::gemm_kernel (tcgen05 cta_group::2, all instantiations of one step)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                 'launches_timed': len(prof), 'gemm_ms_per_step': ms, 'algorithmic_gflop_per_step': flops / 1e9,
-                'peak_source': peak_kind}
+                'peak_source': peak_kind,
+                'method': 'external CUDA-event record nodes around every GEMM launch inside the replayed step graph'}
     return roofline, ms / ms_per_step, launches
 
 

@@ -80,7 +80,8 @@ typedef struct pb200_gemm_params {
     const void* relu_mask;    /* bf16, C layout: result zeroed where mask <= 0 (ReLU backward), or NULL */
     int32_t act;              /* 0 none, 1 ReLU, 2 GELU (erf) */
     int32_t out_fp32;         /* 0: C is bf16, 1: C is fp32 */
-    int32_t accumulate;       /* 1: C += result */
+    int32_t accumulate;       /* 1: C += result. With out_fp32 and no other epilogue option, every (split-K) partial tile
+                                 is TMA-reduce-added straight into C: no workspace, no memset, no reduction kernel */
     float alpha;
     int32_t split_k;          /* 0 = choose automatically, >= 1 = force */
     int32_t tile_n;           /* 0 = choose automatically, 128 or 256 = force */
@@ -182,7 +183,13 @@ int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stri
  *        [12] weight_decay*lr
  *   stats fp64[8] (device): [2] num_tokens (gradient divisor), [4] squared gradient norm (out; reduced in a fixed
  *        order so that data-parallel replicas stay bit-identical). The sqnorm workspace is zero-initialised once.
+ *
+ * fp32 main gradients: weight-gradient GEMMs may reduce-add straight into an fp32 accumulation arena (pb200_gemm_bf16
+ * with out_fp32 = accumulate = 1); pb200_grad32_flush rounds the given element ranges ([n][2] begin/end, device,
+ * multiples of 8) into the bf16 gradient arena (what the allreduce and the optimizer read) and zeroes the source.
  * ---------------------------------------------------------------------------------------------- */
+int pb200_grad32_flush(float* acc32, void* grad_bf16, const int64_t* ranges, int32_t n_ranges, int64_t max_len, void* stream);
+/* optimizer kernels */
 size_t pb200_grad_sqnorm_workspace_bytes(void);
 int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -637,13 +637,18 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     // tile width: wide tiles when N is large enough to keep >= ~1 wave of CTAs busy
     const long long m_blks = (q->m + BM - 1) / BM;
     const long long Zout = q->reduce_batch ? 1 : Zall;
+    // fp32 C with accumulate and no other epilogue work: partial tiles of ANY split count are TMA-reduce-added straight
+    // into C (fp32 main-gradient accumulation: no workspace, no memset, no reduction kernel)
+    const bool direct_acc = q->out_fp32 && q->accumulate && q->alpha == 1.0f && !q->bias && !q->residual && !q->relu_mask &&
+                            q->act == 0 && q->ldc % 4 == 0 && q->c_batch_stride % 4 == 0 &&
+                            (reinterpret_cast<uintptr_t>(q->c) & 15) == 0;
     // 128 x 256 tiles halve the A re-reads and the per-tile overheads; fall back to 128 x 128 only when the wide
     // tiling would leave most SMs without a tile
     int bn = 128;
     if (q->n >= 256 && q->tile_n != 128) {
         const long long tiles256 = Zout * m_blks * ((q->n + 255) / 256);
         const long long kb_all = ((q->k + BK - 1) / BK) * (q->reduce_batch ? Zall : 1);
-        const bool can_split = q->split_k != 1 && kb_all >= 32 && q->workspace != nullptr;   // split-K fills the SMs instead
+        const bool can_split = q->split_k != 1 && kb_all >= 32 && (q->workspace != nullptr || direct_acc);   // split-K fills the SMs instead
         if (tiles256 * 2 >= num_sms() || can_split || q->tile_n == 256) bn = 256;
     }
     const long long n_blks = (q->n + bn - 1) / bn;
@@ -667,7 +672,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         }
     }
     if (splits > total_kb) splits = total_kb;
-    if (splits > 1) {   // partial tiles are reduce-added into ONE fp32 buffer
+    if (splits > 1 && !direct_acc) {   // partial tiles are reduce-added into ONE fp32 buffer
         const size_t need = (size_t)Zout * q->m * q->n * sizeof(float);
         if (!q->workspace || q->workspace_bytes < need) splits = 1;
     }
@@ -681,7 +686,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     CUtensorMap ta, tb, tc;
     int rc;
     int epi = -1;
-    if (splits > 1) epi = 4;
+    if (splits > 1 || direct_acc) epi = 4;
     else if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
         (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && (q->act == 0 || q->act == 1)) {
         if (q->residual) { if (!q->relu_mask && !q->bias && q->act == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) epi = 5; }
@@ -690,7 +695,10 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         else if (q->act == 0) epi = 0;
     }
     const bool tma_store = epi >= 0;
-    if (epi == 4) {
+    if (epi == 4 && direct_acc) {
+        rc = make_tmap(&tc, q->c, q->m, q->n, q->ldc, Zout, q->c_batch_stride, 32, 32, /*fp32=*/true);
+        if (rc) return rc;
+    } else if (epi == 4) {
         PB_CUDA(cudaMemsetAsync(q->workspace, 0, (size_t)Zout * q->m * q->n * sizeof(float), stream));
         rc = make_tmap(&tc, q->workspace, q->m, q->n, q->n, Zout, (long long)q->m * q->n, 32, 32, /*fp32=*/true);
         if (rc) return rc;
@@ -763,7 +771,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
 #undef PB_DISPATCH
     if (rc) return rc;
 
-    if (splits > 1) {
+    if (splits > 1 && !direct_acc) {
         const long long zmn = Zout * q->m * q->n;
         const int threads = 256;
         long long blocks = (zmn / 4 + threads - 1) / threads;

@@ -113,9 +113,41 @@ adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __re
     }
 }
 
+// fp32 main-gradient ranges -> bf16 gradient arena (overwrite); the fp32 source is zeroed so that the next step's
+// weight-gradient GEMMs can reduce-add into it again. ranges: [n][2] (begin, end) element offsets, multiples of 8.
+__global__ void __launch_bounds__(256)
+grad32_flush_kernel(float* __restrict__ acc, bf16* __restrict__ out, const long long* __restrict__ ranges) {
+    const long long begin = ranges[2 * blockIdx.y], end = ranges[2 * blockIdx.y + 1];
+    const long long n8 = (end - begin) >> 3;
+    float4* a4 = reinterpret_cast<float4*>(acc + begin);
+    uint4* o4 = reinterpret_cast<uint4*>(out + begin);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = a4[2 * i], b = a4[2 * i + 1];
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+        o4[i] = o;
+        a4[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a4[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 }  // namespace pb200
 
 using namespace pb200;
+
+extern "C" int pb200_grad32_flush(float* acc32, void* grad_bf16, const int64_t* ranges, int32_t n_ranges, int64_t max_len,
+                                  void* stream_) {
+    if (n_ranges <= 0 || max_len <= 0) return 0;
+    PB_CHECK(acc32 && grad_bf16 && ranges, "grad32_flush: null pointer");
+    long long bx = (max_len / 8 + 255) / 256;
+    const long long cap = (8LL * num_sms() + n_ranges - 1) / n_ranges;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)n_ranges);
+    grad32_flush_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(acc32, (bf16*)grad_bf16, (const long long*)ranges);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" size_t pb200_grad_sqnorm_workspace_bytes(void) { return (size_t)(4 * num_sms() + 2) * sizeof(double); }
 

@@ -20,6 +20,8 @@ RNG_OFFSET_BASE: Optional[Tensor] = None
 # Instrumentation used by bench.py: PROFILE (list) receives (flops, start_event, end_event) per GEMM launch; COUNT
 # ({'launches': n}) counts kernel launches issued through this module. Both None in normal operation.
 PROFILE = None
+PROFILE_TAGS = []          # one "m x n x k flags" string per PROFILE entry
+PROFILE_EXTERNAL = False   # True: events become event-record nodes of a CUDA graph being captured (timed on replay)
 COUNT = None
 
 
@@ -53,22 +55,26 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     p.split_k, p.tile_n, p.cluster_m = split_k, tile_n, cluster_m
     ws = None
     plain = bias is None and residual is None and relu_mask is None and act == 0
-    if split_k != 1 and plain:
+    direct = plain and accumulate and c.dtype == torch.float32 and alpha == 1.0   # reduce-add straight into C
+    if split_k != 1 and plain and not direct:
         zout = 1 if reduce_batch else batch
         tiles = zout * math.ceil(m / 128) * math.ceil(n / 256 if n >= 256 else n / 128)
         sms = lib.pb200_num_sms()
         if split_k > 1 or tiles * 2 <= sms:
             ws = _ws(lib.pb200_gemm_workspace_bytes(m, n, zout, 1), c.device)
-    if ws is None:
+    if ws is None and not direct:
         p.split_k = 1
     p.workspace, p.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
     _count(1 if ws is None else 2)
     if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         e0.record()
         check(lib.pb200_gemm_bf16(byref(p), stream_ptr()))
         e1.record()
         PROFILE.append((2.0 * m * n * k * (batch if batch > 0 else 1), e0, e1))
+        PROFILE_TAGS.append(f'{m}x{n}x{k} z{batch} a_mn{int(a_mn_major)} b_mn{int(b_mn_major)} bias{int(bias is not None)} act{act} '
+                            f'mask{int(relu_mask is not None)} res{int(residual is not None)} splitk{int(ws is not None)}')
         return c
     check(lib.pb200_gemm_bf16(byref(p), stream_ptr()))
     return c
@@ -266,6 +272,13 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
 
 
 _SQNORM_WS = {}
+
+
+def grad32_flush(acc32: Tensor, grad: Tensor, ranges: Tensor, max_len: int) -> None:
+    """bf16 gradient arena <- rounded fp32 main gradients over `ranges` (int64 [n, 2], device); zeroes the source."""
+    _count(1)
+    check(_lib.load().pb200_grad32_flush(acc32.data_ptr(), grad.data_ptr(), ranges.data_ptr(), ranges.shape[0], max_len,
+                                         stream_ptr()))
 
 
 def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:

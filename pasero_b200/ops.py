@@ -43,8 +43,11 @@ class DirectGrads:
 
     active: Optional['DirectGrads'] = None
 
-    def __init__(self, views: dict, on_ready=None):
-        self.views = views            # id(param) -> arena view
+    def __init__(self, views: dict, on_ready=None, views32: Optional[dict] = None):
+        self.views = views            # id(param) -> bf16 arena view
+        # id(param) -> fp32 main-gradient view (GEMM weights): weight-gradient GEMMs TMA-reduce-add their (split-K)
+        # partial tiles straight into it; the Trainer rounds it into the bf16 arena once per optimizer step
+        self.views32 = views32 or {}
         self.written = set()
         self.on_ready = on_ready
 
@@ -78,6 +81,23 @@ def _ready(*params):
         d.ready(*params)
 
 
+def _sink32(param):
+    """fp32 main-gradient view of a GEMM weight (None when the Trainer does not provide one)."""
+    d = DirectGrads.active
+    return d.views32.get(id(param)) if (d is not None and param is not None) else None
+
+
+def _wgrad(dy: Tensor, x: Tensor, param):
+    """dW[N, K] = dy^T x of a Linear, routed to the best sink: fp32 main gradient (always accumulate), bf16 arena view
+    (overwrite / accumulate), or a fresh tensor handed back to autograd. Returns what autograd should see."""
+    v32 = _sink32(param)
+    if v32 is not None:
+        K.linear_wgrad(dy, x, out=v32, accumulate=True)
+        return None
+    out, acc = _sink(param)
+    return _ret(K.linear_wgrad(dy, x, out=out, accumulate=acc), out)
+
+
 def _ret(grad, out):
     """Gradient to hand back to autograd: None when it already went into the arena."""
     return None if out is not None else grad
@@ -102,8 +122,7 @@ class LinearFn(torch.autograd.Function):
         dx = K.linear_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1]:
-            out, acc = _sink(w_param)
-            dw = _ret(K.linear_wgrad(dy, x, out=out, accumulate=acc), out)
+            dw = _wgrad(dy, x, w_param)
         if b_param is not None and ctx.needs_input_grad[2]:
             out, acc = _sink(b_param)
             db = _ret(K.colsum(dy, out=out, accumulate=acc), out)
@@ -130,11 +149,11 @@ class FFNFn(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2 = ctx.params
         dy = _c(dy)
         dh = K.linear_dgrad(dy, w2, relu_mask=h)
-        o, a = _sink(p_w2); dw2 = _ret(K.linear_wgrad(dy, h, out=o, accumulate=a), o)
+        dw2 = _wgrad(dy, h, p_w2)
         o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1)
-        o, a = _sink(p_w1); dw1 = _ret(K.linear_wgrad(dh, x, out=o, accumulate=a), o)
+        dw1 = _wgrad(dh, x, p_w1)
         o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2
@@ -177,11 +196,14 @@ class AttentionFn(torch.autograd.Function):
         p_in_w, p_in_b, p_out_w, p_out_b = ctx.params
         dy = _c(dy)
         d_o = K.linear_dgrad(dy, out_w)
-        so, a = _sink(p_out_w); d_out_w = _ret(K.linear_wgrad(dy, o, out=so, accumulate=a), so)
+        d_out_w = _wgrad(dy, o, p_out_w)
         so, a = _sink(p_out_b); d_out_b = _ret(K.colsum(dy, out=so, accumulate=a), so)
         _ready(p_out_w, p_out_b)
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
+        w32 = _sink32(p_in_w)
+        if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
+            sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
         d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
         if self_attn:
@@ -261,10 +283,13 @@ class AttnSublayerFn(torch.autograd.Function):
         dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b)
         _ready(p_gamma, p_beta)
         d_o = K.linear_dgrad(dy, out_w)
-        so, a = _sink(p_out_w); d_out_w = _ret(K.linear_wgrad(dy, o, out=so, accumulate=a), so)
+        d_out_w = _wgrad(dy, o, p_out_w)
         _ready(p_out_w, p_out_b)
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
+        w32 = _sink32(p_in_w)
+        if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
+            sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
         d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
         if self_attn:
@@ -314,10 +339,10 @@ class FFNSublayerFn(torch.autograd.Function):
         dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2)
         _ready(p_gamma, p_beta)
         dh = K.linear_dgrad(dy, w2, relu_mask=h)
-        o, a = _sink(p_w2); dw2 = _ret(K.linear_wgrad(dy, h, out=o, accumulate=a), o)
+        dw2 = _wgrad(dy, h, p_w2)
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1, residual=dres)
-        o, a = _sink(p_w1); dw1 = _ret(K.linear_wgrad(dh, x, out=o, accumulate=a), o)
+        dw1 = _wgrad(dh, x, p_w1)
         o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None, None
@@ -376,6 +401,11 @@ class EmbedFn(torch.autograd.Function):
         dy = _c(dy)
         if ids_flat is None:
             return K.embed_bwd(dy, None, M, D, scale, p, seed, offset), None, None, None, None, None, None
+        t32 = _sink32(ctx.table)
+        if t32 is not None:       # scatter-add straight into the fp32 main gradient of the (tied) embedding table
+            K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, t32)
+            _ready(ctx.table)
+            return None, None, None, None, None, None, None
         dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
         K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
         so, acc = _sink(ctx.table)
@@ -418,6 +448,9 @@ class ConvGLUFn(torch.autograd.Function):
         dpre = K.glu_bwd(dy, pre, B * Tout, Cout // 2)
         p_w, p_b = ctx.params
         so_w, acc_w = _sink(p_w)
+        w32 = _sink32(p_w)
+        if w32 is not None:
+            so_w, acc_w = w32, True
         dw = so_w if so_w is not None else torch.empty_like(weight)
         K.gemm_raw(dpre.data_ptr(), xp.data_ptr(), dw, Cout, KW * Cin, Tout, lda=Cout, ldb=stride * Cin, ldc=KW * Cin, batch=B,
                    a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True,
@@ -461,8 +494,7 @@ class ProjCEFn(torch.autograd.Function):
         x, table, dlogits = ctx.saved_tensors
         dx = K.linear_dgrad(dlogits, table)
         if ProjCEFn.unit_loss_grad:
-            so, acc = _sink(ctx.table)
-            dtable = _ret(K.linear_wgrad(dlogits, x, out=so, accumulate=acc), so)
+            dtable = _wgrad(dlogits, x, ctx.table)
         else:
             dtable = K.linear_wgrad(dlogits, x) * dloss.to(BF16)
             dx = dx * dloss.to(dx.dtype)

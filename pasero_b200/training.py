@@ -81,6 +81,10 @@ class ParamArena:
         self.numel = off
         self.param = torch.zeros(off, dtype=BF16, device=device)
         self.grad = torch.zeros(off, dtype=BF16, device=device)
+        # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
+        # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
+        self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.is32 = [p.ndim >= 2 for p in self.params]
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=device)
         with torch.no_grad():
@@ -93,6 +97,27 @@ class ParamArena:
     def view(self, flat: Tensor, i: int) -> Tensor:
         p, o = self.params[i], self.offsets[i]
         return flat[o:o + p.numel()].view(p.shape)
+
+    def ranges32(self, lo: int, hi: int) -> tuple:
+        """(ranges, max_len): merged (begin, end) element ranges of the fp32-accumulated parameters inside arena slice
+        [lo, hi) as an int64 [n, 2] device tensor, and the longest range (host int, sizes the flush grid)."""
+        out = []
+        for i, p in enumerate(self.params):
+            o = self.offsets[i]
+            if not self.is32[i] or o < lo or o >= hi:
+                continue
+            end = o + (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            if out and out[-1][1] == o:
+                out[-1][1] = end
+            else:
+                out.append([o, end])
+        max_len = max((e - b for b, e in out), default=0)
+        return torch.tensor(out, dtype=torch.int64, device=self.grad.device).reshape(-1, 2), max_len
+
+    def flush32(self, ranges: tuple) -> None:
+        """grad (bf16) <- round(grad32) over `ranges`; grad32 <- 0."""
+        if ranges[1] > 0:
+            K.grad32_flush(self.grad32, self.grad, ranges[0], ranges[1])
 
     def rebind_grads(self) -> None:
         for i, p in enumerate(self.params):
@@ -131,6 +156,7 @@ class GradBuckets:
             self.sizes[b] += 1
         self.enabled = True
         self.launch_order = []
+        self.pre_launch = None   # callable(bucket index) run on the compute stream before the bucket's allreduce
         self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i) if self.use_autograd_hooks else None)
@@ -148,6 +174,8 @@ class GradBuckets:
 
     def _launch(self, b: int) -> None:
         lo, hi = self.buckets[b]
+        if self.pre_launch is not None:
+            self.pre_launch(b)
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
@@ -206,10 +234,15 @@ class Trainer:
         index = {id(p): i for i, p in enumerate(self.arena.params)}
         on_ready = (lambda p: self.buckets.param_ready(index[id(p)])) if self.buckets is not None else None
         self.direct = ops.DirectGrads({id(p): self.arena.view(self.arena.grad, i) for i, p in enumerate(self.arena.params)},
-                                      on_ready)
+                                      on_ready,
+                                      {id(p): self.arena.view(self.arena.grad32, i) for i, p in enumerate(self.arena.params)
+                                       if self.arena.is32[i]})
         ops.DirectGrads.active = self.direct
+        self._ranges32_all = self.arena.ranges32(0, self.arena.numel)
         if self.buckets is not None:
             self.buckets.use_autograd_hooks = False
+            bucket_ranges = [self.arena.ranges32(lo, hi) for lo, hi in self.buckets.buckets]
+            self.buckets.pre_launch = lambda b: self.arena.flush32(bucket_ranges[b])
         self.scheduler = LRScheduler(cfg)
         self.optimizer_steps = 0     # Adam's state['step']
         self.steps = 0
@@ -278,6 +311,8 @@ class Trainer:
             self._forward_backward(batch)
         if self.buckets is not None:
             self.buckets.finish(self.stats)
+        else:
+            self.arena.flush32(self._ranges32_all)
         self._write_hyper()
         self._optimizer_kernels()
         return self._finish_step()
@@ -353,6 +388,8 @@ class Trainer:
         batch = dict(static)
         batch.update(extras)
         self._forward_backward(batch)
+        if self.buckets is None:
+            self.arena.flush32(self._ranges32_all)   # with buckets: flushed per bucket right before its allreduce
 
     # ------------------------------------------------------------------ checkpoints (reference layout)
     def _named_state(self, flat: Tensor) -> dict:
@@ -433,11 +470,13 @@ class DevicePrefetcher:
     DataLoader's pinned-memory prefetch + `utils.move_to_device` do in the reference (pasero/training.py:367-381,
     pasero/utils.py:691-702). Non-tensor entries pass through unchanged."""
 
-    def __init__(self, batches, device, transform=None):
+    def __init__(self, batches, device, transform=None, stream=None):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.transform = transform
-        self.stream = torch.cuda.Stream(self.device)
+        # pass the same stream to successive prefetchers: the caching allocator keeps one block pool per stream, so a
+        # fresh stream starts with cudaMalloc calls (each one synchronises the device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
         self._next = None
         self._fetch()
 
