@@ -94,6 +94,7 @@ template <bool P_TMEM, bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, P_TMEM ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const AttnTcDev p) {
+    pdl_trigger();
     using Cfg = FwdCfg<P_TMEM>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,11 +110,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-    const int coff = p.Lk - p.Lq;   // causal: key j visible to query i iff j <= i + coff
-    int kv_hi = CAUSAL ? min(kvlen, q0 + 128 + coff) : kvlen;
-    kv_hi = max(kv_hi, 1);
-    const int n1 = min(((kv_hi + 15) >> 4) << 4, p.kv_box);   // keys covered by the MMAs (multiple of 16)
 #ifdef PB_ATTN_TIMING
     const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (warp == 8 && lane == 0 && cta_lin < 4096) {
@@ -139,6 +135,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // set-up above overlaps the previous kernel; global memory is touched only below
+    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+    const int coff = p.Lk - p.Lq;   // causal: key j visible to query i iff j <= i + coff
+    int kv_hi = CAUSAL ? min(kvlen, q0 + 128 + coff) : kvlen;
+    kv_hi = max(kv_hi, 1);
+    const int n1 = min(((kv_hi + 15) >> 4) << 4, p.kv_box);   // keys covered by the MMAs (multiple of 16)
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + Cfg::O_COL, tmem_o2 = tmem_base + Cfg::O2_COL;
 
     if (warp == 8) {
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
                    const AttnTcDev p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -329,8 +332,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-    const int coff = p.Lk - p.Lq;
     const int ni = (p.q_box + 127) >> 7, nj = (p.kv_box + 127) >> 7;
 #ifdef PB_ATTN_TIMING
     const int cta_lin = blockIdx.x + gridDim.x * blockIdx.y;
@@ -358,6 +359,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // set-up above overlaps the previous kernel; global memory is touched only below
+    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+    const int coff = p.Lk - p.Lq;
     const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                    t_dq = tmem_base + 384;
 
@@ -604,7 +608,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
         attr_set = true;
     }
     dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-    kern<<<grid, TC_THREADS, FwdCfg<P_TMEM>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    PB_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), FwdCfg<P_TMEM>::SMEM_BYTES, stream, tq, tk, tv, p));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -638,8 +642,8 @@ int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid(p.H, p.B);
-    if (p.causal) attn_bwd_tc_kernel<true><<<grid, TC_THREADS, BwdCfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
-    else attn_bwd_tc_kernel<false><<<grid, TC_THREADS, BwdCfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+    if (p.causal) PB_CUDA(launch_pdl(attn_bwd_tc_kernel<true>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
+    else PB_CUDA(launch_pdl(attn_bwd_tc_kernel<false>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
     PB_LAUNCH_CHECK();
     return 0;
 }

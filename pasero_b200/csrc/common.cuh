@@ -44,6 +44,32 @@ void set_error(const char* fmt, ...);
 int num_sms();
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Kernels launched through launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining: everything before pdl_wait() (barrier / TMEM / descriptor set-up, index
+// arithmetic) overlaps the predecessor's tail, pdl_wait() returns once the predecessor has completed and its writes
+// are visible. RULE: no global-memory access (read OR write) before pdl_wait(). pdl_trigger() lets the successor's
+// CTAs be scheduled as soon as every CTA of this grid has started.  PB200_PDL=0 disables the launch attribute.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;

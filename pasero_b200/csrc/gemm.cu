@@ -89,6 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int cta_rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -122,6 +123,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; operands / outputs are touched only below
 
     const int m_groups = (p.m_blks + CL - 1) / CL;
     const int total_tiles = p.Z * m_groups * p.n_blks * p.splits;   // cluster-level tiles
@@ -605,11 +607,20 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = GemmCfg<BN, CL == 2>::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     PB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, d));
     PB_LAUNCH_CHECK();
     return 0;

@@ -20,6 +20,8 @@ dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ r
                           float p, uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
                           bf16* __restrict__ sum_out, bf16* __restrict__ y_out, float* __restrict__ mean_out,
                           float* __restrict__ rstd_out) {
+    pdl_trigger();
+    pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -117,6 +119,8 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
                           const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D, float p,
                           uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
                           bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial, int want_lin) {
+    pdl_trigger();
+    pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Philox rng(seed);
@@ -263,6 +267,8 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int P, long long stride, int N,
                        bf16* __restrict__ out, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + cx;
     float a = 0.f;
@@ -291,6 +297,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int P, long long strid
 struct ReduceOut3 { bf16* out[3]; int accumulate[3]; };
 __global__ void __launch_bounds__(256)
 reduce_partials_multi_kernel(const float* __restrict__ partial, int P, long long stride, int N, ReduceOut3 o) {
+    pdl_trigger();
+    pdl_wait();
     bf16* out = o.out[blockIdx.y];
     if (!out) return;
     const float* src = partial + (long long)blockIdx.y * N;
@@ -321,6 +329,8 @@ reduce_partials_multi_kernel(const float* __restrict__ partial, int P, long long
 // column sums of a bf16 [M, N] matrix (bias gradients): partial[split][N]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, int M, int N, long long ld, float* __restrict__ partial) {
+    pdl_trigger();
+    pdl_wait();
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;   // 32 column groups of 8, 8 row lanes
     const int col = blockIdx.x * 256 + cg * 8;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -385,9 +395,9 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
     const int nch = (int)((D + 255) / 256);
     const int grid = (int)((M + LN_WARPS - 1) / LN_WARPS);
 #define PB_LN_FWD(N_)                                                                                         \
-    dropout_add_ln_fwd_kernel<N_><<<grid, LN_WARPS * 32, 0, stream>>>(                                         \
+    PB_CUDA(launch_pdl(dropout_add_ln_fwd_kernel<N_>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,                \
         (const bf16*)x, (const bf16*)residual, (const bf16*)gamma, (const bf16*)beta, (int)M, (int)D, eps, p,  \
-        seed, offset, (const long long*)offset_base, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out)
+        seed, offset, (const long long*)offset_base, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out))
     switch (nch) { case 1: PB_LN_FWD(1); break; case 2: PB_LN_FWD(2); break; case 3: PB_LN_FWD(3); break; default: PB_LN_FWD(4); }
 #undef PB_LN_FWD
     PB_LAUNCH_CHECK();
@@ -410,10 +420,10 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
     }
     const int nch = (int)((D + 255) / 256);
 #define PB_LN_BWD(N_)                                                                                        \
-    dropout_add_ln_bwd_kernel<N_><<<grid, LNB_WARPS * 32, 0, stream>>>(                                       \
+    PB_CUDA(launch_pdl(dropout_add_ln_bwd_kernel<N_>, dim3(grid), dim3(LNB_WARPS * 32), 0, stream,              \
         (const bf16*)dy, (const bf16*)dsum_extra, (const bf16*)sum, (const bf16*)gamma, mean, rstd, (int)M,   \
         (int)D, p, seed, offset, (const long long*)offset_base, (bf16*)dresidual, (bf16*)dx, partial,          \
-        dbias_lin != nullptr ? 1 : 0)
+        dbias_lin != nullptr ? 1 : 0))
     switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();
@@ -422,7 +432,7 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
         o.out[0] = gamma ? (bf16*)dgamma : nullptr; o.out[1] = gamma ? (bf16*)dbeta : nullptr; o.out[2] = (bf16*)dbias_lin;
         o.accumulate[0] = o.accumulate[1] = accumulate & 1; o.accumulate[2] = (accumulate >> 1) & 1;
         dim3 rgrid((unsigned)((D + 31) / 32), 3);
-        reduce_partials_multi_kernel<<<rgrid, 256, 0, stream>>>(partial, grid, 3 * D, (int)D, o);
+        PB_CUDA(launch_pdl(reduce_partials_multi_kernel, rgrid, dim3(256), 0, stream, (const float*)partial, grid, (long long)(3 * D), (int)D, o));
         PB_LAUNCH_CHECK();
     }
     return 0;
@@ -440,10 +450,10 @@ extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld
     const long long splits = colsum_splits(M, N);
     PB_CHECK(workspace && workspace_bytes >= pb200_colsum_workspace_bytes(M, N), "colsum workspace too small");
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)splits);
-    colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, (int)M, (int)N, ld, (float*)workspace);
+    PB_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, (const bf16*)x, (int)M, (int)N, (long long)ld, (float*)workspace));
     PB_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(int)((N + 31) / 32), 256, 0, stream>>>((const float*)workspace, (int)splits, N, (int)N,
-                                                                       (bf16*)out, accumulate);
+    PB_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, stream, (const float*)workspace, (int)splits,
+                       (long long)N, (int)N, (bf16*)out, (int)accumulate));
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -28,6 +28,8 @@ __device__ __forceinline__ float grad_coeff(const float* hyper, const double* st
 __global__ void __launch_bounds__(256)
 grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __restrict__ hyper,
                    double* __restrict__ stats, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    pdl_trigger();
+    pdl_wait();
     const float coeff = grad_coeff(hyper, stats);
     float acc = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __restrict__ exp_avg,
             float* __restrict__ exp_avg_sq, long long n8, const float* __restrict__ hyper,
             const double* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
     const float beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3];
     const float bc2_sqrt = hyper[6], clip = hyper[7];
     const float omb1 = hyper[9], omb2 = hyper[10], step_size = hyper[11], wd_lr = hyper[12];
@@ -117,6 +121,8 @@ adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __re
 // weight-gradient GEMMs can reduce-add into it again. ranges: [n][2] (begin, end) element offsets, multiples of 8.
 __global__ void __launch_bounds__(256)
 grad32_flush_kernel(float* __restrict__ acc, bf16* __restrict__ out, const long long* __restrict__ ranges) {
+    pdl_trigger();
+    pdl_wait();
     const long long begin = ranges[2 * blockIdx.y], end = ranges[2 * blockIdx.y + 1];
     const long long n8 = (end - begin) >> 3;
     float4* a4 = reinterpret_cast<float4*>(acc + begin);
@@ -144,7 +150,7 @@ extern "C" int pb200_grad32_flush(float* acc32, void* grad_bf16, const int64_t* 
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)n_ranges);
-    grad32_flush_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(acc32, (bf16*)grad_bf16, (const long long*)ranges);
+    PB_CUDA(launch_pdl(grad32_flush_kernel, grid, dim3(256), 0, (cudaStream_t)stream_, acc32, (bf16*)grad_bf16, (const long long*)ranges));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -162,7 +168,7 @@ extern "C" int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper
     if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
     double* partials = reinterpret_cast<double*>(workspace) + 1;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
-    grad_sqnorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)grad, n / 8, hyper, stats, partials, ticket);
+    PB_CUDA(launch_pdl(grad_sqnorm_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, (const bf16*)grad, (long long)(n / 8), hyper, stats, partials, ticket));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -173,8 +179,8 @@ extern "C" int pb200_adam_step(void* param, const void* grad, float* exp_avg, fl
     PB_CHECK(n % 8 == 0, "parameter arena length (%lld) must be a multiple of 8", (long long)n);
     long long blocks = (n / 8 + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq, n / 8,
-                                                               hyper, stats);
+    PB_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, (bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq,
+                       (long long)(n / 8), hyper, stats));
     PB_LAUNCH_CHECK();
     return 0;
 }

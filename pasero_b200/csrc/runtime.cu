@@ -3,6 +3,7 @@
 #include "../../include/pasero_b200.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace pb200 {
 
@@ -27,6 +28,15 @@ int num_sms() {
         cached_dev = dev;
     }
     return cached;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PB200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 }  // namespace pb200
