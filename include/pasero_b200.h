@@ -78,6 +78,11 @@ typedef struct pb200_gemm_params {
     const void* bias;         /* bf16 [n] or NULL */
     const void* residual;     /* bf16, C layout, added after the activation, or NULL */
     const void* relu_mask;    /* bf16, C layout: result zeroed where mask <= 0 (ReLU backward), or NULL */
+    void* relu_bits_out;      /* with bias + act == 1: uint32 [n / 32][relu_bits_ld] sign map of the output (bit c % 32 of
+                                 word [c / 32][r] = C[r][c] > 0), or NULL. n % 32 == 0, single batch */
+    const void* relu_bits;    /* such a map used as the ReLU-backward mask instead of relu_mask (1 bit per element instead of
+                                 a bf16 tensor read in the epilogue), or NULL */
+    int64_t relu_bits_ld;     /* words between consecutive 32-column groups (>= m) */
     int32_t act;              /* 0 none, 1 ReLU, 2 GELU (erf) */
     int32_t out_fp32;         /* 0: C is bf16, 1: C is fp32 */
     int32_t accumulate;       /* 1: C += result. With out_fp32 and no other epilogue option, every (split-K) partial tile

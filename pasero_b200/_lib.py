@@ -23,6 +23,7 @@ class GemmParams(Structure):
         ('a_batch_stride', c_int64), ('b_batch_stride', c_int64), ('c_batch_stride', c_int64),
         ('a_mn_major', c_int32), ('b_mn_major', c_int32), ('reduce_batch', c_int32),
         ('bias', c_void_p), ('residual', c_void_p), ('relu_mask', c_void_p),
+        ('relu_bits_out', c_void_p), ('relu_bits', c_void_p), ('relu_bits_ld', c_int64),
         ('act', c_int32), ('out_fp32', c_int32), ('accumulate', c_int32), ('alpha', c_float),
         ('split_k', c_int32), ('tile_n', c_int32), ('cluster_m', c_int32),
         ('workspace', c_void_p), ('workspace_bytes', c_size_t),

@@ -40,6 +40,9 @@ struct GemmDev {
     const bf16* bias;
     const bf16* residual;
     const bf16* relu_mask;
+    uint32_t* relu_bits_out;       // EPI 2: bit (row, col) of word [col / 32][row] = (output > 0)
+    const uint32_t* relu_bits;     // EPI 6: the same words, used as the ReLU-backward mask
+    long long relu_bits_ld;        // words between consecutive 32-column groups (>= rows)
     int act, out_fp32, accumulate;
     int tma_store;       // bf16 output staged through shared memory and written with TMA
     float alpha;
@@ -67,7 +70,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // EPI selects the epilogue at compile time (the generic one carries ~2500 SASS instructions per 64 columns when every
 // option is a run-time flag, which made the kernel epilogue-bound):
 //   -1 generic direct-store path (fp32 out, accumulate, split-K partials, alpha, GELU, residual)
-//    0 plain bf16   1 +bias   2 +bias+ReLU   3 x ReLU-mask   5 +residual (bf16, C layout)   -> staged in smem, written by TMA
+//    0 plain bf16   1 +bias   2 +bias+ReLU (+ optional 1-bit-per-element sign map)   3 x ReLU-mask (bf16 tensor)
+//    5 +residual (bf16, C layout)   6 x ReLU-mask (bit map written by EPI 2: 16x less epilogue traffic than EPI 3)
+//                                                                           -> staged in smem, written by TMA
 //    4 split-K: fp32 partial tile TMA-reduce-added (+=, performed in L2) into one fp32 accumulation buffer
 // CL == 2: CTA pair (see GemmCfg). CL == 4: thread-block clusters of CL CTAs along M with TMA multicast of B: The CTAs of a cluster work on CL consecutive m-blocks of the same
 // n-block, so they need the same B tile: each CTA fetches 1/CL of it and TMA-multicasts that slice into every CTA's
@@ -273,6 +278,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             const int kb_begin = split * p.kb_per_split;
             const bool empty_range = kb_begin >= p.total_kb;
 
+            // Auxiliary epilogue operands are requested BEFORE the accumulator is waited for, and kept one 64-column slab
+            // ahead inside the loop: a dependent global load per 32-column slab (measured) made these epilogues longer
+            // than the next tile's main loop and the whole GEMM ~1.7x slower than its plain variant.
+            uint32_t mword[BN / 32];   // EPI 6: ReLU sign bits of this lane's row for the whole tile
+            uint4 aux_q[2][4];         // EPI 3 / 5: bf16 aux values of the next two 32-column slabs of this lane's row
+            [[maybe_unused]] const long long aux_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
+            [[maybe_unused]] auto load_aux = [&](int c64, int half) {
+                const bf16* aux = EPI == 3 ? p.relu_mask : p.residual;
+                const uint32_t fill = EPI == 3 ? 0x3f803f80u : 0u;
+                const int colh = n0 + c64 * 64 + half * 32;
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    aux_q[half][g8] = make_uint4(fill, fill, fill, fill);
+                    if (row_ok && c64 < BN / 64 && colh + g8 * 8 < p.N)
+                        aux_q[half][g8] = __ldg(reinterpret_cast<const uint4*>(aux + aux_row + colh + g8 * 8));
+                }
+            };
+            if constexpr (EPI == 6) {
+#pragma unroll
+                for (int w = 0; w < BN / 32; ++w) {
+                    mword[w] = 0xffffffffu;
+                    if (row_ok && n0 + w * 32 < p.N) mword[w] = __ldg(p.relu_bits + (long long)((n0 >> 5) + w) * p.relu_bits_ld + row);
+                }
+            }
+            if constexpr (EPI == 3 || EPI == 5) { load_aux(0, 0); load_aux(0, 1); }
+
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
@@ -322,18 +353,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int colh = col0 + half * 32;
-                        // auxiliary operands of this 32-column slab are requested before the TMEM read is waited on
+                        // this slab's auxiliary operands were requested one slab pair ago; refill the slot for c64 + 1
                         uint4 aux_m[4];
                         if constexpr (EPI == 3 || EPI == 5) {
-                            const bf16* aux = EPI == 3 ? p.relu_mask : p.residual;
-                            const uint32_t fill = EPI == 3 ? 0x3f803f80u : 0u;
 #pragma unroll
-                            for (int g8 = 0; g8 < 4; ++g8) {
-                                aux_m[g8] = make_uint4(fill, fill, fill, fill);
-                                if (row_ok && colh + g8 * 8 < p.N)
-                                    aux_m[g8] = __ldg(reinterpret_cast<const uint4*>(aux + coff_row + colh + g8 * 8));
-                            }
+                            for (int g8 = 0; g8 < 4; ++g8) aux_m[g8] = aux_q[half][g8];
+                            load_aux(c64 + 1, half);
                         }
+                        uint32_t mbits = 0xffffffffu;   // EPI 6: ReLU sign bits of this lane's row, columns [colh, colh + 32)
+                        if constexpr (EPI == 6) {
+#pragma unroll
+                            for (int w = 0; w < BN / 32; ++w)
+                                if (w == c64 * 2 + half) mbits = mword[w];
+                        }
+                        (void)colh;
+                        uint32_t obits = 0;             // EPI 2: sign bits produced here
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
                         ptx::tmem_ld_wait();
@@ -354,7 +388,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                             }
                             if constexpr (EPI == 2) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+                                for (int j = 0; j < 8; ++j) {
+                                    obits |= (x[j] > 0.f ? 1u : 0u) << (g8 * 8 + j);
+                                    x[j] = fmaxf(x[j], 0.f);
+                                }
+                            }
+                            if constexpr (EPI == 6) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (!((mbits >> (g8 * 8 + j)) & 1u)) x[j] = 0.f;
                             }
                             if constexpr (EPI == 3) {
                                 const uint32_t mw[4] = {aux_m[g8].x, aux_m[g8].y, aux_m[g8].z, aux_m[g8].w};
@@ -377,6 +419,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                             ov.z = pack_bf16x2(x[4], x[5]); ov.w = pack_bf16x2(x[6], x[7]);
                             const int chunk = half * 4 + g8;   // 16-byte chunk inside the 128-byte row
                             *reinterpret_cast<uint4*>(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = ov;
+                        }
+                        if constexpr (EPI == 2) {   // lanes = consecutive rows: one coalesced 128-byte store per warp
+                            if (p.relu_bits_out && row_ok && colh < p.N)
+                                p.relu_bits_out[(long long)(colh >> 5) * p.relu_bits_ld + row] = obits;
                         }
                     }
                     ptx::fence_proxy_async();
@@ -651,6 +697,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     // fp32 C with accumulate and no other epilogue work: partial tiles of ANY split count are TMA-reduce-added straight
     // into C (fp32 main-gradient accumulation: no workspace, no memset, no reduction kernel)
     const bool direct_acc = q->out_fp32 && q->accumulate && q->alpha == 1.0f && !q->bias && !q->residual && !q->relu_mask &&
+                            !q->relu_bits && !q->relu_bits_out &&
                             q->act == 0 && q->ldc % 4 == 0 && q->c_batch_stride % 4 == 0 &&
                             (reinterpret_cast<uintptr_t>(q->c) & 15) == 0;
     // 128 x 256 tiles halve the A re-reads and the per-tile overheads; fall back to 128 x 128 only when the wide
@@ -700,7 +747,8 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     if (splits > 1 || direct_acc) epi = 4;
     else if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
         (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && (q->act == 0 || q->act == 1)) {
-        if (q->residual) { if (!q->relu_mask && !q->bias && q->act == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) epi = 5; }
+        if (q->residual) { if (!q->relu_mask && !q->relu_bits && !q->bias && q->act == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) epi = 5; }
+        else if (q->relu_bits) { if (!q->relu_mask && !q->bias && q->act == 0 && q->n % 32 == 0 && Zout == 1) epi = 6; }
         else if (q->relu_mask) { if (!q->bias && q->act == 0) epi = 3; }
         else if (q->bias) epi = q->act == 1 ? 2 : 1;
         else if (q->act == 0) epi = 0;
@@ -742,6 +790,13 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     d.bias = reinterpret_cast<const bf16*>(q->bias);
     d.residual = reinterpret_cast<const bf16*>(q->residual);
     d.relu_mask = reinterpret_cast<const bf16*>(q->relu_mask);
+    d.relu_bits_out = reinterpret_cast<uint32_t*>(q->relu_bits_out);
+    d.relu_bits = reinterpret_cast<const uint32_t*>(q->relu_bits);
+    d.relu_bits_ld = q->relu_bits_ld;
+    PB_CHECK(q->relu_bits == nullptr || epi == 6, "relu_bits needs a plain bf16 GEMM with n %% 32 == 0 and a single batch");
+    PB_CHECK(q->relu_bits_out == nullptr || (epi == 2 && q->n % 32 == 0 && Zout == 1),
+             "relu_bits_out needs the bias+ReLU TMA epilogue with n %% 32 == 0 and a single batch");
+    PB_CHECK((q->relu_bits == nullptr && q->relu_bits_out == nullptr) || q->relu_bits_ld >= q->m, "relu_bits_ld must cover the rows");
     d.act = q->act; d.out_fp32 = q->out_fp32; d.accumulate = q->accumulate; d.alpha = q->alpha;
     d.tma_store = tma_store ? 1 : 0;
     d.partial = reinterpret_cast<float*>(q->workspace);
@@ -773,6 +828,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
             case 3: PB_DISPATCH2(BN_, 3); break;                  \
             case 4: PB_DISPATCH2(BN_, 4); break;                  \
             case 5: PB_DISPATCH2(BN_, 5); break;                  \
+            case 6: PB_DISPATCH2(BN_, 6); break;                  \
             default: PB_DISPATCH2(BN_, -1); break;                \
         }                                                         \
     } while (0)

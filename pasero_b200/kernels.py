@@ -30,6 +30,28 @@ def _count(n: int) -> None:
         COUNT['launches'] += n
 
 
+PROFILE_ALL = None   # list of (tag, start_event, end_event) for every non-GEMM wrapper call (tools/step_breakdown.py)
+
+
+def _bracketed(fn):
+    """Times a wrapper with external CUDA events when PROFILE_ALL is a list (instrumented graph capture)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if PROFILE_ALL is None:
+            return fn(*args, **kwargs)
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e0.record()
+        out = fn(*args, **kwargs)
+        e1.record()
+        shapes = 'x'.join(str(d) for a in args[:2] if torch.is_tensor(a) for d in a.shape)
+        PROFILE_ALL.append((f'{fn.__name__} {shapes}', e0, e1))
+        return out
+    return wrapper
+
+
 def _ws(nbytes: int, device) -> Optional[Tensor]:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device) if nbytes > 0 else None
 
@@ -42,7 +64,7 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
              a_mn_major: bool = False, b_mn_major: bool = False, reduce_batch: bool = False,
              bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, relu_mask: Optional[Tensor] = None,
              act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0,
-             cluster_m: int = 0) -> Tensor:
+             cluster_m: int = 0, relu_bits_out: Optional[Tensor] = None, relu_bits: Optional[Tensor] = None) -> Tensor:
     lib = _lib.load()
     p = GemmParams()
     p.a, p.b, p.c = a_ptr, b_ptr, c.data_ptr()
@@ -51,10 +73,13 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     p.a_batch_stride, p.b_batch_stride, p.c_batch_stride = a_batch_stride, b_batch_stride, c_batch_stride
     p.a_mn_major, p.b_mn_major, p.reduce_batch = int(a_mn_major), int(b_mn_major), int(reduce_batch)
     p.bias, p.residual, p.relu_mask = ptr(bias), ptr(residual), ptr(relu_mask)
+    p.relu_bits_out, p.relu_bits = ptr(relu_bits_out), ptr(relu_bits)
+    bits = relu_bits_out if relu_bits_out is not None else relu_bits
+    p.relu_bits_ld = bits.stride(0) if bits is not None else 0
     p.act, p.out_fp32, p.accumulate, p.alpha = act, int(c.dtype == torch.float32), int(accumulate), alpha
     p.split_k, p.tile_n, p.cluster_m = split_k, tile_n, cluster_m
     ws = None
-    plain = bias is None and residual is None and relu_mask is None and act == 0
+    plain = bias is None and residual is None and relu_mask is None and relu_bits is None and act == 0
     direct = plain and accumulate and c.dtype == torch.float32 and alpha == 1.0   # reduce-add straight into C
     if split_k != 1 and plain and not direct:
         zout = 1 if reduce_batch else batch
@@ -80,19 +105,25 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
     return c
 
 
+def relu_bits_supported(N: int, bias: Optional[Tensor]) -> bool:
+    return N % 32 == 0 and bias is not None
+
+
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0,
-               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0, cluster_m: int = 0) -> Tensor:
-    """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual)"""
+               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0, cluster_m: int = 0,
+               relu_bits_out: Optional[Tensor] = None) -> Tensor:
+    """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual). relu_bits_out (int32 [N / 32, M], with act == 1): sign map
+    of y for linear_dgrad(..., relu_bits=...)."""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
     y = torch.empty(M, N, dtype=out_dtype, device=x.device)
     return gemm_raw(x.data_ptr(), w.data_ptr(), y, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, act=act,
-                    residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m)
+                    residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m, relu_bits_out=relu_bits_out)
 
 
 def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out: Optional[Tensor] = None,
-                 accumulate: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+                 accumulate: bool = False, residual: Optional[Tensor] = None, relu_bits: Optional[Tensor] = None) -> Tensor:
     """dx[M, K] = dy[M, N] @ w[N, K]  (optionally masked by relu_mask > 0, or + residual[M, K] in the epilogue:
     the gradient of the skip connection joins the sub-block's input gradient without a separate add kernel)"""
     M, N = dy.shape
@@ -100,7 +131,7 @@ def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out:
     dx = out if out is not None else torch.empty(M, K, dtype=BF16, device=dy.device)
     assert residual is None or (residual.shape == dx.shape and residual.is_contiguous())
     return gemm_raw(dy.data_ptr(), w.data_ptr(), dx, M, K, N, lda=N, ldb=K, ldc=K, b_mn_major=True,
-                    relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1)
+                    relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1, relu_bits=relu_bits)
 
 
 def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
@@ -115,6 +146,7 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
+@_bracketed
 def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, kv_len: Optional[Tensor],
                   causal: bool, scale: float):
     """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection)."""
@@ -130,6 +162,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: 
     return o, lse
 
 
+@_bracketed
 def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, B: int, H: int, Lq: int,
                   Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor):
     lib = _lib.load()
@@ -149,6 +182,7 @@ def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse:
 # --------------------------------------------------------------------------------------------------
 # dropout + residual + LayerNorm
 # --------------------------------------------------------------------------------------------------
+@_bracketed
 def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
                        eps: float, p: float, seed: int, offset: int, need_sum: bool = True):
     lib = _lib.load()
@@ -168,6 +202,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     return (y if has_ln else sum_out), sum_out, mean, rstd
 
 
+@_bracketed
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
                        dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False,
@@ -188,6 +223,7 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
     return dx, dres
 
 
+@_bracketed
 def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
     lib = _lib.load()
     M, N = x.shape
@@ -202,6 +238,7 @@ def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) ->
 # --------------------------------------------------------------------------------------------------
 # embedding epilogue, conv-subsampler pieces
 # --------------------------------------------------------------------------------------------------
+@_bracketed
 def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int, D: int, L: int, scale: float,
               p: float, seed: int, offset: int) -> Tensor:
     lib = _lib.load()
@@ -212,6 +249,7 @@ def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int,
     return out
 
 
+@_bracketed
 def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p: float, seed: int, offset: int,
               padding_idx: int = -1, dtable: Optional[Tensor] = None) -> Optional[Tensor]:
     lib = _lib.load()
@@ -222,6 +260,7 @@ def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p
     return dx
 
 
+@_bracketed
 def glu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
     out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
     _count(1)
@@ -229,6 +268,7 @@ def glu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tenso
     return out
 
 
+@_bracketed
 def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
     din = torch.empty(M, 2 * C, dtype=BF16, device=x.device)
     _count(1)
@@ -236,6 +276,7 @@ def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
     return din
 
 
+@_bracketed
 def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
     dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
     _count(1)
@@ -243,6 +284,7 @@ def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: i
     return dx
 
 
+@_bracketed
 def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
     out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
     _count(1)
@@ -250,6 +292,7 @@ def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tens
     return out
 
 
+@_bracketed
 def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
     _count(1)
     check(_lib.load().pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))
@@ -259,6 +302,7 @@ def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 # loss, optimizer, frontend
 # --------------------------------------------------------------------------------------------------
+@_bracketed
 def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smoothing: float, stats: Tensor,
                   write_grad: bool = True, grad_scale: float = 1.0, row_loss: Optional[Tensor] = None) -> None:
     """logits [B*T, V] bf16 (overwritten with the gradient), target [B, T] int64 (may be a strided view)."""
@@ -274,6 +318,7 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
 _SQNORM_WS = {}
 
 
+@_bracketed
 def grad32_flush(acc32: Tensor, grad: Tensor, ranges: Tensor, max_len: int) -> None:
     """bf16 gradient arena <- rounded fp32 main gradients over `ranges` (int64 [n, 2], device); zeroes the source."""
     _count(1)
@@ -281,6 +326,7 @@ def grad32_flush(acc32: Tensor, grad: Tensor, ranges: Tensor, max_len: int) -> N
                                          stream_ptr()))
 
 
+@_bracketed
 def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
     lib = _lib.load()
     ws = _SQNORM_WS.get(grad.device)
@@ -291,6 +337,7 @@ def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
                                 stream_ptr()))
 
 
+@_bracketed
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor) -> None:
     _count(1)
     check(_lib.load().pb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
@@ -301,6 +348,7 @@ def fbank_num_frames(num_samples: int) -> int:
     return int(_lib.load().pb200_fbank_num_frames(num_samples))
 
 
+@_bracketed
 def fbank_cmvn(pcm: Tensor, sample_offsets: Tensor, frame_offsets: Tensor, batch: int, max_frames: int,
                total_frames: int, pcm_scale: float = 32768.0, cmvn: bool = True, padded_frames: int = 0,
                front_pad: int = 0):

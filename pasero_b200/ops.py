@@ -130,6 +130,15 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+def _fc1_relu(x: Tensor, w1: Tensor, b1: Optional[Tensor]):
+    """h = relu(x W1^T + b1) and, when the shape allows, the 1-bit sign map of h that the fc2 dgrad epilogue uses as
+    its ReLU-backward mask (reading h itself there costs 16x the epilogue traffic)."""
+    bits = None
+    if K.relu_bits_supported(w1.shape[0], b1):
+        bits = torch.empty(w1.shape[0] // 32, x.shape[0], dtype=torch.int32, device=x.device)
+    return K.linear_fwd(x, w1, b1, act=1, relu_bits_out=bits), bits
+
+
 class FFNFn(torch.autograd.Function):
     """y = relu(x W1^T + b1) W2^T + b2 (pasero/models/transformer.py:999-1019); ReLU fused in the fc1 epilogue, its
     backward mask fused in the fc2 dgrad epilogue."""
@@ -137,18 +146,18 @@ class FFNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
         x = _c(x)
-        h = K.linear_fwd(x, w1, b1, act=1)
+        h, bits = _fc1_relu(x, w1, b1)
         y = K.linear_fwd(h, w2, b2)
-        ctx.save_for_backward(x, w1, w2, h)
+        ctx.save_for_backward(x, w1, w2, h, bits)
         ctx.params = (w1, b1, w2, b2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w1, w2, h = ctx.saved_tensors
+        x, w1, w2, h, bits = ctx.saved_tensors
         p_w1, p_b1, p_w2, p_b2 = ctx.params
         dy = _c(dy)
-        dh = K.linear_dgrad(dy, w2, relu_mask=h)
+        dh = K.linear_dgrad(dy, w2, relu_mask=h if bits is None else None, relu_bits=bits)
         dw2 = _wgrad(dy, h, p_w2)
         o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
         _ready(p_w2, p_b2)
@@ -322,23 +331,23 @@ class FFNSublayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, gamma, beta, p, eps):
         x = _c(x)
-        h = K.linear_fwd(x, w1, b1, act=1)
+        h, bits = _fc1_relu(x, w1, b1)
         y = K.linear_fwd(h, w2, b2)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
         out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset)
-        ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd)
+        ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd, bits)
         ctx.cfg = (p, seed, offset)
         ctx.params = (w1, b1, w2, b2, gamma, beta)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, w2, h, s, gamma, mean, rstd = ctx.saved_tensors
+        x, w1, w2, h, s, gamma, mean, rstd, bits = ctx.saved_tensors
         p, seed, offset = ctx.cfg
         p_w1, p_b1, p_w2, p_b2, p_gamma, p_beta = ctx.params
         dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2)
         _ready(p_gamma, p_beta)
-        dh = K.linear_dgrad(dy, w2, relu_mask=h)
+        dh = K.linear_dgrad(dy, w2, relu_mask=h if bits is None else None, relu_bits=bits)
         dw2 = _wgrad(dy, h, p_w2)
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1, residual=dres)

@@ -62,6 +62,14 @@ def test_gemm_dgrad_wgrad(M, N, K):
     h = _rand(M, K, seed=6)
     dxm = k.linear_dgrad(dy, w, relu_mask=h)
     _close(dxm, (dy.float() @ w.float()) * (h.float() > 0), 3e-2, 1e-2, 'dgrad+relu mask')
+    if K % 32 == 0:                              # 1-bit ReLU sign map written by the forward epilogue, applied by dgrad
+        b1 = _rand(K, seed=8)
+        bits = torch.empty(K // 32, M, dtype=torch.int32, device='cuda')
+        hh = k.linear_fwd(dy, w.T.contiguous(), b1, act=1, relu_bits_out=bits)
+        unpacked = ((bits.T.unsqueeze(-1) >> torch.arange(32, device='cuda', dtype=torch.int32)) & 1).reshape(M, K).bool()
+        assert torch.equal(unpacked, hh > 0)
+        dxb = k.linear_dgrad(dy, w, relu_bits=bits)
+        _close(dxb, (dy.float() @ w.float()) * (hh.float() > 0), 3e-2, 1e-2, 'dgrad+relu bits')
     dxr = k.linear_dgrad(dy, w, residual=h)     # skip-connection gradient added in the TMA-store epilogue
     _close(dxr, (dy.float() @ w.float()).to(BF16).float() + h.float(), 3e-2, 1e-2, 'dgrad+residual')
     dw = k.linear_wgrad(dy, x)
