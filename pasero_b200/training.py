@@ -364,6 +364,9 @@ class Trainer:
                 for k, v in tensors.items():
                     static[k].copy_(v)
                 self._graph_body(static, extras)
+                # the warm-up pass accumulated real gradients into the fp32 main-gradient arena; with buckets they are only
+                # flushed (and zeroed) after the replay below, which would add this batch's gradient a second time
+                self.arena.grad32.zero_()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             ops.DropoutState.offset = 0
