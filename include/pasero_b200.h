@@ -131,7 +131,9 @@ int pb200_attention_bwd(const pb200_attn_params* params, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta, int64_t M,
                              int64_t D, float eps, float p, uint64_t seed, uint64_t offset, const int64_t* offset_base,
-                             void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* stream);
+                             void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* keep_out, void* stream);
+/* keep_out (optional, uint8 [M * D / 8]): the dropout keep bits (bit j of byte e / 8 = element e + j kept); passing it
+ * back as keep_mask spares the backward kernel the Philox rounds. */
 size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
 /* backward: dx / dresidual, dgamma, dbeta and (optional) dbias_lin = column sums of dx, i.e. the bias gradient of the
  * Linear whose output was `x` (saves a separate pass over dx). accumulate: bit 0 = add into dgamma/dbeta, bit 1 = add
@@ -139,7 +141,8 @@ size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
 int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                              const float* mean, const float* rstd, int64_t M, int64_t D, float p, uint64_t seed,
                              uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx, void* dgamma, void* dbeta,
-                             void* dbias_lin, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+                             void* dbias_lin, int32_t accumulate, const void* keep_mask, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* column sums of a bf16 [M, N] matrix -> bf16 [N] (bias gradients) */
 size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);

@@ -59,10 +59,10 @@ PROTOTYPES = {
     'pb200_attention_fwd': (c_int32, [POINTER(AttnParams), _P]),
     'pb200_attention_bwd': (c_int32, [POINTER(AttnParams), _P]),
     'pb200_dropout_add_ln_fwd': (c_int32, [_P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,
-                                           _P, _P, _P, _P, _P, _P]),
+                                           _P, _P, _P, _P, _P, _P, _P]),
     'pb200_ln_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'pb200_dropout_add_ln_bwd': (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_uint64, c_uint64,
-                                           _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
+                                           _P, _P, _P, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     'pb200_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'pb200_colsum_bf16': (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_size_t, _P]),
     'pb200_embed_fwd': (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,

@@ -19,7 +19,7 @@ dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ r
                           const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int M, int D, float eps,
                           float p, uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
                           bf16* __restrict__ sum_out, bf16* __restrict__ y_out, float* __restrict__ mean_out,
-                          float* __restrict__ rstd_out) {
+                          float* __restrict__ rstd_out, uint8_t* __restrict__ keep_out) {
     pdl_trigger();
     pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
@@ -39,7 +39,10 @@ dropout_add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ r
             const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + e));
             const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
             uint32_t keep = 0xffu;
-            if (p > 0.f) keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+            if (p > 0.f) {
+                keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+                if (keep_out) keep_out[e >> 3] = (uint8_t)keep;   // one byte per 8 elements: backward skips the Philox rounds
+            }
             uint32_t rw[4] = {0, 0, 0, 0};
             if (residual) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + e));
@@ -118,7 +121,8 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
                           const bf16* __restrict__ sum, const bf16* __restrict__ gamma,
                           const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D, float p,
                           uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
-                          bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial, int want_lin) {
+                          bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial, int want_lin,
+                          const uint8_t* __restrict__ keep_in) {
     pdl_trigger();
     pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
@@ -145,16 +149,18 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
     const int stride = gridDim.x * LNB_WARPS;
     int row = blockIdx.x * LNB_WARPS + warp;
     uint4 nd[NCH], ns[NCH];
+    uint32_t nk[NCH];   // stored dropout keep bits of the next row (when keep_in is given)
     float nmu = 0.f, nrs = 1.f;
     auto fetch = [&](int r) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = c * 256 + lane * 8;
-            nd[c] = make_uint4(0, 0, 0, 0); ns[c] = make_uint4(0, 0, 0, 0);
+            nd[c] = make_uint4(0, 0, 0, 0); ns[c] = make_uint4(0, 0, 0, 0); nk[c] = 0xffu;
             if (r < M && col < D) {
                 const long long e = (long long)r * D + col;
                 nd[c] = __ldg(reinterpret_cast<const uint4*>(dy + e));
                 if (gamma) ns[c] = __ldg(reinterpret_cast<const uint4*>(sum + e));
+                if (keep_in && p > 0.f) nk[c] = (uint32_t)__ldg(keep_in + (e >> 3));
             }
         }
         if (gamma && r < M) { nmu = mean[r]; nrs = rstd[r]; }
@@ -162,8 +168,9 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
     fetch(row);
     for (; row < M; row += stride) {
         uint4 cd[NCH], cs[NCH];
+        uint32_t ck[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cs[c] = ns[c]; }
+        for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cs[c] = ns[c]; ck[c] = nk[c]; }
         const float mu = nmu, rs = nrs;
         fetch(row + stride);
         float s1 = 0.f, s2 = 0.f;
@@ -220,7 +227,7 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
                 for (int j = 0; j < 4; ++j) ow[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
                 if (dresidual) *reinterpret_cast<uint4*>(dresidual + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 if (p > 0.f) {
-                    const uint32_t keep = dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
+                    const uint32_t keep = keep_in ? ck[c] : dropout_keep8(rng, offset, (uint64_t)e >> 3, thresh);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 r = unpack_bf16x2(ow[j]);  // gradient reaching dropout is bf16
@@ -241,24 +248,26 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
         }
     }
     if (!partial) return;
-    // CTA-level sum in a fixed warp order (deterministic), then one partial row per CTA
-    __shared__ float red[3][NCH * 256];
-    for (int w = 0; w < LNB_WARPS; ++w) {
-        if (warp == w) {
+    // CTA-level sum: every warp parks its column sums in shared memory, then each thread adds the 8 warps' values of
+    // its columns in warp order (deterministic) and writes the CTA's partial row
+    extern __shared__ float red[];   // [LNB_WARPS][3][NCH * 256]
+    constexpr int W = NCH * 256;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = c * 256 + lane * 8 + j;
-                    if (w == 0) { red[0][i] = dg[c][j]; red[1][i] = db[c][j]; red[2][i] = dl[c][j]; }
-                    else { red[0][i] += dg[c][j]; red[1][i] += db[c][j]; red[2][i] += dl[c][j]; }
-                }
+        for (int j = 0; j < 8; ++j) {
+            const int i = c * 256 + lane * 8 + j;
+            red[(warp * 3 + 0) * W + i] = dg[c][j];
+            red[(warp * 3 + 1) * W + i] = db[c][j];
+            red[(warp * 3 + 2) * W + i] = dl[c][j];
         }
-        __syncthreads();
-    }
+    __syncthreads();
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
         const int which = i / D, col = i % D;
-        partial[((long long)blockIdx.x * 3 + which) * D + col] = red[which][col];
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < LNB_WARPS; ++w) a += red[(w * 3 + which) * W + col];
+        partial[((long long)blockIdx.x * 3 + which) * D + col] = a;
     }
 }
 
@@ -385,7 +394,7 @@ extern "C" size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D) {
 extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
                                         int64_t M, int64_t D, float eps, float p, uint64_t seed, uint64_t offset,
                                         const int64_t* offset_base, void* sum_out, void* y_out, float* mean_out,
-                                        float* rstd_out, void* stream_) {
+                                        float* rstd_out, void* keep_out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported (multiple of 8, <= 1024)", (long long)D);
@@ -397,7 +406,8 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
 #define PB_LN_FWD(N_)                                                                                         \
     PB_CUDA(launch_pdl(dropout_add_ln_fwd_kernel<N_>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,                \
         (const bf16*)x, (const bf16*)residual, (const bf16*)gamma, (const bf16*)beta, (int)M, (int)D, eps, p,  \
-        seed, offset, (const long long*)offset_base, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out))
+        seed, offset, (const long long*)offset_base, (bf16*)sum_out, (bf16*)y_out, mean_out, rstd_out,         \
+        (uint8_t*)keep_out))
     switch (nch) { case 1: PB_LN_FWD(1); break; case 2: PB_LN_FWD(2); break; case 3: PB_LN_FWD(3); break; default: PB_LN_FWD(4); }
 #undef PB_LN_FWD
     PB_LAUNCH_CHECK();
@@ -407,8 +417,8 @@ extern "C" int pb200_dropout_add_ln_fwd(const void* x, const void* residual, con
 extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                                         const float* mean, const float* rstd, int64_t M, int64_t D, float p,
                                         uint64_t seed, uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx,
-                                        void* dgamma, void* dbeta, void* dbias_lin, int32_t accumulate, void* workspace,
-                                        size_t workspace_bytes, void* stream_) {
+                                        void* dgamma, void* dbeta, void* dbias_lin, int32_t accumulate, const void* keep_mask,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0 && D <= 1024 && D > 0, "LayerNorm width %lld unsupported", (long long)D);
@@ -420,10 +430,13 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
     }
     const int nch = (int)((D + 255) / 256);
 #define PB_LN_BWD(N_)                                                                                        \
-    PB_CUDA(launch_pdl(dropout_add_ln_bwd_kernel<N_>, dim3(grid), dim3(LNB_WARPS * 32), 0, stream,              \
+    PB_CUDA(cudaFuncSetAttribute(dropout_add_ln_bwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 LNB_WARPS * 3 * N_ * 256 * 4));                                                \
+    PB_CUDA(launch_pdl(dropout_add_ln_bwd_kernel<N_>, dim3(grid), dim3(LNB_WARPS * 32),                         \
+                       (size_t)(partial ? LNB_WARPS * 3 * N_ * 256 * 4 : 0), stream,                              \
         (const bf16*)dy, (const bf16*)dsum_extra, (const bf16*)sum, (const bf16*)gamma, mean, rstd, (int)M,   \
         (int)D, p, seed, offset, (const long long*)offset_base, (bf16*)dresidual, (bf16*)dx, partial,          \
-        dbias_lin != nullptr ? 1 : 0))
+        dbias_lin != nullptr ? 1 : 0, (const uint8_t*)keep_mask))
     switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();

@@ -184,7 +184,7 @@ def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse:
 # --------------------------------------------------------------------------------------------------
 @_bracketed
 def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
-                       eps: float, p: float, seed: int, offset: int, need_sum: bool = True):
+                       eps: float, p: float, seed: int, offset: int, need_sum: bool = True, keep_out: Optional[Tensor] = None):
     lib = _lib.load()
     M, D = x.shape
     dev = x.device
@@ -196,7 +196,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     rstd = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     _count(1)
     check(lib.pb200_dropout_add_ln_fwd(x.data_ptr(), ptr(residual), ptr(gamma), ptr(beta), M, D, eps, p, seed, offset,
-                                       ptr(RNG_OFFSET_BASE), ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), stream_ptr()))
+                                       ptr(RNG_OFFSET_BASE), ptr(sum_out), ptr(y), ptr(mean), ptr(rstd), ptr(keep_out), stream_ptr()))
     if sum_out is None:
         sum_out = x  # LN of x alone: the saved pre-norm input is x itself
     return (y if has_ln else sum_out), sum_out, mean, rstd
@@ -206,7 +206,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
                        dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False,
-                       dbias_lin: Optional[Tensor] = None, accumulate_lin: bool = False):
+                       dbias_lin: Optional[Tensor] = None, accumulate_lin: bool = False, keep_mask: Optional[Tensor] = None):
     """dbias_lin (bf16 [D], optional) receives the column sums of dx = the bias gradient of the Linear that produced x."""
     lib = _lib.load()
     M, D = dy.shape
@@ -218,7 +218,7 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
     _count(2 if need_ws else 1)
     check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
                                        p, seed, offset, ptr(RNG_OFFSET_BASE), ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
-                                       ptr(dbias_lin), int(accumulate) | (int(accumulate_lin) << 1), ptr(ws),
+                                       ptr(dbias_lin), int(accumulate) | (int(accumulate_lin) << 1), ptr(keep_mask), ptr(ws),
                                        ws.numel() if ws is not None else 0, stream_ptr()))
     return dx, dres
 

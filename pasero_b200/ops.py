@@ -238,7 +238,12 @@ class AttentionFn(torch.autograd.Function):
                 None, None, None, None, None, None, None)
 
 
-def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias):
+def _keep_buffer(x: Tensor, p: float) -> Optional[Tensor]:
+    """uint8 [M * D / 8] buffer for the dropout keep bits (saved for backward instead of re-running Philox there)."""
+    return torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+
+
+def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=None):
     """Shared backward of `LN(residual + dropout(x))`: returns (dx, dresidual, dgamma, dbeta, dlin_bias) with the
     parameter gradients routed through DirectGrads when active (None is returned for those)."""
     p_gamma, p_beta = params
@@ -250,7 +255,7 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias):
     dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
     dlin = sl if sl is not None else (torch.empty(D, dtype=BF16, device=dy.device) if lin_bias is not None else None)
     dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
-                                    accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al)
+                                    accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep)
     return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
 
 
@@ -277,19 +282,20 @@ class AttnSublayerFn(torch.autograd.Function):
         o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
         y = K.linear_fwd(o, out_w, out_b)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
-        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset)
-        ctx.save_for_backward(x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd)
+        keep = _keep_buffer(y, p)
+        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset, keep_out=keep)
+        ctx.save_for_backward(x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd, keep)
         ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset)
         ctx.params = (in_w, in_b, out_w, out_b, gamma, beta)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd = ctx.saved_tensors
+        x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd, keep = ctx.saved_tensors
         B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset = ctx.dims
         D = H * 64
         p_in_w, p_in_b, p_out_w, p_out_b, p_gamma, p_beta = ctx.params
-        dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b)
+        dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b, keep)
         _ready(p_gamma, p_beta)
         d_o = K.linear_dgrad(dy, out_w)
         d_out_w = _wgrad(dy, o, p_out_w)
@@ -334,18 +340,19 @@ class FFNSublayerFn(torch.autograd.Function):
         h, bits = _fc1_relu(x, w1, b1)
         y = K.linear_fwd(h, w2, b2)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
-        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset)
-        ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd, bits)
+        keep = _keep_buffer(y, p)
+        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset, keep_out=keep)
+        ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd, bits, keep)
         ctx.cfg = (p, seed, offset)
         ctx.params = (w1, b1, w2, b2, gamma, beta)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, w2, h, s, gamma, mean, rstd, bits = ctx.saved_tensors
+        x, w1, w2, h, s, gamma, mean, rstd, bits, keep = ctx.saved_tensors
         p, seed, offset = ctx.cfg
         p_w1, p_b1, p_w2, p_b2, p_gamma, p_beta = ctx.params
-        dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2)
+        dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2, keep)
         _ready(p_gamma, p_beta)
         dh = K.linear_dgrad(dy, w2, relu_mask=h if bits is None else None, relu_bits=bits)
         dw2 = _wgrad(dy, h, p_w2)

@@ -205,6 +205,14 @@ def test_dropout_mask_consistency():
     dx, dres = k.dropout_add_ln_bwd(dy, None, None, None, None, None, p, 1234, 7, True)
     assert torch.equal(dx.float() > 0, keep)
     assert torch.equal(dres, dy)
+    # the keep bits stored by forward (one byte per 8 elements) give backward the same mask without Philox
+    kb = torch.zeros(M * D // 8, dtype=torch.uint8, device='cuda')
+    s1, _, _, _ = k.dropout_add_ln_fwd(x, r, None, None, 1e-5, p, 1234, 7, keep_out=kb)
+    assert torch.equal(s1, s)
+    bits = ((kb.view(-1, 1) >> torch.arange(8, device='cuda', dtype=torch.uint8)) & 1).reshape(M, D).bool()
+    assert torch.equal(bits, keep)
+    dx1, _ = k.dropout_add_ln_bwd(dy, None, None, None, None, None, p, 999, 999, True, keep_mask=kb)   # seed/offset unused
+    assert torch.equal(dx1, dx)
     # a different offset gives a different mask
     s2, _, _, _ = k.dropout_add_ln_fwd(x, r, None, None, 1e-5, p, 1234, 8)
     assert not torch.equal(s2, s)
