@@ -55,11 +55,17 @@ struct GemmDev {
 // traffic (ncu: ~10 TB/s of TMA loads, the chip-wide L2 limit, with the tensor pipe ~50 % busy).
 template <int BN, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int STAGES = PAIR ? 6 : ((BN == 128) ? 6 : 4);
+    // BN == 512 (CTA pair only): one 256 x 512 tile per pair and a single 512-column accumulator — for the N = 512
+    // GEMMs of this model every pair then owns exactly one tile (63 tiles on 74 pairs) instead of 1.7 waves of 256-wide
+    // tiles, and the A operand is fetched once instead of twice
+    static constexpr int STAGES = BN == 512 ? 4 : (PAIR ? 6 : ((BN == 128) ? 6 : 4));
+    static constexpr int NACC = BN == 512 ? 1 : 2;          // accumulator buffers in TMEM
+    static constexpr int NH = BN == 512 ? 2 : 1;            // tcgen05.mma N is at most 256: N-halves per k-step
+    static constexpr int MMA_N = BN / NH;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int TMEM_COLS = NACC * BN;
     static constexpr int EPI_BUF_BYTES = 32 * 128;                 // 32 rows x 64 bf16, SWIZZLE_128B
     static constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -165,12 +171,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                             for (int j = 0; j < BM / 64; ++j)
                                 ptx::tma_load_3d_2sm(&tma, &full_bar[stage], sa + j * (BK * 128), m0 + j * 64, k0, za);
                         }
-                        if (!B_MN) {   // this CTA's BN/2 rows of the B tile
-                            ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sb, k0, n0 + cta_rank * (BN / 2), zb);
-                        } else {
+                        // this CTA's half of each MMA_N-wide slice of the B tile (MMA h reads rows / columns
+                        // [h * MMA_N/2, (h + 1) * MMA_N/2) of both CTAs' B buffers)
 #pragma unroll
-                            for (int j = 0; j < BN / 128; ++j)
-                                ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sb + j * (BK * 128), n0 + cta_rank * (BN / 2) + j * 64, k0, zb);
+                        for (int h = 0; h < Cfg::NH; ++h) {
+                            const int nh = n0 + h * Cfg::MMA_N + cta_rank * (Cfg::MMA_N / 2);
+                            uint8_t* sbh = sb + h * (Cfg::MMA_N / 2) * 128;
+                            if (!B_MN) {
+                                ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sbh, k0, nh, zb);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < Cfg::MMA_N / 128; ++j)
+                                    ptx::tma_load_3d_2sm(&tmb, &full_bar[stage], sbh + j * (BK * 128), nh + j * 64, k0, zb);
+                            }
                         }
                         if (cta_rank != 0) ptx::mbar_arrive_remote(&full_bar[stage], 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -210,7 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread; the leader CTA's in PAIR mode) =====================
         if (lane == 0 && (!PAIR || cta_rank == 0)) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, Cfg::MMA_N, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -218,11 +231,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 const int split = tile % p.splits;
                 const int kb_begin = split * p.kb_per_split;
                 const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-                const int acc = local & 1;
-                const uint32_t acc_phase = (local >> 1) & 1;
+                const int acc = Cfg::NACC == 2 ? (local & 1) : 0;
+                const uint32_t acc_phase = (Cfg::NACC == 2 ? (local >> 1) : local) & 1;
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * BN;   // (acc == 0 when there is a single accumulator)
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -237,8 +250,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                                                     : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                     : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        if (PAIR) ptx::umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-                        else ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        if (PAIR) {
+#pragma unroll
+                            for (int h = 0; h < Cfg::NH; ++h)   // + 16 KB = the next MMA_N/2 rows (K-major) or 64-column boxes (MN-major)
+                                ptx::umma_bf16_2sm(tmem_d + h * Cfg::MMA_N, adesc, bdesc + (uint64_t)(h * (Cfg::MMA_N / 2) * 128 >> 4), idesc,
+                                                   (kb > kb_begin || k > 0) ? 1u : 0u);
+                        } else {
+                            ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        }
                     }
                     // frees the smem slot (in every CTA of the cluster: peers multicast into it / the pair's MMA read it)
                     // when these MMAs retire
@@ -273,8 +292,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             const int n0 = n_blk * BN;
             const int row = m_blk * BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
-            const int acc = local & 1;
-            const uint32_t acc_phase = (local >> 1) & 1;
+            const int acc = Cfg::NACC == 2 ? (local & 1) : 0;
+            const uint32_t acc_phase = (Cfg::NACC == 2 ? (local >> 1) : local) & 1;
             const int kb_begin = split * p.kb_per_split;
             const bool empty_range = kb_begin >= p.total_kb;
 
@@ -340,9 +359,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 const long long coff_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
                 // bias for the whole tile: lane l keeps columns [n0 + 8l, n0 + 8l + 8); broadcast by shuffle later, so
                 // no global-load latency sits between the TMEM reads and the stores
-                uint4 bias_reg = make_uint4(0, 0, 0, 0);
+                uint4 bias_reg = make_uint4(0, 0, 0, 0), bias_reg2 = make_uint4(0, 0, 0, 0);   // columns [0,256) / [256,512)
                 if ((EPI == 1 || EPI == 2) && lane * 8 < BN && n0 + lane * 8 < p.N)
                     bias_reg = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + lane * 8));
+                if ((EPI == 1 || EPI == 2) && BN > 256 && n0 + 256 + lane * 8 < p.N)
+                    bias_reg2 = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + 256 + lane * 8));
 #pragma unroll 1
                 for (int c64 = 0; c64 < BN / 64; ++c64) {
                     const int col0 = n0 + c64 * 64;
@@ -377,9 +398,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 #pragma unroll
                             for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]);
                             if constexpr (EPI == 1 || EPI == 2) {
-                                const int src = c64 * 8 + half * 4 + g8;
-                                const uint32_t bw[4] = {__shfl_sync(0xffffffffu, bias_reg.x, src), __shfl_sync(0xffffffffu, bias_reg.y, src),
-                                                        __shfl_sync(0xffffffffu, bias_reg.z, src), __shfl_sync(0xffffffffu, bias_reg.w, src)};
+                                const int src = (c64 & 3) * 8 + half * 4 + g8;
+                                const uint4 br = (BN > 256 && c64 >= 4) ? bias_reg2 : bias_reg;   // warp-uniform
+                                const uint32_t bw[4] = {__shfl_sync(0xffffffffu, br.x, src), __shfl_sync(0xffffffffu, br.y, src),
+                                                        __shfl_sync(0xffffffffu, br.z, src), __shfl_sync(0xffffffffu, br.w, src)};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float2 b2 = unpack_bf16x2(bw[j]);
@@ -709,6 +731,22 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         const bool can_split = q->split_k != 1 && kb_all >= 32 && (q->workspace != nullptr || direct_acc);   // split-K fills the SMs instead
         if (tiles256 * 2 >= num_sms() || can_split || q->tile_n == 256) bn = 256;
     }
+    // 256 x 512 tiles on CTA pairs (single 512-column accumulator: the epilogue is not overlapped with the next tile, but A
+    // is fetched half as often): pays off for long reductions (8192^3: 1498 -> 1627 TFLOP/s); measured NOT to pay off for
+    // the K <= 2048, N = 512 GEMMs of this model even though each pair would then own exactly one tile, so it is chosen
+    // automatically only when K >= 4096
+    {
+        const long long pairs = num_sms() / 2;
+        const long long tiles512 = Zout * ((m_blks + 1) / 2) * ((q->n + 511) / 512);
+        const bool simple_epi = !q->out_fp32 && !q->accumulate && q->alpha == 1.0f && q->act == 0 && !q->relu_mask &&
+                                !q->relu_bits && !q->relu_bits_out && !(q->bias && q->residual) &&
+                                (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && q->c_batch_stride % 8 == 0 &&
+                                (!q->residual || (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0);
+        const bool fits = q->k >= 4096 && q->n % 512 == 0 && tiles512 >= pairs;
+        if (!a_mn && q->split_k == 1 && m_blks >= 2 && (q->cluster_m == 0 || q->cluster_m == 2) && simple_epi &&
+            ((q->tile_n == 0 && fits) || q->tile_n == 512))
+            bn = 512;
+    }
     const long long n_blks = (q->n + bn - 1) / bn;
     const long long kb_per = (q->k + BK - 1) / BK;
     const long long total_kb = kb_per * (q->reduce_batch ? Zall : 1);
@@ -775,7 +813,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     if (m_blks < 2) cl = 1;
     if (cl == 4 && b_mn && bn == 128) cl = 2;
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
-    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn / cl);
+    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn == 512 ? 128 : bn / cl);
     else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zall, q->b_batch_stride, 64, BK);
     if (rc) return rc;
 
@@ -832,7 +870,18 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
             default: PB_DISPATCH2(BN_, -1); break;                \
         }                                                         \
     } while (0)
-    if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
+    if (bn == 512) {   // CTA pair, K-major A, plain / bias / residual epilogues only (see the tile choice above)
+        PB_CHECK(cl == 2 && !a_mn && (epi == 0 || epi == 1 || epi == 5), "internal: 512-wide tile chosen for an unsupported variant");
+        if (!b_mn) {
+            if (epi == 0) rc = launch_gemm<512, false, false, 0, 2>(ta, tb, tc, d, grid, stream);
+            else if (epi == 1) rc = launch_gemm<512, false, false, 1, 2>(ta, tb, tc, d, grid, stream);
+            else rc = launch_gemm<512, false, false, 5, 2>(ta, tb, tc, d, grid, stream);
+        } else {
+            if (epi == 0) rc = launch_gemm<512, false, true, 0, 2>(ta, tb, tc, d, grid, stream);
+            else if (epi == 1) rc = launch_gemm<512, false, true, 1, 2>(ta, tb, tc, d, grid, stream);
+            else rc = launch_gemm<512, false, true, 5, 2>(ta, tb, tc, d, grid, stream);
+        }
+    } else if (bn == 128) PB_DISPATCH(128); else PB_DISPATCH(256);
 #undef PB_DISPATCH3
 #undef PB_DISPATCH2
 #undef PB_DISPATCH

@@ -42,6 +42,20 @@ def test_gemm_forward(M, N, K, tile_n, cluster_m):
     _close(y, ref, 2e-2, 1e-2, 'linear_fwd')
 
 
+@pytest.mark.parametrize('M,N,K', [(1000, 512, 512), (4096, 1024, 256), (300, 136, 200), (16000, 512, 2048)])
+def test_gemm_tile512(M, N, K):
+    """256 x 512 tiles on CTA pairs (single accumulator, two N = 256 MMAs per k-step): forced, and with each epilogue."""
+    k = _k()
+    x, w, b, r = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    ref = x.float() @ w.float().T
+    _close(k.linear_fwd(x, w, b, tile_n=512), ref + b.float(), 2e-2, 1e-2, 'tile512 bias')
+    _close(k.linear_fwd(x, w, None, tile_n=512), ref, 2e-2, 1e-2, 'tile512 plain')
+    wt = w.T.contiguous()    # [K, N]: the MN-major B operand of a dgrad
+    y = torch.empty(M, N, dtype=BF16, device='cuda')
+    k.gemm_raw(x.data_ptr(), wt.data_ptr(), y, M, N, K, lda=K, ldb=N, ldc=N, b_mn_major=True, residual=r, split_k=1, tile_n=512)
+    _close(y, ref.to(BF16).float() + r.float(), 3e-2, 1e-2, 'tile512 MN-major B + residual')
+
+
 def test_gemm_epilogues():
     k = _k()
     M, N, K = 513, 384, 256

@@ -73,7 +73,7 @@ def main():
         b = torch.randn(N, device=dev).to(BF16)
         dy = torch.randn(M, N, device=dev).to(BF16)
         fl = 2.0 * M * N * K
-        for tn, cl in ((128, 1), (256, 1), (256, 2), (256, 4)):
+        for tn, cl in ((128, 1), (256, 1), (256, 2), (256, 4), (512, 2)):
             t = timeit(lambda: k.linear_fwd(x, w, b, tile_n=tn, cluster_m=cl))
             out[f'fwd {M}x{N}x{K} tn{tn} cl{cl}'] = (t, fl / t / 1e9)
         t = timeit(lambda: torch.nn.functional.linear(x, w, b))
