@@ -32,6 +32,8 @@ class STConfig:
     conv_channels: int = 1024
     conv_kernel_sizes: tuple = (5, 5)
     conv_strides: tuple = (2, 2)
+    conv_activation: str = 'glu'              # 'gelu' for the Whisper family (config.py:2559)
+    positional_encoding: str = 'sinusoidal'   # 'learned': LearnedPositionalEmbedding (modules.py:460-484)
     encoder_prenorm: bool = False
     decoder_prenorm: bool = False
     activation_fn: str = 'relu'
@@ -160,15 +162,18 @@ def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tenso
     for i, (k, s) in enumerate(zip(cfg.conv_kernel_sizes, cfg.conv_strides)):
         x = F.conv1d(x, sd[f'encoder.subsample.conv_layers.{i}.weight'], sd[f'encoder.subsample.conv_layers.{i}.bias'],
                      stride=s, padding=k // 2)
-        x = F.glu(x, dim=1)
+        x = F.glu(x, dim=1) if cfg.conv_activation == 'glu' else F.gelu(x)   # modules.py:803, 831-832
     x = x.transpose(1, 2)
     length = conv_out_length(encoder_input_length, cfg.conv_kernel_sizes, cfg.conv_strides)
     if cfg.scale_embed:
         x = x * math.sqrt(cfg.embed_dim)
     mask = len_to_mask(length, x.shape[1])
     max_len = int(conv_out_length(torch.tensor(cfg.encoder_max_len), cfg.conv_kernel_sizes, cfg.conv_strides))
-    table = sinusoidal_table(max_len, cfg.embed_dim, cfg.positional_encoding_shift)
-    x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
+    if cfg.positional_encoding == 'learned':   # rows shift .. shift + S - 1 of the trainable table
+        x = x + sd['encoder.embed_positions.weight'][cfg.positional_encoding_shift:cfg.positional_encoding_shift + x.shape[1]].unsqueeze(0)
+    else:
+        table = sinusoidal_table(max_len, cfg.embed_dim, cfg.positional_encoding_shift)
+        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
     if layer_outputs is not None:
         layer_outputs['enc_embed'] = x
     for i in range(cfg.encoder_layers):
@@ -186,8 +191,11 @@ def decode(cfg: STConfig, sd, enc: Tensor, enc_mask: Tensor, decoder_input: Tens
     x = F.embedding(decoder_input.clip(min=0), emb, padding_idx=cfg.padding_idx)
     if cfg.scale_embed:
         x = x * math.sqrt(cfg.embed_dim)
-    table = sinusoidal_table(cfg.decoder_max_len, cfg.embed_dim, cfg.positional_encoding_shift)
-    x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
+    if cfg.positional_encoding == 'learned':
+        x = x + sd['decoder.embed_positions.weight'][cfg.positional_encoding_shift:cfg.positional_encoding_shift + x.shape[1]].unsqueeze(0)
+    else:
+        table = sinusoidal_table(cfg.decoder_max_len, cfg.embed_dim, cfg.positional_encoding_shift)
+        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
     for i in range(cfg.decoder_layers):
         x = decoder_layer(cfg, sd, f'decoder.layers.{i}.', x, enc, enc_mask)
         if layer_outputs is not None:

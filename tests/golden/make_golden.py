@@ -73,6 +73,53 @@ def make_task_and_model(pasero, tmp, extra=()):
     return cfg, task, model
 
 
+def make_whisper_model(pasero, tmp):
+    """Whisper-style tiny model (`--arch whisper_base` scaled down; pasero/config.py:2539-2566) on the same dictionary."""
+    from pasero.config import TrainingConfig, get_task_class, get_architecture
+    t = synth.WSP
+    args = ['--task', 'speech_translation', '--arch', 'whisper_base',
+            '--encoder-layers', str(t['encoder_layers']), '--decoder-layers', str(t['decoder_layers']),
+            '--embed-dim', str(t['embed_dim']), '--encoder-ffn-dim', str(t['ffn_dim']), '--decoder-ffn-dim', str(t['ffn_dim']),
+            '--encoder-attention-heads', str(t['heads']), '--decoder-attention-heads', str(t['heads']),
+            '--conv-channels', str(t['conv_channels']), '--data-dir', tmp, '--dict', 'dict.txt', '--tokenizer-path', 'bpecodes',
+            '--source-lang', 'de', '--target-lang', 'en', '--model-dir', os.path.join(tmp, 'model_wsp'),
+            '--encoder-max-len', str(t['encoder_max_len']), '--decoder-max-len', str(t['decoder_max_len']),
+            '--batch-size', '64000', '--dropout', '0', '--label-smoothing', '0.1', '--metrics',
+            '--early-stopping-metric', 'nll_loss', '--max-steps', '1000', '--valid-interval', '1000', '--dataset-type', 'simple',
+            '--dtype', 'float32', '--seed', '1234', '--padding-idx', '1', '--eos-idx', '2', '--bos-idx', '2']
+    cfg = TrainingConfig(*args)
+    task = get_task_class(cfg.task)(cfg.data_dir, cfg.task_cfg)
+    task.setup_for_model(cfg.model_cfg)
+    cfg.dp_size, cfg.dp_rank, cfg.dp_local_size, cfg.dp_local_rank, cfg.start_rank = 1, 0, 1, 0, 0
+    torch.manual_seed(1234)
+    model = get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)
+    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == synth.wsp_param_shapes(), \
+        {k: tuple(v.shape) for k, v in model.named_parameters() if synth.wsp_param_shapes().get(k) != tuple(v.shape)}
+    missing = model.load_state_dict(synth.wsp_state_dict(), strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys, missing
+    return cfg, task, model
+
+
+def golden_model_whisper(pasero, cfg, task, model, out):
+    model.train()
+    batch = synth.model_batch()
+    names = ['enc_0', f"enc_{synth.WSP['encoder_layers'] - 1}", 'dec_0', f"dec_{synth.WSP['decoder_layers'] - 1}"]
+    enc_out, enc_mask, enc_layers = model.encoder(batch['encoder_input'].clone(), batch['encoder_input_length'], return_layers=names)
+    logits, dec_layers = model.decoder(enc_out, enc_mask, batch['decoder_input'][:, :-1], return_layers=names)
+    loss, logs = model(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    model.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    torch.save({
+        'cfg': synth.WSP, 'state_dict_keys': sorted(model.state_dict().keys()),
+        'loss': loss.item(), 'logs': logs, 'encoder_out': enc_out.detach(), 'encoder_mask': enc_mask, 'logits': logits.detach(),
+        'layers': {k: v.detach() for k, v in {**enc_layers, **dec_layers}.items()},
+        'grads': {k: synth.summarize_grad(v) for k, v in grads.items()},
+        'param_names': [k for k, _ in model.named_parameters()],
+    }, os.path.join(out, 'st_wsp_model.pt'))
+    print('whisper-style model golden: loss', loss.item(), logs, 'params', sum(p.numel() for p in model.parameters()))
+
+
 def golden_fbank(out):
     import torchaudio
     res = {}
@@ -210,6 +257,15 @@ def golden_training_curve(pasero, cfg, task, model, out):
 def main():
     out = HERE
     pasero = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'whisper':      # only the Whisper-style fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            make_task_and_model(pasero, tmp)                  # writes dict.txt / bpecodes
+            cfg3, task3, model3 = make_whisper_model(pasero, tmp)
+            golden_model_whisper(pasero, cfg3, task3, model3, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     golden_fbank(out)
     tmp = tempfile.mkdtemp()
     try:
@@ -218,6 +274,8 @@ def main():
         golden_model(pasero, cfg, task, model, out)
         cfg2, task2, model2 = make_task_and_model(pasero, tmp)
         golden_training_curve(pasero, cfg2, task2, model2, out)
+        cfg3, task3, model3 = make_whisper_model(pasero, tmp)
+        golden_model_whisper(pasero, cfg3, task3, model3, out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -135,6 +135,71 @@ def tiny_state_dict() -> dict:
     return sd
 
 
+# ---- Whisper-style variant (BASELINE config 4 shape family, pasero/config.py:2539-2566): pre-norm, GELU, learned positions,
+# conv k=3,3 strides 1,2 with GELU, no embedding scale, no key bias, final encoder / decoder LayerNorm
+WSP = dict(vocab_size=200, encoder_layers=2, decoder_layers=2, embed_dim=128, ffn_dim=256, heads=2, conv_channels=128,
+           encoder_max_len=400, decoder_max_len=64)
+
+
+def wsp_param_shapes() -> dict:
+    t = WSP
+    d, f, c, v = t['embed_dim'], t['ffn_dim'], t['conv_channels'], t['vocab_size']
+    shapes = {
+        'encoder.subsample.conv_layers.0.weight': (c, 80, 3), 'encoder.subsample.conv_layers.0.bias': (c,),
+        'encoder.subsample.conv_layers.1.weight': (d, c, 3), 'encoder.subsample.conv_layers.1.bias': (d,),
+        'encoder.embed_positions.weight': (t['encoder_max_len'] // 2, d),
+    }
+
+    def attn(prefix):
+        for p in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+            shapes[f'{prefix}.{p}.weight'] = (d, d)
+            if p != 'k_proj':            # attention_key_bias=False (modules.py:516-522)
+                shapes[f'{prefix}.{p}.bias'] = (d,)
+
+    def ln(prefix):
+        shapes[f'{prefix}.weight'] = (d,)
+        shapes[f'{prefix}.bias'] = (d,)
+
+    def ffn(prefix):
+        shapes[f'{prefix}.fc1.weight'] = (f, d)
+        shapes[f'{prefix}.fc1.bias'] = (f,)
+        shapes[f'{prefix}.fc2.weight'] = (d, f)
+        shapes[f'{prefix}.fc2.bias'] = (d,)
+
+    for i in range(t['encoder_layers']):
+        p = f'encoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm')
+    ln('encoder.layer_norm')
+    shapes['decoder.embed_tokens.weight'] = (v, d)
+    shapes['decoder.embed_positions.weight'] = (t['decoder_max_len'], d)
+    for i in range(t['decoder_layers']):
+        p = f'decoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm')
+        attn(p + '.encoder_attn'); ln(p + '.encoder_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm')
+    ln('decoder.layer_norm')
+    return shapes
+
+
+def wsp_state_dict() -> dict:
+    rng = np.random.RandomState(77)
+    sd = {}
+    for name, shape in wsp_param_shapes().items():
+        if 'layer_norm' in name:
+            w = (1.0 + 0.1 * rng.randn(*shape)) if name.endswith('weight') else 0.05 * rng.randn(*shape)
+        elif name.endswith('bias'):
+            w = 0.02 * rng.randn(*shape)
+        elif name.endswith('embed_positions.weight'):
+            w = 0.05 * rng.randn(*shape)
+        elif name == 'decoder.embed_tokens.weight':
+            w = rng.randn(*shape) * shape[1] ** -0.5
+            w[PAD] = 0
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            w = rng.randn(*shape) * fan_in ** -0.5
+        sd[name] = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+    return sd
+
+
 def summarize_grad(g: torch.Tensor) -> dict:
     """Compact but discriminating digest of a gradient tensor (full tensor when small)."""
     g = g.detach().float()

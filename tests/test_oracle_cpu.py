@@ -134,6 +134,45 @@ def curve_close(got: list, want: list, pointwise_steps: int = 100, pointwise_tol
         assert abs(a - b) / b < window_tol, (s0, a, b)
 
 
+def wsp_cfg(**kw) -> om.STConfig:
+    """Whisper-style variant (pasero/config.py:2539-2566 scaled down like tests/golden/synth.WSP)."""
+    t = synth.WSP
+    return om.STConfig(embed_dim=t['embed_dim'], encoder_layers=t['encoder_layers'], decoder_layers=t['decoder_layers'],
+                       encoder_attention_heads=t['heads'], decoder_attention_heads=t['heads'],
+                       encoder_ffn_dim=t['ffn_dim'], decoder_ffn_dim=t['ffn_dim'], conv_channels=t['conv_channels'],
+                       vocab_size=t['vocab_size'], conv_kernel_sizes=(3, 3), conv_strides=(1, 2), conv_activation='gelu',
+                       positional_encoding='learned', positional_encoding_shift=0, scale_embed=False, encoder_prenorm=True,
+                       decoder_prenorm=True, activation_fn='gelu', encoder_max_len=t['encoder_max_len'],
+                       decoder_max_len=t['decoder_max_len'], **kw)
+
+
+def test_whisper_variant_matches_reference():
+    """Pre-norm + GELU + learned positions + GELU conv subsampler (k=3,3 strides 1,2) + no key bias: BASELINE config 4's
+    architecture family, pinned to the reference's own outputs like the default ST model."""
+    gold = torch.load(os.path.join(GOLD, 'st_wsp_model.pt'), weights_only=False)
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.wsp_state_dict().items()}
+    batch = synth.model_batch()
+    layers = {}
+    loss, logs = om.forward(wsp_cfg(), sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'], layers)
+    assert abs(loss.item() - gold['loss']) < 1e-3 * abs(gold['loss'])
+    assert logs['num_tokens'] == gold['logs']['num_tokens'] and logs['num_lines'] == gold['logs']['num_lines']
+    assert abs(logs['nll_loss'] - gold['logs']['nll_loss']) < 1e-3 * gold['logs']['nll_loss']
+    assert torch.allclose(layers['encoder_out'], gold['encoder_out'], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(layers['logits'], gold['logits'], atol=2e-4, rtol=1e-4)
+    for k, v in gold['layers'].items():
+        assert torch.allclose(layers[k], v, atol=2e-4, rtol=1e-4), k
+    loss.backward()
+    assert sorted(sd.keys()) == sorted(gold['param_names'])
+    for k, d in gold['grads'].items():
+        g = sd[k].grad
+        if 'full' in d:
+            assert torch.allclose(g, d['full'], atol=2e-4, rtol=2e-3), k
+        else:
+            g2 = g.reshape(g.shape[0], -1)
+            assert torch.allclose(g2[:4], d['rows'], atol=2e-4, rtol=2e-3), k
+            assert torch.allclose(g2.sum(1), d['row_sum'], atol=2e-3, rtol=2e-3), k
+
+
 def test_train_step_curve_matches_reference():
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
     cfg = tiny_cfg()
