@@ -168,6 +168,9 @@ int pb200_embed_bwd(const void* dy, const int64_t* ids, int64_t M, int64_t D, fl
  * ---------------------------------------------------------------------------------------------- */
 int pb200_glu_fwd(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
 int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t C, void* din, void* stream);
+/* GELU (erf) for the Whisper-style variant (pasero/config.py:2539-2566: activation_fn / conv_activation = gelu):
+ * forward writes gelu(in [B, T, C]) into rows [front_pad, front_pad + T) of a zero-padded [B, Tp, C] layout */
+int pb200_gelu_fwd(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
 int pb200_gelu_bwd(const void* dy, const void* pre, int64_t n, void* dx, void* stream);
 int pb200_col2im(const void* dcol, int32_t B, int32_t Tin, int32_t Tout, int32_t C, int32_t KW, int32_t stride,
                  void* dx, void* stream);

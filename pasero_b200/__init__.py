@@ -13,6 +13,6 @@ __all__ = ['TransformerConfig', 'TrainingConfig', 'DistributedConfig', 'build_mo
 def build_model(cfg: TrainingConfig, task):
     """`arch_cls(model_cfg, dist_cfg, task)` of the reference (cli/train.py:220) for arch == 'transformer'."""
     from .transformer import Transformer
-    if cfg.arch != 'transformer':
-        raise NotImplementedError(f'arch {cfg.arch!r}: only the `transformer` family is on the ST hot path')
+    if cfg.arch not in TrainingConfig.ARCH_PRESETS:
+        raise NotImplementedError(f'arch {cfg.arch!r}: only {sorted(TrainingConfig.ARCH_PRESETS)} are on the ST hot path')
     return Transformer(cfg.model_cfg, cfg, task)

@@ -30,6 +30,7 @@ class TransformerConfig:
     decoder_prenorm: bool = False
     scale_embed: bool = True
     scale_attn: bool = True
+    attention_key_bias: bool = True                # False for the Whisper family: k_proj has no bias (modules.py:516-522)
     shared_embeddings: bool = True
     tied_output_projection: bool = True
     input_dim: Optional[int] = None
@@ -60,12 +61,13 @@ class TransformerConfig:
             unsupported.append('attention_dropout > 0')
         if self.activation_dropout:
             unsupported.append('activation_dropout > 0')
-        if self.activation_fn != 'relu':
+        if self.activation_fn not in ('relu', 'gelu'):
             unsupported.append(f'activation_fn={self.activation_fn}')
-        if self.conv_activation != 'glu':
+        if self.conv_activation not in ('glu', 'gelu'):
             unsupported.append(f'conv_activation={self.conv_activation}')
-        if self.encoder_positional_encoding != 'sinusoidal' or self.decoder_positional_encoding != 'sinusoidal':
-            unsupported.append('non-sinusoidal positions')
+        for pe in (self.encoder_positional_encoding, self.decoder_positional_encoding):
+            if pe not in ('sinusoidal', 'learned'):
+                unsupported.append(f'positional encoding {pe}')
         if not self.tied_output_projection:
             unsupported.append('untied output projection')
         if self.prompt_loss != 1.0:
@@ -123,12 +125,28 @@ class TrainingConfig(DistributedConfig):
 
     OUT_OF_SCOPE = ('fsdp', 'flat_fp16', 'amp', 'lora_rank', 'moe_', 'checkpoint_activations')
 
+    # model-config presets selected by `arch` (pasero/config.py: register_model_config). `whisper_base` :2539-2566.
+    ARCH_PRESETS = {
+        'transformer': {},
+        'whisper_base': dict(encoder_layers=6, decoder_layers=6, embed_dim=512, encoder_ffn_dim=2048, decoder_ffn_dim=2048,
+                             encoder_attention_heads=8, decoder_attention_heads=8, encoder_prenorm=True, decoder_prenorm=True,
+                             activation_fn='gelu', encoder_positional_encoding='learned', decoder_positional_encoding='learned',
+                             positional_encoding_shift=0, scale_embed=False, input_dim=80, conv_input_dim=80, conv_channels=512,
+                             conv_kernel_sizes=(3, 3), conv_strides=(1, 2), conv_activation='gelu', encoder_max_len=3000,
+                             decoder_max_len=448, attention_key_bias=False),
+    }
+
     @classmethod
     def from_dict(cls, opts: dict) -> 'TrainingConfig':
         opts = {k.replace('-', '_'): v for k, v in opts.items()}
         model_fields = {f.name for f in fields(TransformerConfig)}
         train_fields = {f.name for f in fields(cls)} - {'model_cfg', 'extra'}
         cfg = cls()
+        arch = opts.get('arch', cfg.arch)
+        if arch not in cls.ARCH_PRESETS:
+            raise NotImplementedError(f'arch {arch!r}: only {sorted(cls.ARCH_PRESETS)} are on the ST hot path')
+        for k, v in cls.ARCH_PRESETS[arch].items():
+            setattr(cfg.model_cfg, k, v)
         for k, v in opts.items():
             if k in model_fields:
                 setattr(cfg.model_cfg, k, v)

@@ -166,6 +166,36 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
     }
 }
 
+// GELU (erf) forward into a (possibly zero-padded) [B, Tp, C] layout: out[b, front_pad + t] = gelu(in[b, t]) for
+// t < T, zeros elsewhere — the Whisper-style conv front end (the next conv's TMA view reads the padded layout) and,
+// with B = 1, Tp = T, the FFN activation.
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C, bf16* __restrict__ out, int Tp,
+                                int front_pad) {
+    const int c8 = C >> 3;
+    const long long total = (long long)B * Tp * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c8) * 8;
+        const long long rp = i / c8;
+        const int tp = (int)(rp % Tp);
+        const int b = (int)(rp / Tp);
+        const int t = tp - front_pad;
+        uint4 ov = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && t < T) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)b * T + t) * C + c));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x = unpack_bf16x2(xw[j]);
+                ow[j] = pack_bf16x2(0.5f * x.x * (1.f + erff(x.x * 0.70710678f)), 0.5f * x.y * (1.f + erff(x.y * 0.70710678f)));
+            }
+            ov = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        *reinterpret_cast<uint4*>(out + rp * C + c) = ov;
+    }
+}
+
 // GELU (erf) elementwise fwd/bwd for the Whisper-style conv front end and FFN backward
 __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, long long n8,
                                 bf16* __restrict__ dx) {
@@ -301,6 +331,16 @@ extern "C" int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t 
     PB_CHECK(C % 8 == 0, "glu: C must be a multiple of 8");
     glu_bwd_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)in, M, C,
                                                                           (bf16*)din);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pb200_gelu_fwd(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad,
+                              void* stream_) {
+    if (B == 0 || T == 0) return 0;
+    PB_CHECK(C % 8 == 0 && Tp >= T + front_pad, "gelu_fwd: bad shape");
+    gelu_fwd_kernel<<<ew_grid((long long)B * Tp * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)in, B, T, C,
+                                                                                           (bf16*)out, Tp, front_pad);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -277,6 +277,25 @@ def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
 
 
 @_bracketed
+def gelu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
+    """gelu(x [B*T, C]) written into rows [front_pad, front_pad + T) of a zero-padded [B, Tp, C] tensor."""
+    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    _count(1)
+    check(_lib.load().pb200_gelu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    return out
+
+
+@_bracketed
+def gelu_bwd(dy: Tensor, pre: Tensor) -> Tensor:
+    """dx = dy * gelu'(pre), elementwise over contiguous bf16 tensors of the same shape."""
+    assert dy.is_contiguous() and pre.is_contiguous() and dy.numel() == pre.numel()
+    dx = torch.empty_like(dy)
+    _count(1)
+    check(_lib.load().pb200_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
+    return dx
+
+
+@_bracketed
 def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
     dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
     _count(1)

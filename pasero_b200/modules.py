@@ -76,6 +76,33 @@ class SinusoidalPositionalEmbedding(nn.Module):
         return self.table(length).unsqueeze(0).detach()
 
 
+class LearnedPositionalEmbedding(nn.Module):
+    """pasero/models/modules.py:460-484: a trainable [num_embeddings + shift, D] table, row shift + t for position t
+    (same rows for every batch element on the training path)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, shift: int = 0):
+        super().__init__()
+        self.shift = shift
+        self.weight = nn.Parameter(torch.empty(num_embeddings + shift, embedding_dim))
+        nn.init.normal_(self.weight, mean=0, std=embedding_dim ** -0.5)   # utils.embed_init
+        self.weight._pb200_bf16_grad = True   # gradient = batch sum written in bf16 (not a GEMM weight gradient)
+
+    def table(self, length: int) -> Tensor:
+        assert length + self.shift - 1 < self.weight.size(0), (
+            f'input sequence is too long: {length}, positional embedding size: {self.weight.size(0)}')
+        return self.weight[self.shift:self.shift + length]
+
+    def forward(self, length: int, offset: int = 0) -> Tensor:
+        assert offset == 0, 'incremental decoding offsets are outside the training path'
+        return self.table(length).unsqueeze(0)
+
+
+def positional_embedding(kind: str, num_embeddings: int, embedding_dim: int, shift: int):
+    if kind == 'learned':
+        return LearnedPositionalEmbedding(num_embeddings, embedding_dim, shift)
+    return SinusoidalPositionalEmbedding(num_embeddings, embedding_dim, shift)
+
+
 class MultiheadAttention(nn.Module):
     """pasero/models/modules.py:487-771, training path: separate q/k/v/out projections with bias, 1/sqrt(d_h)
     scaling, key-padding mask given as (B, S) bool (True = masked) or causal masking.
@@ -84,9 +111,13 @@ class MultiheadAttention(nn.Module):
     projection GEMM and cross-attention two; state_dict exposes the reference's k_proj/v_proj/q_proj/out_proj keys.
     """
 
-    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, causal: bool = False, scaled: bool = True):
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, causal: bool = False, scaled: bool = True,
+                 key_bias: bool = True):
         super().__init__()
         self.embed_dim, self.num_heads, self.dropout, self.causal, self.scaled = embed_dim, num_heads, dropout, causal, scaled
+        # key_bias=False (Whisper family): the k rows of the fused bias stay zero, are not in the state_dict and get no
+        # gradient (a key bias shifts every score of a query by the same amount: softmax ignores it)
+        self.key_bias = key_bias
         self.head_dim = embed_dim // num_heads
         if self.head_dim != 64:
             raise NotImplementedError('pasero_b200 attention kernels are specialised for head_dim 64')
@@ -102,6 +133,8 @@ class MultiheadAttention(nn.Module):
         for i in range(3):  # k, v, q: xavier_uniform with gain 1/sqrt(2) (modules.py:565-573)
             nn.init.xavier_uniform_(self.in_proj_weight.data[i * D:(i + 1) * D], gain=1 / math.sqrt(2))
         nn.init.uniform_(self.in_proj_bias, -1 / math.sqrt(D), 1 / math.sqrt(D))
+        if not self.key_bias:
+            nn.init.constant_(self.in_proj_bias.data[:D], 0.0)
         nn.init.xavier_uniform_(self.out_proj.weight, gain=1.0)
         nn.init.constant_(self.out_proj.bias, 0.0)
 
@@ -116,11 +149,14 @@ class MultiheadAttention(nn.Module):
         for name, i in self._ORDER.items():
             w, b = self._block(i)
             destination[prefix + name + '.weight'] = w if keep_vars else w.detach()
-            destination[prefix + name + '.bias'] = b if keep_vars else b.detach()
+            if name != 'k_proj' or self.key_bias:
+                destination[prefix + name + '.bias'] = b if keep_vars else b.detach()
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         for name, i in self._ORDER.items():
             for kind, dst in zip(('weight', 'bias'), self._block(i)):
+                if kind == 'bias' and name == 'k_proj' and not self.key_bias:
+                    continue
                 key = prefix + name + '.' + kind
                 if key in state_dict:
                     with torch.no_grad():
@@ -159,7 +195,7 @@ class MultiheadAttention(nn.Module):
         out = ops.AttentionFn.apply(
             query.reshape(B * T, D), None if self_attn else key.reshape(B * S, D), self.in_proj_weight, self.in_proj_bias,
             self.out_proj.weight, self.out_proj.bias, key_lengths, B, T, S, self.num_heads, self.causal,
-            ops.attention_scale(self.head_dim, self.scaled))
+            ops.attention_scale(self.head_dim, self.scaled), self.key_bias)
         return out.view(B, T, D), None
 
 
@@ -171,15 +207,17 @@ class ConvolutionSubsampler(nn.Module):
     def __init__(self, in_channels: int, mid_channels: int, out_channels: int, kernel_sizes=(3, 3), strides=None,
                  activation: str = 'glu'):
         super().__init__()
-        if activation != 'glu':
-            raise NotImplementedError('only the GLU subsampler is covered')
+        if activation not in ('glu', 'gelu'):
+            raise NotImplementedError(f'conv activation {activation!r} is not covered')
+        self.activation = activation
+        r = 2 if activation == 'glu' else 1      # GLU halves the channels (modules.py:788)
         self.kernel_sizes = tuple(kernel_sizes)
         self.strides = tuple(strides) if strides else tuple(2 for _ in kernel_sizes)
         assert len(self.strides) == len(self.kernel_sizes)
         self.channels = []
         for i, k in enumerate(self.kernel_sizes):
-            cin = in_channels if i == 0 else mid_channels // 2
-            cout = out_channels * 2 if i == len(self.kernel_sizes) - 1 else mid_channels
+            cin = in_channels if i == 0 else mid_channels // r
+            cout = out_channels * r if i == len(self.kernel_sizes) - 1 else mid_channels
             w = torch.empty(cout, cin, k)
             nn.init.kaiming_uniform_(w, a=math.sqrt(5))            # nn.Conv1d default
             bound = 1 / math.sqrt(cin * k)
@@ -242,7 +280,8 @@ class ConvolutionSubsampler(nn.Module):
                 rows, front = self.padded_rows(t_out, i + 1)
             else:
                 rows, front = t_out, 0
-            x = ops.ConvGLUFn.apply(x, self.weights[i], self.biases[i], B, t, self.channels[i][0], k, s, rows, front, i > 0)
+            x = ops.ConvGLUFn.apply(x, self.weights[i], self.biases[i], B, t, self.channels[i][0], k, s, rows, front, i > 0,
+                                    self.activation)
             t = t_out
         return x, self.get_new_length(length)
 

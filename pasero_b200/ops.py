@@ -176,8 +176,9 @@ class AttentionFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, query, key, in_w, in_b, out_w, out_b, kv_len, B, Lq, Lk, H, causal, scale):
+    def forward(ctx, query, key, in_w, in_b, out_w, out_b, kv_len, B, Lq, Lk, H, causal, scale, key_bias=True):
         D = H * 64
+        ctx.key_bias = key_bias
         query = _c(query)
         self_attn = key is None
         if self_attn:
@@ -214,14 +215,18 @@ class AttentionFn(torch.autograd.Function):
         if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
-        d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
+        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
             dquery = K.linear_dgrad(dkvq, in_w)
             K.linear_wgrad(dkvq, query, out=d_in_w, accumulate=acc_w)
-            K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+            if kb:
+                K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+            else:
+                K.colsum(dkvq[:, D:], out=d_in_b[D:], accumulate=acc_b)
             dkey = None
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
@@ -231,11 +236,14 @@ class AttentionFn(torch.autograd.Function):
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
             K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
             K.linear_wgrad(dq, query, out=d_in_w[2 * D:], accumulate=acc_w)
-            K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            if kb:
+                K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            else:
+                K.colsum(dkv[:, D:], out=d_in_b[D:2 * D], accumulate=acc_b)
             K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
         _ready(p_in_w, p_in_b)
         return (dquery, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 def _keep_buffer(x: Tensor, p: float) -> Optional[Tensor]:
@@ -266,8 +274,9 @@ class AttnSublayerFn(torch.autograd.Function):
     dgrad GEMM (no column-sum pass over dy, no separate add kernel)."""
 
     @staticmethod
-    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps):
+    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps, key_bias=True):
         D = H * 64
+        ctx.key_bias = key_bias
         x = _c(x)
         self_attn = key is None
         if self_attn:
@@ -306,14 +315,18 @@ class AttnSublayerFn(torch.autograd.Function):
         if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
-        d_in_b = sink_b if sink_b is not None else torch.empty(3 * D, dtype=BF16, device=dy.device)
+        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
             dx = K.linear_dgrad(dkvq, in_w, residual=dres)
             K.linear_wgrad(dkvq, x, out=d_in_w, accumulate=acc_w)
-            K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+            if kb:
+                K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+            else:
+                K.colsum(dkvq[:, D:], out=d_in_b[D:], accumulate=acc_b)
             dkey = None
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
@@ -323,11 +336,14 @@ class AttnSublayerFn(torch.autograd.Function):
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
             K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
             K.linear_wgrad(dq, x, out=d_in_w[2 * D:], accumulate=acc_w)
-            K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            if kb:
+                K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+            else:
+                K.colsum(dkv[:, D:], out=d_in_b[D:2 * D], accumulate=acc_b)
             K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
         _ready(p_in_w, p_in_b)
         return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 class FFNSublayerFn(torch.autograd.Function):
@@ -396,39 +412,86 @@ class DropoutAddLNFn(torch.autograd.Function):
 
 
 class EmbedFn(torch.autograd.Function):
-    """dropout(bf16(bf16(src * scale) + pos)): src = table[ids] (decoder tokens) or a feature matrix (encoder)."""
+    """dropout(bf16(bf16(src * scale) + pos)): src = table[ids] (decoder tokens) or a feature matrix (encoder).
+    `pos_table` (optional): the trainable LearnedPositionalEmbedding weight whose rows [shift, shift + L) are `pos`; its
+    gradient is the sum over the batch of the gradient reaching the sum (pasero/models/modules.py:460-484)."""
 
     @staticmethod
-    def forward(ctx, src, ids, pos, scale, p, L, padding_idx):
+    def forward(ctx, src, ids, pos, scale, p, L, padding_idx, pos_table=None, shift=0):
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
         M = ids.numel() if ids is not None else src.shape[0]
         D = src.shape[1]
         ids_flat = _c(ids).view(-1) if ids is not None else None
-        out = K.embed_fwd(ids_flat, _c(src), pos, M, D, L, scale, p, seed, offset)
+        out = K.embed_fwd(ids_flat, _c(src), pos.detach() if pos is not None else None, M, D, L, scale, p, seed, offset)
         ctx.save_for_backward(ids_flat)
-        ctx.cfg = (M, D, scale, p, seed, offset, padding_idx, src.shape[0])
+        ctx.cfg = (M, D, scale, p, seed, offset, padding_idx, src.shape[0], L, shift)
         ctx.table = src if ids is not None else None
+        ctx.pos_table = pos_table
         return out
 
     @staticmethod
     def backward(ctx, dy):
         (ids_flat,) = ctx.saved_tensors
-        M, D, scale, p, seed, offset, padding_idx, rows = ctx.cfg
+        M, D, scale, p, seed, offset, padding_idx, rows, L, shift = ctx.cfg
         dy = _c(dy)
+        dpos = None
+        dense = None   # gradient reaching bf16(src * scale) + pos, i.e. dropout'(dy)
+        if ctx.pos_table is not None:
+            dense = K.embed_bwd(dy, None, M, D, 1.0, p, seed, offset)
+            so, acc = _sink(ctx.pos_table)
+            full = so if so is not None else torch.zeros_like(ctx.pos_table)
+            if so is not None and not acc:
+                full.zero_()       # rows outside [shift, shift + L) get no gradient this step
+            K.colsum(dense.view(M // L, L * D), out=full[shift:shift + L].view(-1), accumulate=acc)
+            _ready(ctx.pos_table)
+            dpos = _ret(full, so)
         if ids_flat is None:
-            return K.embed_bwd(dy, None, M, D, scale, p, seed, offset), None, None, None, None, None, None
+            dx = dense if (dense is not None and scale == 1.0) else K.embed_bwd(dy, None, M, D, scale, p, seed, offset)
+            return dx, None, None, None, None, None, None, dpos, None
         t32 = _sink32(ctx.table)
         if t32 is not None:       # scatter-add straight into the fp32 main gradient of the (tied) embedding table
             K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, t32)
             _ready(ctx.table)
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, dpos, None
         dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
         K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
         so, acc = _sink(ctx.table)
         dtable = so if so is not None else torch.empty(rows, D, dtype=BF16, device=dy.device)
         K.f32_to_bf16(dtable32, dtable, accumulate=acc)
         _ready(ctx.table)
-        return _ret(dtable, so), None, None, None, None, None, None
+        return _ret(dtable, so), None, None, None, None, None, None, dpos, None
+
+
+class FFNGeluFn(torch.autograd.Function):
+    """y = gelu(x W1^T + b1) W2^T + b2 (erf GELU; pasero/models/transformer.py:999-1019 with activation_fn = gelu, the
+    Whisper family). The pre-activation is kept for the backward pass, the activation is its own elementwise kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _c(x)
+        pre = K.linear_fwd(x, w1, b1)
+        M, F_ = pre.shape
+        h = K.gelu_fwd(pre, 1, M, F_, M, 0).view(M, F_)
+        y = K.linear_fwd(h, w2, b2)
+        ctx.save_for_backward(x, w1, w2, pre, h)
+        ctx.params = (w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pre, h = ctx.saved_tensors
+        p_w1, p_b1, p_w2, p_b2 = ctx.params
+        dy = _c(dy)
+        dh = K.linear_dgrad(dy, w2)
+        dw2 = _wgrad(dy, h, p_w2)
+        o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
+        _ready(p_w2, p_b2)
+        dpre = K.gelu_bwd(dh, pre)
+        dx = K.linear_dgrad(dpre, w1)
+        dw1 = _wgrad(dpre, x, p_w1)
+        o, a = _sink(p_b1); db1 = _ret(K.colsum(dpre, out=o, accumulate=a), o)
+        _ready(p_w1, p_b1)
+        return dx, dw1, db1, dw2, db2
 
 
 class ConvGLUFn(torch.autograd.Function):
@@ -441,14 +504,18 @@ class ConvGLUFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, xp, weight, bias, B, Tin, Cin, KW, stride, out_Tp, out_front_pad, need_input_grad):
+    def forward(ctx, xp, weight, bias, B, Tin, Cin, KW, stride, out_Tp, out_front_pad, need_input_grad, act='glu'):
         Tp = xp.shape[1]
         Cout = weight.shape[0]
         Tout = 1 + (Tin + 2 * (KW // 2) - KW) // stride
         pre = torch.empty(B * Tout, Cout, dtype=BF16, device=xp.device)
         K.gemm_raw(xp.data_ptr(), weight.data_ptr(), pre, Tout, Cout, KW * Cin, lda=stride * Cin, ldb=KW * Cin, ldc=Cout,
                    batch=B, a_batch_stride=Tp * Cin, b_batch_stride=0, c_batch_stride=Tout * Cout, bias=bias, split_k=1)
-        out = K.glu_fwd(pre, B, Tout, Cout // 2, out_Tp, out_front_pad)
+        if act == 'glu':
+            out = K.glu_fwd(pre, B, Tout, Cout // 2, out_Tp, out_front_pad)
+        else:   # GELU keeps all Cout channels (Whisper-style front end, modules.py:803)
+            out = K.gelu_fwd(pre, B, Tout, Cout, out_Tp, out_front_pad)
+        ctx.act = act
         ctx.save_for_backward(xp, weight, pre)
         ctx.dims = (B, Tin, Cin, KW, stride, Tout, Tp, out_Tp, out_front_pad, need_input_grad)
         ctx.params = (weight, bias)
@@ -459,9 +526,13 @@ class ConvGLUFn(torch.autograd.Function):
         xp, weight, pre = ctx.saved_tensors
         B, Tin, Cin, KW, stride, Tout, Tp, out_Tp, out_front_pad, need_input_grad = ctx.dims
         Cout = weight.shape[0]
-        # gradient w.r.t. the GLU output rows (drop the padding rows of the padded layout)
-        dy = _c(dout[:, out_front_pad:out_front_pad + Tout]).view(B * Tout, Cout // 2)
-        dpre = K.glu_bwd(dy, pre, B * Tout, Cout // 2)
+        # gradient w.r.t. the activation's output rows (drop the padding rows of the padded layout)
+        if ctx.act == 'glu':
+            dy = _c(dout[:, out_front_pad:out_front_pad + Tout]).view(B * Tout, Cout // 2)
+            dpre = K.glu_bwd(dy, pre, B * Tout, Cout // 2)
+        else:
+            dy = _c(dout[:, out_front_pad:out_front_pad + Tout]).view(B * Tout, Cout)
+            dpre = K.gelu_bwd(dy, pre)
         p_w, p_b = ctx.params
         so_w, acc_w = _sink(p_w)
         w32 = _sink32(p_w)
@@ -484,7 +555,7 @@ class ConvGLUFn(torch.autograd.Function):
             front = KW // 2
             dxp = torch.zeros_like(xp)
             dxp[:, front:front + Tin] = dx.view(B, Tin, Cin)
-        return dxp, dw, db, None, None, None, None, None, None, None, None
+        return dxp, dw, db, None, None, None, None, None, None, None, None, None
 
 
 class ProjCEFn(torch.autograd.Function):
@@ -524,9 +595,10 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     return y.view(*shape[:-1], weight.shape[0])
 
 
-def ffn(x: Tensor, w1, b1, w2, b2) -> Tensor:
+def ffn(x: Tensor, w1, b1, w2, b2, activation: str = 'relu') -> Tensor:
     shape = x.shape
-    return FFNFn.apply(x.reshape(-1, shape[-1]), w1, b1, w2, b2).view(shape)
+    fn = FFNFn if activation == 'relu' else FFNGeluFn
+    return fn.apply(x.reshape(-1, shape[-1]), w1, b1, w2, b2).view(shape)
 
 
 def dropout_add_ln(x: Tensor, residual: Optional[Tensor], gamma, beta, p: float, eps: float) -> Tensor:
@@ -541,7 +613,8 @@ def attn_sublayer(x: Tensor, key: Optional[Tensor], attn, ln, kv_len, causal: bo
     S = T if key is None else key.shape[1]
     out = AttnSublayerFn.apply(x.reshape(B * T, D), None if key is None else key.reshape(B * S, D), attn.in_proj_weight,
                                attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias, ln.weight, ln.bias, kv_len,
-                               B, T, S, attn.num_heads, causal, attention_scale(attn.head_dim, attn.scaled), float(p), float(eps))
+                               B, T, S, attn.num_heads, causal, attention_scale(attn.head_dim, attn.scaled), float(p), float(eps),
+                               attn.key_bias)
     return out.view(B, T, D)
 
 

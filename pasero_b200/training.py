@@ -84,7 +84,7 @@ class ParamArena:
         # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
         # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
         self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
-        self.is32 = [p.ndim >= 2 for p in self.params]
+        self.is32 = [p.ndim >= 2 and not getattr(p, '_pb200_bf16_grad', False) for p in self.params]
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=device)
         with torch.no_grad():

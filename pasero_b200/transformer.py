@@ -28,7 +28,7 @@ class TransformerEncoderLayer(nn.Module):
         super().__init__()
         self.cfg, self.layer_id = cfg, layer_id
         self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.encoder_attention_heads, dropout=cfg.attention_dropout,
-                                                    scaled=cfg.scale_attn)
+                                                    scaled=cfg.scale_attn, key_bias=cfg.attention_key_bias)
         self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.fc1 = modules.Linear(cfg.embed_dim, cfg.encoder_ffn_dim)
         self.fc2 = modules.Linear(cfg.encoder_ffn_dim, cfg.embed_dim)
@@ -41,7 +41,7 @@ class TransformerEncoderLayer(nn.Module):
         p = self.dropout_p if self.training else 0.0
         eps = self.cfg.norm_eps
         ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
-        if not self.prenorm:   # post-norm (the ST default): each sub-block is one fused autograd node
+        if not self.prenorm and self.cfg.activation_fn == 'relu':   # post-norm ReLU (the ST default): fused autograd nodes
             x = ops.attn_sublayer(x, None, self.self_attn, ln1, key_lengths if key_lengths is not None else
                                   self.self_attn.key_lengths_of(padding_mask), False, p, eps)
             x = ops.ffn_sublayer(x, self.fc1, self.fc2, ln2, p, eps)
@@ -57,7 +57,7 @@ class TransformerEncoderLayer(nn.Module):
         residual = x
         if self.prenorm:
             x = ops.dropout_add_ln(x, None, ln2.weight, ln2.bias, 0.0, eps)
-        x = ops.ffn(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+        x = ops.ffn(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.cfg.activation_fn)
         if self.prenorm:
             x = ops.dropout_add_ln(x, residual, None, None, p, eps)
         else:
@@ -72,10 +72,11 @@ class TransformerDecoderLayer(nn.Module):
         super().__init__()
         self.cfg, self.layer_id = cfg, layer_id
         self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.decoder_attention_heads, dropout=cfg.attention_dropout,
-                                                    causal=True, scaled=cfg.scale_attn)
+                                                    causal=True, scaled=cfg.scale_attn, key_bias=cfg.attention_key_bias)
         self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.encoder_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.decoder_attention_heads,
-                                                       dropout=cfg.attention_dropout, scaled=cfg.scale_attn)
+                                                       dropout=cfg.attention_dropout, scaled=cfg.scale_attn,
+                                                       key_bias=cfg.attention_key_bias)
         self.encoder_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.fc1 = modules.Linear(cfg.embed_dim, cfg.decoder_ffn_dim)
         self.fc2 = modules.Linear(cfg.decoder_ffn_dim, cfg.embed_dim)
@@ -99,7 +100,7 @@ class TransformerDecoderLayer(nn.Module):
             raise NotImplementedError('incremental decoding is outside the training path')
         p = self.dropout_p if self.training else 0.0
         eps = self.cfg.norm_eps
-        if not self.prenorm:
+        if not self.prenorm and self.cfg.activation_fn == 'relu':
             x = ops.attn_sublayer(x, None, self.self_attn, self.self_attn_layer_norm, None, True, p, eps)
             enc_len = encoder_lengths if encoder_lengths is not None else self.encoder_attn.key_lengths_of(encoder_mask)
             x = ops.attn_sublayer(x, encoder_out, self.encoder_attn, self.encoder_attn_layer_norm, enc_len, False, p, eps)
@@ -110,7 +111,8 @@ class TransformerDecoderLayer(nn.Module):
                         lambda h: self.encoder_attn(h, encoder_out, encoder_out, attn_mask=encoder_mask,
                                                     key_lengths=encoder_lengths)[0], p, eps)
         x = self._block(x, self.final_layer_norm,
-                        lambda h: ops.ffn(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias), p, eps)
+                        lambda h: ops.ffn(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                          self.cfg.activation_fn), p, eps)
         return x, ({self.name: x} if self.name in return_layers else {})
 
 
@@ -130,8 +132,8 @@ class TransformerEncoder(nn.Module):
         self.subsample = modules.ConvolutionSubsampler(conv_input_dim, cfg.conv_channels or conv_input_dim, cfg.embed_dim,
                                                        cfg.conv_kernel_sizes, cfg.conv_strides, cfg.conv_activation)
         encoder_max_len = int(self.subsample.get_new_length(torch.tensor(cfg.encoder_max_len)))
-        self.embed_positions = modules.SinusoidalPositionalEmbedding(encoder_max_len, cfg.embed_dim,
-                                                                     shift=cfg.positional_encoding_shift)
+        self.embed_positions = modules.positional_embedding(cfg.encoder_positional_encoding, encoder_max_len, cfg.embed_dim,
+                                                            cfg.positional_encoding_shift)
         self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
         self.dropout_p = defined(cfg.embed_dropout, cfg.dropout)
         self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, dist_cfg, i) for i in range(cfg.encoder_layers)])
@@ -156,7 +158,9 @@ class TransformerEncoder(nn.Module):
         S = x.numel() // (B * D)
         p = self.dropout_p if self.training else 0.0
         pos = self.embed_positions.table(S)
-        x = ops.EmbedFn.apply(x.reshape(B * S, D), None, pos, float(self.embed_scale), float(p), S, -1).view(B, S, D)
+        learned = self.embed_positions.weight if isinstance(self.embed_positions, modules.LearnedPositionalEmbedding) else None
+        x = ops.EmbedFn.apply(x.reshape(B * S, D), None, pos, float(self.embed_scale), float(p), S, -1, learned,
+                              self.embed_positions.shift).view(B, S, D)
         padding_mask = len_to_mask(length, size=S)
         key_lengths = length.clamp(max=S).to(torch.int32)
         layer_outputs = {}
@@ -178,8 +182,8 @@ class TransformerDecoder(nn.Module):
         self.padding_idx = task.padding_idx
         self.embed_tokens = embed if embed is not None else modules.Embedding(task.decoder_num_embeddings, cfg.embed_dim,
                                                                               self.padding_idx)
-        self.embed_positions = modules.SinusoidalPositionalEmbedding(cfg.decoder_max_len, cfg.embed_dim,
-                                                                     shift=cfg.positional_encoding_shift)
+        self.embed_positions = modules.positional_embedding(cfg.decoder_positional_encoding, cfg.decoder_max_len, cfg.embed_dim,
+                                                            cfg.positional_encoding_shift)
         self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
         self.dropout_p = defined(cfg.embed_dropout, cfg.decoder_dropout, cfg.dropout)
         self.layers = nn.ModuleList([TransformerDecoderLayer(cfg, dist_cfg, i) for i in range(cfg.decoder_layers)])
@@ -191,8 +195,9 @@ class TransformerDecoder(nn.Module):
         D = self.cfg.embed_dim
         p = self.dropout_p if self.training else 0.0
         pos = self.embed_positions.table(T)
+        learned = self.embed_positions.weight if isinstance(self.embed_positions, modules.LearnedPositionalEmbedding) else None
         x = ops.EmbedFn.apply(self.embed_tokens.weight, decoder_input, pos, float(self.embed_scale), float(p), T,
-                              self.padding_idx).view(B, T, D)
+                              self.padding_idx, learned, self.embed_positions.shift).view(B, T, D)
         layer_outputs = {}
         for layer in self.layers:
             x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths)

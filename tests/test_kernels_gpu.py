@@ -283,6 +283,22 @@ def test_glu():
 
 
 # ---------------------------------------------------------------------------------------------- loss / optimizer
+def test_gelu_padded_layout():
+    """erf-GELU forward into the zero-padded [B, Tp, C] layout (Whisper-style conv front end) and its backward."""
+    k = _k()
+    B, T, C, Tp, front = 3, 37, 64, 42, 2
+    x = _rand(B * T, C, seed=1)
+    out = k.gelu_fwd(x, B, T, C, Tp, front)
+    ref = F.gelu(x.float()).view(B, T, C)
+    assert torch.equal(out[:, :front], torch.zeros_like(out[:, :front]))
+    assert torch.equal(out[:, front + T:], torch.zeros_like(out[:, front + T:]))
+    _close(out[:, front:front + T], ref, 1e-2, 1e-2, 'gelu fwd')
+    dy = _rand(B * T, C, seed=2)
+    xr = x.float().requires_grad_(True)
+    F.gelu(xr).backward(dy.float())
+    _close(k.gelu_bwd(dy, x), xr.grad, 1e-2, 1e-2, 'gelu bwd')
+
+
 @pytest.mark.parametrize('V', [8032, 1000])
 def test_ls_ce(V):
     k = _k()

@@ -114,6 +114,84 @@ def oracle_bf16_curve(steps: int) -> list:
     return rows
 
 
+def wsp_training_cfg(**kw):
+    from pasero_b200 import TrainingConfig
+    t = synth.WSP
+    opts = dict(arch='whisper_base', encoder_layers=t['encoder_layers'], decoder_layers=t['decoder_layers'], embed_dim=t['embed_dim'],
+                encoder_ffn_dim=t['ffn_dim'], decoder_ffn_dim=t['ffn_dim'], encoder_attention_heads=t['heads'],
+                decoder_attention_heads=t['heads'], conv_channels=t['conv_channels'], encoder_max_len=t['encoder_max_len'],
+                decoder_max_len=t['decoder_max_len'], batch_size=64000, dropout=0.0, label_smoothing=0.1, dtype='bfloat16',
+                lr=synth.TRAIN['lr'], warmup=synth.TRAIN['warmup'], max_steps=1000)
+    opts.update(kw)
+    return TrainingConfig.from_dict(opts)
+
+
+def test_whisper_variant_matches_reference_and_oracle():
+    """BASELINE config 4's architecture family (pre-norm, GELU FFN, learned positions, GELU conv front end k=3,3 strides
+    1,2, no key bias, final LayerNorms) on the CUDA path: against the reference's golden vectors and the oracle's full
+    gradients, and through the Trainer (DirectGrads / fp32 main gradients / learned-position gradient sink)."""
+    from oracle import model as om
+    from pasero_b200 import build_model
+    from pasero_b200.training import Trainer
+    from tests.test_oracle_cpu import wsp_cfg
+    gold = torch.load(os.path.join(GOLD, 'st_wsp_model.pt'), weights_only=False)
+    cfg = wsp_training_cfg()
+    task = tiny_task(cfg)
+    model = build_model(cfg, task)
+    missing = model.load_state_dict(synth.wsp_state_dict(), strict=False)
+    assert not missing.unexpected_keys and not missing.missing_keys, missing
+    assert sorted(k for k in model.state_dict() if not k.endswith('_float_tensor')) == sorted(gold['param_names'])
+    model.to(BF16).cuda().train()
+    batch = synth.model_batch()
+    cb = to_cuda(batch)
+    names = list(gold['layers'].keys())
+    enc_out, enc_mask, enc_layers = model.encoder(cb['encoder_input'], cb['encoder_input_length'], return_layers=names)
+    logits, dec_layers = model.decoder(enc_out, enc_mask, cb['decoder_input'][:, :-1], return_layers=names,
+                                       encoder_lengths=model.encoder._last_lengths)
+    assert torch.equal(enc_mask.cpu(), gold['encoder_mask'])
+    assert rel_to_max(enc_out, gold['encoder_out']) < 3e-2
+    assert rel_to_max(logits, gold['logits']) < 3e-2
+    for k, want in gold['layers'].items():
+        assert rel_to_max({**enc_layers, **dec_layers}[k], want) < 3e-2, k
+    loss, logs = model(**cb)
+    assert abs(loss.item() - gold['loss']) / gold['loss'] < 1e-2
+    assert logs['num_tokens'] == gold['logs']['num_tokens']
+    model.zero_grad()
+    loss.backward()
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.wsp_state_dict().items()}
+    oloss, _ = om.forward(wsp_cfg(), sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'])
+    oloss.backward()
+    saved = [(p, p.data) for p in model.parameters()]
+    for p in model.parameters():
+        p.data = p.grad
+    try:
+        grads = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if k in sd}
+    finally:
+        for p, d in saved:
+            p.data = d
+    bad = {}
+    for k, g in grads.items():
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), sd[k].grad.flatten(), dim=0).item()
+        if rel_to_max(g, sd[k].grad) > 0.3 or cos < 0.985:
+            bad[k] = (rel_to_max(g, sd[k].grad), cos)
+    assert not bad, bad
+    # through the Trainer: three optimizer steps against the oracle's bf16-semantics train_step
+    from oracle import optim as oo
+    model2 = build_model(cfg, task)
+    model2.load_state_dict(synth.wsp_state_dict(), strict=False)
+    trainer = Trainer(cfg, task, model2)
+    osd = {k: v.clone().to(BF16).requires_grad_(True) for k, v in synth.wsp_state_dict().items()}   # bf16 parameters, fp32 moments
+    state, hp = {}, dict(lr=synth.TRAIN['lr'], warmup=synth.TRAIN['warmup'], max_steps=1000, clip_norm=1.0)
+    batches = synth.train_batches()
+    obatches = [{k: (v.to(BF16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in b.items()} for b in batches]
+    for step in range(3):
+        logs = trainer.train_step(iter([batches[step]]))
+        ologs = oo.train_step(wsp_cfg(), osd, [obatches[step]], state, step, hp, om.forward)
+        assert logs['num_tokens'] == ologs['num_tokens']
+        assert abs(logs['loss'] - ologs['loss']) / ologs['loss'] < 1e-2, (step, logs['loss'], ologs['loss'])
+        assert abs(logs['gnorm'] - ologs['gnorm']) / ologs['gnorm'] < 5e-2, (step, logs['gnorm'], ologs['gnorm'])
+
+
 def test_loss_curve_200_steps_matches_oracle():
     from pasero_b200.training import Trainer
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
