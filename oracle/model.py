@@ -156,6 +156,19 @@ def decoder_layer(cfg: STConfig, sd, prefix: str, x: Tensor, enc: Tensor, enc_ma
     return x
 
 
+def adapters(cfg: STConfig, sd, prefix: str, x: Tensor, names) -> Tensor:
+    """AdapterLayer.forward stacked after a Transformer layer (pasero/models/modules.py:344-357, adapters.py:248-252,
+    296-300): x + up(relu(down(LayerNorm(x)))) for every adapter name present in the state dict (eps = nn.LayerNorm default)."""
+    for name in names:
+        p = f'{prefix}adapters.{name}.'
+        if p + 'down.weight' not in sd:
+            continue
+        h = F.layer_norm(x, (x.shape[-1],), sd[p + 'layer_norm.weight'], sd[p + 'layer_norm.bias'], 1e-5)
+        h = F.relu(F.linear(h, sd[p + 'down.weight'], sd[p + 'down.bias']))
+        x = x + F.linear(h, sd[p + 'up.weight'], sd[p + 'up.bias'])
+    return x
+
+
 def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tensor, layer_outputs: Optional[dict] = None):
     """ConvolutionSubsampler.forward (modules.py:819-834) + TransformerEncoder.forward (transformer.py:697-752)."""
     x = encoder_input.transpose(1, 2)
@@ -178,6 +191,7 @@ def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tenso
         layer_outputs['enc_embed'] = x
     for i in range(cfg.encoder_layers):
         x = encoder_layer(cfg, sd, f'encoder.layers.{i}.', x, mask)
+        x = adapters(cfg, sd, f'encoder.layers.{i}.', x, cfg.extra.get('encoder_adapters', ('default',)))
         if layer_outputs is not None:
             layer_outputs[f'enc_{i}'] = x
     if cfg.encoder_prenorm:
@@ -198,6 +212,7 @@ def decode(cfg: STConfig, sd, enc: Tensor, enc_mask: Tensor, decoder_input: Tens
         x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
     for i in range(cfg.decoder_layers):
         x = decoder_layer(cfg, sd, f'decoder.layers.{i}.', x, enc, enc_mask)
+        x = adapters(cfg, sd, f'decoder.layers.{i}.', x, cfg.extra.get('decoder_adapters', ('default',)))
         if layer_outputs is not None:
             layer_outputs[f'dec_{i}'] = x
     if cfg.decoder_prenorm:

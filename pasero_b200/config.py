@@ -31,6 +31,18 @@ class TransformerConfig:
     scale_embed: bool = True
     scale_attn: bool = True
     attention_key_bias: bool = True                # False for the Whisper family: k_proj has no bias (modules.py:516-522)
+    # adapter_transformer (pasero/config.py:1323-1369): bottleneck adapters after each layer, base parameters frozen
+    adapters: bool = False                         # set by the `adapter_*` architectures
+    encoder_adapter_dim: int = 64
+    decoder_adapter_dim: int = 64
+    encoder_adapter_layer_ids: Optional[tuple] = None
+    decoder_adapter_layer_ids: Optional[tuple] = None
+    encoder_adapters: Optional[tuple] = None       # names of stacked adapters (default: ('default',)); () disables
+    decoder_adapters: Optional[tuple] = None
+    encoder_adapters_by: tuple = ()                # 'source_lang' / 'target_lang' / 'lang' / 'domain': one adapter per value
+    decoder_adapters_by: tuple = ()
+    adapter_zero_init: bool = False
+    train_all_params: bool = False
     shared_embeddings: bool = True
     tied_output_projection: bool = True
     input_dim: Optional[int] = None
@@ -128,6 +140,7 @@ class TrainingConfig(DistributedConfig):
     # model-config presets selected by `arch` (pasero/config.py: register_model_config). `whisper_base` :2539-2566.
     ARCH_PRESETS = {
         'transformer': {},
+        'adapter_transformer': dict(adapters=True),
         'whisper_base': dict(encoder_layers=6, decoder_layers=6, embed_dim=512, encoder_ffn_dim=2048, decoder_ffn_dim=2048,
                              encoder_attention_heads=8, decoder_attention_heads=8, encoder_prenorm=True, decoder_prenorm=True,
                              activation_fn='gelu', encoder_positional_encoding='learned', decoder_positional_encoding='learned',

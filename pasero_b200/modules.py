@@ -103,6 +103,34 @@ def positional_embedding(kind: str, num_embeddings: int, embedding_dim: int, shi
     return SinusoidalPositionalEmbedding(num_embeddings, embedding_dim, shift)
 
 
+class AdapterLayer(nn.Module):
+    """pasero/models/modules.py:248-357 in its Bapna et al. configuration (LayerNorm, biases, ReLU, residual, scaling 1):
+    x + up(relu(down(LayerNorm(x)))). Built from the same kernels as a feed-forward block: LayerNorm, the fused
+    bias+ReLU / ReLU-mask GEMM pair, and the residual add."""
+
+    def __init__(self, input_dim: int, projection_dim: int, zero_init: bool = False):
+        super().__init__()
+        if projection_dim % 8:
+            raise NotImplementedError('adapter bottleneck dimension must be a multiple of 8')
+        self.down = Linear(input_dim, projection_dim)
+        self.up = Linear(projection_dim, input_dim)
+        self.layer_norm = nn.LayerNorm(input_dim)
+        if zero_init:
+            nn.init.kaiming_uniform_(self.down.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.up.weight)
+        else:
+            nn.init.uniform_(self.down.weight, -1e-6, 1e-6)
+            nn.init.uniform_(self.up.weight, -1e-6, 1e-6)
+        nn.init.zeros_(self.down.bias)
+        nn.init.zeros_(self.up.bias)
+
+    def forward(self, x: Tensor) -> Tensor:
+        ln = self.layer_norm
+        h = ops.dropout_add_ln(x, None, ln.weight, ln.bias, 0.0, ln.eps)
+        h = ops.ffn(h, self.down.weight, self.down.bias, self.up.weight, self.up.bias)
+        return ops.dropout_add_ln(h, x, None, None, 0.0, ln.eps)     # residual + h
+
+
 class MultiheadAttention(nn.Module):
     """pasero/models/modules.py:487-771, training path: separate q/k/v/out projections with bias, 1/sqrt(d_h)
     scaling, key-padding mask given as (B, S) bool (True = masked) or causal masking.

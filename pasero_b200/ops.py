@@ -5,6 +5,7 @@ Dropout masks are Philox(seed, offset): `DropoutState` hands out a fresh offset 
 regenerate the same mask without storing it.
 """
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -43,7 +44,10 @@ class DirectGrads:
 
     active: Optional['DirectGrads'] = None
 
-    def __init__(self, views: dict, on_ready=None, views32: Optional[dict] = None):
+    def __init__(self, views: dict, on_ready=None, views32: Optional[dict] = None, params=()):
+        # keyed by id(param): `owners` holds weak references so that a recycled id (a parameter of a model that has been
+        # garbage-collected while this sink is still installed) is never mistaken for one of ours
+        self.owners = {id(p): weakref.ref(p) for p in params}
         self.views = views            # id(param) -> bf16 arena view
         # id(param) -> fp32 main-gradient view (GEMM weights): weight-gradient GEMMs TMA-reduce-add their (split-K)
         # partial tiles straight into it; the Trainer rounds it into the bf16 arena once per optimizer step
@@ -54,9 +58,13 @@ class DirectGrads:
     def start_step(self) -> None:
         self.written.clear()
 
+    def owns(self, param) -> bool:
+        ref = self.owners.get(id(param))
+        return ref is not None and ref() is param
+
     def sink(self, param) -> tuple:
         """(out tensor, accumulate flag) for this parameter, or (None, False) when not managed."""
-        view = self.views.get(id(param))
+        view = self.views.get(id(param)) if self.owns(param) else None
         if view is None:
             return None, False
         acc = id(param) in self.written
@@ -66,7 +74,7 @@ class DirectGrads:
     def ready(self, *params) -> None:
         if self.on_ready is not None:
             for p in params:
-                if p is not None and id(p) in self.views:
+                if p is not None and self.owns(p):
                     self.on_ready(p)
 
 
@@ -84,7 +92,7 @@ def _ready(*params):
 def _sink32(param):
     """fp32 main-gradient view of a GEMM weight (None when the Trainer does not provide one)."""
     d = DirectGrads.active
-    return d.views32.get(id(param)) if (d is not None and param is not None) else None
+    return d.views32.get(id(param)) if (d is not None and param is not None and d.owns(param)) else None
 
 
 def _wgrad(dy: Tensor, x: Tensor, param):
@@ -251,11 +259,26 @@ def _keep_buffer(x: Tensor, p: float) -> Optional[Tensor]:
     return torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
 
 
-def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=None):
+def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=None, need_ln=True, need_lin=True):
     """Shared backward of `LN(residual + dropout(x))`: returns (dx, dresidual, dgamma, dbeta, dlin_bias) with the
-    parameter gradients routed through DirectGrads when active (None is returned for those)."""
+    parameter gradients routed through DirectGrads when active (None is returned for those). need_ln / need_lin = False
+    (frozen parameters) skip the corresponding column sums."""
     p_gamma, p_beta = params
     D = dy.shape[1]
+    if not need_ln or not need_lin:
+        dgamma = dbeta = dlin = None
+        sg = sb = sl = None
+        ag = ab = al = False
+        if need_ln:
+            sg, ag = _sink(p_gamma); sb, ab = _sink(p_beta)
+            dgamma = sg if sg is not None else torch.empty(D, dtype=BF16, device=dy.device)
+            dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
+        if need_lin and lin_bias is not None:
+            sl, al = _sink(lin_bias)
+            dlin = sl if sl is not None else torch.empty(D, dtype=BF16, device=dy.device)
+        dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
+                                        accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep)
+        return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
     sg, ag = _sink(p_gamma)
     sb, ab = _sink(p_beta)
     sl, al = _sink(lin_bias)
@@ -304,11 +327,24 @@ class AttnSublayerFn(torch.autograd.Function):
         B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset = ctx.dims
         D = H * 64
         p_in_w, p_in_b, p_out_w, p_out_b, p_gamma, p_beta = ctx.params
-        dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b, keep)
+        need = ctx.needs_input_grad   # (x, key, in_w, in_b, out_w, out_b, gamma, beta, ...): frozen parameters cost nothing
+        dy, dres, dgamma, dbeta, d_out_b = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_out_b, keep,
+                                                   need_ln=need[6], need_lin=need[5])
         _ready(p_gamma, p_beta)
         d_o = K.linear_dgrad(dy, out_w)
-        d_out_w = _wgrad(dy, o, p_out_w)
+        d_out_w = _wgrad(dy, o, p_out_w) if need[4] else None
         _ready(p_out_w, p_out_b)
+        if not need[2]:   # frozen projections: only the input gradients
+            if self_attn:
+                dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+                K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
+                                dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
+                return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 10
+            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            dkey = K.linear_dgrad(dkv, in_w[:2 * D]) if need[1] else None
+            return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 10
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
         w32 = _sink32(p_in_w)
@@ -368,14 +404,18 @@ class FFNSublayerFn(torch.autograd.Function):
         x, w1, w2, h, s, gamma, mean, rstd, bits, keep = ctx.saved_tensors
         p, seed, offset = ctx.cfg
         p_w1, p_b1, p_w2, p_b2, p_gamma, p_beta = ctx.params
-        dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2, keep)
+        need = ctx.needs_input_grad    # frozen parameters (adapter training): no weight-gradient GEMMs / column sums
+        dy, dres, dgamma, dbeta, db2 = _ln_bwd(_c(dout), s, gamma, mean, rstd, p, seed, offset, (p_gamma, p_beta), p_b2, keep,
+                                               need_ln=need[5], need_lin=need[4])
         _ready(p_gamma, p_beta)
         dh = K.linear_dgrad(dy, w2, relu_mask=h if bits is None else None, relu_bits=bits)
-        dw2 = _wgrad(dy, h, p_w2)
+        dw2 = _wgrad(dy, h, p_w2) if need[3] else None
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1, residual=dres)
-        dw1 = _wgrad(dh, x, p_w1)
-        o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
+        dw1 = _wgrad(dh, x, p_w1) if need[1] else None
+        db1 = None
+        if need[2]:
+            o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None, None
 

@@ -198,6 +198,19 @@ class SpeechTranslationTask:
     def decoder_num_embeddings(self) -> int:
         return len(self.dictionary)
 
+    def get_langs_or_domains(self, key: str) -> set:
+        """pasero/tasks/translation.py (TranslationTask.get_langs_or_domains): the values `key` can take in this task's
+        corpora, read from the flat config (`source_langs` / `target_langs` / `domains` lists or the single
+        `source_lang` / `target_lang` / `domain`)."""
+        extra = self.cfg.extra
+
+        def values(name):
+            v = extra.get(name + 's') or ([extra[name]] if extra.get(name) else [])
+            return set(v)
+        if key == 'lang':
+            return values('source_lang') | values('target_lang')
+        return values(key)
+
     def should_skip(self, source_len: int, target_len: int) -> bool:
         ratio = source_len / max(1, target_len)
         return bool(source_len == 0 or source_len > self.max_source_len or target_len > self.max_target_len or

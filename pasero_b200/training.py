@@ -236,7 +236,7 @@ class Trainer:
         self.direct = ops.DirectGrads({id(p): self.arena.view(self.arena.grad, i) for i, p in enumerate(self.arena.params)},
                                       on_ready,
                                       {id(p): self.arena.view(self.arena.grad32, i) for i, p in enumerate(self.arena.params)
-                                       if self.arena.is32[i]})
+                                       if self.arena.is32[i]}, params=self.arena.params)
         ops.DirectGrads.active = self.direct
         self._ranges32_all = self.arena.ranges32(0, self.arena.numel)
         if self.buckets is not None:

@@ -21,12 +21,48 @@ def defined(*args):
     return next((x for x in args if x is not None), None)
 
 
-class TransformerEncoderLayer(nn.Module):
+_LANG_PREFIX, _DOMAIN_PREFIX = 'lang:', 'domain:'
+
+
+def _adapter_names(cfg: TransformerConfig, task, side: str) -> tuple:
+    """adapters.py:67-105: explicit names, or one adapter per language / domain of the task, or ('default',)."""
+    explicit = getattr(cfg, f'{side}_adapters')
+    by = getattr(cfg, f'{side}_adapters_by')
+    if explicit is not None:
+        names = list(explicit)
+    elif by:
+        names = []
+        for key in by:
+            prefix = _DOMAIN_PREFIX if key == 'domain' else _LANG_PREFIX
+            names += [f'{prefix}{v}' for v in sorted(task.get_langs_or_domains(key))]
+    else:
+        names = ['default']
+    return tuple(dict.fromkeys(names))
+
+
+class _AdapterMixin:
+    """AdapterTransformer{Encoder,Decoder}Layer of the reference (adapters.py:232-301): adapters applied after the layer."""
+
+    def init_adapters(self, cfg, dim: int, names, enabled: bool) -> None:
+        self.adapters = nn.ModuleDict({uid: modules.AdapterLayer(cfg.embed_dim, dim, cfg.adapter_zero_init) for uid in names}) \
+            if enabled else None
+        self.adapters_in_use = tuple(names) if enabled else ()
+
+    def apply_adapters(self, x: Tensor) -> Tensor:
+        for uid in self.adapters_in_use:
+            x = self.adapters[uid](x)
+        return x
+
+
+class TransformerEncoderLayer(nn.Module, _AdapterMixin):
     """pasero/models/transformer.py:913-1099"""
 
-    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int):
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int, adapter_names=()):
         super().__init__()
         self.cfg, self.layer_id = cfg, layer_id
+        self.init_adapters(cfg, cfg.encoder_adapter_dim, adapter_names, bool(
+            cfg.adapters and cfg.encoder_adapter_dim and adapter_names and
+            (cfg.encoder_adapter_layer_ids is None or layer_id in cfg.encoder_adapter_layer_ids)))
         self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.encoder_attention_heads, dropout=cfg.attention_dropout,
                                                     scaled=cfg.scale_attn, key_bias=cfg.attention_key_bias)
         self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
@@ -45,7 +81,7 @@ class TransformerEncoderLayer(nn.Module):
             x = ops.attn_sublayer(x, None, self.self_attn, ln1, key_lengths if key_lengths is not None else
                                   self.self_attn.key_lengths_of(padding_mask), False, p, eps)
             x = ops.ffn_sublayer(x, self.fc1, self.fc2, ln2, p, eps)
-            return x, ({self.name: x} if self.name in return_layers else {})
+            return self.apply_adapters(x), ({self.name: x} if self.name in return_layers else {})
         residual = x
         if self.prenorm:
             x = ops.dropout_add_ln(x, None, ln1.weight, ln1.bias, 0.0, eps)
@@ -62,15 +98,18 @@ class TransformerEncoderLayer(nn.Module):
             x = ops.dropout_add_ln(x, residual, None, None, p, eps)
         else:
             x = ops.dropout_add_ln(x, residual, ln2.weight, ln2.bias, p, eps)
-        return x, ({self.name: x} if self.name in return_layers else {})
+        return self.apply_adapters(x), ({self.name: x} if self.name in return_layers else {})
 
 
-class TransformerDecoderLayer(nn.Module):
+class TransformerDecoderLayer(nn.Module, _AdapterMixin):
     """pasero/models/transformer.py:1102-1417"""
 
-    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int):
+    def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, layer_id: int, adapter_names=()):
         super().__init__()
         self.cfg, self.layer_id = cfg, layer_id
+        self.init_adapters(cfg, cfg.decoder_adapter_dim, adapter_names, bool(
+            cfg.adapters and cfg.decoder_adapter_dim and adapter_names and
+            (cfg.decoder_adapter_layer_ids is None or layer_id in cfg.decoder_adapter_layer_ids)))
         self.self_attn = modules.MultiheadAttention(cfg.embed_dim, cfg.decoder_attention_heads, dropout=cfg.attention_dropout,
                                                     causal=True, scaled=cfg.scale_attn, key_bias=cfg.attention_key_bias)
         self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
@@ -105,7 +144,7 @@ class TransformerDecoderLayer(nn.Module):
             enc_len = encoder_lengths if encoder_lengths is not None else self.encoder_attn.key_lengths_of(encoder_mask)
             x = ops.attn_sublayer(x, encoder_out, self.encoder_attn, self.encoder_attn_layer_norm, enc_len, False, p, eps)
             x = ops.ffn_sublayer(x, self.fc1, self.fc2, self.final_layer_norm, p, eps)
-            return x, ({self.name: x} if self.name in return_layers else {})
+            return self.apply_adapters(x), ({self.name: x} if self.name in return_layers else {})
         x = self._block(x, self.self_attn_layer_norm, lambda h: self.self_attn(h, h, h)[0], p, eps)
         x = self._block(x, self.encoder_attn_layer_norm,
                         lambda h: self.encoder_attn(h, encoder_out, encoder_out, attn_mask=encoder_mask,
@@ -113,7 +152,18 @@ class TransformerDecoderLayer(nn.Module):
         x = self._block(x, self.final_layer_norm,
                         lambda h: ops.ffn(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                                           self.cfg.activation_fn), p, eps)
-        return x, ({self.name: x} if self.name in return_layers else {})
+        return self.apply_adapters(x), ({self.name: x} if self.name in return_layers else {})
+
+
+def _select_adapters(layers, by: tuple, meta: Optional[dict]) -> None:
+    """AdapterTransformer{Encoder,Decoder}.forward (adapters.py:186-197, 219-229): with `*_adapters_by`, the adapters of
+    the batch's language / domain are the ones in use."""
+    if not by:
+        return
+    names = tuple(f"{_DOMAIN_PREFIX if key == 'domain' else _LANG_PREFIX}{(meta or {})[key]}" for key in by)
+    for layer in layers:
+        if layer.adapters is not None:
+            layer.adapters_in_use = names
 
 
 class TransformerEncoder(nn.Module):
@@ -136,7 +186,9 @@ class TransformerEncoder(nn.Module):
                                                             cfg.positional_encoding_shift)
         self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
         self.dropout_p = defined(cfg.embed_dropout, cfg.dropout)
-        self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, dist_cfg, i) for i in range(cfg.encoder_layers)])
+        self.adapter_names = _adapter_names(cfg, task, 'encoder') if cfg.adapters else ()
+        self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, dist_cfg, i, self.adapter_names)
+                                     for i in range(cfg.encoder_layers)])
         self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.encoder_prenorm else None
 
     def forward(self, encoder_input: Tensor, encoder_input_length: Tensor, return_layers=(), meta: dict = {},
@@ -144,6 +196,7 @@ class TransformerEncoder(nn.Module):
         """encoder_input (B, S, 80) bf16 features (or, with padded_layout=(frames,), the zero-padded layout written
         by the fbank kernel). Returns (encoder_out (B, S', D), padding_mask (B, S') bool True = pad, layer_outputs)."""
         return_layers = return_layers or ()
+        _select_adapters(self.layers, self.cfg.encoder_adapters_by if self.cfg.adapters else (), meta)
         if encoder_input.ndim != 3:
             raise NotImplementedError('text encoder inputs are outside the ST path')
         x = encoder_input
@@ -186,11 +239,14 @@ class TransformerDecoder(nn.Module):
                                                             cfg.positional_encoding_shift)
         self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
         self.dropout_p = defined(cfg.embed_dropout, cfg.decoder_dropout, cfg.dropout)
-        self.layers = nn.ModuleList([TransformerDecoderLayer(cfg, dist_cfg, i) for i in range(cfg.decoder_layers)])
+        self.adapter_names = _adapter_names(cfg, task, 'decoder') if cfg.adapters else ()
+        self.layers = nn.ModuleList([TransformerDecoderLayer(cfg, dist_cfg, i, self.adapter_names)
+                                     for i in range(cfg.decoder_layers)])
         self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.decoder_prenorm else None
         self.output_projection = None  # tied (cfg.tied_output_projection)
 
-    def features(self, encoder_out, encoder_mask, decoder_input, return_layers=(), encoder_lengths=None):
+    def features(self, encoder_out, encoder_mask, decoder_input, return_layers=(), encoder_lengths=None, meta=None):
+        _select_adapters(self.layers, self.cfg.decoder_adapters_by if self.cfg.adapters else (), meta)
         B, T = decoder_input.shape
         D = self.cfg.embed_dim
         p = self.dropout_p if self.training else 0.0
@@ -211,7 +267,7 @@ class TransformerDecoder(nn.Module):
         """Returns (logits (B, T, V), layer_outputs)"""
         if state is not None:
             raise NotImplementedError('incremental decoding is outside the training path')
-        x, layer_outputs = self.features(encoder_out, encoder_mask, decoder_input, return_layers or (), encoder_lengths)
+        x, layer_outputs = self.features(encoder_out, encoder_mask, decoder_input, return_layers or (), encoder_lengths, meta)
         return self.embed_tokens.projection(x), layer_outputs
 
 
@@ -225,6 +281,14 @@ class Transformer(nn.Module):
         self.batch_by = None
         self.encoder = self.build_encoder()
         self.decoder = self.build_decoder(embed=None)
+        if cfg.adapters:   # AdapterTransformer (adapters.py:62-119)
+            by = sorted(set(cfg.encoder_adapters_by) | set(cfg.decoder_adapters_by))
+            self.batch_by = by or None
+            self.find_unused_parameters = bool(by)
+            if not cfg.train_all_params:
+                for name, param in self.named_parameters():
+                    if 'adapters' not in name.split('.'):
+                        param.requires_grad = False
         self.defer_logs = False   # True: logs hold device scalars (no host sync inside forward)
         self._stats = None
 
@@ -261,7 +325,7 @@ class Transformer(nn.Module):
         dec_in = decoder_input[:, :-1]
         enc_kwargs = {k: v for k, v in kwargs.items() if k in ('return_layers', 'meta', 'padded_layout')}
         encoder_out, encoder_mask, _ = self.encoder(encoder_input, encoder_input_length, **enc_kwargs)
-        x, _ = self.decoder.features(encoder_out, encoder_mask, dec_in, (), self.encoder._last_lengths)
+        x, _ = self.decoder.features(encoder_out, encoder_mask, dec_in, (), self.encoder._last_lengths, kwargs.get('meta'))
         return self.compute_loss(x, target, {}, fused=True)
 
     def compute_loss(self, logits_or_features: Tensor, target: Tensor, layer_outputs: dict, *args, fused: bool = False, **kwargs):

@@ -40,7 +40,7 @@ def import_reference():
     return pasero
 
 
-def make_task_and_model(pasero, tmp, extra=()):
+def make_task_and_model(pasero, tmp, extra=(), adapters=False):
     from pasero.config import TrainingConfig, get_task_class, get_architecture
     dict_path = os.path.join(tmp, 'dict.txt')
     with open(dict_path, 'w') as f:
@@ -66,8 +66,8 @@ def make_task_and_model(pasero, tmp, extra=()):
     torch.manual_seed(1234)
     model = get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)
     # seeded, reference-independent weights (bf16-representable), so the fixtures need not carry them
-    sd = synth.tiny_state_dict()
-    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == synth.tiny_param_shapes()
+    sd = synth.adapter_state_dict() if adapters else synth.tiny_state_dict()
+    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == (synth.adapter_param_shapes() if adapters else synth.tiny_param_shapes())
     missing = model.load_state_dict(sd, strict=False)
     assert all('_float_tensor' in k for k in missing.missing_keys) and not missing.unexpected_keys, missing
     return cfg, task, model
@@ -98,6 +98,28 @@ def make_whisper_model(pasero, tmp):
     missing = model.load_state_dict(synth.wsp_state_dict(), strict=False)
     assert not missing.missing_keys and not missing.unexpected_keys, missing
     return cfg, task, model
+
+
+def golden_model_adapters(pasero, tmp, out):
+    """`--arch adapter_transformer` on the tiny ST model (pasero/models/adapters.py): adapters trained, base frozen."""
+    cfg, task, model = make_task_and_model(pasero, tmp, ('--arch', 'adapter_transformer', '--encoder-adapter-dim',
+                                                                    str(synth.ADAPTER_DIM), '--decoder-adapter-dim',
+                                                                    str(synth.ADAPTER_DIM)), adapters=True)
+    model.train()
+    batch = synth.model_batch()
+    enc_out, enc_mask, _ = model.encoder(batch['encoder_input'].clone(), batch['encoder_input_length'], meta=batch['meta'])
+    logits, _ = model.decoder(enc_out, enc_mask, batch['decoder_input'][:, :-1], meta=batch['meta'])
+    loss, logs = model(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    model.zero_grad()
+    loss.backward()
+    trainable = [k for k, p in model.named_parameters() if p.requires_grad]
+    assert all('adapters' in k for k in trainable) and trainable
+    torch.save({
+        'loss': loss.item(), 'logs': logs, 'encoder_out': enc_out.detach(), 'logits': logits.detach(),
+        'trainable': trainable, 'param_names': [k for k, _ in model.named_parameters()],
+        'grads': {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
+    }, os.path.join(out, 'st_adapter_model.pt'))
+    print('adapter model golden: loss', loss.item(), logs, 'trainable', len(trainable), 'of', len(list(model.parameters())))
 
 
 def golden_model_whisper(pasero, cfg, task, model, out):
@@ -257,6 +279,13 @@ def golden_training_curve(pasero, cfg, task, model, out):
 def main():
     out = HERE
     pasero = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'adapters':     # only the adapter fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            golden_model_adapters(pasero, tmp, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'whisper':      # only the Whisper-style fixture
         tmp = tempfile.mkdtemp()
         try:
@@ -276,6 +305,7 @@ def main():
         golden_training_curve(pasero, cfg2, task2, model2, out)
         cfg3, task3, model3 = make_whisper_model(pasero, tmp)
         golden_model_whisper(pasero, cfg3, task3, model3, out)
+        golden_model_adapters(pasero, tmp, out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -200,6 +200,43 @@ def wsp_state_dict() -> dict:
     return sd
 
 
+# ---- adapter variant (pasero/models/adapters.py, `--arch adapter_transformer`): the tiny ST model + a bottleneck adapter
+# after every layer; only the adapters are trained (base parameters frozen)
+ADAPTER_DIM = 16
+
+
+def adapter_param_shapes() -> dict:
+    t = TINY
+    d = t['embed_dim']
+    shapes = dict(tiny_param_shapes())
+    for side, n in (('encoder', t['encoder_layers']), ('decoder', t['decoder_layers'])):
+        for i in range(n):
+            p = f'{side}.layers.{i}.adapters.default'
+            shapes[p + '.down.weight'] = (ADAPTER_DIM, d)
+            shapes[p + '.down.bias'] = (ADAPTER_DIM,)
+            shapes[p + '.up.weight'] = (d, ADAPTER_DIM)
+            shapes[p + '.up.bias'] = (d,)
+            shapes[p + '.layer_norm.weight'] = (d,)
+            shapes[p + '.layer_norm.bias'] = (d,)
+    return shapes
+
+
+def adapter_state_dict() -> dict:
+    sd = dict(tiny_state_dict())
+    rng = np.random.RandomState(55)
+    for name, shape in adapter_param_shapes().items():
+        if name in sd:
+            continue
+        if 'layer_norm' in name:
+            w = (1.0 + 0.1 * rng.randn(*shape)) if name.endswith('weight') else 0.05 * rng.randn(*shape)
+        elif name.endswith('bias'):
+            w = 0.02 * rng.randn(*shape)
+        else:
+            w = rng.randn(*shape) * shape[1] ** -0.5
+        sd[name] = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+    return sd
+
+
 def summarize_grad(g: torch.Tensor) -> dict:
     """Compact but discriminating digest of a gradient tensor (full tensor when small)."""
     g = g.detach().float()

@@ -173,6 +173,25 @@ def test_whisper_variant_matches_reference():
             assert torch.allclose(g2.sum(1), d['row_sum'], atol=2e-3, rtol=2e-3), k
 
 
+def test_adapter_variant_matches_reference():
+    """`adapter_transformer` (bottleneck adapters after every layer, base frozen): loss, logits and the adapter gradients
+    against the reference's own outputs."""
+    gold = torch.load(os.path.join(GOLD, 'st_adapter_model.pt'), weights_only=False)
+    sd = {k: v.clone().requires_grad_(k in gold['trainable']) for k, v in synth.adapter_state_dict().items()}
+    assert sorted(sd) == sorted(gold['param_names'])
+    batch = synth.model_batch()
+    layers = {}
+    loss, logs = om.forward(tiny_cfg(), sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'], layers)
+    assert abs(loss.item() - gold['loss']) < 1e-4 * abs(gold['loss'])
+    assert torch.allclose(layers['encoder_out'], gold['encoder_out'], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(layers['logits'], gold['logits'], atol=2e-4, rtol=1e-4)
+    loss.backward()
+    assert sorted(gold['grads']) == sorted(gold['trainable'])
+    for k, g in gold['grads'].items():
+        assert torch.allclose(sd[k].grad, g, atol=2e-4, rtol=2e-3), k
+    assert all(sd[k].grad is None for k in sd if k not in gold['trainable'])
+
+
 def test_train_step_curve_matches_reference():
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
     cfg = tiny_cfg()

@@ -192,6 +192,63 @@ def test_whisper_variant_matches_reference_and_oracle():
         assert abs(logs['gnorm'] - ologs['gnorm']) / ologs['gnorm'] < 5e-2, (step, logs['gnorm'], ologs['gnorm'])
 
 
+def test_adapter_variant_matches_reference_and_trains_only_adapters():
+    """`arch: adapter_transformer` (pasero/models/adapters.py): bottleneck adapters after every layer, base frozen. Forward
+    and the adapter gradients against the reference's golden vectors; a Trainer step must leave the frozen parameters
+    bit-identical and move only the adapters."""
+    from pasero_b200 import build_model
+    from pasero_b200.training import Trainer
+    gold = torch.load(os.path.join(GOLD, 'st_adapter_model.pt'), weights_only=False)
+    cfg = tiny_training_cfg(arch='adapter_transformer', encoder_adapter_dim=synth.ADAPTER_DIM, decoder_adapter_dim=synth.ADAPTER_DIM)
+    task = tiny_task(cfg)
+    model = build_model(cfg, task)
+    missing = model.load_state_dict(synth.adapter_state_dict(), strict=False)
+    assert not missing.unexpected_keys and all('_float_tensor' in k for k in missing.missing_keys), missing
+    names = [k for k in model.state_dict() if not k.endswith('_float_tensor')]
+    assert sorted(names) == sorted(gold['param_names'])
+    model.to(BF16).cuda().train()
+    batch = synth.model_batch()
+    cb = to_cuda(batch)
+    enc_out, enc_mask, _ = model.encoder(cb['encoder_input'], cb['encoder_input_length'], meta=batch['meta'])
+    logits, _ = model.decoder(enc_out, enc_mask, cb['decoder_input'][:, :-1], encoder_lengths=model.encoder._last_lengths,
+                              meta=batch['meta'])
+    assert rel_to_max(enc_out, gold['encoder_out']) < 3e-2
+    assert rel_to_max(logits, gold['logits']) < 3e-2
+    loss, logs = model(**cb)
+    assert abs(loss.item() - gold['loss']) / gold['loss'] < 1e-2
+    model.zero_grad()
+    loss.backward()
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    assert len(trainable) == len(gold['trainable'])
+    assert all(p.grad is None for p in model.parameters() if not p.requires_grad)
+    saved = [(p, p.data) for p in trainable]
+    for p in trainable:
+        p.data = p.grad
+    try:
+        grads = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if k in gold['grads']}
+    finally:
+        for p, d in saved:
+            p.data = d
+    bad = {}
+    for k, want in gold['grads'].items():
+        cos = torch.nn.functional.cosine_similarity(grads[k].flatten(), want.flatten(), dim=0).item()
+        if rel_to_max(grads[k], want) > 0.3 or cos < 0.98:
+            bad[k] = (rel_to_max(grads[k], want), cos)
+    assert not bad, bad
+    # Trainer: only the adapters move
+    model2 = build_model(cfg, task)
+    model2.load_state_dict(synth.adapter_state_dict(), strict=False)
+    trainer = Trainer(cfg, task, model2)
+    before = {k: v.detach().clone() for k, v in model2.state_dict().items() if v.is_floating_point()}
+    for step in range(2):       # lr(0) = 0: the second step is the first that moves parameters
+        logs = trainer.train_step(iter([synth.train_batches()[step]]))
+        assert logs['gnorm'] > 0
+    after = model2.state_dict()
+    moved = {k for k in before if not torch.equal(before[k], after[k])}
+    assert moved and all('adapters' in k for k in moved), sorted(moved)[:5]
+    assert trainer.arena.numel < sum(p.numel() for p in model2.parameters()) // 4     # the arenas hold the adapters only
+
+
 def test_loss_curve_200_steps_matches_oracle():
     from pasero_b200.training import Trainer
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
