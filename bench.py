@@ -156,7 +156,7 @@ def run_reference(args):
     value, ms = time_oracle(batch, max(1, args.steps), max(0, args.warmup), threads)
     sample = f'{batch} utterances x 10 s (of the {B_PER_GPU}-utterance step), {args.steps} steps after {args.warmup} warm-up'
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': 0, 'steps': args.steps,
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus),
         'cpu_baseline': {'value': value, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample},

@@ -257,6 +257,9 @@ class Trainer:
         ops.ProjCEFn.unit_loss_grad = True
         ops.DropoutState.reseed(cfg.seed if cfg.seed is not None else int(time.time()))
         self._graphs = {}
+        # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
+        # (tools/ddp_check.py) but the processes hang at teardown / in long runs on this stack (NCCL 2.28.9, torch 2.11)
+        self.graph_collectives = os.environ.get('PB200_GRAPH_NCCL', '0') == '1'
         self.saved = True
 
     # ------------------------------------------------------------------ step pieces
@@ -358,20 +361,30 @@ class Trainer:
             self._write_hyper()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
+            # graph_collectives: the bucketed allreduces (side stream, launched from backward as buckets complete) and the
+            # scalar allreduce are captured INSIDE the graph, so they overlap backward exactly as in the eager step;
+            # otherwise every bucket is reduced between the graph and the optimizer kernels
+            in_graph = self.buckets is not None and self.graph_collectives
             if self.buckets is not None:
-                self.buckets.start_step(sync=False)   # the allreduce runs between the two graph segments
-            with torch.cuda.stream(side):   # warm-up outside capture (lazy inits, workspace sizes)
+                self.buckets.start_step(sync=in_graph)
+            with torch.cuda.stream(side):   # warm-up outside capture (lazy inits, workspace sizes, NCCL communicators)
                 for k, v in tensors.items():
                     static[k].copy_(v)
                 self._graph_body(static, extras)
+                if in_graph:
+                    self.buckets.finish(self.stats)
                 # the warm-up pass accumulated real gradients into the fp32 main-gradient arena; with buckets they are only
                 # flushed (and zeroed) after the replay below, which would add this batch's gradient a second time
                 self.arena.grad32.zero_()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             ops.DropoutState.offset = 0
+            if self.buckets is not None:
+                self.buckets.start_step(sync=in_graph)
             with torch.cuda.graph(graph):
                 self._graph_body(static, extras)
+                if in_graph:
+                    self.buckets.finish(self.stats)
             self._graphs[key] = (graph, static)
         graph, static = self._graphs[key]
         for k, v in tensors.items():
@@ -379,7 +392,7 @@ class Trainer:
         self._write_hyper()
         graph.replay()
         self.rng_base += 1
-        if self.buckets is not None:
+        if self.buckets is not None and not self.graph_collectives:
             self.buckets.allreduce_all(self.stats)
         self._optimizer_kernels()
         return self._finish_step()
