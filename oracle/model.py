@@ -171,17 +171,23 @@ def adapters(cfg: STConfig, sd, prefix: str, x: Tensor, names) -> Tensor:
 
 def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tensor, layer_outputs: Optional[dict] = None):
     """ConvolutionSubsampler.forward (modules.py:819-834) + TransformerEncoder.forward (transformer.py:697-752)."""
-    x = encoder_input.transpose(1, 2)
-    for i, (k, s) in enumerate(zip(cfg.conv_kernel_sizes, cfg.conv_strides)):
-        x = F.conv1d(x, sd[f'encoder.subsample.conv_layers.{i}.weight'], sd[f'encoder.subsample.conv_layers.{i}.bias'],
-                     stride=s, padding=k // 2)
-        x = F.glu(x, dim=1) if cfg.conv_activation == 'glu' else F.gelu(x)   # modules.py:803, 831-832
-    x = x.transpose(1, 2)
-    length = conv_out_length(encoder_input_length, cfg.conv_kernel_sizes, cfg.conv_strides)
+    if encoder_input.ndim == 2:     # token ids (`--task translation`): the shared embedding table, transformer.py:728-732
+        x = F.embedding(encoder_input.clip(min=0), sd['encoder.embed_tokens.weight'], padding_idx=cfg.padding_idx)
+        length = encoder_input_length
+        kernel_sizes = strides = ()
+    else:
+        kernel_sizes, strides = cfg.conv_kernel_sizes, cfg.conv_strides
+        x = encoder_input.transpose(1, 2)
+        for i, (k, s) in enumerate(zip(kernel_sizes, strides)):
+            x = F.conv1d(x, sd[f'encoder.subsample.conv_layers.{i}.weight'], sd[f'encoder.subsample.conv_layers.{i}.bias'],
+                         stride=s, padding=k // 2)
+            x = F.glu(x, dim=1) if cfg.conv_activation == 'glu' else F.gelu(x)   # modules.py:803, 831-832
+        x = x.transpose(1, 2)
+        length = conv_out_length(encoder_input_length, kernel_sizes, strides)
     if cfg.scale_embed:
         x = x * math.sqrt(cfg.embed_dim)
     mask = len_to_mask(length, x.shape[1])
-    max_len = int(conv_out_length(torch.tensor(cfg.encoder_max_len), cfg.conv_kernel_sizes, cfg.conv_strides))
+    max_len = int(conv_out_length(torch.tensor(cfg.encoder_max_len), kernel_sizes, strides))
     if cfg.positional_encoding == 'learned':   # rows shift .. shift + S - 1 of the trainable table
         x = x + sd['encoder.embed_positions.weight'][cfg.positional_encoding_shift:cfg.positional_encoding_shift + x.shape[1]].unsqueeze(0)
     else:

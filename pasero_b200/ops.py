@@ -457,7 +457,10 @@ class EmbedFn(torch.autograd.Function):
     gradient is the sum over the batch of the gradient reaching the sum (pasero/models/modules.py:460-484)."""
 
     @staticmethod
-    def forward(ctx, src, ids, pos, scale, p, L, padding_idx, pos_table=None, shift=0):
+    def forward(ctx, src, ids, pos, scale, p, L, padding_idx, pos_table=None, shift=0, notify_ready=True):
+        # notify_ready=False: the table is used again later in backward order (an encoder sharing it embeds tokens too);
+        # only its last user reports the parameter's gradient complete (data-parallel bucket bookkeeping)
+        ctx.notify_ready = notify_ready
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
         M = ids.numel() if ids is not None else src.shape[0]
         D = src.shape[1]
@@ -487,19 +490,21 @@ class EmbedFn(torch.autograd.Function):
             dpos = _ret(full, so)
         if ids_flat is None:
             dx = dense if (dense is not None and scale == 1.0) else K.embed_bwd(dy, None, M, D, scale, p, seed, offset)
-            return dx, None, None, None, None, None, None, dpos, None
+            return dx, None, None, None, None, None, None, dpos, None, None
         t32 = _sink32(ctx.table)
         if t32 is not None:       # scatter-add straight into the fp32 main gradient of the (tied) embedding table
             K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, t32)
-            _ready(ctx.table)
-            return None, None, None, None, None, None, None, dpos, None
+            if ctx.notify_ready:
+                _ready(ctx.table)
+            return None, None, None, None, None, None, None, dpos, None, None
         dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
         K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
         so, acc = _sink(ctx.table)
         dtable = so if so is not None else torch.empty(rows, D, dtype=BF16, device=dy.device)
         K.f32_to_bf16(dtable32, dtable, accumulate=acc)
-        _ready(ctx.table)
-        return _ret(dtable, so), None, None, None, None, None, None, dpos, None
+        if ctx.notify_ready:
+            _ready(ctx.table)
+        return _ret(dtable, so), None, None, None, None, None, None, dpos, None, None
 
 
 class FFNGeluFn(torch.autograd.Function):

@@ -198,6 +198,14 @@ class SpeechTranslationTask:
     def decoder_num_embeddings(self) -> int:
         return len(self.dictionary)
 
+    @classmethod
+    def text(cls, cfg: TrainingConfig, dictionary: Dictionary, target_tags: tuple = ()) -> 'SpeechTranslationTask':
+        """The text-input flavour (`--task translation`, pasero/tasks/translation.py): same batch contract, but
+        `encoder_input` holds token ids of the (shared) dictionary, so the encoder needs an embedding table."""
+        task = cls(cfg, dictionary, target_tags)
+        task.encoder_num_embeddings = len(dictionary)
+        return task
+
     def get_langs_or_domains(self, key: str) -> set:
         """pasero/tasks/translation.py (TranslationTask.get_langs_or_domains): the values `key` can take in this task's
         corpora, read from the flat config (`source_langs` / `target_langs` / `domains` lists or the single

@@ -172,16 +172,26 @@ class TransformerEncoder(nn.Module):
     def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task=None, embed=None):
         super().__init__()
         self.cfg = cfg
-        self.embed_tokens = None  # SpeechTranslationTask.encoder_num_embeddings == 0 (speech_translation.py:29-31)
-        input_dim = cfg.input_dim or cfg.embed_dim
-        if not cfg.conv_kernel_sizes:
-            raise NotImplementedError('the ST path expects a conv subsampler (conv_kernel_sizes)')
-        conv_input_dim = cfg.conv_input_dim or input_dim
-        if conv_input_dim != input_dim:
-            raise NotImplementedError('in_linear (input_dim != conv_input_dim) is a "next" row of SURVEY.md §8f')
-        self.subsample = modules.ConvolutionSubsampler(conv_input_dim, cfg.conv_channels or conv_input_dim, cfg.embed_dim,
-                                                       cfg.conv_kernel_sizes, cfg.conv_strides, cfg.conv_activation)
-        encoder_max_len = int(self.subsample.get_new_length(torch.tensor(cfg.encoder_max_len)))
+        self.padding_idx = getattr(task, 'padding_idx', 1)
+        num_embeddings = getattr(task, 'encoder_num_embeddings', 0)
+        # SpeechTranslationTask.encoder_num_embeddings == 0 (speech_translation.py:29-31): features, no embedding table.
+        # Text tasks (`--task translation`): token ids through an embedding table, shared with the decoder when
+        # `shared_embeddings` (transformer.py:150-176, 624-640)
+        if num_embeddings > 0:
+            self.embed_tokens = embed if embed is not None else modules.Embedding(num_embeddings, cfg.embed_dim, self.padding_idx)
+            self.subsample = None
+            encoder_max_len = cfg.encoder_max_len
+        else:
+            self.embed_tokens = None
+            input_dim = cfg.input_dim or cfg.embed_dim
+            if not cfg.conv_kernel_sizes:
+                raise NotImplementedError('feature inputs expect a conv subsampler (conv_kernel_sizes)')
+            conv_input_dim = cfg.conv_input_dim or input_dim
+            if conv_input_dim != input_dim:
+                raise NotImplementedError('in_linear (input_dim != conv_input_dim) is a "next" row of SURVEY.md §8f')
+            self.subsample = modules.ConvolutionSubsampler(conv_input_dim, cfg.conv_channels or conv_input_dim, cfg.embed_dim,
+                                                           cfg.conv_kernel_sizes, cfg.conv_strides, cfg.conv_activation)
+            encoder_max_len = int(self.subsample.get_new_length(torch.tensor(cfg.encoder_max_len)))
         self.embed_positions = modules.positional_embedding(cfg.encoder_positional_encoding, encoder_max_len, cfg.embed_dim,
                                                             cfg.positional_encoding_shift)
         self.embed_scale = math.sqrt(cfg.embed_dim) if cfg.scale_embed else 1.0
@@ -197,23 +207,30 @@ class TransformerEncoder(nn.Module):
         by the fbank kernel). Returns (encoder_out (B, S', D), padding_mask (B, S') bool True = pad, layer_outputs)."""
         return_layers = return_layers or ()
         _select_adapters(self.layers, self.cfg.encoder_adapters_by if self.cfg.adapters else (), meta)
-        if encoder_input.ndim != 3:
-            raise NotImplementedError('text encoder inputs are outside the ST path')
-        x = encoder_input
-        if x.dtype != BF16:
-            x = x.to(BF16)
-        if padded_layout is not None:
-            x, length = self.subsample.forward_padded(x, padded_layout[0], encoder_input_length)
-        else:
-            x, length = self.subsample(x, encoder_input_length)
         B = encoder_input.shape[0]
         D = self.cfg.embed_dim
-        S = x.numel() // (B * D)
         p = self.dropout_p if self.training else 0.0
-        pos = self.embed_positions.table(S)
         learned = self.embed_positions.weight if isinstance(self.embed_positions, modules.LearnedPositionalEmbedding) else None
-        x = ops.EmbedFn.apply(x.reshape(B * S, D), None, pos, float(self.embed_scale), float(p), S, -1, learned,
-                              self.embed_positions.shift).view(B, S, D)
+        if encoder_input.ndim == 2:      # token ids (text tasks)
+            if self.embed_tokens is None:
+                raise RuntimeError('token-id encoder input needs a task with encoder_num_embeddings > 0')
+            S = encoder_input.shape[1]
+            length = encoder_input_length
+            # this is the last use of the (possibly shared) table in backward order: it reports the parameter ready
+            x = ops.EmbedFn.apply(self.embed_tokens.weight, encoder_input, self.embed_positions.table(S), float(self.embed_scale),
+                                  float(p), S, self.padding_idx, learned, self.embed_positions.shift, True).view(B, S, D)
+        else:
+            x = encoder_input
+            if x.dtype != BF16:
+                x = x.to(BF16)
+            if padded_layout is not None:
+                x, length = self.subsample.forward_padded(x, padded_layout[0], encoder_input_length)
+            else:
+                x, length = self.subsample(x, encoder_input_length)
+            S = x.numel() // (B * D)
+            pos = self.embed_positions.table(S)
+            x = ops.EmbedFn.apply(x.reshape(B * S, D), None, pos, float(self.embed_scale), float(p), S, -1, learned,
+                                  self.embed_positions.shift).view(B, S, D)
         padding_mask = len_to_mask(length, size=S)
         key_lengths = length.clamp(max=S).to(torch.int32)
         layer_outputs = {}
@@ -244,6 +261,7 @@ class TransformerDecoder(nn.Module):
                                      for i in range(cfg.decoder_layers)])
         self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.decoder_prenorm else None
         self.output_projection = None  # tied (cfg.tied_output_projection)
+        self.table_shared_with_encoder = False   # set by Transformer when the encoder embeds tokens with the same table
 
     def features(self, encoder_out, encoder_mask, decoder_input, return_layers=(), encoder_lengths=None, meta=None):
         _select_adapters(self.layers, self.cfg.decoder_adapters_by if self.cfg.adapters else (), meta)
@@ -253,7 +271,7 @@ class TransformerDecoder(nn.Module):
         pos = self.embed_positions.table(T)
         learned = self.embed_positions.weight if isinstance(self.embed_positions, modules.LearnedPositionalEmbedding) else None
         x = ops.EmbedFn.apply(self.embed_tokens.weight, decoder_input, pos, float(self.embed_scale), float(p), T,
-                              self.padding_idx, learned, self.embed_positions.shift).view(B, T, D)
+                              self.padding_idx, learned, self.embed_positions.shift, not self.table_shared_with_encoder).view(B, T, D)
         layer_outputs = {}
         for layer in self.layers:
             x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths)
@@ -279,8 +297,13 @@ class Transformer(nn.Module):
         self.cfg, self.dist_cfg, self.task = cfg, dist_cfg, task
         self.find_unused_parameters = False
         self.batch_by = None
-        self.encoder = self.build_encoder()
-        self.decoder = self.build_decoder(embed=None)
+        if getattr(task, 'encoder_num_embeddings', 0) > 0 and cfg.shared_embeddings:   # transformer.py:150-176
+            self.decoder = self.build_decoder(embed=None)
+            self.encoder = self.build_encoder(embed=self.decoder.embed_tokens)
+            self.decoder.table_shared_with_encoder = True
+        else:
+            self.encoder = self.build_encoder()
+            self.decoder = self.build_decoder(embed=None)
         if cfg.adapters:   # AdapterTransformer (adapters.py:62-119)
             by = sorted(set(cfg.encoder_adapters_by) | set(cfg.decoder_adapters_by))
             self.batch_by = by or None

@@ -122,6 +122,46 @@ def golden_model_adapters(pasero, tmp, out):
     print('adapter model golden: loss', loss.item(), logs, 'trainable', len(trainable), 'of', len(list(model.parameters())))
 
 
+def golden_model_text(pasero, tmp, out):
+    """`--task translation --arch transformer` (token-id encoder, shared embeddings) on the tiny dimensions."""
+    from pasero.config import TrainingConfig, get_task_class, get_architecture
+    t = synth.TINY
+    args = ['--task', 'translation', '--arch', 'transformer',
+            '--encoder-layers', str(t['encoder_layers']), '--decoder-layers', str(t['decoder_layers']),
+            '--embed-dim', str(t['embed_dim']), '--encoder-ffn-dim', str(t['ffn_dim']), '--decoder-ffn-dim', str(t['ffn_dim']),
+            '--encoder-attention-heads', str(t['heads']), '--decoder-attention-heads', str(t['heads']),
+            '--data-dir', tmp, '--dict', 'dict.txt', '--tokenizer-path', 'bpecodes', '--source-lang', 'de', '--target-lang', 'en',
+            '--model-dir', os.path.join(tmp, 'model_text'), '--batch-size', '4000', '--dropout', '0', '--label-smoothing', '0.1',
+            '--metrics', '--early-stopping-metric', 'nll_loss', '--max-steps', '1000', '--valid-interval', '1000',
+            '--dataset-type', 'simple', '--dtype', 'float32', '--seed', '1234']
+    cfg = TrainingConfig(*args)
+    task = get_task_class(cfg.task)(cfg.data_dir, cfg.task_cfg)
+    task.setup_for_model(cfg.model_cfg)
+    cfg.dp_size, cfg.dp_rank, cfg.dp_local_size, cfg.dp_local_rank, cfg.start_rank = 1, 0, 1, 0, 0
+    torch.manual_seed(1234)
+    model = get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)
+    assert model.encoder.embed_tokens is model.decoder.embed_tokens
+    want = synth.text_param_shapes()
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items() if '_float_tensor' not in k} == want
+    missing = model.load_state_dict(synth.text_state_dict(), strict=False)
+    assert all('_float_tensor' in k for k in missing.missing_keys) and not missing.unexpected_keys, missing
+    model.train()
+    batch = synth.text_batch()
+    names = ['enc_0', f"enc_{t['encoder_layers'] - 1}", f"dec_{t['decoder_layers'] - 1}"]
+    enc_out, enc_mask, enc_layers = model.encoder(batch['encoder_input'].clone(), batch['encoder_input_length'], return_layers=names)
+    logits, dec_layers = model.decoder(enc_out, enc_mask, batch['decoder_input'][:, :-1], return_layers=names)
+    loss, logs = model(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    model.zero_grad()
+    loss.backward()
+    torch.save({
+        'loss': loss.item(), 'logs': logs, 'encoder_out': enc_out.detach(), 'encoder_mask': enc_mask, 'logits': logits.detach(),
+        'layers': {k: v.detach() for k, v in {**enc_layers, **dec_layers}.items()},
+        'grads': {k: synth.summarize_grad(p.grad) for k, p in model.named_parameters()},
+        'param_names': [k for k, _ in model.named_parameters()],
+    }, os.path.join(out, 'st_text_model.pt'))
+    print('text model golden: loss', loss.item(), logs)
+
+
 def golden_model_whisper(pasero, cfg, task, model, out):
     model.train()
     batch = synth.model_batch()
@@ -279,6 +319,14 @@ def golden_training_curve(pasero, cfg, task, model, out):
 def main():
     out = HERE
     pasero = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'text':         # only the text-encoder fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            make_task_and_model(pasero, tmp)                  # writes dict.txt / bpecodes
+            golden_model_text(pasero, tmp, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'adapters':     # only the adapter fixture
         tmp = tempfile.mkdtemp()
         try:
@@ -306,6 +354,7 @@ def main():
         cfg3, task3, model3 = make_whisper_model(pasero, tmp)
         golden_model_whisper(pasero, cfg3, task3, model3, out)
         golden_model_adapters(pasero, tmp, out)
+        golden_model_text(pasero, tmp, out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

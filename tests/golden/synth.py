@@ -237,6 +237,36 @@ def adapter_state_dict() -> dict:
     return sd
 
 
+# ---- text-input variant (BASELINE configs 1 / 5 family: `--task translation`, token-id encoder sharing its embedding
+# table with the decoder and the output projection; pasero/models/transformer.py:610-752)
+def text_param_shapes() -> dict:
+    shapes = {k: v for k, v in tiny_param_shapes().items() if not k.startswith('encoder.subsample')}
+    shapes['encoder.embed_tokens.weight'] = shapes['decoder.embed_tokens.weight']
+    return shapes
+
+
+def text_state_dict() -> dict:
+    sd = {k: v for k, v in tiny_state_dict().items() if not k.startswith('encoder.subsample')}
+    sd['encoder.embed_tokens.weight'] = sd['decoder.embed_tokens.weight']     # shared_embeddings (config.py:1064-1067)
+    return sd
+
+
+def text_batch() -> dict:
+    rng = np.random.RandomState(21)
+    src_lens, dec_lens = [17, 9, 12, 5], [9, 12, 5, 7]
+    B, Sm, Tm = len(src_lens), max(src_lens), max(dec_lens)
+    src = torch.full((B, Sm), PAD, dtype=torch.int64)
+    dec = torch.full((B, Tm), PAD, dtype=torch.int64)
+    pm = torch.zeros(B, Tm, dtype=torch.bool)
+    for b, (s_, t) in enumerate(zip(src_lens, dec_lens)):
+        src[b, :s_] = torch.from_numpy(np.concatenate([rng.randint(4, TINY['vocab_size'], s_ - 1), [EOS]]))
+        dec[b, :t] = torch.from_numpy(np.concatenate([[BOS], rng.randint(4, TINY['vocab_size'], t - 2), [EOS]]))
+        pm[b, 0] = True
+    return {'encoder_input': src, 'encoder_input_length': torch.tensor(src_lens), 'decoder_input': dec, 'prompt_mask': pm,
+            'prompt_length': torch.ones(B, dtype=torch.int64), 'indices': torch.arange(B),
+            'meta': {'source_lang': 'de', 'target_lang': 'en'}}
+
+
 def summarize_grad(g: torch.Tensor) -> dict:
     """Compact but discriminating digest of a gradient tensor (full tensor when small)."""
     g = g.detach().float()

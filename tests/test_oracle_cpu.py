@@ -192,6 +192,27 @@ def test_adapter_variant_matches_reference():
     assert all(sd[k].grad is None for k in sd if k not in gold['trainable'])
 
 
+def test_text_encoder_variant_matches_reference():
+    """Token-id encoder with shared embeddings (`--task translation`): BASELINE configs 1 / 5 family."""
+    gold = torch.load(os.path.join(GOLD, 'st_text_model.pt'), weights_only=False)
+    base = {k: v.clone() for k, v in synth.text_state_dict().items()}
+    shared = base['decoder.embed_tokens.weight'].requires_grad_(True)
+    sd = {k: (shared if k.endswith('embed_tokens.weight') else v.requires_grad_(True)) for k, v in base.items()}
+    batch = synth.text_batch()
+    layers = {}
+    loss, logs = om.forward(tiny_cfg(encoder_max_len=256), sd, batch['encoder_input'], batch['encoder_input_length'],
+                            batch['decoder_input'], layers)
+    assert abs(loss.item() - gold['loss']) < 1e-4 * abs(gold['loss'])
+    assert torch.equal(len_mask := om.len_to_mask(batch['encoder_input_length'], batch['encoder_input'].shape[1]), gold['encoder_mask'])
+    assert torch.allclose(layers['encoder_out'], gold['encoder_out'], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(layers['logits'], gold['logits'], atol=2e-4, rtol=1e-4)
+    for k, v in gold['layers'].items():
+        assert torch.allclose(layers[k], v, atol=2e-4, rtol=1e-4), k
+    loss.backward()
+    for name, want in gold['grads'].items():
+        _check_digest(name, sd[name].grad, want, rtol=2e-3, atol=2e-4)
+
+
 def test_train_step_curve_matches_reference():
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
     cfg = tiny_cfg()

@@ -249,6 +249,49 @@ def test_adapter_variant_matches_reference_and_trains_only_adapters():
     assert trainer.arena.numel < sum(p.numel() for p in model2.parameters()) // 4     # the arenas hold the adapters only
 
 
+def test_text_encoder_variant_matches_reference():
+    """Token-id encoder sharing its embedding table with the decoder and the output projection (`--task translation`,
+    BASELINE configs 1 / 5 family): activations, loss and gradients against the reference's golden vectors, and two
+    Trainer steps (the shared table receives three gradient contributions in the fp32 arena)."""
+    from pasero_b200 import build_model
+    from pasero_b200.task import Dictionary, SpeechTranslationTask
+    from pasero_b200.training import Trainer
+    gold = torch.load(os.path.join(GOLD, 'st_text_model.pt'), weights_only=False)
+    cfg = tiny_training_cfg(encoder_max_len=256, conv_kernel_sizes=None, input_dim=None, conv_input_dim=None, conv_channels=None)
+    task = SpeechTranslationTask.text(cfg, Dictionary(tokens=[f'tok{i}' for i in range(synth.TINY['vocab_size'] - 4)]))
+    model = build_model(cfg, task)
+    assert model.encoder.embed_tokens is model.decoder.embed_tokens
+    missing = model.load_state_dict(synth.text_state_dict(), strict=False)
+    assert not missing.unexpected_keys and all('_float_tensor' in k for k in missing.missing_keys), missing
+    model.to(BF16).cuda().train()
+    batch = synth.text_batch()
+    cb = to_cuda(batch)
+    names = list(gold['layers'].keys())
+    enc_out, enc_mask, enc_layers = model.encoder(cb['encoder_input'], cb['encoder_input_length'], return_layers=names)
+    logits, dec_layers = model.decoder(enc_out, enc_mask, cb['decoder_input'][:, :-1], return_layers=names,
+                                       encoder_lengths=model.encoder._last_lengths)
+    assert torch.equal(enc_mask.cpu(), gold['encoder_mask'])
+    assert rel_to_max(enc_out, gold['encoder_out']) < 3e-2
+    assert rel_to_max(logits, gold['logits']) < 3e-2
+    for k, want in gold['layers'].items():
+        assert rel_to_max({**enc_layers, **dec_layers}[k], want) < 3e-2, k
+    loss, logs = model(**cb)
+    assert abs(loss.item() - gold['loss']) / gold['loss'] < 1e-2
+    model.zero_grad()
+    loss.backward()
+    g = model.decoder.embed_tokens.weight.grad.float().cpu()
+    want = gold['grads']['encoder.embed_tokens.weight']
+    got_rows = g.reshape(g.shape[0], -1)
+    assert rel_to_max(got_rows.sum(1), want['row_sum']) < 0.1 and rel_to_max(got_rows[:4], want['rows']) < 0.3
+    model2 = build_model(cfg, task)
+    model2.load_state_dict(synth.text_state_dict(), strict=False)
+    trainer = Trainer(cfg, task, model2)
+    for step in range(2):
+        logs = trainer.train_step(iter([synth.text_batch()]))
+        assert abs(logs['loss'] - gold['logs']['loss']) / gold['logs']['loss'] < (1e-2 if step == 0 else 0.2)
+        assert logs['num_tokens'] == gold['logs']['num_tokens'] and logs['gnorm'] > 0
+
+
 def test_loss_curve_200_steps_matches_oracle():
     from pasero_b200.training import Trainer
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
