@@ -48,7 +48,7 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
     // targets may be a strided [B, T] view (decoder_input[:, 1:]); row = b * T + t
     const long long tgt = target[(row / T) * target_stride0 + (row % T)];
     bf16* x = logits + row * ld;
-    const int v8 = V >> 3;
+    const int v8 = (V + 7) >> 3;   // the last vector may hold padding columns (c >= V): masked below, written back as 0
     if (tgt == padding_idx) {
         if (write_grad)
             for (int i = threadIdx.x; i < v8; i += CE_THREADS) reinterpret_cast<uint4*>(x)[i] = make_uint4(0, 0, 0, 0);
@@ -62,8 +62,9 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_bf16x2(w[j]);
-            mx = fmaxf(mx, fmaxf(f.x, f.y));
-            sx += f.x + f.y;
+            const int c = i * 8 + 2 * j;
+            if (c < V) { mx = fmaxf(mx, f.x); sx += f.x; }
+            if (c + 1 < V) { mx = fmaxf(mx, f.y); sx += f.y; }
         }
     }
     mx = block_reduce_max(mx, red);
@@ -75,7 +76,9 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_bf16x2(w[j]);
-            se += __expf(f.x - mx) + __expf(f.y - mx);
+            const int c = i * 8 + 2 * j;
+            if (c < V) se += __expf(f.x - mx);
+            if (c + 1 < V) se += __expf(f.y - mx);
         }
     }
     se = block_reduce_sum(se, red);
@@ -104,6 +107,8 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
             float g0 = __expf(f.x - lse) - uni, g1 = __expf(f.y - lse) - uni;
             if (c == tgt) g0 -= (1.f - eps);
             if (c + 1 == tgt) g1 -= (1.f - eps);
+            if (c >= V) g0 = 0.f;
+            if (c + 1 >= V) g1 = 0.f;
             o[j] = pack_bf16x2(g0 * grad_scale, g1 * grad_scale);
         }
         reinterpret_cast<uint4*>(x)[i] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -118,7 +123,8 @@ extern "C" int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t 
                                    int64_t V, int64_t ld, int64_t padding_idx, float label_smoothing, float grad_scale,
                                    int32_t write_grad, double* stats, float* row_loss, void* stream_) {
     if (B * T == 0) return 0;
-    PB_CHECK(V % 8 == 0 && ld % 8 == 0, "cross-entropy: V (%lld) and ld must be multiples of 8", (long long)V);
+    PB_CHECK(ld % 8 == 0 && ld >= (V + 7) / 8 * 8, "cross-entropy: ld (%lld) must be a multiple of 8 covering V (%lld) rounded up to 8",
+             (long long)ld, (long long)V);
     PB_CHECK(stats != nullptr, "cross-entropy: stats buffer required");
     ls_ce_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
         (bf16*)logits, (const long long*)target, target_stride0, (int)T, (int)V, ld, padding_idx, label_smoothing,

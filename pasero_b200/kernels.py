@@ -323,11 +323,14 @@ def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 @_bracketed
 def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smoothing: float, stats: Tensor,
-                  write_grad: bool = True, grad_scale: float = 1.0, row_loss: Optional[Tensor] = None) -> None:
-    """logits [B*T, V] bf16 (overwritten with the gradient), target [B, T] int64 (may be a strided view)."""
+                  write_grad: bool = True, grad_scale: float = 1.0, row_loss: Optional[Tensor] = None,
+                  vocab: Optional[int] = None) -> None:
+    """logits [B*T, >= V] bf16 (columns [0, V) overwritten with the gradient), target [B, T] int64 (may be a strided
+    view). `vocab` = V when the logits carry padding columns (table rows rounded up to a multiple of 8)."""
     B, T = target.shape
     assert target.stride(1) == 1 and target.dtype == torch.int64
-    V = logits.shape[1]
+    V = vocab if vocab is not None else logits.shape[1]
+    assert V <= logits.shape[1]
     _count(1)
     check(_lib.load().pb200_ls_ce_fwd_bwd(logits.data_ptr(), target.data_ptr(), target.stride(0), B, T, V,
                                           logits.stride(0), padding_idx, label_smoothing, grad_scale, int(write_grad),

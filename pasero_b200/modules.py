@@ -322,12 +322,34 @@ class ConvolutionSubsampler(nn.Module):
 
 
 class Embedding(nn.Embedding):
-    """pasero/models/modules.py:890-947 (no partial freezing on this path)."""
+    """pasero/models/modules.py:890-947 (no partial freezing on this path). The table is stored with its row count
+    rounded up to a multiple of 8 (TMA / 16-byte rows of the tied projection's logits; e.g. Whisper's 51 865 -> 51 872):
+    the extra rows are zero, never receive a gradient (their logits are exactly 0 and the loss kernel only reads the real
+    `vocab_size` columns) and are trimmed from / padded into the state_dict, which keeps the reference's shapes."""
 
     def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: int):
-        super().__init__(num_embeddings, embedding_dim, padding_idx)
+        self.vocab_size = num_embeddings
+        super().__init__((num_embeddings + 7) // 8 * 8, embedding_dim, padding_idx)
         nn.init.normal_(self.weight, mean=0, std=embedding_dim ** -0.5)
         nn.init.constant_(self.weight[padding_idx], 0)
+        nn.init.constant_(self.weight[num_embeddings:], 0)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        w = self.weight if keep_vars else self.weight.detach()
+        destination[prefix + 'weight'] = w[:self.vocab_size]
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + 'weight'
+        if key in state_dict:
+            w = state_dict[key]
+            if w.shape[0] not in (self.vocab_size, self.weight.shape[0]) or w.shape[1] != self.weight.shape[1]:
+                error_msgs.append(f'size mismatch for {key}: {tuple(w.shape)} vs ({self.vocab_size}, {self.weight.shape[1]})')
+                return
+            with torch.no_grad():
+                self.weight[:w.shape[0]].copy_(w)
+                self.weight[w.shape[0]:].zero_()
+        elif strict:
+            missing_keys.append(key)
 
     def projection(self, input: Tensor) -> Tensor:
-        return ops.linear(input, self.weight, None)
+        return ops.linear(input, self.weight, None)[..., :self.vocab_size]

@@ -612,11 +612,13 @@ class ProjCEFn(torch.autograd.Function):
     unit_loss_grad = False   # Trainer sets this when the loss is the root of backward (grad_output == 1)
 
     @staticmethod
-    def forward(ctx, x, table, target, padding_idx, label_smoothing, stats):
+    def forward(ctx, x, table, target, padding_idx, label_smoothing, stats, vocab=None):
+        # vocab: number of real rows of `table` (the rest is zero padding up to a multiple of 8: their logits are exactly
+        # 0, the loss kernel neither reads nor overwrites them, so they act as zero gradients in backward)
         x = _c(x)
         logits = K.linear_fwd(x, table, None)
         before = stats[0].clone()
-        K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True)
+        K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True, vocab=vocab)
         ctx.save_for_backward(x, table, logits)
         ctx.table = table
         return (stats[0] - before).float()
@@ -630,7 +632,7 @@ class ProjCEFn(torch.autograd.Function):
         else:
             dtable = K.linear_wgrad(dlogits, x) * dloss.to(BF16)
             dx = dx * dloss.to(dx.dtype)
-        return dx, dtable, None, None, None, None
+        return dx, dtable, None, None, None, None, None
 
 
 # functional front-ends ------------------------------------------------------------------------------

@@ -320,6 +320,29 @@ class Trainer:
         self._optimizer_kernels()
         return self._finish_step()
 
+    @torch.no_grad()
+    def valid_step(self, batch: Optional[dict]) -> dict:
+        """Teacher-forced validation loss of one batch (pasero/training.py:519-547): eval mode (no dropout), no
+        gradients, logs summed over the data-parallel ranks. `batch=None` (a rank that ran out of validation batches,
+        datasets.py:551-555) contributes nothing but still takes part in the reduction."""
+        vals = torch.zeros(4, dtype=torch.float64, device=self.device)
+        if batch is not None:
+            batch = self.move_to_device(batch)
+            batch.setdefault('meta', {})
+            was_training = self.model.training
+            self.model.eval()
+            try:
+                _, logs = self.model(**batch)
+            finally:
+                self.model.train(was_training)
+            vals[0], vals[1], vals[2], vals[3] = logs['loss'], logs['nll_loss'], logs['num_tokens'], logs['num_lines']
+        if self.distributed:
+            dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        v = vals.tolist()
+        if batch is None and not self.distributed:
+            return {}
+        return {'loss': v[0], 'nll_loss': v[1], 'num_tokens': int(v[2]), 'num_lines': int(v[3])}
+
     def _finish_step(self) -> dict:
         self.scheduler.step()
         self.optimizer_steps += 1

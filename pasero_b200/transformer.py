@@ -361,7 +361,8 @@ class Transformer(nn.Module):
         eps = float(self.cfg.label_smoothing or 0.0)
         if fused:
             x = logits_or_features.reshape(B * T, -1)
-            loss = ops.ProjCEFn.apply(x, self.decoder.embed_tokens.weight, target, self.padding_idx, eps, stats)
+            emb = self.decoder.embed_tokens
+            loss = ops.ProjCEFn.apply(x, emb.weight, target, self.padding_idx, eps, stats, emb.vocab_size)
         else:
             loss = LogitsCEFn.apply(logits_or_features.reshape(B * T, -1), target, self.padding_idx, eps, stats)
         delta = stats[:3] - before

@@ -292,6 +292,51 @@ def test_text_encoder_variant_matches_reference():
         assert logs['num_tokens'] == gold['logs']['num_tokens'] and logs['gnorm'] > 0
 
 
+def test_vocabulary_not_multiple_of_8():
+    """Whisper's 51 865-entry vocabulary is not a multiple of 8: the table is stored zero-padded, the state_dict keeps the
+    reference's shape, loss and gradients equal those of the unpadded problem."""
+    from pasero_b200 import modules, ops
+    V, D, M = 203, 128, 24
+    emb = modules.Embedding(V, D, 1).to(BF16).cuda()
+    assert emb.weight.shape[0] == 208 and emb.state_dict()['weight'].shape[0] == V
+    assert torch.equal(emb.weight[V:], torch.zeros_like(emb.weight[V:]))
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(M, D, generator=g, device='cuda').to(BF16).requires_grad_(True)
+    target = torch.randint(4, V, (4, 6), generator=g, device='cuda')
+    target[0, -2:] = 1
+    stats = torch.zeros(8, dtype=torch.float64, device='cuda')
+    loss = ops.ProjCEFn.apply(x, emb.weight, target, 1, 0.1, stats, V)
+    ops.ProjCEFn.unit_loss_grad = False
+    loss.backward()
+    xr = x.detach().float().requires_grad_(True)
+    wr = emb.weight.detach().float()[:V].requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy((xr @ wr.T), target.reshape(-1), ignore_index=1, reduction='sum', label_smoothing=0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) / ref.item() < 1e-2
+    assert rel_to_max(x.grad, xr.grad) < 3e-2
+    assert rel_to_max(emb.weight.grad[:V], wr.grad) < 3e-2
+    assert torch.equal(emb.weight.grad[V:], torch.zeros_like(emb.weight.grad[V:]))
+    logits = emb.projection(x.detach())
+    assert logits.shape == (M, V)
+
+
+def test_valid_step_matches_oracle_and_leaves_training_state_alone():
+    from oracle import model as om
+    from pasero_b200.training import Trainer
+    cfg, task, model = build(seed=1, dropout=0.3)
+    trainer = Trainer(cfg, task, model)
+    batch = synth.model_batch()
+    before = trainer.arena.param.clone()
+    logs = trainer.valid_step(batch)
+    sd = {k: v.clone() for k, v in synth.tiny_state_dict().items()}
+    _, ologs = om.forward(tiny_cfg(), sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'])
+    assert logs['num_tokens'] == ologs['num_tokens'] and logs['num_lines'] == ologs['num_lines']
+    assert abs(logs['loss'] - ologs['loss']) / ologs['loss'] < 1e-2          # dropout 0.3 would show up here if active
+    assert abs(logs['nll_loss'] - ologs['nll_loss']) / ologs['nll_loss'] < 1e-2
+    assert torch.equal(trainer.arena.param, before) and trainer.model.training and trainer.steps == 0
+    assert trainer.valid_step(None) == {}
+
+
 def test_loss_curve_200_steps_matches_oracle():
     from pasero_b200.training import Trainer
     gold = torch.load(os.path.join(GOLD, 'st_tiny_train.pt'), weights_only=False)
