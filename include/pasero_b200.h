@@ -172,6 +172,8 @@ int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t C, void* di
  * forward writes gelu(in [B, T, C]) into rows [front_pad, front_pad + T) of a zero-padded [B, Tp, C] layout */
 int pb200_gelu_fwd(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
 int pb200_gelu_bwd(const void* dy, const void* pre, int64_t n, void* dx, void* stream);
+/* backward of a stand-alone ReLU (the encoder's in_linear, pasero/models/transformer.py:647-651): dx = dy where h > 0 */
+int pb200_relu_bwd(const void* dy, const void* h, int64_t n, void* dx, void* stream);
 int pb200_col2im(const void* dcol, int32_t B, int32_t Tin, int32_t Tout, int32_t C, int32_t KW, int32_t stride,
                  void* dx, void* stream);
 int pb200_pad_rows(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);

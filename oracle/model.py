@@ -177,7 +177,10 @@ def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tenso
         kernel_sizes = strides = ()
     else:
         kernel_sizes, strides = cfg.conv_kernel_sizes, cfg.conv_strides
-        x = encoder_input.transpose(1, 2)
+        x = encoder_input
+        if 'encoder.in_linear.0.weight' in sd:      # Linear + ReLU in front of the subsampler, transformer.py:647-651, 735-736
+            x = F.relu(F.linear(x, sd['encoder.in_linear.0.weight'], sd['encoder.in_linear.0.bias']))
+        x = x.transpose(1, 2)
         for i, (k, s) in enumerate(zip(kernel_sizes, strides)):
             x = F.conv1d(x, sd[f'encoder.subsample.conv_layers.{i}.weight'], sd[f'encoder.subsample.conv_layers.{i}.bias'],
                          stride=s, padding=k // 2)

@@ -73,6 +73,7 @@ PROTOTYPES = {
     'pb200_glu_bwd': (c_int32, [_P, _P, c_int64, c_int32, _P, _P]),
     'pb200_gelu_fwd': (c_int32, [_P, c_int32, c_int32, c_int32, _P, c_int32, c_int32, _P]),
     'pb200_gelu_bwd': (c_int32, [_P, _P, c_int64, _P, _P]),
+    'pb200_relu_bwd': (c_int32, [_P, _P, c_int64, _P, _P]),
     'pb200_col2im': (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'pb200_pad_rows': (c_int32, [_P, c_int32, c_int32, c_int32, _P, c_int32, c_int32, _P]),
     'pb200_f32_to_bf16': (c_int32, [_P, c_int64, _P, c_int32, _P]),

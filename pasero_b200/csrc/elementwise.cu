@@ -196,6 +196,23 @@ __global__ void gelu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C
     }
 }
 
+// dx = dy where the ReLU output h > 0, else 0 (backward of a stand-alone ReLU, e.g. the encoder's in_linear)
+__global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h, long long n8, bf16* __restrict__ dx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy) + i);
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h) + i);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, hw[4] = {hv.x, hv.y, hv.z, hv.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // bf16 > 0  <=>  sign bit clear and not +0
+            const uint32_t lo = ((int)(hw[j] << 16) > 0) ? 0x0000ffffu : 0u;
+            const uint32_t hi = ((int)(hw[j] & 0xffff0000u) > 0) ? 0xffff0000u : 0u;
+            ow[j] = dw[j] & (lo | hi);
+        }
+        reinterpret_cast<uint4*>(dx)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
 // GELU (erf) elementwise fwd/bwd for the Whisper-style conv front end and FFN backward
 __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, long long n8,
                                 bf16* __restrict__ dx) {
@@ -331,6 +348,14 @@ extern "C" int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t 
     PB_CHECK(C % 8 == 0, "glu: C must be a multiple of 8");
     glu_bwd_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)in, M, C,
                                                                           (bf16*)din);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pb200_relu_bwd(const void* dy, const void* h, int64_t n, void* dx, void* stream_) {
+    if (n == 0) return 0;
+    PB_CHECK(n % 8 == 0, "relu_bwd: n must be a multiple of 8");
+    relu_bwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)h, n / 8, (bf16*)dx);
     PB_LAUNCH_CHECK();
     return 0;
 }

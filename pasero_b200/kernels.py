@@ -296,6 +296,16 @@ def gelu_bwd(dy: Tensor, pre: Tensor) -> Tensor:
 
 
 @_bracketed
+def relu_bwd(dy: Tensor, h: Tensor) -> Tensor:
+    """dx = dy * (h > 0) for contiguous bf16 tensors of the same shape (h = the ReLU's output)."""
+    assert dy.is_contiguous() and h.is_contiguous() and dy.numel() == h.numel()
+    dx = torch.empty_like(dy)
+    _count(1)
+    check(_lib.load().pb200_relu_bwd(dy.data_ptr(), h.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
+    return dx
+
+
+@_bracketed
 def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
     dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
     _count(1)

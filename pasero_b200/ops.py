@@ -147,6 +147,33 @@ def _fc1_relu(x: Tensor, w1: Tensor, b1: Optional[Tensor]):
     return K.linear_fwd(x, w1, b1, act=1, relu_bits_out=bits), bits
 
 
+class LinearReluFn(torch.autograd.Function):
+    """h = relu(x @ W^T + b) with the activation fused in the GEMM epilogue (the encoder's `in_linear`,
+    pasero/models/transformer.py:647-651)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        h = K.linear_fwd(x, weight, bias, act=1)
+        ctx.save_for_backward(x, weight, h)
+        ctx.params = (weight, bias)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, weight, h = ctx.saved_tensors
+        w_param, b_param = ctx.params
+        dpre = K.relu_bwd(_c(dh), h)
+        dx = K.linear_dgrad(dpre, weight) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dpre, x, w_param) if ctx.needs_input_grad[1] else None
+        db = None
+        if b_param is not None and ctx.needs_input_grad[2]:
+            out, acc = _sink(b_param)
+            db = _ret(K.colsum(dpre, out=out, accumulate=acc), out)
+        _ready(w_param, b_param)
+        return dx, dw, db
+
+
 class FFNFn(torch.autograd.Function):
     """y = relu(x W1^T + b1) W2^T + b2 (pasero/models/transformer.py:999-1019); ReLU fused in the fc1 epilogue, its
     backward mask fused in the fc2 dgrad epilogue."""

@@ -179,7 +179,7 @@ class TransformerEncoder(nn.Module):
         # `shared_embeddings` (transformer.py:150-176, 624-640)
         if num_embeddings > 0:
             self.embed_tokens = embed if embed is not None else modules.Embedding(num_embeddings, cfg.embed_dim, self.padding_idx)
-            self.subsample = None
+            self.subsample = self.in_linear = None
             encoder_max_len = cfg.encoder_max_len
         else:
             self.embed_tokens = None
@@ -187,8 +187,9 @@ class TransformerEncoder(nn.Module):
             if not cfg.conv_kernel_sizes:
                 raise NotImplementedError('feature inputs expect a conv subsampler (conv_kernel_sizes)')
             conv_input_dim = cfg.conv_input_dim or input_dim
-            if conv_input_dim != input_dim:
-                raise NotImplementedError('in_linear (input_dim != conv_input_dim) is a "next" row of SURVEY.md §8f')
+            # in_linear (transformer.py:647-651): Linear(input_dim -> conv_input_dim) + ReLU in front of the subsampler,
+            # e.g. 768-d wav2vec features -> 80 in the IWSLT2023 recipe; state_dict keys in_linear.0.{weight,bias}
+            self.in_linear = nn.ModuleList([modules.Linear(input_dim, conv_input_dim)]) if conv_input_dim != input_dim else None
             self.subsample = modules.ConvolutionSubsampler(conv_input_dim, cfg.conv_channels or conv_input_dim, cfg.embed_dim,
                                                            cfg.conv_kernel_sizes, cfg.conv_strides, cfg.conv_activation)
             encoder_max_len = int(self.subsample.get_new_length(torch.tensor(cfg.encoder_max_len)))
@@ -223,6 +224,11 @@ class TransformerEncoder(nn.Module):
             x = encoder_input
             if x.dtype != BF16:
                 x = x.to(BF16)
+            if self.in_linear is not None:
+                if padded_layout is not None:
+                    raise NotImplementedError('the fused fbank layout feeds the subsampler directly (no in_linear)')
+                lin = self.in_linear[0]
+                x = ops.LinearReluFn.apply(x.reshape(-1, x.shape[-1]), lin.weight, lin.bias).view(B, x.shape[1], -1)
             if padded_layout is not None:
                 x, length = self.subsample.forward_padded(x, padded_layout[0], encoder_input_length)
             else:

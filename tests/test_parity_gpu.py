@@ -320,6 +320,38 @@ def test_vocabulary_not_multiple_of_8():
     assert logits.shape == (M, V)
 
 
+def test_in_linear_matches_oracle():
+    """`input_dim != conv_input_dim`: Linear + ReLU in front of the conv subsampler (pasero/models/transformer.py:647-651;
+    768 -> 80 in the IWSLT2023 recipe). Pinned by the oracle restatement only (no reference fixture for this piece)."""
+    from oracle import model as om
+    from pasero_b200 import build_model
+    cfg = tiny_training_cfg(input_dim=96)
+    task = tiny_task(cfg)
+    model = build_model(cfg, task)
+    rng = np.random.RandomState(5)
+    sd = dict(synth.tiny_state_dict())
+    sd['encoder.in_linear.0.weight'] = torch.from_numpy((rng.randn(80, 96) * 96 ** -0.5).astype(np.float32)).to(BF16).float()
+    sd['encoder.in_linear.0.bias'] = torch.from_numpy((0.02 * rng.randn(80)).astype(np.float32)).to(BF16).float()
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all('_float_tensor' in k for k in missing.missing_keys), missing
+    model.to(BF16).cuda().train()
+    batch = synth.model_batch()
+    batch['encoder_input'] = torch.from_numpy(rng.randn(*batch['encoder_input'].shape[:2], 96).astype(np.float32)).to(BF16).float()
+    for b, n in enumerate(batch['encoder_input_length'].tolist()):
+        batch['encoder_input'][b, n:] = 0
+    loss, logs = model(**to_cuda(batch))
+    model.zero_grad()
+    loss.backward()
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    oloss, ologs = om.forward(tiny_cfg(), osd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'])
+    oloss.backward()
+    assert abs(loss.item() - oloss.item()) / oloss.item() < 1e-2
+    lin = model.encoder.in_linear[0]
+    for got, want in ((lin.weight.grad, osd['encoder.in_linear.0.weight'].grad), (lin.bias.grad, osd['encoder.in_linear.0.bias'].grad)):
+        cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
+        assert cos > 0.98 and rel_to_max(got, want) < 0.3, (cos, rel_to_max(got, want))
+
+
 def test_valid_step_matches_oracle_and_leaves_training_state_alone():
     from oracle import model as om
     from pasero_b200.training import Trainer
