@@ -15,6 +15,8 @@
 #include "../../include/pasero_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
 
@@ -196,6 +198,187 @@ fbank_kernel(const float* __restrict__ pcm, const long long* __restrict__ sample
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: register-resident FFT. 16 lanes per frame (two frames per warp), 16 complex points per lane.
+//   256-point complex FFT as 16 x 16 (Cooley-Tukey): lane n1 holds z[n1 + 16 n2] and runs a 16-point DFT over n2 in
+//   registers, multiplies by W256^(n1 k2), the 16 x 16 values are transposed between the lanes through a padded
+//   shared-memory tile (conflict free), lane k2 runs the second 16-point DFT over n1 and holds Z[16 k1 + k2].
+//   Shared memory traffic per frame drops from ~250 to ~110 accesses per lane and the strided Stockham stores (8-way
+//   bank conflicts in the first two radix-4 passes of v1) disappear.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// forward 4-point DFT (W4 = -i), in place
+__device__ __forceinline__ void dft4(float2& u0, float2& u1, float2& u2, float2& u3) {
+    const float2 a = cadd(u0, u2), b = csub(u0, u2), c = cadd(u1, u3), d = mul_mi(csub(u1, u3));
+    u0 = cadd(a, c); u1 = cadd(b, d); u2 = csub(a, c); u3 = csub(b, d);
+}
+
+// forward 16-point DFT in registers, natural order in and out: n = 4 n_a + n_b, k = k_a + 4 k_b
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508978f, R = 0.70710678118654752f;
+    float2 t[4][4];   // t[n_b][k_a]
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        float2 u0 = v[nb], u1 = v[4 + nb], u2 = v[8 + nb], u3 = v[12 + nb];
+        dft4(u0, u1, u2, u3);
+        t[nb][0] = u0; t[nb][1] = u1; t[nb][2] = u2; t[nb][3] = u3;
+    }
+    // twiddles W16^(n_b k_a) = exp(-2 pi i n_b k_a / 16)
+    t[1][1] = cmul(t[1][1], make_float2(C1, -S1));
+    t[1][2] = cmul(t[1][2], make_float2(R, -R));
+    t[1][3] = cmul(t[1][3], make_float2(S1, -C1));
+    t[2][1] = cmul(t[2][1], make_float2(R, -R));
+    t[2][2] = mul_mi(t[2][2]);
+    t[2][3] = cmul(t[2][3], make_float2(-R, -R));
+    t[3][1] = cmul(t[3][1], make_float2(S1, -C1));
+    t[3][2] = cmul(t[3][2], make_float2(-R, -R));
+    t[3][3] = cmul(t[3][3], make_float2(-C1, S1));
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        float2 u0 = t[0][ka], u1 = t[1][ka], u2 = t[2][ka], u3 = t[3][ka];
+        dft4(u0, u1, u2, u3);
+        v[ka] = u0; v[ka + 4] = u1; v[ka + 8] = u2; v[ka + 12] = u3;
+    }
+}
+
+static constexpr int FB2_TILE = 16 * 17;   // float2 per half-warp: 16 x 16 transpose tile padded to 17, reused for Z[256]
+
+struct FbankSmem2 {
+    alignas(16) float samples[SAMPLES_PER_CTA + 8];
+    alignas(16) float out[FR_PER_CTA][NMEL];
+    alignas(16) float2 tile[FB_WARPS][2][FB2_TILE];
+    alignas(16) float power[FB_WARPS][2][NC + 8];
+    alignas(16) float window[WIN];
+    alignas(16) float2 w256[NC];
+    alignas(16) float2 w512[NC + 1];
+    alignas(16) float mel_w[MAX_MEL_TAPS];
+    int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
+};
+
+__global__ void __launch_bounds__(FB_THREADS)
+fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
+                const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
+                float pcm_scale) {
+    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
+    FbankSmem2& s = *reinterpret_cast<FbankSmem2*>(fb_smem_raw);
+    const int b = blockIdx.y;
+    const long long s0 = sample_off[b];
+    const long long f_begin = frame_off[b];
+    const int nframes = (int)(frame_off[b + 1] - f_begin);
+    const int f0 = blockIdx.x * FR_PER_CTA;
+    if (f0 >= nframes) return;
+    const int nf = min(FR_PER_CTA, nframes - f0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hl = lane & 15, half = lane >> 4;
+
+    const FbankTables& T = g_fbank_tables;
+    for (int i = tid; i < WIN; i += FB_THREADS) s.window[i] = T.window[i];
+    for (int i = tid; i < NC; i += FB_THREADS) s.w256[i] = T.w256[i];
+    for (int i = tid; i <= NC; i += FB_THREADS) s.w512[i] = T.w512[i];
+    for (int i = tid; i < MAX_MEL_TAPS; i += FB_THREADS) s.mel_w[i] = T.mel_w[i];
+    for (int i = tid; i < NMEL; i += FB_THREADS) {
+        s.mel_start[i] = T.mel_start[i]; s.mel_len[i] = T.mel_len[i]; s.mel_off[i] = T.mel_off[i];
+    }
+    const int nsamp = (nf - 1) * SHIFT + WIN;
+    const float* src = pcm + s0 + (long long)f0 * SHIFT;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = nsamp >> 2;
+        for (int i = tid; i < n4; i += FB_THREADS) reinterpret_cast<float4*>(s.samples)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        for (int i = (n4 << 2) + tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    float2* tile = s.tile[warp][half];
+    float* pw = s.power[warp][half];
+    // two frames per warp iteration; frames beyond nf are computed on frame nf - 1 and not stored (keeps the warp converged)
+    for (int fr0 = warp * 2; fr0 < nf; fr0 += FB_WARPS * 2) {
+        const int fr = fr0 + half;
+        const bool live = fr < nf;
+        const float* x = s.samples + (live ? fr : nf - 1) * SHIFT;
+        // DC offset over the 400 samples of the frame
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < WIN / 16; ++i) sum += x[hl + 16 * i] * pcm_scale;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / WIN);
+        // z[n] = y[2n] + i y[2n+1], n = hl + 16 n2 (pre-emphasis 0.97, Povey window, zero-padded beyond 200)
+        float2 v[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const int n = hl + 16 * n2;
+            float2 z = make_float2(0.f, 0.f);
+            if (n < WIN / 2) {
+                const int j = 2 * n;
+                const float xm1 = x[j > 0 ? j - 1 : 0] * pcm_scale - mean;
+                const float x0 = x[j] * pcm_scale - mean;
+                const float x1 = x[j + 1] * pcm_scale - mean;
+                z.x = (x0 - 0.97f * xm1) * s.window[j];
+                z.y = (x1 - 0.97f * x0) * s.window[j + 1];
+            }
+            v[n2] = z;
+        }
+        dft16(v);                                   // A[n1 = hl][k2]
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], s.w256[(hl * k2) & (NC - 1)]);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) tile[k2 * 17 + hl] = v[k2];   // transpose through the padded tile
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = tile[hl * 17 + n1];   // lane k2 = hl: A'[n1][k2]
+        __syncwarp();
+        dft16(v);                                   // Z[16 k1 + hl] in v[k1]
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) tile[16 * k1 + hl] = v[k1];
+        __syncwarp();
+        // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
+#pragma unroll 1
+        for (int k = hl; k <= NC; k += 16) {
+            const float2 zk = tile[k & (NC - 1)];
+            const float2 zc = tile[(NC - k) & (NC - 1)];
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            const float2 wo = cmul(s.w512[k], o);
+            const float re = e.x + wo.x, im = e.y + wo.y;
+            pw[k] = re * re + im * im;
+        }
+        __syncwarp();
+        // sparse mel projection + log: 80 bins over the 16 lanes
+        for (int m = hl; m < NMEL; m += 16) {
+            const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
+            float acc = 0.f;
+            for (int i = 0; i < ln; ++i) acc = fmaf(pw[st + i], s.mel_w[of + i], acc);
+            if (live) s.out[fr][m] = logf(fmaxf(acc, 1.1920928955078125e-07f));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    float* dst = feats + (f_begin + f0) * NMEL;
+    const float* so = &s.out[0][0];
+    const int total = nf * NMEL;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int i = tid; i < (total >> 2); i += FB_THREADS)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(so)[i];
+    } else {
+        for (int i = tid; i < total; i += FB_THREADS) dst[i] = so[i];
+    }
+    if (stats != nullptr && tid < NMEL) {
+        double sm = 0.0, sq = 0.0;
+        for (int fr = 0; fr < nf; ++fr) {
+            const double val = (double)s.out[fr][tid];
+            sm += val; sq += val * val;
+        }
+        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], sm);
+        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], sq);
+    }
+}
+
 // CMVN: x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) with fp64 statistics, in place; optionally
 // also writes bf16 features into a zero-padded [B, padded_frames, 80] buffer (front_pad zero frames
 // before each utterance, zeros after its last frame) for the conv subsampler.
@@ -290,6 +473,7 @@ static int upload_fbank_tables() {
     for (int i = off; i < MAX_MEL_TAPS; ++i) t.mel_w[i] = 0.f;
     PB_CUDA(cudaMemcpyToSymbol(g_fbank_tables, &t, sizeof(FbankTables)));
     PB_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem2)));
     if (dev < 64) done_for_device[dev] = 1;
     return 0;
 }
@@ -322,9 +506,15 @@ extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets,
     PB_CUDA(cudaMemsetAsync(stats, 0, pb200_fbank_workspace_bytes(batch), stream));
     if (max_frames > 0) {
         dim3 grid((max_frames + FR_PER_CTA - 1) / FR_PER_CTA, batch);
-        fbank_kernel<<<grid, FB_THREADS, sizeof(FbankSmem), stream>>>(
-            pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
-            feats, stats, pcm_scale);
+        static const bool use_v1 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v1"); }();
+        if (use_v1)
+            fbank_kernel<<<grid, FB_THREADS, sizeof(FbankSmem), stream>>>(
+                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
+                feats, stats, pcm_scale);
+        else
+            fbank_kernel_v2<<<grid, FB_THREADS, sizeof(FbankSmem2), stream>>>(
+                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
+                feats, stats, pcm_scale);
         PB_LAUNCH_CHECK();
     }
     if (cmvn || feats_bf16_padded) {

@@ -308,8 +308,8 @@ class ConvolutionSubsampler(nn.Module):
                 rows, front = self.padded_rows(t_out, i + 1)
             else:
                 rows, front = t_out, 0
-            x = ops.ConvGLUFn.apply(x, self.weights[i], self.biases[i], B, t, self.channels[i][0], k, s, rows, front, i > 0,
-                                    self.activation)
+            x = ops.ConvGLUFn.apply(x, self.weights[i], self.biases[i], B, t, self.channels[i][0], k, s, rows, front,
+                                    i > 0 or x.requires_grad, self.activation)
             t = t_out
         return x, self.get_new_length(length)
 
@@ -317,7 +317,7 @@ class ConvolutionSubsampler(nn.Module):
         """x (B, S, D) bf16 -> (B, S', D'), new lengths"""
         B, T, C = x.shape
         rows, front = self.padded_rows(T, 0)
-        xp = K.pad_rows(x.contiguous(), B, T, C, rows, front)
+        xp = ops.PadRowsFn.apply(x, rows, front) if x.requires_grad else K.pad_rows(x.contiguous(), B, T, C, rows, front)
         return self.forward_padded(xp, T, length)
 
 

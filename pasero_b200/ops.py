@@ -566,6 +566,22 @@ class FFNGeluFn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2
 
 
+class PadRowsFn(torch.autograd.Function):
+    """[B, T, C] -> zero-padded [B, Tp, C] with the data at rows [front, front + T) (the conv subsampler's input layout);
+    differentiable so that an `in_linear` in front of the subsampler receives its gradient."""
+
+    @staticmethod
+    def forward(ctx, x, Tp, front):
+        B, T, C = x.shape
+        ctx.dims = (T, front)
+        return K.pad_rows(_c(x), B, T, C, Tp, front)
+
+    @staticmethod
+    def backward(ctx, dout):
+        T, front = ctx.dims
+        return _c(dout[:, front:front + T]), None, None
+
+
 class ConvGLUFn(torch.autograd.Function):
     """One layer of the conv subsampler: Conv1d(kernel KW, stride, padding KW//2) + GLU over channels
     (pasero/models/modules.py:829-834) as a TMA-described implicit GEMM over the zero-padded [B, Tp, C] input
