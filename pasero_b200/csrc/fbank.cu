@@ -337,8 +337,7 @@ fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sam
         for (int k1 = 0; k1 < 16; ++k1) tile[16 * k1 + hl] = v[k1];
         __syncwarp();
         // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
-#pragma unroll 1
-        for (int k = hl; k <= NC; k += 16) {
+        auto untangle = [&](int k) {
             const float2 zk = tile[k & (NC - 1)];
             const float2 zc = tile[(NC - k) & (NC - 1)];
             const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
@@ -346,13 +345,24 @@ fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sam
             const float2 wo = cmul(s.w512[k], o);
             const float re = e.x + wo.x, im = e.y + wo.y;
             pw[k] = re * re + im * im;
-        }
+        };
+#pragma unroll
+        for (int i = 0; i < 16; ++i) untangle(hl + 16 * i);    // independent iterations: loads overlap
+        if (hl == 0) untangle(NC);
         __syncwarp();
         // sparse mel projection + log: 80 bins over the 16 lanes
         for (int m = hl; m < NMEL; m += 16) {
             const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
-            float acc = 0.f;
-            for (int i = 0; i < ln; ++i) acc = fmaf(pw[st + i], s.mel_w[of + i], acc);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four partial sums: the tap loop is a latency chain otherwise
+            int i = 0;
+            for (; i + 4 <= ln; i += 4) {
+                a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
+                a1 = fmaf(pw[st + i + 1], s.mel_w[of + i + 1], a1);
+                a2 = fmaf(pw[st + i + 2], s.mel_w[of + i + 2], a2);
+                a3 = fmaf(pw[st + i + 3], s.mel_w[of + i + 3], a3);
+            }
+            for (; i < ln; ++i) a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
+            const float acc = (a0 + a1) + (a2 + a3);
             if (live) s.out[fr][m] = logf(fmaxf(acc, 1.1920928955078125e-07f));
         }
         __syncwarp();
