@@ -93,6 +93,10 @@ typedef struct pb200_gemm_params {
     int32_t cluster_m;        /* 0 = choose automatically; 1, 2 or 4 CTAs per cluster sharing the B tile by TMA multicast */
     void* workspace;          /* fp32 split-K partials; may be NULL when split_k == 1 */
     size_t workspace_bytes;
+    float* a_rowsum;          /* fp32 [m] or NULL: a_rowsum[i] += sum_k op(A)[i][k], computed by the tensor core next to the
+                                 product. For weight gradients (op(A) = dY^T) this is the bias gradient, so dY is not read
+                                 again by a column-sum kernel. Needs a_mn_major, out_fp32 + accumulate and no other epilogue
+                                 option; additions are atomic (order not fixed, like the split-K reduce-adds) */
 } pb200_gemm_params;
 
 size_t pb200_gemm_workspace_bytes(int64_t m, int64_t n, int64_t batch, int32_t max_splits);
@@ -148,6 +152,9 @@ int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void*
 size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);
 int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out, int32_t accumulate, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* the same sums into an fp32 [N] vector (fp32 main gradients of biases, see pb200_grad32_flush) */
+int pb200_colsum_f32(const void* x, int64_t M, int64_t N, int64_t ld, float* out, int32_t accumulate, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding epilogue: out[r] = dropout(bf16(bf16(src_row * scale) + pos[r % L])), src_row = src[ids[r]]

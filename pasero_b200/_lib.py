@@ -27,6 +27,7 @@ class GemmParams(Structure):
         ('act', c_int32), ('out_fp32', c_int32), ('accumulate', c_int32), ('alpha', c_float),
         ('split_k', c_int32), ('tile_n', c_int32), ('cluster_m', c_int32),
         ('workspace', c_void_p), ('workspace_bytes', c_size_t),
+        ('a_rowsum', c_void_p),
     ]
 
 
@@ -65,6 +66,7 @@ PROTOTYPES = {
                                            _P, _P, _P, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     'pb200_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'pb200_colsum_bf16': (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_size_t, _P]),
+    'pb200_colsum_f32': (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_size_t, _P]),
     'pb200_embed_fwd': (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,
                                   _P, c_int64, _P, _P]),
     'pb200_embed_bwd': (c_int32, [_P, _P, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64, _P, c_int64, c_int64,

@@ -47,6 +47,7 @@ struct GemmDev {
     int tma_store;       // bf16 output staged through shared memory and written with TMA
     float alpha;
     float* partial;      // split-K partials [split][Z][M][N] fp32
+    float* a_rowsum;     // EPI 7: fp32 [M], += sum_k op(A)[m][k] (bias gradient folded into the weight-gradient GEMM)
 };
 
 // PAIR: the CTA pair of a 2-CTA cluster works as one tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128
@@ -71,6 +72,18 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// EPI 7 = EPI 4 + row sums of op(A) (the bias gradient of the Linear whose weight gradient this GEMM computes): one more
+// N = 16 MMA per k-step against an all-ones B operand into 16 extra TMEM columns (the tiles of one A row block take turns
+// on it), so dY is not read a second time by a column-sum kernel. The extra columns leave room for a single accumulator only.
+static constexpr int ONES_BYTES = 1152;   // 16 all-ones rows read as 8-row groups 16 B apart (any layout of ones is ones)
+template <int BN, int EPI, bool PAIR>
+struct GemmEpiCfg {
+    static constexpr int NACC = EPI == 7 ? 1 : GemmCfg<BN, PAIR>::NACC;
+    static constexpr int TMEM_COLS = EPI == 7 ? (BN >= 256 ? 512 : 256) : GemmCfg<BN, PAIR>::TMEM_COLS;
+    static constexpr int ROWSUM_COL = BN;   // EPI 7: first of the 16 row-sum columns
+    static constexpr int SMEM_BYTES = GemmCfg<BN, PAIR>::SMEM_BYTES + (EPI == 7 ? ONES_BYTES : 0);
+};
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // EPI selects the epilogue at compile time (the generic one carries ~2500 SASS instructions per 64 columns when every
@@ -90,7 +103,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmc, const GemmDev p) {
     constexpr bool PAIR = (CL == 2);
     using Cfg = GemmCfg<BN, PAIR>;
+    using ECfg = GemmEpiCfg<BN, EPI, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int NACC = ECfg::NACC;
+    static_assert(EPI != 7 || (A_MN && BN <= 256 && CL <= 2), "row sums: weight-gradient form only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
@@ -99,6 +115,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    [[maybe_unused]] uint32_t* ones = reinterpret_cast<uint32_t*>(epi_smem + Cfg::EPI_BYTES + 256);   // EPI 7
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5;
@@ -127,8 +144,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        if (PAIR) { ptx::tmem_alloc_2sm(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish_2sm(); }
-        else { ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
+        if (PAIR) { ptx::tmem_alloc_2sm(tmem_ptr, ECfg::TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_ptr, ECfg::TMEM_COLS); ptx::tmem_relinquish(); }
+    }
+    if (EPI == 7 && warp == 3) {   // bf16 1.0 everywhere; read by the tensor core (async proxy)
+        for (int i = lane; i < ONES_BYTES / 4; i += 32) ones[i] = 0x3f803f80u;
+        ptx::fence_proxy_async();
     }
     ptx::tc_fence_before();
     if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before any remote arrive
@@ -224,6 +245,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         // ===================== MMA issuer (one thread; the leader CTA's in PAIR mode) =====================
         if (lane == 0 && (!PAIR || cta_rank == 0)) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, Cfg::MMA_N, A_MN, B_MN);
+            [[maybe_unused]] constexpr uint32_t idesc_rs = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, 16, A_MN, false);
+            [[maybe_unused]] const uint64_t ones_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(ones), 16, 16);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -231,8 +254,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                 const int split = tile % p.splits;
                 const int kb_begin = split * p.kb_per_split;
                 const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-                const int acc = Cfg::NACC == 2 ? (local & 1) : 0;
-                const uint32_t acc_phase = (Cfg::NACC == 2 ? (local >> 1) : local) & 1;
+                const int acc = NACC == 2 ? (local & 1) : 0;
+                const uint32_t acc_phase = (NACC == 2 ? (local >> 1) : local) & 1;
+                // EPI 7: the n_blks tiles that share this tile's A operand take turns on the row-sum MMA (k-step s of the
+                // tile belongs to n-block s % n_blks), so the extra tensor work is spread evenly over the CTAs
+                [[maybe_unused]] int rs_wait = EPI == 7 ? (tile / p.splits) % p.n_blks : 0;
+                [[maybe_unused]] uint32_t rs_acc = 0;
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;   // (acc == 0 when there is a single accumulator)
@@ -257,6 +284,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                                                    (kb > kb_begin || k > 0) ? 1u : 0u);
                         } else {
                             ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        }
+                        if constexpr (EPI == 7) {
+                            if (rs_wait == 0) {
+                                if (PAIR) ptx::umma_bf16_2sm(tmem_base + ECfg::ROWSUM_COL, adesc, ones_desc, idesc_rs, rs_acc);
+                                else ptx::umma_bf16(tmem_base + ECfg::ROWSUM_COL, adesc, ones_desc, idesc_rs, rs_acc);
+                                rs_acc = 1u;
+                                rs_wait = p.n_blks;
+                            }
+                            --rs_wait;
                         }
                     }
                     // frees the smem slot (in every CTA of the cluster: peers multicast into it / the pair's MMA read it)
@@ -292,8 +328,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             const int n0 = n_blk * BN;
             const int row = m_blk * BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
-            const int acc = Cfg::NACC == 2 ? (local & 1) : 0;
-            const uint32_t acc_phase = (Cfg::NACC == 2 ? (local >> 1) : local) & 1;
+            const int acc = NACC == 2 ? (local & 1) : 0;
+            const uint32_t acc_phase = (NACC == 2 ? (local >> 1) : local) & 1;
             const int kb_begin = split * p.kb_per_split;
             const bool empty_range = kb_begin >= p.total_kb;
 
@@ -327,7 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 
-            if constexpr (EPI == 4) {
+            if constexpr (EPI == 4 || EPI == 7) {
                 // split-K partial: 32-column fp32 slabs -> swizzled smem -> TMA reduce-add into the fp32 accumulator
 #pragma unroll 1
                 for (int c32 = 0; c32 < BN / 32; ++c32) {
@@ -348,6 +384,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
                     if (lane == 0) {
                         ptx::tma_reduce_add_3d(&tmc, buf, col0, m_blk * BM + ew * 32, z);
                         ptx::tma_store_commit();
+                    }
+                }
+                if constexpr (EPI == 7) {
+                    if ((min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin) * (BK / 16) > n_blk) {   // this tile had a turn (warp-uniform);
+                        // the lane's partial row sum sits in every one of the 16 extra columns
+                        uint32_t v[32];
+                        __syncwarp();
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + ECfg::ROWSUM_COL, v);
+                        ptx::tmem_ld_wait();
+                        if (row_ok && !empty_range) atomicAdd(p.a_rowsum + row, __uint_as_float(v[0]));
                     }
                 }
                 ptx::tc_fence_before();
@@ -560,7 +606,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     if (CL > 1) ptx::cluster_sync_all(); else __syncthreads();   // no CTA leaves while peers may still signal its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, ECfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, ECfg::TMEM_COLS);
     }
 }
 
@@ -667,13 +713,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CL == 2>::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmEpiCfg<BN, EPI, CL == 2>::SMEM_BYTES));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN, CL == 2>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = GemmEpiCfg<BN, EPI, CL == 2>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -783,6 +829,11 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     int rc;
     int epi = -1;
     if (splits > 1 || direct_acc) epi = 4;
+    if (q->a_rowsum) {
+        PB_CHECK(direct_acc && a_mn && Zout == 1 && bn != 512,
+                 "a_rowsum needs the weight-gradient form: MN-major A, fp32 C with accumulate, no other epilogue option, one output batch");
+        epi = 7;
+    }
     else if (!q->out_fp32 && !q->accumulate && splits == 1 && q->c_batch_stride % 8 == 0 && q->alpha == 1.0f &&
         (reinterpret_cast<uintptr_t>(q->c) & 15) == 0 && (q->act == 0 || q->act == 1)) {
         if (q->residual) { if (!q->relu_mask && !q->relu_bits && !q->bias && q->act == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) epi = 5; }
@@ -792,7 +843,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
         else if (q->act == 0) epi = 0;
     }
     const bool tma_store = epi >= 0;
-    if (epi == 4 && direct_acc) {
+    if ((epi == 4 || epi == 7) && direct_acc) {
         rc = make_tmap(&tc, q->c, q->m, q->n, q->ldc, Zout, q->c_batch_stride, 32, 32, /*fp32=*/true);
         if (rc) return rc;
     } else if (epi == 4) {
@@ -816,6 +867,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     if (q->cluster_m == 0 && bn != 512 && out_tiles * splits <= num_sms()) cl = 1;
     if (cl == 4 && b_mn && bn == 128) cl = 2;
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+    if (epi == 7 && cl == 4) cl = 2;
     if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn == 512 ? 128 : bn / cl);
     else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zall, q->b_batch_stride, 64, BK);
     if (rc) return rc;
@@ -841,6 +893,7 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     d.act = q->act; d.out_fp32 = q->out_fp32; d.accumulate = q->accumulate; d.alpha = q->alpha;
     d.tma_store = tma_store ? 1 : 0;
     d.partial = reinterpret_cast<float*>(q->workspace);
+    d.a_rowsum = q->a_rowsum;
 
     const long long m_groups = (m_blks + cl - 1) / cl;
     const long long cluster_tiles = Zout * m_groups * n_blks * splits;
@@ -873,7 +926,15 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
             default: PB_DISPATCH2(BN_, -1); break;                \
         }                                                         \
     } while (0)
-    if (bn == 512) {   // CTA pair, K-major A, plain / bias / residual epilogues only (see the tile choice above)
+    if (epi == 7) {    // weight-gradient form only (MN-major A), CTA pair or single CTAs
+        if (bn == 128) {
+            if (cl == 1) { if (b_mn) rc = launch_gemm<128, true, true, 7, 1>(ta, tb, tc, d, grid, stream); else rc = launch_gemm<128, true, false, 7, 1>(ta, tb, tc, d, grid, stream); }
+            else { if (b_mn) rc = launch_gemm<128, true, true, 7, 2>(ta, tb, tc, d, grid, stream); else rc = launch_gemm<128, true, false, 7, 2>(ta, tb, tc, d, grid, stream); }
+        } else {
+            if (cl == 1) { if (b_mn) rc = launch_gemm<256, true, true, 7, 1>(ta, tb, tc, d, grid, stream); else rc = launch_gemm<256, true, false, 7, 1>(ta, tb, tc, d, grid, stream); }
+            else { if (b_mn) rc = launch_gemm<256, true, true, 7, 2>(ta, tb, tc, d, grid, stream); else rc = launch_gemm<256, true, false, 7, 2>(ta, tb, tc, d, grid, stream); }
+        }
+    } else if (bn == 512) {   // CTA pair, K-major A, plain / bias / residual epilogues only (see the tile choice above)
         PB_CHECK(cl == 2 && !a_mn && (epi == 0 || epi == 1 || epi == 5), "internal: 512-wide tile chosen for an unsupported variant");
         if (!b_mn) {
             if (epi == 0) rc = launch_gemm<512, false, false, 0, 2>(ta, tb, tc, d, grid, stream);

@@ -271,11 +271,16 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
     }
 }
 
-// out[n] (bf16) = (accumulate ? out[n] : 0) + sum_p partial[p * stride + n]
+// out[n] (bf16 or fp32) = (accumulate ? out[n] : 0) + sum_p partial[p * stride + n]
 // block = 32 columns x 8 partial-row lanes: coalesced 128-byte reads, tree-free smem reduce over the 8 lanes.
+__device__ __forceinline__ float out_load(const bf16* p) { return bf16_to_f(*p); }
+__device__ __forceinline__ float out_load(const float* p) { return *p; }
+__device__ __forceinline__ void out_store(bf16* p, float v) { *p = f_to_bf16(v); }
+__device__ __forceinline__ void out_store(float* p, float v) { *p = v; }
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int P, long long stride, int N,
-                       bf16* __restrict__ out, int accumulate) {
+                       OutT* __restrict__ out, int accumulate) {
     pdl_trigger();
     pdl_wait();
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
@@ -297,8 +302,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int P, long long strid
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += red[r][cx];
-        if (accumulate) s += bf16_to_f(out[n]);
-        out[n] = f_to_bf16(s);
+        if (accumulate) s += out_load(out + n);
+        out_store(out + n, s);
     }
 }
 
@@ -455,8 +460,21 @@ extern "C" size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N) {
     return (size_t)colsum_splits(M, N) * (size_t)N * sizeof(float);
 }
 
+static int colsum_impl(const void* x, int64_t M, int64_t N, int64_t ld, void* out, bool out_fp32, int32_t accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream_);
+
 extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld, void* out, int32_t accumulate,
                                  void* workspace, size_t workspace_bytes, void* stream_) {
+    return colsum_impl(x, M, N, ld, out, false, accumulate, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int pb200_colsum_f32(const void* x, int64_t M, int64_t N, int64_t ld, float* out, int32_t accumulate,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+    return colsum_impl(x, M, N, ld, out, true, accumulate, workspace, workspace_bytes, stream_);
+}
+
+static int colsum_impl(const void* x, int64_t M, int64_t N, int64_t ld, void* out, bool out_fp32, int32_t accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PB_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
     if (N == 0) return 0;
@@ -465,8 +483,12 @@ extern "C" int pb200_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ld
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)splits);
     PB_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, (const bf16*)x, (int)M, (int)N, (long long)ld, (float*)workspace));
     PB_LAUNCH_CHECK();
-    PB_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, stream, (const float*)workspace, (int)splits,
-                       (long long)N, (int)N, (bf16*)out, (int)accumulate));
+    if (out_fp32)
+        PB_CUDA(launch_pdl(reduce_partials_kernel<float>, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, stream, (const float*)workspace,
+                           (int)splits, (long long)N, (int)N, (float*)out, (int)accumulate));
+    else
+        PB_CUDA(launch_pdl(reduce_partials_kernel<bf16>, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, stream, (const float*)workspace,
+                           (int)splits, (long long)N, (int)N, (bf16*)out, (int)accumulate));
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -64,9 +64,11 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
              a_mn_major: bool = False, b_mn_major: bool = False, reduce_batch: bool = False,
              bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, relu_mask: Optional[Tensor] = None,
              act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0,
-             cluster_m: int = 0, relu_bits_out: Optional[Tensor] = None, relu_bits: Optional[Tensor] = None) -> Tensor:
+             cluster_m: int = 0, relu_bits_out: Optional[Tensor] = None, relu_bits: Optional[Tensor] = None,
+             a_rowsum: Optional[Tensor] = None) -> Tensor:
     lib = _lib.load()
     p = GemmParams()
+    p.a_rowsum = ptr(a_rowsum)
     p.a, p.b, p.c = a_ptr, b_ptr, c.data_ptr()
     p.m, p.n, p.k, p.batch = m, n, k, batch
     p.lda, p.ldb, p.ldc = lda, ldb, ldc
@@ -134,13 +136,18 @@ def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out:
                     relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1, relu_bits=relu_bits)
 
 
-def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
-    """dw[N, K] = dy[M, N]^T @ x[M, K]"""
+def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
+                 bias_grad32: Optional[Tensor] = None) -> Tensor:
+    """dw[N, K] = dy[M, N]^T @ x[M, K]. bias_grad32 (fp32 [N], needs an fp32 `out` with accumulate): += column sums of
+    dy, computed inside the same GEMM (one more 16-column MMA per k-step against an all-ones operand)."""
     M, N = dy.shape
     K = x.shape[1]
     dw = out if out is not None else torch.empty(N, K, dtype=BF16, device=dy.device)
-    return gemm_raw(dy.data_ptr(), x.data_ptr(), dw, N, K, M, lda=N, ldb=K, ldc=K, a_mn_major=True, b_mn_major=True,
-                    accumulate=accumulate)
+    if bias_grad32 is not None:
+        assert bias_grad32.dtype == torch.float32 and bias_grad32.numel() == N and bias_grad32.is_contiguous()
+        assert dw.dtype == torch.float32 and accumulate, 'fused bias gradient needs the fp32 accumulate path'
+    return gemm_raw(dy.data_ptr(), x.data_ptr(), dw, N, K, M, lda=dy.stride(0), ldb=x.stride(0), ldc=dw.stride(0),
+                    a_mn_major=True, b_mn_major=True, accumulate=accumulate, a_rowsum=bias_grad32)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -230,8 +237,8 @@ def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) ->
     out = out if out is not None else torch.empty(N, dtype=BF16, device=x.device)
     ws = _ws(lib.pb200_colsum_workspace_bytes(M, N), x.device)
     _count(2)
-    check(lib.pb200_colsum_bf16(x.data_ptr(), M, N, x.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(),
-                                ws.numel(), stream_ptr()))
+    fn = lib.pb200_colsum_f32 if out.dtype == torch.float32 else lib.pb200_colsum_bf16   # fp32: main gradient of a bias
+    check(fn(x.data_ptr(), M, N, x.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(), stream_ptr()))
     return out
 
 

@@ -153,6 +153,7 @@ class MultiheadAttention(nn.Module):
             raise NotImplementedError('attention dropout is not covered yet (reference default is 0.0)')
         self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
         self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
+        self.in_proj_bias._pb200_f32_grad = True   # gradient accumulated in fp32 by the weight-gradient GEMM (ops._wgrad_bias)
         self.out_proj = Linear(embed_dim, embed_dim)
         self.reset_parameters()
 
@@ -251,6 +252,7 @@ class ConvolutionSubsampler(nn.Module):
             bound = 1 / math.sqrt(cin * k)
             self.register_parameter(f'weight{i}', nn.Parameter(w.permute(0, 2, 1).reshape(cout, k * cin).contiguous()))
             self.register_parameter(f'bias{i}', nn.Parameter(torch.empty(cout).uniform_(-bound, bound)))
+            getattr(self, f'bias{i}')._pb200_f32_grad = True
             self.channels.append((cin, cout))
 
     @property

@@ -106,6 +106,40 @@ def _wgrad(dy: Tensor, x: Tensor, param):
     return _ret(K.linear_wgrad(dy, x, out=out, accumulate=acc), out)
 
 
+def _wgrad_bias(dy: Tensor, x: Tensor, w_out: Tensor, acc_w: bool, b32: Optional[Tensor], b_out: Optional[Tensor],
+                acc_b: bool) -> None:
+    """w_out (+)= dy^T x and the bias gradient (column sums of dy) of the same Linear. A bias with an fp32 main gradient
+    (b32) gets its sums from the weight-gradient GEMM itself when that one accumulates in fp32 too — dy is then read once
+    instead of twice; otherwise a column-sum kernel writes b32 (+=) or the bf16 sink b_out."""
+    fuse = b32 is not None and w_out.dtype == torch.float32 and acc_w
+    K.linear_wgrad(dy, x, out=w_out, accumulate=acc_w, bias_grad32=b32 if fuse else None)
+    if b32 is not None:
+        if not fuse:
+            K.colsum(dy, out=b32, accumulate=True)
+    elif b_out is not None:
+        K.colsum(dy, out=b_out, accumulate=acc_b)
+
+
+def _linear_grads(dy: Tensor, x: Tensor, w_param, b_param, need_w: bool = True, need_b: bool = True):
+    """(dW, db) of y = x W^T + b for autograd (None where the gradient went straight into a DirectGrads sink)."""
+    dw = db = None
+    need_b = need_b and b_param is not None
+    b32 = _sink32(b_param) if need_b else None
+    w32 = _sink32(w_param) if need_w else None
+    if w32 is not None and b32 is not None:
+        _wgrad_bias(dy, x, w32, True, b32, None, False)
+        return None, None
+    if need_w:
+        dw = _wgrad(dy, x, w_param)
+    if need_b:
+        if b32 is not None:
+            K.colsum(dy, out=b32, accumulate=True)
+        else:
+            o, a = _sink(b_param)
+            db = _ret(K.colsum(dy, out=o, accumulate=a), o)
+    return dw, db
+
+
 def _ret(grad, out):
     """Gradient to hand back to autograd: None when it already went into the arena."""
     return None if out is not None else grad
@@ -128,12 +162,7 @@ class LinearFn(torch.autograd.Function):
         w_param, b_param = ctx.params
         dy = _c(dy)
         dx = K.linear_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
-        dw = db = None
-        if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy, x, w_param)
-        if b_param is not None and ctx.needs_input_grad[2]:
-            out, acc = _sink(b_param)
-            db = _ret(K.colsum(dy, out=out, accumulate=acc), out)
+        dw, db = _linear_grads(dy, x, w_param, b_param, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         _ready(w_param, b_param)
         return dx, dw, db
 
@@ -165,11 +194,7 @@ class LinearReluFn(torch.autograd.Function):
         w_param, b_param = ctx.params
         dpre = K.relu_bwd(_c(dh), h)
         dx = K.linear_dgrad(dpre, weight) if ctx.needs_input_grad[0] else None
-        dw = _wgrad(dpre, x, w_param) if ctx.needs_input_grad[1] else None
-        db = None
-        if b_param is not None and ctx.needs_input_grad[2]:
-            out, acc = _sink(b_param)
-            db = _ret(K.colsum(dpre, out=out, accumulate=acc), out)
+        dw, db = _linear_grads(dpre, x, w_param, b_param, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         _ready(w_param, b_param)
         return dx, dw, db
 
@@ -193,12 +218,10 @@ class FFNFn(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2 = ctx.params
         dy = _c(dy)
         dh = K.linear_dgrad(dy, w2, relu_mask=h if bits is None else None, relu_bits=bits)
-        dw2 = _wgrad(dy, h, p_w2)
-        o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
+        dw2, db2 = _linear_grads(dy, h, p_w2, p_b2)
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1)
-        dw1 = _wgrad(dh, x, p_w1)
-        o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
+        dw1, db1 = _linear_grads(dh, x, p_w1, p_b1)
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2
 
@@ -241,8 +264,7 @@ class AttentionFn(torch.autograd.Function):
         p_in_w, p_in_b, p_out_w, p_out_b = ctx.params
         dy = _c(dy)
         d_o = K.linear_dgrad(dy, out_w)
-        d_out_w = _wgrad(dy, o, p_out_w)
-        so, a = _sink(p_out_b); d_out_b = _ret(K.colsum(dy, out=so, accumulate=a), so)
+        d_out_w, d_out_b = _linear_grads(dy, o, p_out_w, p_out_b)
         _ready(p_out_w, p_out_b)
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
@@ -251,17 +273,18 @@ class AttentionFn(torch.autograd.Function):
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
         d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        b32 = _sink32(p_in_b)    # fp32 main gradient of the fused bias: filled by the weight-gradient GEMMs themselves
         kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
             dquery = K.linear_dgrad(dkvq, in_w)
-            K.linear_wgrad(dkvq, query, out=d_in_w, accumulate=acc_w)
             if kb:
-                K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+                _wgrad_bias(dkvq, query, d_in_w, acc_w, b32, d_in_b, acc_b)
             else:
-                K.colsum(dkvq[:, D:], out=d_in_b[D:], accumulate=acc_b)
+                K.linear_wgrad(dkvq, query, out=d_in_w, accumulate=acc_w)
+                K.colsum(dkvq[:, D:], out=(b32 if b32 is not None else d_in_b)[D:], accumulate=acc_b or b32 is not None)
             dkey = None
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
@@ -269,13 +292,12 @@ class AttentionFn(torch.autograd.Function):
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
             dquery = K.linear_dgrad(dq, in_w[2 * D:])
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
-            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
-            K.linear_wgrad(dq, query, out=d_in_w[2 * D:], accumulate=acc_w)
             if kb:
-                K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+                _wgrad_bias(dkv, key_c, d_in_w[:2 * D], acc_w, b32[:2 * D] if b32 is not None else None, d_in_b[:2 * D], acc_b)
             else:
-                K.colsum(dkv[:, D:], out=d_in_b[D:2 * D], accumulate=acc_b)
-            K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
+                K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
+                K.colsum(dkv[:, D:], out=(b32 if b32 is not None else d_in_b)[D:2 * D], accumulate=acc_b or b32 is not None)
+            _wgrad_bias(dq, query, d_in_w[2 * D:], acc_w, b32[2 * D:] if b32 is not None else None, d_in_b[2 * D:], acc_b)
         _ready(p_in_w, p_in_b)
         return (dquery, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b,
                 None, None, None, None, None, None, None, None)
@@ -379,17 +401,18 @@ class AttnSublayerFn(torch.autograd.Function):
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
         d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        b32 = _sink32(p_in_b)    # fp32 main gradient of the fused bias: filled by the weight-gradient GEMMs themselves
         kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
             dx = K.linear_dgrad(dkvq, in_w, residual=dres)
-            K.linear_wgrad(dkvq, x, out=d_in_w, accumulate=acc_w)
             if kb:
-                K.colsum(dkvq, out=d_in_b, accumulate=acc_b)
+                _wgrad_bias(dkvq, x, d_in_w, acc_w, b32, d_in_b, acc_b)
             else:
-                K.colsum(dkvq[:, D:], out=d_in_b[D:], accumulate=acc_b)
+                K.linear_wgrad(dkvq, x, out=d_in_w, accumulate=acc_w)
+                K.colsum(dkvq[:, D:], out=(b32 if b32 is not None else d_in_b)[D:], accumulate=acc_b or b32 is not None)
             dkey = None
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
@@ -397,13 +420,12 @@ class AttnSublayerFn(torch.autograd.Function):
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
             dx = K.linear_dgrad(dq, in_w[2 * D:], residual=dres)
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
-            K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
-            K.linear_wgrad(dq, x, out=d_in_w[2 * D:], accumulate=acc_w)
             if kb:
-                K.colsum(dkv, out=d_in_b[:2 * D], accumulate=acc_b)
+                _wgrad_bias(dkv, key_c, d_in_w[:2 * D], acc_w, b32[:2 * D] if b32 is not None else None, d_in_b[:2 * D], acc_b)
             else:
-                K.colsum(dkv[:, D:], out=d_in_b[D:2 * D], accumulate=acc_b)
-            K.colsum(dq, out=d_in_b[2 * D:], accumulate=acc_b)
+                K.linear_wgrad(dkv, key_c, out=d_in_w[:2 * D], accumulate=acc_w)
+                K.colsum(dkv[:, D:], out=(b32 if b32 is not None else d_in_b)[D:2 * D], accumulate=acc_b or b32 is not None)
+            _wgrad_bias(dq, x, d_in_w[2 * D:], acc_w, b32[2 * D:] if b32 is not None else None, d_in_b[2 * D:], acc_b)
         _ready(p_in_w, p_in_b)
         return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta,
                 None, None, None, None, None, None, None, None, None, None)
@@ -439,10 +461,7 @@ class FFNSublayerFn(torch.autograd.Function):
         dw2 = _wgrad(dy, h, p_w2) if need[3] else None
         _ready(p_w2, p_b2)
         dx = K.linear_dgrad(dh, w1, residual=dres)
-        dw1 = _wgrad(dh, x, p_w1) if need[1] else None
-        db1 = None
-        if need[2]:
-            o, a = _sink(p_b1); db1 = _ret(K.colsum(dh, out=o, accumulate=a), o)
+        dw1, db1 = _linear_grads(dh, x, p_w1, p_b1, need[1], need[2])
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2, dgamma, dbeta, None, None
 
@@ -555,13 +574,11 @@ class FFNGeluFn(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2 = ctx.params
         dy = _c(dy)
         dh = K.linear_dgrad(dy, w2)
-        dw2 = _wgrad(dy, h, p_w2)
-        o, a = _sink(p_b2); db2 = _ret(K.colsum(dy, out=o, accumulate=a), o)
+        dw2, db2 = _linear_grads(dy, h, p_w2, p_b2)
         _ready(p_w2, p_b2)
         dpre = K.gelu_bwd(dh, pre)
         dx = K.linear_dgrad(dpre, w1)
-        dw1 = _wgrad(dpre, x, p_w1)
-        o, a = _sink(p_b1); db1 = _ret(K.colsum(dpre, out=o, accumulate=a), o)
+        dw1, db1 = _linear_grads(dpre, x, p_w1, p_b1)
         _ready(p_w1, p_b1)
         return dx, dw1, db1, dw2, db2
 
@@ -627,11 +644,16 @@ class ConvGLUFn(torch.autograd.Function):
         if w32 is not None:
             so_w, acc_w = w32, True
         dw = so_w if so_w is not None else torch.empty_like(weight)
+        b32 = _sink32(p_b)
+        fuse_b = b32 is not None and w32 is not None   # bias gradient = row sums of the GEMM's A operand (see _wgrad_bias)
         K.gemm_raw(dpre.data_ptr(), xp.data_ptr(), dw, Cout, KW * Cin, Tout, lda=Cout, ldb=stride * Cin, ldc=KW * Cin, batch=B,
                    a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True,
-                   accumulate=acc_w)
+                   accumulate=acc_w, a_rowsum=b32 if fuse_b else None)
         so_b, acc_b = _sink(p_b)
-        db = K.colsum(dpre, out=so_b, accumulate=acc_b)
+        if b32 is not None:
+            db = b32 if fuse_b else K.colsum(dpre, out=b32, accumulate=True)
+        else:
+            db = K.colsum(dpre, out=so_b, accumulate=acc_b)
         _ready(p_w, p_b)
         dw, db = _ret(dw, so_w), _ret(db, so_b)
         dxp = None

@@ -84,7 +84,10 @@ class ParamArena:
         # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
         # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
         self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
-        self.is32 = [p.ndim >= 2 and not getattr(p, '_pb200_bf16_grad', False) for p in self.params]
+        # ... and of the biases flagged `_pb200_f32_grad` (in-projection, fc1, conv): their gradient is a by-product of the
+        # weight-gradient GEMM (pb200_gemm_params.a_rowsum), added atomically in fp32
+        self.is32 = [(p.ndim >= 2 and not getattr(p, '_pb200_bf16_grad', False)) or getattr(p, '_pb200_f32_grad', False)
+                     for p in self.params]
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=device)
         with torch.no_grad():

@@ -67,6 +67,7 @@ class TransformerEncoderLayer(nn.Module, _AdapterMixin):
                                                     scaled=cfg.scale_attn, key_bias=cfg.attention_key_bias)
         self.self_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.fc1 = modules.Linear(cfg.embed_dim, cfg.encoder_ffn_dim)
+        self.fc1.bias._pb200_f32_grad = True   # see ops._wgrad_bias
         self.fc2 = modules.Linear(cfg.encoder_ffn_dim, cfg.embed_dim)
         self.final_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.prenorm = cfg.encoder_prenorm
@@ -118,6 +119,7 @@ class TransformerDecoderLayer(nn.Module, _AdapterMixin):
                                                        key_bias=cfg.attention_key_bias)
         self.encoder_attn_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.fc1 = modules.Linear(cfg.embed_dim, cfg.decoder_ffn_dim)
+        self.fc1.bias._pb200_f32_grad = True   # see ops._wgrad_bias
         self.fc2 = modules.Linear(cfg.decoder_ffn_dim, cfg.embed_dim)
         self.final_layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps)
         self.prenorm = cfg.decoder_prenorm

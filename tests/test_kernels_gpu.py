@@ -93,6 +93,27 @@ def test_gemm_dgrad_wgrad(M, N, K):
     _close(dw2, 2 * ref, 4e-2 * math.sqrt(M / 256), 2e-2, 'wgrad accumulate')
 
 
+@pytest.mark.parametrize('M,N,K', [(16000, 1536, 512), (16000, 2048, 512), (3072, 512, 512), (3072, 1024, 512),
+                                   (1000, 200, 136), (16000, 512, 2048), (77, 64, 64)])
+def test_wgrad_fused_bias_grad(M, N, K):
+    """pb200_gemm_params.a_rowsum: the bias gradient (column sums of dy) out of the weight-gradient GEMM itself — every
+    tile shape / CTA-pair / split-K variant the training step reaches, accumulating into non-zero fp32 buffers"""
+    k = _k()
+    dy, x = _rand(M, N, seed=1), _rand(M, K, seed=2)
+    w32 = torch.full((N, K), 0.5, dtype=torch.float32, device='cuda')
+    b32 = torch.full((N,), -2.0, dtype=torch.float32, device='cuda')
+    for rep in range(2):   # second round: accumulate on top
+        k.linear_wgrad(dy, x, out=w32, accumulate=True, bias_grad32=b32)
+    ref_w = 0.5 + 2 * (dy.float().T @ x.float())
+    ref_b = -2.0 + 2 * dy.float().sum(0)
+    _close(w32, ref_w, 1e-2 * math.sqrt(M / 256), 1e-3, 'wgrad fp32')
+    _close(b32, ref_b, 1e-3 * math.sqrt(M), 1e-4, 'fused bias grad')
+    # the stand-alone fp32 column-sum kernel (fallback for shapes / paths the GEMM cannot fold it into)
+    c32 = torch.full((N,), -2.0, dtype=torch.float32, device='cuda')
+    k.colsum(dy, out=c32, accumulate=True)
+    _close(c32, -2.0 + dy.float().sum(0), 1e-3 * math.sqrt(M), 1e-4, 'colsum fp32')
+
+
 def test_gemm_conv_view():
     """strided conv1d (k=5, s=2, p=2) as a GEMM over an overlapping-row view of the zero-padded input"""
     k = _k()
