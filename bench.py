@@ -344,6 +344,7 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
     replay are read back. (Events around eager launches over-count: each bracket then also holds the host's launch
     latency.) Split-K launches are timed with their memset and reduction kernels; FLOPs are the algorithmic 2*M*N*K."""
     from pasero_b200 import kernels as K
+    from pasero_b200 import ops
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -356,6 +357,11 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
     saved = dict(trainer._graphs)
     trainer._graphs.clear()
     K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = [], True, {'launches': 0}
+    # kernel durations are taken with every kernel on ONE stream: in the production step the weight-gradient GEMMs run on
+    # a second stream next to the dependent chain, where a bracket would also hold the time its kernel waited for SMs
+    two_streams = ops.WgradStream.enabled
+    ops.WgradStream.enabled = False
+    serial_ms = ms_per_step
     try:
         step(pcm_dev, dec_dev)            # warm-up pass + capture (both go through the instrumented wrappers)
         if trainer._graphs:
@@ -380,7 +386,20 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
                 g[1] += s_.elapsed_time(e_)
             for tag, (n, t, f) in sorted(groups.items(), key=lambda x: -x[1][1]):
                 sys.stderr.write(f'{tag:60s} n={n:3d} total {t * 1e3:8.1f} us  avg {t / n * 1e3:7.1f} us  {f * n / t / 1e9:7.1f} TFLOP/s\n')
+        if two_streams:   # the single-stream step the kernel times belong to (un-instrumented), for the share below
+            K.PROFILE_EXTERNAL = False
+            trainer._graphs.clear()
+            for _ in range(2):
+                step(pcm_dev, dec_dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                step(pcm_dev, dec_dev)
+            e1.record()
+            torch.cuda.synchronize()
+            serial_ms = e0.elapsed_time(e1) / 5
     finally:
+        ops.WgradStream.enabled = two_streams
         K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = None, False, None
         trainer._graphs.clear()
         trainer._graphs.update(saved)
@@ -390,10 +409,12 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
                 'launches_timed': len(prof), 'gemm_ms_per_step': ms, 'gemm_ms_per_step_raw': ms_raw,
                 'event_bracket_overhead_us': overhead * 1e3, 'achieved_raw': flops / (ms_raw / 1e3) / 1e12,
                 'algorithmic_gflop_per_step': flops / 1e9, 'peak_source': peak_kind,
+                'single_stream_step_ms': serial_ms,
                 'method': 'external CUDA-event record nodes around every GEMM launch inside the replayed step graph; the '
                           'bracket overhead (same bracket around a ~1 us kernel minus its un-instrumented chain time) is '
-                          'subtracted per launch; *_raw keep the uncorrected sums'}
-    return roofline, ms / ms_per_step, launches
+                          'subtracted per launch; *_raw keep the uncorrected sums. Timed with all kernels on one stream '
+                          '(single_stream_step_ms); the production step overlaps the weight-gradient GEMMs on a second stream'}
+    return roofline, ms / serial_ms, launches
 
 
 if __name__ == '__main__':

@@ -5,6 +5,7 @@ Dropout masks are Philox(seed, offset): `DropoutState` hands out a fresh offset 
 regenerate the same mask without storing it.
 """
 import math
+import os
 import weakref
 from typing import Optional
 
@@ -78,6 +79,42 @@ class DirectGrads:
                     self.on_ready(p)
 
 
+class WgradStream:
+    """Second CUDA stream for the weight-gradient GEMMs that accumulate into the fp32 main-gradient arena. Nothing reads
+    those sums before the gradient flush, so the GEMMs need not sit on backward's critical path: forked onto this stream
+    they fill the SMs that the dependent chain (dgrad -> attention backward -> LayerNorm backward ...) leaves idle at
+    kernel tails and in the decoder's small launches. Works the same eagerly and under CUDA-graph capture (the fork /
+    join become graph edges). Operands are kept referenced until `join()` so the caching allocator cannot hand their
+    memory to a later kernel of the main stream while the GEMM still reads it. PB200_WGRAD_STREAM=0 disables it."""
+    enabled = os.environ.get('PB200_WGRAD_STREAM', '1') != '0'
+    _streams: dict = {}
+    _pending: list = []
+    _forked = None      # the side stream with un-joined work, if any
+
+    @classmethod
+    def run(cls, fn, *operands) -> None:
+        if not cls.enabled:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        side = cls._streams.get(main.device)
+        if side is None:
+            side = cls._streams[main.device] = torch.cuda.Stream(device=main.device)
+        side.wait_stream(main)          # operands were produced on the main stream
+        with torch.cuda.stream(side):
+            fn()
+        cls._pending.extend(operands)
+        cls._forked = side
+
+    @classmethod
+    def join(cls) -> None:
+        """The current stream waits for every forked GEMM (call before anything reads the fp32 main gradients)."""
+        if cls._forked is not None:
+            torch.cuda.current_stream().wait_stream(cls._forked)
+            cls._forked = None
+            cls._pending.clear()
+
+
 def _sink(param):
     d = DirectGrads.active
     return d.sink(param) if (d is not None and param is not None) else (None, False)
@@ -100,7 +137,7 @@ def _wgrad(dy: Tensor, x: Tensor, param):
     (overwrite / accumulate), or a fresh tensor handed back to autograd. Returns what autograd should see."""
     v32 = _sink32(param)
     if v32 is not None:
-        K.linear_wgrad(dy, x, out=v32, accumulate=True)
+        WgradStream.run(lambda: K.linear_wgrad(dy, x, out=v32, accumulate=True), dy, x)
         return None
     out, acc = _sink(param)
     return _ret(K.linear_wgrad(dy, x, out=out, accumulate=acc), out)
@@ -112,7 +149,10 @@ def _wgrad_bias(dy: Tensor, x: Tensor, w_out: Tensor, acc_w: bool, b32: Optional
     (b32) gets its sums from the weight-gradient GEMM itself when that one accumulates in fp32 too — dy is then read once
     instead of twice; otherwise a column-sum kernel writes b32 (+=) or the bf16 sink b_out."""
     fuse = b32 is not None and w_out.dtype == torch.float32 and acc_w
-    K.linear_wgrad(dy, x, out=w_out, accumulate=acc_w, bias_grad32=b32 if fuse else None)
+    if w_out.dtype == torch.float32 and acc_w:   # fp32 main gradient: off the critical path
+        WgradStream.run(lambda: K.linear_wgrad(dy, x, out=w_out, accumulate=True, bias_grad32=b32 if fuse else None), dy, x)
+    else:
+        K.linear_wgrad(dy, x, out=w_out, accumulate=acc_w)
     if b32 is not None:
         if not fuse:
             K.colsum(dy, out=b32, accumulate=True)

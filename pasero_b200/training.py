@@ -119,6 +119,7 @@ class ParamArena:
 
     def flush32(self, ranges: tuple) -> None:
         """grad (bf16) <- round(grad32) over `ranges`; grad32 <- 0."""
+        ops.WgradStream.join()   # the weight-gradient GEMMs forked onto the side stream have to land first
         if ranges[1] > 0:
             K.grad32_flush(self.grad32, self.grad, ranges[0], ranges[1])
 
@@ -430,6 +431,7 @@ class Trainer:
         batch = dict(static)
         batch.update(extras)
         self._forward_backward(batch)
+        ops.WgradStream.join()                       # (a captured graph must end with every forked stream joined)
         if self.buckets is None:
             self.arena.flush32(self._ranges32_all)   # with buckets: flushed per bucket right before its allreduce
 
