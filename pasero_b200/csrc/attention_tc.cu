@@ -313,25 +313,12 @@ struct BwdCfg {
     // TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ chunk i [384 + 64 i, ...)
 };
 
-// 16-byte global -> shared copy, zero-filled when `valid` is false
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0)
-                 : "memory");
-}
-// rows [0, box) x 64 bf16 of head `h` of a [L, ld] matrix -> SWIZZLE_128B K-major tile (128-byte rows, 16-byte chunk index
-// XOR row & 7: the layout TMA writes and the UMMA descriptors read); rows >= L are zero-filled. 256 threads.
-__device__ __forceinline__ void load_tile_ldgsts(uint8_t* tile, const bf16* g, long long ld, int L, int box, int tid) {
-    for (int i = tid; i < box * 8; i += 256) {
-        const int r = i >> 3, c = i & 7;
-        cp_async16_zfill(tile + r * 128 + ((c ^ (r & 7)) << 4), g + (long long)(r < L ? r : 0) * ld + c * 8, r < L);
-    }
-}
-
-// LDGSTS: the operands are fetched with cp.async by the 256 softmax threads instead of four TMA boxes. A TMA box of
-// 250 x 128-byte rows at a 1-2 KB stride is limited by the TMA unit's outstanding requests x DRAM latency (timeline:
-// ~13 k cycles for the four boxes, ~30 % of the CTA's life with nothing to overlap); 256 threads keep 32 x 16-byte
-// requests each in flight.
-template <bool CAUSAL, bool LDGSTS>
+// The four operands arrive as 128-row tiles on four one-shot barriers, in the order the first iteration consumes them:
+// (K_0, Q_0) -> S^T of iteration 0; (V_0, dO_0) -> dP^T; (Q_1, dO_1) and (K_1, V_1) land while iteration 0 computes.
+// Measured: the CTAs of a wave run in lock-step, so the load phase is a DRAM burst of 148 x 192 KB (operand tiles + the
+// O / dO rows of delta) at ~4.4 TB/s, ~30 % of the CTA's life; neither these finer barriers nor cp.async loads by the
+// 256 softmax threads (tried, removed) shortened it — only a second resident CTA per SM would (192 KB of smem: no room).
+template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
@@ -348,8 +335,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     float* sLse = reinterpret_cast<float*>(sdST + BwdCfg::PT);
     float* sDelta = sLse + 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
-    uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_acc = bars + 3, *bar_load2 = bars + 4;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bar_s = bars, *bar_p = bars + 1, *bar_acc = bars + 2;
+    uint64_t* bar_ld = bars + 3;   // [4]: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
@@ -368,8 +356,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     if (warp == 8) {
         if (lane == 0) {
             ptx::prefetch_tmap(&tmq); ptx::prefetch_tmap(&tmk); ptx::prefetch_tmap(&tmv); ptx::prefetch_tmap(&tmdo);
-            ptx::mbar_init(bar_load, LDGSTS ? 256 : 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_acc, 1);
-            ptx::mbar_init(bar_load2, LDGSTS ? 256 : 1);
+            ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_acc, 1);
+            for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar_ld[i], 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -388,17 +376,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
     if (warp == 8) {
         if (lane == 0) {
-            // K and Q first: the S^T chain of the first iteration starts while V and dO are still in flight
-            if (!LDGSTS) {
-                ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)(p.q_box + p.kv_box) * 128u);
-                ptx::tma_load_3d(&tmk, bar_load, sK, h * 64, 0, b);
-                ptx::tma_load_3d(&tmq, bar_load, sQ, h * 64, 0, b);
-                ptx::mbar_arrive_expect_tx(bar_load2, (uint32_t)(p.q_box + p.kv_box) * 128u);
-                ptx::tma_load_3d(&tmv, bar_load2, sV, h * 64, 0, b);
-                ptx::tma_load_3d(&tmdo, bar_load2, sdO, h * 64, 0, b);
+            {
+                const uint32_t qb = (uint32_t)min(p.q_box, 128) * 128u, kb = (uint32_t)min(p.kv_box, 128) * 128u;   // bytes per tile box
+                ptx::mbar_arrive_expect_tx(&bar_ld[0], qb + kb);
+                ptx::tma_load_3d(&tmk, &bar_ld[0], sK, h * 64, 0, b);
+                ptx::tma_load_3d(&tmq, &bar_ld[0], sQ, h * 64, 0, b);
+                ptx::mbar_arrive_expect_tx(&bar_ld[1], qb + kb);
+                ptx::tma_load_3d(&tmv, &bar_ld[1], sV, h * 64, 0, b);
+                ptx::tma_load_3d(&tmdo, &bar_ld[1], sdO, h * 64, 0, b);
+                if (ni > 1) {
+                    ptx::mbar_arrive_expect_tx(&bar_ld[2], 2 * qb);
+                    ptx::tma_load_3d(&tmq, &bar_ld[2], sQ + 16384, h * 64, 128, b);
+                    ptx::tma_load_3d(&tmdo, &bar_ld[2], sdO + 16384, h * 64, 128, b);
+                }
+                if (nj > 1) {
+                    ptx::mbar_arrive_expect_tx(&bar_ld[3], 2 * kb);
+                    ptx::tma_load_3d(&tmk, &bar_ld[3], sK + 16384, h * 64, 128, b);
+                    ptx::tma_load_3d(&tmv, &bar_ld[3], sV + 16384, h * 64, 128, b);
+                }
             }
             TSTAMP(1);
-            ptx::mbar_wait(bar_load, 0);
+            ptx::mbar_wait(&bar_ld[0], 0);
             ptx::tc_fence_after();
             TSTAMP(2);
             const uint32_t idesc_cd = ptx::make_idesc_bf16(128, 64, false, true);
@@ -417,12 +415,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
-                        ptx::mbar_wait(bar_load2, 0);
+                        ptx::mbar_wait(&bar_ld[1], 0);
                         ptx::tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
                     } else {
+                        if (j == 0 && i == 1) { ptx::mbar_wait(&bar_ld[2], 0); ptx::tc_fence_after(); }   // Q_1, dO_1
+                        if (j == 1 && i == 0) { ptx::mbar_wait(&bar_ld[3], 0); ptx::tc_fence_after(); }   // K_1, V_1
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
@@ -465,15 +465,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const int t = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        if (LDGSTS) {   // two cp.async groups: (K, Q) then (V, dO); they land while delta is computed below
-            const int tid = threadIdx.x;
-            load_tile_ldgsts(sK, p.k + (long long)b * p.Lk * p.ldk + h * 64, p.ldk, p.Lk, p.kv_box, tid);
-            load_tile_ldgsts(sQ, p.q + (long long)b * p.Lq * p.ldq + h * 64, p.ldq, p.Lq, p.q_box, tid);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            load_tile_ldgsts(sV, p.v + (long long)b * p.Lk * p.ldv + h * 64, p.ldv, p.Lk, p.kv_box, tid);
-            load_tile_ldgsts(sdO, p.dout + (long long)b * p.Lq * p.lddo + h * 64, p.lddo, p.Lq, p.q_box, tid);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
         {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
             const int r = threadIdx.x;   // 0..255
             float l2 = INFINITY, dl = 0.f;
@@ -493,14 +484,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
             }
             sLse[r] = l2; sDelta[r] = dl;
-        }
-        if (LDGSTS) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            ptx::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            ptx::mbar_arrive(bar_load);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(bar_load2);
         }
         ptx::bar_sync(1, 256);
         if (warp == 0) TSTAMP(8);
@@ -672,30 +655,22 @@ int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
     p.lddq = q->lddq; p.lddk = q->lddk; p.lddv = q->lddv;
     p.q = (const bf16*)q->q; p.k = (const bf16*)q->k; p.v = (const bf16*)q->v;
     p.ldq = q->ldq; p.ldk = q->ldk; p.ldv = q->ldv;
-    // measured: no gain from the cp.async path (the load phase is bound by the burst of 148 CTAs x 128 KB hitting DRAM at
-    // once, not by the TMA unit), so TMA stays the default; PB200_ATTN_BWD_TMA=0 selects cp.async for experiments
-    static const bool use_tma = [] { const char* e = getenv("PB200_ATTN_BWD_TMA"); return !(e && e[0] == '0'); }();
+    // 128-row tile boxes (see the kernel: one barrier per pair of tiles)
+    const int qbox = p.q_box < 128 ? p.q_box : 128, kbox = p.kv_box < 128 ? p.kv_box : 128;
     CUtensorMap tq, tk, tv, tdo;
-    if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, p.q_box)) return rc;
-    if (int rc = make_tmap(&tdo, q->dout, q->Lq, (long long)q->H * 64, q->lddo, q->B, (long long)q->Lq * q->lddo, 64, p.q_box)) return rc;
-    if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, p.kv_box)) return rc;
-    if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, p.kv_box)) return rc;
+    if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, qbox)) return rc;
+    if (int rc = make_tmap(&tdo, q->dout, q->Lq, (long long)q->H * 64, q->lddo, q->B, (long long)q->Lq * q->lddo, 64, qbox)) return rc;
+    if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, kbox)) return rc;
+    if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, kbox)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid(p.H, p.B);
-    if (use_tma) {
-        if (p.causal) PB_CUDA(launch_pdl(attn_bwd_tc_kernel<true, false>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-        else PB_CUDA(launch_pdl(attn_bwd_tc_kernel<false, false>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-    } else {
-        if (p.causal) PB_CUDA(launch_pdl(attn_bwd_tc_kernel<true, true>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-        else PB_CUDA(launch_pdl(attn_bwd_tc_kernel<false, true>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-    }
+    if (p.causal) PB_CUDA(launch_pdl(attn_bwd_tc_kernel<true>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
+    else PB_CUDA(launch_pdl(attn_bwd_tc_kernel<false>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
     PB_LAUNCH_CHECK();
     return 0;
 }
