@@ -141,12 +141,16 @@ int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* ga
 size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
 /* backward: dx / dresidual, dgamma, dbeta and (optional) dbias_lin = column sums of dx, i.e. the bias gradient of the
  * Linear whose output was `x` (saves a separate pass over dx). accumulate: bit 0 = add into dgamma/dbeta, bit 1 = add
- * into dbias_lin. */
+ * into dbias_lin, bit 2 = leave the CTA partials in `workspace` and skip the final reduction: the caller runs
+ * pb200_ln_bwd_reduce on them later / on another stream (the parameter gradients have no consumer inside backward, so
+ * that small kernel need not sit on the critical path). */
 int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, const void* sum, const void* gamma,
                              const float* mean, const float* rstd, int64_t M, int64_t D, float p, uint64_t seed,
                              uint64_t offset, const int64_t* offset_base, void* dresidual, void* dx, void* dgamma, void* dbeta,
                              void* dbias_lin, int32_t accumulate, const void* keep_mask, void* workspace, size_t workspace_bytes,
                              void* stream);
+int pb200_ln_bwd_reduce(const void* workspace, int64_t M, int64_t D, void* dgamma, void* dbeta, void* dbias_lin,
+                        int32_t accumulate, void* stream);
 
 /* column sums of a bf16 [M, N] matrix -> bf16 [N] (bias gradients) */
 size_t pb200_colsum_workspace_bytes(int64_t M, int64_t N);

@@ -445,14 +445,23 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
     switch (nch) { case 1: PB_LN_BWD(1); break; case 2: PB_LN_BWD(2); break; case 3: PB_LN_BWD(3); break; default: PB_LN_BWD(4); }
 #undef PB_LN_BWD
     PB_LAUNCH_CHECK();
-    if (partial) {
-        ReduceOut3 o;
-        o.out[0] = gamma ? (bf16*)dgamma : nullptr; o.out[1] = gamma ? (bf16*)dbeta : nullptr; o.out[2] = (bf16*)dbias_lin;
-        o.accumulate[0] = o.accumulate[1] = accumulate & 1; o.accumulate[2] = (accumulate >> 1) & 1;
-        dim3 rgrid((unsigned)((D + 31) / 32), 3);
-        PB_CUDA(launch_pdl(reduce_partials_multi_kernel, rgrid, dim3(256), 0, stream, (const float*)partial, grid, (long long)(3 * D), (int)D, o));
-        PB_LAUNCH_CHECK();
-    }
+    if (partial && !(accumulate & 4))
+        return pb200_ln_bwd_reduce(workspace, M, D, gamma ? dgamma : nullptr, gamma ? dbeta : nullptr, dbias_lin, accumulate, stream_);
+    return 0;
+}
+
+extern "C" int pb200_ln_bwd_reduce(const void* workspace, int64_t M, int64_t D, void* dgamma, void* dbeta, void* dbias_lin,
+                                   int32_t accumulate, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (M == 0) return 0;
+    PB_CHECK(workspace != nullptr, "LN backward reduce: null workspace");
+    ReduceOut3 o;
+    o.out[0] = (bf16*)dgamma; o.out[1] = (bf16*)dbeta; o.out[2] = (bf16*)dbias_lin;
+    o.accumulate[0] = o.accumulate[1] = accumulate & 1; o.accumulate[2] = (accumulate >> 1) & 1;
+    dim3 rgrid((unsigned)((D + 31) / 32), 3);
+    PB_CUDA(launch_pdl(reduce_partials_multi_kernel, rgrid, dim3(256), 0, stream, (const float*)workspace, ln_bwd_grid((int)M),
+                       (long long)(3 * D), (int)D, o));
+    PB_LAUNCH_CHECK();
     return 0;
 }
 

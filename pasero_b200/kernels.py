@@ -213,20 +213,32 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
                        dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False,
-                       dbias_lin: Optional[Tensor] = None, accumulate_lin: bool = False, keep_mask: Optional[Tensor] = None):
-    """dbias_lin (bf16 [D], optional) receives the column sums of dx = the bias gradient of the Linear that produced x."""
+                       dbias_lin: Optional[Tensor] = None, accumulate_lin: bool = False, keep_mask: Optional[Tensor] = None,
+                       side_run=None):
+    """dbias_lin (bf16 [D], optional) receives the column sums of dx = the bias gradient of the Linear that produced x.
+    side_run(fn, *keepalive): when given, the small kernel that reduces the CTA partials into dgamma / dbeta / dbias_lin is
+    handed to it (ops.WgradStream.run: another stream) together with its private partials buffer."""
     lib = _lib.load()
     M, D = dy.shape
     dev = dy.device
     dx = torch.empty(M, D, dtype=BF16, device=dev)
     dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
     need_ws = (gamma is not None and (dgamma is not None or dbeta is not None)) or dbias_lin is not None
-    ws = _ws(lib.pb200_ln_bwd_workspace_bytes(M, D), dev) if need_ws else None
+    defer = need_ws and side_run is not None
+    ws = None
+    if need_ws:   # deferred reduction: the buffer must outlive this call on the launching stream -> not the shared scratch
+        nbytes = lib.pb200_ln_bwd_workspace_bytes(M, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if defer else _ws(nbytes, dev)
     _count(2 if need_ws else 1)
+    flags = int(accumulate) | (int(accumulate_lin) << 1)
     check(lib.pb200_dropout_add_ln_bwd(dy.data_ptr(), ptr(dsum_extra), ptr(sum_), ptr(gamma), ptr(mean), ptr(rstd), M, D,
                                        p, seed, offset, ptr(RNG_OFFSET_BASE), ptr(dres), dx.data_ptr(), ptr(dgamma), ptr(dbeta),
-                                       ptr(dbias_lin), int(accumulate) | (int(accumulate_lin) << 1), ptr(keep_mask), ptr(ws),
+                                       ptr(dbias_lin), flags | (4 if defer else 0), ptr(keep_mask), ptr(ws),
                                        ws.numel() if ws is not None else 0, stream_ptr()))
+    if defer:
+        has_ln = gamma is not None
+        side_run(lambda: check(lib.pb200_ln_bwd_reduce(ws.data_ptr(), M, D, ptr(dgamma) if has_ln else None,
+                                                       ptr(dbeta) if has_ln else None, ptr(dbias_lin), flags, stream_ptr())), ws)
     return dx, dres
 
 

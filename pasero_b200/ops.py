@@ -365,8 +365,11 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=No
         if need_lin and lin_bias is not None:
             sl, al = _sink(lin_bias)
             dlin = sl if sl is not None else torch.empty(D, dtype=BF16, device=dy.device)
+        # every output is an arena sink (nothing is handed back to autograd): the partials' reduction can leave the chain
+        side = WgradStream.run if ((dgamma is None or sg is not None) and (dbeta is None or sb is not None)
+                                   and (dlin is None or sl is not None)) else None
         dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
-                                        accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep)
+                                        accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep, side_run=side)
         return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
     sg, ag = _sink(p_gamma)
     sb, ab = _sink(p_beta)
@@ -374,8 +377,9 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=No
     dgamma = sg if sg is not None else torch.empty(D, dtype=BF16, device=dy.device)
     dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
     dlin = sl if sl is not None else (torch.empty(D, dtype=BF16, device=dy.device) if lin_bias is not None else None)
+    side = WgradStream.run if (sg is not None and (dbeta is None or sb is not None) and (dlin is None or sl is not None)) else None
     dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
-                                    accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep)
+                                    accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep, side_run=side)
     return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
 
 
