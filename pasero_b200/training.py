@@ -129,6 +129,47 @@ class ParamArena:
                 p.grad = self.view(self.grad, i)
 
 
+class P2PAllreduce:
+    """Gradient allreduce over NVLink peer memory (csrc/comm.cu): every rank maps every other rank's bf16 gradient arena
+    and signal pad (CUDA IPC) once; a bucket is then reduced in place by ONE kernel launch with no host-side state, so
+    — unlike the NCCL call it replaces — it is captured in the step's CUDA graph and overlaps backward there as well.
+    Single node, <= 8 ranks, one process per GPU."""
+
+    def __init__(self, grad: Tensor, group=None):
+        import ctypes
+        lib = K._lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError('peer-memory allreduce covers one node (<= 8 ranks)')
+        self.grad = grad
+        self.signal = torch.zeros(lib.pb200_p2p_signal_bytes() // 4, dtype=torch.int32, device=grad.device)
+        torch.cuda.synchronize(grad.device)      # the zero-fill has landed before any peer can post a flag
+        mine = []
+        for t in (grad, self.signal):
+            handle, offset = ctypes.create_string_buffer(64), ctypes.c_int64()
+            K.check(lib.pb200_p2p_export(t.data_ptr(), handle, ctypes.byref(offset)))
+            mine.append((handle.raw, offset.value))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (os.uname().nodename, mine), group=group)
+        if len({host for host, _ in everyone}) != 1:
+            raise RuntimeError('peer-memory allreduce needs all ranks on one node')
+        self._data = (ctypes.c_void_p * 8)()
+        self._sig = (ctypes.c_void_p * 8)()
+        for r, (_, handles) in enumerate(everyone):
+            for arr, own, (handle, offset) in zip((self._data, self._sig), (grad, self.signal), handles):
+                if r == self.rank:
+                    arr[r] = own.data_ptr()
+                else:
+                    ptr = ctypes.c_void_p()
+                    K.check(lib.pb200_p2p_import(handle, offset, ctypes.byref(ptr)))
+                    arr[r] = ptr.value
+        dist.barrier(group)
+
+    def allreduce(self, lo: int, hi: int) -> None:
+        """grad[lo:hi] <- sum over ranks, in place, on the current stream."""
+        K.check(K._lib.load().pb200_allreduce_p2p(self._data, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
+
+
 class GradBuckets:
     """Bucketed allreduce of the gradient arena, overlapped with backward (replaces torch DDP's reducer,
     pasero/training.py:243-250). Buckets are contiguous arena slices of ~bucket_bytes, filled back to front."""
@@ -161,6 +202,7 @@ class GradBuckets:
         self.enabled = True
         self.launch_order = []
         self.pre_launch = None   # callable(bucket index) run on the compute stream before the bucket's allreduce
+        self.p2p = None          # P2PAllreduce: peer-memory kernel instead of the NCCL call (CUDA-graph capturable)
         self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i) if self.use_autograd_hooks else None)
@@ -183,7 +225,10 @@ class GradBuckets:
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                if self.p2p is not None:
+                    self.p2p.allreduce(lo, hi)
+                else:
+                    dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         self.pending[b] = -1
@@ -198,6 +243,10 @@ class GradBuckets:
         """Non-overlapped variant used between CUDA-graph segments: every bucket, then the step scalars."""
         self.pending = [0] * len(self.buckets)
         self.finish(stats)
+
+    def reduce_stats(self, stats: Tensor) -> None:
+        """The step scalars alone (NCCL, 32 bytes): after a graph whose buckets were reduced by captured P2P kernels."""
+        dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
 
     def finish(self, stats: Optional[Tensor] = None) -> None:
         """Flush buckets whose hooks never fired (unused parameters), reduce the step scalars, rejoin the stream."""
@@ -264,6 +313,21 @@ class Trainer:
         # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
         # (tools/ddp_check.py) but the processes hang at teardown / in long runs on this stack (NCCL 2.28.9, torch 2.11)
         self.graph_collectives = os.environ.get('PB200_GRAPH_NCCL', '0') == '1'
+        # Peer-memory allreduce (default when the ranks share a node): one capturable kernel per bucket, so the reductions
+        # are part of the step graph and overlap backward. Every rank must take the same decision: agree on it.
+        if self.buckets is not None and os.environ.get('PB200_P2P_ALLREDUCE', '1') != '0':
+            p2p, err = None, ''
+            try:
+                p2p = P2PAllreduce(self.arena.grad)
+            except Exception as e:  # noqa: BLE001  (no peer access / IPC, several nodes, > 8 ranks): NCCL stays
+                err = str(e)
+            ok = torch.tensor([1 if p2p is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self.buckets.p2p = p2p
+                self.graph_collectives = True
+            elif dist.get_rank() == 0:
+                print(f'pasero_b200: peer-memory allreduce unavailable ({err or "failed on another rank"}); using NCCL', flush=True)
         self.saved = True
 
     # ------------------------------------------------------------------ step pieces
@@ -377,6 +441,7 @@ class Trainer:
         key = tuple((k, tuple(v.shape)) for k, v in sorted(tensors.items()))
         key = key + tuple(sorted((k, v) for k, v in batch.items() if isinstance(v, (int, tuple))))
         self.model.train()
+        p2p_graph = self.buckets is not None and self.buckets.p2p is not None
         if key not in self._graphs:
             static = {}
             for k, v in tensors.items():
@@ -399,7 +464,7 @@ class Trainer:
                     static[k].copy_(v)
                 self._graph_body(static, extras)
                 if in_graph:
-                    self.buckets.finish(self.stats)
+                    self.buckets.finish(None if p2p_graph else self.stats)
                 # the warm-up pass accumulated real gradients into the fp32 main-gradient arena; with buckets they are only
                 # flushed (and zeroed) after the replay below, which would add this batch's gradient a second time
                 self.arena.grad32.zero_()
@@ -411,7 +476,7 @@ class Trainer:
             with torch.cuda.graph(graph):
                 self._graph_body(static, extras)
                 if in_graph:
-                    self.buckets.finish(self.stats)
+                    self.buckets.finish(None if p2p_graph else self.stats)
             self._graphs[key] = (graph, static)
         graph, static = self._graphs[key]
         for k, v in tensors.items():
@@ -421,6 +486,8 @@ class Trainer:
         self.rng_base += 1
         if self.buckets is not None and not self.graph_collectives:
             self.buckets.allreduce_all(self.stats)
+        elif p2p_graph:
+            self.buckets.reduce_stats(self.stats)   # the buckets were reduced inside the graph
         self._optimizer_kernels()
         return self._finish_step()
 
