@@ -313,9 +313,11 @@ class Trainer:
         # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
         # (tools/ddp_check.py) but the processes hang at teardown / in long runs on this stack (NCCL 2.28.9, torch 2.11)
         self.graph_collectives = os.environ.get('PB200_GRAPH_NCCL', '0') == '1'
-        # Peer-memory allreduce (default when the ranks share a node): one capturable kernel per bucket, so the reductions
-        # are part of the step graph and overlap backward. Every rank must take the same decision: agree on it.
-        if self.buckets is not None and os.environ.get('PB200_P2P_ALLREDUCE', '1') != '0':
+        # Peer-memory allreduce (PB200_P2P_ALLREDUCE=1): one capturable kernel per bucket, so the reductions are part of
+        # the step graph and overlap backward. EXPERIMENTAL, off by default: verified at N = 2 (tools/ddp_check.py: update
+        # == single-process accumulation, eager and graph; 9.41 -> 9.25 ms/step), but the one N = 8 run timed out and
+        # could not be diagnosed before the round's GPU budget ran out. Every rank must take the same decision: agree on it.
+        if self.buckets is not None and os.environ.get('PB200_P2P_ALLREDUCE', '0') == '1':
             p2p, err = None, ''
             try:
                 p2p = P2PAllreduce(self.arena.grad)
