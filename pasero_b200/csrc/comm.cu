@@ -24,10 +24,12 @@ namespace pb200 {
 static constexpr int P2P_MAX_RANKS = 8;
 static constexpr int P2P_BLOCKS = 32;        // co-resident with the GEMM CTAs (no dynamic shared memory): enough for NVLink
 static constexpr int P2P_THREADS = 512;
+static constexpr long long P2P_TIMEOUT_CYCLES = 20000000000LL;   // ~10 s at 1.9 GHz
 
 struct P2PDev {
     bf16* data[P2P_MAX_RANKS];               // every rank's gradient arena, as mapped in this process
     uint32_t* sig[P2P_MAX_RANKS];            // every rank's signal pad: [2][P2P_BLOCKS][P2P_MAX_RANKS] flags + [P2P_BLOCKS] generations
+                                             // + 1 word: number of barrier waits that timed out (a hang becomes an error)
     int rank, world;
 };
 
@@ -62,7 +64,13 @@ __device__ __forceinline__ void rank_barrier(const P2PDev& c, int phase, uint32_
         __threadfence_system();
         st_release_sys(flag_of(c.sig[peer], phase, blockIdx.x, c.rank), gen);
         const uint32_t* mine = flag_of(c.sig[c.rank], phase, blockIdx.x, peer);
-        while ((int32_t)(ld_acquire_sys(mine) - gen) < 0) { }
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - gen) < 0) {
+            if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {   // a peer never arrived: give up instead of hanging the GPU
+                atomicAdd(c.sig[c.rank] + 2 * P2P_BLOCKS * P2P_MAX_RANKS + P2P_BLOCKS, 1u);
+                break;
+            }
+        }
     }
     __syncthreads();
 }
@@ -115,7 +123,7 @@ typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 using namespace pb200;
 
 extern "C" size_t pb200_p2p_signal_bytes(void) {
-    return (size_t)(2 * P2P_BLOCKS * P2P_MAX_RANKS + P2P_BLOCKS) * sizeof(uint32_t);
+    return (size_t)(2 * P2P_BLOCKS * P2P_MAX_RANKS + P2P_BLOCKS + 1) * sizeof(uint32_t);
 }
 
 // IPC handle (64 bytes) of the allocation that holds `ptr`, and ptr's byte offset inside it

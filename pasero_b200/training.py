@@ -165,6 +165,11 @@ class P2PAllreduce:
                     arr[r] = ptr.value
         dist.barrier(group)
 
+    def timeouts(self) -> int:
+        """Barrier waits that gave up (~10 s) since start-up; non-zero means a peer never arrived and the gradients of that
+        step are not to be trusted (synchronises)."""
+        return int(self.signal[-1].item())
+
     def allreduce(self, lo: int, hi: int) -> None:
         """grad[lo:hi] <- sum over ranks, in place, on the current stream."""
         K.check(K._lib.load().pb200_allreduce_p2p(self._data, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
