@@ -2,13 +2,16 @@
 Dictionary ids, NumpyFile feature container, sample binarisation, length bucketing and collation.
 
 Mirrors pasero/preprocessing.py:45-236 (Dictionary), pasero/files.py:103-192 (NumpyFile),
-pasero/tasks/speech_translation.py:42-86 (preprocess), pasero/tasks/task.py:531-610 (collate, build_batches),
+pasero/tasks/speech_translation.py:42-86 and pasero/tasks/translation.py:343-540 (preprocess, language-code / domain
+tags), pasero/preprocessing.py:239-269 (tag helpers), pasero/tasks/task.py:531-610 (collate, build_batches),
 pasero/utils.py:709-736, 783-843 (tokens_as_tensor, build_batches), pasero/datasets.py:708-730 (buffered_batching).
 The numpy global RNG is consumed in the same order as the reference, so seeded runs produce identical batches.
 """
 import collections
+import itertools
 import os
 import pickle
+import re
 from typing import Callable, Iterable, Optional
 
 import numpy as np
@@ -63,6 +66,31 @@ class Dictionary:
         if append_eos:
             ids.append(self.eos_idx)
         return np.array(ids, dtype=np.int64)
+
+
+# ---- language-code / domain tags (pasero/preprocessing.py:239-269) ----
+_LANG_CODE_REGEX = re.compile(r'<lang:(.+?)>')
+_DOMAIN_TAG_REGEX = re.compile(r'<domain:(.+?)>')
+
+
+def get_lang_code(lang: Optional[str]) -> Optional[str]:
+    return f'<lang:{lang}>' if lang else None
+
+
+def get_domain_tag(domain: Optional[str]) -> Optional[str]:
+    return f'<domain:{domain}>' if domain else None
+
+
+def is_tag(token: str) -> bool:
+    return bool(_LANG_CODE_REGEX.fullmatch(token) or _DOMAIN_TAG_REGEX.fullmatch(token))
+
+
+def split_tags(line: str) -> list:
+    """[tag, ..., rest]: the leading tags of a line that already carries some, and the line without them."""
+    tags = list(itertools.takewhile(is_tag, line.split()))
+    for tag in tags:   # strip this tag and the blanks around it only (the line may span several lines)
+        line = re.sub(rf'\s*{re.escape(tag)}\s*', '', line, count=1)
+    return [*tags, line]
 
 
 class NumpyFile:
@@ -180,7 +208,12 @@ class SpeechTranslationTask:
     def __init__(self, cfg: TrainingConfig, dictionary: Dictionary, target_tags: tuple = ()):
         self.cfg = cfg
         self.dictionary = dictionary
-        self.target_tags = tuple(target_tags)
+        self.target_tags = tuple(target_tags)   # always prepended (pre-tokenised pipelines that carry their own tags)
+        # tag options of TranslationTaskConfig (pasero/config.py:1940-1960), read from the flat config
+        opt = cfg.extra.get
+        self.lang_code, self.source_lang_code = bool(opt('lang_code')), bool(opt('source_lang_code'))
+        self.target_lang_code, self.domain_tag = bool(opt('target_lang_code')), bool(opt('domain_tag'))
+        self.cfg_source_tags, self.cfg_target_tags = list(opt('source_tags') or ()), list(opt('target_tags') or ())
         self.prepend_bos = True
         self.max_source_len = cfg.max_source_len
         self.max_target_len = cfg.max_target_len
@@ -219,6 +252,40 @@ class SpeechTranslationTask:
             return values('source_lang') | values('target_lang')
         return values(key)
 
+    def get_source_tags(self, meta: dict) -> list:
+        """Tags prepended to SOURCE lines (pasero/tasks/translation.py:369-388): configured tags, the TARGET language code
+        when `lang_code`, the source language code, the domain tag."""
+        tags = list(meta.get('source_tags') or self.cfg_source_tags)
+        if self.lang_code:
+            assert meta.get('target_lang'), 'missing target language information'
+            tags.append(get_lang_code(meta.get('target_lang')))
+        if self.source_lang_code:
+            assert meta.get('source_lang'), 'missing source language information'
+            tags.append(get_lang_code(meta.get('source_lang')))
+        if self.domain_tag:
+            tags.append(get_domain_tag(meta.get('domain')))
+        return [t for t in tags if t]
+
+    def get_target_tags(self, meta: dict) -> list:
+        """Tags prepended to TARGET lines and excluded from the loss through the prompt mask (translation.py:390-403)."""
+        tags = list(meta.get('target_tags') or self.cfg_target_tags)
+        if self.target_lang_code:
+            assert meta.get('target_lang'), 'missing target language information'
+            tags.append(get_lang_code(meta.get('target_lang')))
+        return [t for t in tags if t]
+
+    def check_tags(self) -> None:
+        """Every tag this configuration can emit is in the dictionary (translation.py:343-367)."""
+        need = []
+        if self.domain_tag:
+            need += [get_domain_tag(d) for d in self.get_langs_or_domains('domain')]
+        if self.source_lang_code:
+            need += [get_lang_code(lang) for lang in self.get_langs_or_domains('source_lang')]
+        if self.lang_code or self.target_lang_code:
+            need += [get_lang_code(lang) for lang in self.get_langs_or_domains('target_lang')]
+        for tag in need:
+            assert tag in self.dictionary.indices, f'{tag} is OOV'
+
     def should_skip(self, source_len: int, target_len: int) -> bool:
         ratio = source_len / max(1, target_len)
         return bool(source_len == 0 or source_len > self.max_source_len or target_len > self.max_target_len or
@@ -227,14 +294,30 @@ class SpeechTranslationTask:
     def preprocess(self, sample: dict, truncate: bool = False, tokenize: bool = False, append_eos: bool = False) -> dict:
         """pasero/tasks/speech_translation.py:42-86 with pre-tokenised targets (BPE itself is CPU string work that
         stays with the reference's tokenizers): features pass through, target -> ids with BOS/EOS, prompt mask."""
-        if tokenize:
-            raise NotImplementedError('subword tokenisation is outside the hot path; pass BPE-split targets')
-        source, target, meta = sample['source'], sample['target'], sample.get('meta', {})
+        source, target, meta = sample['source'], sample['target'], sample.get('meta') or {}
         source_cutoff = self.max_source_len if truncate else None
         target_cutoff = self.max_target_len if truncate else None
+        text_source = isinstance(source, str)     # `--task translation`: the source is a line of text too
+        # `tokenize` keeps the reference's meaning for the tags — they are added only then (translation.py:450-452; the
+        # speech task always adds the target tags, speech_translation.py:56-58) — but the subword split itself is CPU
+        # string work that stays with the reference's tokenizers: lines arrive BPE-split and are split on blanks here.
         tags = list(self.target_tags)
-        encoder_input = source[:source_cutoff]
-        target_tok = tags + (target.split() if target is not None else [])
+        src_tags = []
+        if text_source:
+            *src_tags, source = split_tags(source)
+            if target is not None:
+                *pre, target = split_tags(target)
+                tags += pre
+            if tokenize:
+                src_tags += self.get_source_tags(meta)
+                tags += self.get_target_tags(meta)
+            # (without `tokenize` the reference drops even the tags the source line carried: translation.py:461)
+            source_tok = src_tags + source.split() if tokenize else source.split()
+            encoder_input = self.dictionary.to_indices(source_tok, max_len=source_cutoff, prepend_bos=False, append_eos=True)
+        else:
+            tags += self.get_target_tags(meta)
+            encoder_input = source[:source_cutoff]
+        target_tok = tags + (target.split() if target else [])
         decoder_input = self.dictionary.to_indices(target_tok, max_len=target_cutoff, prepend_bos=self.prepend_bos,
                                                    append_eos=append_eos)
         prompt_mask = np.zeros_like(decoder_input, dtype=bool)

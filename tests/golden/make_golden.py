@@ -162,6 +162,106 @@ def golden_model_text(pasero, tmp, out):
     print('text model golden: loss', loss.item(), logs)
 
 
+def golden_preprocess_tags(pasero, tmp, out):
+    """`TranslationTask.preprocess` / `SpeechTranslationTask.preprocess` with language-code and domain tags
+    (pasero/tasks/translation.py:369-540, speech_translation.py:42-86; `lang_code: True` is what the TED-top20 recipe of
+    BASELINE config 5 trains with). The fixture carries the dictionary, the BPE-split lines (subword splitting stays with
+    the reference's tokenizer) and the arrays the reference produced from them."""
+    import json
+    from pasero.config import TrainingConfig, get_task_class
+    from pasero.preprocessing import split_tags
+    lines = [('Guten Morgen , wie geht es Ihnen heute ?', 'Good morning , how are you today ?'),
+             ('Das ist ein kleiner Test .', 'This is a small test .'),
+             ('<lang:en> Hallo Welt', '<lang:en> <domain:ted> Hello world'),
+             ('Eine sehr lange Zeile ' + 'mit vielen Worten ' * 6, 'A very long line ' + 'with many words ' * 6),
+             ('Ja', 'Yes indeed it is')]
+    d = os.path.join(tmp, 'tags')
+    os.makedirs(d, exist_ok=True)
+    shutil.copy(os.path.join(REF, 'examples/TED/de-en/bpecodes'), os.path.join(d, 'bpecodes'))
+
+    def make(task_name, flags, dict_tokens):
+        with open(os.path.join(d, 'dict.txt'), 'w') as f:
+            for tok in dict_tokens:
+                f.write(f'{tok} 1\n')
+        args = ['--task', task_name, '--arch', 'transformer', '--data-dir', d, '--dict', 'dict.txt', '--tokenizer-path', 'bpecodes',
+                '--source-lang', 'de', '--target-lang', 'en', '--model-dir', os.path.join(d, 'model'), '--metrics',
+                '--early-stopping-metric', 'nll_loss', '--dataset-type', 'simple', '--dtype', 'float32', '--max-steps', '1000',
+                '--valid-interval', '1000', '--batch-size', '4000'] + list(flags)
+        if task_name == 'speech_translation':
+            args += ['--input-dim', '80', '--conv-input-dim', '80', '--conv-channels', '64', '--conv-kernel-sizes', '5', '5',
+                     '--encoder-max-len', '3000']
+        cfg = TrainingConfig(*args)
+        task = get_task_class(cfg.task)(cfg.data_dir, cfg.task_cfg)
+        task.setup_for_model(cfg.model_cfg)
+        return cfg, task
+
+    # vocabulary = the subwords of the lines above (minus a few, to exercise <unk>) + the tags
+    with open(os.path.join(REF, 'examples/TED/de-en/dict.txt')) as f:
+        real_vocab = [line.split()[0] for line in f if line.strip()]
+    _, probe = make('translation', [], real_vocab)
+    subwords = []
+    for src, tgt in lines:
+        for side, text in (('src', src), ('tgt', tgt)):
+            *_, rest = split_tags(text)
+            for tok in (probe.src_preprocessor if side == 'src' else probe.tgt_preprocessor).tokenize(rest):
+                if tok not in subwords:
+                    subwords.append(tok)
+    dropped = subwords[3::11]
+    tags = ['<lang:de>', '<lang:en>', '<lang:fr>', '<domain:ted>', '<domain:news>']
+    dict_tokens = [t for t in subwords if t not in dropped] + tags
+
+    configs = {
+        'lang_code': ['--lang-code'],
+        'both_codes': ['--source-lang-code', '--target-lang-code'],
+        'domain_and_cfg_tags': ['--domain-tag', '--target-tags', '<lang:fr>', '--source-tags', '<domain:news>'],
+        'plain': [],
+        'short': ['--lang-code', '--target-lang-code', '--max-source-len', '7', '--max-target-len', '6'],
+    }
+    metas = [{'source_lang': 'de', 'target_lang': 'en', 'domain': 'ted'},
+             {'source_lang': 'de', 'target_lang': 'en', 'domain': 'ted', 'target_tags': ['<domain:ted>', '<lang:en>']}]
+    cases = []
+    for name, flags in configs.items():
+        for task_name in ('translation', 'speech_translation'):
+            cfg, task = make(task_name, flags, dict_tokens)
+            for li, (src, tgt) in enumerate(lines):
+                for meta in metas:
+                    for tokenize, truncate in ((True, False), (False, False), (True, True)):
+                        *src_tags, src_rest = split_tags(src)
+                        *tgt_tags, tgt_rest = split_tags(tgt)
+                        if task_name == 'speech_translation':
+                            frames = 20 + 13 * li
+                            source_ref = np.zeros((frames, 80), dtype=np.float16)
+                            tgt_text, tgt_pre = tgt_rest, ' '.join(task.tgt_preprocessor.tokenize(tgt_rest))
+                            if not tokenize:
+                                tgt_text = tgt_pre     # tokenize=False: the reference splits the given line on blanks
+                            res = task.preprocess({'source': source_ref, 'target': tgt_text, 'meta': dict(meta)},
+                                                  truncate=truncate, tokenize=tokenize, append_eos=True)
+                            case = {'task': task_name, 'config': name, 'flags': flags, 'meta': meta, 'tokenize': tokenize,
+                                    'truncate': truncate, 'frames': frames, 'target_bpe': tgt_pre}
+                            if res:
+                                case['encoder_len'] = int(len(res['encoder_input']))
+                        else:
+                            src_pre = ' '.join(src_tags + task.src_preprocessor.tokenize(src_rest))
+                            tgt_pre = ' '.join(tgt_tags + task.tgt_preprocessor.tokenize(tgt_rest))
+                            s_in, t_in = (src, tgt) if tokenize else (src_pre, tgt_pre)
+                            res = task.preprocess({'source': s_in, 'target': t_in, 'meta': dict(meta)},
+                                                  truncate=truncate, tokenize=tokenize, append_eos=True)
+                            case = {'task': task_name, 'config': name, 'flags': flags, 'meta': meta, 'tokenize': tokenize,
+                                    'truncate': truncate, 'source_bpe': src_pre, 'target_bpe': tgt_pre}
+                            if res:
+                                case['encoder_input'] = res['encoder_input'].tolist()
+                        case['skipped'] = not res
+                        if res:
+                            case['decoder_input'] = res['decoder_input'].tolist()
+                            case['prompt_mask'] = res['prompt_mask'].astype(int).tolist()
+                        case['max_source_len'] = int(task.max_source_len)
+                        case['max_target_len'] = int(task.max_target_len)
+                        cases.append(case)
+    with open(os.path.join(out, 'preprocess_tags.json'), 'w') as f:
+        json.dump({'dict_tokens': dict_tokens, 'cases': cases}, f)
+    print('preprocess/tags golden:', len(cases), 'cases,', sum(c['skipped'] for c in cases), 'skipped,', len(dict_tokens), 'dictionary tokens')
+
+
 def golden_model_whisper(pasero, cfg, task, model, out):
     model.train()
     batch = synth.model_batch()
@@ -327,6 +427,13 @@ def main():
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'tags':         # only the preprocess / tags fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            golden_preprocess_tags(pasero, tmp, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'adapters':     # only the adapter fixture
         tmp = tempfile.mkdtemp()
         try:
@@ -355,6 +462,7 @@ def main():
         golden_model_whisper(pasero, cfg3, task3, model3, out)
         golden_model_adapters(pasero, tmp, out)
         golden_model_text(pasero, tmp, out)
+        golden_preprocess_tags(pasero, tmp, out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

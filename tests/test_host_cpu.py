@@ -113,6 +113,63 @@ def test_preprocess_and_skip():
     assert len(t['encoder_input']) == 100 and len(t['decoder_input']) == 6 and t['decoder_input'][-1] == 2
 
 
+def test_preprocess_tags_bit_exact_with_reference():
+    """Language-code / domain tags (`lang_code: True` of the TED-top20 recipe, `source_lang_code`, `target_lang_code`,
+    `domain_tag`, configured and per-line tags, lines that already carry tags) for the text and the speech task:
+    encoder ids, decoder ids and prompt masks equal the arrays the reference's `preprocess` produced
+    (tests/golden/make_golden.py: golden_preprocess_tags). Subword splitting stays with the reference's tokenizer: the
+    fixture carries the BPE-split lines."""
+    import json
+    with open(os.path.join(GOLD, 'preprocess_tags.json')) as f:
+        g = json.load(f)
+    d = Dictionary(tokens=g['dict_tokens'])
+    tasks = {}
+    n_checked = 0
+    for c in g['cases']:
+        key = (c['task'], c['config'])
+        if key not in tasks:
+            opts = {}
+            flags = list(c['flags'])
+            while flags:
+                name = flags.pop(0)[2:].replace('-', '_')
+                vals = []
+                while flags and not flags[0].startswith('--'):
+                    vals.append(flags.pop(0))
+                opts[name] = (True if not vals else (int(vals[0]) if vals[0].isdigit() else vals))
+            kw = {k: opts.pop(k) for k in ('max_source_len', 'max_target_len') if k in opts}
+            if c['task'] == 'translation':
+                kw.update(encoder_max_len=256, input_dim=None, conv_input_dim=None)
+                cfg = tiny_training_cfg(task='translation', **kw, **opts)
+                task = SpeechTranslationTask.text(cfg, d)
+            else:
+                cfg = tiny_training_cfg(**kw, **opts)
+                task = SpeechTranslationTask(cfg, d)
+            assert (task.max_source_len, task.max_target_len) == (c['max_source_len'], c['max_target_len'])
+            tasks[key] = task
+        task = tasks[key]
+        if c['task'] == 'translation':
+            source = c['source_bpe']
+        else:
+            source = np.zeros((c['frames'], 80), dtype=np.float16)
+        out = task.preprocess({'source': source, 'target': c['target_bpe'], 'meta': dict(c['meta'])},
+                              truncate=c['truncate'], tokenize=c['tokenize'], append_eos=True)
+        assert (not out) == c['skipped'], c
+        if out:
+            if c['task'] == 'translation':
+                assert out['encoder_input'].tolist() == c['encoder_input'], c
+            else:
+                assert len(out['encoder_input']) == c['encoder_len']
+            assert out['decoder_input'].tolist() == c['decoder_input'], c
+            assert out['prompt_mask'].astype(int).tolist() == c['prompt_mask'], c
+            n_checked += 1
+    assert n_checked > 200
+    # every tag the configuration can emit must be in the dictionary (translation.py:343-367)
+    cfg = tiny_training_cfg(lang_code=True, target_langs=['en', 'xx'])
+    with pytest.raises(AssertionError, match='OOV'):
+        SpeechTranslationTask(cfg, d).check_tags()
+    SpeechTranslationTask(tiny_training_cfg(lang_code=True, domain_tag=True, target_lang='en', domain='ted'), d).check_tags()
+
+
 def test_numpy_file_roundtrip(tmp_path):
     rng = np.random.RandomState(0)
     feats = [rng.randn(n, 80).astype(np.float32) for n in (5, 17, 1)]
