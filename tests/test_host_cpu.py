@@ -205,6 +205,33 @@ def test_state_dict_keys_match_reference():
     assert sorted(layout['model_3.bin']['model']) == sorted(sd.keys())
 
 
+def test_params_regex_matches_reference_names():
+    """--train-params-regex / --freeze-params-regex act on the reference's parameter names (cli/train.py:230-242), also
+    where this package stores several of them in one tensor."""
+    from pasero_b200 import reference_param_names
+    task = tiny_task()
+    model = build_model(tiny_training_cfg(), task)
+    names = reference_param_names(model)
+    ref_keys = {k for refs in names.values() for k in refs}
+    import json
+    with open(os.path.join(GOLD, 'checkpoint_layout.json')) as f:
+        layout = json.load(f)
+    want = {k for k in layout['model_3.bin']['model'] if '_float_tensor' not in k}
+    assert ref_keys == want, (sorted(ref_keys - want)[:5], sorted(want - ref_keys)[:5])
+    fused = [refs for refs in names.values() if len(refs) == 3]
+    assert fused and all({r.split('.')[-2] for r in refs} == {'k_proj', 'v_proj', 'q_proj'} for refs in fused)
+
+    model = build_model(tiny_training_cfg(train_params_regex=r'.*(layer_norm|fc1|self_attn\.[kvq]_proj)\.'), task)
+    for name, p in model.named_parameters():
+        ref = names[name][0]
+        assert p.requires_grad == bool(re.match(r'.*(layer_norm|fc1|self_attn\.[kvq]_proj)\.', ref)), (name, ref)
+    assert any(p.requires_grad for p in model.parameters()) and not all(p.requires_grad for p in model.parameters())
+    model = build_model(tiny_training_cfg(freeze_params_regex=r'encoder\.'), task)
+    assert all(p.requires_grad != n.startswith('encoder.') for n, p in model.named_parameters())
+    with pytest.raises(NotImplementedError):   # a regex that cuts a fused projection apart
+        build_model(tiny_training_cfg(train_params_regex=r'.*q_proj'), task)
+
+
 def test_config_surface():
     cfg = TrainingConfig.from_dict({'task': 'speech_translation', 'arch': 'transformer', 'encoder_layers': 12,
                                     'input_dim': 80, 'conv_input_dim': 80, 'conv_channels': 1024, 'conv_kernel_sizes': [5, 5],
