@@ -197,8 +197,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'   # NCCL prints its version banner on stdout; stdout carries ONE JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            del os.environ['NCCL_DEBUG']        # at these levels NCCL prints its version banner on stdout, which carries ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     assert world == max(1, args.gpus), f'--gpus {args.gpus} but WORLD_SIZE={world}'
     W = max(3, args.warmup)
