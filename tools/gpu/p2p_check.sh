@@ -1,0 +1,8 @@
+#!/bin/bash
+# gpurun --gpus N -- 'bash tools/gpu/p2p_check.sh N': stand-alone check of the peer-memory allreduce kernel (bounded)
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 \
+    tools/p2p_check.py > gpurun_out/p2p_check_n$N.log 2>&1
+echo "p2p_check N=$N rc=$?"
+grep -v "^\*\*\*\|OMP_NUM" gpurun_out/p2p_check_n$N.log | tail -20
