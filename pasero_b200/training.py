@@ -66,7 +66,9 @@ class LRScheduler:
 class ParamArena:
     """Flat storage for parameters (bf16), gradients (bf16) and Adam moments (fp32); parameters become views."""
 
-    def __init__(self, model: torch.nn.Module, device):
+    def __init__(self, model: torch.nn.Module, device, grad_factory=None):
+        """grad_factory(numel) -> zeroed bf16 tensor: lets the Trainer place the gradient arena in memory that other ranks
+        can map (P2PAllreduce with symmetric memory); default: the caching allocator."""
         self.params, self.names, self.offsets = [], [], []
         seen = set()
         off = 0
@@ -80,7 +82,7 @@ class ParamArena:
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
         self.param = torch.zeros(off, dtype=BF16, device=device)
-        self.grad = torch.zeros(off, dtype=BF16, device=device)
+        self.grad = torch.zeros(off, dtype=BF16, device=device) if grad_factory is None else grad_factory(off)
         # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
         # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
         self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
@@ -133,7 +135,22 @@ class P2PAllreduce:
     """Gradient allreduce over NVLink peer memory (csrc/comm.cu): every rank maps every other rank's bf16 gradient arena
     and signal pad (CUDA IPC) once; a bucket is then reduced in place by ONE kernel launch with no host-side state, so
     — unlike the NCCL call it replaces — it is captured in the step's CUDA graph and overlaps backward there as well.
-    Single node, <= 8 ranks, one process per GPU."""
+    Single node, <= 8 ranks, one process per GPU.
+
+    Two ways to obtain the peer mappings (PB200_P2P_MAP): 'ipc' (default) exports the caching allocator's blocks with legacy
+    CUDA IPC (cudaIpcOpenMemHandle: every process then owns a context on each peer GPU); 'symm' uses torch's symmetric
+    memory (cuMem handles exchanged by its rendezvous; the gradient arena must then come from `symmetric_empty`)."""
+
+    @staticmethod
+    def mapping() -> str:
+        return os.environ.get('PB200_P2P_MAP', 'ipc')
+
+    @staticmethod
+    def symmetric_empty(numel: int, dtype, device) -> Tensor:
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(numel, dtype=dtype, device=device)
+        t.zero_()
+        return t
 
     def __init__(self, grad: Tensor, group=None):
         import ctypes
@@ -142,7 +159,21 @@ class P2PAllreduce:
         if self.world > 8:
             raise RuntimeError('peer-memory allreduce covers one node (<= 8 ranks)')
         self.grad = grad
-        self.signal = torch.zeros(lib.pb200_p2p_signal_bytes() // 4, dtype=torch.int32, device=grad.device)
+        words = lib.pb200_p2p_signal_bytes() // 4
+        self._data = (ctypes.c_void_p * 8)()
+        self._sig = (ctypes.c_void_p * 8)()
+        if self.mapping() == 'symm':
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = group if group is not None else dist.group.WORLD
+            self.signal = self.symmetric_empty(words, torch.int32, grad.device)
+            torch.cuda.synchronize(grad.device)
+            self._handles = (symm_mem.rendezvous(grad, pg), symm_mem.rendezvous(self.signal, pg))   # kept alive: they own the mappings
+            for arr, own, handle in zip((self._data, self._sig), (grad, self.signal), self._handles):
+                for r in range(self.world):
+                    arr[r] = own.data_ptr() if r == self.rank else int(handle.buffer_ptrs[r]) + int(handle.offset)
+            dist.barrier(group)
+            return
+        self.signal = torch.zeros(words, dtype=torch.int32, device=grad.device)
         torch.cuda.synchronize(grad.device)      # the zero-fill has landed before any peer can post a flag
         mine = []
         for t in (grad, self.signal):
@@ -153,8 +184,6 @@ class P2PAllreduce:
         dist.all_gather_object(everyone, (os.uname().nodename, mine), group=group)
         if len({host for host, _ in everyone}) != 1:
             raise RuntimeError('peer-memory allreduce needs all ranks on one node')
-        self._data = (ctypes.c_void_p * 8)()
-        self._sig = (ctypes.c_void_p * 8)()
         for r, (_, handles) in enumerate(everyone):
             for arr, own, (handle, offset) in zip((self._data, self._sig), (grad, self.signal), handles):
                 if r == self.rank:
@@ -283,7 +312,10 @@ class Trainer:
         self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)
         model.to(self.dtype)
         model.to(self.device)
-        self.arena = ParamArena(model, self.device)
+        # (experimental peer-memory allreduce with symmetric memory: the gradient arena has to be allocated there)
+        symm = (self.distributed and os.environ.get('PB200_P2P_ALLREDUCE', '0') == '1' and P2PAllreduce.mapping() == 'symm')
+        self.arena = ParamArena(model, self.device,
+                                (lambda n: P2PAllreduce.symmetric_empty(n, BF16, self.device)) if symm else None)
         self.param_names = list(self.arena.names)
         if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.arena.param, src=0)

@@ -6,3 +6,7 @@ timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     tools/p2p_check.py > gpurun_out/p2p_check_n$N.log 2>&1
 echo "p2p_check N=$N rc=$?"
 grep -v "^\*\*\*\|OMP_NUM" gpurun_out/p2p_check_n$N.log | tail -20
+PB200_P2P_MAP=symm timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 \
+    tools/p2p_check.py > gpurun_out/p2p_check_symm_n$N.log 2>&1
+echo "p2p_check (symmetric memory) N=$N rc=$?"
+grep -v "^\*\*\*\|OMP_NUM" gpurun_out/p2p_check_symm_n$N.log | tail -20

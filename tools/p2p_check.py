@@ -3,7 +3,8 @@
 Each rank fills a bf16 buffer with rank-dependent values, reduces buckets of several sizes in place with
 pb200_allreduce_p2p (eagerly and from a captured CUDA graph) and compares with NCCL's allreduce of the same data; then
 times both. Every wait in the kernel gives up after ~10 s (P2PAllreduce.timeouts()), so a missing peer shows up as an
-error line, not as a hung box. Run it under `timeout` all the same."""
+error line, not as a hung box. Run it under `timeout` all the same. PB200_P2P_MAP=symm selects torch symmetric memory
+(cuMem handles) instead of legacy CUDA IPC for the peer mappings."""
 import os
 import sys
 import time
@@ -22,10 +23,10 @@ def main():
     n = 70_000_000
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     src = (torch.randn(n, device=dev, generator=g) * 0.01).to(torch.bfloat16)
-    buf = torch.empty_like(src)
+    buf = (P2PAllreduce.symmetric_empty(n, torch.bfloat16, dev) if P2PAllreduce.mapping() == 'symm' else torch.empty_like(src))
     t0 = time.time()
     comm = P2PAllreduce(buf)
-    print(f'[{rank}] peer mapping done in {time.time() - t0:.2f} s', flush=True)
+    print(f'[{rank}] peer mapping ({P2PAllreduce.mapping()}) done in {time.time() - t0:.2f} s', flush=True)
     ok = True
     for lo, hi in ((0, 8), (8, 8 * 1001), (4096, 4096 + 12_500_000), (0, n)):
         buf.copy_(src)
