@@ -236,6 +236,7 @@ class GradBuckets:
         self.enabled = True
         self.launch_order = []
         self.pre_launch = None   # callable(bucket index) run on the compute stream before the bucket's allreduce
+        self.pre_all = None      # callable() doing the same for the whole arena at once (allreduce_all)
         self.p2p = None          # P2PAllreduce: peer-memory kernel instead of the NCCL call (CUDA-graph capturable)
         self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
         for i, p in enumerate(arena.params):
@@ -274,9 +275,27 @@ class GradBuckets:
         self.launch_order = []
 
     def allreduce_all(self, stats: Optional[Tensor] = None) -> None:
-        """Non-overlapped variant used between CUDA-graph segments: every bucket, then the step scalars."""
-        self.pending = [0] * len(self.buckets)
-        self.finish(stats)
+        """Non-overlapped variant used between the step's CUDA graph and the optimizer kernels. Nothing runs next to these
+        reductions, so buckets buy nothing here: ONE allreduce over the whole arena (a single large message, one launch)
+        and the step scalars behind it."""
+        if self.pre_all is not None:
+            self.pre_all()
+        elif self.pre_launch is not None:
+            for b in range(len(self.buckets)):
+                self.pre_launch(b)
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM, group=self.group)
+                if stats is not None:
+                    dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream().wait_stream(self.stream)
+        else:
+            dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM, group=self.group)
+            if stats is not None:
+                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+        self.pending = [-1] * len(self.buckets)
+        self.launch_order = list(range(len(self.buckets)))
 
     def reduce_stats(self, stats: Tensor) -> None:
         """The step scalars alone (NCCL, 32 bytes): after a graph whose buckets were reduced by captured P2P kernels."""
@@ -333,6 +352,7 @@ class Trainer:
             self.buckets.use_autograd_hooks = False
             bucket_ranges = [self.arena.ranges32(lo, hi) for lo, hi in self.buckets.buckets]
             self.buckets.pre_launch = lambda b: self.arena.flush32(bucket_ranges[b])
+            self.buckets.pre_all = lambda: self.arena.flush32(self._ranges32_all)
         self.scheduler = LRScheduler(cfg)
         self.optimizer_steps = 0     # Adam's state['step']
         self.steps = 0

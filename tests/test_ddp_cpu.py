@@ -60,6 +60,23 @@ def _worker(rank: int, world: int, port: int, q):
         assert stats[:4].tolist() == [10.0 * 3, 10.0, 201.0, 8.0]
         # buckets complete in reverse-layer order (the last bucket holds the last parameters)
         assert launched_before_finish == sorted(launched_before_finish)
+        # graph mode: one allreduce over the whole arena between the step graph and the optimizer (allreduce_all)
+        flushed = []
+        buckets.pre_all = lambda: flushed.append('all')
+        buckets.start_step(sync=False)
+        for i in range(len(arena.params)):
+            arena.view(arena.grad, i).fill_(0.0 if arena.names[i] == 'unused' else float(2 * rank + 1))
+            buckets.param_ready(i)                       # disabled inside the graph: nothing is launched
+        assert buckets.launch_order == []
+        stats = torch.tensor([1.0 + rank, 2.0, 3.0, 4.0, 0, 0, 0, 0], dtype=torch.float64)
+        buckets.allreduce_all(stats)
+        expect = float(sum(2 * r + 1 for r in range(world)))
+        for i, name in enumerate(arena.names):
+            g = arena.view(arena.grad, i).float()
+            assert torch.all(g == (0.0 if name == 'unused' else expect)), (name, g.unique())
+        assert stats[:4].tolist() == [3.0, 4.0, 6.0, 8.0] and flushed == ['all']
+        assert sorted(buckets.launch_order) == list(range(len(buckets.buckets)))
+        buckets.pre_all = None
         # no_sync micro-batch: nothing is reduced
         buckets.start_step(sync=False)
         arena.grad.fill_(float(rank))
