@@ -170,6 +170,20 @@ def test_preprocess_tags_bit_exact_with_reference():
     SpeechTranslationTask(tiny_training_cfg(lang_code=True, domain_tag=True, target_lang='en', domain='ted'), d).check_tags()
 
 
+def test_fbank_plan_offsets_match_oracle_frame_counts():
+    """Host side of the frontend: frame counts (snip_edges, 25 ms / 10 ms at 16 kHz) and the concatenated-batch offsets
+    of a ragged batch, including utterances shorter than one window (0 frames)."""
+    from oracle import fbank as of
+    from pasero_b200 import frontend
+    lengths = [160000, 400, 399, 0, 16000, 480000, 561, 560, 559]
+    plan = frontend.FbankPlan(lengths, 'cpu')
+    want = [of.num_frames(n) for n in lengths]
+    assert plan.frames == want == [998, 1, 0, 0, 98, 2998, 2, 2, 1]
+    assert plan.sample_offsets.tolist() == np.concatenate([[0], np.cumsum(lengths)]).tolist()
+    assert plan.frame_offsets.tolist() == np.concatenate([[0], np.cumsum(want)]).tolist()
+    assert (plan.batch, plan.max_frames, plan.total_frames, plan.total_samples) == (9, 2998, sum(want), sum(lengths))
+
+
 def test_numpy_file_roundtrip(tmp_path):
     rng = np.random.RandomState(0)
     feats = [rng.randn(n, 80).astype(np.float32) for n in (5, 17, 1)]
