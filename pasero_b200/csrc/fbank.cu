@@ -389,6 +389,160 @@ fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sam
     }
 }
 
+// v3 (experimental, PB200_FBANK=v3): v2 with a leaner shared-memory footprint — the power spectrum reuses the transpose
+// tile, the log-mel rows go straight to global memory and the CMVN statistics are pre-reduced in shared memory — so that
+// three CTAs (24 warps) instead of two fit an SM: v2 is issue/latency bound at ~0.3 IPC per scheduler with 4 warps each.
+struct FbankSmem3 {
+    alignas(16) float samples[SAMPLES_PER_CTA + 8];
+    double stat[NMEL][2];
+    alignas(16) float2 tile[FB_WARPS][2][FB2_TILE];
+    alignas(16) float window[WIN];
+    alignas(16) float2 w256[NC];
+    alignas(16) float2 w512[NC + 1];
+    alignas(16) float mel_w[MAX_MEL_TAPS];
+    int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
+};
+
+__global__ void __launch_bounds__(FB_THREADS)
+fbank_kernel_v3(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
+                const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
+                float pcm_scale) {
+    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
+    FbankSmem3& s = *reinterpret_cast<FbankSmem3*>(fb_smem_raw);
+    const int b = blockIdx.y;
+    const long long s0 = sample_off[b];
+    const long long f_begin = frame_off[b];
+    const int nframes = (int)(frame_off[b + 1] - f_begin);
+    const int f0 = blockIdx.x * FR_PER_CTA;
+    if (f0 >= nframes) return;
+    const int nf = min(FR_PER_CTA, nframes - f0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hl = lane & 15, half = lane >> 4;
+
+    const FbankTables& T = g_fbank_tables;
+    for (int i = tid; i < WIN; i += FB_THREADS) s.window[i] = T.window[i];
+    for (int i = tid; i < NC; i += FB_THREADS) s.w256[i] = T.w256[i];
+    for (int i = tid; i <= NC; i += FB_THREADS) s.w512[i] = T.w512[i];
+    for (int i = tid; i < MAX_MEL_TAPS; i += FB_THREADS) s.mel_w[i] = T.mel_w[i];
+    for (int i = tid; i < NMEL; i += FB_THREADS) {
+        s.mel_start[i] = T.mel_start[i]; s.mel_len[i] = T.mel_len[i]; s.mel_off[i] = T.mel_off[i];
+        s.stat[i][0] = 0.0; s.stat[i][1] = 0.0;
+    }
+    const int nsamp = (nf - 1) * SHIFT + WIN;
+    const float* src = pcm + s0 + (long long)f0 * SHIFT;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = nsamp >> 2;
+        for (int i = tid; i < n4; i += FB_THREADS) reinterpret_cast<float4*>(s.samples)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        for (int i = (n4 << 2) + tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    float2* tile = s.tile[warp][half];
+    float* pw = reinterpret_cast<float*>(tile);   // the power spectrum (257 floats) overwrites the tile once Z has been read
+    float* dst = feats + (f_begin + f0) * NMEL;
+    float st_sum[NMEL / 16], st_sq[NMEL / 16];     // CMVN statistics of this lane's 5 mel bins over this half-warp's frames
+#pragma unroll
+    for (int i = 0; i < NMEL / 16; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+    // two frames per warp iteration; frames beyond nf are computed on frame nf - 1 and not stored (keeps the warp converged)
+    for (int fr0 = warp * 2; fr0 < nf; fr0 += FB_WARPS * 2) {
+        const int fr = fr0 + half;
+        const bool live = fr < nf;
+        const float* x = s.samples + (live ? fr : nf - 1) * SHIFT;
+        // DC offset over the 400 samples of the frame
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < WIN / 16; ++i) sum += x[hl + 16 * i] * pcm_scale;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / WIN);
+        // z[n] = y[2n] + i y[2n+1], n = hl + 16 n2 (pre-emphasis 0.97, Povey window, zero-padded beyond 200)
+        float2 v[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const int n = hl + 16 * n2;
+            float2 z = make_float2(0.f, 0.f);
+            if (n < WIN / 2) {
+                const int j = 2 * n;
+                const float xm1 = x[j > 0 ? j - 1 : 0] * pcm_scale - mean;
+                const float x0 = x[j] * pcm_scale - mean;
+                const float x1 = x[j + 1] * pcm_scale - mean;
+                z.x = (x0 - 0.97f * xm1) * s.window[j];
+                z.y = (x1 - 0.97f * x0) * s.window[j + 1];
+            }
+            v[n2] = z;
+        }
+        dft16(v);                                   // A[n1 = hl][k2]
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], s.w256[(hl * k2) & (NC - 1)]);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) tile[k2 * 17 + hl] = v[k2];   // transpose through the padded tile
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = tile[hl * 17 + n1];   // lane k2 = hl: A'[n1][k2]
+        __syncwarp();
+        dft16(v);                                   // Z[16 k1 + hl] in v[k1]
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) tile[16 * k1 + hl] = v[k1];
+        __syncwarp();
+        // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
+        auto untangle = [&](int k) -> float {
+            const float2 zk = tile[k & (NC - 1)];
+            const float2 zc = tile[(NC - k) & (NC - 1)];
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            const float2 wo = cmul(s.w512[k], o);
+            const float re = e.x + wo.x, im = e.y + wo.y;
+            return re * re + im * im;
+        };
+        float pk[17];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = untangle(hl + 16 * i);    // independent iterations: loads overlap
+        pk[16] = untangle(NC);                                           // (every lane computes it, lane 0 stores it)
+        __syncwarp();                                                    // every Z value has been read: the tile may go
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pw[hl + 16 * i] = pk[i];
+        if (hl == 0) pw[NC] = pk[16];
+        __syncwarp();
+        // sparse mel projection + log: 80 bins over the 16 lanes
+#pragma unroll
+        for (int mi = 0; mi < NMEL / 16; ++mi) {
+            const int m = hl + 16 * mi;
+            const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four partial sums: the tap loop is a latency chain otherwise
+            int i = 0;
+            for (; i + 4 <= ln; i += 4) {
+                a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
+                a1 = fmaf(pw[st + i + 1], s.mel_w[of + i + 1], a1);
+                a2 = fmaf(pw[st + i + 2], s.mel_w[of + i + 2], a2);
+                a3 = fmaf(pw[st + i + 3], s.mel_w[of + i + 3], a3);
+            }
+            for (; i < ln; ++i) a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
+            const float acc = (a0 + a1) + (a2 + a3);
+            if (live) {
+                const float val = logf(fmaxf(acc, 1.1920928955078125e-07f));
+                dst[(long long)fr * NMEL + m] = val;
+                st_sum[mi] += val; st_sq[mi] = fmaf(val, val, st_sq[mi]);
+            }
+        }
+        __syncwarp();
+    }
+    if (stats != nullptr) {
+#pragma unroll
+        for (int mi = 0; mi < NMEL / 16; ++mi) {
+            atomicAdd(&s.stat[hl + 16 * mi][0], (double)st_sum[mi]);
+            atomicAdd(&s.stat[hl + 16 * mi][1], (double)st_sq[mi]);
+        }
+    }
+    __syncthreads();
+
+    if (stats != nullptr && tid < NMEL) {
+        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], s.stat[tid][0]);
+        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], s.stat[tid][1]);
+    }
+}
+
 // CMVN: x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) with fp64 statistics, in place; optionally
 // also writes bf16 features into a zero-padded [B, padded_frames, 80] buffer (front_pad zero frames
 // before each utterance, zeros after its last frame) for the conv subsampler.
@@ -484,6 +638,7 @@ static int upload_fbank_tables() {
     PB_CUDA(cudaMemcpyToSymbol(g_fbank_tables, &t, sizeof(FbankTables)));
     PB_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
     PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem2)));
+    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem3)));
     if (dev < 64) done_for_device[dev] = 1;
     return 0;
 }
@@ -517,7 +672,12 @@ extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets,
     if (max_frames > 0) {
         dim3 grid((max_frames + FR_PER_CTA - 1) / FR_PER_CTA, batch);
         static const bool use_v1 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v1"); }();
-        if (use_v1)
+        static const bool use_v3 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v3"); }();
+        if (use_v3)
+            fbank_kernel_v3<<<grid, FB_THREADS, sizeof(FbankSmem3), stream>>>(
+                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
+                feats, stats, pcm_scale);
+        else if (use_v1)
             fbank_kernel<<<grid, FB_THREADS, sizeof(FbankSmem), stream>>>(
                 pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
                 feats, stats, pcm_scale);
