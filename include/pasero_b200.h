@@ -173,6 +173,10 @@ int pb200_p2p_export(const void* ptr, void* handle_out /* 64 bytes */, int64_t* 
 int pb200_p2p_import(const void* handle, int64_t offset, void** ptr_out);
 int pb200_allreduce_p2p(void* const* data, void* const* signal, int32_t rank, int32_t world, int64_t begin, int64_t count,
                         void* stream);
+/* the same reduction done by the NVSwitch (NVLS): mc_data = multicast address of the arenas (e.g. torch symmetric memory's
+ * multicast_ptr); multimem.ld_reduce sums a chunk of all ranks in the switch, multimem.st broadcasts the result */
+int pb200_allreduce_nvls(void* mc_data, void* const* signal, int32_t rank, int32_t world, int64_t begin, int64_t count,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding epilogue: out[r] = dropout(bf16(bf16(src_row * scale) + pos[r % L])), src_row = src[ids[r]]

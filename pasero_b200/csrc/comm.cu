@@ -116,6 +116,38 @@ allreduce_p2p_kernel(const P2PDev c, long long begin, long long count) {
     if (threadIdx.x == 0) gens[blockIdx.x] = gen;
 }
 
+// NVLS variant: the arenas are bound to one NVSwitch multicast object (torch symmetric memory hands out its address).
+// multimem.ld_reduce makes the SWITCH add the 16-byte chunk of all ranks (fp32 accumulation) and return the sum;
+// multimem.st broadcasts the rounded result into every rank's arena. Per rank only 1/N of the bucket crosses its links in
+// each direction (the two-shot kernel above moves (N - 1)/N). Same slice ownership, same flag barriers (unicast pads).
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_16(void* mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(P2P_THREADS)
+allreduce_nvls_kernel(const P2PDev c, bf16* __restrict__ mc, long long begin, long long count) {
+    uint32_t* gens = c.sig[c.rank] + 2 * P2P_BLOCKS * P2P_MAX_RANKS;
+    const uint32_t gen = gens[blockIdx.x] + 1;
+    rank_barrier(c, 0, gen);
+    const long long chunks = count >> 3;
+    const long long per = (chunks + c.world - 1) / c.world;
+    const long long c0 = per * c.rank;
+    const long long c1 = c0 + per < chunks ? c0 + per : chunks;
+    for (long long i = c0 + (long long)blockIdx.x * P2P_THREADS + threadIdx.x; i < c1; i += (long long)P2P_BLOCKS * P2P_THREADS) {
+        bf16* p = mc + begin + (i << 3);
+        multimem_st_16(p, multimem_ld_reduce_bf16x8(p));
+    }
+    __threadfence_system();
+    rank_barrier(c, 1, gen);
+    if (threadIdx.x == 0) gens[blockIdx.x] = gen;
+}
+
 typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 
 }  // namespace pb200
@@ -170,6 +202,27 @@ extern "C" int pb200_allreduce_p2p(void* const* data, void* const* signal, int32
     }
     c.rank = rank; c.world = world;
     allreduce_p2p_kernel<<<P2P_BLOCKS, P2P_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(c, (long long)begin, (long long)count);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same reduction through the NVSwitch multicast mapping `mc_data` of the arenas (NVLS). signal[r]: unicast signal pads
+// as for pb200_allreduce_p2p; data pointers are not needed.
+extern "C" int pb200_allreduce_nvls(void* mc_data, void* const* signal, int32_t rank, int32_t world, int64_t begin,
+                                    int64_t count, void* stream_) {
+    PB_CHECK(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world, "allreduce_nvls: bad rank/world (%d/%d)", rank, world);
+    PB_CHECK(begin % 8 == 0 && count % 8 == 0, "allreduce_nvls: begin and count must be multiples of 8 elements");
+    PB_CHECK(mc_data != nullptr, "allreduce_nvls: no multicast mapping");
+    if (count == 0 || world == 1) return 0;
+    P2PDev c;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) {
+        c.data[r] = nullptr;
+        c.sig[r] = r < world ? reinterpret_cast<uint32_t*>(signal[r]) : nullptr;
+        PB_CHECK(r >= world || c.sig[r], "allreduce_nvls: null signal pad for rank %d", r);
+    }
+    c.rank = rank; c.world = world;
+    allreduce_nvls_kernel<<<P2P_BLOCKS, P2P_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+        c, reinterpret_cast<bf16*>(mc_data), (long long)begin, (long long)count);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -159,6 +159,7 @@ class P2PAllreduce:
         if self.world > 8:
             raise RuntimeError('peer-memory allreduce covers one node (<= 8 ranks)')
         self.grad = grad
+        self._mc = 0
         words = lib.pb200_p2p_signal_bytes() // 4
         self._data = (ctypes.c_void_p * 8)()
         self._sig = (ctypes.c_void_p * 8)()
@@ -171,6 +172,12 @@ class P2PAllreduce:
             for arr, own, handle in zip((self._data, self._sig), (grad, self.signal), self._handles):
                 for r in range(self.world):
                     arr[r] = own.data_ptr() if r == self.rank else int(handle.buffer_ptrs[r]) + int(handle.offset)
+            # PB200_P2P_NVLS=1: let the NVSwitch do the sum (multimem.ld_reduce / multimem.st on the multicast mapping)
+            mc = int(getattr(self._handles[0], 'multicast_ptr', 0) or 0)
+            if os.environ.get('PB200_P2P_NVLS', '0') == '1':
+                if not mc:
+                    raise RuntimeError('PB200_P2P_NVLS=1 but the symmetric-memory allocation has no multicast mapping')
+                self._mc = mc + int(self._handles[0].offset)
             dist.barrier(group)
             return
         self.signal = torch.zeros(words, dtype=torch.int32, device=grad.device)
@@ -201,7 +208,11 @@ class P2PAllreduce:
 
     def allreduce(self, lo: int, hi: int) -> None:
         """grad[lo:hi] <- sum over ranks, in place, on the current stream."""
-        K.check(K._lib.load().pb200_allreduce_p2p(self._data, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
+        lib = K._lib.load()
+        if self._mc:
+            K.check(lib.pb200_allreduce_nvls(self._mc, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
+        else:
+            K.check(lib.pb200_allreduce_p2p(self._data, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
 
 
 class GradBuckets:
