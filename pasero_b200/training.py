@@ -450,6 +450,7 @@ class Trainer:
             if self.buckets is not None:
                 self.buckets.start_step(sync=last)   # no_sync() on all but the last micro-batch (training.py:407)
             self._forward_backward(batch)
+            ops.WgradStream.join()   # per micro-batch: the forked GEMMs' operands are kept referenced until the join
         if self.buckets is not None:
             self.buckets.finish(self.stats)
         else:
