@@ -212,7 +212,8 @@ int pb200_f32_to_bf16(const float* in, int64_t n, void* out, int32_t accumulate,
  * Label-smoothed cross-entropy over bf16 logits [B*T, V] (row stride ld), targets int64 read as
  * target[b * target_stride0 + t]; rows whose target == padding_idx contribute nothing. Overwrites the
  * logits with d loss / d logits (bf16) when write_grad != 0. stats (fp64): [0] += loss (nats, summed),
- * [1] += nll (nats, summed), [2] += number of non-pad targets.  (pasero/models/transformer.py:323-380)
+ * [1] += nll (nats, summed), [2] += number of non-pad targets, [7] += number of targets outside [0, V) (treated as
+ * padding; the caller raises, as F.cross_entropy does).  stats has >= 8 entries.  (pasero/models/transformer.py:323-380)
  * ---------------------------------------------------------------------------------------------- */
 int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T, int64_t V,
                         int64_t ld, int64_t padding_idx, float label_smoothing, float grad_scale, int32_t write_grad,

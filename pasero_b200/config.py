@@ -60,6 +60,44 @@ class TransformerConfig:
     prompt_loss: float = 1.0
     model_type: str = 'encoder_decoder'
 
+    # options of the reference's TransformerConfig (pasero/config.py:1054-1319) that select code outside this path: a
+    # reference config object is accepted only while they keep the listed value
+    REFERENCE_ONLY = dict(rms_norm=False, has_bias=True, norm_bias=True, encoder_embed_norm=False, decoder_embed_norm=False,
+                          shared_norm=False, parallel_attention=False, attention_heads_kv=None, sliding_window=None,
+                          lora_rank=0, shift_encoder_layers=None, shift_decoder_layers=None, max_qkv=None,
+                          checkpoint_activations=False)
+
+    @classmethod
+    def adopt(cls, cfg, task: str = 'speech_translation') -> 'TransformerConfig':
+        """This path's view of a model configuration. `cfg` is either one of ours (returned as is) or the reference's own
+        `TransformerConfig` / `AdapterTransformerConfig` object as `cli/train.py:220` hands it to a registered model:
+        every option this path reads is copied by name; adapters are switched on by the config CLASS in the reference
+        (pasero/config.py:1322-1369, models/adapters.py:62-119), i.e. by the presence of `encoder_adapter_dim`."""
+        if isinstance(cfg, cls):
+            return cfg
+        out = cls()
+        for f in fields(cls):
+            if hasattr(cfg, f.name):
+                v = getattr(cfg, f.name)
+                setattr(out, f.name, tuple(v) if isinstance(v, list) else v)
+        out.adapters = bool(getattr(cfg, 'adapters', hasattr(cfg, 'encoder_adapter_dim')))
+        if out.decoder_prenorm is None:
+            out.decoder_prenorm = out.encoder_prenorm
+        if out.conv_activation is None:
+            out.conv_activation = 'glu'
+        if out.model_type is None:
+            out.model_type = 'encoder_decoder'
+        bad = []
+        for name, keep in cls.REFERENCE_ONLY.items():
+            v = getattr(cfg, name, keep)
+            if name == 'attention_heads_kv' and v in (out.encoder_attention_heads, out.decoder_attention_heads):
+                continue
+            if v != keep and not (keep is None and not v):
+                bad.append(f'{name}={v!r}')
+        if bad:
+            raise NotImplementedError('pasero_b200 does not cover: ' + ', '.join(bad))
+        return out.finalize(task)
+
     def finalize(self, task: str = 'speech_translation') -> 'TransformerConfig':
         if self.label_smoothing is None:
             self.label_smoothing = 0.1 if task in ('translation', 'speech_translation') else 0.0
@@ -150,6 +188,36 @@ class TrainingConfig(DistributedConfig):
     }
 
     @classmethod
+    def adopt(cls, cfg) -> 'TrainingConfig':
+        """This path's view of a training configuration: `cfg` is one of ours (returned as is) or the reference's own
+        `TrainingConfig` (pasero/config.py:1469-1868) as `cli/train.py:287` hands it to the Trainer. Options are copied by
+        name; options that switch on a subsystem outside the data-parallel ST step raise."""
+        if isinstance(cfg, cls):
+            return cfg
+        out = cls()
+        skip = {'model_cfg', 'extra'}
+        for f in fields(cls):
+            if f.name not in skip and hasattr(cfg, f.name) and getattr(cfg, f.name) is not None:
+                v = getattr(cfg, f.name)
+                setattr(out, f.name, tuple(v) if isinstance(v, list) else v)
+        for name in ('freeze_params_regex', 'train_params_regex'):
+            if getattr(cfg, name, None):
+                out.extra[name] = getattr(cfg, name)
+        bad = [f'{k}={getattr(cfg, k)!r}' for k in ('fsdp', 'amp') if getattr(cfg, k, False)]
+        if getattr(cfg, 'tp_size', 1) != 1:
+            bad.append(f'tp_size={cfg.tp_size}')
+        if bad:
+            raise NotImplementedError('options outside the ST data-parallel path: ' + ', '.join(bad))
+        if out.dtype != 'bfloat16':
+            raise NotImplementedError('the sm_100a kernels compute in bfloat16 (dtype: bfloat16)')
+        out.model_cfg = TransformerConfig.adopt(getattr(cfg, 'model_cfg', None) or TransformerConfig(), out.task)
+        out.save_interval = out.save_interval or out.valid_interval
+        out.max_source_len = out.max_source_len or out.model_cfg.encoder_max_len
+        out.max_target_len = out.max_target_len or out.model_cfg.decoder_max_len
+        out._reference = cfg
+        return out
+
+    @classmethod
     def from_dict(cls, opts: dict) -> 'TrainingConfig':
         opts = {k.replace('-', '_'): v for k, v in opts.items()}
         model_fields = {f.name for f in fields(TransformerConfig)}
@@ -189,6 +257,9 @@ class TrainingConfig(DistributedConfig):
 
     def as_dict(self) -> dict:
         """Flat dict in the reference's `cfg.as_dict()` style (stored under 'args' in checkpoints)."""
+        ref = getattr(self, '_reference', None)
+        if ref is not None:       # adopted from the reference's own TrainingConfig: its as_dict() is the authority
+            return ref.as_dict()
         out = {f.name: getattr(self, f.name) for f in fields(self) if f.name not in ('model_cfg', 'extra')}
         out.update({f.name: getattr(self.model_cfg, f.name) for f in fields(self.model_cfg)})
         out.update(self.extra)

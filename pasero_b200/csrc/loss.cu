@@ -38,7 +38,7 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red) {
     return r;
 }
 
-// stats (fp64): [0] += sum loss (nats), [1] += sum nll (nats), [2] += #non-pad targets
+// stats (fp64): [0] += sum loss (nats), [1] += sum nll (nats), [2] += #non-pad targets, [7] += #targets out of range
 __global__ void __launch_bounds__(CE_THREADS)
 ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, long long target_stride0,
              int T, int V, long long ld, long long padding_idx, float eps, float grad_scale, int write_grad,
@@ -49,7 +49,11 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
     const long long tgt = target[(row / T) * target_stride0 + (row % T)];
     bf16* x = logits + row * ld;
     const int v8 = (V + 7) >> 3;   // the last vector may hold padding columns (c >= V): masked below, written back as 0
-    if (tgt == padding_idx) {
+    // a target id outside [0, V) (F.cross_entropy raises for it): no loss, zero gradient, and stats[7] counts it so that
+    // the host raises when it reads the step's scalars (Trainer.read_logs) instead of training on a wrong loss
+    const bool bad = tgt != padding_idx && (tgt < 0 || tgt >= V);
+    if (bad && threadIdx.x == 0) atomicAdd(&stats[7], 1.0);
+    if (tgt == padding_idx || bad) {
         if (write_grad)
             for (int i = threadIdx.x; i < v8; i += CE_THREADS) reinterpret_cast<uint4*>(x)[i] = make_uint4(0, 0, 0, 0);
         if (row_loss && threadIdx.x == 0) row_loss[row] = 0.f;

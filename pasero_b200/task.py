@@ -94,71 +94,106 @@ def split_tags(line: str) -> list:
 
 
 class NumpyFile:
-    """Feature container of the reference (pasero/files.py:103-192): a pickled header
-    {'positions', 'lengths', 'dim', 'dtype'} followed by the raw rows of every utterance."""
+    """Reader / writer for the reference's feature container (pasero/files.py:103-192): a pickled header
+    {'positions', 'lengths', 'dim', 'dtype'} followed by the raw rows of every utterance; header slots whose position is
+    0 are unused and skipped (files.py:112-115). Files are interchangeable with the reference's (tests/golden/
+    features_ref.npy was written by it).
+
+    B200-side design: the file is memory-mapped once, `f[i]` is a zero-copy view, and `pack()` lays a whole batch out
+    in one (pinned) staging buffer — ragged rows back to back plus offsets — which is what the device-side collate
+    (`pasero_b200.frontend.collate_features`) consumes: one H2D copy of the true bytes instead of a padded fp32 tensor."""
 
     def __init__(self, path: str):
         self._path = path
-        self._file = open(path, 'rb')
-        header = pickle.load(self._file)
+        with open(path, 'rb') as file:
+            header = pickle.load(file)
         self._dim = int(header['dim'])
         self._dtype = np.dtype(header['dtype'])
-        self._itemsize = self._dim * self._dtype.itemsize
-        pos_len = [(p, n) for p, n in zip(header['positions'], header['lengths']) if p > 0]  # skip empty slots
-        self._positions = np.array([p for p, _ in pos_len], dtype=np.int64)
-        self._lengths = np.array([n for _, n in pos_len], dtype=np.int64)
+        used = np.asarray(header['positions'], dtype=np.int64) > 0
+        self._positions = np.asarray(header['positions'], dtype=np.int64)[used]
+        self._lengths = np.asarray(header['lengths'], dtype=np.int64)[used]
+        self._map = np.memmap(path, dtype=np.uint8, mode='r') if len(self._positions) else np.zeros(0, dtype=np.uint8)
         self._index = 0
+
+    # ---- writing ---------------------------------------------------------------------------------
+    @staticmethod
+    def _header(positions, lengths, dim: int, dtype: str) -> bytes:
+        return pickle.dumps({'positions': positions, 'lengths': lengths, 'dim': np.array(dim, dtype=np.int64), 'dtype': dtype})
 
     @classmethod
     def build(cls, path: str, features: Iterable[np.ndarray], dtype: str = 'float16', num_feats: Optional[int] = None):
-        def write_header(file, positions, lengths, dim):
-            pickle.dump({'positions': positions, 'lengths': lengths, 'dim': np.array(dim, dtype=np.int64), 'dtype': dtype}, file)
-        if num_feats is None:
-            num_feats = len(features)
-        d = os.path.dirname(path)
-        if d:
-            os.makedirs(d, exist_ok=True)
+        """Byte-compatible with the reference's writer: the header is pickled with `num_feats` slots (may exceed the number
+        of utterances actually written), rows follow in order."""
+        slots = len(features) if num_feats is None else num_feats
+        positions, lengths = np.zeros(slots, dtype=np.int64), np.zeros(slots, dtype=np.int64)
+        if os.path.dirname(path):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        dim = 0
         with open(path, 'wb') as file:
-            dim = 0
-            positions = np.zeros(num_feats, dtype=np.int64)
-            lengths = np.zeros(num_feats, dtype=np.int64)
-            write_header(file, positions, lengths, dim)
-            for i, x in enumerate(features):
-                x = x.astype(dtype)
-                positions[i] = file.tell()
-                lengths[i] = x.shape[0]
-                dim = x.shape[1]
-                file.write(x.tobytes())
+            cursor = file.write(cls._header(positions, lengths, dim, dtype))    # fixed size: int64 arrays of `slots` entries
+            for i, rows in enumerate(features):
+                rows = np.ascontiguousarray(rows, dtype=dtype)
+                positions[i], lengths[i], dim = cursor, rows.shape[0], rows.shape[1]
+                cursor += file.write(rows.tobytes())
             file.seek(0)
-            write_header(file, positions, lengths, dim)
+            file.write(cls._header(positions, lengths, dim, dtype))
         return cls(path)
 
+    # ---- reading ---------------------------------------------------------------------------------
     def __len__(self):
         return len(self._positions)
+
+    @property
+    def dim(self) -> int:
+        return self._dim
+
+    @property
+    def dtype(self) -> np.dtype:
+        return self._dtype
 
     def get_positions(self):
         return np.arange(len(self._positions)), self._lengths
 
+    def __getitem__(self, index: int) -> np.ndarray:
+        """Zero-copy (read-only) view of utterance `index`: (frames, dim), or (frames,) when dim == 1."""
+        n = int(self._lengths[index])
+        begin = int(self._positions[index])
+        x = self._map[begin:begin + n * self._dim * self._dtype.itemsize].view(self._dtype)
+        return x.reshape(n, self._dim) if self._dim > 1 else x
+
     def seek(self, index: int):
         self._index = index
-        self._file.seek(self._positions[index])
+
+    def tell(self) -> int:
+        return self._index
 
     def __iter__(self):
         return self
 
     def __next__(self) -> np.ndarray:
+        """The reference's iteration protocol (files.py:164-175): an owned copy of the next utterance."""
         if self._index >= len(self._positions):
             raise StopIteration
-        self._file.seek(self._positions[self._index])
-        length = int(self._lengths[self._index])
-        x = np.frombuffer(self._file.read(length * self._itemsize), dtype=self._dtype).copy()
-        if self._dim > 1:
-            x = x.reshape(length, self._dim)
+        x = np.array(self[self._index])
         self._index += 1
         return x
 
+    def pack(self, indices, out: Optional[np.ndarray] = None):
+        """Utterances `indices` back to back in one buffer: (rows [sum frames, dim] in the file's dtype, offsets int64
+        [len + 1] in frames). `out` (e.g. the numpy view of a pinned tensor, at least sum-frames rows) is filled in place."""
+        indices = [int(i) for i in indices]
+        offsets = np.zeros(len(indices) + 1, dtype=np.int64)
+        np.cumsum(self._lengths[indices], out=offsets[1:])
+        total = int(offsets[-1])
+        if out is None:
+            out = np.empty((total, self._dim), dtype=self._dtype)
+        assert out.dtype == self._dtype and out.shape[0] >= total and out.shape[1] == self._dim
+        for j, i in enumerate(indices):
+            out[offsets[j]:offsets[j + 1]] = self[i].reshape(-1, self._dim)
+        return out[:total], offsets
+
     def close(self):
-        self._file.close()
+        self._map = np.zeros(0, dtype=np.uint8)
 
 
 def tokens_as_tensor(token_list: list, padding_idx: int, dtype: Optional[torch.dtype] = None):

@@ -15,6 +15,7 @@ import math
 import os
 import time
 from collections import defaultdict
+from collections.abc import Mapping
 from typing import Iterator, Optional
 
 import torch
@@ -333,6 +334,7 @@ class Trainer:
                  data_parallel: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError('pasero_b200.Trainer needs a CUDA device: the sm_100a kernels have no CPU fallback')
+        cfg = TrainingConfig.adopt(cfg)      # ours, or the reference's own TrainingConfig (cli/train.py:287)
         self.cfg, self.task, self.model = cfg, task, model
         self.device = torch.device(device or f'cuda:{torch.cuda.current_device()}')
         self.dtype = BF16
@@ -340,13 +342,25 @@ class Trainer:
         self.dp_size = dist.get_world_size() if self.distributed else 1
         cfg.dp_size = self.dp_size
         self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)
+        if getattr(model, 'find_unused_parameters', False):
+            # `*_adapters_by`: a different subset of the adapters is used from step to step. The reference skips Adam
+            # entirely for parameters without a gradient (per-parameter step counters, optimization.py:77-86) and DDP
+            # leaves globally unused gradients untouched; the flat-arena optimizer here updates every element every
+            # step, which would decay the idle adapters' moments and re-apply stale gradients. Refuse rather than
+            # silently train something else (the model itself runs: forward / backward parity is tested).
+            raise NotImplementedError('pasero_b200.Trainer does not cover encoder/decoder_adapters_by (parameters unused in '
+                                      'some steps); train with one adapter set per run (encoder_adapters / decoder_adapters)')
         model.to(self.dtype)
         model.to(self.device)
+        from . import reference_param_names
+        ref_names = reference_param_names(model)     # before the arena: afterwards every parameter shares one storage
         # (experimental peer-memory allreduce with symmetric memory: the gradient arena has to be allocated there)
         symm = (self.distributed and os.environ.get('PB200_P2P_ALLREDUCE', '0') == '1' and P2PAllreduce.mapping() == 'symm')
         self.arena = ParamArena(model, self.device,
                                 (lambda n: P2PAllreduce.symmetric_empty(n, BF16, self.device)) if symm else None)
         self.param_names = list(self.arena.names)
+        # the reference's names of the TRAINABLE parameters: optimizer state is keyed by them (pasero/training.py:899-906)
+        self.reference_names = [r for n in self.arena.names for r in ref_names[n]]
         if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.arena.param, src=0)
         self.buckets = GradBuckets(self.arena, cfg.bucket_bytes) if self.distributed else None
@@ -375,7 +389,6 @@ class Trainer:
         self._stats_ring = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(4)]
         self.rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
         model.defer_logs = True
-        ops.ProjCEFn.unit_loss_grad = True
         ops.DropoutState.reseed(cfg.seed if cfg.seed is not None else int(time.time()))
         self._graphs = {}
         # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
@@ -426,7 +439,11 @@ class Trainer:
 
     def _forward_backward(self, batch: dict):
         loss, logs = self.model(**batch)
-        loss.backward()
+        ops.ProjCEFn.unit_loss_grad = True      # the loss is the root of this backward (grad_output == 1): scoped to it
+        try:
+            loss.backward()
+        finally:
+            ops.ProjCEFn.unit_loss_grad = False
         return logs
 
     def _optimizer_kernels(self) -> None:
@@ -498,6 +515,8 @@ class Trainer:
         """Synchronises on the step's single deferred D2H copy and returns python numbers."""
         event.synchronize()
         s = host.tolist()
+        if s[7] > 0:    # counted by the loss kernel (csrc/loss.cu); the reference's F.cross_entropy raises for these
+            raise RuntimeError(f'{int(s[7])} target ids outside [0, vocabulary size) in this step')
         logs = {'loss': s[0] / math.log(2), 'nll_loss': s[1] / math.log(2), 'num_tokens': int(s[2]), 'num_lines': int(s[3]),
                 'gnorm': math.sqrt(max(s[4], 0.0)), 'lr': lr, 'loss_scale': 1.0}
         return logs
@@ -511,6 +530,8 @@ class Trainer:
         tensors = {k: v for k, v in batch.items() if torch.is_tensor(v)}
         key = tuple((k, tuple(v.shape)) for k, v in sorted(tensors.items()))
         key = key + tuple(sorted((k, v) for k, v in batch.items() if isinstance(v, (int, tuple))))
+        # anything in `meta` may select code paths (adapters by language / domain): a graph is only replayed for the same meta
+        key = key + tuple(sorted((k, str(v)) for k, v in (batch.get('meta') or {}).items() if k != 'step'))
         self.model.train()
         p2p_graph = self.buckets is not None and self.buckets.p2p is not None
         if key not in self._graphs:
@@ -574,23 +595,33 @@ class Trainer:
             self.arena.flush32(self._ranges32_all)   # with buckets: flushed per bucket right before its allreduce
 
     # ------------------------------------------------------------------ checkpoints (reference layout)
-    def _named_state(self, flat: Tensor) -> dict:
-        """View a flat arena (moments) through the model's state_dict hooks -> tensors keyed by reference names."""
+    def named_arena(self, flat: Tensor) -> dict:
+        """A flat arena (gradients, Adam moments) as tensors keyed by the reference's parameter names: the trainable
+        parameters are pointed at their slices of `flat` and read back through the model's state_dict hooks (fused
+        k|v|q projection -> three `*_proj` entries, tap-major conv weights -> [Cout, Cin, KW]). Frozen parameters are not
+        part of any arena and are left out, like in the reference's name-keyed optimizer state."""
         saved = [p.data for p in self.arena.params]
+        wanted = set(self.reference_names)
         try:
             for i, p in enumerate(self.arena.params):
                 p.data = self.arena.view(flat, i)
-            return {k: v.detach().clone().cpu() for k, v in self.model.state_dict().items() if v.is_floating_point() and v.numel() > 1}
+            return {k: v.detach().clone() for k, v in self.model.state_dict().items() if k in wanted}
         finally:
             for p, d in zip(self.arena.params, saved):
                 p.data = d
 
+    def _named_state(self, flat: Tensor) -> dict:
+        return {k: v.cpu() for k, v in self.named_arena(flat).items()}
+
     def _load_named_state(self, flat: Tensor, state: dict) -> None:
+        """Inverse of named_arena for the trainable parameters' entries of `state`; anything else in `state` (frozen
+        parameters written by an older checkpoint) is ignored rather than copied into live weights."""
         saved = [p.data for p in self.arena.params]
+        wanted = set(self.reference_names)
         try:
             for i, p in enumerate(self.arena.params):
                 p.data = self.arena.view(flat, i)
-            self.model.load_state_dict({k: v for k, v in state.items()}, strict=False)
+            self.model.load_state_dict({k: v for k, v in state.items() if k in wanted}, strict=False)
         finally:
             for p, d in zip(self.arena.params, saved):
                 p.data = d
@@ -602,7 +633,7 @@ class Trainer:
         """{'state': {param_name: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} — the reference keys
         optimizer state by parameter *name* (pasero/training.py:899-906)."""
         m, v = self._named_state(self.arena.exp_avg), self._named_state(self.arena.exp_avg_sq)
-        names = [k for k in m if not k.endswith('_float_tensor')]
+        names = list(m)
         state = {k: {'step': self.optimizer_steps, 'exp_avg': m[k], 'exp_avg_sq': v[k]} for k in names}
         group = {'lr': self.scheduler.get_last_lr()[0], 'betas': tuple(self.cfg.adam_betas), 'eps': self.cfg.adam_eps,
                  'weight_decay': self.cfg.weight_decay, 'amsgrad': False, 'params': names}
@@ -709,30 +740,32 @@ class DevicePrefetcher:
         return dev
 
 
-class LazyLogs(dict):
-    """Step logs whose values are fetched from the deferred D2H copy on first access (no sync inside the step)."""
+class LazyLogs(Mapping):
+    """Step logs whose values are fetched from the deferred D2H copy on first access (no sync inside the step). A
+    read-only Mapping: every access path (`[]`, `get`, `in`, `len`, iteration, `dict(logs)`, `{**logs}`) loads first.
+    The pinned host slot is reused `len(ring)` steps later; reading after that raises instead of returning another
+    step's numbers."""
 
-    def __init__(self, trainer: Trainer, host: Tensor, event, lr: float):
-        super().__init__()
-        self._src, self._loaded = (host, event, lr), False
+    def __init__(self, trainer: 'Trainer', host: Tensor, event, lr: float):
+        self._src, self._data = (host, event, lr), None
+        self._trainer, self._step = trainer, trainer.steps
 
-    def _load(self):
-        if not self._loaded:   # must happen before the ring slot is reused (4 steps later)
-            self._loaded = True
-            super().update(Trainer.read_logs(*self._src))
+    def _load(self) -> dict:
+        if self._data is None:
+            if self._trainer.steps - self._step >= len(self._trainer._stats_ring):
+                raise RuntimeError(f'logs of step {self._step} were not read before their host buffer was reused '
+                                   f'({len(self._trainer._stats_ring)} steps later)')
+            self._data = Trainer.read_logs(*self._src)
+        return self._data
 
     def __getitem__(self, k):
-        self._load()
-        return super().__getitem__(k)
+        return self._load()[k]
 
-    def items(self):
-        self._load()
-        return super().items()
+    def __iter__(self):
+        return iter(self._load())
 
-    def keys(self):
-        self._load()
-        return super().keys()
+    def __len__(self):
+        return len(self._load())
 
     def __repr__(self):
-        self._load()
-        return super().__repr__()
+        return repr(self._load())

@@ -302,6 +302,10 @@ class Transformer(nn.Module):
 
     def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task):
         super().__init__()
+        # `cfg`: ours, or the reference's TransformerConfig / AdapterTransformerConfig when built through the reference's
+        # registry (`get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)`, cli/train.py:220)
+        self.reference_cfg = cfg
+        cfg = TransformerConfig.adopt(cfg, getattr(dist_cfg, 'task', 'speech_translation'))
         self.cfg, self.dist_cfg, self.task = cfg, dist_cfg, task
         self.find_unused_parameters = False
         self.batch_by = None

@@ -416,9 +416,36 @@ def golden_training_curve(pasero, cfg, task, model, out):
     print('training golden: first', rows[0], 'last', rows[-1])
 
 
+def numpy_file_features():
+    """Seeded utterances of the NumpyFile fixture (float32 in, stored as float16 like examples/*/extract-features.py)."""
+    rng = np.random.RandomState(31)
+    return [rng.randn(n, 80).astype(np.float32) for n in (7, 1, 23, 40, 3)]
+
+
+def golden_numpy_file(pasero, out):
+    """A feature file written by the reference's own NumpyFile.build (pasero/files.py:122-159), with two unused slots
+    (num_feats > number of utterances: positions stay 0 and the reader must skip them, files.py:112-115), plus what the
+    reference's reader returns for it."""
+    from pasero.files import NumpyFile
+    path = os.path.join(out, 'features_ref.npy')
+    f = NumpyFile.build(path, numpy_file_features(), dtype='float16', num_feats=7)
+    idx, lengths = f.get_positions()
+    rows = [next(f) for _ in range(len(idx))]
+    f.seek(2)
+    third = next(f)
+    f.close()
+    np.savez(os.path.join(out, 'features_ref_read.npz'), lengths=lengths, third=third,
+             checksum=np.array([float(r.astype(np.float64).sum()) for r in rows]),
+             **{f'row{i}': r for i, r in enumerate(rows)})
+    print('numpy file golden:', os.path.getsize(path), 'bytes,', len(rows), 'utterances, lengths', lengths.tolist())
+
+
 def main():
     out = HERE
     pasero = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'numpyfile':    # only the NumpyFile fixture
+        golden_numpy_file(pasero, out)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'text':         # only the text-encoder fixture
         tmp = tempfile.mkdtemp()
         try:
@@ -463,6 +490,7 @@ def main():
         golden_model_adapters(pasero, tmp, out)
         golden_model_text(pasero, tmp, out)
         golden_preprocess_tags(pasero, tmp, out)
+        golden_numpy_file(pasero, out)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

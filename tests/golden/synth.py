@@ -274,3 +274,116 @@ def summarize_grad(g: torch.Tensor) -> dict:
         return {'full': g.clone()}
     g2 = g.reshape(g.shape[0], -1)
     return {'rows': g2[:4].clone(), 'row_sum': g2.sum(1), 'col_sum': g2.sum(0), 'abs_sum': g2.abs().sum()}
+
+
+# ---- BASELINE-sized variants (tests/test_real_shapes_gpu.py): the same parameter layouts at the true dimensions of
+# BASELINE configs 2 / 4 / 5. No reference-generated fixture is committed for these (hundreds of MB): the CUDA path is
+# compared with the oracle (itself pinned to the reference on the tiny fixtures) on weights and batches seeded here.
+REAL_ST = dict(vocab_size=8032, encoder_layers=12, decoder_layers=6, embed_dim=512, ffn_dim=2048, heads=8, conv_channels=1024)
+REAL_WSP = dict(vocab_size=51865, encoder_layers=12, decoder_layers=12, embed_dim=768, ffn_dim=3072, heads=12,
+                conv_channels=768, encoder_max_len=3000, decoder_max_len=448)
+REAL_BIG = dict(vocab_size=70376, encoder_layers=6, decoder_layers=6, embed_dim=1024, ffn_dim=4096, heads=16, adapter_dim=64)
+
+
+def sized_param_shapes(t: dict, family: str = 'st') -> dict:
+    """Reference-named parameter shapes for dimension dict `t`; family: 'st' (conv k=5,5 + GLU, sinusoidal, post-norm),
+    'wsp' (Whisper family) or 'text' (shared token embedding, optional adapters when t has 'adapter_dim')."""
+    d, f, v = t['embed_dim'], t['ffn_dim'], t['vocab_size']
+    c = t.get('conv_channels')
+    shapes = {}
+    if family == 'st':
+        shapes.update({'encoder.subsample.conv_layers.0.weight': (c, 80, 5), 'encoder.subsample.conv_layers.0.bias': (c,),
+                       'encoder.subsample.conv_layers.1.weight': (2 * d, c // 2, 5), 'encoder.subsample.conv_layers.1.bias': (2 * d,)})
+    elif family == 'wsp':
+        shapes.update({'encoder.subsample.conv_layers.0.weight': (c, 80, 3), 'encoder.subsample.conv_layers.0.bias': (c,),
+                       'encoder.subsample.conv_layers.1.weight': (d, c, 3), 'encoder.subsample.conv_layers.1.bias': (d,),
+                       'encoder.embed_positions.weight': (t['encoder_max_len'] // 2, d)})
+    key_bias = family != 'wsp'
+
+    def attn(prefix):
+        for p in ('k_proj', 'v_proj', 'q_proj', 'out_proj'):
+            shapes[f'{prefix}.{p}.weight'] = (d, d)
+            if p != 'k_proj' or key_bias:
+                shapes[f'{prefix}.{p}.bias'] = (d,)
+
+    def ln(prefix):
+        shapes[f'{prefix}.weight'] = (d,)
+        shapes[f'{prefix}.bias'] = (d,)
+
+    def ffn(prefix):
+        shapes[f'{prefix}.fc1.weight'] = (f, d)
+        shapes[f'{prefix}.fc1.bias'] = (f,)
+        shapes[f'{prefix}.fc2.weight'] = (d, f)
+        shapes[f'{prefix}.fc2.bias'] = (d,)
+
+    def adapter(prefix):
+        a = t.get('adapter_dim')
+        if a:
+            p = prefix + '.adapters.default'
+            shapes[p + '.down.weight'] = (a, d)
+            shapes[p + '.down.bias'] = (a,)
+            shapes[p + '.up.weight'] = (d, a)
+            shapes[p + '.up.bias'] = (d,)
+            ln(p + '.layer_norm')
+
+    for i in range(t['encoder_layers']):
+        p = f'encoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm'); adapter(p)
+    if family == 'wsp':
+        ln('encoder.layer_norm')
+    shapes['decoder.embed_tokens.weight'] = (v, d)
+    if family == 'wsp':
+        shapes['decoder.embed_positions.weight'] = (t['decoder_max_len'], d)
+    for i in range(t['decoder_layers']):
+        p = f'decoder.layers.{i}'
+        attn(p + '.self_attn'); ln(p + '.self_attn_layer_norm')
+        attn(p + '.encoder_attn'); ln(p + '.encoder_attn_layer_norm'); ffn(p); ln(p + '.final_layer_norm'); adapter(p)
+    if family == 'wsp':
+        ln('decoder.layer_norm')
+    return shapes
+
+
+def sized_state_dict(t: dict, family: str = 'st', seed: int = 3) -> dict:
+    """Seeded bf16-representable fp32 weights for `sized_param_shapes(t, family)` (xavier-like scales so that 12 + 6
+    post-norm layers stay well conditioned; adapters get a visible scale instead of the reference's 1e-6 init)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for name, shape in sized_param_shapes(t, family).items():
+        if 'layer_norm' in name:
+            w = (1.0 + 0.1 * rng.randn(*shape)) if name.endswith('weight') else 0.05 * rng.randn(*shape)
+        elif name.endswith('bias'):
+            w = 0.02 * rng.randn(*shape)
+        elif name.endswith('embed_positions.weight'):
+            w = 0.05 * rng.randn(*shape)
+        elif name == 'decoder.embed_tokens.weight':
+            w = rng.randn(*shape) * shape[1] ** -0.5
+            w[PAD] = 0
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            w = rng.randn(*shape) * fan_in ** -0.5
+        sd[name] = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+    if family == 'text':
+        sd['encoder.embed_tokens.weight'] = sd['decoder.embed_tokens.weight']
+    return sd
+
+
+def sized_batch(seed: int, frames, dec_lens, vocab: int, text: bool = False) -> dict:
+    """Ragged batch: `frames` feature frames (or source tokens when text) and `dec_lens` decoder-input lengths per line."""
+    rng = np.random.RandomState(seed)
+    B, Tm = len(frames), max(dec_lens)
+    dec = torch.full((B, Tm), PAD, dtype=torch.int64)
+    pm = torch.zeros(B, Tm, dtype=torch.bool)
+    if text:
+        x = torch.full((B, max(frames)), PAD, dtype=torch.int64)
+    else:
+        x = torch.zeros(B, max(frames), 80)
+    for b, (f, t) in enumerate(zip(frames, dec_lens)):
+        if text:
+            x[b, :f] = torch.from_numpy(np.concatenate([rng.randint(4, vocab, f - 1), [EOS]]))
+        else:
+            x[b, :f] = torch.from_numpy(rng.randn(f, 80).astype(np.float32)).to(torch.bfloat16).float()
+        dec[b, :t] = torch.from_numpy(np.concatenate([[BOS], rng.randint(4, vocab, t - 2), [EOS]]))
+        pm[b, 0] = True
+    return {'encoder_input': x, 'encoder_input_length': torch.tensor(frames), 'decoder_input': dec, 'prompt_mask': pm,
+            'prompt_length': torch.ones(B, dtype=torch.int64), 'indices': torch.arange(B),
+            'meta': {'source_lang': 'de', 'target_lang': 'en'}}

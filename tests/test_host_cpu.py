@@ -195,6 +195,31 @@ def test_numpy_file_roundtrip(tmp_path):
     assert next(f).shape == (17, 80)
 
 
+def test_numpy_file_written_by_the_reference():
+    """tests/golden/features_ref.npy was written by the reference's NumpyFile.build (make_golden.py: 5 utterances in a
+    7-slot header); features_ref_read.npz is what the reference's own reader returned for it. Our reader must return the
+    same arrays, and our writer must produce the same bytes."""
+    from tests.golden.make_golden import numpy_file_features
+    want = np.load(os.path.join(GOLD, 'features_ref_read.npz'))
+    f = NumpyFile(os.path.join(GOLD, 'features_ref.npy'))
+    assert len(f) == 5 and f.dim == 80 and f.dtype == np.float16
+    assert f.get_positions()[0].tolist() == [0, 1, 2, 3, 4] and np.array_equal(f.get_positions()[1], want['lengths'])
+    rows = list(f)
+    for i, r in enumerate(rows):
+        assert r.dtype == np.float16 and np.array_equal(r, want[f'row{i}']) and np.array_equal(f[i], want[f'row{i}'])
+    f.seek(2)
+    assert np.array_equal(next(f), want['third']) and f.tell() == 3
+    packed, offsets = f.pack([3, 0, 4])
+    assert offsets.tolist() == [0, 40, 47, 50] and np.array_equal(packed[40:47], want['row0'])
+
+
+def test_numpy_file_writer_is_byte_compatible(tmp_path):
+    from tests.golden.make_golden import numpy_file_features
+    path = str(tmp_path / 'ours.npy')
+    NumpyFile.build(path, numpy_file_features(), dtype='float16', num_feats=7)
+    assert open(path, 'rb').read() == open(os.path.join(GOLD, 'features_ref.npy'), 'rb').read()
+
+
 def test_state_dict_keys_match_reference():
     import json
     gold = torch.load(os.path.join(GOLD, 'st_tiny_model.pt'), weights_only=False)
