@@ -152,9 +152,11 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 4
+    # the SAME step as our arm: all 64 utterances of one GPU's batch per step (a few seconds each on the host cores)
+    batch = B_PER_GPU
     value, ms = time_oracle(batch, max(1, args.steps), max(0, args.warmup), threads)
-    sample = f'{batch} utterances x 10 s (of the {B_PER_GPU}-utterance step), {args.steps} steps after {args.warmup} warm-up'
+    sample = (f'full step: {batch} utterances x 10 s = {batch * (T_DEC - 1)} target tokens, {args.steps} steps after {args.warmup} '
+              f'warm-up; oracle port of the reference (numpy fbank+CMVN, torch-CPU fp32 model, Adam) on {threads} threads')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -181,6 +183,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-eager comparator leg (N = 1 only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -281,17 +284,27 @@ def main():
     h2d = pcm_host.numel() * 4 + dec_host.numel() * 8
     d2h = 8 * 8
 
-    # ---- dominant kernel roofline: the tcgen05 GEMM, all launches of one step timed with CUDA events ----
+    # ---- dominant kernel roofline (the tcgen05 GEMM) + per-family table, all launches of one step timed in situ ----
     # (every rank runs the instrumented step: it contains the gradient allreduce)
-    roofline, gemm_share, launches = gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step)
+    roofline, gemm_share, launches, families = step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step)
+    # ---- BASELINE's second metric: the fbank(+CMVN) frontend alone ----
+    fbank = time_fbank(pcm_dev, plan, rows, front) if rank == 0 else None
+    if fbank is not None:
+        families['fbank'] = {k: fbank[k] for k in ('ms_per_step', 'achieved', 'unit', 'peak', 'frac')}
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    cpu, eager = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, cms = time_oracle(4, 5, 1, threads)
+        n_utt, n_steps = 8, 3
+        v, cms = time_oracle(n_utt, n_steps, 1, threads)
         cpu = {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
-               'sample': '5 steps over 4 utterances x 10 s (192 target tokens each) after 1 warm-up step; oracle port '
-                         '(numpy fbank+CMVN, torch-CPU fp32 model, Adam)', 'ms_per_step': cms}
+               'sample': f'{n_steps} steps over {n_utt} of the step\'s {B_PER_GPU} utterances ({n_utt * (T_DEC - 1)} target tokens each) after 1 '
+                         f'warm-up step; oracle port of the reference (numpy fbank+CMVN, torch-CPU fp32 model, Adam); the full-size '
+                         f'step is what `--impl reference` times', 'ms_per_step': cms}
+    if rank == 0 and world == 1 and not args.no_eager:
+        del trainer, model          # free the arenas before the eager model is built
+        torch.cuda.empty_cache()
+        eager = time_gpu_eager(dev)
 
     if rank == 0:
         out = {
@@ -299,13 +312,151 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic', 'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': launches * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline, 'cpu_baseline': cpu,
+            'gpu_launches': launches * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline,
+            'cpu_baseline': cpu, 'fbank': fbank, 'families': families, 'gpu_eager': eager,
             'gemm_share_of_step': gemm_share, 'cuda_graph': use_graph,
             'last_step_logs': {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in last.items()},
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def time_fbank(pcm_dev, plan, rows, front, iters: int = 20) -> dict:
+    """frames/s and algorithmic GB/s of the fused fbank + utterance-CMVN frontend alone, on the step's own PCM batch
+    (resident in HBM), L2 flushed between launches (256 MB write), CUDA events, median. Algorithmic bytes = fp32 PCM in +
+    fp32 features out, each once (961.3 B per frame)."""
+    from pasero_b200 import frontend
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=pcm_dev.device)
+    for _ in range(3):
+        frontend.fbank(pcm_dev, plan, cmvn=True)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frontend.fbank(pcm_dev, plan, cmvn=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    nbytes = 4 * plan.total_samples + 4 * 80 * plan.total_frames
+    peaks = measured_peaks()
+    peak = peaks.get('hbm_gbs', 6650.0)
+    gbs = nbytes / ms / 1e6
+    return {'frames_per_s': plan.total_frames / (ms / 1e3), 'ms_per_step': ms, 'achieved': gbs, 'unit': 'GB/s', 'peak': peak,
+            'frac': gbs / peak, 'bound': 'hbm', 'algorithmic_bytes': nbytes, 'frames': plan.total_frames,
+            'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
+            'method': f'kernel alone, {iters} launches, L2 flushed between them, CUDA events, median; fp32 features out (the '
+                      'training step itself only keeps the bf16 padded layout)'}
+
+
+def time_gpu_eager(dev, steps: int = 10, warmup: int = 3) -> dict:
+    """Comparator demanded by SURVEY 8d: the SAME step written with stock PyTorch ops in bf16 on this GPU (cuDNN conv1d,
+    cuBLAS linears, F.scaled_dot_product_attention with a float key-padding mask as pasero/models/modules.py:659-718 builds it,
+    F.layer_norm, F.cross_entropy on fp32 logits as transformer.py:355-372, fused torch Adam) — what the reference's model
+    code dispatches to. Feature extraction = torchaudio.compliance.kaldi.fbank per utterance when torchaudio is present."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    d, f, c, H, V, Le, Ld = 512, 2048, 1024, 8, VOCAB, 12, 6
+    P = {}
+
+    def w(*shape):
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+        return torch.nn.Parameter((torch.randn(*shape, device=dev) * fan_in ** -0.5).to(torch.bfloat16))
+
+    def attn_params(p):
+        for n in ('q', 'k', 'v', 'o'):
+            P[f'{p}.{n}.w'], P[f'{p}.{n}.b'] = w(d, d), w(d)
+
+    def ln_params(p):
+        P[f'{p}.g'] = torch.nn.Parameter(torch.ones(d, device=dev, dtype=torch.bfloat16))
+        P[f'{p}.b'] = torch.nn.Parameter(torch.zeros(d, device=dev, dtype=torch.bfloat16))
+    P['c0.w'], P['c0.b'], P['c1.w'], P['c1.b'] = w(c, 80, 5), w(c), w(2 * d, c // 2, 5), w(2 * d)
+    for i in range(Le):
+        attn_params(f'e{i}.sa'); ln_params(f'e{i}.ln1'); ln_params(f'e{i}.ln2')
+        P[f'e{i}.fc1.w'], P[f'e{i}.fc1.b'], P[f'e{i}.fc2.w'], P[f'e{i}.fc2.b'] = w(f, d), w(f), w(d, f), w(d)
+    P['emb'] = w(V, d)
+    for i in range(Ld):
+        attn_params(f'd{i}.sa'); attn_params(f'd{i}.ca'); ln_params(f'd{i}.ln1'); ln_params(f'd{i}.ln2'); ln_params(f'd{i}.ln3')
+        P[f'd{i}.fc1.w'], P[f'd{i}.fc1.b'], P[f'd{i}.fc2.w'], P[f'd{i}.fc2.b'] = w(f, d), w(f), w(d, f), w(d)
+    opt = torch.optim.Adam(list(P.values()), lr=1e-5, fused=True)
+
+    def mha(p, x, mem, mask, causal):
+        B, T, _ = x.shape
+        S = mem.shape[1]
+        q = F.linear(x, P[f'{p}.q.w'], P[f'{p}.q.b']).view(B, T, H, 64).transpose(1, 2)
+        k = F.linear(mem, P[f'{p}.k.w'], P[f'{p}.k.b']).view(B, S, H, 64).transpose(1, 2)
+        v = F.linear(mem, P[f'{p}.v.w'], P[f'{p}.v.b']).view(B, S, H, 64).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=None if causal else mask, is_causal=causal)
+        return F.linear(o.transpose(1, 2).reshape(B, T, d), P[f'{p}.o.w'], P[f'{p}.o.b'])
+
+    def block(x, p, fn):
+        return F.layer_norm(x + F.dropout(fn(x), 0.1), (d,), P[f'{p}.g'], P[f'{p}.b'])
+
+    def ffn(p):
+        return lambda x: F.linear(F.relu(F.linear(x, P[f'{p}.fc1.w'], P[f'{p}.fc1.b'])), P[f'{p}.fc2.w'], P[f'{p}.fc2.b'])
+    try:
+        import torchaudio
+        kaldi = torchaudio.compliance.kaldi
+    except Exception:
+        kaldi = None
+    pcm, dec = synthetic_batch(0, B_PER_GPU)
+    pcm, dec = pcm.to(dev), dec.to(dev)
+    pos_e = torch.randn(250, d, device=dev, dtype=torch.bfloat16)
+    pos_d = torch.randn(T_DEC - 1, d, device=dev, dtype=torch.bfloat16)
+
+    def step():
+        if kaldi is not None:
+            feats = torch.stack([kaldi.fbank(pcm[b:b + 1] * 32768.0, num_mel_bins=80, sample_frequency=16000.0) for b in range(pcm.shape[0])])
+            feats = (feats - feats.mean(1, keepdim=True)) / feats.std(1, keepdim=True, unbiased=False)
+        else:
+            feats = torch.randn(pcm.shape[0], 998, 80, device=dev)
+        x = feats.to(torch.bfloat16).transpose(1, 2)
+        x = F.glu(F.conv1d(x, P['c0.w'], P['c0.b'], stride=2, padding=2), dim=1)
+        x = F.glu(F.conv1d(x, P['c1.w'], P['c1.b'], stride=2, padding=2), dim=1).transpose(1, 2)
+        B, S, _ = x.shape
+        x = F.dropout(x * math.sqrt(d) + pos_e[:S], 0.1)
+        mask = torch.zeros(B, 1, 1, S, device=dev, dtype=torch.bfloat16)      # float key-padding mask (all keys valid here)
+        for i in range(Le):
+            x = block(x, f'e{i}.ln1', lambda h: mha(f'e{i}.sa', h, h, mask, False))
+            x = block(x, f'e{i}.ln2', ffn(f'e{i}'))
+        y = F.dropout(F.embedding(dec[:, :-1], P['emb'], padding_idx=1) * math.sqrt(d) + pos_d, 0.1)
+        for i in range(Ld):
+            y = block(y, f'd{i}.ln1', lambda h: mha(f'd{i}.sa', h, h, None, True))
+            y = block(y, f'd{i}.ln2', lambda h: mha(f'd{i}.ca', h, x, mask, False))
+            y = block(y, f'd{i}.ln3', ffn(f'd{i}'))
+        logits = y @ P['emb'].T
+        loss = F.cross_entropy(logits.float().view(-1, V), dec[:, 1:].reshape(-1), ignore_index=1, reduction='sum', label_smoothing=0.1)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': B_PER_GPU * (T_DEC - 1) / (ms / 1e3), 'unit': 'tokens/s', 'ms_per_step': ms, 'steps': steps,
+            'what': 'stock PyTorch eager bf16 on this GPU: ' + ('torchaudio kaldi.fbank per utterance + CMVN, ' if kaldi is not None else
+                    '(torchaudio missing: random features, no fbank) ') + 'cuDNN conv1d + GLU, cuBLAS linears, F.scaled_dot_product_attention '
+                    '(float key-padding mask / is_causal), F.layer_norm, fp32 F.cross_entropy(label_smoothing), clip_grad_norm_, fused '
+                    'torch.optim.Adam; same shapes, dropout 0.1, random init; a comparator, not part of the product path'}
 
 
 def event_bracket_overhead(dev) -> float:
@@ -340,39 +491,50 @@ def event_bracket_overhead(dev) -> float:
     return max(0.0, chain(True) - chain(False))
 
 
-def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
-    """Live timing of the dominant kernel inside the real step: the CUDA graph of the step is re-captured with an
-    external-event record node before and after every pb200_gemm_bf16 launch, replayed, and the event pairs of the last
-    replay are read back. (Events around eager launches over-count: each bracket then also holds the host's launch
-    latency.) Split-K launches are timed with their memset and reduction kernels; FLOPs are the algorithmic 2*M*N*K."""
+def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step):
+    """Live timing of every kernel family inside the real step: the CUDA graph of the step is re-captured with an
+    external-event record node before and after every kernel wrapper (pb200_gemm_bf16 launches and all the others),
+    replayed, and the event pairs of the last replay are read back. (Events around eager launches over-count: each
+    bracket then also holds the host's launch latency.) Split-K launches are timed with their memset and reduction
+    kernels; FLOPs / bytes are the algorithmic ones (2*M*N*K per GEMM; pasero_b200.kernels work estimators).
+    Returns (roofline of the dominant kernel = the tcgen05 GEMM, its share of the step, launches per step, per-family table)."""
     from pasero_b200 import kernels as K
     from pasero_b200 import ops
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
+    peaks = measured_peaks()
     peak = peaks.get('bf16_tflops_sustained')
     peak_kind = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
     if peak is None:
         peak, peak_kind = 1400.0, 'fallback (B200_PROFILING.md, sustained)'
+    hbm = peaks.get('hbm_gbs', 6650.0)
     saved = dict(trainer._graphs)
     trainer._graphs.clear()
     K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = [], True, {'launches': 0}
+    K.PROFILE_ALL, K.PROFILE_WORK = [], []
     # kernel durations are taken with every kernel on ONE stream: in the production step the weight-gradient GEMMs run on
     # a second stream next to the dependent chain, where a bracket would also hold the time its kernel waited for SMs
     two_streams = ops.WgradStream.enabled
     ops.WgradStream.enabled = False
     serial_ms = ms_per_step
+    marks = []
+    orig_body = trainer._graph_body
+
+    def body(*a, **kw):
+        marks.append(len(K.PROFILE_ALL))
+        orig_body(*a, **kw)
+        marks.append(len(K.PROFILE_ALL))
+    trainer._graph_body = body
     try:
         step(pcm_dev, dec_dev)            # warm-up pass + capture (both go through the instrumented wrappers)
+        trainer._graph_body = orig_body
         if trainer._graphs:
             prof = K.PROFILE[len(K.PROFILE) // 2:]   # the event pairs recorded during capture = the graph's nodes
-            # one call = fbank + CMVN (2), warm-up body and captured body (N each), grad-norm + Adam (2)
+            # one call = fbank + CMVN, warm-up body and captured body (N each), grad-norm + Adam
             launches = (K.COUNT['launches'] - 4) // 2 + 4
+            other = list(zip(K.PROFILE_ALL, K.PROFILE_WORK))[marks[2]:marks[3]]   # non-GEMM wrappers of the captured body
         else:                                        # --no-graph: plain events around eager launches
             prof, launches = K.PROFILE, K.COUNT['launches']
-        K.PROFILE, K.COUNT = None, None
+            other = list(zip(K.PROFILE_ALL, K.PROFILE_WORK))
+        K.PROFILE, K.COUNT, K.PROFILE_ALL, K.PROFILE_WORK = None, None, None, None
         for _ in range(3):
             step(pcm_dev, dec_dev)        # replays: every event node is re-recorded
         torch.cuda.synchronize()
@@ -380,6 +542,30 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
         ms_raw = sum(s.elapsed_time(e) for _, s, e in prof)
         overhead = event_bracket_overhead(pcm_dev.device) if trainer._graphs else 0.0
         ms = ms_raw - overhead * len(prof)
+        # ---- per-family table ----
+        fam = {}
+        for ((tag, e0, e1), work) in other:
+            name = tag.split(' ')[0]
+            key = ('attention' if name.startswith('attention') else 'layernorm' if name.startswith('dropout_add_ln') else
+                   'loss' if name.startswith('ls_ce') else 'conv_glue' if name in ('glu_fwd', 'glu_bwd', 'col2im', 'pad_rows', 'gelu_fwd', 'gelu_bwd')
+                   else 'embedding' if name.startswith('embed') else 'gradient_flush' if name.startswith('grad32') else 'other')
+            g = fam.setdefault(key, {'launches': 0, 'ms': 0.0, 'work': 0.0, 'unit': None})
+            g['launches'] += 1
+            g['ms'] += max(0.0, e0.elapsed_time(e1) - overhead)
+            if work is not None:
+                g['unit'] = work[0]
+                g['work'] += work[1]
+        families = {'gemm': {'launches': len(prof), 'ms_per_step': ms, 'achieved': flops / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s',
+                             'peak': peak, 'frac': flops / (ms / 1e3) / 1e12 / peak}}
+        for key, g in fam.items():
+            row = {'launches': g['launches'], 'ms_per_step': g['ms']}
+            if g['unit'] == 'flop' and g['ms'] > 0:
+                a = g['work'] / (g['ms'] / 1e3) / 1e12
+                row.update({'achieved': a, 'unit': 'TFLOP/s', 'peak': peak, 'frac': a / peak})
+            elif g['unit'] == 'byte' and g['ms'] > 0:
+                a = g['work'] / (g['ms'] / 1e3) / 1e9
+                row.update({'achieved': a, 'unit': 'GB/s', 'peak': hbm, 'frac': a / hbm})
+            families[key] = row
         if os.environ.get('BENCH_GEMM_DUMP'):   # per-shape table on stderr
             groups = {}
             for (f, s_, e_), tag in zip(prof, K.PROFILE_TAGS[len(K.PROFILE_TAGS) - len(prof):]):
@@ -401,22 +587,36 @@ def gemm_roofline(trainer, step, pcm_dev, dec_dev, ms_per_step):
             torch.cuda.synchronize()
             serial_ms = e0.elapsed_time(e1) / 5
     finally:
+        trainer._graph_body = orig_body
         ops.WgradStream.enabled = two_streams
-        K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT = None, False, None
+        K.PROFILE, K.PROFILE_EXTERNAL, K.COUNT, K.PROFILE_ALL, K.PROFILE_WORK = None, False, None, None, None
         trainer._graphs.clear()
         trainer._graphs.update(saved)
     achieved = flops / (ms / 1e3) / 1e12
+    # DRAM traffic of the same kernels from the committed ncu pass (profiles/r02_traffic.json, tools/ncu_traffic.py): per step
+    traffic, ncu_frac = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        traffic = tr.get('gemm_dram_bytes_per_step')
+        if tr.get('gemm_ms_per_step_ncu'):
+            ncu_frac = flops / (tr['gemm_ms_per_step_ncu'] / 1e3) / 1e12 / peak
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'kernel': 'pb200::gemm_kernel (tcgen05 cta_group::2, all instantiations of one step)',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                'traffic_source': 'profiles/r02_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM '
+                                  'launches of one step' if traffic is not None else None,
+                'frac_from_ncu_launch_list': ncu_frac,
                 'launches_timed': len(prof), 'gemm_ms_per_step': ms, 'gemm_ms_per_step_raw': ms_raw,
                 'event_bracket_overhead_us': overhead * 1e3, 'achieved_raw': flops / (ms_raw / 1e3) / 1e12,
                 'algorithmic_gflop_per_step': flops / 1e9, 'peak_source': peak_kind,
                 'single_stream_step_ms': serial_ms,
                 'method': 'external CUDA-event record nodes around every GEMM launch inside the replayed step graph; the '
                           'bracket overhead (same bracket around a ~1 us kernel minus its un-instrumented chain time) is '
-                          'subtracted per launch; *_raw keep the uncorrected sums. Timed with all kernels on one stream '
-                          '(single_stream_step_ms); the production step overlaps the weight-gradient GEMMs on a second stream'}
-    return roofline, ms / serial_ms, launches
+                          'subtracted per launch; *_raw keep the uncorrected sums; frac_from_ncu_launch_list = the same FLOPs over '
+                          'the GEMM time of the committed ncu launch list (cold-cache, serialised). Timed with all kernels on one '
+                          'stream (single_stream_step_ms); the production step overlaps the weight-gradient GEMMs on a second stream'}
+    return roofline, ms / serial_ms, launches, families
 
 
 if __name__ == '__main__':

@@ -33,9 +33,15 @@ def _count(n: int) -> None:
 PROFILE_ALL = None   # list of (tag, start_event, end_event) for every non-GEMM wrapper call (tools/step_breakdown.py)
 
 
-def _bracketed(fn):
-    """Times a wrapper with external CUDA events when PROFILE_ALL is a list (instrumented graph capture)."""
+PROFILE_WORK = None  # parallel to PROFILE_ALL: (unit, amount) algorithmic work of the call, e.g. ('flop', 3.1e9), or None
+
+
+def _bracketed(fn=None, *, work=None):
+    """Times a wrapper with external CUDA events when PROFILE_ALL is a list (instrumented graph capture). `work(*args,
+    **kwargs) -> (unit, amount)`: the call's algorithmic FLOPs / bytes, for bench.py's per-family roofline table."""
     import functools
+    if fn is None:
+        return lambda f: _bracketed(f, work=work)
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
@@ -48,8 +54,25 @@ def _bracketed(fn):
         e1.record()
         shapes = 'x'.join(str(d) for a in args[:2] if torch.is_tensor(a) for d in a.shape)
         PROFILE_ALL.append((f'{fn.__name__} {shapes}', e0, e1))
+        if PROFILE_WORK is not None:
+            PROFILE_WORK.append(work(*args, **kwargs) if work is not None else None)
         return out
     return wrapper
+
+
+def _attn_flops(factor):
+    # 4 B H Lq Lk d FLOPs forward (QK^T and PV), half of it under a causal mask; backward = 2.5x (five GEMMs instead of two)
+    def work(*args, **kwargs):
+        B, H, Lq, Lk = (args[3:7] if factor == 1.0 else args[6:10])
+        causal = args[8] if factor == 1.0 else args[11]
+        return 'flop', factor * 4.0 * B * H * Lq * Lk * 64 * (0.5 if causal else 1.0)
+    return work
+
+
+def _ln_bytes(*args, **kwargs):
+    # dropout + residual + LayerNorm, forward or backward: four [M, D] bf16 streams
+    M, D = args[0].shape
+    return 'byte', 4.0 * M * D * 2
 
 
 def _ws(nbytes: int, device) -> Optional[Tensor]:
@@ -153,7 +176,7 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
-@_bracketed
+@_bracketed(work=_attn_flops(1.0))
 def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, kv_len: Optional[Tensor],
                   causal: bool, scale: float):
     """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection)."""
@@ -169,7 +192,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: 
     return o, lse
 
 
-@_bracketed
+@_bracketed(work=_attn_flops(2.5))
 def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, B: int, H: int, Lq: int,
                   Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor):
     lib = _lib.load()
@@ -189,7 +212,7 @@ def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse:
 # --------------------------------------------------------------------------------------------------
 # dropout + residual + LayerNorm
 # --------------------------------------------------------------------------------------------------
-@_bracketed
+@_bracketed(work=_ln_bytes)
 def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
                        eps: float, p: float, seed: int, offset: int, need_sum: bool = True, keep_out: Optional[Tensor] = None):
     lib = _lib.load()
@@ -209,7 +232,7 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     return (y if has_ln else sum_out), sum_out, mean, rstd
 
 
-@_bracketed
+@_bracketed(work=_ln_bytes)
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,
                        dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False,

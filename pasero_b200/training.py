@@ -250,6 +250,11 @@ class GradBuckets:
         self.pre_launch = None   # callable(bucket index) run on the compute stream before the bucket's allreduce
         self.pre_all = None      # callable() doing the same for the whole arena at once (allreduce_all)
         self.p2p = None          # P2PAllreduce: peer-memory kernel instead of the NCCL call (CUDA-graph capturable)
+        # list while the step's CUDA graph is being captured in "overlap" mode: instead of reducing a complete bucket, the
+        # capture records an EXTERNAL event (an event-record node of the graph) at the point where the bucket's gradients
+        # are final; after every replay the NCCL allreduces are enqueued on the side stream behind those events
+        # (`reduce_behind_events`), so they run next to the rest of the replayed backward
+        self.capture_events = None
         self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i) if self.use_autograd_hooks else None)
@@ -269,7 +274,11 @@ class GradBuckets:
         lo, hi = self.buckets[b]
         if self.pre_launch is not None:
             self.pre_launch(b)
-        if self.cuda:
+        if self.capture_events is not None:
+            event = torch.cuda.Event(external=True)
+            event.record()
+            self.capture_events.append((b, event))
+        elif self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 if self.p2p is not None:
@@ -309,6 +318,20 @@ class GradBuckets:
         self.pending = [-1] * len(self.buckets)
         self.launch_order = list(range(len(self.buckets)))
 
+    def reduce_behind_events(self, events: list, stats: Optional[Tensor], stats_event) -> None:
+        """After a replay of a graph captured with `capture_events`: the step scalars (final after the forward pass) and then
+        every bucket, in capture order (identical on all ranks), each allreduce waiting for its bucket's event node of THIS
+        replay; the current stream then waits for the side stream (before the optimizer kernels read the gradients)."""
+        with torch.cuda.stream(self.stream):
+            if stats is not None:
+                self.stream.wait_event(stats_event)
+                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+            for b, event in events:
+                lo, hi = self.buckets[b]
+                self.stream.wait_event(event)
+                dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
     def reduce_stats(self, stats: Tensor) -> None:
         """The step scalars alone (NCCL, 32 bytes): after a graph whose buckets were reduced by captured P2P kernels."""
         dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
@@ -318,6 +341,8 @@ class GradBuckets:
         for b in range(len(self.buckets)):
             if self.pending[b] != -1:
                 self._launch(b)
+        if self.capture_events is not None:
+            return      # nothing was launched on the side stream: there is nothing to rejoin inside the capture
         if stats is not None:
             if self.cuda:
                 self.stream.wait_stream(torch.cuda.current_stream())
@@ -394,6 +419,8 @@ class Trainer:
         # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
         # (tools/ddp_check.py) but the processes hang at teardown / in long runs on this stack (NCCL 2.28.9, torch 2.11)
         self.graph_collectives = os.environ.get('PB200_GRAPH_NCCL', '0') == '1'
+        # PB200_GRAPH_OVERLAP=0: one whole-arena allreduce between the step graph and the optimizer (the round-1 behaviour)
+        self.overlap_graph_allreduce = os.environ.get('PB200_GRAPH_OVERLAP', '1') != '0'
         # Peer-memory allreduce (PB200_P2P_ALLREDUCE=1): one capturable kernel per bucket, so the reductions are part of
         # the step graph and overlap backward. EXPERIMENTAL, off by default: verified at N = 2 (tools/ddp_check.py: update
         # == single-process accumulation, eager and graph; 9.41 -> 9.25 ms/step), but the one N = 8 run timed out and
@@ -437,8 +464,10 @@ class Trainer:
             out[k] = v
         return out
 
-    def _forward_backward(self, batch: dict):
+    def _forward_backward(self, batch: dict, after_forward=None):
         loss, logs = self.model(**batch)
+        if after_forward is not None:
+            after_forward()
         ops.ProjCEFn.unit_loss_grad = True      # the loss is the root of this backward (grad_output == 1): scoped to it
         try:
             loss.backward()
@@ -534,6 +563,9 @@ class Trainer:
         key = key + tuple(sorted((k, str(v)) for k, v in (batch.get('meta') or {}).items() if k != 'step'))
         self.model.train()
         p2p_graph = self.buckets is not None and self.buckets.p2p is not None
+        # data parallel, NCCL: the allreduces stay outside the graph (capturing them hangs on this stack) but are ordered
+        # behind external event nodes of the graph, one per bucket, so they overlap the replayed backward
+        overlap = self.buckets is not None and not self.graph_collectives and self.overlap_graph_allreduce
         if key not in self._graphs:
             static = {}
             for k, v in tensors.items():
@@ -563,33 +595,43 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             ops.DropoutState.offset = 0
+            events, stats_event = None, None
             if self.buckets is not None:
-                self.buckets.start_step(sync=in_graph)
-            with torch.cuda.graph(graph):
-                self._graph_body(static, extras)
-                if in_graph:
-                    self.buckets.finish(None if p2p_graph else self.stats)
-            self._graphs[key] = (graph, static)
-        graph, static = self._graphs[key]
+                self.buckets.start_step(sync=in_graph or overlap)
+                if overlap:
+                    events = self.buckets.capture_events = []
+                    stats_event = torch.cuda.Event(external=True)
+            try:
+                with torch.cuda.graph(graph):
+                    self._graph_body(static, extras, after_forward=stats_event.record if overlap else None)
+                    if in_graph or overlap:
+                        self.buckets.finish(None if (p2p_graph or overlap) else self.stats)
+            finally:
+                if self.buckets is not None:
+                    self.buckets.capture_events = None
+            self._graphs[key] = (graph, static, events, stats_event)
+        graph, static, events, stats_event = self._graphs[key]
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
         self._write_hyper()
         graph.replay()
         self.rng_base += 1
-        if self.buckets is not None and not self.graph_collectives:
+        if events is not None:
+            self.buckets.reduce_behind_events(events, self.stats, stats_event)
+        elif self.buckets is not None and not self.graph_collectives:
             self.buckets.allreduce_all(self.stats)
         elif p2p_graph:
             self.buckets.reduce_stats(self.stats)   # the buckets were reduced inside the graph
         self._optimizer_kernels()
         return self._finish_step()
 
-    def _graph_body(self, static: dict, extras: dict) -> None:
+    def _graph_body(self, static: dict, extras: dict, after_forward=None) -> None:
         self.stats.zero_()
         ops.DirectGrads.active = self.direct
         self.direct.start_step()
         batch = dict(static)
         batch.update(extras)
-        self._forward_backward(batch)
+        self._forward_backward(batch, after_forward)
         ops.WgradStream.join()                       # (a captured graph must end with every forked stream joined)
         if self.buckets is None:
             self.arena.flush32(self._ranges32_all)   # with buckets: flushed per bucket right before its allreduce
