@@ -224,7 +224,7 @@ def main():
     use_graph = not args.no_graph
 
     def step(pcm_flat, dec):
-        _, padded = frontend.fbank(pcm_flat, plan, cmvn=True, padded_frames=rows, front_pad=front)
+        _, padded = frontend.fbank(pcm_flat, plan, cmvn=True, padded_frames=rows, front_pad=front, keep_fp32=False)
         batch = {'encoder_input': padded, 'encoder_input_length': plan.frames_tensor, 'decoder_input': dec,
                  'padded_layout': (F,), 'meta': {}}
         if use_graph:
@@ -528,7 +528,7 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step):
         trainer._graph_body = orig_body
         if trainer._graphs:
             prof = K.PROFILE[len(K.PROFILE) // 2:]   # the event pairs recorded during capture = the graph's nodes
-            # one call = fbank + CMVN, warm-up body and captured body (N each), grad-norm + Adam
+            # one call = fbank + CMVN / layout (two launches), warm-up body and captured body (N each), grad-norm + Adam
             launches = (K.COUNT['launches'] - 4) // 2 + 4
             other = list(zip(K.PROFILE_ALL, K.PROFILE_WORK))[marks[2]:marks[3]]   # non-GEMM wrappers of the captured body
         else:                                        # --no-graph: plain events around eager launches

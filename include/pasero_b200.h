@@ -45,9 +45,14 @@ int32_t pb200_num_sms(void);
  *                  frames(b) = 1 + (samples(b) - 400) / 160  (pb200_fbank_num_frames)
  *   max_frames     host-side upper bound on frames per utterance (grid sizing)
  *   pcm_scale      multiplier applied to samples on load (32768 for [-1,1) floats)
- *   feats          fp32 [total_frames, 80] out; normalised in place when cmvn != 0
+ *   cmvn           bit 0: normalise per utterance; bit 1 (needs feats_bf16_padded): the fp32 rows are only scratch
+ *                  (they keep the raw log-mel values), the normalised features are written to the padded layout alone
+ *   feats          fp32 [total_frames, 80] out (16-byte aligned); normalised in place when cmvn == 1
  *   feats_bf16_padded  optional bf16 [batch, padded_frames, 80]: features of utterance b at rows
  *                  [front_pad, front_pad + frames(b)), zeros elsewhere (conv subsampler input layout)
+ *   workspace      pb200_fbank_workspace_bytes(batch) bytes (fp64 statistics + tile counters). It must be ZERO on first
+ *                  use; every successful call leaves it zeroed again, so a caller that keeps the buffer (one per stream)
+ *                  never issues a memset. One launch does everything (framing .. CMVN .. padded layout).
  * ---------------------------------------------------------------------------------------------- */
 int pb200_fbank_init(void);
 int64_t pb200_fbank_num_frames(int64_t num_samples);

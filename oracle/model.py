@@ -195,7 +195,7 @@ def encode(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tenso
         x = x + sd['encoder.embed_positions.weight'][cfg.positional_encoding_shift:cfg.positional_encoding_shift + x.shape[1]].unsqueeze(0)
     else:
         table = sinusoidal_table(max_len, cfg.embed_dim, cfg.positional_encoding_shift)
-        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
+        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype).to(x.device)
     if layer_outputs is not None:
         layer_outputs['enc_embed'] = x
     for i in range(cfg.encoder_layers):
@@ -218,7 +218,7 @@ def decode(cfg: STConfig, sd, enc: Tensor, enc_mask: Tensor, decoder_input: Tens
         x = x + sd['decoder.embed_positions.weight'][cfg.positional_encoding_shift:cfg.positional_encoding_shift + x.shape[1]].unsqueeze(0)
     else:
         table = sinusoidal_table(cfg.decoder_max_len, cfg.embed_dim, cfg.positional_encoding_shift)
-        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype)
+        x = x + positions(table, x.shape[1], cfg.positional_encoding_shift, x.dtype).to(x.device)
     for i in range(cfg.decoder_layers):
         x = decoder_layer(cfg, sd, f'decoder.layers.{i}.', x, enc, enc_mask)
         x = adapters(cfg, sd, f'decoder.layers.{i}.', x, cfg.extra.get('decoder_adapters', ('default',)))

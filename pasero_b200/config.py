@@ -1,7 +1,8 @@
 """Configuration surface of the ST training path, mirroring the reference's flat YAML / CLI option names
 (pasero/config.py: TransformerConfig :1054-1319, TrainingConfig :1469-1868, TranslationTaskConfig :1871-2090,
 DistributedConfig :500-546). Only the options this path reads are typed here; anything else found in a
-reference YAML is kept in `extra` (and rejected if it switches on a subsystem that is out of scope).
+reference YAML is kept in `extra` (and rejected if it switches on a subsystem that is out of scope); a key that is not an option of
+the reference either is an error, as in the reference (pasero/config.py:1748-1750).
 """
 from dataclasses import dataclass, field, fields
 from typing import Optional
@@ -217,6 +218,39 @@ class TrainingConfig(DistributedConfig):
         out._reference = cfg
         return out
 
+    @staticmethod
+    def reference_option_names() -> set:
+        """Every option name the reference's config classes declare (generated by tests/golden/make_golden.py options)."""
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_options.json')) as f:
+            return set(json.load(f))
+
+    @classmethod
+    def from_argv(cls, argv) -> 'TrainingConfig':
+        """The reference's command-line surface (pasero/config.py:1711-1760): `-c/--config FILE.yaml` first, then
+        `--option-name value...` overrides (CLI > YAML > defaults); a flag without a value is True, several values make a list."""
+        opts, i, argv = {}, 0, list(argv)
+        cli = {}
+        while i < len(argv):
+            tok = argv[i]
+            if tok in ('-c', '--config'):
+                with open(argv[i + 1]) as f:
+                    opts.update(yaml.safe_load(f) or {})
+                i += 2
+                continue
+            if not tok.startswith('--'):
+                raise ValueError(f'unexpected argument {tok!r}')
+            j = i + 1
+            vals = []
+            while j < len(argv) and not (argv[j].startswith('--') and not argv[j][2:3].isdigit()) and argv[j] != '-c':
+                vals.append(yaml.safe_load(argv[j]))
+                j += 1
+            cli[tok[2:].replace('-', '_')] = True if not vals else (vals[0] if len(vals) == 1 else vals)
+            i = j
+        opts.update(cli)
+        return cls.from_dict(opts)
+
     @classmethod
     def from_dict(cls, opts: dict) -> 'TrainingConfig':
         opts = {k.replace('-', '_'): v for k, v in opts.items()}
@@ -228,13 +262,25 @@ class TrainingConfig(DistributedConfig):
             raise NotImplementedError(f'arch {arch!r}: only {sorted(cls.ARCH_PRESETS)} are on the ST hot path')
         for k, v in cls.ARCH_PRESETS[arch].items():
             setattr(cfg.model_cfg, k, v)
+        def coerce(v):   # YAML 1.1 reads "1e-4" as a string: numbers written that way still mean numbers
+            if isinstance(v, str):
+                try:
+                    return float(v) if any(c in v for c in '.eE') else int(v)
+                except ValueError:
+                    return v
+            return v
         for k, v in opts.items():
+            v = [coerce(x) for x in v] if isinstance(v, list) else coerce(v)
             if k in model_fields:
                 setattr(cfg.model_cfg, k, v)
             elif k in train_fields:
                 setattr(cfg, k, tuple(v) if isinstance(v, list) else v)
             else:
                 cfg.extra[k] = v
+        # an option neither this path nor the reference knows is a typo: error, as the reference does (config.py:1748-1750)
+        unknown = sorted(set(cfg.extra) - cls.reference_option_names())
+        if unknown:
+            raise ValueError(f'unknown option(s): {", ".join(unknown)}')
         for k, v in cfg.extra.items():
             if v and any(k.startswith(p) for p in cls.OUT_OF_SCOPE):
                 raise NotImplementedError(f'option {k}={v!r} selects a subsystem outside the ST data-parallel path')

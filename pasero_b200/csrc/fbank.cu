@@ -1,12 +1,11 @@
 // pasero_b200 — fused Kaldi-compatible log-mel filterbank + utterance CMVN for 16 kHz PCM.
 //
-// One pass over the PCM: framing (25 ms / 10 ms, snip_edges), per-frame DC removal, pre-emphasis
-// 0.97, Povey window, zero-pad 400 -> 512, real FFT (as a 256-point complex FFT of the even/odd
-// packed signal, radix-4 Stockham in shared memory, one warp per frame), power spectrum, sparse
-// 80-bin mel projection, log(max(., FLT_EPSILON)). Per-utterance, per-bin sum / sum-of-squares are
-// accumulated in fp64 for the CMVN pass, which normalises in place (the 20 MB feature block of a
-// 64-utterance batch is still L2 resident) and can also emit the zero-padded bf16 layout that the
-// conv subsampler's TMA descriptors read.
+// One pass over the PCM: framing (25 ms / 10 ms, snip_edges), per-frame DC removal, pre-emphasis 0.97, Povey window,
+// zero-pad 400 -> 512, real FFT (a 256-point complex FFT of the even/odd packed frame, 16 lanes per frame, 16 x 16 in
+// registers), power spectrum, 80-bin mel projection, log(max(., FLT_EPSILON)), per-utterance mean / variance
+// normalisation, optionally straight into the zero-padded bf16 layout that the conv subsampler's TMA descriptors read.
+// fbank_kernel_v4 (below) does all of it in ONE persistent launch; fbank_kernel_v2 + cmvn_kernel are last round's
+// two-launch path, kept behind PB200_FBANK=v2 for A/B measurements.
 //
 // The reference has no fbank code (features are pre-extracted, pasero/files.py:103-192); the
 // arithmetic follows torchaudio.compliance.kaldi.fbank (kaldi.py:514-646, _get_window :154-217,
@@ -50,153 +49,6 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// radix-4 Stockham pass over 256 complex points held in shared memory; one warp, 2 butterflies/lane
-template <int NS>
-__device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst,
-                                         const float2* __restrict__ tw, int lane) {
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int j = lane + it * 32;          // 0..63
-        const int k = j & (NS - 1);
-        float2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
-        if (NS > 1) {
-            const int t = k * (64 / NS);       // twiddle index into W_256
-            v1 = cmul(v1, tw[t]);
-            v2 = cmul(v2, tw[2 * t]);
-            v3 = cmul(v3, tw[3 * t]);
-        }
-        // radix-4 butterfly (forward transform: multiply by -i)
-        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-        const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-        const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i * (v1 - v3)
-        const int d = ((j - k) << 2) + k;
-        dst[d] = make_float2(a0.x + a2.x, a0.y + a2.y);
-        dst[d + NS] = make_float2(a1.x + a3.x, a1.y + a3.y);
-        dst[d + 2 * NS] = make_float2(a0.x - a2.x, a0.y - a2.y);
-        dst[d + 3 * NS] = make_float2(a1.x - a3.x, a1.y - a3.y);
-    }
-}
-
-struct FbankSmem {
-    alignas(16) float samples[SAMPLES_PER_CTA + 8];
-    alignas(16) float out[FR_PER_CTA][NMEL];
-    alignas(16) float2 buf[FB_WARPS][2][NC];
-    alignas(16) float window[WIN];
-    alignas(16) float2 w256[NC];
-    alignas(16) float2 w512[NC + 1];
-    alignas(16) float mel_w[MAX_MEL_TAPS];
-    alignas(16) float power[FB_WARPS][NC + 8];
-    int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
-};
-
-__global__ void __launch_bounds__(FB_THREADS)
-fbank_kernel(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
-             const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
-             float pcm_scale) {
-    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
-    FbankSmem& s = *reinterpret_cast<FbankSmem*>(fb_smem_raw);
-    const int b = blockIdx.y;
-    const long long s0 = sample_off[b];
-    const long long f_begin = frame_off[b];
-    const int nframes = (int)(frame_off[b + 1] - f_begin);
-    const int f0 = blockIdx.x * FR_PER_CTA;
-    if (f0 >= nframes) return;
-    const int nf = min(FR_PER_CTA, nframes - f0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- stage constants and this tile's samples (coalesced; 16-byte vectors when aligned) ----
-    const FbankTables& T = g_fbank_tables;
-    for (int i = tid; i < WIN; i += FB_THREADS) s.window[i] = T.window[i];
-    for (int i = tid; i < NC; i += FB_THREADS) s.w256[i] = T.w256[i];
-    for (int i = tid; i <= NC; i += FB_THREADS) s.w512[i] = T.w512[i];
-    for (int i = tid; i < MAX_MEL_TAPS; i += FB_THREADS) s.mel_w[i] = T.mel_w[i];
-    for (int i = tid; i < NMEL; i += FB_THREADS) {
-        s.mel_start[i] = T.mel_start[i]; s.mel_len[i] = T.mel_len[i]; s.mel_off[i] = T.mel_off[i];
-    }
-    const int nsamp = (nf - 1) * SHIFT + WIN;
-    const float* src = pcm + s0 + (long long)f0 * SHIFT;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const int n4 = nsamp >> 2;
-        for (int i = tid; i < n4; i += FB_THREADS) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
-            reinterpret_cast<float4*>(s.samples)[i] = v;
-        }
-        for (int i = (n4 << 2) + tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    // ---- one warp per frame ----
-    for (int fr = warp; fr < nf; fr += FB_WARPS) {
-        const float* x = s.samples + fr * SHIFT;
-        float2* b0 = s.buf[warp][0];
-        float2* b1 = s.buf[warp][1];
-        // DC offset (mean over the 400-sample frame)
-        float sum = 0.f;
-        for (int i = lane; i < WIN; i += 32) sum += x[i] * pcm_scale;
-        const float mean = warp_sum(sum) * (1.0f / WIN);
-        // pre-emphasis + window, packed as z[n] = y[2n] + i y[2n+1]; zero-padded to 256 complex points
-        for (int n = lane; n < NC; n += 32) {
-            float2 z = make_float2(0.f, 0.f);
-            if (n < WIN / 2) {
-                const int j = 2 * n;
-                const float xm1 = x[j > 0 ? j - 1 : 0] * pcm_scale - mean;
-                const float x0 = x[j] * pcm_scale - mean;
-                const float x1 = x[j + 1] * pcm_scale - mean;
-                z.x = (x0 - 0.97f * xm1) * s.window[j];
-                z.y = (x1 - 0.97f * x0) * s.window[j + 1];
-            }
-            b0[n] = z;
-        }
-        __syncwarp();
-        fft_pass<1>(b0, b1, s.w256, lane);  __syncwarp();
-        fft_pass<4>(b1, b0, s.w256, lane);  __syncwarp();
-        fft_pass<16>(b0, b1, s.w256, lane); __syncwarp();
-        fft_pass<64>(b1, b0, s.w256, lane); __syncwarp();
-        // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
-        for (int k = lane; k <= NC; k += 32) {
-            const float2 zk = b0[k & (NC - 1)];
-            const float2 zc = b0[(NC - k) & (NC - 1)];
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            const float2 wo = cmul(s.w512[k], o);
-            const float re = e.x + wo.x, im = e.y + wo.y;
-            s.power[warp][k] = re * re + im * im;
-        }
-        __syncwarp();
-        // sparse mel projection + log
-        for (int m = lane; m < NMEL; m += 32) {
-            const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
-            float acc = 0.f;
-            for (int i = 0; i < ln; ++i) acc = fmaf(s.power[warp][st + i], s.mel_w[of + i], acc);
-            s.out[fr][m] = logf(fmaxf(acc, 1.1920928955078125e-07f));
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- coalesced store of the [nf x 80] tile, and fp64 per-bin statistics for CMVN ----
-    float* dst = feats + (f_begin + f0) * NMEL;
-    const float* so = &s.out[0][0];
-    const int total = nf * NMEL;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        for (int i = tid; i < (total >> 2); i += FB_THREADS)
-            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(so)[i];
-    } else {
-        for (int i = tid; i < total; i += FB_THREADS) dst[i] = so[i];
-    }
-    if (stats != nullptr && tid < NMEL) {
-        double sm = 0.0, sq = 0.0;
-        for (int fr = 0; fr < nf; ++fr) {
-            const double v = (double)s.out[fr][tid];
-            sm += v; sq += v * v;
-        }
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], sm);
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], sq);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // v2: register-resident FFT. 16 lanes per frame (two frames per warp), 16 complex points per lane.
@@ -389,161 +241,372 @@ fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sam
     }
 }
 
-// v3 (experimental, PB200_FBANK=v3): v2 with a leaner shared-memory footprint — the power spectrum reuses the transpose
-// tile, the log-mel rows go straight to global memory and the CMVN statistics are pre-reduced in shared memory — so that
-// three CTAs (24 warps) instead of two fit an SM: v2 is issue/latency bound at ~0.3 IPC per scheduler with 4 warps each.
-struct FbankSmem3 {
-    alignas(16) float samples[SAMPLES_PER_CTA + 8];
-    double stat[NMEL][2];
-    alignas(16) float2 tile[FB_WARPS][2][FB2_TILE];
-    alignas(16) float window[WIN];
-    alignas(16) float2 w256[NC];
-    alignas(16) float2 w512[NC + 1];
-    alignas(16) float mel_w[MAX_MEL_TAPS];
-    int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
+
+// ---------------------------------------------------------------------------------------------
+// v4 (default): ONE persistent kernel for framing, windowing, FFT, mel, log AND the utterance CMVN.
+//
+//   * grid = 2 CTAs per SM, each walks a contiguous range of 32-frame tiles; the tile's 5 360 PCM samples arrive by
+//     cp.async into a double buffer while the previous tile is being transformed (no register staging);
+//   * 16 lanes per frame as in v2 (256-point complex FFT of the even/odd packed frame as 16 x 16, one padded shared-memory
+//     transpose), but every per-lane constant lives in registers for the life of the CTA: the lane's 26 window taps
+//     (pre-multiplied by the PCM scale), its 15 inter-stage twiddles, its untangle phase; DC removal and pre-emphasis are
+//     folded into one 3-instruction form  z[j] = w[j] * (x[j] - 0.97 x[j-1] - 0.03 mean)  and the frame is read from shared
+//     memory exactly once (the DC sum comes from the same registers);
+//   * the real-FFT untangle exchanges Z[k] <-> Z[256-k] between lanes l and 16-l with shuffles (no shared-memory round
+//     trip) and needs no twiddle table: W512^(16 k1 + l) = W32^k1 (immediates after unrolling) * W512^l (lane constant);
+//   * mel projection through the triangle-complement identity: the 81 intervals between consecutive filter centres
+//     partition the FFT bins; with T_j = sum of P over interval j and U_j = sum of u_k P (u_k = position of bin k inside
+//     its interval), filter m = U_m + (T_{m+1} - U_{m+1}). Each power value is read once instead of twice, and the power
+//     spectrum is stored in a permuted, padded layout (built on the host) in which lane l finds interval l + 16 i at a
+//     fixed offset: the 20-step accumulation is fully unrolled, conflict free and free of per-lane loop bounds;
+//   * the tile's log-mel rows are staged in shared memory, copied out with one coalesced pass and summed per bin in fp64
+//     (E[x^2] - mean^2 needs every bit); the sums stay in registers across the tiles of one utterance and end in the
+//     utterance's global accumulators with one atomicAdd per bin and run;
+//   * utterance CMVN + output layouts are a second, PDL-launched, fully parallel pass (cmvn_layout_kernel) over the rows,
+//     which are still L2 resident: a "last CTA of the utterance normalises it" variant inside this kernel was measured
+//     first and left 148 SMs idle behind 64 finalising CTAs (~20 us of tail, ncu: SMs active 76 % of the duration).
+// ---------------------------------------------------------------------------------------------
+static constexpr int F4_THREADS = 256;
+static constexpr int F4_HW = F4_THREADS / 16;                        // half-warps per CTA
+static constexpr int F4_FRAMES = 2 * F4_HW;                          // frames per tile
+static constexpr int F4_SAMPLES = (F4_FRAMES - 1) * SHIFT + WIN;     // 5360
+static constexpr int F4_NGROUP = 5;                                  // mel intervals per lane (j = lane + 16 i)
+// Slot of bin k = group base + F4_STRIDE * (position inside its interval) + lane. Loads (fixed position, consecutive lanes)
+// are conflict free for any stride; stride 19 and rows of 400 floats (the two half-warps of a warp 16 banks apart) keep
+// the scattered stores of 16 consecutive bins at <= 2 wavefronts (exhaustive search over strides / offsets; 17 gave 3.5).
+static constexpr int F4_STRIDE = 19;
+// widest interval (FFT bins) of each group (checked on the host) and the group's first slot = stride * running sum of the widths
+__host__ __device__ constexpr int f4_maxc(int i) { return i == 0 ? 2 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 5 : 8; }
+__host__ __device__ constexpr int f4_base(int i) { return F4_STRIDE * (i == 0 ? 0 : i == 1 ? 2 : i == 2 ? 4 : i == 3 ? 7 : 12); }
+static constexpr int F4_LAST = 20 * 19;                              // interval 80 (8 bins): one bin per lane 0..7
+static constexpr int F4_TRASH = F4_LAST + 8;                         // bin 0 (below the 20 Hz cut-off)
+static constexpr int F4_PB = 400;
+
+struct Fbank4Tables {
+    short perm[NC];        // FFT bin k -> slot in the permuted power buffer
+    float uperm[F4_PB];    // slot -> u_k (0 for unused slots)
+};
+__device__ Fbank4Tables g_fbank4_tables;
+
+struct Fbank4Smem {
+    alignas(16) float samples[2][F4_SAMPLES + 16];      // + 16: the window's zero taps of the last frame read past the tile
+    alignas(16) float2 tile[F4_HW][FB2_TILE];
+    alignas(16) float pbuf[F4_HW][F4_PB];
+    alignas(16) float uperm[F4_PB];
+    alignas(16) uint32_t pperm[2][16][4];   // lane -> byte offsets into its power buffer of bins 16 k1 + lane, two per word
+    alignas(16) float stash[F4_FRAMES][NMEL];   // the tile's log-mel rows: coalesced store + exact (fp64) statistics
 };
 
-__global__ void __launch_bounds__(FB_THREADS)
-fbank_kernel_v3(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
-                const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
-                float pcm_scale) {
-    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
-    FbankSmem3& s = *reinterpret_cast<FbankSmem3*>(fb_smem_raw);
-    const int b = blockIdx.y;
-    const long long s0 = sample_off[b];
-    const long long f_begin = frame_off[b];
-    const int nframes = (int)(frame_off[b + 1] - f_begin);
-    const int f0 = blockIdx.x * FR_PER_CTA;
-    if (f0 >= nframes) return;
-    const int nf = min(FR_PER_CTA, nframes - f0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int hl = lane & 15, half = lane >> 4;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-    const FbankTables& T = g_fbank_tables;
-    for (int i = tid; i < WIN; i += FB_THREADS) s.window[i] = T.window[i];
-    for (int i = tid; i < NC; i += FB_THREADS) s.w256[i] = T.w256[i];
-    for (int i = tid; i <= NC; i += FB_THREADS) s.w512[i] = T.w512[i];
-    for (int i = tid; i < MAX_MEL_TAPS; i += FB_THREADS) s.mel_w[i] = T.mel_w[i];
-    for (int i = tid; i < NMEL; i += FB_THREADS) {
-        s.mel_start[i] = T.mel_start[i]; s.mel_len[i] = T.mel_len[i]; s.mel_off[i] = T.mel_off[i];
-        s.stat[i][0] = 0.0; s.stat[i][1] = 0.0;
-    }
-    const int nsamp = (nf - 1) * SHIFT + WIN;
-    const float* src = pcm + s0 + (long long)f0 * SHIFT;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const int n4 = nsamp >> 2;
-        for (int i = tid; i < n4; i += FB_THREADS) reinterpret_cast<float4*>(s.samples)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        for (int i = (n4 << 2) + tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    float2* tile = s.tile[warp][half];
-    float* pw = reinterpret_cast<float*>(tile);   // the power spectrum (257 floats) overwrites the tile once Z has been read
-    float* dst = feats + (f_begin + f0) * NMEL;
-    float st_sum[NMEL / 16], st_sq[NMEL / 16];     // CMVN statistics of this lane's 5 mel bins over this half-warp's frames
-#pragma unroll
-    for (int i = 0; i < NMEL / 16; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
-    // two frames per warp iteration; frames beyond nf are computed on frame nf - 1 and not stored (keeps the warp converged)
-    for (int fr0 = warp * 2; fr0 < nf; fr0 += FB_WARPS * 2) {
-        const int fr = fr0 + half;
-        const bool live = fr < nf;
-        const float* x = s.samples + (live ? fr : nf - 1) * SHIFT;
-        // DC offset over the 400 samples of the frame
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < WIN / 16; ++i) sum += x[hl + 16 * i] * pcm_scale;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.0f / WIN);
-        // z[n] = y[2n] + i y[2n+1], n = hl + 16 n2 (pre-emphasis 0.97, Povey window, zero-padded beyond 200)
-        float2 v[16];
-#pragma unroll
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const int n = hl + 16 * n2;
-            float2 z = make_float2(0.f, 0.f);
-            if (n < WIN / 2) {
-                const int j = 2 * n;
-                const float xm1 = x[j > 0 ? j - 1 : 0] * pcm_scale - mean;
-                const float x0 = x[j] * pcm_scale - mean;
-                const float x1 = x[j + 1] * pcm_scale - mean;
-                z.x = (x0 - 0.97f * xm1) * s.window[j];
-                z.y = (x1 - 0.97f * x0) * s.window[j + 1];
-            }
-            v[n2] = z;
-        }
-        dft16(v);                                   // A[n1 = hl][k2]
-#pragma unroll
-        for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], s.w256[(hl * k2) & (NC - 1)]);
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) tile[k2 * 17 + hl] = v[k2];   // transpose through the padded tile
-        __syncwarp();
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = tile[hl * 17 + n1];   // lane k2 = hl: A'[n1][k2]
-        __syncwarp();
-        dft16(v);                                   // Z[16 k1 + hl] in v[k1]
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) tile[16 * k1 + hl] = v[k1];
-        __syncwarp();
-        // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
-        auto untangle = [&](int k) -> float {
-            const float2 zk = tile[k & (NC - 1)];
-            const float2 zc = tile[(NC - k) & (NC - 1)];
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            const float2 wo = cmul(s.w512[k], o);
-            const float re = e.x + wo.x, im = e.y + wo.y;
-            return re * re + im * im;
-        };
-        float pk[17];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = untangle(hl + 16 * i);    // independent iterations: loads overlap
-        pk[16] = untangle(NC);                                           // (every lane computes it, lane 0 stores it)
-        __syncwarp();                                                    // every Z value has been read: the tile may go
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pw[hl + 16 * i] = pk[i];
-        if (hl == 0) pw[NC] = pk[16];
-        __syncwarp();
-        // sparse mel projection + log: 80 bins over the 16 lanes
-#pragma unroll
-        for (int mi = 0; mi < NMEL / 16; ++mi) {
-            const int m = hl + 16 * mi;
-            const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four partial sums: the tap loop is a latency chain otherwise
-            int i = 0;
-            for (; i + 4 <= ln; i += 4) {
-                a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
-                a1 = fmaf(pw[st + i + 1], s.mel_w[of + i + 1], a1);
-                a2 = fmaf(pw[st + i + 2], s.mel_w[of + i + 2], a2);
-                a3 = fmaf(pw[st + i + 3], s.mel_w[of + i + 3], a3);
-            }
-            for (; i < ln; ++i) a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
-            const float acc = (a0 + a1) + (a2 + a3);
-            if (live) {
-                const float val = logf(fmaxf(acc, 1.1920928955078125e-07f));
-                dst[(long long)fr * NMEL + m] = val;
-                st_sum[mi] += val; st_sq[mi] = fmaf(val, val, st_sq[mi]);
-            }
-        }
-        __syncwarp();
-    }
-    if (stats != nullptr) {
-#pragma unroll
-        for (int mi = 0; mi < NMEL / 16; ++mi) {
-            atomicAdd(&s.stat[hl + 16 * mi][0], (double)st_sum[mi]);
-            atomicAdd(&s.stat[hl + 16 * mi][1], (double)st_sq[mi]);
-        }
-    }
-    __syncthreads();
-
-    if (stats != nullptr && tid < NMEL) {
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], s.stat[tid][0]);
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], s.stat[tid][1]);
+// W32^k = exp(-2 pi i k / 32) as (cos, sin) of the positive angle; k is a compile-time constant after unrolling
+__device__ __forceinline__ float2 cs32(int k) {
+    switch (k) {
+        case 0: return make_float2(1.f, 0.f);
+        case 1: return make_float2(0.98078528040323043f, 0.19509032201612825f);
+        case 2: return make_float2(0.92387953251128674f, 0.38268343236508978f);
+        case 3: return make_float2(0.83146961230254524f, 0.55557023301960218f);
+        case 4: return make_float2(0.70710678118654752f, 0.70710678118654752f);
+        case 5: return make_float2(0.55557023301960218f, 0.83146961230254524f);
+        case 6: return make_float2(0.38268343236508978f, 0.92387953251128674f);
+        case 7: return make_float2(0.19509032201612825f, 0.98078528040323043f);
+        case 8: return make_float2(0.f, 1.f);
+        case 9: return make_float2(-0.19509032201612825f, 0.98078528040323043f);
+        case 10: return make_float2(-0.38268343236508978f, 0.92387953251128674f);
+        case 11: return make_float2(-0.55557023301960218f, 0.83146961230254524f);
+        case 12: return make_float2(-0.70710678118654752f, 0.70710678118654752f);
+        case 13: return make_float2(-0.83146961230254524f, 0.55557023301960218f);
+        case 14: return make_float2(-0.92387953251128674f, 0.38268343236508978f);
+        default: return make_float2(-0.98078528040323043f, 0.19509032201612825f);
     }
 }
 
-// CMVN: x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) with fp64 statistics, in place; optionally
+// stats == nullptr: no statistics wanted (no CMVN pass follows)
+__global__ void __launch_bounds__(F4_THREADS, 2)
+fbank_kernel_v4(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
+                const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
+                int batch, int tiles_per_utt, float pcm_scale) {
+    pdl_trigger();      // the CMVN / layout kernel may be scheduled as soon as SMs free up (it waits for this grid's completion)
+    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
+    Fbank4Smem& sm = *reinterpret_cast<Fbank4Smem*>(fb_smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hl = lane & 15, half = lane >> 4, hw = warp * 2 + half;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- lane constants ----
+    const FbankTables& T = g_fbank_tables;
+    float wr[26];
+#pragma unroll
+    for (int n2 = 0; n2 < 13; ++n2) {
+        const int j = 2 * hl + 32 * n2;
+        wr[2 * n2] = j < WIN ? T.window[j] * pcm_scale : 0.f;
+        wr[2 * n2 + 1] = j + 1 < WIN ? T.window[j + 1] * pcm_scale : 0.f;
+    }
+    float2 tw[16];
+#pragma unroll
+    for (int k2 = 1; k2 < 16; ++k2) tw[k2] = T.w256[(hl * k2) & (NC - 1)];
+    const float2 g = make_float2(T.w512[hl].y, -T.w512[hl].x);      // -i * W512^hl
+    if (tid < 128) {
+        const int l = tid >> 3, q = tid & 7;
+        sm.pperm[q >> 2][l][q & 3] = (uint32_t)g_fbank4_tables.perm[16 * (2 * q) + l] * 4u |
+                         ((uint32_t)g_fbank4_tables.perm[16 * (2 * q + 1) + l] * 4u) << 16;
+    }
+    for (int i = tid; i < F4_PB; i += F4_THREADS) sm.uperm[i] = g_fbank4_tables.uperm[i];
+    for (int i = tid; i < F4_HW * F4_PB; i += F4_THREADS) (&sm.pbuf[0][0])[i] = 0.f;    // unused slots stay 0 for good
+    for (int i = tid; i < 2 * (F4_SAMPLES + 16); i += F4_THREADS) (&sm.samples[0][0])[i] = 0.f;   // never a NaN bit pattern
+
+    __syncthreads();
+
+    const long long total_tiles = (long long)batch * tiles_per_utt;
+    const int t_hi = (int)(((long long)blockIdx.x + 1) * total_tiles / gridDim.x);
+    // first non-empty tile at or after t (CTA-uniform)
+    auto next_tile = [&](int t) {
+        while (t < t_hi) {
+            const int b = t / tiles_per_utt;
+            const int nframes = (int)(frame_off[b + 1] - frame_off[b]);
+            if ((t - b * tiles_per_utt) * F4_FRAMES < nframes) break;
+            ++t;
+        }
+        return t;
+    };
+    auto issue_loads = [&](int t, int buf) {
+        const int b = t / tiles_per_utt, f0 = (t - b * tiles_per_utt) * F4_FRAMES;
+        const int nframes = (int)(frame_off[b + 1] - frame_off[b]);
+        const int nf = min(F4_FRAMES, nframes - f0);
+        const int nsamp = (nf - 1) * SHIFT + WIN;                 // a multiple of 4
+        const float* src = pcm + sample_off[b] + (long long)f0 * SHIFT;
+        float* dst = sm.samples[buf];
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid; i < (nsamp >> 2); i += F4_THREADS) cp_async16(dst + 4 * i, src + 4 * i);
+        } else {
+            for (int i = tid; i < nsamp; i += F4_THREADS) cp_async4(dst + i, src + i);
+        }
+    };
+
+    double s1 = 0.0, s2 = 0.0;      // threads 0..79: sum / sum of squares of bin `tid` over the current run of tiles
+    int run_b = -1;
+
+    // statistics of the finished run of tiles (all of utterance b) -> the utterance's fp64 accumulators
+    auto flush = [&](int b) {
+        if (stats != nullptr && tid < NMEL) {
+            atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], s1);
+            atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], s2);
+        }
+        s1 = s2 = 0.0;
+    };
+
+    int cur = next_tile((int)((long long)blockIdx.x * total_tiles / gridDim.x));
+    int buf = 0;
+    if (cur < t_hi) issue_loads(cur, buf);
+    cp_async_commit();
+    float2* tile = sm.tile[hw];
+    float* pb = sm.pbuf[hw];
+
+    while (cur < t_hi) {
+        const int b = cur / tiles_per_utt, f0 = (cur - b * tiles_per_utt) * F4_FRAMES;
+        const long long f_begin = frame_off[b];
+        const int nf = min(F4_FRAMES, (int)(frame_off[b + 1] - f_begin) - f0);
+        if (b != run_b) {
+            if (run_b >= 0) flush(run_b);
+            run_b = b;
+        }
+        cp_async_wait_all();
+        __syncthreads();                       // the tile's samples are visible; everybody is done with the other buffer
+        const int nxt = next_tile(cur + 1);
+        if (nxt < t_hi) issue_loads(nxt, buf ^ 1);
+        cp_async_commit();
+
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int fr = hw + F4_HW * rr;
+            const bool live = fr < nf;
+            const float* x = sm.samples[buf] + (live ? fr : nf - 1) * SHIFT;   // dead lanes redo the last frame (no store)
+            float2 v[16];
+            float xm[13];
+            float sum = 0.f;
+#pragma unroll
+            for (int n2 = 0; n2 < 13; ++n2) {
+                // n2 == 12, lanes >= 8: samples 400.. of the frame. Their window taps are 0 and the sample buffers only ever
+                // hold finite values (zero-filled at start), so they are loaded like the rest and only kept out of the DC sum
+                const int j = 2 * hl + 32 * n2;
+                v[n2] = *reinterpret_cast<const float2*>(x + j);
+                xm[n2] = x[(n2 == 0 && hl == 0) ? 0 : j - 1];
+                const float part = v[n2].x + v[n2].y;
+                sum += (n2 < 12 || hl < 8) ? part : 0.f;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+            const float c = sum * ((1.f - 0.97f) / WIN);        // pre-emphasised DC offset
+#pragma unroll
+            for (int n2 = 0; n2 < 13; ++n2) {
+                const float y0 = fmaf(-0.97f, xm[n2], v[n2].x) - c;
+                const float y1 = fmaf(-0.97f, v[n2].x, v[n2].y) - c;
+                v[n2] = make_float2(wr[2 * n2] * y0, wr[2 * n2 + 1] * y1);
+            }
+            v[13] = v[14] = v[15] = make_float2(0.f, 0.f);
+            dft16(v);                                   // A[n1 = hl][k2]
+#pragma unroll
+            for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], tw[k2]);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) tile[k2 * 17 + hl] = v[k2];
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = tile[hl * 17 + n1];
+            __syncwarp();
+            dft16(v);                                   // Z[16 k1 + hl] in v[k1]
+            // real-FFT untangle: 2 X[k] = (Z[k] + conj Z[256-k]) + (-i W512^k) (Z[k] - conj Z[256-k]);  Z[256-k] sits in
+            // lane 16 - hl, register 15 - k1 (lane 0: its own register 16 - k1)
+            uint32_t pq[8];
+            {
+                const uint4 a = *reinterpret_cast<const uint4*>(&sm.pperm[0][hl][0]);
+                const uint4 bq = *reinterpret_cast<const uint4*>(&sm.pperm[1][hl][0]);
+                pq[0] = a.x; pq[1] = a.y; pq[2] = a.z; pq[3] = a.w; pq[4] = bq.x; pq[5] = bq.y; pq[6] = bq.z; pq[7] = bq.w;
+            }
+            char* pbytes = reinterpret_cast<char*>(pb);
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const float2 give = v[15 - k1];
+                float2 zc;
+                zc.x = __shfl_sync(FULL, give.x, (16 - hl) & 15, 16);
+                zc.y = __shfl_sync(FULL, give.y, (16 - hl) & 15, 16);
+                if (hl == 0) zc = v[(16 - k1) & 15];
+                const float2 zk = v[k1];
+                const float sx = zk.x + zc.x, sy = zk.y - zc.y;
+                const float dx = zk.x - zc.x, dy = zk.y + zc.y;
+                const float tx = g.x * dx - g.y * dy, ty = g.x * dy + g.y * dx;
+                const float2 w = cs32(k1);              // W32^k1 = (w.x, -w.y)
+                const float xr = fmaf(w.x, tx, fmaf(w.y, ty, sx));
+                const float xi = fmaf(w.x, ty, fmaf(-w.y, tx, sy));
+                const uint32_t off = (k1 & 1) ? pq[k1 >> 1] >> 16 : pq[k1 >> 1] & 0xffffu;
+                *reinterpret_cast<float*>(pbytes + off) = fmaf(xr, xr, xi * xi);    // 4 |X[k]|^2
+            }
+            __syncwarp();
+            float um[F4_NGROUP], vm[F4_NGROUP];
+#pragma unroll
+            for (int i = 0; i < F4_NGROUP; ++i) {
+                float ts = 0.f, us = 0.f;
+#pragma unroll
+                for (int t = 0; t < f4_maxc(i); ++t) {
+                    const float pv = pb[f4_base(i) + F4_STRIDE * t + hl];
+                    ts += pv;
+                    us = fmaf(sm.uperm[f4_base(i) + F4_STRIDE * t + hl], pv, us);
+                }
+                um[i] = us; vm[i] = ts - us;
+            }
+            // interval 80: one bin per lane 0..7; lanes 8..15 read slots whose u is 1 (contribution pv - 1 * pv = 0)
+            float v80;
+            { const float pv = pb[F4_LAST + hl]; v80 = fmaf(-sm.uperm[F4_LAST + hl], pv, pv); }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v80 += __shfl_xor_sync(FULL, v80, o);
+            __syncwarp();                               // pbuf / tile are free for the next frame
+            float nb[F4_NGROUP];
+#pragma unroll
+            for (int i = 0; i < F4_NGROUP; ++i) nb[i] = __shfl_sync(FULL, vm[i], (hl + 1) & 15, 16);
+            float* dst = &sm.stash[live ? fr : 0][hl];
+#pragma unroll
+            for (int i = 0; i < F4_NGROUP; ++i) {
+                const float up = hl < 15 ? nb[i] : (i < F4_NGROUP - 1 ? nb[i + 1 < F4_NGROUP ? i + 1 : i] : v80);
+                const float mel4 = um[i] + up;
+                // mel = mel4 / 4: log(max(mel, eps)) = log(max(mel4, 4 eps)) - log 4
+                const float val = logf(fmaxf(mel4, 4.f * 1.1920928955078125e-07f)) - 1.3862943611198906f;
+                if (live) dst[16 * i] = val;
+            }
+        }
+        __syncthreads();
+        {   // the tile's rows: one coalesced copy to global memory, and bin `tid`'s statistics in fp64
+            float4* out4 = reinterpret_cast<float4*>(feats + (f_begin + f0) * NMEL);
+            const float4* st4 = reinterpret_cast<const float4*>(&sm.stash[0][0]);
+            for (int i = tid; i < nf * (NMEL / 4); i += F4_THREADS) out4[i] = st4[i];
+            if (tid < NMEL && stats != nullptr) {
+                for (int fr = 0; fr < nf; ++fr) {
+                    const double val = (double)sm.stash[fr][tid];
+                    s1 += val;
+                    s2 = fma(val, val, s2);
+                }
+            }
+        }
+        cur = nxt;
+        buf ^= 1;
+    }
+    if (run_b >= 0) flush(run_b);
+}
+
+
+// Utterance CMVN + output layouts (second pass of v4): x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) from the fp64
+// statistics. One CTA per (utterance, block of CM_ROWS output rows); 16-byte accesses; writes the fp32 rows in place
+// (mode bit 0 without bit 1) and / or the zero-padded bf16 layout (features of utterance b at rows [front_pad, front_pad +
+// frames(b)), zeros elsewhere). The last CTA to finish clears the statistics and its own counter: the workspace is left
+// zeroed for the next call (no memset in the step).
+static constexpr int CM_ROWS = 32;
+__global__ void __launch_bounds__(256)
+cmvn_layout_kernel(float* __restrict__ feats, const long long* __restrict__ frame_off, double* __restrict__ stats,
+                   int* __restrict__ done, int batch, int mode, bf16* __restrict__ padded, int padded_frames, int front_pad,
+                   int row_blocks) {
+    __shared__ __align__(16) float s_mean[NMEL];
+    __shared__ __align__(16) float s_rstd[NMEL];
+    __shared__ int s_last;
+    const int b = blockIdx.x / row_blocks, rb = blockIdx.x - b * row_blocks;
+    const int tid = threadIdx.x;
+    pdl_wait();                 // the fbank kernel's rows and statistics are complete and visible
+    const long long f_begin = frame_off[b];
+    const int nframes = (int)(frame_off[b + 1] - f_begin);
+    const int rows = padded != nullptr ? padded_frames : nframes;
+    const int r0 = rb * CM_ROWS, r1 = min(rows, r0 + CM_ROWS);
+    if (r0 < r1) {
+        if (tid < NMEL) {
+            float mean = 0.f, rstd = 1.f;
+            if ((mode & 1) && nframes > 0) {
+                const double sm1 = __ldcg(&stats[((long long)b * NMEL + tid) * 2 + 0]);
+                const double sm2 = __ldcg(&stats[((long long)b * NMEL + tid) * 2 + 1]);
+                const double mu = sm1 / nframes;
+                double var = sm2 / nframes - mu * mu;
+                if (var < 1e-10) var = 1e-10;
+                mean = (float)mu;
+                rstd = (float)(1.0 / sqrt(var));
+            }
+            s_mean[tid] = mean; s_rstd[tid] = rstd;
+        }
+        __syncthreads();
+        const bool write_f32 = (mode & 1) && !(mode & 2);
+        for (int i = tid; i < (r1 - r0) * (NMEL / 4); i += 256) {
+            const int r = r0 + i / (NMEL / 4), m4 = i % (NMEL / 4);
+            const int f = padded != nullptr ? r - front_pad : r;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f >= 0 && f < nframes) {
+                float4* p = reinterpret_cast<float4*>(feats + (f_begin + f) * NMEL) + m4;
+                x = __ldcg(p);
+                const float4 mu = *reinterpret_cast<const float4*>(&s_mean[4 * m4]);
+                const float4 rs = *reinterpret_cast<const float4*>(&s_rstd[4 * m4]);
+                x.x = (x.x - mu.x) * rs.x; x.y = (x.y - mu.y) * rs.y; x.z = (x.z - mu.z) * rs.z; x.w = (x.w - mu.w) * rs.w;
+                if (write_f32) *p = x;
+            }
+            if (padded != nullptr)
+                *reinterpret_cast<uint2*>(padded + ((long long)b * padded_frames + r) * NMEL + 4 * m4) =
+                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+        }
+    }
+    // every CTA has read its statistics before the last one clears them
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        for (long long i = tid; i < (long long)batch * NMEL * 2; i += 256) stats[i] = 0.0;
+        if (tid == 0) *done = 0;
+    }
+}
+
+// (v2 path) CMVN: x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) with fp64 statistics, in place; optionally
+
 // also writes bf16 features into a zero-padded [B, padded_frames, 80] buffer (front_pad zero frames
 // before each utterance, zeros after its last frame) for the conv subsampler.
 __global__ void cmvn_kernel(float* __restrict__ feats, const long long* __restrict__ frame_off,
@@ -636,9 +699,40 @@ static int upload_fbank_tables() {
     }
     for (int i = off; i < MAX_MEL_TAPS; ++i) t.mel_w[i] = 0.f;
     PB_CUDA(cudaMemcpyToSymbol(g_fbank_tables, &t, sizeof(FbankTables)));
-    PB_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+    // v4: the 81 intervals between consecutive filter centres (interval j = [lo + j delta, lo + (j + 1) delta)) partition the
+    // FFT bins 1..255; u_k = position of bin k inside its interval = its weight in filter j (1 - u_k in filter j - 1)
+    static Fbank4Tables t4;
+    {
+        int cnt[NMEL + 1] = {0}, first[NMEL + 1];
+        for (int j = 0; j <= NMEL; ++j) first[j] = -1;
+        int jk[NC];
+        for (int k = 0; k < NC; ++k) {
+            const double pos = (mel_scale(fft_bin_width * k) - mel_low) / delta;
+            const int j = pos < 0.0 ? -1 : (int)floor(pos);
+            jk[k] = j;
+            PB_CHECK(j <= NMEL, "mel interval out of range");
+            if (j >= 0) { if (first[j] < 0) first[j] = k; ++cnt[j]; }
+        }
+        for (int i = 0; i < F4_PB; ++i) t4.uperm[i] = 0.f;
+        for (int i = 8; i < 16; ++i) t4.uperm[F4_LAST + i] = 1.f;    // lanes 8..15 of the interval-80 read: weight 1 - u = 0
+        for (int k = 0; k < NC; ++k) {
+            const int j = jk[k];
+            int slot = F4_TRASH;
+            if (j == NMEL) {
+                PB_CHECK(k - first[j] < 8, "last mel interval wider than 8 bins");
+                slot = F4_LAST + (k - first[j]);
+            } else if (j >= 0) {
+                const int i = j / 16, l = j % 16, tt = k - first[j];
+                PB_CHECK(tt < f4_maxc(i), "mel interval wider than the unrolled accumulation");
+                slot = f4_base(i) + F4_STRIDE * tt + l;
+            }
+            t4.perm[k] = (short)slot;
+            if (j >= 0) t4.uperm[slot] = (float)((mel_scale(fft_bin_width * k) - mel_low) / delta - j);
+        }
+    }
+    PB_CUDA(cudaMemcpyToSymbol(g_fbank4_tables, &t4, sizeof(Fbank4Tables)));
     PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem2)));
-    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem3)));
+    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fbank4Smem)));
     if (dev < 64) done_for_device[dev] = 1;
     return 0;
 }
@@ -653,7 +747,12 @@ extern "C" int64_t pb200_fbank_num_frames(int64_t num_samples) {
     return num_samples < WIN ? 0 : 1 + (num_samples - WIN) / SHIFT;
 }
 
-extern "C" size_t pb200_fbank_workspace_bytes(int32_t batch) { return (size_t)batch * NMEL * 2 * sizeof(double); }
+// workspace: fp64 statistics [batch][80][2], then one int (completion counter of the CMVN pass). It must be ZERO when
+// first used and is left zeroed by every successful call (the last CTA of the CMVN pass clears it), so a caller that
+// keeps the buffer never needs a memset again.
+extern "C" size_t pb200_fbank_workspace_bytes(int32_t batch) {
+    return (size_t)batch * NMEL * 2 * sizeof(double) + 16;
+}
 
 extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets, const int64_t* frame_offsets,
                                 int32_t batch, int32_t max_frames, float pcm_scale, int32_t cmvn, float* feats,
@@ -665,38 +764,62 @@ extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets,
     PB_CHECK(pcm && sample_offsets && frame_offsets && feats, "null pointer");
     PB_CHECK(workspace_bytes >= pb200_fbank_workspace_bytes(batch) && workspace, "fbank workspace too small");
     PB_CHECK(!feats_bf16_padded || padded_frames >= max_frames + front_pad, "padded_frames too small");
+    PB_CHECK(!(cmvn & 2) || feats_bf16_padded, "cmvn bit 1 (fp32 rows are scratch) needs the bf16 padded output");
+    PB_CHECK((reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(feats_bf16_padded) & 7) == 0,
+             "fbank outputs must be 16-byte aligned");
     int rc = upload_fbank_tables();
     if (rc) return rc;
     double* stats = reinterpret_cast<double*>(workspace);
-    PB_CUDA(cudaMemsetAsync(stats, 0, pb200_fbank_workspace_bytes(batch), stream));
+    int* done = reinterpret_cast<int*>(stats + (size_t)batch * NMEL * 2);
+    const bool second_pass = (cmvn & 1) || feats_bf16_padded;
+    static const bool use_v2 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v2"); }();
+    if (!use_v2) {
+        const int tiles_per_utt = (max_frames + F4_FRAMES - 1) / F4_FRAMES;
+        const long long total_tiles = (long long)batch * tiles_per_utt;
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            PB_CUDA(cudaGetDevice(&dev));
+            PB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        if (total_tiles > 0) {
+            const long long grid = total_tiles < 2LL * sms ? total_tiles : 2LL * sms;
+            fbank_kernel_v4<<<(unsigned)grid, F4_THREADS, sizeof(Fbank4Smem), stream>>>(
+                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets), feats,
+                (cmvn & 1) ? stats : nullptr, batch, tiles_per_utt, pcm_scale);
+            PB_LAUNCH_CHECK();
+        }
+        if (second_pass) {
+            const int rows = feats_bf16_padded ? padded_frames : max_frames;
+            const int row_blocks = (rows + CM_ROWS - 1) / CM_ROWS;
+            if (row_blocks > 0) {
+                PB_CUDA(launch_pdl(cmvn_layout_kernel, dim3((unsigned)(batch * row_blocks)), dim3(256), 0, stream, feats,
+                                   reinterpret_cast<const long long*>(frame_offsets), stats, done, batch, cmvn,
+                                   reinterpret_cast<bf16*>(feats_bf16_padded), padded_frames, front_pad, row_blocks));
+                PB_LAUNCH_CHECK();
+            }
+        }
+        return 0;
+    }
+    PB_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * NMEL * 2 * sizeof(double), stream));
     if (max_frames > 0) {
         dim3 grid((max_frames + FR_PER_CTA - 1) / FR_PER_CTA, batch);
-        static const bool use_v1 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v1"); }();
-        static const bool use_v3 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v3"); }();
-        if (use_v3)
-            fbank_kernel_v3<<<grid, FB_THREADS, sizeof(FbankSmem3), stream>>>(
-                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
-                feats, stats, pcm_scale);
-        else if (use_v1)
-            fbank_kernel<<<grid, FB_THREADS, sizeof(FbankSmem), stream>>>(
-                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
-                feats, stats, pcm_scale);
-        else
-            fbank_kernel_v2<<<grid, FB_THREADS, sizeof(FbankSmem2), stream>>>(
-                pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
-                feats, stats, pcm_scale);
+        fbank_kernel_v2<<<grid, FB_THREADS, sizeof(FbankSmem2), stream>>>(
+            pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
+            feats, stats, pcm_scale);
         PB_LAUNCH_CHECK();
     }
-    if (cmvn || feats_bf16_padded) {
+    if ((cmvn & 1) || feats_bf16_padded) {
         const int rows = feats_bf16_padded ? padded_frames : max_frames;
         if (rows > 0) {
             int bx = (int)(((long long)rows * NMEL + 255) / 256);
             if (bx > 64) bx = 64;
             dim3 grid(bx, batch);
-            cmvn_kernel<<<grid, 256, 0, stream>>>(feats, reinterpret_cast<const long long*>(frame_offsets), stats, cmvn,
+            cmvn_kernel<<<grid, 256, 0, stream>>>(feats, reinterpret_cast<const long long*>(frame_offsets), stats, cmvn & 1,
                                                  reinterpret_cast<bf16*>(feats_bf16_padded), padded_frames, front_pad);
             PB_LAUNCH_CHECK();
         }
+        PB_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * NMEL * 2 * sizeof(double), stream));   // same contract as v4
     }
     return 0;
 }

@@ -37,13 +37,14 @@ class FbankPlan:
 
 
 def fbank(pcm: Tensor, plan: FbankPlan, cmvn: bool = True, pcm_scale: float = 32768.0,
-          padded_frames: int = 0, front_pad: int = 0):
+          padded_frames: int = 0, front_pad: int = 0, keep_fp32: bool = True):
     """pcm: fp32 [total_samples] on the GPU (utterances concatenated, samples in [-1, 1)).
-    Returns (features fp32 [total_frames, 80], bf16 [B, padded_frames, 80] or None)."""
+    Returns (features fp32 [total_frames, 80], bf16 [B, padded_frames, 80] or None). keep_fp32=False: only the bf16 padded
+    layout holds the normalised features (what the training step consumes); the fp32 tensor is scratch."""
     if not pcm.is_cuda:
         raise RuntimeError('pasero_b200.frontend.fbank needs the PCM on the GPU (no CPU fallback)')
     return K.fbank_cmvn(pcm, plan.sample_offsets, plan.frame_offsets, plan.batch, plan.max_frames, plan.total_frames,
-                        pcm_scale=pcm_scale, cmvn=cmvn, padded_frames=padded_frames, front_pad=front_pad)
+                        pcm_scale=pcm_scale, cmvn=cmvn, padded_frames=padded_frames, front_pad=front_pad, keep_fp32=keep_fp32)
 
 
 def fbank_batch(pcm: Tensor, cmvn: bool = True) -> Tensor:

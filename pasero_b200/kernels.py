@@ -422,20 +422,30 @@ def fbank_num_frames(num_samples: int) -> int:
     return int(_lib.load().pb200_fbank_num_frames(num_samples))
 
 
+_FBANK_WS = {}
+
+
 @_bracketed
 def fbank_cmvn(pcm: Tensor, sample_offsets: Tensor, frame_offsets: Tensor, batch: int, max_frames: int,
                total_frames: int, pcm_scale: float = 32768.0, cmvn: bool = True, padded_frames: int = 0,
-               front_pad: int = 0):
+               front_pad: int = 0, keep_fp32: bool = True):
     """pcm fp32 [total_samples]; offsets int64 [batch+1] on device. Returns (feats fp32 [total_frames, 80],
-    bf16 padded [batch, padded_frames, 80] or None)."""
+    bf16 padded [batch, padded_frames, 80] or None). keep_fp32=False (needs the padded output and cmvn): the fp32 rows are
+    only the kernel's scratch (raw log-mel), the normalised features exist in the bf16 padded layout alone."""
     lib = _lib.load()
     dev = pcm.device
     assert pcm.dtype == torch.float32 and pcm.is_contiguous()
     feats = torch.empty(total_frames, 80, dtype=torch.float32, device=dev)
     padded = torch.empty(batch, padded_frames, 80, dtype=BF16, device=dev) if padded_frames > 0 else None
-    ws = _ws(lib.pb200_fbank_workspace_bytes(batch), dev)
-    _count(2)
+    # statistics + tile counters: zero on first use, left zeroed by every call (see pb200_fbank_workspace_bytes) -> one
+    # persistent buffer per (device, stream, batch), no memset in the step
+    key = (dev, stream_ptr(), batch)
+    ws = _FBANK_WS.get(key)
+    if ws is None:
+        ws = _FBANK_WS[key] = torch.zeros(max(int(lib.pb200_fbank_workspace_bytes(batch)), 16), dtype=torch.uint8, device=dev)
+    mode = int(cmvn) | (2 if (cmvn and not keep_fp32 and padded is not None) else 0)
+    _count(2 if (cmvn or padded is not None) else 1)
     check(lib.pb200_fbank_cmvn(pcm.data_ptr(), sample_offsets.data_ptr(), frame_offsets.data_ptr(), batch, max_frames,
-                               pcm_scale, int(cmvn), feats.data_ptr(), ptr(padded), padded_frames, front_pad,
-                               ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()))
+                               pcm_scale, mode, feats.data_ptr(), ptr(padded), padded_frames, front_pad,
+                               ws.data_ptr(), ws.numel(), stream_ptr()))
     return feats, padded

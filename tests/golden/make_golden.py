@@ -440,9 +440,34 @@ def golden_numpy_file(pasero, out):
     print('numpy file golden:', os.path.getsize(path), 'bytes,', len(rows), 'utterances, lengths', lengths.tolist())
 
 
+def reference_option_names(pasero):
+    """Names of every option the reference's config classes declare (pasero/config.py: `argument` class attributes of all
+    Config subclasses). pasero_b200.config uses the list to tell an option of the reference that this path does not read
+    (kept, ignored) from a misspelt one (an error, as in pasero/config.py:1748-1750). Names only, no code."""
+    import inspect
+    from pasero import config as C
+    names = set()
+    for _, cls in inspect.getmembers(C, inspect.isclass):
+        if issubclass(cls, C.Config):
+            for klass in cls.__mro__:
+                for k, v in list(vars(klass).items()):
+                    if isinstance(v, C.argument) or (k in getattr(klass, '__annotations__', {}) and not k.startswith('_')):
+                        names.add(k)
+                    if isinstance(v, C.argument):      # `--domain` for `domains`, `--source-lang` for `source_langs`, ...
+                        for alias in (getattr(v, 'aliases', None) or ()):
+                            names.add(alias.lstrip('-').replace('-', '_'))
+    path = os.path.join(ROOT, 'pasero_b200', 'reference_options.json')
+    with open(path, 'w') as f:
+        json.dump(sorted(names), f, indent=0)
+    print('reference option names:', len(names))
+
+
 def main():
     out = HERE
     pasero = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'options':      # only the option-name list
+        reference_option_names(pasero)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'numpyfile':    # only the NumpyFile fixture
         golden_numpy_file(pasero, out)
         return
@@ -491,6 +516,7 @@ def main():
         golden_model_text(pasero, tmp, out)
         golden_preprocess_tags(pasero, tmp, out)
         golden_numpy_file(pasero, out)
+        reference_option_names(pasero)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

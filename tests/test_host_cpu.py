@@ -284,3 +284,22 @@ def test_config_surface():
     with pytest.raises(NotImplementedError):
         TrainingConfig.from_dict({'dtype': 'float16'})
     assert cfg.as_dict()['encoder_layers'] == 12
+
+
+def test_config_argv_surface_and_unknown_options(tmp_path):
+    """CLI > YAML > defaults like the reference (pasero/config.py:1711-1760); a key that neither this path nor the reference
+    declares is an error (config.py:1748-1750), a reference option this path does not read is kept in `extra`."""
+    import yaml
+    path = tmp_path / 'cfg.yaml'
+    yaml.safe_dump(dict(task='speech_translation', arch='transformer', encoder_layers=12, conv_kernel_sizes=[5, 5], input_dim=80,
+                        conv_channels=1024, dtype='bfloat16', dict='de-en/dict.txt', metrics=[], dataset_type='simple'), open(path, 'w'))
+    cfg = TrainingConfig.from_argv(['-c', str(path), '--decoder-layers', '3', '--conv-kernel-sizes', '3', '3', '--lr', '1e-4',
+                                    '--dropout', '0.2'])
+    assert (cfg.model_cfg.encoder_layers, cfg.model_cfg.decoder_layers, cfg.model_cfg.conv_kernel_sizes) == (12, 3, (3, 3))
+    assert cfg.lr == 1e-4 and cfg.model_cfg.dropout == 0.2 and cfg.extra['dict'] == 'de-en/dict.txt'
+    with pytest.raises(ValueError, match='encoder_layerz'):
+        TrainingConfig.from_argv(['--encoder-layerz', '3'])
+    with pytest.raises(ValueError, match='not_an_option'):
+        TrainingConfig.from_dict({'not_an_option': 1})
+    with pytest.raises(NotImplementedError):
+        TrainingConfig.from_dict({'fsdp': True})
