@@ -111,7 +111,9 @@ int pb200_gemm_bf16(const pb200_gemm_params* params, void* stream);
  * Multi-head attention, head_dim 64, length-masked (kv_len) and/or causal; replaces
  * MultiheadAttention.forward's SDPA / flash-attn call (pasero/models/modules.py:648-734).
  * q/k/v rows are tokens ([B*L, ld]), head h occupies columns [h*64, h*64+64) from the given pointer.
- * lse: fp32 [B, H, Lq] (written by fwd, read by bwd); delta: fp32 [B, H, Lq] scratch written by bwd.
+ * lse: fp32 [B, H, Lq] (written by fwd, read by bwd); delta: unused (kept for ABI stability; may be NULL).
+ * Any Lq / Lk: blocks of 256 keys (and 256 queries in backward) are processed on chip by tcgen05 kernels, longer
+ * sequences are tiled over such blocks and merged exactly (workspace, see below).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pb200_attn_params {
     const void* q; const void* k; const void* v;
@@ -127,8 +129,18 @@ typedef struct pb200_attn_params {
     float* delta;
     void* dq; void* dk; void* dv;
     int64_t lddq, lddk, lddv;
+    /* attention dropout (pasero/models/modules.py:686-731; 0 = off). Keep decision of (b, h, query, key) =
+     * Philox(seed, offset + (*offset_base << 12)), 16 bits each. drop_mask: uint32 [B, H, Lq, ceil(Lk / 32)], bit j of word w
+     * = key 32 w + j kept; WRITTEN by fwd, READ by bwd (required when dropout_p > 0). */
+    float dropout_p;
+    uint64_t seed, offset;
+    const int64_t* offset_base;
+    uint32_t* drop_mask;
+    /* partial results when Lk > 256 (fwd) or Lq > 256 / Lk > 256 (bwd): pb200_attention_workspace_bytes; may be NULL otherwise */
+    void* workspace; size_t workspace_bytes;
 } pb200_attn_params;
 
+size_t pb200_attention_workspace_bytes(const pb200_attn_params* params, int32_t backward);
 int pb200_attention_fwd(const pb200_attn_params* params, void* stream);
 int pb200_attention_bwd(const pb200_attn_params* params, void* stream);
 

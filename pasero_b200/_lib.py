@@ -41,6 +41,8 @@ class AttnParams(Structure):
         ('dout', c_void_p), ('lddo', c_int64), ('delta', c_void_p),
         ('dq', c_void_p), ('dk', c_void_p), ('dv', c_void_p),
         ('lddq', c_int64), ('lddk', c_int64), ('lddv', c_int64),
+        ('dropout_p', c_float), ('seed', c_uint64), ('offset', c_uint64), ('offset_base', c_void_p), ('drop_mask', c_void_p),
+        ('workspace', c_void_p), ('workspace_bytes', c_size_t),
     ]
 
 
@@ -57,6 +59,7 @@ PROTOTYPES = {
                                    c_size_t, _P]),
     'pb200_gemm_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int32]),
     'pb200_gemm_bf16': (c_int32, [POINTER(GemmParams), _P]),
+    'pb200_attention_workspace_bytes': (c_size_t, [POINTER(AttnParams), c_int32]),
     'pb200_attention_fwd': (c_int32, [POINTER(AttnParams), _P]),
     'pb200_attention_bwd': (c_int32, [POINTER(AttnParams), _P]),
     'pb200_dropout_add_ln_fwd': (c_int32, [_P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,

@@ -108,8 +108,6 @@ class TransformerConfig:
             self.conv_kernel_sizes = tuple(self.conv_kernel_sizes)
             self.conv_strides = tuple(self.conv_strides) if self.conv_strides else tuple(2 for _ in self.conv_kernel_sizes)
         unsupported = []
-        if self.attention_dropout:
-            unsupported.append('attention_dropout > 0')
         if self.activation_dropout:
             unsupported.append('activation_dropout > 0')
         if self.activation_fn not in ('relu', 'gelu'):

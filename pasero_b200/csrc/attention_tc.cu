@@ -1,6 +1,12 @@
-// pasero_b200 — tcgen05/TMEM attention for sequences that fit one tile row (Lk <= 256; backward: Lq <= 256 too),
-// head_dim 64, bf16 in / fp32 softmax. This is the path the ST training step runs on (250 encoder positions,
-// 48 target positions); longer sequences use the online-softmax kernels in attention.cu.
+// pasero_b200 — tcgen05/TMEM attention, head_dim 64, bf16 in / fp32 softmax, any sequence length.
+// One block of <= 256 keys (and, in backward, <= 256 queries) is processed entirely on chip — this is the whole problem for
+// the ST training step (250 encoder positions, 48 target positions). Longer sequences are tiled over such blocks by the
+// grid: forward CTAs write per-key-block partial outputs + log-sum-exps that attn_combine_kernel merges (exact: the
+// partials are softmax-normalised inside their block); backward CTAs own a (query block, key block) pair — P is rebuilt
+// from the GLOBAL log-sum-exp, so the pair's dQ / dK / dV contributions are exact partial sums that attn_reduce_kernel adds.
+// Attention dropout (pasero/models/modules.py:686-731): the forward kernel draws the keep bits of its P tile from
+// Philox(seed, offset) — 16 bits per decision — writes them as one uint32 per (query, 32 keys) and the backward kernel
+// reads them back (P o M / (1 - p) feeds the P V and dV products, dP o M / (1 - p) the softmax backward).
 //
 // Forward, one CTA per (128-query tile, head, batch element):
 //   TMA loads Q [128 x 64], K and V [Lk x 64] (SWIZZLE_128B boxes cut straight out of the fused projection output),
@@ -41,7 +47,27 @@ struct AttnTcDev {
     const float* lse_in;
     bf16* dq; bf16* dk; bf16* dv;
     long long lddq, lddk, lddv;
+    // tiling over blocks of 256 keys / queries
+    int n_kc;                   // forward: key blocks (gridDim.x = query tiles * n_kc)
+    bf16* o_part; float* lse_part;          // forward partials [n_kc][B*Lq][H*64] / [n_kc][B*H*Lq] when n_kc > 1
+    int n_qb, n_kb;             // backward: query / key blocks (gridDim.z = n_qb * n_kb)
+    int q_tma_rows, kv_tma_rows;            // rows of the TMA boxes (backward)
+    bf16* dq_part; bf16* dk_part; bf16* dv_part;   // backward partials [n_kb][B*Lq][H*64], [n_qb][B*Lk][H*64] (x2)
+    // attention dropout
+    uint32_t* mask; int mask_ld;            // keep bits [B*H*Lq][mask_ld] (mask_ld = ceil(Lk / 32) words)
+    uint32_t thresh16; float keep_scale;    // keep iff u16 >= thresh16; 1 / (1 - p)
+    unsigned long long seed, offset; const long long* offset_base;
 };
+
+// 32 keep bits (bit j <-> key 32 * word + j) of one query row
+__device__ __forceinline__ uint32_t attn_keep32(const Philox& rng, unsigned long long offset, long long row, int mask_ld, int word,
+                                                uint32_t thresh16) {
+    const unsigned long long idx = ((unsigned long long)row * mask_ld + word) * 4ull;
+    uint32_t m = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) m |= dropout_keep8(rng, offset, idx + g, thresh16) << (8 * g);
+    return m;
+}
 
 // Optional in-kernel timeline (build with -DPB_ATTN_TIMING): per CTA 16 slots of clock64() at the phase boundaries of
 // the MMA warp (slots 0-7) and of softmax warp 0 (slots 8-13), slot 14 = %globaltimer at entry, slot 15 = SM id.
@@ -93,7 +119,7 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-template <bool P_TMEM, bool CAUSAL>
+template <bool P_TMEM, bool CAUSAL, bool DROPOUT>
 __global__ void __launch_bounds__(TC_THREADS, P_TMEM ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const AttnTcDev p) {
@@ -112,7 +138,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_qt = gridDim.x / p.n_kc;
+    const int kc = blockIdx.x / n_qt;                       // key block of this CTA (256 keys)
+    const int q0 = (blockIdx.x - kc * n_qt) * 128, k0 = kc * 256, h = blockIdx.y, b = blockIdx.z;
 #ifdef PB_ATTN_TIMING
     const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (warp == 8 && lane == 0 && cta_lin < 4096) {
@@ -139,10 +167,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();   // set-up above overlaps the previous kernel; global memory is touched only below
-    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-    const int coff = p.Lk - p.Lq;   // causal: key j visible to query i iff j <= i + coff
+    // keys of this block are indexed from k0: [0, kvlen) are unmasked, causal: key j visible to query i iff j <= i + coff
+    const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;
+    const int coff = p.Lk - p.Lq - k0;
     int kv_hi = CAUSAL ? min(kvlen, q0 + 128 + coff) : kvlen;
-    kv_hi = max(kv_hi, 1);
+    kv_hi = max(kv_hi, 1);   // a block without a visible key still runs: every P is 0, the partial is (0, -inf)
     const int n1 = min(((kv_hi + 15) >> 4) << 4, p.kv_box);   // keys covered by the MMAs (multiple of 16)
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + Cfg::O_COL, tmem_o2 = tmem_base + Cfg::O2_COL;
 
@@ -151,8 +180,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             TSTAMP(1);
             ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)(128 + 2 * p.kv_box) * 128u);
             ptx::tma_load_3d(&tmq, bar_load, sQ, h * 64, q0, b);
-            ptx::tma_load_3d(&tmk, bar_load, sK, h * 64, 0, b);
-            ptx::tma_load_3d(&tmv, bar_load, sV, h * 64, 0, b);
+            ptx::tma_load_3d(&tmk, bar_load, sK, h * 64, k0, b);
+            ptx::tma_load_3d(&tmv, bar_load, sV, h * 64, k0, b);
             ptx::mbar_wait(bar_load, 0);
             ptx::tc_fence_after();
             TSTAMP(2);
@@ -191,6 +220,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const float sl2 = p.scale * LOG2E_F;
         const int nch = (n1 + 31) >> 5;
         const int c_begin = half * 4, c_end = min(nch, half * 4 + 4);   // this warp's 32-key chunks
+        const Philox rng(p.seed);
+        const unsigned long long drop_offset = DROPOUT ? p.offset + (p.offset_base ? ((unsigned long long)*p.offset_base << 12) : 0ull) : 0ull;
         if (warp == 0) TSTAMP(8);
         ptx::mbar_wait(bar_s, 0);
         ptx::tc_fence_after();
@@ -228,21 +259,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             ptx::tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
             ptx::tmem_ld_wait();
             uint32_t pk[16];
+            uint32_t keep = 0xffffffffu;
+            if (DROPOUT) {   // keep bits of this row's 32 keys: drawn here, stored for the backward pass
+                const long long mrow = ((long long)b * p.H + h) * p.Lq + qrow;
+                keep = attn_keep32(rng, drop_offset, mrow, p.mask_ld, (k0 >> 5) + c, p.thresh16);
+                if (qrow < p.Lq && (k0 >> 5) + c < p.mask_ld) p.mask[mrow * p.mask_ld + (k0 >> 5) + c] = keep;
+            }
             if (c * 32 + 32 <= lim_lo) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc));
-                    const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc));
-                    sum0 += p0; sum1 += p1;
+                    float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc));
+                    float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc));
+                    sum0 += p0; sum1 += p1;          // the softmax denominator ignores dropout
+                    if (DROPOUT) { p0 = (keep >> (2 * j)) & 1u ? p0 : 0.f; p1 = (keep >> (2 * j + 1)) & 1u ? p1 : 0.f; }
                     pk[j] = pack_bf16x2(p0, p1);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int col = c * 32 + 2 * j;
-                    const float p0 = col < lim ? ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc)) : 0.f;
-                    const float p1 = col + 1 < lim ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc)) : 0.f;
+                    float p0 = col < lim ? ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -msc)) : 0.f;
+                    float p1 = col + 1 < lim ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -msc)) : 0.f;
                     sum0 += p0; sum1 += p1;
+                    if (DROPOUT) { p0 = (keep >> (2 * j)) & 1u ? p0 : 0.f; p1 = (keep >> (2 * j + 1)) & 1u ? p1 : 0.f; }
                     pk[j] = pack_bf16x2(p0, p1);
                 }
             }
@@ -270,8 +309,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         ptx::mbar_wait(bar_o, 0);
         ptx::tc_fence_after();
         if (warp == 0) TSTAMP(12);
-        const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        bf16* orow = p.o + ((long long)b * p.Lq + qrow) * p.ldo + h * 64 + half * 32;   // this warp: 32 of the 64 columns
+        const float inv = sum > 0.f ? (DROPOUT ? p.keep_scale : 1.f) / sum : 0.f;
+        // one key block: the output itself; several: this block's softmax-normalised partial (merged by attn_combine_kernel)
+        bf16* orow = p.n_kc == 1 ? p.o + ((long long)b * p.Lq + qrow) * p.ldo + h * 64 + half * 32   // this warp: 32 of the 64 columns
+                                 : p.o_part + (((long long)kc * p.B + b) * p.Lq + qrow) * (p.H * 64) + h * 64 + half * 32;
         {
             uint32_t v[32], w[32];
             ptx::tmem_ld_32x32(tmem_o + lane_base + half * 32, v);
@@ -290,8 +331,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
             }
         }
-        if (half == 0 && p.lse && qrow < p.Lq)
-            p.lse[((long long)b * p.H + h) * p.Lq + qrow] = sum > 0.f ? m_use * p.scale + logf(sum) : -INFINITY;
+        if (half == 0 && qrow < p.Lq) {
+            float* lse_out = p.n_kc == 1 ? p.lse : p.lse_part + (long long)kc * p.B * p.H * p.Lq;
+            if (lse_out) lse_out[((long long)b * p.H + h) * p.Lq + qrow] = sum > 0.f ? m_use * p.scale + logf(sum) : -INFINITY;
+        }
         ptx::tc_fence_before();
         if (warp == 0) TSTAMP(13);
     }
@@ -318,7 +361,7 @@ struct BwdCfg {
 // Measured: the CTAs of a wave run in lock-step, so the load phase is a DRAM burst of 148 x 192 KB (operand tiles + the
 // O / dO rows of delta) at ~4.4 TB/s, ~30 % of the CTA's life; neither these finer barriers nor cp.async loads by the
 // 256 softmax threads (tried, removed) shortened it — only a second resident CTA per SM would (192 KB of smem: no room).
-template <bool CAUSAL>
+template <bool CAUSAL, bool DROPOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
@@ -341,7 +384,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    const int ni = (p.q_box + 127) >> 7, nj = (p.kv_box + 127) >> 7;
+    // this CTA's (query block, key block) pair: 256 queries x 256 keys, indexed from (q0, k0)
+    const int qi = blockIdx.z / p.n_kb, kj = blockIdx.z - qi * p.n_kb;
+    const int q0 = qi * 256, k0 = kj * 256;
+    const int q_box = min(256, ((p.Lq - q0 + 15) >> 4) << 4), kv_box = min(256, ((p.Lk - k0 + 15) >> 4) << 4);
+    const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
+    const int ni = (q_box + 127) >> 7, nj = (kv_box + 127) >> 7;
+    const bool part = p.n_qb * p.n_kb > 1;
 #ifdef PB_ATTN_TIMING
     const int cta_lin = blockIdx.x + gridDim.x * blockIdx.y;
     if (warp == 8 && lane == 0 && cta_lin < 4096) {
@@ -369,30 +418,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();   // set-up above overlaps the previous kernel; global memory is touched only below
-    const int kvlen = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-    const int coff = p.Lk - p.Lq;
+    const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
+    const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
     const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                    t_dq = tmem_base + 384;
 
     if (warp == 8) {
         if (lane == 0) {
             {
-                const uint32_t qb = (uint32_t)min(p.q_box, 128) * 128u, kb = (uint32_t)min(p.kv_box, 128) * 128u;   // bytes per tile box
+                const uint32_t qb = (uint32_t)p.q_tma_rows * 128u, kb = (uint32_t)p.kv_tma_rows * 128u;   // bytes per tile box
                 ptx::mbar_arrive_expect_tx(&bar_ld[0], qb + kb);
-                ptx::tma_load_3d(&tmk, &bar_ld[0], sK, h * 64, 0, b);
-                ptx::tma_load_3d(&tmq, &bar_ld[0], sQ, h * 64, 0, b);
+                ptx::tma_load_3d(&tmk, &bar_ld[0], sK, h * 64, k0, b);
+                ptx::tma_load_3d(&tmq, &bar_ld[0], sQ, h * 64, q0, b);
                 ptx::mbar_arrive_expect_tx(&bar_ld[1], qb + kb);
-                ptx::tma_load_3d(&tmv, &bar_ld[1], sV, h * 64, 0, b);
-                ptx::tma_load_3d(&tmdo, &bar_ld[1], sdO, h * 64, 0, b);
+                ptx::tma_load_3d(&tmv, &bar_ld[1], sV, h * 64, k0, b);
+                ptx::tma_load_3d(&tmdo, &bar_ld[1], sdO, h * 64, q0, b);
                 if (ni > 1) {
                     ptx::mbar_arrive_expect_tx(&bar_ld[2], 2 * qb);
-                    ptx::tma_load_3d(&tmq, &bar_ld[2], sQ + 16384, h * 64, 128, b);
-                    ptx::tma_load_3d(&tmdo, &bar_ld[2], sdO + 16384, h * 64, 128, b);
+                    ptx::tma_load_3d(&tmq, &bar_ld[2], sQ + 16384, h * 64, q0 + 128, b);
+                    ptx::tma_load_3d(&tmdo, &bar_ld[2], sdO + 16384, h * 64, q0 + 128, b);
                 }
                 if (nj > 1) {
                     ptx::mbar_arrive_expect_tx(&bar_ld[3], 2 * kb);
-                    ptx::tma_load_3d(&tmk, &bar_ld[3], sK + 16384, h * 64, 128, b);
-                    ptx::tma_load_3d(&tmv, &bar_ld[3], sV + 16384, h * 64, 128, b);
+                    ptx::tma_load_3d(&tmk, &bar_ld[3], sK + 16384, h * 64, k0 + 128, b);
+                    ptx::tma_load_3d(&tmv, &bar_ld[3], sV + 16384, h * 64, k0 + 128, b);
                 }
             }
             TSTAMP(1);
@@ -403,9 +452,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             const uint32_t idesc_e = ptx::make_idesc_bf16(128, 64, true, true);
             int it = 0;
             for (int j = 0; j < nj; ++j) {
-                const int kc = min(128, p.kv_box - 128 * j);       // key rows of this tile inside the TMA box
+                const int kc = min(128, kv_box - 128 * j);       // key rows of this tile inside the TMA box
                 for (int i = 0; i < ni; ++i, ++it) {
-                    const int nq = min(128, p.q_box - 128 * i);     // query columns of this chunk inside the box
+                    const int nq = min(128, q_box - 128 * i);     // query columns of this chunk inside the box
                     const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
                     // S^T = K_j Q_i^T and dP^T = V_j dO_i^T. Independent chains are interleaved step by step: consecutive
                     // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
@@ -466,12 +515,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
         {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
-            const int r = threadIdx.x;   // 0..255
+            const int r = threadIdx.x;   // 0..255: query q0 + r
             float l2 = INFINITY, dl = 0.f;
-            if (r < p.Lq) {
-                l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + r] * LOG2E_F;
-                const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.Lq + r) * p.ldo + h * 64);
-                const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + r) * p.lddo + h * 64);
+            if (r < Lq_blk) {
+                l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + q0 + r] * LOG2E_F;
+                const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.Lq + q0 + r) * p.ldo + h * 64);
+                const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + q0 + r) * p.lddo + h * 64);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const uint4 a = __ldg(po + g), d = __ldg(pd + g);
@@ -490,10 +539,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 
         int it = 0;
         for (int j = 0; j < nj; ++j) {
-            const int key = 128 * j + t;
+            const int key = 128 * j + t;            // block-local key of this thread
             const bool rowok = key < kvlen;
             for (int i = 0; i < ni; ++i, ++it) {
-                const int nq = min(128, p.q_box - 128 * i);
+                const int nq = min(128, q_box - 128 * i);
                 const int nch = (nq + 31) >> 5;
                 ptx::mbar_wait(bar_s, it & 1);
                 ptx::tc_fence_after();
@@ -508,6 +557,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                     const int qb = 128 * i + c * 32;
                     const float4* l4 = reinterpret_cast<const float4*>(sLse + qb);
                     const float4* d4 = reinterpret_cast<const float4*>(sDelta + qb);
+                    // keep bits of (query qb + e, this thread's key): lane e fetches query qb + e's word of this warp's 32
+                    // keys (the warp's keys share one word: key = k0 + 128 j + 32 quarter + lane), broadcast by shuffle below
+                    uint32_t mword = 0xffffffffu;
+                    if (DROPOUT) {
+                        const int qrow = q0 + qb + lane;
+                        const int word = (k0 + 128 * j + quarter * 32) >> 5;
+                        mword = (qrow < p.Lq && word < p.mask_ld) ? p.mask[(((long long)b * p.H + h) * p.Lq + qrow) * p.mask_ld + word] : 0u;
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {   // 8 queries = one 16-byte chunk of P^T and of dS^T
                         const float4 la = l4[2 * g], lb = l4[2 * g + 1], da = d4[2 * g], db = d4[2 * g + 1];
@@ -517,7 +574,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             pe[e] = ex2(fmaf(__uint_as_float(s[8 * g + e]), sl2, -lv[e]));
-                            ds[e] = pe[e] * (__uint_as_float(dp[8 * g + e]) - dv[e]);
+                            float dpe = __uint_as_float(dp[8 * g + e]);
+                            bool kept = true;
+                            if (DROPOUT) {      // d(P o M / (1 - p)) / dP: the dropped entries pass no gradient, the kept ones are scaled
+                                kept = (__shfl_sync(0xffffffffu, mword, 8 * g + e) >> lane) & 1u;
+                                dpe = kept ? dpe * p.keep_scale : 0.f;
+                            }
+                            ds[e] = pe[e] * (dpe - dv[e]);
+                            if (DROPOUT) pe[e] = kept ? pe[e] * p.keep_scale : 0.f;   // P^T as it multiplied V in the forward pass (-> dV)
                             if (CAUSAL) {
                                 const bool ok = key <= qb + 8 * g + e + coff;
                                 pe[e] = ok ? pe[e] : 0.f;
@@ -545,8 +609,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                     ptx::mbar_wait(bar_acc, it & 1);
                     ptx::tc_fence_after();
                     // half 0 drains dV, half 1 drains dK (64 columns each)
-                    bf16* dst = half == 0 ? p.dv + ((long long)b * p.Lk + key) * p.lddv + h * 64
-                                          : p.dk + ((long long)b * p.Lk + key) * p.lddk + h * 64;
+                    // a single block pair writes the gradients themselves, otherwise this pair's partial sums
+                    // (dk_part / dv_part [n_qb][B*Lk][H*64], added up by attn_reduce_kernel)
+                    const long long krow = (long long)b * p.Lk + k0 + key;
+                    bf16* dst = !part ? (half == 0 ? p.dv + krow * p.lddv + h * 64 : p.dk + krow * p.lddk + h * 64)
+                                      : (half == 0 ? p.dv_part : p.dk_part) + ((long long)qi * p.B * p.Lk + krow) * (p.H * 64) + h * 64;
                     const float mul = half == 0 ? 1.0f : p.scale;
                     const uint32_t src = (half == 0 ? t_dv : t_dk) + lane_base;
 #pragma unroll
@@ -554,7 +621,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(src + hh * 32, v);
                         ptx::tmem_ld_wait();
-                        if (key < p.Lk) {
+                        if (key < Lk_blk) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 uint4 ov;
@@ -573,12 +640,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs); each warp drains
         // 32 of the 64 columns of its rows
         for (int i = 0; i < ni; ++i) {
-            const int qrow = 128 * i + t;
-            bf16* dst = p.dq + ((long long)b * p.Lq + qrow) * p.lddq + h * 64 + half * 32;
+            const int qrow = 128 * i + t;           // block-local query
+            const long long grow = (long long)b * p.Lq + q0 + qrow;
+            bf16* dst = (!part ? p.dq + grow * p.lddq : p.dq_part + ((long long)kj * p.B * p.Lq + grow) * (p.H * 64)) + h * 64 + half * 32;
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
             ptx::tmem_ld_wait();
-            if (qrow < p.Lq) {
+            if (qrow < Lq_blk) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 ov;
@@ -601,77 +669,206 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
 }
 
+// =====================================================================================================
+// merging the per-block partials of long sequences
+// =====================================================================================================
+// forward: out = sum_c w_c O_c with w_c = exp(lse_c - lse), lse = log sum_c exp(lse_c); one thread per (row, head, 8 columns)
+__global__ void attn_combine_kernel(const bf16* __restrict__ o_part, const float* __restrict__ lse_part, int n_kc, int B, int H,
+                                    int Lq, bf16* __restrict__ o, long long ldo, float* __restrict__ lse) {
+    pdl_wait();
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Lq * H * 8;
+    if (idx >= total) return;
+    const int g = (int)(idx & 7), h = (int)((idx >> 3) % H);
+    const long long row = idx / (8LL * H);             // b * Lq + q
+    const int b = (int)(row / Lq), q = (int)(row - (long long)b * Lq);
+    const long long lidx = ((long long)b * H + h) * Lq + q, lstride = (long long)B * H * Lq;
+    float m = -INFINITY;
+    for (int c = 0; c < n_kc; ++c) m = fmaxf(m, lse_part[c * lstride + lidx]);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float den = 0.f;
+    if (m > -INFINITY) {
+        for (int c = 0; c < n_kc; ++c) {
+            const float w = __expf(lse_part[c * lstride + lidx] - m);
+            den += w;
+            const uint4 v = *reinterpret_cast<const uint4*>(o_part + ((long long)c * B * Lq + row) * (H * 64) + h * 64 + g * 8);
+            const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(vw[e]);
+                acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
+                acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
+            }
+        }
+    }
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    uint4 ov;
+    ov.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); ov.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+    ov.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); ov.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + row * ldo + h * 64 + g * 8) = ov;
+    if (g == 0 && lse) lse[lidx] = den > 0.f ? m + logf(den) : -INFINITY;
+}
+
+// backward: out[row, :] = sum_c part[c][row, :] (fp32 accumulation); one thread per (row, 8 columns)
+__global__ void attn_reduce_kernel(const bf16* __restrict__ part, int n, long long rows, int cols, bf16* __restrict__ out,
+                                   long long ldout) {
+    pdl_wait();
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c8 = cols >> 3;
+    if (idx >= rows * c8) return;
+    const long long row = idx / c8;
+    const int g = (int)(idx - row * c8);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < n; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(part + ((long long)c * rows + row) * cols + g * 8);
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(vw[e]);
+            acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+        }
+    }
+    uint4 ov;
+    ov.x = pack_bf16x2(acc[0], acc[1]); ov.y = pack_bf16x2(acc[2], acc[3]);
+    ov.z = pack_bf16x2(acc[4], acc[5]); ov.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + row * ldout + g * 8) = ov;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int round16(int x) { return ((x + 15) / 16) * 16; }
+static int blocks256(int L) { return (L + 255) / 256; }
 
-bool attn_tc_supported(const pb200_attn_params* q, bool backward) {
-    if (q->head_dim != 64 || q->Lk < 1 || q->Lk > 256 || q->Lq < 1) return false;
-    if (backward && q->Lq > 256) return false;
+int attn_tc_check(const pb200_attn_params* q, bool backward) {
+    PB_CHECK(q->head_dim == 64 && q->Lk >= 1 && q->Lq >= 1, "attention: head_dim 64, non-empty sequences");
     auto al = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
-    if (!al(q->q) || !al(q->k) || !al(q->v) || !al(q->o)) return false;
-    if (backward && (!al(q->dout) || !al(q->dq) || !al(q->dk) || !al(q->dv))) return false;
-    return true;
+    PB_CHECK(al(q->q) && al(q->k) && al(q->v) && al(q->o), "attention: q / k / v / o must be 16-byte aligned");
+    PB_CHECK(!backward || (al(q->dout) && al(q->dq) && al(q->dk) && al(q->dv)), "attention: dout / dq / dk / dv must be 16-byte aligned");
+    PB_CHECK(q->dropout_p >= 0.f && q->dropout_p < 1.f, "attention: dropout_p in [0, 1)");
+    PB_CHECK(q->dropout_p == 0.f || q->drop_mask, "attention dropout needs the keep-bit buffer (drop_mask)");
+    return 0;
+}
+
+// bytes of partial results for sequences longer than one 256-key (backward: 256-query) block
+size_t attn_tc_workspace_bytes(const pb200_attn_params* q, bool backward) {
+    const size_t D = (size_t)q->H * 64;
+    const size_t nq = blocks256(q->Lq), nk = blocks256(q->Lk);
+    if (!backward) return nk > 1 ? nk * ((size_t)q->B * q->Lq * D * 2 + (size_t)q->B * q->H * q->Lq * 4) : 0;
+    if (nq * nk == 1) return 0;
+    // every block pair writes partials (also where only one of the two sums has several terms: one code path)
+    return nk * (size_t)q->B * q->Lq * D * 2 + 2 * nq * (size_t)q->B * q->Lk * D * 2;
 }
 
 static AttnTcDev tc_dev(const pb200_attn_params* q) {
     AttnTcDev p = {};
     p.o = (bf16*)q->o; p.lse = q->lse; p.kv_len = q->kv_len; p.ldo = q->ldo;
     p.B = q->B; p.H = q->H; p.Lq = q->Lq; p.Lk = q->Lk; p.causal = q->causal; p.scale = q->scale;
-    p.kv_box = round16(q->Lk);
+    p.n_kc = blocks256(q->Lk); p.n_qb = blocks256(q->Lq); p.n_kb = p.n_kc;
+    p.kv_box = p.n_kc > 1 ? 256 : round16(q->Lk);
+    p.mask = q->drop_mask; p.mask_ld = (q->Lk + 31) / 32;
+    p.thresh16 = dropout_thresh16(q->dropout_p);
+    p.keep_scale = q->dropout_p > 0.f ? 1.f / (1.f - q->dropout_p) : 1.f;
+    p.seed = q->seed; p.offset = q->offset; p.offset_base = (const long long*)q->offset_base;
     return p;
 }
 
-template <bool P_TMEM, bool CAUSAL>
+template <bool CAUSAL, bool DROPOUT>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcDev& p,
                       cudaStream_t stream) {
-    auto kern = attn_fwd_tc_kernel<P_TMEM, CAUSAL>;
+    auto kern = attn_fwd_tc_kernel<true, CAUSAL, DROPOUT>;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<P_TMEM>::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<true>::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-    PB_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), FwdCfg<P_TMEM>::SMEM_BYTES, stream, tq, tk, tv, p));
+    dim3 grid(((p.Lq + 127) / 128) * p.n_kc, p.H, p.B);
+    PB_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), FwdCfg<true>::SMEM_BYTES, stream, tq, tk, tv, p));
     PB_LAUNCH_CHECK();
     return 0;
 }
 
-int attn_fwd_tc(const pb200_attn_params* q, cudaStream_t stream, bool p_in_tmem) {
+int attn_fwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
+    if (int rc = attn_tc_check(q, false)) return rc;
     AttnTcDev p = tc_dev(q);
     p.q_box = 128;
+    if (p.n_kc > 1) {
+        PB_CHECK(q->workspace && q->workspace_bytes >= attn_tc_workspace_bytes(q, false), "attention_fwd: workspace too small for Lk > 256");
+        p.o_part = (bf16*)q->workspace;
+        p.lse_part = (float*)((char*)q->workspace + (size_t)p.n_kc * q->B * q->Lq * q->H * 64 * 2);
+    }
     CUtensorMap tq, tk, tv;
     if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, 128)) return rc;
     if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, p.kv_box)) return rc;
     if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, p.kv_box)) return rc;
-    if (p.causal) return p_in_tmem ? launch_fwd<true, true>(tq, tk, tv, p, stream) : launch_fwd<false, true>(tq, tk, tv, p, stream);
-    return p_in_tmem ? launch_fwd<true, false>(tq, tk, tv, p, stream) : launch_fwd<false, false>(tq, tk, tv, p, stream);
+    const bool drop = q->dropout_p > 0.f;
+    int rc;
+    if (p.causal) rc = drop ? launch_fwd<true, true>(tq, tk, tv, p, stream) : launch_fwd<true, false>(tq, tk, tv, p, stream);
+    else rc = drop ? launch_fwd<false, true>(tq, tk, tv, p, stream) : launch_fwd<false, false>(tq, tk, tv, p, stream);
+    if (rc) return rc;
+    if (p.n_kc > 1) {
+        const long long total = (long long)q->B * q->Lq * q->H * 8;
+        PB_CUDA(launch_pdl(attn_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const bf16*)p.o_part,
+                           (const float*)p.lse_part, p.n_kc, p.B, p.H, p.Lq, p.o, p.ldo, p.lse));
+        PB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <bool CAUSAL, bool DROPOUT>
+static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                      const AttnTcDev& p, cudaStream_t stream) {
+    auto kern = attn_bwd_tc_kernel<CAUSAL, DROPOUT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(p.H, p.B, p.n_qb * p.n_kb);
+    PB_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
+    PB_LAUNCH_CHECK();
+    return 0;
 }
 
 int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
+    if (int rc = attn_tc_check(q, true)) return rc;
     AttnTcDev p = tc_dev(q);
-    p.q_box = round16(q->Lq);
     p.o_in = (const bf16*)q->o; p.dout = (const bf16*)q->dout; p.lddo = q->lddo; p.lse_in = q->lse;
     p.dq = (bf16*)q->dq; p.dk = (bf16*)q->dk; p.dv = (bf16*)q->dv;
     p.lddq = q->lddq; p.lddk = q->lddk; p.lddv = q->lddv;
     p.q = (const bf16*)q->q; p.k = (const bf16*)q->k; p.v = (const bf16*)q->v;
     p.ldq = q->ldq; p.ldk = q->ldk; p.ldv = q->ldv;
-    // 128-row tile boxes (see the kernel: one barrier per pair of tiles)
-    const int qbox = p.q_box < 128 ? p.q_box : 128, kbox = p.kv_box < 128 ? p.kv_box : 128;
-    CUtensorMap tq, tk, tv, tdo;
-    if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, qbox)) return rc;
-    if (int rc = make_tmap(&tdo, q->dout, q->Lq, (long long)q->H * 64, q->lddo, q->B, (long long)q->Lq * q->lddo, 64, qbox)) return rc;
-    if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, kbox)) return rc;
-    if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, kbox)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
-        PB_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
-        attr_set = true;
+    // 128-row tile boxes (see the kernel: one barrier per pair of tiles); a single short block gets a box of its own size
+    p.q_tma_rows = p.n_qb > 1 ? 128 : (round16(q->Lq) < 128 ? round16(q->Lq) : 128);
+    p.kv_tma_rows = p.n_kb > 1 ? 128 : (round16(q->Lk) < 128 ? round16(q->Lk) : 128);
+    const bool part = p.n_qb * p.n_kb > 1;
+    const size_t D = (size_t)q->H * 64;
+    if (part) {
+        PB_CHECK(q->workspace && q->workspace_bytes >= attn_tc_workspace_bytes(q, true), "attention_bwd: workspace too small for > 256 positions");
+        p.dq_part = (bf16*)q->workspace;
+        p.dk_part = p.dq_part + (size_t)p.n_kb * q->B * q->Lq * D;
+        p.dv_part = p.dk_part + (size_t)p.n_qb * q->B * q->Lk * D;
     }
-    dim3 grid(p.H, p.B);
-    if (p.causal) PB_CUDA(launch_pdl(attn_bwd_tc_kernel<true>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-    else PB_CUDA(launch_pdl(attn_bwd_tc_kernel<false>, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
-    PB_LAUNCH_CHECK();
+    CUtensorMap tq, tk, tv, tdo;
+    if (int rc = make_tmap(&tq, q->q, q->Lq, (long long)q->H * 64, q->ldq, q->B, (long long)q->Lq * q->ldq, 64, p.q_tma_rows)) return rc;
+    if (int rc = make_tmap(&tdo, q->dout, q->Lq, (long long)q->H * 64, q->lddo, q->B, (long long)q->Lq * q->lddo, 64, p.q_tma_rows)) return rc;
+    if (int rc = make_tmap(&tk, q->k, q->Lk, (long long)q->H * 64, q->ldk, q->B, (long long)q->Lk * q->ldk, 64, p.kv_tma_rows)) return rc;
+    if (int rc = make_tmap(&tv, q->v, q->Lk, (long long)q->H * 64, q->ldv, q->B, (long long)q->Lk * q->ldv, 64, p.kv_tma_rows)) return rc;
+    const bool drop = q->dropout_p > 0.f;
+    int rc;
+    if (p.causal) rc = drop ? launch_bwd<true, true>(tq, tk, tv, tdo, p, stream) : launch_bwd<true, false>(tq, tk, tv, tdo, p, stream);
+    else rc = drop ? launch_bwd<false, true>(tq, tk, tv, tdo, p, stream) : launch_bwd<false, false>(tq, tk, tv, tdo, p, stream);
+    if (rc) return rc;
+    if (part) {
+        auto reduce = [&](const bf16* src, int n, long long rows, bf16* dst, long long ld) -> int {
+            const long long total = rows * (long long)(D / 8);
+            PB_CUDA(launch_pdl(attn_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, src, n, rows, (int)D, dst, ld));
+            PB_LAUNCH_CHECK();
+            return 0;
+        };
+        // the outputs are column slices of wider matrices (ld > H * 64): reduce row by row into them
+        if (int r = reduce(p.dq_part, p.n_kb, (long long)q->B * q->Lq, p.dq, p.lddq)) return r;
+        if (int r = reduce(p.dk_part, p.n_qb, (long long)q->B * q->Lk, p.dk, p.lddk)) return r;
+        if (int r = reduce(p.dv_part, p.n_qb, (long long)q->B * q->Lk, p.dv, p.lddv)) return r;
+    }
     return 0;
 }
 

@@ -293,8 +293,8 @@ struct Fbank4Smem {
     alignas(16) float2 tile[F4_HW][FB2_TILE];
     alignas(16) float pbuf[F4_HW][F4_PB];
     alignas(16) float uperm[F4_PB];
+    alignas(16) float stash0[F4_HW][NMEL];     // log-mel rows of the tile's first 16 frames (the other 16 wait in `tile`)
     alignas(16) uint32_t pperm[2][16][4];   // lane -> byte offsets into its power buffer of bins 16 k1 + lane, two per word
-    alignas(16) float stash[F4_FRAMES][NMEL];   // the tile's log-mel rows: coalesced store + exact (fp64) statistics
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -509,24 +509,31 @@ fbank_kernel_v4(const float* __restrict__ pcm, const long long* __restrict__ sam
             float nb[F4_NGROUP];
 #pragma unroll
             for (int i = 0; i < F4_NGROUP; ++i) nb[i] = __shfl_sync(FULL, vm[i], (hl + 1) & 15, 16);
-            float* dst = &sm.stash[live ? fr : 0][hl];
+            // the frame's row waits for the tile's coalesced copy-out: the first frame of this half-warp in the small stash,
+            // the second one in the half-warp's own transpose tile (free until the next tile's first stage)
+            float* dst = (rr == 0 ? &sm.stash0[hw][0] : reinterpret_cast<float*>(tile)) + hl;
 #pragma unroll
             for (int i = 0; i < F4_NGROUP; ++i) {
                 const float up = hl < 15 ? nb[i] : (i < F4_NGROUP - 1 ? nb[i + 1 < F4_NGROUP ? i + 1 : i] : v80);
                 const float mel4 = um[i] + up;
                 // mel = mel4 / 4: log(max(mel, eps)) = log(max(mel4, 4 eps)) - log 4
                 const float val = logf(fmaxf(mel4, 4.f * 1.1920928955078125e-07f)) - 1.3862943611198906f;
-                if (live) dst[16 * i] = val;
+                dst[16 * i] = val;
             }
         }
         __syncthreads();
-        {   // the tile's rows: one coalesced copy to global memory, and bin `tid`'s statistics in fp64
+        {   // the tile's rows: one coalesced copy to global memory, and bin `tid`'s statistics in fp64.
+            auto row_of = [&](int fr) -> const float* {
+                return fr < F4_HW ? &sm.stash0[fr][0] : reinterpret_cast<const float*>(sm.tile[fr - F4_HW]);
+            };
             float4* out4 = reinterpret_cast<float4*>(feats + (f_begin + f0) * NMEL);
-            const float4* st4 = reinterpret_cast<const float4*>(&sm.stash[0][0]);
-            for (int i = tid; i < nf * (NMEL / 4); i += F4_THREADS) out4[i] = st4[i];
+            for (int i = tid; i < nf * (NMEL / 4); i += F4_THREADS) {
+                const int fr = i / (NMEL / 4), m4 = i - fr * (NMEL / 4);
+                out4[i] = *reinterpret_cast<const float4*>(row_of(fr) + 4 * m4);
+            }
             if (tid < NMEL && stats != nullptr) {
                 for (int fr = 0; fr < nf; ++fr) {
-                    const double val = (double)sm.stash[fr][tid];
+                    const double val = (double)row_of(fr)[tid];
                     s1 += val;
                     s2 = fma(val, val, s2);
                 }
@@ -544,7 +551,7 @@ fbank_kernel_v4(const float* __restrict__ pcm, const long long* __restrict__ sam
 // (mode bit 0 without bit 1) and / or the zero-padded bf16 layout (features of utterance b at rows [front_pad, front_pad +
 // frames(b)), zeros elsewhere). The last CTA to finish clears the statistics and its own counter: the workspace is left
 // zeroed for the next call (no memset in the step).
-static constexpr int CM_ROWS = 32;
+static constexpr int CM_ROWS = 64;      // 64 rows x 20 float4 = 5 per thread, all five loads in flight together
 __global__ void __launch_bounds__(256)
 cmvn_layout_kernel(float* __restrict__ feats, const long long* __restrict__ frame_off, double* __restrict__ stats,
                    int* __restrict__ done, int batch, int mode, bf16* __restrict__ padded, int padded_frames, int front_pad,
@@ -560,6 +567,18 @@ cmvn_layout_kernel(float* __restrict__ feats, const long long* __restrict__ fram
     const int rows = padded != nullptr ? padded_frames : nframes;
     const int r0 = rb * CM_ROWS, r1 = min(rows, r0 + CM_ROWS);
     if (r0 < r1) {
+        const bool write_f32 = (mode & 1) && !(mode & 2);
+        constexpr int PER = CM_ROWS * (NMEL / 4) / 256;
+        float4 x[PER];
+        float4* src[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * 256;
+            const int r = r0 + i / (NMEL / 4), m4 = i % (NMEL / 4);
+            const int f = padded != nullptr ? r - front_pad : r;
+            src[u] = (r < r1 && f >= 0 && f < nframes) ? reinterpret_cast<float4*>(feats + (f_begin + f) * NMEL) + m4 : nullptr;
+            x[u] = src[u] != nullptr ? __ldcg(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (tid < NMEL) {
             float mean = 0.f, rstd = 1.f;
             if ((mode & 1) && nframes > 0) {
@@ -574,22 +593,21 @@ cmvn_layout_kernel(float* __restrict__ feats, const long long* __restrict__ fram
             s_mean[tid] = mean; s_rstd[tid] = rstd;
         }
         __syncthreads();
-        const bool write_f32 = (mode & 1) && !(mode & 2);
-        for (int i = tid; i < (r1 - r0) * (NMEL / 4); i += 256) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * 256;
             const int r = r0 + i / (NMEL / 4), m4 = i % (NMEL / 4);
-            const int f = padded != nullptr ? r - front_pad : r;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (f >= 0 && f < nframes) {
-                float4* p = reinterpret_cast<float4*>(feats + (f_begin + f) * NMEL) + m4;
-                x = __ldcg(p);
+            if (r >= r1) continue;
+            float4 v = x[u];
+            if (src[u] != nullptr) {
                 const float4 mu = *reinterpret_cast<const float4*>(&s_mean[4 * m4]);
                 const float4 rs = *reinterpret_cast<const float4*>(&s_rstd[4 * m4]);
-                x.x = (x.x - mu.x) * rs.x; x.y = (x.y - mu.y) * rs.y; x.z = (x.z - mu.z) * rs.z; x.w = (x.w - mu.w) * rs.w;
-                if (write_f32) *p = x;
+                v.x = (v.x - mu.x) * rs.x; v.y = (v.y - mu.y) * rs.y; v.z = (v.z - mu.z) * rs.z; v.w = (v.w - mu.w) * rs.w;
+                if (write_f32) *src[u] = v;
             }
             if (padded != nullptr)
                 *reinterpret_cast<uint2*>(padded + ((long long)b * padded_frames + r) * NMEL + 4 * m4) =
-                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
         }
     }
     // every CTA has read its statistics before the last one clears them

@@ -176,35 +176,50 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
-@_bracketed(work=_attn_flops(1.0))
-def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, kv_len: Optional[Tensor],
-                  causal: bool, scale: float):
-    """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection)."""
+def _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, backward):
+    """Fills the C struct; dropout = None or (p, seed, offset, mask uint32 [B, H, Lq, ceil(Lk / 32)]). Returns (params, keepalive)."""
     lib = _lib.load()
-    o = torch.empty(B * Lq, H * 64, dtype=BF16, device=q.device)
-    lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
     p = AttnParams()
     p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
     p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     p.B, p.H, p.Lq, p.Lk, p.head_dim, p.causal, p.scale = B, H, Lq, Lk, 64, int(causal), scale
-    _count(1)
+    if dropout is not None and dropout[0] > 0:
+        p.dropout_p, p.seed, p.offset, p.offset_base, p.drop_mask = dropout[0], dropout[1], dropout[2], ptr(RNG_OFFSET_BASE), dropout[3].data_ptr()
+    nbytes = lib.pb200_attention_workspace_bytes(byref(p), int(backward))
+    ws = _ws(nbytes, q.device)
+    p.workspace, p.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
+    return p, ws
+
+
+def attention_mask_buffer(B: int, H: int, Lq: int, Lk: int, device='cuda') -> Tensor:
+    """Keep-bit buffer of the attention dropout: one int32 word per (b, h, query, 32 keys); written by attention_fwd."""
+    return torch.empty(B, H, Lq, (Lk + 31) // 32, dtype=torch.int32, device=device)
+
+
+@_bracketed(work=_attn_flops(1.0))
+def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, kv_len: Optional[Tensor],
+                  causal: bool, scale: float, dropout=None):
+    """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection).
+    dropout: None or (p, seed, offset, mask) with mask = attention_mask_buffer(...) (filled here, read by attention_bwd)."""
+    lib = _lib.load()
+    o = torch.empty(B * Lq, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
+    p, ws = _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, False)
+    _count(1 if ws is None else 2)
     check(lib.pb200_attention_fwd(byref(p), stream_ptr()))
     return o, lse
 
 
 @_bracketed(work=_attn_flops(2.5))
 def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, B: int, H: int, Lq: int,
-                  Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor):
+                  Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor,
+                  dropout=None):
     lib = _lib.load()
-    delta = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
-    p = AttnParams()
-    p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
-    p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
-    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.causal, p.scale = B, H, Lq, Lk, 64, int(causal), scale
-    p.dout, p.lddo, p.delta = dout.data_ptr(), dout.stride(0), delta.data_ptr()
+    p, ws = _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, True)
+    p.dout, p.lddo = dout.data_ptr(), dout.stride(0)
     p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     p.lddq, p.lddk, p.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
-    _count(3)
+    _count(1 if ws is None else 4)
     check(lib.pb200_attention_bwd(byref(p), stream_ptr()))
     return dq, dk, dv
 

@@ -149,8 +149,6 @@ class MultiheadAttention(nn.Module):
         self.head_dim = embed_dim // num_heads
         if self.head_dim != 64:
             raise NotImplementedError('pasero_b200 attention kernels are specialised for head_dim 64')
-        if dropout:
-            raise NotImplementedError('attention dropout is not covered yet (reference default is 0.0)')
         self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
         self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
         self.in_proj_bias._pb200_f32_grad = True   # gradient accumulated in fp32 by the weight-gradient GEMM (ops._wgrad_bias)
@@ -224,7 +222,7 @@ class MultiheadAttention(nn.Module):
         out = ops.AttentionFn.apply(
             query.reshape(B * T, D), None if self_attn else key.reshape(B * S, D), self.in_proj_weight, self.in_proj_bias,
             self.out_proj.weight, self.out_proj.bias, key_lengths, B, T, S, self.num_heads, self.causal,
-            ops.attention_scale(self.head_dim, self.scaled), self.key_bias)
+            ops.attention_scale(self.head_dim, self.scaled), self.key_bias, float(self.dropout) if self.training else 0.0)
         return out.view(B, T, D), None
 
 

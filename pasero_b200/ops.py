@@ -274,7 +274,7 @@ class AttentionFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, query, key, in_w, in_b, out_w, out_b, kv_len, B, Lq, Lk, H, causal, scale, key_bias=True):
+    def forward(ctx, query, key, in_w, in_b, out_w, out_b, kv_len, B, Lq, Lk, H, causal, scale, key_bias=True, attn_p=0.0):
         D = H * 64
         ctx.key_bias = key_bias
         query = _c(query)
@@ -289,9 +289,11 @@ class AttentionFn(torch.autograd.Function):
             q2 = K.linear_fwd(query, in_w[2 * D:], in_b[2 * D:])         # [B*Lq, D]
             k2, v2 = kv[:, :D], kv[:, D:]
             kvq = None
-        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
+        drop = _attn_dropout(attn_p, B, H, Lq, Lk, query.device)
+        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale, dropout=drop)
         y = K.linear_fwd(o, out_w, out_b)
         ctx.save_for_backward(query, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len)
+        ctx.drop = drop
         ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn)
         ctx.params = (in_w, in_b, out_w, out_b)
         return y
@@ -318,7 +320,7 @@ class AttentionFn(torch.autograd.Function):
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
-                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
+                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
             dquery = K.linear_dgrad(dkvq, in_w)
             if kb:
                 _wgrad_bias(dkvq, query, d_in_w, acc_w, b32, d_in_b, acc_b)
@@ -329,7 +331,7 @@ class AttentionFn(torch.autograd.Function):
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
             dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
-            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dquery = K.linear_dgrad(dq, in_w[2 * D:])
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
             if kb:
@@ -340,7 +342,15 @@ class AttentionFn(torch.autograd.Function):
             _wgrad_bias(dq, query, d_in_w[2 * D:], acc_w, b32[2 * D:] if b32 is not None else None, d_in_b[2 * D:], acc_b)
         _ready(p_in_w, p_in_b)
         return (dquery, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
+
+
+def _attn_dropout(p: float, B: int, H: int, Lq: int, Lk: int, device):
+    """(p, seed, offset, keep-bit buffer) of one attention call (pasero/models/modules.py:686-731), or None when p == 0."""
+    if not p or p <= 0:
+        return None
+    seed, offset = DropoutState.next()
+    return float(p), seed, offset, K.attention_mask_buffer(B, H, Lq, Lk, device)
 
 
 def _keep_buffer(x: Tensor, p: float) -> Optional[Tensor]:
@@ -390,7 +400,7 @@ class AttnSublayerFn(torch.autograd.Function):
     dgrad GEMM (no column-sum pass over dy, no separate add kernel)."""
 
     @staticmethod
-    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps, key_bias=True):
+    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps, key_bias=True, attn_p=0.0):
         D = H * 64
         ctx.key_bias = key_bias
         x = _c(x)
@@ -404,7 +414,9 @@ class AttnSublayerFn(torch.autograd.Function):
             kv = K.linear_fwd(key_c, in_w[:2 * D], in_b[:2 * D])
             q2 = K.linear_fwd(x, in_w[2 * D:], in_b[2 * D:])
             k2, v2 = kv[:, :D], kv[:, D:]
-        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale)
+        drop = _attn_dropout(attn_p, B, H, Lq, Lk, x.device)
+        ctx.drop = drop
+        o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale, dropout=drop)
         y = K.linear_fwd(o, out_w, out_b)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
         keep = _keep_buffer(y, p)
@@ -431,13 +443,13 @@ class AttnSublayerFn(torch.autograd.Function):
             if self_attn:
                 dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
                 K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
-                                dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
-                return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 10
+                                dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
+                return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
             dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
-            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dkey = K.linear_dgrad(dkv, in_w[:2 * D]) if need[1] else None
-            return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 10
+            return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
         w32 = _sink32(p_in_w)
@@ -450,7 +462,7 @@ class AttnSublayerFn(torch.autograd.Function):
         if self_attn:
             dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
-                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D])
+                            dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
             dx = K.linear_dgrad(dkvq, in_w, residual=dres)
             if kb:
                 _wgrad_bias(dkvq, x, d_in_w, acc_w, b32, d_in_b, acc_b)
@@ -461,7 +473,7 @@ class AttnSublayerFn(torch.autograd.Function):
         else:
             dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
             dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
-            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:])
+            K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dx = K.linear_dgrad(dq, in_w[2 * D:], residual=dres)
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
             if kb:
@@ -472,7 +484,7 @@ class AttnSublayerFn(torch.autograd.Function):
             _wgrad_bias(dq, x, d_in_w[2 * D:], acc_w, b32[2 * D:] if b32 is not None else None, d_in_b[2 * D:], acc_b)
         _ready(p_in_w, p_in_b)
         return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 class FFNSublayerFn(torch.autograd.Function):
@@ -770,7 +782,7 @@ def attn_sublayer(x: Tensor, key: Optional[Tensor], attn, ln, kv_len, causal: bo
     out = AttnSublayerFn.apply(x.reshape(B * T, D), None if key is None else key.reshape(B * S, D), attn.in_proj_weight,
                                attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias, ln.weight, ln.bias, kv_len,
                                B, T, S, attn.num_heads, causal, attention_scale(attn.head_dim, attn.scaled), float(p), float(eps),
-                               attn.key_bias)
+                               attn.key_bias, float(attn.dropout) if attn.training else 0.0)
     return out.view(B, T, D)
 
 

