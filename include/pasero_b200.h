@@ -224,6 +224,12 @@ int pb200_col2im(const void* dcol, int32_t B, int32_t Tin, int32_t Tout, int32_t
                  void* dx, void* stream);
 int pb200_pad_rows(const void* in, int32_t B, int32_t T, int32_t C, void* out, int32_t Tp, int32_t front_pad, void* stream);
 int pb200_f32_to_bf16(const float* in, int64_t n, void* out, int32_t accumulate, void* stream);
+/* Device-side collate of a feature batch (Task.collate right-padding + cast, pasero/tasks/task.py:531-571, utils.py:709-736):
+ * `rows` = the utterances' feature rows back to back (fp16 when rows_fp16 != 0 — the NumpyFile default, pasero/files.py:122-159
+ * — else fp32), offsets int64 [B + 1] in rows; utterance b -> rows [front_pad, front_pad + len_b) of out[b] (bf16 [B, Tp, C]),
+ * zeros elsewhere. */
+int pb200_collate_features(const void* rows, int32_t rows_fp16, const int64_t* offsets, int32_t B, int32_t C, void* out,
+                           int32_t Tp, int32_t front_pad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Label-smoothed cross-entropy over bf16 logits [B*T, V] (row stride ld), targets int64 read as

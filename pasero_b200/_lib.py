@@ -88,6 +88,7 @@ PROTOTYPES = {
     'pb200_col2im': (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'pb200_pad_rows': (c_int32, [_P, c_int32, c_int32, c_int32, _P, c_int32, c_int32, _P]),
     'pb200_f32_to_bf16': (c_int32, [_P, c_int64, _P, c_int32, _P]),
+    'pb200_collate_features': (c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, c_int32, c_int32, _P]),
     'pb200_ls_ce_fwd_bwd': (c_int32, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float,
                                       c_int32, _P, _P, _P]),
     'pb200_grad32_flush': (c_int32, [_P, _P, _P, c_int32, c_int64, _P]),

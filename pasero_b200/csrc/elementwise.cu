@@ -6,6 +6,7 @@
 //   * col2im gather for the strided-conv input gradient
 // All tensors bf16, 16-byte vectorised, fp32 math with the reference's bf16 rounding points.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "../../include/pasero_b200.h"
 
 namespace pb200 {
@@ -394,6 +395,57 @@ extern "C" int pb200_pad_rows(const void* in, int32_t B, int32_t T, int32_t C, v
     PB_CHECK(C % 8 == 0 && Tp >= T + front_pad, "pad_rows: bad shape");
     pad_rows_kernel<<<ew_grid((long long)B * Tp * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)in, B, T, C,
                                                                                            (bf16*)out, Tp, front_pad);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Device-side collate of a feature batch (Task.collate's right-padding + `.to(dtype)`, pasero/tasks/task.py:531-571,
+// pasero/utils.py:709-736): the utterances' rows arrive back to back (fp16 as the reference stores them in a NumpyFile, or
+// fp32), `offsets` [B + 1] (rows) delimits them; utterance b lands at rows [front_pad, front_pad + len_b) of out[b], bf16,
+// zeros elsewhere — either the plain (B, Tp, C) batch tensor (front_pad = 0) or the conv subsampler's padded layout.
+template <typename T>
+__global__ void collate_features_kernel(const T* __restrict__ rows, const long long* __restrict__ offsets, int B, int C,
+                                        bf16* __restrict__ out, int Tp, int front_pad) {
+    const int c8 = C >> 3;
+    const long long total = (long long)B * Tp * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c8) * 8;
+        const long long rp = i / c8;
+        const int t = (int)(rp % Tp) - front_pad;
+        const int b = (int)(rp / Tp);
+        const long long begin = offsets[b];
+        const int len = (int)(offsets[b + 1] - begin);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && t < len) {
+            const T* src = rows + (begin + t) * C + c;
+            float f[8];
+            if (sizeof(T) == 2) {
+                const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 x = __half22float2(h2[e]); f[2 * e] = x.x; f[2 * e + 1] = x.y; }
+            } else {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = bq.x; f[5] = bq.y; f[6] = bq.z; f[7] = bq.w;
+            }
+            v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+        *reinterpret_cast<uint4*>(out + rp * C + c) = v;
+    }
+}
+
+extern "C" int pb200_collate_features(const void* rows, int32_t rows_fp16, const int64_t* offsets, int32_t B, int32_t C, void* out,
+                                      int32_t Tp, int32_t front_pad, void* stream_) {
+    if (B == 0 || Tp == 0) return 0;
+    PB_CHECK(C % 8 == 0 && rows && offsets && out, "collate_features: C must be a multiple of 8, pointers non-null");
+    const auto grid = ew_grid((long long)B * Tp * (C / 8));
+    if (rows_fp16)
+        collate_features_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream_>>>((const __half*)rows, (const long long*)offsets, B, C,
+                                                                              (bf16*)out, Tp, front_pad);
+    else
+        collate_features_kernel<float><<<grid, 256, 0, (cudaStream_t)stream_>>>((const float*)rows, (const long long*)offsets, B, C,
+                                                                             (bf16*)out, Tp, front_pad);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -53,3 +53,18 @@ def fbank_batch(pcm: Tensor, cmvn: bool = True) -> Tensor:
     plan = FbankPlan([N] * B, pcm.device)
     feats, _ = fbank(pcm.reshape(-1).contiguous(), plan, cmvn=cmvn)
     return feats.view(B, plan.max_frames, NUM_MEL)
+
+
+def collate_features(packed_rows, offsets, padded_rows: int, front_pad: int = 0, device='cuda', stream=None):
+    """GPU fast path for pre-extracted features (the reference's NumpyFile -> Task.collate -> move_to_device chain,
+    pasero/files.py:164-175, pasero/tasks/task.py:531-571, pasero/utils.py:691-736): `packed_rows` / `offsets` as returned by
+    `pasero_b200.task.NumpyFile.pack` (ragged rows back to back in the file's dtype, ideally in a pinned buffer). ONE
+    host->device copy of the true bytes, then one kernel pads + casts into the bf16 batch tensor — with
+    (padded_rows, front_pad) = `ConvolutionSubsampler.padded_rows(max_len)` directly in the conv subsampler's input layout
+    (pass `padded_layout=(max_len,)` to the model). Returns (bf16 [B, padded_rows, C], lengths int64 [B] on the device)."""
+    rows = torch.as_tensor(packed_rows)
+    offs = torch.as_tensor(offsets, dtype=torch.int64)
+    rows_d = rows.to(device, non_blocking=True)
+    offs_d = offs.to(device, non_blocking=True)
+    B = offs.numel() - 1
+    return K.collate_features(rows_d, offs_d, B, padded_rows, front_pad), (offs_d[1:] - offs_d[:-1])

@@ -379,6 +379,19 @@ def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tens
 
 
 @_bracketed
+def collate_features(rows: Tensor, offsets: Tensor, B: int, Tp: int, front_pad: int = 0) -> Tensor:
+    """rows: fp16 / fp32 [total_rows, C] on the device (utterances back to back), offsets int64 [B + 1] (device, in rows).
+    Returns bf16 [B, Tp, C]: utterance b at rows [front_pad, front_pad + len_b), zeros elsewhere."""
+    assert rows.dtype in (torch.float16, torch.float32) and rows.is_contiguous() and offsets.dtype == torch.int64
+    C = rows.shape[1]
+    out = torch.empty(B, Tp, C, dtype=BF16, device=rows.device)
+    _count(1)
+    check(_lib.load().pb200_collate_features(rows.data_ptr(), int(rows.dtype == torch.float16), offsets.data_ptr(), B, C,
+                                             out.data_ptr(), Tp, front_pad, stream_ptr()))
+    return out
+
+
+@_bracketed
 def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
     _count(1)
     check(_lib.load().pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))

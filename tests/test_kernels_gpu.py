@@ -173,7 +173,8 @@ def test_attention(B, H, Lq, Lk, causal, masked):
     D = H * 64
     q2, kv2 = _rand(B * Lq, D, seed=1), _rand(B * Lk, 2 * D, seed=2)
     k2, v2 = kv2[:, :D], kv2[:, D:]
-    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32) if masked else None
+    gen = torch.Generator(device='cuda').manual_seed(17 + Lq + Lk)   # seeded: the key lengths are part of the test case
+    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32, generator=gen) if masked else None
     if masked:
         kv_len[0] = Lk
     scale = 1 / 8
@@ -205,7 +206,8 @@ def test_attention_dropout(B, H, Lq, Lk, causal, masked, p):
     D = H * 64
     q2, kv2 = _rand(B * Lq, D, seed=1), _rand(B * Lk, 2 * D, seed=2)
     k2, v2 = kv2[:, :D], kv2[:, D:]
-    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32) if masked else None
+    gen = torch.Generator(device='cuda').manual_seed(23 + Lq + Lk)
+    kv_len = torch.randint(1, Lk + 1, (B,), device='cuda', dtype=torch.int32, generator=gen) if masked else None
     if masked:
         kv_len[0] = Lk
     scale = 1 / 8

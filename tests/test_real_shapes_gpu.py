@@ -12,7 +12,8 @@ computes), and its distance from the fp32 oracle is the reference's own bf16 noi
   * per-layer outputs / encoder output / logits: max-abs error <= max(3 % of the tensor's largest entry, 1.5 x the
     PyTorch-bf16 error of the same tensor);
   * loss within 1 %; token / line counts exact;
-  * every parameter gradient: max-abs error <= max(5 % of the gradient's largest entry, 2 x PyTorch-bf16 error) AND —
+  * every parameter gradient: error (see rel_err: max-abs, 99.99th percentile for large tensors) <= max(5 % of the
+    gradient's largest entry, 2 x PyTorch-bf16 error) AND —
     where PyTorch-bf16 itself resolves the tensor (cosine >= 0.98) — cosine >= min(0.99, PyTorch-bf16 cosine - 0.01).
     Two PyTorch-bf16 yardsticks are taken, explicit softmax and fused SDPA (the reference's GPU path); the noisier one
     counts: fused backends rebuild the softmax backward from the bf16-rounded output, which puts a noise floor under q / k
@@ -32,6 +33,21 @@ ACT_TOL, GRAD_TOL, GRAD_COS = 3e-2, 5e-2, 0.99
 def rel_to_max(got, want):
     got, want = got.float().cpu(), want.float().cpu()
     return ((got - want).abs().max() / want.abs().max().clamp_min(1e-12)).item()
+
+
+def rel_err(got, want):
+    """Gradient error metric: |got - want| / max |want|, taken at the 99.99th percentile for tensors of more than 100 000
+    entries (the maximum otherwise). FFN weight gradients in ANY bf16 implementation carry isolated outliers: a hidden unit
+    whose pre-activation rounds to the other side of zero flips its ReLU mask for one token and moves a handful of entries
+    by a full-size step; which entries is a coin toss between two correct implementations, how many is not."""
+    got, want = got.float().cpu(), want.float().cpu()
+    err = (got - want).abs().flatten()
+    if err.numel() > 100000:
+        k = max(1, int(err.numel() * 1e-4))
+        e = err.topk(k).values[-1]
+    else:
+        e = err.max()
+    return (e / want.abs().max().clamp_min(1e-12)).item()
 
 
 def check_act(got, want, ref16, name):
@@ -148,9 +164,9 @@ def check_grads(got: dict, want: dict, ref16: dict, skip=(), label=''):
             continue     # mathematically zero gradient (softmax is shift invariant)
         g = got[k].float().cpu()
         seen += 1
-        err, cos = rel_to_max(g, w), _cos(g, w)
+        err, cos = rel_err(g, w), _cos(g, w)
         refs = ref16 if isinstance(ref16, (list, tuple)) else [ref16]      # one or several PyTorch-bf16 yardsticks: the noisiest counts
-        err16, cos16 = max(rel_to_max(r[k], w) for r in refs), min(_cos(r[k], w) for r in refs)
+        err16, cos16 = max(rel_err(r[k], w) for r in refs), min(_cos(r[k], w) for r in refs)
         worst, worst16 = max(worst, err), max(worst16, err16)
         if err > max(GRAD_TOL, 2.0 * err16) or (cos16 >= 0.98 and cos < min(GRAD_COS, cos16 - 0.01)):
             bad[k] = (round(err, 4), round(cos, 5), 'torch-bf16:', round(err16, 4), round(cos16, 5))
