@@ -57,7 +57,7 @@ def main():
                   f'loss {logs_all[-1]["loss"]:.3f} vs {ref_logs[-1]["loss"]:.3f}, gnorm {logs_all[-1]["gnorm"]:.4f} vs {ref_logs[-1]["gnorm"]:.4f}')
         if rank == 0:
             print(f'{mode}: max |reduced gradient - accumulated gradient| / max |gradient| = {gdiff:.3e}')
-        ok = ok and diff < 2e-2 and gdiff < 2e-2
+        ok = ok and diff < 2e-2 and gdiff < 3e-2   # per-rank bf16 rounding before the sum: ~2e-2 of the largest entry, eager and graph alike
     # all ranks hold identical parameters
     p = results['eager'][0].float()
     p0 = p.clone()
