@@ -242,6 +242,20 @@ int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stri
                         int64_t ld, int64_t padding_idx, float label_smoothing, float grad_scale, int32_t write_grad,
                         double* stats, float* row_loss, void* stream);
 
+/* The same loss for large vocabularies, evaluated over column chunks [chunk_begin, chunk_begin + chunk_cols) of the
+ * projection so that no [B*T, V] tensor exists in HBM (the reference holds three fp32 ones, transformer.py:355-372):
+ *   pass 1, per chunk: pb200_ce_chunk_stats folds the chunk's logits (bf16 [B*T, chunk_cols], row stride ld) into row_state
+ *           (fp32 [4][B*T]: running max, sum exp, sum of logits, target logit; chunk_begin == 0 initialises it);
+ *   pb200_ce_chunk_finish: row_state -> stats ([0] loss, [1] nll, [2] tokens, [7] bad targets) and lse fp32 [B*T];
+ *   pass 2, per chunk: pb200_ce_chunk_grad overwrites the recomputed chunk with d loss / d logits (the caller runs the
+ *           chunk's dgrad / wgrad GEMMs on it). */
+int pb200_ce_chunk_stats(const void* logits, int64_t ld, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
+                         int64_t chunk_begin, int64_t chunk_cols, int64_t padding_idx, float* row_state, void* stream);
+int pb200_ce_chunk_finish(const float* row_state, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T, int64_t V,
+                          int64_t padding_idx, float label_smoothing, double* stats, float* lse, void* stream);
+int pb200_ce_chunk_grad(void* logits, int64_t ld, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
+                        int64_t chunk_begin, int64_t chunk_cols, int64_t V, float label_smoothing, const float* lse, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer over the flat arenas (pasero/training.py:455-487; pasero/optimization.py:56-149, 390-427).
  *   hyper fp32[16] (device): [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] 1-beta1^t

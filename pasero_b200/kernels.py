@@ -417,6 +417,38 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
                                           stats.data_ptr(), ptr(row_loss), stream_ptr()))
 
 
+# vocabularies of at least this many entries take the chunked projection + cross-entropy (ops.ProjCEFn): no [B*T, V] tensor
+# in HBM; CE_CHUNK_COLS logits columns are alive at a time (L2 resident at BASELINE batch sizes)
+CE_CHUNK_MIN_VOCAB = 32768
+CE_CHUNK_COLS = 8192
+
+
+@_bracketed
+def ce_chunk_stats(logits: Tensor, target: Tensor, c0: int, cols: int, padding_idx: int, row_state: Tensor) -> None:
+    B, T = target.shape
+    _count(1)
+    check(_lib.load().pb200_ce_chunk_stats(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols,
+                                           padding_idx, row_state.data_ptr(), stream_ptr()))
+
+
+@_bracketed
+def ce_chunk_finish(row_state: Tensor, target: Tensor, V: int, padding_idx: int, label_smoothing: float, stats: Tensor) -> Tensor:
+    B, T = target.shape
+    lse = torch.empty(B * T, dtype=torch.float32, device=row_state.device)
+    _count(1)
+    check(_lib.load().pb200_ce_chunk_finish(row_state.data_ptr(), target.data_ptr(), target.stride(0), B, T, V, padding_idx,
+                                            label_smoothing, stats.data_ptr(), lse.data_ptr(), stream_ptr()))
+    return lse
+
+
+@_bracketed
+def ce_chunk_grad(logits: Tensor, target: Tensor, c0: int, cols: int, V: int, label_smoothing: float, lse: Tensor) -> None:
+    B, T = target.shape
+    _count(1)
+    check(_lib.load().pb200_ce_chunk_grad(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols, V,
+                                          label_smoothing, lse.data_ptr(), stream_ptr()))
+
+
 _SQNORM_WS = {}
 
 

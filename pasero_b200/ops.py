@@ -726,9 +726,16 @@ class ConvGLUFn(torch.autograd.Function):
 
 class ProjCEFn(torch.autograd.Function):
     """Tied output projection + label-smoothed cross-entropy (pasero/models/modules.py:935-947,
-    transformer.py:323-380). The logits are produced once in bf16 and overwritten in place by their gradient in the
+    transformer.py:323-380). Returns the summed loss (fp32 0-dim); `stats` (fp64[8], device) receives loss / nll / token
+    count.
+
+    V < kernels.CE_CHUNK_MIN_VOCAB: the logits are produced once in bf16 and overwritten in place by their gradient in the
     same pass that computes the loss; no fp32 copy, no softmax tensor.
-    Returns the summed loss (fp32 0-dim); `stats` (fp64[8], device) receives loss / nll / token count."""
+    Larger vocabularies (BASELINE config 5: 70 376): the projection is evaluated in chunks of kernels.CE_CHUNK_COLS columns
+    that never leave L2 — pass 1 folds each chunk into per-row online log-sum-exp statistics, pass 2 recomputes the chunk,
+    turns it into d loss / d logits in place and feeds it straight to the chunk's dgrad / wgrad GEMMs. Neither the logits
+    nor their gradient exist as a [B*T, V] tensor (the reference: three fp32 copies, transformer.py:357, 367); the price is
+    the projection GEMM a second time (+1/3 of the projection FLOPs)."""
 
     unit_loss_grad = False   # Trainer sets this when the loss is the root of backward (grad_output == 1)
 
@@ -737,15 +744,70 @@ class ProjCEFn(torch.autograd.Function):
         # vocab: number of real rows of `table` (the rest is zero padding up to a multiple of 8: their logits are exactly
         # 0, the loss kernel neither reads nor overwrites them, so they act as zero gradients in backward)
         x = _c(x)
-        logits = K.linear_fwd(x, table, None)
+        V = vocab if vocab is not None else table.shape[0]
+        ctx.table = table
         before = stats[0].clone()
+        if V >= K.CE_CHUNK_MIN_VOCAB:
+            ctx.chunked = True
+            need_grad = torch.is_grad_enabled() and (x.requires_grad or table.requires_grad)
+            dx32, dtable = ProjCEFn._chunked(x, table, target, padding_idx, label_smoothing, stats, V, need_grad)
+            ctx.save_for_backward(dx32, dtable)
+            return (stats[0] - before).float()
+        ctx.chunked = False
+        logits = K.linear_fwd(x, table, None)
         K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True, vocab=vocab)
         ctx.save_for_backward(x, table, logits)
-        ctx.table = table
         return (stats[0] - before).float()
 
     @staticmethod
+    def _chunked(x, table, target, padding_idx, eps, stats, V, need_grad):
+        """Both passes. Returns (dx fp32 [M, D] or None, dtable bf16 [rows, D] or None when it went into the Trainer's
+        fp32 main-gradient arena). Gradients are those of the summed loss (grad_output == 1); backward rescales otherwise."""
+        M, D = x.shape
+        cols = K.CE_CHUNK_COLS
+        buf = torch.empty(M, cols, dtype=BF16, device=x.device)
+        state = torch.empty(4, M, dtype=torch.float32, device=x.device)
+        chunks = [(c0, min(cols, V - c0)) for c0 in range(0, V, cols)]
+
+        def project(c0, n):
+            # rows [c0, c0 + n8) of the table, n8 = n rounded up to 8 (inside the zero-padded table): logits of this chunk
+            n8 = (n + 7) // 8 * 8
+            return K.gemm_raw(x.data_ptr(), table[c0:c0 + n8].data_ptr(), buf, M, n8, D, lda=D, ldb=D, ldc=cols, split_k=1), n8
+        for c0, n in chunks:
+            project(c0, n)
+            K.ce_chunk_stats(buf, target, c0, n, padding_idx, state)
+        lse = K.ce_chunk_finish(state, target, V, padding_idx, eps, stats)
+        if not need_grad:
+            return None, None
+        dx32 = torch.zeros(M, D, dtype=torch.float32, device=x.device)
+        t32 = _sink32(table)
+        dtable = None if t32 is not None else torch.zeros_like(table)
+        for c0, n in chunks:
+            _, n8 = project(c0, n)
+            K.ce_chunk_grad(buf, target, c0, n, V, eps, lse)
+            g = buf[:, :n8]
+            # dx += dlogits_c W_c (fp32 accumulation across the chunks), dW_c = dlogits_c^T x
+            K.gemm_raw(g.data_ptr(), table[c0:c0 + n8].data_ptr(), dx32, M, D, n8, lda=cols, ldb=D, ldc=D, b_mn_major=True,
+                       accumulate=True)
+            if t32 is not None:
+                K.linear_wgrad(g, x, out=t32[c0:c0 + n8], accumulate=True)
+            else:
+                K.linear_wgrad(g, x, out=dtable[c0:c0 + n8], accumulate=False)
+        return dx32, dtable
+
+    @staticmethod
     def backward(ctx, dloss):
+        if ctx.chunked:
+            dx32, dtable = ctx.saved_tensors
+            if dx32 is None:
+                raise RuntimeError('ProjCEFn: gradients were not computed in forward (it ran without grad)')
+            if not ProjCEFn.unit_loss_grad:
+                dx32 = dx32 * dloss
+                if dtable is not None:
+                    dtable = dtable * dloss.to(dtable.dtype)
+                elif float(dloss) != 1.0:
+                    raise RuntimeError('ProjCEFn: the table gradient already sits in the gradient arena; scale the loss instead')
+            return dx32.to(BF16), dtable, None, None, None, None, None
         x, table, dlogits = ctx.saved_tensors
         dx = K.linear_dgrad(dlogits, table)
         if ProjCEFn.unit_loss_grad:
