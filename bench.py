@@ -184,9 +184,13 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-eager comparator leg (N = 1 only)')
+    ap.add_argument('--workload', default='st', choices=['st', 'whisper_small', 'big_adapters'],
+                    help="st = the headline (BASELINE configs[1]/[2]); whisper_small / big_adapters = configs[3] / [4], reported separately")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload != 'st':
+        return run_other_workload(args)
 
     import torch.distributed as dist
     from pasero_b200 import build_model, frontend
@@ -318,6 +322,118 @@ def main():
             'last_step_logs': {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in last.items()},
         }
         print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_other_workload(args):
+    """BASELINE configs[3] (Whisper-small fine-tuning shape: 30 s mel inputs, 12+12 layers, d = 768, V = 51 865) and
+    configs[4] (Transformer-big + language adapters shape: d = 1024, V = 70 376, text batches, adapters trained, base frozen):
+    the same Trainer step on synthetic features / token ids. Reported separately from the headline; same JSON keys."""
+    import torch.distributed as dist
+    from pasero_b200 import TrainingConfig, build_model
+    from pasero_b200.task import Dictionary, SpeechTranslationTask
+    from pasero_b200.training import DevicePrefetcher, Trainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    W = max(3, args.warmup)
+    rng = np.random.RandomState(4321 + rank)
+    if args.workload == 'whisper_small':
+        V, B, T = 51865, 16, 129
+        cfg = TrainingConfig.from_dict(dict(
+            arch='whisper_base', encoder_layers=12, decoder_layers=12, embed_dim=768, encoder_ffn_dim=3072, decoder_ffn_dim=3072,
+            encoder_attention_heads=12, decoder_attention_heads=12, conv_channels=768, encoder_max_len=3000, decoder_max_len=448,
+            batch_size=64000, dropout=0.1, label_smoothing=0.1, dtype='bfloat16', lr=1e-4, warmup=4000, max_steps=100000, seed=1234))
+        task = SpeechTranslationTask(cfg, Dictionary(tokens=[f't{i}' for i in range(V - 4)]))
+        enc_host = torch.from_numpy(rng.randn(B, 3000, 80).astype(np.float32)).to(torch.bfloat16)
+        enc_len = torch.full((B,), 3000, dtype=torch.int64)
+        what = ('BASELINE configs[3]: Whisper-small shape (12+12 layers, d=768, 12 heads, ffn 3072, pre-norm, GELU, learned positions, '
+                'conv k=3,3 strides 1,2), synthetic 30 s mel inputs (16, 3000, 80), 128 targets per line, V=51865, bf16')
+    else:
+        V, B, T, S = 70376, 128, 33, 32
+        cfg = TrainingConfig.from_dict(dict(
+            task='translation', arch='adapter_transformer', encoder_layers=6, decoder_layers=6, embed_dim=1024, encoder_ffn_dim=4096,
+            decoder_ffn_dim=4096, encoder_attention_heads=16, decoder_attention_heads=16, encoder_adapter_dim=64, decoder_adapter_dim=64,
+            encoder_max_len=256, batch_size=4096, dropout=0.1, label_smoothing=0.1, dtype='bfloat16', lr=5e-4, warmup=4000,
+            max_steps=100000, seed=1234))
+        task = SpeechTranslationTask.text(cfg, Dictionary(tokens=[f't{i}' for i in range(V - 4)]))
+        enc_host = torch.from_numpy(rng.randint(4, V, size=(B, S)).astype(np.int64))
+        enc_len = torch.full((B,), S, dtype=torch.int64)
+        what = ('BASELINE configs[4]: Transformer-big shape (6+6 layers, d=1024, 16 heads, ffn 4096, V=70376, shared embeddings) + '
+                'bottleneck adapters (dim 64) after every layer, base frozen (adapter_transformer), 128 x 32 text batches, bf16; '
+                'projection + CE over vocabulary chunks (no [M, V] logits in HBM)')
+    dec = rng.randint(4, V, size=(B, T)).astype(np.int64)
+    dec[:, 0] = 2
+    dec[:, -1] = 2
+    dec_host = torch.from_numpy(dec)
+    torch.manual_seed(1234)
+    model = build_model(cfg, task)
+    trainer = Trainer(cfg, task, model)
+    enc_host, dec_host = enc_host.pin_memory(), dec_host.pin_memory()
+    enc_dev, dec_dev, len_dev = enc_host.to(dev), dec_host.to(dev), enc_len.to(dev)
+    tokens_per_step = B * (T - 1) * world
+
+    def step(enc, d):
+        return trainer.train_step_graphed({'encoder_input': enc, 'encoder_input_length': len_dev, 'decoder_input': d, 'meta': {}})
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        logs = step(enc_dev, dec_dev)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        logs = step(enc_dev, dec_dev)
+    e1.record()
+    barrier()
+    clock_info = clocks.stop() if clocks else None
+    last = dict(logs.items())
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    copy_stream = torch.cuda.Stream(dev)
+    for a, b in DevicePrefetcher(((enc_host, dec_host) for _ in range(W)), dev, stream=copy_stream):
+        step(a, b)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sink, prev = 0.0, None
+    for a, b in DevicePrefetcher(((enc_host, dec_host) for _ in range(args.steps)), dev, stream=copy_stream):
+        lg = step(a, b)
+        if prev is not None:
+            sink += prev['loss']
+        prev = lg
+    sink += prev['loss']
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    roofline, gemm_share, launches, families = step_rooflines(trainer, step, enc_dev, dec_dev, ms_per_step, eager_launches=2)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'target tokens/sec/box (train step, fwd+bwd+Adam)', 'value': tokens_per_step / (ms_per_step / 1e3), 'unit': 'tokens/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': what, 'lines_per_gpu': B, 'target_len': T - 1, 'parallelism': f'dp{world}',
+                       'l2_policy': 'per-step working set exceeds the 126 MB L2'},
+            'e2e': {'value': tokens_per_step / (e2e_ms / 1e3), 'unit': 'tokens/s',
+                    'h2d_bytes_per_step': enc_host.numel() * enc_host.element_size() + dec_host.numel() * 8, 'd2h_bytes_per_step': 64},
+            'gpu_launches': launches * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline, 'cpu_baseline': None,
+            'families': families, 'gemm_share_of_step': gemm_share, 'cuda_graph': True,
+            'trainable_parameters': trainer.arena.numel, 'last_step_logs': {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in last.items()},
+        }))
     if world > 1:
         dist.destroy_process_group()
 
@@ -491,7 +607,7 @@ def event_bracket_overhead(dev) -> float:
     return max(0.0, chain(True) - chain(False))
 
 
-def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step):
+def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step, eager_launches: int = 4):
     """Live timing of every kernel family inside the real step: the CUDA graph of the step is re-captured with an
     external-event record node before and after every kernel wrapper (pb200_gemm_bf16 launches and all the others),
     replayed, and the event pairs of the last replay are read back. (Events around eager launches over-count: each
@@ -528,8 +644,8 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step):
         trainer._graph_body = orig_body
         if trainer._graphs:
             prof = K.PROFILE[len(K.PROFILE) // 2:]   # the event pairs recorded during capture = the graph's nodes
-            # one call = fbank + CMVN / layout (two launches), warm-up body and captured body (N each), grad-norm + Adam
-            launches = (K.COUNT['launches'] - 4) // 2 + 4
+            # one call = the eager launches around the graph (fbank + CMVN / layout, grad-norm + Adam), warm-up body and captured body (N each)
+            launches = (K.COUNT['launches'] - eager_launches) // 2 + eager_launches
             other = list(zip(K.PROFILE_ALL, K.PROFILE_WORK))[marks[2]:marks[3]]   # non-GEMM wrappers of the captured body
         else:                                        # --no-graph: plain events around eager launches
             prof, launches = K.PROFILE, K.COUNT['launches']

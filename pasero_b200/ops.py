@@ -749,7 +749,7 @@ class ProjCEFn(torch.autograd.Function):
         before = stats[0].clone()
         if V >= K.CE_CHUNK_MIN_VOCAB:
             ctx.chunked = True
-            need_grad = torch.is_grad_enabled() and (x.requires_grad or table.requires_grad)
+            need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]   # (grad mode is off inside forward: ask autograd)
             dx32, dtable = ProjCEFn._chunked(x, table, target, padding_idx, label_smoothing, stats, V, need_grad)
             ctx.save_for_backward(dx32, dtable)
             return (stats[0] - before).float()
