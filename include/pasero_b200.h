@@ -178,24 +178,6 @@ int pb200_colsum_f32(const void* x, int64_t M, int64_t N, int64_t ld, float* out
                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Gradient allreduce over NVLink peer memory (one node, <= 8 ranks, one process per GPU); replaces the per-bucket NCCL
- * allreduce of torch DDP (pasero/training.py:243-250). Every rank exports its bf16 gradient arena and a zeroed signal
- * pad (pb200_p2p_signal_bytes) with pb200_p2p_export, exchanges the 64-byte handles + offsets out of band, and maps
- * the peers' with pb200_p2p_import. pb200_allreduce_p2p then sums arena elements [begin, begin + count) over all ranks
- * in place (two-shot: each rank reduces 1/world of the range in fp32, rounds once, writes the result into every arena);
- * one kernel, no host state: CUDA-graph capturable, every rank must issue the same sequence of calls.
- * ---------------------------------------------------------------------------------------------- */
-size_t pb200_p2p_signal_bytes(void);
-int pb200_p2p_export(const void* ptr, void* handle_out /* 64 bytes */, int64_t* offset_out);
-int pb200_p2p_import(const void* handle, int64_t offset, void** ptr_out);
-int pb200_allreduce_p2p(void* const* data, void* const* signal, int32_t rank, int32_t world, int64_t begin, int64_t count,
-                        void* stream);
-/* the same reduction done by the NVSwitch (NVLS): mc_data = multicast address of the arenas (e.g. torch symmetric memory's
- * multicast_ptr); multimem.ld_reduce sums a chunk of all ranks in the switch, multimem.st broadcasts the result */
-int pb200_allreduce_nvls(void* mc_data, void* const* signal, int32_t rank, int32_t world, int64_t begin, int64_t count,
-                         void* stream);
-
-/* ------------------------------------------------------------------------------------------------
  * Embedding epilogue: out[r] = dropout(bf16(bf16(src_row * scale) + pos[r % L])), src_row = src[ids[r]]
  * when ids != NULL else src[r]   (pasero/models/transformer.py:739-744, 874-878; modules.py:415-457,916-933)
  * Backward: dx (no ids) or fp32 atomics into dtable[ids[r]] (rows == padding_idx skipped).

@@ -70,11 +70,6 @@ PROTOTYPES = {
                                            _P, _P, _P, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     'pb200_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'pb200_colsum_bf16': (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_size_t, _P]),
-    'pb200_p2p_signal_bytes': (c_size_t, []),
-    'pb200_p2p_export': (c_int32, [_P, _P, POINTER(c_int64)]),
-    'pb200_p2p_import': (c_int32, [_P, c_int64, POINTER(c_void_p)]),
-    'pb200_allreduce_p2p': (c_int32, [_P, _P, c_int32, c_int32, c_int64, c_int64, _P]),
-    'pb200_allreduce_nvls': (c_int32, [_P, _P, c_int32, c_int32, c_int64, c_int64, _P]),
     'pb200_colsum_f32': (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_size_t, _P]),
     'pb200_embed_fwd': (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,
                                   _P, c_int64, _P, _P]),

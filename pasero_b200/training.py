@@ -67,9 +67,7 @@ class LRScheduler:
 class ParamArena:
     """Flat storage for parameters (bf16), gradients (bf16) and Adam moments (fp32); parameters become views."""
 
-    def __init__(self, model: torch.nn.Module, device, grad_factory=None):
-        """grad_factory(numel) -> zeroed bf16 tensor: lets the Trainer place the gradient arena in memory that other ranks
-        can map (P2PAllreduce with symmetric memory); default: the caching allocator."""
+    def __init__(self, model: torch.nn.Module, device):
         self.params, self.names, self.offsets = [], [], []
         seen = set()
         off = 0
@@ -83,7 +81,7 @@ class ParamArena:
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
         self.param = torch.zeros(off, dtype=BF16, device=device)
-        self.grad = torch.zeros(off, dtype=BF16, device=device) if grad_factory is None else grad_factory(off)
+        self.grad = torch.zeros(off, dtype=BF16, device=device)
         # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
         # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
         self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
@@ -132,90 +130,6 @@ class ParamArena:
                 p.grad = self.view(self.grad, i)
 
 
-class P2PAllreduce:
-    """Gradient allreduce over NVLink peer memory (csrc/comm.cu): every rank maps every other rank's bf16 gradient arena
-    and signal pad (CUDA IPC) once; a bucket is then reduced in place by ONE kernel launch with no host-side state, so
-    — unlike the NCCL call it replaces — it is captured in the step's CUDA graph and overlaps backward there as well.
-    Single node, <= 8 ranks, one process per GPU.
-
-    Two ways to obtain the peer mappings (PB200_P2P_MAP): 'ipc' (default) exports the caching allocator's blocks with legacy
-    CUDA IPC (cudaIpcOpenMemHandle: every process then owns a context on each peer GPU); 'symm' uses torch's symmetric
-    memory (cuMem handles exchanged by its rendezvous; the gradient arena must then come from `symmetric_empty`)."""
-
-    @staticmethod
-    def mapping() -> str:
-        return os.environ.get('PB200_P2P_MAP', 'ipc')
-
-    @staticmethod
-    def symmetric_empty(numel: int, dtype, device) -> Tensor:
-        import torch.distributed._symmetric_memory as symm_mem
-        t = symm_mem.empty(numel, dtype=dtype, device=device)
-        t.zero_()
-        return t
-
-    def __init__(self, grad: Tensor, group=None):
-        import ctypes
-        lib = K._lib.load()
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world > 8:
-            raise RuntimeError('peer-memory allreduce covers one node (<= 8 ranks)')
-        self.grad = grad
-        self._mc = 0
-        words = lib.pb200_p2p_signal_bytes() // 4
-        self._data = (ctypes.c_void_p * 8)()
-        self._sig = (ctypes.c_void_p * 8)()
-        if self.mapping() == 'symm':
-            import torch.distributed._symmetric_memory as symm_mem
-            pg = group if group is not None else dist.group.WORLD
-            self.signal = self.symmetric_empty(words, torch.int32, grad.device)
-            torch.cuda.synchronize(grad.device)
-            self._handles = (symm_mem.rendezvous(grad, pg), symm_mem.rendezvous(self.signal, pg))   # kept alive: they own the mappings
-            for arr, own, handle in zip((self._data, self._sig), (grad, self.signal), self._handles):
-                for r in range(self.world):
-                    arr[r] = own.data_ptr() if r == self.rank else int(handle.buffer_ptrs[r]) + int(handle.offset)
-            # PB200_P2P_NVLS=1: let the NVSwitch do the sum (multimem.ld_reduce / multimem.st on the multicast mapping)
-            mc = int(getattr(self._handles[0], 'multicast_ptr', 0) or 0)
-            if os.environ.get('PB200_P2P_NVLS', '0') == '1':
-                if not mc:
-                    raise RuntimeError('PB200_P2P_NVLS=1 but the symmetric-memory allocation has no multicast mapping')
-                self._mc = mc + int(self._handles[0].offset)
-            dist.barrier(group)
-            return
-        self.signal = torch.zeros(words, dtype=torch.int32, device=grad.device)
-        torch.cuda.synchronize(grad.device)      # the zero-fill has landed before any peer can post a flag
-        mine = []
-        for t in (grad, self.signal):
-            handle, offset = ctypes.create_string_buffer(64), ctypes.c_int64()
-            K.check(lib.pb200_p2p_export(t.data_ptr(), handle, ctypes.byref(offset)))
-            mine.append((handle.raw, offset.value))
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, (os.uname().nodename, mine), group=group)
-        if len({host for host, _ in everyone}) != 1:
-            raise RuntimeError('peer-memory allreduce needs all ranks on one node')
-        for r, (_, handles) in enumerate(everyone):
-            for arr, own, (handle, offset) in zip((self._data, self._sig), (grad, self.signal), handles):
-                if r == self.rank:
-                    arr[r] = own.data_ptr()
-                else:
-                    ptr = ctypes.c_void_p()
-                    K.check(lib.pb200_p2p_import(handle, offset, ctypes.byref(ptr)))
-                    arr[r] = ptr.value
-        dist.barrier(group)
-
-    def timeouts(self) -> int:
-        """Barrier waits that gave up (~10 s) since start-up; non-zero means a peer never arrived and the gradients of that
-        step are not to be trusted (synchronises)."""
-        return int(self.signal[-1].item())
-
-    def allreduce(self, lo: int, hi: int) -> None:
-        """grad[lo:hi] <- sum over ranks, in place, on the current stream."""
-        lib = K._lib.load()
-        if self._mc:
-            K.check(lib.pb200_allreduce_nvls(self._mc, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
-        else:
-            K.check(lib.pb200_allreduce_p2p(self._data, self._sig, self.rank, self.world, lo, hi - lo, K.stream_ptr()))
-
-
 class GradBuckets:
     """Bucketed allreduce of the gradient arena, overlapped with backward (replaces torch DDP's reducer,
     pasero/training.py:243-250). Buckets are contiguous arena slices of ~bucket_bytes, filled back to front."""
@@ -249,7 +163,6 @@ class GradBuckets:
         self.launch_order = []
         self.pre_launch = None   # callable(bucket index) run on the compute stream before the bucket's allreduce
         self.pre_all = None      # callable() doing the same for the whole arena at once (allreduce_all)
-        self.p2p = None          # P2PAllreduce: peer-memory kernel instead of the NCCL call (CUDA-graph capturable)
         # list while the step's CUDA graph is being captured in "overlap" mode: instead of reducing a complete bucket, the
         # capture records an EXTERNAL event (an event-record node of the graph) at the point where the bucket's gradients
         # are final; after every replay the NCCL allreduces are enqueued on the side stream behind those events
@@ -281,10 +194,7 @@ class GradBuckets:
         elif self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                if self.p2p is not None:
-                    self.p2p.allreduce(lo, hi)
-                else:
-                    dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         self.pending[b] = -1
@@ -332,10 +242,6 @@ class GradBuckets:
                 dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         torch.cuda.current_stream().wait_stream(self.stream)
 
-    def reduce_stats(self, stats: Tensor) -> None:
-        """The step scalars alone (NCCL, 32 bytes): after a graph whose buckets were reduced by captured P2P kernels."""
-        dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
-
     def finish(self, stats: Optional[Tensor] = None) -> None:
         """Flush buckets whose hooks never fired (unused parameters), reduce the step scalars, rejoin the stream."""
         for b in range(len(self.buckets)):
@@ -379,16 +285,24 @@ class Trainer:
         model.to(self.device)
         from . import reference_param_names
         ref_names = reference_param_names(model)     # before the arena: afterwards every parameter shares one storage
-        # (experimental peer-memory allreduce with symmetric memory: the gradient arena has to be allocated there)
-        symm = (self.distributed and os.environ.get('PB200_P2P_ALLREDUCE', '0') == '1' and P2PAllreduce.mapping() == 'symm')
-        self.arena = ParamArena(model, self.device,
-                                (lambda n: P2PAllreduce.symmetric_empty(n, BF16, self.device)) if symm else None)
+        self.arena = ParamArena(model, self.device)
         self.param_names = list(self.arena.names)
         # the reference's names of the TRAINABLE parameters: optimizer state is keyed by them (pasero/training.py:899-906)
         self.reference_names = [r for n in self.arena.names for r in ref_names[n]]
         if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.arena.param, src=0)
-        self.buckets = GradBuckets(self.arena, cfg.bucket_bytes) if self.distributed else None
+        # a communicator of its own for the gradient buckets, on HIGH-PRIORITY streams: the step's persistent GEMM kernels follow
+        # each other without a gap (programmatic dependent launch), and a normal-priority NCCL kernel is only scheduled once
+        # the whole backward has drained — which is exactly the overlap that is wanted (measured at N = 8: 0.01 ms gained
+        # without, see profiles/README.md)
+        group = None
+        if self.distributed and os.environ.get('PB200_NCCL_PRIORITY', '1') != '0':
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                group = dist.new_group(backend='nccl', pg_options=opts)
+            except Exception:   # noqa: BLE001  (another backend / an old torch): the default group does the job
+                group = None
+        self.buckets = GradBuckets(self.arena, cfg.bucket_bytes, group) if self.distributed else None
         # parameter gradients go straight into the arena (no AccumulateGrad adds, no per-step memset)
         index = {id(p): i for i, p in enumerate(self.arena.params)}
         on_ready = (lambda p: self.buckets.param_ready(index[id(p)])) if self.buckets is not None else None
@@ -416,28 +330,11 @@ class Trainer:
         model.defer_logs = True
         ops.DropoutState.reseed(cfg.seed if cfg.seed is not None else int(time.time()))
         self._graphs = {}
-        # EXPERIMENTAL, off by default: with the collectives captured in the graph the N=2 update is correct
-        # (tools/ddp_check.py) but the processes hang at teardown / in long runs on this stack (NCCL 2.28.9, torch 2.11)
-        self.graph_collectives = os.environ.get('PB200_GRAPH_NCCL', '0') == '1'
-        # PB200_GRAPH_OVERLAP=0: one whole-arena allreduce between the step graph and the optimizer (the round-1 behaviour)
+        # Data parallel + CUDA graph: NCCL calls are not captured (capturing them hangs on this stack: NCCL 2.28.9, torch 2.11);
+        # the step graph carries one EXTERNAL event-record node per gradient bucket instead and the allreduces are enqueued
+        # on the side stream behind those events after every replay, so they run next to the rest of the replayed backward.
+        # PB200_GRAPH_OVERLAP=0: one whole-arena allreduce between the step graph and the optimizer (the round-1 behaviour).
         self.overlap_graph_allreduce = os.environ.get('PB200_GRAPH_OVERLAP', '1') != '0'
-        # Peer-memory allreduce (PB200_P2P_ALLREDUCE=1): one capturable kernel per bucket, so the reductions are part of
-        # the step graph and overlap backward. EXPERIMENTAL, off by default: verified at N = 2 (tools/ddp_check.py: update
-        # == single-process accumulation, eager and graph; 9.41 -> 9.25 ms/step), but the one N = 8 run timed out and
-        # could not be diagnosed before the round's GPU budget ran out. Every rank must take the same decision: agree on it.
-        if self.buckets is not None and os.environ.get('PB200_P2P_ALLREDUCE', '0') == '1':
-            p2p, err = None, ''
-            try:
-                p2p = P2PAllreduce(self.arena.grad)
-            except Exception as e:  # noqa: BLE001  (no peer access / IPC, several nodes, > 8 ranks): NCCL stays
-                err = str(e)
-            ok = torch.tensor([1 if p2p is not None else 0], device=self.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 1:
-                self.buckets.p2p = p2p
-                self.graph_collectives = True
-            elif dist.get_rank() == 0:
-                print(f'pasero_b200: peer-memory allreduce unavailable ({err or "failed on another rank"}); using NCCL', flush=True)
         self.saved = True
 
     # ------------------------------------------------------------------ step pieces
@@ -562,10 +459,9 @@ class Trainer:
         # anything in `meta` may select code paths (adapters by language / domain): a graph is only replayed for the same meta
         key = key + tuple(sorted((k, str(v)) for k, v in (batch.get('meta') or {}).items() if k != 'step'))
         self.model.train()
-        p2p_graph = self.buckets is not None and self.buckets.p2p is not None
         # data parallel, NCCL: the allreduces stay outside the graph (capturing them hangs on this stack) but are ordered
         # behind external event nodes of the graph, one per bucket, so they overlap the replayed backward
-        overlap = self.buckets is not None and not self.graph_collectives and self.overlap_graph_allreduce
+        overlap = self.buckets is not None and self.overlap_graph_allreduce
         if key not in self._graphs:
             static = {}
             for k, v in tensors.items():
@@ -577,18 +473,12 @@ class Trainer:
             self._write_hyper()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            # graph_collectives: the bucketed allreduces (side stream, launched from backward as buckets complete) and the
-            # scalar allreduce are captured INSIDE the graph, so they overlap backward exactly as in the eager step;
-            # otherwise every bucket is reduced between the graph and the optimizer kernels
-            in_graph = self.buckets is not None and self.graph_collectives
             if self.buckets is not None:
-                self.buckets.start_step(sync=in_graph)
+                self.buckets.start_step(sync=False)     # warm-up pass: no collectives
             with torch.cuda.stream(side):   # warm-up outside capture (lazy inits, workspace sizes, NCCL communicators)
                 for k, v in tensors.items():
                     static[k].copy_(v)
                 self._graph_body(static, extras)
-                if in_graph:
-                    self.buckets.finish(None if p2p_graph else self.stats)
                 # the warm-up pass accumulated real gradients into the fp32 main-gradient arena; with buckets they are only
                 # flushed (and zeroed) after the replay below, which would add this batch's gradient a second time
                 self.arena.grad32.zero_()
@@ -597,15 +487,15 @@ class Trainer:
             ops.DropoutState.offset = 0
             events, stats_event = None, None
             if self.buckets is not None:
-                self.buckets.start_step(sync=in_graph or overlap)
+                self.buckets.start_step(sync=overlap)
                 if overlap:
                     events = self.buckets.capture_events = []
                     stats_event = torch.cuda.Event(external=True)
             try:
                 with torch.cuda.graph(graph):
                     self._graph_body(static, extras, after_forward=stats_event.record if overlap else None)
-                    if in_graph or overlap:
-                        self.buckets.finish(None if (p2p_graph or overlap) else self.stats)
+                    if overlap:
+                        self.buckets.finish(None)
             finally:
                 if self.buckets is not None:
                     self.buckets.capture_events = None
@@ -618,10 +508,8 @@ class Trainer:
         self.rng_base += 1
         if events is not None:
             self.buckets.reduce_behind_events(events, self.stats, stats_event)
-        elif self.buckets is not None and not self.graph_collectives:
+        elif self.buckets is not None:
             self.buckets.allreduce_all(self.stats)
-        elif p2p_graph:
-            self.buckets.reduce_stats(self.stats)   # the buckets were reduced inside the graph
         self._optimizer_kernels()
         return self._finish_step()
 
