@@ -352,17 +352,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 struct BwdCfg {
     static constexpr int T = 256 * 128;                 // one [256 x 64] bf16 operand
     static constexpr int PT = 128 * 256;                // one [128 x 128] bf16 tile (two 64-column blocks)
-    static constexpr int SMEM_BYTES = 4 * T + 2 * PT + 2 * 256 * 4 + 1024 /*align*/ + 64 /*barriers*/;
+    static constexpr int SMEM_BYTES = 4 * T + 2 * PT + 2 * 256 * 4 + 1024 /*align*/ + 128 /*barriers*/;
     // TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ chunk i [384 + 64 i, ...)
 };
 
-// The four operands arrive as 128-row tiles on four one-shot barriers, in the order the first iteration consumes them:
-// (K_0, Q_0) -> S^T of iteration 0; (V_0, dO_0) -> dP^T; (Q_1, dO_1) and (K_1, V_1) land while iteration 0 computes.
-// Measured: the CTAs of a wave run in lock-step, so the load phase is a DRAM burst of 148 x 192 KB (operand tiles + the
-// O / dO rows of delta) at ~4.4 TB/s, ~30 % of the CTA's life; neither these finer barriers nor cp.async loads by the
-// 256 softmax threads (tried, removed) shortened it — only a second resident CTA per SM would (192 KB of smem: no room).
+// PERSISTENT: one CTA per SM walks the (head, batch, query block, key block) items of the launch. Round 1 ran one CTA per
+// item and measured ~30 % of each CTA's life waiting for its 192 KB of operands (all CTAs of a wave load in lock-step;
+// shared memory and TMEM leave no room for a second resident CTA). Here a dedicated TMA warp refills every operand buffer
+// as soon as the LAST MMA that reads it has retired (tcgen05.commit on a "buffer free" barrier): K_0 / V_0 of the next
+// item are requested after the current item's first key tile is finished, Q_0 / dO_0 after its second-to-last iteration,
+// so the next item's first S^T / dP^T products start the moment the current item's last chains are issued.
+// Operand tiles are 128 rows; load groups: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1).
+static constexpr int BWD_THREADS = 320;   // 8 softmax / drain warps, 1 MMA warp, 1 TMA warp
+
 template <bool CAUSAL, bool DROPOUT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                    const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
                    const AttnTcDev p) {
@@ -379,34 +383,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     float* sDelta = sLse + 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
     uint64_t* bar_s = bars, *bar_p = bars + 1, *bar_acc = bars + 2;
-    uint64_t* bar_ld = bars + 3;   // [4]: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* bar_ld = bars + 3;     // [4] operand group landed: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1)
+    uint64_t* bar_free = bars + 7;   // [4] buffers reusable: (K_0, V_0), (Q_0, dO_0), (Q_1, dO_1), (K_1, V_1)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.x, b = blockIdx.y;
-    // this CTA's (query block, key block) pair: 256 queries x 256 keys, indexed from (q0, k0)
-    const int qi = blockIdx.z / p.n_kb, kj = blockIdx.z - qi * p.n_kb;
-    const int q0 = qi * 256, k0 = kj * 256;
-    const int q_box = min(256, ((p.Lq - q0 + 15) >> 4) << 4), kv_box = min(256, ((p.Lk - k0 + 15) >> 4) << 4);
-    const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
-    const int ni = (q_box + 127) >> 7, nj = (kv_box + 127) >> 7;
-    const bool part = p.n_qb * p.n_kb > 1;
-#ifdef PB_ATTN_TIMING
-    const int cta_lin = blockIdx.x + gridDim.x * blockIdx.y;
-    if (warp == 8 && lane == 0 && cta_lin < 4096) {
-        unsigned long long gt; unsigned smid;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        g_attn_t[cta_lin * 16 + 14] = (long long)gt; g_attn_t[cta_lin * 16 + 15] = smid;
-    }
-    if (warp == 8) TSTAMP(0);
-#endif
+    const int pairs = p.n_qb * p.n_kb;
+    const int total_items = p.H * p.B * pairs;
+    const bool part = pairs > 1;
 
     if (warp == 8) {
         if (lane == 0) {
             ptx::prefetch_tmap(&tmq); ptx::prefetch_tmap(&tmk); ptx::prefetch_tmap(&tmv); ptx::prefetch_tmap(&tmdo);
             ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_acc, 1);
-            for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar_ld[i], 1);
+            for (int i = 0; i < 4; ++i) { ptx::mbar_init(&bar_ld[i], 1); ptx::mbar_init(&bar_free[i], 1); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -418,254 +408,294 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();   // set-up above overlaps the previous kernel; global memory is touched only below
-    const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
-    const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
     const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                    t_dq = tmem_base + 384;
 
-    if (warp == 8) {
+    // item -> (head, batch, query block, key block) and the block's extents
+    struct Item { int h, b, qi, kj, q0, k0, q_box, kv_box, ni, nj; };
+    auto decode = [&](int item) {
+        Item w;
+        const int pair = item % pairs, hb = item / pairs;
+        w.h = hb % p.H; w.b = hb / p.H;
+        w.qi = pair / p.n_kb; w.kj = pair - w.qi * p.n_kb;
+        w.q0 = w.qi * 256; w.k0 = w.kj * 256;
+        w.q_box = min(256, ((p.Lq - w.q0 + 15) >> 4) << 4);
+        w.kv_box = min(256, ((p.Lk - w.k0 + 15) >> 4) << 4);
+        w.ni = (w.q_box + 127) >> 7; w.nj = (w.kv_box + 127) >> 7;
+        return w;
+    };
+
+    if (warp == 9) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            {
-                const uint32_t qb = (uint32_t)p.q_tma_rows * 128u, kb = (uint32_t)p.kv_tma_rows * 128u;   // bytes per tile box
+            const uint32_t qb = (uint32_t)p.q_tma_rows * 128u, kb = (uint32_t)p.kv_tma_rows * 128u;   // bytes per tile box
+            uint32_t n = 0, n2 = 0, n3 = 0;   // items so far / items so far that used load group 2 / 3 (barrier phases)
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+                const Item w = decode(item);
+                const uint32_t fpar = (n & 1) ^ 1;     // "free" barriers: the first pass falls through (fresh barriers)
+                ptx::mbar_wait(&bar_free[0], fpar);    // K_0, V_0
+                ptx::mbar_wait(&bar_free[1], fpar);    // Q_0, dO_0
                 ptx::mbar_arrive_expect_tx(&bar_ld[0], qb + kb);
-                ptx::tma_load_3d(&tmk, &bar_ld[0], sK, h * 64, k0, b);
-                ptx::tma_load_3d(&tmq, &bar_ld[0], sQ, h * 64, q0, b);
+                ptx::tma_load_3d(&tmk, &bar_ld[0], sK, w.h * 64, w.k0, w.b);
+                ptx::tma_load_3d(&tmq, &bar_ld[0], sQ, w.h * 64, w.q0, w.b);
                 ptx::mbar_arrive_expect_tx(&bar_ld[1], qb + kb);
-                ptx::tma_load_3d(&tmv, &bar_ld[1], sV, h * 64, k0, b);
-                ptx::tma_load_3d(&tmdo, &bar_ld[1], sdO, h * 64, q0, b);
-                if (ni > 1) {
+                ptx::tma_load_3d(&tmv, &bar_ld[1], sV, w.h * 64, w.k0, w.b);
+                ptx::tma_load_3d(&tmdo, &bar_ld[1], sdO, w.h * 64, w.q0, w.b);
+                ptx::mbar_wait(&bar_free[2], fpar);    // Q_1, dO_1
+                if (w.ni > 1) {
                     ptx::mbar_arrive_expect_tx(&bar_ld[2], 2 * qb);
-                    ptx::tma_load_3d(&tmq, &bar_ld[2], sQ + 16384, h * 64, q0 + 128, b);
-                    ptx::tma_load_3d(&tmdo, &bar_ld[2], sdO + 16384, h * 64, q0 + 128, b);
+                    ptx::tma_load_3d(&tmq, &bar_ld[2], sQ + 16384, w.h * 64, w.q0 + 128, w.b);
+                    ptx::tma_load_3d(&tmdo, &bar_ld[2], sdO + 16384, w.h * 64, w.q0 + 128, w.b);
+                    ++n2;
                 }
-                if (nj > 1) {
+                ptx::mbar_wait(&bar_free[3], fpar);    // K_1, V_1
+                if (w.nj > 1) {
                     ptx::mbar_arrive_expect_tx(&bar_ld[3], 2 * kb);
-                    ptx::tma_load_3d(&tmk, &bar_ld[3], sK + 16384, h * 64, k0 + 128, b);
-                    ptx::tma_load_3d(&tmv, &bar_ld[3], sV + 16384, h * 64, k0 + 128, b);
+                    ptx::tma_load_3d(&tmk, &bar_ld[3], sK + 16384, w.h * 64, w.k0 + 128, w.b);
+                    ptx::tma_load_3d(&tmv, &bar_ld[3], sV + 16384, w.h * 64, w.k0 + 128, w.b);
+                    ++n3;
                 }
             }
-            TSTAMP(1);
-            ptx::mbar_wait(&bar_ld[0], 0);
-            ptx::tc_fence_after();
-            TSTAMP(2);
+            (void)n2; (void)n3;
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
             const uint32_t idesc_cd = ptx::make_idesc_bf16(128, 64, false, true);
             const uint32_t idesc_e = ptx::make_idesc_bf16(128, 64, true, true);
-            int it = 0;
-            for (int j = 0; j < nj; ++j) {
-                const int kc = min(128, kv_box - 128 * j);       // key rows of this tile inside the TMA box
-                for (int i = 0; i < ni; ++i, ++it) {
-                    const int nq = min(128, q_box - 128 * i);     // query columns of this chunk inside the box
-                    const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
-                    // S^T = K_j Q_i^T and dP^T = V_j dO_i^T. Independent chains are interleaved step by step: consecutive
-                    // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
-                    const uint64_t kd = kdesc(sK + j * 16384, 0), qd = kdesc(sQ + i * 16384, 0);
-                    const uint64_t vd = kdesc(sV + j * 16384, 0), dod = kdesc(sdO + i * 16384, 0);
-                    if (it == 0) {
+            uint32_t it = 0, n = 0, n2 = 0, n3 = 0;   // iterations / items / uses of load groups 2 and 3 so far (barrier phases)
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+                const Item w = decode(item);
+                const uint32_t lpar = n & 1;
+                int local = 0;
+                for (int j = 0; j < w.nj; ++j) {
+                    const int kc = min(128, w.kv_box - 128 * j);       // key rows of this tile inside the TMA box
+                    for (int i = 0; i < w.ni; ++i, ++it, ++local) {
+                        const int nq = min(128, w.q_box - 128 * i);     // query columns of this chunk inside the box
+                        const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
+                        // S^T = K_j Q_i^T and dP^T = V_j dO_i^T. Independent chains are interleaved step by step: consecutive
+                        // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
+                        const uint64_t kd = kdesc(sK + j * 16384, 0), qd = kdesc(sQ + i * 16384, 0);
+                        const uint64_t vd = kdesc(sV + j * 16384, 0), dod = kdesc(sdO + i * 16384, 0);
+                        if (local == 0) {
+                            ptx::mbar_wait(&bar_ld[0], lpar);
+                            ptx::tc_fence_after();
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
-                        ptx::mbar_wait(&bar_ld[1], 0);
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                            ptx::mbar_wait(&bar_ld[1], lpar);
+                            ptx::tc_fence_after();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                        } else {
+                            if (j == 0 && i == 1) { ptx::mbar_wait(&bar_ld[2], n2 & 1); ++n2; ptx::tc_fence_after(); }   // Q_1, dO_1
+                            if (j == 1 && i == 0) { ptx::mbar_wait(&bar_ld[3], n3 & 1); ++n3; ptx::tc_fence_after(); }   // K_1, V_1
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                                ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                            }
+                        }
+                        ptx::umma_commit(bar_s);
+                        ptx::mbar_wait(bar_p, it & 1);
                         ptx::tc_fence_after();
+                        const int qsteps = nq >> 4, ksteps = kc >> 4;
+                        const uint64_t ptd = kdesc(sPT, 0), dstd = kdesc(sdST, 0), dst_mn = mndesc(sdST, 0, 16384);
+                        const uint64_t do_mn = mndesc(sdO + i * 16384, 0, 8192), q_mn = mndesc(sQ + i * 16384, 0, 8192);
+                        const uint64_t k_mn = mndesc(sK + j * 16384, 0, 8192);
+                        const uint32_t acc_i = i > 0 ? 1u : 0u, acc_j = j > 0 ? 1u : 0u;
+                        const uint32_t t_dqi = t_dq + 64 * i;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
-                    } else {
-                        if (j == 0 && i == 1) { ptx::mbar_wait(&bar_ld[2], 0); ptx::tc_fence_after(); }   // Q_1, dO_1
-                        if (j == 1 && i == 0) { ptx::mbar_wait(&bar_ld[3], 0); ptx::tc_fence_after(); }   // K_1, V_1
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
-                            ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                        for (int kk = 0; kk < 8; ++kk) {   // the three chains interleaved
+                            if (kk < qsteps) {
+                                // dV_j += P^T dO_i ; dK_j += dS^T Q_i
+                                ptx::umma_bf16_lh(t_dv, lo32(ptd) + kstep16(kk), hi32(ptd), lo32(do_mn) + 128 * kk, hi32(do_mn), idesc_cd,
+                                                  kk > 0 ? 1u : acc_i);
+                                ptx::umma_bf16_lh(t_dk, lo32(dstd) + kstep16(kk), hi32(dstd), lo32(q_mn) + 128 * kk, hi32(q_mn), idesc_cd,
+                                                  kk > 0 ? 1u : acc_i);
+                            }
+                            if (kk < ksteps)   // dQ_i += dS K_j   (A = dS^T read MN-major)
+                                ptx::umma_bf16_lh(t_dqi, lo32(dst_mn) + 128 * kk, hi32(dst_mn), lo32(k_mn) + 128 * kk, hi32(k_mn), idesc_e,
+                                                  kk > 0 ? 1u : acc_j);
                         }
+                        ptx::umma_commit(bar_acc);
+                        // operand buffers whose last reader has just been issued go back to the TMA warp (the commit arrives
+                        // when these MMAs have retired); buffers this item never used are released with the last iteration
+                        const bool last = (j == w.nj - 1 && i == w.ni - 1);
+                        if (j == 0 && i == w.ni - 1) ptx::umma_commit(&bar_free[0]);                 // K_0, V_0
+                        if (j == w.nj - 1 && i == 0) ptx::umma_commit(&bar_free[1]);                 // Q_0, dO_0
+                        if ((w.ni > 1 && j == w.nj - 1 && i == 1) || (w.ni == 1 && last)) ptx::umma_commit(&bar_free[2]);   // Q_1, dO_1
+                        if ((w.nj > 1 && j == 1 && i == w.ni - 1) || (w.nj == 1 && last)) ptx::umma_commit(&bar_free[3]);   // K_1, V_1
                     }
-                    ptx::umma_commit(bar_s);
-                    if (it == 0) TSTAMP(3);
-                    ptx::mbar_wait(bar_p, it & 1);
-                    ptx::tc_fence_after();
-                    if (it == 0) TSTAMP(4);
-                    const int qsteps = nq >> 4, ksteps = kc >> 4;
-                    const uint64_t ptd = kdesc(sPT, 0), dstd = kdesc(sdST, 0), dst_mn = mndesc(sdST, 0, 16384);
-                    const uint64_t do_mn = mndesc(sdO + i * 16384, 0, 8192), q_mn = mndesc(sQ + i * 16384, 0, 8192);
-                    const uint64_t k_mn = mndesc(sK + j * 16384, 0, 8192);
-                    const uint32_t acc_i = i > 0 ? 1u : 0u, acc_j = j > 0 ? 1u : 0u;
-                    const uint32_t t_dqi = t_dq + 64 * i;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {   // the three chains interleaved
-                        if (kk < qsteps) {
-                            // dV_j += P^T dO_i ; dK_j += dS^T Q_i
-                            ptx::umma_bf16_lh(t_dv, lo32(ptd) + kstep16(kk), hi32(ptd), lo32(do_mn) + 128 * kk, hi32(do_mn), idesc_cd,
-                                              kk > 0 ? 1u : acc_i);
-                            ptx::umma_bf16_lh(t_dk, lo32(dstd) + kstep16(kk), hi32(dstd), lo32(q_mn) + 128 * kk, hi32(q_mn), idesc_cd,
-                                              kk > 0 ? 1u : acc_i);
-                        }
-                        if (kk < ksteps)   // dQ_i += dS K_j   (A = dS^T read MN-major)
-                            ptx::umma_bf16_lh(t_dqi, lo32(dst_mn) + 128 * kk, hi32(dst_mn), lo32(k_mn) + 128 * kk, hi32(k_mn), idesc_e,
-                                              kk > 0 ? 1u : acc_j);
-                    }
-                    ptx::umma_commit(bar_acc);
-                    if (it == 0) TSTAMP(5);
                 }
             }
-            TSTAMP(6);
+            // the last item's "buffer free" arrivals are asynchronous (tcgen05.commit) and have no consumer: they must have
+            // landed in this CTA's shared memory before the CTA may exit and the memory is handed to another block
+            if (n > 0)
+                for (int g = 0; g < 4; ++g) ptx::mbar_wait(&bar_free[g], (n - 1) & 1);
         }
     } else {
+        // ===================== softmax / drain warps =====================
         // warps w and w + 4 own the same 32 key rows (TMEM lanes) and split the query columns / output columns
         const int quarter = warp & 3, half = warp >> 2;
         const int t = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
-            const int r = threadIdx.x;   // 0..255: query q0 + r
-            float l2 = INFINITY, dl = 0.f;
-            if (r < Lq_blk) {
-                l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + q0 + r] * LOG2E_F;
-                const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.Lq + q0 + r) * p.ldo + h * 64);
-                const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + q0 + r) * p.lddo + h * 64);
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const Item w = decode(item);
+            const int h = w.h, b = w.b, q0 = w.q0, k0 = w.k0, qi = w.qi, kj = w.kj, ni = w.ni, nj = w.nj;
+            const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
+            const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
+            const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
+            ptx::bar_sync(1, 256);     // everybody is done with the previous item's lse / delta
+            {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
+                const int r = threadIdx.x;   // 0..255: query q0 + r
+                float l2 = INFINITY, dl = 0.f;
+                if (r < Lq_blk) {
+                    l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + q0 + r] * LOG2E_F;
+                    const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.Lq + q0 + r) * p.ldo + h * 64);
+                    const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + q0 + r) * p.lddo + h * 64);
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint4 a = __ldg(po + g), d = __ldg(pd + g);
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+                    for (int g = 0; g < 8; ++g) {
+                        const uint4 a = __ldg(po + g), d = __ldg(pd + g);
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 af = unpack_bf16x2(aw[e]), df = unpack_bf16x2(dw[e]);
-                        dl = fmaf(af.x, df.x, dl); dl = fmaf(af.y, df.y, dl);
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 af = unpack_bf16x2(aw[e]), df = unpack_bf16x2(dw[e]);
+                            dl = fmaf(af.x, df.x, dl); dl = fmaf(af.y, df.y, dl);
+                        }
                     }
                 }
+                sLse[r] = l2; sDelta[r] = dl;
             }
-            sLse[r] = l2; sDelta[r] = dl;
-        }
-        ptx::bar_sync(1, 256);
-        if (warp == 0) TSTAMP(8);
+            ptx::bar_sync(1, 256);
 
-        int it = 0;
-        for (int j = 0; j < nj; ++j) {
-            const int key = 128 * j + t;            // block-local key of this thread
-            const bool rowok = key < kvlen;
-            for (int i = 0; i < ni; ++i, ++it) {
-                const int nq = min(128, q_box - 128 * i);
-                const int nch = (nq + 31) >> 5;
-                ptx::mbar_wait(bar_s, it & 1);
-                ptx::tc_fence_after();
-                if (warp == 0 && it == 0) TSTAMP(9);
-                if (warp == 0 && it == 1) TSTAMP(11);
-#pragma unroll 1
-                for (int c = half; c < nch; c += 2) {
-                    uint32_t s[32], dp[32];
-                    ptx::tmem_ld_32x32(t_s + lane_base + c * 32, s);
-                    ptx::tmem_ld_32x32(t_dp + lane_base + c * 32, dp);
-                    ptx::tmem_ld_wait();
-                    const int qb = 128 * i + c * 32;
-                    const float4* l4 = reinterpret_cast<const float4*>(sLse + qb);
-                    const float4* d4 = reinterpret_cast<const float4*>(sDelta + qb);
-                    // keep bits of (query qb + e, this thread's key): lane e fetches query qb + e's word of this warp's 32
-                    // keys (the warp's keys share one word: key = k0 + 128 j + 32 quarter + lane), broadcast by shuffle below
-                    uint32_t mword = 0xffffffffu;
-                    if (DROPOUT) {
-                        const int qrow = q0 + qb + lane;
-                        const int word = (k0 + 128 * j + quarter * 32) >> 5;
-                        mword = (qrow < p.Lq && word < p.mask_ld) ? p.mask[(((long long)b * p.H + h) * p.Lq + qrow) * p.mask_ld + word] : 0u;
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {   // 8 queries = one 16-byte chunk of P^T and of dS^T
-                        const float4 la = l4[2 * g], lb = l4[2 * g + 1], da = d4[2 * g], db = d4[2 * g + 1];
-                        const float lv[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-                        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-                        float pe[8], ds[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            pe[e] = ex2(fmaf(__uint_as_float(s[8 * g + e]), sl2, -lv[e]));
-                            float dpe = __uint_as_float(dp[8 * g + e]);
-                            bool kept = true;
-                            if (DROPOUT) {      // d(P o M / (1 - p)) / dP: the dropped entries pass no gradient, the kept ones are scaled
-                                kept = (__shfl_sync(0xffffffffu, mword, 8 * g + e) >> lane) & 1u;
-                                dpe = kept ? dpe * p.keep_scale : 0.f;
-                            }
-                            ds[e] = pe[e] * (dpe - dv[e]);
-                            if (DROPOUT) pe[e] = kept ? pe[e] * p.keep_scale : 0.f;   // P^T as it multiplied V in the forward pass (-> dV)
-                            if (CAUSAL) {
-                                const bool ok = key <= qb + 8 * g + e + coff;
-                                pe[e] = ok ? pe[e] : 0.f;
-                                ds[e] = ok ? ds[e] : 0.f;
-                            }
-                        }
-                        uint4 pw, dw;
-                        pw.x = pack_bf16x2(pe[0], pe[1]); pw.y = pack_bf16x2(pe[2], pe[3]);
-                        pw.z = pack_bf16x2(pe[4], pe[5]); pw.w = pack_bf16x2(pe[6], pe[7]);
-                        dw.x = pack_bf16x2(ds[0], ds[1]); dw.y = pack_bf16x2(ds[2], ds[3]);
-                        dw.z = pack_bf16x2(ds[4], ds[5]); dw.w = pack_bf16x2(ds[6], ds[7]);
-                        if (!rowok) { pw = make_uint4(0, 0, 0, 0); dw = make_uint4(0, 0, 0, 0); }   // masked / unloaded key row
-                        const int c8 = c * 4 + g;
-                        const int off = (c8 >> 3) * 16384 + t * 128 + (((c8 & 7) ^ (t & 7)) << 4);
-                        *reinterpret_cast<uint4*>(sPT + off) = pw;
-                        *reinterpret_cast<uint4*>(sdST + off) = dw;
-                    }
-                }
-                ptx::fence_proxy_async();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(bar_p);
-                if (warp == 0 && it == 0) TSTAMP(10);
-                if (warp == 0 && it == 1) TSTAMP(12);
-                if (i == ni - 1) {   // dV_j and dK_j are complete once this iteration's MMAs retire
-                    ptx::mbar_wait(bar_acc, it & 1);
+            for (int j = 0; j < nj; ++j) {
+                const int key = 128 * j + t;            // block-local key of this thread
+                const bool rowok = key < kvlen;
+                for (int i = 0; i < ni; ++i, ++it) {
+                    const int nq = min(128, w.q_box - 128 * i);
+                    const int nch = (nq + 31) >> 5;
+                    ptx::mbar_wait(bar_s, it & 1);
                     ptx::tc_fence_after();
-                    // half 0 drains dV, half 1 drains dK (64 columns each)
-                    // a single block pair writes the gradients themselves, otherwise this pair's partial sums
-                    // (dk_part / dv_part [n_qb][B*Lk][H*64], added up by attn_reduce_kernel)
-                    const long long krow = (long long)b * p.Lk + k0 + key;
-                    bf16* dst = !part ? (half == 0 ? p.dv + krow * p.lddv + h * 64 : p.dk + krow * p.lddk + h * 64)
-                                      : (half == 0 ? p.dv_part : p.dk_part) + ((long long)qi * p.B * p.Lk + krow) * (p.H * 64) + h * 64;
-                    const float mul = half == 0 ? 1.0f : p.scale;
-                    const uint32_t src = (half == 0 ? t_dv : t_dk) + lane_base;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32(src + hh * 32, v);
+#pragma unroll 1
+                    for (int c = half; c < nch; c += 2) {
+                        uint32_t s[32], dp[32];
+                        ptx::tmem_ld_32x32(t_s + lane_base + c * 32, s);
+                        ptx::tmem_ld_32x32(t_dp + lane_base + c * 32, dp);
                         ptx::tmem_ld_wait();
-                        if (key < Lk_blk) {
+                        const int qb = 128 * i + c * 32;
+                        const float4* l4 = reinterpret_cast<const float4*>(sLse + qb);
+                        const float4* d4 = reinterpret_cast<const float4*>(sDelta + qb);
+                        // keep bits of (query qb + e, this thread's key): lane e fetches query qb + e's word of this warp's 32
+                        // keys (the warp's keys share one word: key = k0 + 128 j + 32 quarter + lane), broadcast by shuffle below
+                        uint32_t mword = 0xffffffffu;
+                        if (DROPOUT) {
+                            const int qrow = q0 + qb + lane;
+                            const int word = (k0 + 128 * j + quarter * 32) >> 5;
+                            mword = (qrow < p.Lq && word < p.mask_ld) ? p.mask[(((long long)b * p.H + h) * p.Lq + qrow) * p.mask_ld + word] : 0u;
+                        }
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                uint4 ov;
-                                ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * mul, __uint_as_float(v[8 * g + 1]) * mul);
-                                ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * mul, __uint_as_float(v[8 * g + 3]) * mul);
-                                ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * mul, __uint_as_float(v[8 * g + 5]) * mul);
-                                ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * mul, __uint_as_float(v[8 * g + 7]) * mul);
-                                *reinterpret_cast<uint4*>(dst + hh * 32 + g * 8) = ov;
+                        for (int g = 0; g < 4; ++g) {   // 8 queries = one 16-byte chunk of P^T and of dS^T
+                            const float4 la = l4[2 * g], lb = l4[2 * g + 1], da = d4[2 * g], db = d4[2 * g + 1];
+                            const float lv[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+                            const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                            float pe[8], ds[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                pe[e] = ex2(fmaf(__uint_as_float(s[8 * g + e]), sl2, -lv[e]));
+                                float dpe = __uint_as_float(dp[8 * g + e]);
+                                bool kept = true;
+                                if (DROPOUT) {      // d(P o M / (1 - p)) / dP: the dropped entries pass no gradient, the kept ones are scaled
+                                    kept = (__shfl_sync(0xffffffffu, mword, 8 * g + e) >> lane) & 1u;
+                                    dpe = kept ? dpe * p.keep_scale : 0.f;
+                                }
+                                ds[e] = pe[e] * (dpe - dv[e]);
+                                if (DROPOUT) pe[e] = kept ? pe[e] * p.keep_scale : 0.f;   // P^T as it multiplied V in the forward pass (-> dV)
+                                if (CAUSAL) {
+                                    const bool ok = key <= qb + 8 * g + e + coff;
+                                    pe[e] = ok ? pe[e] : 0.f;
+                                    ds[e] = ok ? ds[e] : 0.f;
+                                }
                             }
+                            uint4 pw, dw;
+                            pw.x = pack_bf16x2(pe[0], pe[1]); pw.y = pack_bf16x2(pe[2], pe[3]);
+                            pw.z = pack_bf16x2(pe[4], pe[5]); pw.w = pack_bf16x2(pe[6], pe[7]);
+                            dw.x = pack_bf16x2(ds[0], ds[1]); dw.y = pack_bf16x2(ds[2], ds[3]);
+                            dw.z = pack_bf16x2(ds[4], ds[5]); dw.w = pack_bf16x2(ds[6], ds[7]);
+                            if (!rowok) { pw = make_uint4(0, 0, 0, 0); dw = make_uint4(0, 0, 0, 0); }   // masked / unloaded key row
+                            const int c8 = c * 4 + g;
+                            const int off = (c8 >> 3) * 16384 + t * 128 + (((c8 & 7) ^ (t & 7)) << 4);
+                            *reinterpret_cast<uint4*>(sPT + off) = pw;
+                            *reinterpret_cast<uint4*>(sdST + off) = dw;
                         }
                     }
+                    ptx::fence_proxy_async();
                     ptx::tc_fence_before();
-                }
-            }
-        }
-        // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs); each warp drains
-        // 32 of the 64 columns of its rows
-        for (int i = 0; i < ni; ++i) {
-            const int qrow = 128 * i + t;           // block-local query
-            const long long grow = (long long)b * p.Lq + q0 + qrow;
-            bf16* dst = (!part ? p.dq + grow * p.lddq : p.dq_part + ((long long)kj * p.B * p.Lq + grow) * (p.H * 64)) + h * 64 + half * 32;
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
-            ptx::tmem_ld_wait();
-            if (qrow < Lq_blk) {
+                    ptx::mbar_arrive(bar_p);
+                    if (i == ni - 1) {   // dV_j and dK_j are complete once this iteration's MMAs retire
+                        ptx::mbar_wait(bar_acc, it & 1);
+                        ptx::tc_fence_after();
+                        // half 0 drains dV, half 1 drains dK (64 columns each)
+                        // a single block pair writes the gradients themselves, otherwise this pair's partial sums
+                        // (dk_part / dv_part [n_qb][B*Lk][H*64], added up by attn_reduce_kernel)
+                        const long long krow = (long long)b * p.Lk + k0 + key;
+                        bf16* dst = !part ? (half == 0 ? p.dv + krow * p.lddv + h * 64 : p.dk + krow * p.lddk + h * 64)
+                                          : (half == 0 ? p.dv_part : p.dk_part) + ((long long)qi * p.B * p.Lk + krow) * (p.H * 64) + h * 64;
+                        const float mul = half == 0 ? 1.0f : p.scale;
+                        const uint32_t src = (half == 0 ? t_dv : t_dk) + lane_base;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 ov;
-                    ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * p.scale, __uint_as_float(v[8 * g + 1]) * p.scale);
-                    ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * p.scale, __uint_as_float(v[8 * g + 3]) * p.scale);
-                    ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * p.scale, __uint_as_float(v[8 * g + 5]) * p.scale);
-                    ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * p.scale, __uint_as_float(v[8 * g + 7]) * p.scale);
-                    *reinterpret_cast<uint4*>(dst + g * 8) = ov;
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32(src + hh * 32, v);
+                            ptx::tmem_ld_wait();
+                            if (key < Lk_blk) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    uint4 ov;
+                                    ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * mul, __uint_as_float(v[8 * g + 1]) * mul);
+                                    ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * mul, __uint_as_float(v[8 * g + 3]) * mul);
+                                    ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * mul, __uint_as_float(v[8 * g + 5]) * mul);
+                                    ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * mul, __uint_as_float(v[8 * g + 7]) * mul);
+                                    *reinterpret_cast<uint4*>(dst + hh * 32 + g * 8) = ov;
+                                }
+                            }
+                        }
+                        ptx::tc_fence_before();
+                    }
                 }
             }
+            // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs); each warp drains
+            // 32 of the 64 columns of its rows. The next item's first dQ MMA is issued behind its first bar_p, i.e. after
+            // this drain in every softmax thread's program order.
+            for (int i = 0; i < ni; ++i) {
+                const int qrow = 128 * i + t;           // block-local query
+                const long long grow = (long long)b * p.Lq + q0 + qrow;
+                bf16* dst = (!part ? p.dq + grow * p.lddq : p.dq_part + ((long long)kj * p.B * p.Lq + grow) * (p.H * 64)) + h * 64 + half * 32;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
+                ptx::tmem_ld_wait();
+                if (qrow < Lq_blk) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 ov;
+                        ov.x = pack_bf16x2(__uint_as_float(v[8 * g]) * p.scale, __uint_as_float(v[8 * g + 1]) * p.scale);
+                        ov.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * p.scale, __uint_as_float(v[8 * g + 3]) * p.scale);
+                        ov.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * p.scale, __uint_as_float(v[8 * g + 5]) * p.scale);
+                        ov.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * p.scale, __uint_as_float(v[8 * g + 7]) * p.scale);
+                        *reinterpret_cast<uint4*>(dst + g * 8) = ov;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
         }
-        ptx::tc_fence_before();
-        if (warp == 0) TSTAMP(13);
     }
     __syncthreads();
     if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
-        TSTAMP(7);
     }
 }
 
@@ -822,8 +852,15 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid(p.H, p.B, p.n_qb * p.n_kb);
-    PB_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        PB_CUDA(cudaGetDevice(&dev));
+        PB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long items = (long long)p.H * p.B * p.n_qb * p.n_kb;
+    dim3 grid((unsigned)(items < sms ? items : sms));      // persistent: one CTA per SM walks the items
+    PB_CUDA(launch_pdl(kern, grid, dim3(BWD_THREADS), BwdCfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p));
     PB_LAUNCH_CHECK();
     return 0;
 }
