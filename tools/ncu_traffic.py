@@ -1,7 +1,7 @@
 """Per-kernel-family DRAM traffic and device time per step from an ncu launch list taken with
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv ...
 over a window of whole training steps of bench.py (cold-cache, serialised launches: compare SHARES of time, the byte
-counts are per launch). Usage: ncu_traffic.py launches.csv STEPS_IN_WINDOW [out.json]"""
+counts are per launch). Usage: ncu_traffic.py launches.csv STEPS_IN_WINDOW|gemm:LAUNCHES_PER_STEP [out.json]"""
 import collections
 import csv
 import json
@@ -9,7 +9,7 @@ import re
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-steps = float(sys.argv[2])
+steps_arg = sys.argv[2]   # a number, or gemm:<launches per step> to derive it from the window's GEMM launch count
 h = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
 hdr = rows[h]
 ki, mi, ui, vi, idi = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'), hdr.index('Metric Value'), hdr.index('ID')
@@ -46,6 +46,7 @@ for lid, m in launch.items():
     a['ns'] += m.get('gpu__time_duration.sum', 0.0)
     a['read'] += m.get('dram__bytes_read.sum', 0.0)
     a['write'] += m.get('dram__bytes_write.sum', 0.0)
+steps = agg['gemm']['launches'] / float(steps_arg[5:]) if steps_arg.startswith('gemm:') else float(steps_arg)
 tot_ns = sum(a['ns'] for a in agg.values())
 out = {'steps_in_window': steps, 'families': {}}
 print(f'{"family":12s} {"launches/step":>13s} {"ms/step":>9s} {"share":>6s} {"DRAM read MB/step":>18s} {"DRAM write MB/step":>19s}')
