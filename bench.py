@@ -654,10 +654,21 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step, eager_launches:
         for _ in range(3):
             step(pcm_dev, dec_dev)        # replays: every event node is re-recorded
         torch.cuda.synchronize()
+        overhead = event_bracket_overhead(pcm_dev.device) if trainer._graphs else 0.0
+        # pb200::gemm_ln_kernel (Linear + dropout + residual + LayerNorm in one kernel, csrc/gemm_ln.cu) is timed with the GEMMs
+        # but is a kernel of its own: its time also holds the LayerNorm tail, so it gets its own family row and the roofline
+        # of the dominant kernel (pb200::gemm_kernel) is taken over gemm_kernel's launches only; `frac_with_fused_ln` counts
+        # both kernels' time against the Linear FLOPs alone.
+        tags = K_TAGS = K.PROFILE_TAGS[len(K.PROFILE_TAGS) - len(prof):]
+        fused = [(f, s_, e_) for (f, s_, e_), t in zip(prof, tags) if 'fused' in t]
+        prof_all = prof
+        prof = [(f, s_, e_) for (f, s_, e_), t in zip(prof, tags) if 'fused' not in t]
+        tags = [t for t in tags if 'fused' not in t]
         flops = sum(f for f, _, _ in prof)
         ms_raw = sum(s.elapsed_time(e) for _, s, e in prof)
-        overhead = event_bracket_overhead(pcm_dev.device) if trainer._graphs else 0.0
         ms = ms_raw - overhead * len(prof)
+        fused_flops = sum(f for f, _, _ in fused)
+        fused_ms = sum(s.elapsed_time(e) for _, s, e in fused) - overhead * len(fused)
         # ---- per-family table ----
         fam = {}
         for ((tag, e0, e1), work) in other:
@@ -673,6 +684,11 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step, eager_launches:
                 g['work'] += work[1]
         families = {'gemm': {'launches': len(prof), 'ms_per_step': ms, 'achieved': flops / (ms / 1e3) / 1e12, 'unit': 'TFLOP/s',
                              'peak': peak, 'frac': flops / (ms / 1e3) / 1e12 / peak}}
+        if fused:
+            families['linear_ln_fused'] = {'launches': len(fused), 'ms_per_step': fused_ms, 'achieved': fused_flops / (fused_ms / 1e3) / 1e12,
+                                           'unit': 'TFLOP/s', 'peak': peak, 'frac': fused_flops / (fused_ms / 1e3) / 1e12 / peak,
+                                           'note': 'pb200::gemm_ln_kernel: out-projection / fc2 GEMM + dropout + residual + LayerNorm; '
+                                                   'FLOPs of the Linear only, the time also holds the LayerNorm tail'}
         for key, g in fam.items():
             row = {'launches': g['launches'], 'ms_per_step': g['ms']}
             if g['unit'] == 'flop' and g['ms'] > 0:
@@ -684,7 +700,7 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step, eager_launches:
             families[key] = row
         if os.environ.get('BENCH_GEMM_DUMP'):   # per-shape table on stderr
             groups = {}
-            for (f, s_, e_), tag in zip(prof, K.PROFILE_TAGS[len(K.PROFILE_TAGS) - len(prof):]):
+            for (f, s_, e_), tag in zip(prof_all, K_TAGS):
                 g = groups.setdefault(tag, [0, 0.0, f])
                 g[0] += 1
                 g[1] += s_.elapsed_time(e_)
@@ -723,6 +739,8 @@ def step_rooflines(trainer, step, pcm_dev, dec_dev, ms_per_step, eager_launches:
                 'traffic_source': 'profiles/r02_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM '
                                   'launches of one step' if traffic is not None else None,
                 'frac_from_ncu_launch_list': ncu_frac,
+                'frac_with_fused_ln': (flops + fused_flops) / ((ms + fused_ms) / 1e3) / 1e12 / peak,
+                'fused_linear_ln_launches': len(fused), 'fused_linear_ln_ms_per_step': fused_ms,
                 'launches_timed': len(prof), 'gemm_ms_per_step': ms, 'gemm_ms_per_step_raw': ms_raw,
                 'event_bracket_overhead_us': overhead * 1e3, 'achieved_raw': flops / (ms_raw / 1e3) / 1e12,
                 'algorithmic_gflop_per_step': flops / 1e9, 'peak_source': peak_kind,

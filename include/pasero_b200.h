@@ -155,6 +155,16 @@ int pb200_dropout_add_ln_fwd(const void* x, const void* residual, const void* ga
                              void* sum_out, void* y_out, float* mean_out, float* rstd_out, void* keep_out, void* stream);
 /* keep_out (optional, uint8 [M * D / 8]): the dropout keep bits (bit j of byte e / 8 = element e + j kept); passing it
  * back as keep_mask spares the backward kernel the Philox rounds. */
+/* The Linear that produces x fused with the tail above, for d_model = 512 (one kernel: A [M, K] bf16 @ w [512, K]^T + bias ->
+ * dropout -> + residual -> `sum_out` -> LayerNorm -> `y_out`; mean / rstd / keep bits as pb200_dropout_add_ln_fwd writes them).
+ * Replaces nn.Linear + dropout + residual + nn.LayerNorm of a post-norm sub-block (pasero/models/modules.py:737,
+ * transformer.py:1016, 1043-1054, 1073-1086) without x ever reaching HBM. The keep decisions are a counter hash of
+ * (seed, offset + (*offset_base << 12), element), NOT the Philox stream of the unfused kernel: keep_out is required when
+ * p > 0 and is what backward reads. */
+int pb200_linear_dropout_add_ln_fwd(const void* a, const void* w, const void* bias, const void* residual, const void* gamma,
+                                    const void* beta, int64_t M, int64_t K, float eps, float p, uint64_t seed, uint64_t offset,
+                                    const int64_t* offset_base, void* sum_out, void* y_out, float* mean_out, float* rstd_out,
+                                    void* keep_out, void* stream);
 size_t pb200_ln_bwd_workspace_bytes(int64_t M, int64_t D);
 /* backward: dx / dresidual, dgamma, dbeta and (optional) dbias_lin = column sums of dx, i.e. the bias gradient of the
  * Linear whose output was `x` (saves a separate pass over dx). accumulate: bit 0 = add into dgamma/dbeta, bit 1 = add

@@ -64,6 +64,8 @@ PROTOTYPES = {
     'pb200_attention_bwd': (c_int32, [POINTER(AttnParams), _P]),
     'pb200_dropout_add_ln_fwd': (c_int32, [_P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,
                                            _P, _P, _P, _P, _P, _P, _P]),
+    'pb200_linear_dropout_add_ln_fwd': (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_uint64, c_uint64,
+                                                  _P, _P, _P, _P, _P, _P, _P]),
     'pb200_ln_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'pb200_ln_bwd_reduce': (c_int32, [_P, c_int64, c_int64, _P, _P, _P, c_int32, _P]),
     'pb200_dropout_add_ln_bwd': (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_uint64, c_uint64,

@@ -4,8 +4,8 @@
 // zero-pad 400 -> 512, real FFT (a 256-point complex FFT of the even/odd packed frame, 16 lanes per frame, 16 x 16 in
 // registers), power spectrum, 80-bin mel projection, log(max(., FLT_EPSILON)), per-utterance mean / variance
 // normalisation, optionally straight into the zero-padded bf16 layout that the conv subsampler's TMA descriptors read.
-// fbank_kernel_v4 (below) does all of it in ONE persistent launch; fbank_kernel_v2 + cmvn_kernel are last round's
-// two-launch path, kept behind PB200_FBANK=v2 for A/B measurements.
+// fbank_kernel_v4 (below) does the transform in ONE persistent launch; cmvn_layout_kernel, launched behind it with programmatic
+// dependent launch, normalises the (L2-resident) rows and writes the output layouts.
 //
 // The reference has no fbank code (features are pre-extracted, pasero/files.py:103-192); the
 // arithmetic follows torchaudio.compliance.kaldi.fbank (kaldi.py:514-646, _get_window :154-217,
@@ -26,20 +26,11 @@ static constexpr int SHIFT = 160;
 static constexpr int NFFT = 512;
 static constexpr int NC = NFFT / 2;   // 256-point complex FFT
 static constexpr int NMEL = 80;
-static constexpr int FR_PER_CTA = 32;
-static constexpr int FB_WARPS = 8;
-static constexpr int FB_THREADS = FB_WARPS * 32;
-static constexpr int SAMPLES_PER_CTA = (FR_PER_CTA - 1) * SHIFT + WIN;  // 5360
-static constexpr int MAX_MEL_TAPS = 640;
 
 struct FbankTables {
     float window[WIN];
     float2 w256[NC];        // exp(-2 pi i k / 256)
     float2 w512[NC + 1];    // exp(-2 pi i k / 512), k = 0..256
-    int mel_start[NMEL];
-    int mel_len[NMEL];
-    int mel_off[NMEL];
-    float mel_w[MAX_MEL_TAPS];
 };
 
 __device__ FbankTables g_fbank_tables;
@@ -51,12 +42,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 
 
 // ---------------------------------------------------------------------------------------------
-// v2: register-resident FFT. 16 lanes per frame (two frames per warp), 16 complex points per lane.
+// Register-resident FFT: 16 lanes per frame (two frames per warp), 16 complex points per lane.
 //   256-point complex FFT as 16 x 16 (Cooley-Tukey): lane n1 holds z[n1 + 16 n2] and runs a 16-point DFT over n2 in
 //   registers, multiplies by W256^(n1 k2), the 16 x 16 values are transposed between the lanes through a padded
 //   shared-memory tile (conflict free), lane k2 runs the second 16-point DFT over n1 and holds Z[16 k1 + k2].
-//   Shared memory traffic per frame drops from ~250 to ~110 accesses per lane and the strided Stockham stores (8-way
-//   bank conflicts in the first two radix-4 passes of v1) disappear.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -98,156 +87,12 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 
 static constexpr int FB2_TILE = 16 * 17;   // float2 per half-warp: 16 x 16 transpose tile padded to 17, reused for Z[256]
 
-struct FbankSmem2 {
-    alignas(16) float samples[SAMPLES_PER_CTA + 8];
-    alignas(16) float out[FR_PER_CTA][NMEL];
-    alignas(16) float2 tile[FB_WARPS][2][FB2_TILE];
-    alignas(16) float power[FB_WARPS][2][NC + 8];
-    alignas(16) float window[WIN];
-    alignas(16) float2 w256[NC];
-    alignas(16) float2 w512[NC + 1];
-    alignas(16) float mel_w[MAX_MEL_TAPS];
-    int mel_start[NMEL], mel_len[NMEL], mel_off[NMEL];
-};
-
-__global__ void __launch_bounds__(FB_THREADS)
-fbank_kernel_v2(const float* __restrict__ pcm, const long long* __restrict__ sample_off,
-                const long long* __restrict__ frame_off, float* __restrict__ feats, double* __restrict__ stats,
-                float pcm_scale) {
-    extern __shared__ __align__(16) uint8_t fb_smem_raw[];
-    FbankSmem2& s = *reinterpret_cast<FbankSmem2*>(fb_smem_raw);
-    const int b = blockIdx.y;
-    const long long s0 = sample_off[b];
-    const long long f_begin = frame_off[b];
-    const int nframes = (int)(frame_off[b + 1] - f_begin);
-    const int f0 = blockIdx.x * FR_PER_CTA;
-    if (f0 >= nframes) return;
-    const int nf = min(FR_PER_CTA, nframes - f0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int hl = lane & 15, half = lane >> 4;
-
-    const FbankTables& T = g_fbank_tables;
-    for (int i = tid; i < WIN; i += FB_THREADS) s.window[i] = T.window[i];
-    for (int i = tid; i < NC; i += FB_THREADS) s.w256[i] = T.w256[i];
-    for (int i = tid; i <= NC; i += FB_THREADS) s.w512[i] = T.w512[i];
-    for (int i = tid; i < MAX_MEL_TAPS; i += FB_THREADS) s.mel_w[i] = T.mel_w[i];
-    for (int i = tid; i < NMEL; i += FB_THREADS) {
-        s.mel_start[i] = T.mel_start[i]; s.mel_len[i] = T.mel_len[i]; s.mel_off[i] = T.mel_off[i];
-    }
-    const int nsamp = (nf - 1) * SHIFT + WIN;
-    const float* src = pcm + s0 + (long long)f0 * SHIFT;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const int n4 = nsamp >> 2;
-        for (int i = tid; i < n4; i += FB_THREADS) reinterpret_cast<float4*>(s.samples)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        for (int i = (n4 << 2) + tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < nsamp; i += FB_THREADS) s.samples[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    float2* tile = s.tile[warp][half];
-    float* pw = s.power[warp][half];
-    // two frames per warp iteration; frames beyond nf are computed on frame nf - 1 and not stored (keeps the warp converged)
-    for (int fr0 = warp * 2; fr0 < nf; fr0 += FB_WARPS * 2) {
-        const int fr = fr0 + half;
-        const bool live = fr < nf;
-        const float* x = s.samples + (live ? fr : nf - 1) * SHIFT;
-        // DC offset over the 400 samples of the frame
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < WIN / 16; ++i) sum += x[hl + 16 * i] * pcm_scale;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.0f / WIN);
-        // z[n] = y[2n] + i y[2n+1], n = hl + 16 n2 (pre-emphasis 0.97, Povey window, zero-padded beyond 200)
-        float2 v[16];
-#pragma unroll
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const int n = hl + 16 * n2;
-            float2 z = make_float2(0.f, 0.f);
-            if (n < WIN / 2) {
-                const int j = 2 * n;
-                const float xm1 = x[j > 0 ? j - 1 : 0] * pcm_scale - mean;
-                const float x0 = x[j] * pcm_scale - mean;
-                const float x1 = x[j + 1] * pcm_scale - mean;
-                z.x = (x0 - 0.97f * xm1) * s.window[j];
-                z.y = (x1 - 0.97f * x0) * s.window[j + 1];
-            }
-            v[n2] = z;
-        }
-        dft16(v);                                   // A[n1 = hl][k2]
-#pragma unroll
-        for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], s.w256[(hl * k2) & (NC - 1)]);
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) tile[k2 * 17 + hl] = v[k2];   // transpose through the padded tile
-        __syncwarp();
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = tile[hl * 17 + n1];   // lane k2 = hl: A'[n1][k2]
-        __syncwarp();
-        dft16(v);                                   // Z[16 k1 + hl] in v[k1]
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) tile[16 * k1 + hl] = v[k1];
-        __syncwarp();
-        // untangle the packed real transform: X[k] = E[k] + W512^k O[k], power = |X[k]|^2, k = 0..256
-        auto untangle = [&](int k) {
-            const float2 zk = tile[k & (NC - 1)];
-            const float2 zc = tile[(NC - k) & (NC - 1)];
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            const float2 wo = cmul(s.w512[k], o);
-            const float re = e.x + wo.x, im = e.y + wo.y;
-            pw[k] = re * re + im * im;
-        };
-#pragma unroll
-        for (int i = 0; i < 16; ++i) untangle(hl + 16 * i);    // independent iterations: loads overlap
-        if (hl == 0) untangle(NC);
-        __syncwarp();
-        // sparse mel projection + log: 80 bins over the 16 lanes
-        for (int m = hl; m < NMEL; m += 16) {
-            const int st = s.mel_start[m], ln = s.mel_len[m], of = s.mel_off[m];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four partial sums: the tap loop is a latency chain otherwise
-            int i = 0;
-            for (; i + 4 <= ln; i += 4) {
-                a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
-                a1 = fmaf(pw[st + i + 1], s.mel_w[of + i + 1], a1);
-                a2 = fmaf(pw[st + i + 2], s.mel_w[of + i + 2], a2);
-                a3 = fmaf(pw[st + i + 3], s.mel_w[of + i + 3], a3);
-            }
-            for (; i < ln; ++i) a0 = fmaf(pw[st + i], s.mel_w[of + i], a0);
-            const float acc = (a0 + a1) + (a2 + a3);
-            if (live) s.out[fr][m] = logf(fmaxf(acc, 1.1920928955078125e-07f));
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-
-    float* dst = feats + (f_begin + f0) * NMEL;
-    const float* so = &s.out[0][0];
-    const int total = nf * NMEL;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        for (int i = tid; i < (total >> 2); i += FB_THREADS)
-            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(so)[i];
-    } else {
-        for (int i = tid; i < total; i += FB_THREADS) dst[i] = so[i];
-    }
-    if (stats != nullptr && tid < NMEL) {
-        double sm = 0.0, sq = 0.0;
-        for (int fr = 0; fr < nf; ++fr) {
-            const double val = (double)s.out[fr][tid];
-            sm += val; sq += val * val;
-        }
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 0], sm);
-        atomicAdd(&stats[((long long)b * NMEL + tid) * 2 + 1], sq);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // v4 (default): ONE persistent kernel for framing, windowing, FFT, mel, log AND the utterance CMVN.
 //
 //   * grid = 2 CTAs per SM, each walks a contiguous range of 32-frame tiles; the tile's 5 360 PCM samples arrive by
 //     cp.async into a double buffer while the previous tile is being transformed (no register staging);
-//   * 16 lanes per frame as in v2 (256-point complex FFT of the even/odd packed frame as 16 x 16, one padded shared-memory
+//   * 16 lanes per frame (256-point complex FFT of the even/odd packed frame as 16 x 16, one padded shared-memory
 //     transpose), but every per-lane constant lives in registers for the life of the CTA: the lane's 26 window taps
 //     (pre-multiplied by the PCM scale), its 15 inter-stage twiddles, its untangle phase; DC removal and pre-emphasis are
 //     folded into one 3-instruction form  z[j] = w[j] * (x[j] - 0.97 x[j-1] - 0.03 mean)  and the frame is read from shared
@@ -296,6 +141,8 @@ struct Fbank4Smem {
     alignas(16) float stash0[F4_HW][NMEL];     // log-mel rows of the tile's first 16 frames (the other 16 wait in `tile`)
     alignas(16) uint32_t pperm[2][16][4];   // lane -> byte offsets into its power buffer of bins 16 k1 + lane, two per word
 };
+
+static_assert(2 * (sizeof(Fbank4Smem) + 1024) <= 228 * 1024, "two fbank CTAs (256 threads x 128 registers each) must fit one SM's shared memory");
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -623,49 +470,6 @@ cmvn_layout_kernel(float* __restrict__ feats, const long long* __restrict__ fram
     }
 }
 
-// (v2 path) CMVN: x <- (x - mean) / sqrt(max(E[x^2] - mean^2, 1e-10)) with fp64 statistics, in place; optionally
-
-// also writes bf16 features into a zero-padded [B, padded_frames, 80] buffer (front_pad zero frames
-// before each utterance, zeros after its last frame) for the conv subsampler.
-__global__ void cmvn_kernel(float* __restrict__ feats, const long long* __restrict__ frame_off,
-                            const double* __restrict__ stats, int normalize, bf16* __restrict__ out_bf16,
-                            int padded_frames, int front_pad) {
-    const int b = blockIdx.y;
-    const long long f_begin = frame_off[b];
-    const int nframes = (int)(frame_off[b + 1] - f_begin);
-    __shared__ double s_mean[NMEL], s_rstd[NMEL];
-    if (threadIdx.x < NMEL) {
-        double mean = 0.0, rstd = 1.0;
-        if (normalize && nframes > 0) {
-            const double sm = stats[((long long)b * NMEL + threadIdx.x) * 2 + 0];
-            const double sq = stats[((long long)b * NMEL + threadIdx.x) * 2 + 1];
-            mean = sm / nframes;
-            double var = sq / nframes - mean * mean;
-            if (var < 1e-10) var = 1e-10;
-            rstd = 1.0 / sqrt(var);
-        }
-        s_mean[threadIdx.x] = mean; s_rstd[threadIdx.x] = rstd;
-    }
-    __syncthreads();
-    const int rows = out_bf16 ? padded_frames : nframes;
-    const long long total = (long long)rows * NMEL;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int m = (int)(i % NMEL);
-        const long long r = i / NMEL;
-        const long long f = out_bf16 ? r - front_pad : r;
-        float v = 0.f;
-        if (f >= 0 && f < nframes) {
-            float* p = feats + (f_begin + f) * NMEL + m;
-            v = *p;
-            if (normalize) {
-                v = (float)(((double)v - s_mean[m]) * s_rstd[m]);
-                *p = v;
-            }
-        }
-        if (out_bf16) out_bf16[((long long)b * padded_frames + r) * NMEL + m] = f_to_bf16(v);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // host: tables (computed once per process in fp64, mirroring torchaudio's formulas)
@@ -693,29 +497,6 @@ static int upload_fbank_tables() {
     const double fft_bin_width = sample_freq / NFFT;
     const double mel_low = mel_scale(low), mel_high = mel_scale(high);
     const double delta = (mel_high - mel_low) / (NMEL + 1);
-    int off = 0;
-    for (int m = 0; m < NMEL; ++m) {
-        const double left = mel_low + m * delta, center = left + delta, right = center + delta;
-        int start = -1, len = 0;
-        std::vector<float> w;
-        for (int k = 0; k < NC; ++k) {  // torchaudio builds 256 columns and pads the Nyquist column with 0
-            const double mel = mel_scale(fft_bin_width * k);
-            const double up = (mel - left) / (center - left), down = (right - mel) / (right - center);
-            const double v = fmax(0.0, fmin(up, down));
-            if (v > 0.0) {
-                if (start < 0) start = k;
-                while ((int)w.size() < k - start) w.push_back(0.f);
-                w.push_back((float)v);
-            }
-        }
-        if (start < 0) start = 0;
-        len = (int)w.size();
-        PB_CHECK(off + len <= MAX_MEL_TAPS, "mel filter table overflow");
-        t.mel_start[m] = start; t.mel_len[m] = len; t.mel_off[m] = off;
-        for (int i = 0; i < len; ++i) t.mel_w[off + i] = w[i];
-        off += len;
-    }
-    for (int i = off; i < MAX_MEL_TAPS; ++i) t.mel_w[i] = 0.f;
     PB_CUDA(cudaMemcpyToSymbol(g_fbank_tables, &t, sizeof(FbankTables)));
     // v4: the 81 intervals between consecutive filter centres (interval j = [lo + j delta, lo + (j + 1) delta)) partition the
     // FFT bins 1..255; u_k = position of bin k inside its interval = its weight in filter j (1 - u_k in filter j - 1)
@@ -749,8 +530,9 @@ static int upload_fbank_tables() {
         }
     }
     PB_CUDA(cudaMemcpyToSymbol(g_fbank4_tables, &t4, sizeof(Fbank4Tables)));
-    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem2)));
     PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fbank4Smem)));
+    // two CTAs per SM (2 x 108 KB + the per-block reserve): ask for the largest shared-memory carve-out
+    PB_CUDA(cudaFuncSetAttribute(fbank_kernel_v4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (dev < 64) done_for_device[dev] = 1;
     return 0;
 }
@@ -790,8 +572,7 @@ extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets,
     double* stats = reinterpret_cast<double*>(workspace);
     int* done = reinterpret_cast<int*>(stats + (size_t)batch * NMEL * 2);
     const bool second_pass = (cmvn & 1) || feats_bf16_padded;
-    static const bool use_v2 = [] { const char* e = getenv("PB200_FBANK"); return e && !strcmp(e, "v2"); }();
-    if (!use_v2) {
+    {
         const int tiles_per_utt = (max_frames + F4_FRAMES - 1) / F4_FRAMES;
         const long long total_tiles = (long long)batch * tiles_per_utt;
         static int sms = 0;
@@ -817,27 +598,6 @@ extern "C" int pb200_fbank_cmvn(const float* pcm, const int64_t* sample_offsets,
                 PB_LAUNCH_CHECK();
             }
         }
-        return 0;
-    }
-    PB_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * NMEL * 2 * sizeof(double), stream));
-    if (max_frames > 0) {
-        dim3 grid((max_frames + FR_PER_CTA - 1) / FR_PER_CTA, batch);
-        fbank_kernel_v2<<<grid, FB_THREADS, sizeof(FbankSmem2), stream>>>(
-            pcm, reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<const long long*>(frame_offsets),
-            feats, stats, pcm_scale);
-        PB_LAUNCH_CHECK();
-    }
-    if ((cmvn & 1) || feats_bf16_padded) {
-        const int rows = feats_bf16_padded ? padded_frames : max_frames;
-        if (rows > 0) {
-            int bx = (int)(((long long)rows * NMEL + 255) / 256);
-            if (bx > 64) bx = 64;
-            dim3 grid(bx, batch);
-            cmvn_kernel<<<grid, 256, 0, stream>>>(feats, reinterpret_cast<const long long*>(frame_offsets), stats, cmvn & 1,
-                                                 reinterpret_cast<bf16*>(feats_bf16_padded), padded_frames, front_pad);
-            PB_LAUNCH_CHECK();
-        }
-        PB_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * NMEL * 2 * sizeof(double), stream));   // same contract as v4
     }
     return 0;
 }

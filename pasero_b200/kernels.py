@@ -247,6 +247,46 @@ def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Te
     return (y if has_ln else sum_out), sum_out, mean, rstd
 
 
+def linear_ln_supported(M: int, N: int, K: int, residual, gamma) -> bool:
+    """The fused Linear + dropout + residual + LayerNorm kernel (csrc/gemm_ln.cu) holds one output row per TMEM lane: d_model
+    must be exactly 512 (all 512 accumulator columns). It runs one 256 x 512 tile per CTA pair, which pays off when the
+    rows fill the 74 pairs (encoder side); the decoder's 3 072 rows stay on the separate kernels."""
+    return N == 512 and K % 64 == 0 and M >= 8192 and M * N < 2 ** 32 and residual is not None and gamma is not None
+
+
+def linear_dropout_add_ln_fwd(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tensor, gamma: Tensor,
+                              beta: Optional[Tensor], eps: float, p: float, seed: int, offset: int,
+                              keep_out: Optional[Tensor] = None):
+    """(y, sum, mean, rstd) of  sum = residual + dropout(a @ w^T + bias),  y = LayerNorm(sum) * gamma + beta  in ONE kernel:
+    the Linear's output never reaches HBM. keep_out (uint8 [M * 512 / 8], required when p > 0) receives the dropout keep
+    bits in the layout dropout_add_ln_bwd(keep_mask=...) reads."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    assert linear_ln_supported(M, N, K, residual, gamma) and w.shape[1] == K
+    assert a.dtype == BF16 and w.dtype == BF16 and a.is_contiguous() and w.is_contiguous() and residual.is_contiguous()
+    assert p == 0.0 or (keep_out is not None and keep_out.numel() == M * N // 8)
+    dev = a.device
+    y = torch.empty(M, N, dtype=BF16, device=dev)
+    s = torch.empty(M, N, dtype=BF16, device=dev)
+    mean = torch.empty(M, dtype=torch.float32, device=dev)
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    _count(1)
+    args = (a.data_ptr(), w.data_ptr(), ptr(bias), residual.data_ptr(), gamma.data_ptr(), ptr(beta), M, K, eps, p, seed, offset,
+            ptr(RNG_OFFSET_BASE), s.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(keep_out), stream_ptr())
+    if PROFILE is not None:    # timed with the GEMMs (its FLOPs are the Linear's; the LayerNorm tail rides along)
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e0.record()
+        check(lib.pb200_linear_dropout_add_ln_fwd(*args))
+        e1.record()
+        PROFILE.append((2.0 * M * N * K, e0, e1))
+        PROFILE_TAGS.append(f'{M}x{N}x{K} linear+dropout+residual+LN fused')
+    else:
+        check(lib.pb200_linear_dropout_add_ln_fwd(*args))
+    return y, s, mean, rstd
+
+
 @_bracketed(work=_ln_bytes)
 def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[Tensor], gamma: Optional[Tensor],
                        mean, rstd, p: float, seed: int, offset: int, need_dresidual: bool,

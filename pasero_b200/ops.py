@@ -353,11 +353,6 @@ def _attn_dropout(p: float, B: int, H: int, Lq: int, Lk: int, device):
     return float(p), seed, offset, K.attention_mask_buffer(B, H, Lq, Lk, device)
 
 
-def _keep_buffer(x: Tensor, p: float) -> Optional[Tensor]:
-    """uint8 [M * D / 8] buffer for the dropout keep bits (saved for backward instead of re-running Philox there)."""
-    return torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
-
-
 def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=None, need_ln=True, need_lin=True):
     """Shared backward of `LN(residual + dropout(x))`: returns (dx, dresidual, dgamma, dbeta, dlin_bias) with the
     parameter gradients routed through DirectGrads when active (None is returned for those). need_ln / need_lin = False
@@ -393,6 +388,23 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=No
     return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), _ret(dlin, sl)
 
 
+FUSE_LINEAR_LN = True    # tests / tools switch it off to compare the fused kernel with the two-kernel path
+
+
+def _linear_dropout_add_ln(a: Tensor, w: Tensor, b: Optional[Tensor], residual: Tensor, gamma, beta, eps: float, p: float,
+                           seed: int, offset: int):
+    """(out, sum, mean, rstd, keep bits) of LN(residual + dropout(a w^T + b)): one fused kernel when the shape allows
+    (d_model 512, encoder-sized row counts: csrc/gemm_ln.cu), else the GEMM followed by the dropout + residual + LN kernel."""
+    M, N = a.shape[0], w.shape[0]
+    keep = torch.empty(M * N // 8, dtype=torch.uint8, device=a.device) if p > 0 else None
+    if FUSE_LINEAR_LN and K.linear_ln_supported(M, N, a.shape[1], residual, gamma):
+        out, s, mean, rstd = K.linear_dropout_add_ln_fwd(a, w, b, residual, gamma, beta, eps, p, seed, offset, keep_out=keep)
+    else:
+        y = K.linear_fwd(a, w, b)
+        out, s, mean, rstd = K.dropout_add_ln_fwd(y, residual, gamma, beta, eps, p, seed, offset, keep_out=keep)
+    return out, s, mean, rstd, keep
+
+
 class AttnSublayerFn(torch.autograd.Function):
     """Post-norm attention sub-block in one autograd node: LN(x + dropout(MHA(x, key))) (pasero/models/transformer.py
     :1021-1054, 1246-1289). Compared with AttentionFn followed by DropoutAddLNFn, the backward gets the out-projection
@@ -417,10 +429,8 @@ class AttnSublayerFn(torch.autograd.Function):
         drop = _attn_dropout(attn_p, B, H, Lq, Lk, x.device)
         ctx.drop = drop
         o, lse = K.attention_fwd(q2, k2, v2, B, H, Lq, Lk, kv_len, causal, scale, dropout=drop)
-        y = K.linear_fwd(o, out_w, out_b)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
-        keep = _keep_buffer(y, p)
-        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset, keep_out=keep)
+        out, s, mean, rstd, keep = _linear_dropout_add_ln(o, out_w, out_b, x, gamma, beta, eps, p, seed, offset)
         ctx.save_for_backward(x, key_c, in_w, out_w, q2, k2, v2, o, lse, kv_len, s, gamma, mean, rstd, keep)
         ctx.dims = (B, Lq, Lk, H, causal, scale, self_attn, p, seed, offset)
         ctx.params = (in_w, in_b, out_w, out_b, gamma, beta)
@@ -495,10 +505,8 @@ class FFNSublayerFn(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, gamma, beta, p, eps):
         x = _c(x)
         h, bits = _fc1_relu(x, w1, b1)
-        y = K.linear_fwd(h, w2, b2)
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
-        keep = _keep_buffer(y, p)
-        out, s, mean, rstd = K.dropout_add_ln_fwd(y, x, gamma, beta, eps, p, seed, offset, keep_out=keep)
+        out, s, mean, rstd, keep = _linear_dropout_add_ln(h, w2, b2, x, gamma, beta, eps, p, seed, offset)
         ctx.save_for_backward(x, w1, w2, h, s, gamma, mean, rstd, bits, keep)
         ctx.cfg = (p, seed, offset)
         ctx.params = (w1, b1, w2, b2, gamma, beta)

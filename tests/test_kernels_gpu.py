@@ -276,6 +276,90 @@ def test_dropout_add_ln(M, D):
     _close(dl2, 2 * dx.float().sum(0), 0.1 * math.sqrt(M / 100), 3e-2, 'ln dbias_lin accumulate')
 
 
+@pytest.mark.parametrize('M,K,p', [(16000, 512, 0.0), (16000, 2048, 0.1), (8192, 512, 0.1), (8300, 1024, 0.25)])
+def test_linear_dropout_add_ln_fused(M, K, p):
+    """csrc/gemm_ln.cu against the two-kernel path it replaces (GEMM, then dropout + residual + LayerNorm) and against an
+    fp32 torch restatement of pasero/models/transformer.py:1043-1054 applied to the kernel's own keep bits."""
+    k = _k()
+    D = 512
+    a, w = _rand(M, K, seed=1), _rand(D, K, scale=K ** -0.5, seed=2)
+    bias, r = _rand(D, scale=0.1, seed=3), _rand(M, D, seed=4)
+    g, b = (1 + 0.1 * _rand(D, seed=5).float()).to(BF16), _rand(D, scale=0.1, seed=6)
+    keep = torch.zeros(M * D // 8, dtype=torch.uint8, device='cuda') if p > 0 else None
+    y, s, mean, rstd = k.linear_dropout_add_ln_fwd(a, w, bias, r, g, b, 1e-5, p, 99, 5, keep_out=keep)
+    x = k.linear_fwd(a, w, bias)                       # the Linear's bf16 output (same tcgen05 accumulation order)
+    if p > 0:
+        bits = ((keep.view(M, D // 8, 1).int() >> torch.arange(8, device='cuda').view(1, 1, 8)) & 1).view(M, D).bool()
+        frac = bits.float().mean().item()
+        assert abs(frac - (1 - p)) < 2e-3, frac
+        # no structure along rows / columns / neighbours: per-row and per-column keep rates stay within 5 sigma
+        sig_r, sig_c = math.sqrt(p * (1 - p) / D), math.sqrt(p * (1 - p) / M)
+        assert (bits.float().mean(1) - (1 - p)).abs().max().item() < 5.5 * sig_r
+        assert (bits.float().mean(0) - (1 - p)).abs().max().item() < 5.5 * sig_c
+        f = bits.float() - (1 - p)
+        for shift in ((0, 1), (1, 0), (0, 2), (1, 1)):
+            corr = (f[:M - shift[0], :D - shift[1]] * f[shift[0]:, shift[1]:]).mean().item() / (p * (1 - p))
+            assert abs(corr) < 5 / math.sqrt(M * D), (shift, corr)
+        xd = torch.where(bits, (x.float() * (1 / (1 - p))).to(BF16), torch.zeros_like(x))
+    else:
+        xd = x
+    s_ref = (xd.float() + r.float()).to(BF16)
+    assert torch.equal(s, s_ref), (s.float() - s_ref.float()).abs().max().item()
+    ref = F.layer_norm(s_ref.float(), (D,), g.float(), b.float(), 1e-5)
+    _close(y, ref, 2e-2, 1e-2, 'fused ln fwd')
+    mu = s_ref.float().mean(1)
+    var = s_ref.float().var(1, unbiased=False)
+    assert torch.allclose(mean, mu, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(rstd, (var + 1e-5).rsqrt(), rtol=1e-4)
+    if p == 0:      # identical to the unfused kernels up to the last bf16 rounding of y
+        y2, s2, mean2, rstd2 = k.dropout_add_ln_fwd(x, r, g, b, 1e-5, 0.0, 0, 0)
+        assert torch.equal(s2, s)
+        assert (y2.float() - y.float()).abs().max().item() <= 2 ** -6 * max(1.0, y2.float().abs().max().item())
+    else:           # backward consumes the stored bits
+        dy = _rand(M, D, seed=7)
+        dg, db = torch.empty(D, dtype=BF16, device='cuda'), torch.empty(D, dtype=BF16, device='cuda')
+        dx, dres = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, p, 99, 5, True, dg, db, keep_mask=keep)
+        assert torch.equal(dx.float() != 0, bits & (dres.float() != 0))
+
+
+def test_sublayers_fused_linear_ln_matches_two_kernel_path():
+    """The post-norm sub-block nodes (ops.AttnSublayerFn / FFNSublayerFn) at an encoder-sized row count, where their forward
+    ends in the fused Linear + dropout + residual + LayerNorm kernel: outputs and every gradient against the same nodes
+    with the fusion switched off (p = 0: the two paths differ only by the last bf16 rounding of the LayerNorm output)."""
+    from pasero_b200 import ops
+    B, L, D, H, F_ = 36, 250, 512, 8, 2048          # 9 000 rows: not a multiple of the 256-row tile
+    x0 = _rand(B * L, D, seed=1)
+    in_w, in_b = _rand(3 * D, D, scale=D ** -0.5, seed=2), _rand(3 * D, scale=0.1, seed=3)
+    out_w, out_b = _rand(D, D, scale=D ** -0.5, seed=4), _rand(D, scale=0.1, seed=5)
+    w1, b1 = _rand(F_, D, scale=D ** -0.5, seed=6), _rand(F_, scale=0.1, seed=7)
+    w2, b2 = _rand(D, F_, scale=F_ ** -0.5, seed=8), _rand(D, scale=0.1, seed=9)
+    g1, e1 = (1 + 0.1 * _rand(D, seed=10).float()).to(BF16), _rand(D, scale=0.1, seed=11)
+    g2, e2 = (1 + 0.1 * _rand(D, seed=12).float()).to(BF16), _rand(D, scale=0.1, seed=13)
+    kv_len = torch.full((B,), L, dtype=torch.int32, device='cuda')
+    kv_len[::3] = 201
+    dy = _rand(B * L, D, seed=14)
+
+    def run(fuse):
+        ops.FUSE_LINEAR_LN = fuse
+        leaves = [t.clone().requires_grad_(True) for t in (x0, in_w, in_b, out_w, out_b, g1, e1, w1, b1, w2, b2, g2, e2)]
+        x, iw, ib, ow, ob, ga, ea, a1, c1, a2, c2, gb, eb = leaves
+        h = ops.AttnSublayerFn.apply(x, None, iw, ib, ow, ob, ga, ea, kv_len, B, L, L, H, False, 0.125, 0.0, 1e-5)
+        y = ops.FFNSublayerFn.apply(h, a1, c1, a2, c2, gb, eb, 0.0, 1e-5)
+        y.backward(dy)
+        return [y.detach()] + [t.grad for t in leaves]
+
+    try:
+        fused = run(True)
+        plain = run(False)
+    finally:
+        ops.FUSE_LINEAR_LN = True
+    names = ['y', 'dx', 'in_w', 'in_b', 'out_w', 'out_b', 'ln1.g', 'ln1.b', 'fc1.w', 'fc1.b', 'fc2.w', 'fc2.b', 'ln2.g', 'ln2.b']
+    for n, a, b in zip(names, fused, plain):
+        scale = b.float().abs().max().item()
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 0.02 * scale + 1e-6, (n, err, scale)
+
+
 def test_dropout_mask_consistency():
     k = _k()
     M, D, p = 512, 512, 0.1
