@@ -183,6 +183,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--bucket-mb', type=float, default=0.0, help='gradient allreduce bucket size (MB); 0 = the configuration default (25)')
     ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-eager comparator leg (N = 1 only)')
     ap.add_argument('--workload', default='st', choices=['st', 'whisper_small', 'big_adapters'],
                     help="st = the headline (BASELINE configs[1]/[2]); whisper_small / big_adapters = configs[3] / [4], reported separately")
@@ -210,7 +211,7 @@ def main():
     assert world == max(1, args.gpus), f'--gpus {args.gpus} but WORLD_SIZE={world}'
     W = max(3, args.warmup)
 
-    cfg = st_config()
+    cfg = st_config(**({'bucket_bytes': int(args.bucket_mb * 2 ** 20)} if args.bucket_mb > 0 else {}))
     task = SpeechTranslationTask(cfg, Dictionary(tokens=[f't{i}' for i in range(VOCAB - 4)]))
     torch.manual_seed(1234)
     model = build_model(cfg, task)

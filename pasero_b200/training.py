@@ -294,7 +294,9 @@ class Trainer:
         # a communicator of its own for the gradient buckets, on HIGH-PRIORITY streams: the step's persistent GEMM kernels follow
         # each other without a gap (programmatic dependent launch), and a normal-priority NCCL kernel is only scheduled once
         # the whole backward has drained — which is exactly the overlap that is wanted (measured at N = 8: 0.01 ms gained
-        # without, see profiles/README.md)
+        # without, see profiles/README.md). NCCL's own CTA count is left alone: capping it (ncclConfig max_ctas 2 / 4 / 8) made the
+        # N = 8 step slower (10.12 / 9.44 / 9.32 vs 9.19 ms, profiles/r02_n8_sweep.txt) — the exposed part is the LAST bucket's
+        # allreduce, which only gets longer with fewer CTAs.
         group = None
         if self.distributed and os.environ.get('PB200_NCCL_PRIORITY', '1') != '0':
             try:
