@@ -265,7 +265,11 @@ int pb200_grad32_flush(float* acc32, void* grad_bf16, const int64_t* ranges, int
 size_t pb200_grad_sqnorm_workspace_bytes(void);
 int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper, double* stats, void* workspace,
                       size_t workspace_bytes, void* stream);
-int pb200_adam_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
+/* master: NULL (parameters updated in place with the reference's 16-bit rounding points, optimization.Adam with
+ * memory_efficient_fp16) or an fp32 copy of the parameters (MixedPrecisionAdam / FlatFP16Adam): the update is applied to it and
+ * `param` receives its rounded image. hyper[13] = 1 / loss scale, hyper[14] != 0 selects the fp32-gradient semantics in the norm.
+ * pb200_grad_sqnorm also sets stats[5] = 1 when the norm is not finite; pb200_adam_step then changes nothing. */
+int pb200_adam_step(void* param, float* master, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
                     const double* stats, void* stream);
 
 #ifdef __cplusplus

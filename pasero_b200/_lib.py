@@ -94,30 +94,50 @@ PROTOTYPES = {
     'pb200_grad32_flush': (c_int32, [_P, _P, _P, c_int32, c_int64, _P]),
     'pb200_grad_sqnorm_workspace_bytes': (c_size_t, []),
     'pb200_grad_sqnorm': (c_int32, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
-    'pb200_adam_step': (c_int32, [_P, _P, _P, _P, c_int64, _P, _P, _P]),
+    'pb200_adam_step': (c_int32, [_P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
 }
 
 _lib = None
 
 
-def load() -> ctypes.CDLL:
-    """Loads the shared library (once) and installs the prototypes. Raises if it is missing."""
-    global _lib
+class _HalfBuild:
+    """View of the library whose entry points resolve to the float16 build of the kernels (suffix _f16, csrc/f16_symbols.h);
+    the library-wide ones (error string, SM count, ABI version) exist once."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name + '_f16', None) if name not in SHARED else None
+        fn = fn if fn is not None else getattr(self._lib, name)
+        setattr(self, name, fn)
+        return fn
+
+
+SHARED = ('pb200_abi_version', 'pb200_last_error_string', 'pb200_num_sms')
+_half = None
+
+
+def load(dtype=None):
+    """Loads the shared library (once) and installs the prototypes. Raises if it is missing. dtype torch.float16 returns the
+    float16 build's entry points under the same names; anything else (None, bfloat16, float32) the bfloat16 build's."""
+    global _lib, _half
     if _lib is not None:
-        return _lib
+        return _half if dtype == torch.float16 else _lib
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f'{LIB_PATH} is missing: build it with `python -m pasero_b200.build` '
             '(pasero_b200 has no CPU or PyTorch fallback for its CUDA kernels)')
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in PROTOTYPES.items():
-        fn = getattr(lib, name)  # AttributeError here = ABI mismatch between header and library
-        fn.restype = restype
-        fn.argtypes = argtypes
+        for sym in ((name,) if name in SHARED else (name, name + '_f16')):
+            fn = getattr(lib, sym)  # AttributeError here = ABI mismatch between header and library
+            fn.restype = restype
+            fn.argtypes = argtypes
     if lib.pb200_abi_version() != 1:
         raise RuntimeError('libpasero_b200.so ABI version mismatch')
-    _lib = lib
-    return lib
+    _lib, _half = lib, _HalfBuild(lib)
+    return _half if dtype == torch.float16 else _lib
 
 
 def check(rc: int) -> None:

@@ -167,12 +167,17 @@ class TrainingConfig(DistributedConfig):
     max_source_len: Optional[int] = None
     max_target_len: Optional[int] = None
     buffer_size: int = 5000
+    # float16 training (pasero/config.py:1537-1550, training.py:289-306): with `dtype: float16` the loss is scaled dynamically
+    # (GradScaler); memory_efficient_fp16 (default) = Adam on the 16-bit parameters, otherwise an fp32 master copy
+    # (MixedPrecisionAdam, or FlatFP16Adam with flat_fp16 — the same arithmetic on this path's flat arenas)
+    flat_fp16: bool = False
+    memory_efficient_fp16: bool = True
     bucket_bytes: int = 25 * 2 ** 20      # gradient allreduce bucket (torch DDP default: 25 MB)
     cuda_graphs: bool = False              # capture forward+backward+optimizer per batch shape
     model_cfg: TransformerConfig = field(default_factory=TransformerConfig)
     extra: dict = field(default_factory=dict)
 
-    OUT_OF_SCOPE = ('fsdp', 'flat_fp16', 'amp', 'lora_rank', 'moe_', 'checkpoint_activations')
+    OUT_OF_SCOPE = ('fsdp', 'amp', 'lora_rank', 'moe_', 'checkpoint_activations')
 
     # model-config presets selected by `arch` (pasero/config.py: register_model_config). `whisper_base` :2539-2566.
     ARCH_PRESETS = {
@@ -207,8 +212,8 @@ class TrainingConfig(DistributedConfig):
             bad.append(f'tp_size={cfg.tp_size}')
         if bad:
             raise NotImplementedError('options outside the ST data-parallel path: ' + ', '.join(bad))
-        if out.dtype != 'bfloat16':
-            raise NotImplementedError('the sm_100a kernels compute in bfloat16 (dtype: bfloat16)')
+        if out.dtype not in ('bfloat16', 'float16'):
+            raise NotImplementedError('the sm_100a kernels compute in bfloat16 or float16 (dtype: bfloat16 | float16)')
         out.model_cfg = TransformerConfig.adopt(getattr(cfg, 'model_cfg', None) or TransformerConfig(), out.task)
         out.save_interval = out.save_interval or out.valid_interval
         out.max_source_len = out.max_source_len or out.model_cfg.encoder_max_len
@@ -284,8 +289,8 @@ class TrainingConfig(DistributedConfig):
                 raise NotImplementedError(f'option {k}={v!r} selects a subsystem outside the ST data-parallel path')
         if cfg.tp_size != 1:
             raise NotImplementedError('tensor parallelism is out of scope (pasero/training.py:180-183)')
-        if cfg.dtype != 'bfloat16':
-            raise NotImplementedError('the sm_100a kernels compute in bfloat16 (dtype: bfloat16)')
+        if cfg.dtype not in ('bfloat16', 'float16'):
+            raise NotImplementedError('the sm_100a kernels compute in bfloat16 or float16 (dtype: bfloat16 | float16)')
         cfg.model_cfg.finalize(cfg.task)
         cfg.save_interval = cfg.save_interval or cfg.valid_interval
         cfg.max_source_len = cfg.max_source_len or cfg.model_cfg.encoder_max_len

@@ -1,22 +1,34 @@
 // pasero_b200 — shared device/host helpers for the sm_100a kernels.
 #pragma once
+#ifdef PB200_HALF
+#include "f16_symbols.h"   // float16 build: namespace pb200 -> pb200_h, exported names get the suffix _f16
+#endif
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
+// library-wide plumbing shared by the bfloat16 and the float16 build of the kernels (runtime.cu, compiled once)
+namespace pb200_rt {
+void set_error(const char* fmt, ...);
+int num_sms();
+bool pdl_enabled();
+}  // namespace pb200_rt
+
 namespace pb200 {
+using pb200_rt::set_error;
+using pb200_rt::num_sms;
+using pb200_rt::pdl_enabled;
 
 // ---------------------------------------------------------------------------------------------
 // error reporting (C-ABI: every entry point returns 0 or a non-zero code; the text of the last
 // failure on this thread is available from pb200_last_error_string())
 // ---------------------------------------------------------------------------------------------
-void set_error(const char* fmt, ...);
-
 #define PB_CHECK(cond, ...)                                  \
     do {                                                     \
         if (!(cond)) {                                       \
-            ::pb200::set_error(__VA_ARGS__);                 \
+            ::pb200_rt::set_error(__VA_ARGS__);                 \
             return 1;                                        \
         }                                                    \
     } while (0)
@@ -25,7 +37,7 @@ void set_error(const char* fmt, ...);
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \
         if (_e != cudaSuccess) {                                                          \
-            ::pb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+            ::pb200_rt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
                                __FILE__, __LINE__);                                       \
             return 2;                                                                     \
         }                                                                                 \
@@ -35,13 +47,11 @@ void set_error(const char* fmt, ...);
     do {                                                                                  \
         cudaError_t _e = cudaPeekAtLastError();                                           \
         if (_e != cudaSuccess) {                                                          \
-            ::pb200::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),\
+            ::pb200_rt::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),\
                                __FILE__, __LINE__);                                       \
             return 3;                                                                     \
         }                                                                                 \
     } while (0)
-
-int num_sms();
 
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL). Kernels launched through launch_pdl() may be scheduled while the previous
@@ -50,7 +60,6 @@ int num_sms();
 // are visible. RULE: no global-memory access (read OR write) before pdl_wait(). pdl_trigger() lets the successor's
 // CTAs be scheduled as soon as every CTA of this grid has started.  PB200_PDL=0 disables the launch attribute.
 // ---------------------------------------------------------------------------------------------
-bool pdl_enabled();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -72,8 +81,32 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
+// The 16-bit element type of activations, weights and gradients. The kernels are written against the names below; the
+// library holds two builds of them: bfloat16 (the default; `dtype: bfloat16`) and, compiled with -DPB200_HALF, IEEE
+// float16 (`dtype: float16`, pasero/training.py:289-293) — there `bf16` / `bf162` ARE __half / __half2 and every helper
+// rounds to half. Same tensor-core instruction (tcgen05.mma kind::f16), same accumulators, same kernels.
+#ifdef PB200_HALF
+typedef __half bf16;
+typedef __half2 bf162;
+static constexpr uint32_t ELEM_ONE_X2 = 0x3c003c00u;     // two 1.0 values
+__device__ __forceinline__ float bf16_to_f(bf16 x) { return __half2float(x); }
+__device__ __forceinline__ bf16 f_to_bf16(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float round_bf16(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    bf162 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+    bf162 h = *reinterpret_cast<bf162*>(&v);
+    return __half22float2(h);
+}
+// the low / high element of a packed pair as fp32
+__device__ __forceinline__ float elem_lo_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float elem_hi_f(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+#else
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+static constexpr uint32_t ELEM_ONE_X2 = 0x3f803f80u;     // two 1.0 values
 
 __device__ __forceinline__ float bf16_to_f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ bf16 f_to_bf16(float x) { return __float2bfloat16_rn(x); }
@@ -88,6 +121,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     bf162 h = *reinterpret_cast<bf162*>(&v);
     return __bfloat1622float2(h);
 }
+// the low / high element of a packed pair as fp32 (a bfloat16 is the top half of an fp32)
+__device__ __forceinline__ float elem_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float elem_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -20,6 +20,11 @@
 
 namespace pb200 {
 
+#ifdef PB200_HALF
+static constexpr CUtensorMapDataType ELEM_TMAP_TYPE = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+static constexpr CUtensorMapDataType ELEM_TMAP_TYPE = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#endif
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int GEMM_THREADS = 256;
@@ -148,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         else { ptx::tmem_alloc(tmem_ptr, ECfg::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     if (EPI == 7 && warp == 3) {   // bf16 1.0 everywhere; read by the tensor core (async proxy)
-        for (int i = lane; i < ONES_BYTES / 4; i += 32) ones[i] = 0x3f803f80u;
+        for (int i = lane; i < ONES_BYTES / 4; i += 32) ones[i] = ELEM_ONE_X2;
         ptx::fence_proxy_async();
     }
     ptx::tc_fence_before();
@@ -341,7 +346,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             [[maybe_unused]] const long long aux_row = (long long)z * p.c_batch_stride + (long long)row * p.ldc;
             [[maybe_unused]] auto load_aux = [&](int c64, int half) {
                 const bf16* aux = EPI == 3 ? p.relu_mask : p.residual;
-                const uint32_t fill = EPI == 3 ? 0x3f803f80u : 0u;
+                const uint32_t fill = EPI == 3 ? ELEM_ONE_X2 : 0u;
                 const int colh = n0 + c64 * 64 + half * 32;
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
@@ -698,7 +703,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols,
     cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)bs * esz};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : ELEM_TMAP_TYPE, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS,

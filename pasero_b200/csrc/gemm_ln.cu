@@ -271,12 +271,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ 
                                                       __uint_as_float(v[g8 * 8 + 2 * j + 1]) + bb[2 * j + 1]);   // the Linear's bf16 output
                             if (drop) {
                                 const uint32_t k2 = (kbits[half] >> (g8 * 8 + 2 * j)) & 3u;
-                                xw = pack_bf16x2(__uint_as_float(xw << 16) * p.keep_scale, __uint_as_float(xw & 0xffff0000u) * p.keep_scale);
+                                xw = pack_bf16x2(elem_lo_f(xw) * p.keep_scale, elem_hi_f(xw) * p.keep_scale);
                                 xw &= ((k2 & 1u) ? 0x0000ffffu : 0u) | ((k2 & 2u) ? 0xffff0000u : 0u);
                             }
                             const bf162 sum2 = __hadd2(*reinterpret_cast<const bf162*>(&xw), *reinterpret_cast<const bf162*>(&rw[j]));
                             ow[j] = *reinterpret_cast<const uint32_t*>(&sum2);
-                            const float o0 = __uint_as_float(ow[j] << 16), o1 = __uint_as_float(ow[j] & 0xffff0000u);
+                            const float o0 = elem_lo_f(ow[j]), o1 = elem_hi_f(ow[j]);
                             v[g8 * 8 + 2 * j] = __float_as_uint(o0); v[g8 * 8 + 2 * j + 1] = __float_as_uint(o1);
                             s1 += o0 + o1;
                             s2 = fmaf(o0, o0, s2); s2 = fmaf(o1, o1, s2);

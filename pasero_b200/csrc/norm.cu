@@ -139,7 +139,7 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = c * 256 + lane * 8;
-        uint4 gv = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        uint4 gv = make_uint4(ELEM_ONE_X2, ELEM_ONE_X2, ELEM_ONE_X2, ELEM_ONE_X2);
         if (gamma && col < D) gv = __ldg(reinterpret_cast<const uint4*>(gamma + col));
         const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll

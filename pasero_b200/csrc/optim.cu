@@ -10,8 +10,14 @@
 //   hyper (fp32[16]): [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1 - beta1^t
 //                     [6] sqrt(1 - beta2^t)  [7] clip_norm  [8] grad multiplier numerator (dp_size)
 //                     [9] 1 - beta1  [10] 1 - beta2  [11] lr / (1 - beta1^t)  [12] weight_decay * lr
+//                     [13] 1 / loss scale (GradScaler.unscale_, 1 when there is no loss scaling)
+//                     [14] != 0: fp32-gradient semantics (MixedPrecisionAdam / FlatFP16Adam, optimization.py:167-298): the
+//                          16-bit gradients are converted to fp32 BEFORE unscaling / normalising / clipping, so those
+//                          multiplications do not round to 16 bits, and the update is applied to an fp32 master copy
 //                     (derived scalars are computed by the host in fp64, like the reference's Python floats)
 //   stats (fp64[8]) : [2] num_tokens (divisor; <=0 -> 1)   [4] out: sum of squares of the scaled grads
+//                     [5] out: 1 when that sum is not finite (an inf / nan gradient: GradScaler's found_inf) — the Adam
+//                         kernel then leaves parameters and moments untouched (GradScaler.step skips the update)
 #include "common.cuh"
 #include "../../include/pasero_b200.h"
 
@@ -31,6 +37,8 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
     pdl_trigger();
     pdl_wait();
     const float coeff = grad_coeff(hyper, stats);
+    const float inv_scale = hyper[13] != 0.f ? hyper[13] : 1.0f;    // (0 = not set: no loss scaling)
+    const bool f32g = hyper[14] != 0.f;
     float acc = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(grad) + i);
@@ -38,7 +46,14 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_bf16x2(w[j]);
-            const float a = round_bf16(f.x * coeff), b = round_bf16(f.y * coeff);
+            float a, b;
+            if (f32g) {
+                a = f.x * inv_scale * coeff; b = f.y * inv_scale * coeff;
+            } else {
+                a = f.x; b = f.y;
+                if (inv_scale != 1.0f) { a = round_bf16(a * inv_scale); b = round_bf16(b * inv_scale); }
+                a = round_bf16(a * coeff); b = round_bf16(b * coeff);
+            }
             acc += a * a + b * b;
         }
     }
@@ -60,16 +75,20 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
         double t = 0.0;
         for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(partials)[i];
         stats[4] = t;
+        stats[5] = isfinite(t) ? 0.0 : 1.0;
         *ticket = 0;
     }
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __restrict__ exp_avg,
+adam_kernel(bf16* __restrict__ param, float* __restrict__ master, const bf16* __restrict__ grad, float* __restrict__ exp_avg,
             float* __restrict__ exp_avg_sq, long long n8, const float* __restrict__ hyper,
             const double* __restrict__ stats) {
     pdl_trigger();
     pdl_wait();
+    if (stats[5] != 0.0) return;      // an inf / nan gradient was found: the step is skipped (GradScaler.step)
+    const float inv_scale = hyper[13] != 0.f ? hyper[13] : 1.0f;
+    const bool f32g = master != nullptr;
     const float beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3];
     const float bc2_sqrt = hyper[6], clip = hyper[7];
     const float omb1 = hyper[9], omb2 = hyper[10], step_size = hyper[11], wd_lr = hyper[12];
@@ -94,10 +113,22 @@ adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __re
             const float2 pf = unpack_bf16x2(pw[j]);
             g[2 * j] = gf.x; g[2 * j + 1] = gf.y; p[2 * j] = pf.x; p[2 * j + 1] = pf.y;
         }
+        if (f32g) {   // the update works on the fp32 master copy; the 16-bit parameters are its rounded image
+            const float4 q0 = reinterpret_cast<const float4*>(master)[2 * i], q1 = reinterpret_cast<const float4*>(master)[2 * i + 1];
+            p[0] = q0.x; p[1] = q0.y; p[2] = q0.z; p[3] = q0.w; p[4] = q1.x; p[5] = q1.y; p[6] = q1.z; p[7] = q1.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float gj = round_bf16(g[j] * coeff);
-            if (clip > 0.f) gj = round_bf16(gj * clip_coef);
+            float gj;
+            if (f32g) {
+                gj = g[j] * inv_scale * coeff;
+                if (clip > 0.f) gj *= clip_coef;
+            } else {
+                gj = g[j];
+                if (inv_scale != 1.0f) gj = round_bf16(gj * inv_scale);
+                gj = round_bf16(gj * coeff);
+                if (clip > 0.f) gj = round_bf16(gj * clip_coef);
+            }
             m[j] = m[j] * beta1 + gj * omb1;
             v[j] = v[j] * beta2 + gj * gj * omb2;
             const float denom = sqrtf(v[j]) / bc2_sqrt + eps;
@@ -110,6 +141,10 @@ adam_kernel(bf16* __restrict__ param, const bf16* __restrict__ grad, float* __re
         po.x = pack_bf16x2(p[0], p[1]); po.y = pack_bf16x2(p[2], p[3]);
         po.z = pack_bf16x2(p[4], p[5]); po.w = pack_bf16x2(p[6], p[7]);
         reinterpret_cast<uint4*>(param)[i] = po;
+        if (f32g) {
+            reinterpret_cast<float4*>(master)[2 * i] = make_float4(p[0], p[1], p[2], p[3]);
+            reinterpret_cast<float4*>(master)[2 * i + 1] = make_float4(p[4], p[5], p[6], p[7]);
+        }
         reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(m[0], m[1], m[2], m[3]);
         reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(m[4], m[5], m[6], m[7]);
         reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -173,13 +208,13 @@ extern "C" int pb200_grad_sqnorm(const void* grad, int64_t n, const float* hyper
     return 0;
 }
 
-extern "C" int pb200_adam_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+extern "C" int pb200_adam_step(void* param, float* master, const void* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                const float* hyper, const double* stats, void* stream_) {
     if (n == 0) return 0;
     PB_CHECK(n % 8 == 0, "parameter arena length (%lld) must be a multiple of 8", (long long)n);
     long long blocks = (n / 8 + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    PB_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, (bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq,
+    PB_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, (bf16*)param, master, (const bf16*)grad, exp_avg, exp_avg_sq,
                        (long long)(n / 8), hyper, stats));
     PB_LAUNCH_CHECK();
     return 0;

@@ -306,11 +306,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;
     return d;
 }
-// 32-bit instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate.
+// 32-bit instruction descriptor for kind::f16 with the build's 16-bit element type as inputs (format 1 = bfloat16, 0 = float16),
+// fp32 accumulate.
+#ifdef PB200_HALF
+static constexpr uint32_t IDESC_AB_FORMAT = 0u;
+#else
+static constexpr uint32_t IDESC_AB_FORMAT = 1u;
+#endif
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
     return (1u << 4)                        // D format: F32
-           | (1u << 7)                      // A format: BF16
-           | (1u << 10)                     // B format: BF16
+           | (IDESC_AB_FORMAT << 7)         // A format
+           | (IDESC_AB_FORMAT << 10)        // B format
            | ((a_mn_major ? 1u : 0u) << 15) // A major
            | ((b_mn_major ? 1u : 0u) << 16) // B major
            | ((uint32_t)(N >> 3) << 17)     // N / 8

@@ -5,7 +5,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
-namespace pb200 {
+namespace pb200_rt {
 
 static thread_local char g_err[1024] = "";
 
@@ -39,8 +39,8 @@ bool pdl_enabled() {
     return v != 0;
 }
 
-}  // namespace pb200
+}  // namespace pb200_rt
 
 extern "C" int32_t pb200_abi_version(void) { return PB200_ABI_VERSION; }
-extern "C" const char* pb200_last_error_string(void) { return pb200::g_err; }
-extern "C" int32_t pb200_num_sms(void) { return pb200::num_sms(); }
+extern "C" const char* pb200_last_error_string(void) { return pb200_rt::g_err; }
+extern "C" int32_t pb200_num_sms(void) { return pb200_rt::num_sms(); }

@@ -37,14 +37,16 @@ class FbankPlan:
 
 
 def fbank(pcm: Tensor, plan: FbankPlan, cmvn: bool = True, pcm_scale: float = 32768.0,
-          padded_frames: int = 0, front_pad: int = 0, keep_fp32: bool = True):
+          padded_frames: int = 0, front_pad: int = 0, keep_fp32: bool = True, dtype=torch.bfloat16):
     """pcm: fp32 [total_samples] on the GPU (utterances concatenated, samples in [-1, 1)).
-    Returns (features fp32 [total_frames, 80], bf16 [B, padded_frames, 80] or None). keep_fp32=False: only the bf16 padded
-    layout holds the normalised features (what the training step consumes); the fp32 tensor is scratch."""
+    Returns (features fp32 [total_frames, 80], 16-bit [B, padded_frames, 80] or None). keep_fp32=False: only the padded 16-bit
+    layout (`dtype`: bfloat16, or float16 for a `dtype: float16` model) holds the normalised features (what the training step
+    consumes); the fp32 tensor is scratch."""
     if not pcm.is_cuda:
         raise RuntimeError('pasero_b200.frontend.fbank needs the PCM on the GPU (no CPU fallback)')
     return K.fbank_cmvn(pcm, plan.sample_offsets, plan.frame_offsets, plan.batch, plan.max_frames, plan.total_frames,
-                        pcm_scale=pcm_scale, cmvn=cmvn, padded_frames=padded_frames, front_pad=front_pad, keep_fp32=keep_fp32)
+                        pcm_scale=pcm_scale, cmvn=cmvn, padded_frames=padded_frames, front_pad=front_pad, keep_fp32=keep_fp32,
+                        out_dtype=dtype)
 
 
 def fbank_batch(pcm: Tensor, cmvn: bool = True) -> Tensor:
@@ -55,7 +57,7 @@ def fbank_batch(pcm: Tensor, cmvn: bool = True) -> Tensor:
     return feats.view(B, plan.max_frames, NUM_MEL)
 
 
-def collate_features(packed_rows, offsets, padded_rows: int, front_pad: int = 0, device='cuda', stream=None):
+def collate_features(packed_rows, offsets, padded_rows: int, front_pad: int = 0, device='cuda', stream=None, dtype=torch.bfloat16):
     """GPU fast path for pre-extracted features (the reference's NumpyFile -> Task.collate -> move_to_device chain,
     pasero/files.py:164-175, pasero/tasks/task.py:531-571, pasero/utils.py:691-736): `packed_rows` / `offsets` as returned by
     `pasero_b200.task.NumpyFile.pack` (ragged rows back to back in the file's dtype, ideally in a pinned buffer). ONE
@@ -67,4 +69,4 @@ def collate_features(packed_rows, offsets, padded_rows: int, front_pad: int = 0,
     rows_d = rows.to(device, non_blocking=True)
     offs_d = offs.to(device, non_blocking=True)
     B = offs.numel() - 1
-    return K.collate_features(rows_d, offs_d, B, padded_rows, front_pad), (offs_d[1:] - offs_d[:-1])
+    return K.collate_features(rows_d, offs_d, B, padded_rows, front_pad, out_dtype=dtype), (offs_d[1:] - offs_d[:-1])

@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import AttnParams, GemmParams, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+ELEM_DTYPES = (torch.bfloat16, torch.float16)   # the two builds of the kernels (csrc/common.cuh): `dtype: bfloat16 | float16`
 
 # device int64 scalar added (<< 12) to every dropout offset; set by the Trainer when it captures CUDA graphs so that
 # replays draw fresh masks. None -> offsets are used as given.
@@ -88,8 +89,12 @@ def gemm_raw(a_ptr: int, b_ptr: int, c: Tensor, m: int, n: int, k: int, *, lda: 
              bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, relu_mask: Optional[Tensor] = None,
              act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: int = 0, tile_n: int = 0,
              cluster_m: int = 0, relu_bits_out: Optional[Tensor] = None, relu_bits: Optional[Tensor] = None,
-             a_rowsum: Optional[Tensor] = None) -> Tensor:
-    lib = _lib.load()
+             a_rowsum: Optional[Tensor] = None, elem_dtype=None) -> Tensor:
+    """elem_dtype: the operands' 16-bit type (bfloat16 / float16 pick the library build); defaults to C's when C is 16-bit."""
+    if elem_dtype is None:
+        assert c.dtype != torch.float32, 'gemm_raw: an fp32 C does not tell the operands\' 16-bit type: pass elem_dtype'
+        elem_dtype = c.dtype
+    lib = _lib.load(elem_dtype)
     p = GemmParams()
     p.a_rowsum = ptr(a_rowsum)
     p.a, p.b, p.c = a_ptr, b_ptr, c.data_ptr()
@@ -135,16 +140,16 @@ def relu_bits_supported(N: int, bias: Optional[Tensor]) -> bool:
 
 
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0,
-               residual: Optional[Tensor] = None, out_dtype=BF16, tile_n: int = 0, cluster_m: int = 0,
+               residual: Optional[Tensor] = None, out_dtype=None, tile_n: int = 0, cluster_m: int = 0,
                relu_bits_out: Optional[Tensor] = None) -> Tensor:
     """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual). relu_bits_out (int32 [N / 32, M], with act == 1): sign map
     of y for linear_dgrad(..., relu_bits=...)."""
     M, K = x.shape
     N = w.shape[0]
-    assert w.shape[1] == K and x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
-    y = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    assert w.shape[1] == K and x.dtype in ELEM_DTYPES and w.dtype == x.dtype and x.is_contiguous() and w.is_contiguous()
+    y = torch.empty(M, N, dtype=out_dtype or x.dtype, device=x.device)
     return gemm_raw(x.data_ptr(), w.data_ptr(), y, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, act=act,
-                    residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m, relu_bits_out=relu_bits_out)
+                    residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m, relu_bits_out=relu_bits_out, elem_dtype=x.dtype)
 
 
 def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out: Optional[Tensor] = None,
@@ -153,10 +158,10 @@ def linear_dgrad(dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, out:
     the gradient of the skip connection joins the sub-block's input gradient without a separate add kernel)"""
     M, N = dy.shape
     K = w.shape[1]
-    dx = out if out is not None else torch.empty(M, K, dtype=BF16, device=dy.device)
+    dx = out if out is not None else torch.empty(M, K, dtype=dy.dtype, device=dy.device)
     assert residual is None or (residual.shape == dx.shape and residual.is_contiguous())
     return gemm_raw(dy.data_ptr(), w.data_ptr(), dx, M, K, N, lda=N, ldb=K, ldc=K, b_mn_major=True,
-                    relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1, relu_bits=relu_bits)
+                    relu_mask=relu_mask, residual=residual, accumulate=accumulate, split_k=1, relu_bits=relu_bits, elem_dtype=dy.dtype)
 
 
 def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
@@ -165,12 +170,12 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate
     dy, computed inside the same GEMM (one more 16-column MMA per k-step against an all-ones operand)."""
     M, N = dy.shape
     K = x.shape[1]
-    dw = out if out is not None else torch.empty(N, K, dtype=BF16, device=dy.device)
+    dw = out if out is not None else torch.empty(N, K, dtype=dy.dtype, device=dy.device)
     if bias_grad32 is not None:
         assert bias_grad32.dtype == torch.float32 and bias_grad32.numel() == N and bias_grad32.is_contiguous()
         assert dw.dtype == torch.float32 and accumulate, 'fused bias gradient needs the fp32 accumulate path'
     return gemm_raw(dy.data_ptr(), x.data_ptr(), dw, N, K, M, lda=dy.stride(0), ldb=x.stride(0), ldc=dw.stride(0),
-                    a_mn_major=True, b_mn_major=True, accumulate=accumulate, a_rowsum=bias_grad32)
+                    a_mn_major=True, b_mn_major=True, accumulate=accumulate, a_rowsum=bias_grad32, elem_dtype=dy.dtype)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -178,7 +183,7 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate
 # --------------------------------------------------------------------------------------------------
 def _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, backward):
     """Fills the C struct; dropout = None or (p, seed, offset, mask uint32 [B, H, Lq, ceil(Lk / 32)]). Returns (params, keepalive)."""
-    lib = _lib.load()
+    lib = _lib.load(q.dtype)
     p = AttnParams()
     p.q, p.k, p.v, p.o, p.lse, p.kv_len = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), ptr(kv_len)
     p.ldq, p.ldk, p.ldv, p.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
@@ -201,8 +206,8 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: 
                   causal: bool, scale: float, dropout=None):
     """q/k/v: 2-D bf16 views [B*L, >= H*64] with stride(1) == 1 (e.g. column slices of a fused projection).
     dropout: None or (p, seed, offset, mask) with mask = attention_mask_buffer(...) (filled here, read by attention_bwd)."""
-    lib = _lib.load()
-    o = torch.empty(B * Lq, H * 64, dtype=BF16, device=q.device)
+    lib = _lib.load(q.dtype)
+    o = torch.empty(B * Lq, H * 64, dtype=q.dtype, device=q.device)
     lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
     p, ws = _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, False)
     _count(1 if ws is None else 2)
@@ -214,7 +219,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: 
 def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, B: int, H: int, Lq: int,
                   Lk: int, kv_len: Optional[Tensor], causal: bool, scale: float, dq: Tensor, dk: Tensor, dv: Tensor,
                   dropout=None):
-    lib = _lib.load()
+    lib = _lib.load(q.dtype)
     p, ws = _attn_params(q, k, v, o, lse, kv_len, B, H, Lq, Lk, causal, scale, dropout, True)
     p.dout, p.lddo = dout.data_ptr(), dout.stride(0)
     p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -230,13 +235,13 @@ def attention_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse:
 @_bracketed(work=_ln_bytes)
 def dropout_add_ln_fwd(x: Tensor, residual: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
                        eps: float, p: float, seed: int, offset: int, need_sum: bool = True, keep_out: Optional[Tensor] = None):
-    lib = _lib.load()
+    lib = _lib.load(x.dtype)
     M, D = x.shape
     dev = x.device
     has_ln = gamma is not None
     plain = residual is None and p == 0.0
-    sum_out = None if (has_ln and (plain or not need_sum)) else torch.empty(M, D, dtype=BF16, device=dev)
-    y = torch.empty(M, D, dtype=BF16, device=dev) if has_ln else None
+    sum_out = None if (has_ln and (plain or not need_sum)) else torch.empty(M, D, dtype=x.dtype, device=dev)
+    y = torch.empty(M, D, dtype=x.dtype, device=dev) if has_ln else None
     mean = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     rstd = torch.empty(M, dtype=torch.float32, device=dev) if has_ln else None
     _count(1)
@@ -260,15 +265,15 @@ def linear_dropout_add_ln_fwd(a: Tensor, w: Tensor, bias: Optional[Tensor], resi
     """(y, sum, mean, rstd) of  sum = residual + dropout(a @ w^T + bias),  y = LayerNorm(sum) * gamma + beta  in ONE kernel:
     the Linear's output never reaches HBM. keep_out (uint8 [M * 512 / 8], required when p > 0) receives the dropout keep
     bits in the layout dropout_add_ln_bwd(keep_mask=...) reads."""
-    lib = _lib.load()
+    lib = _lib.load(a.dtype)
     M, K = a.shape
     N = w.shape[0]
     assert linear_ln_supported(M, N, K, residual, gamma) and w.shape[1] == K
-    assert a.dtype == BF16 and w.dtype == BF16 and a.is_contiguous() and w.is_contiguous() and residual.is_contiguous()
+    assert a.dtype in ELEM_DTYPES and w.dtype == a.dtype and a.is_contiguous() and w.is_contiguous() and residual.is_contiguous()
     assert p == 0.0 or (keep_out is not None and keep_out.numel() == M * N // 8)
     dev = a.device
-    y = torch.empty(M, N, dtype=BF16, device=dev)
-    s = torch.empty(M, N, dtype=BF16, device=dev)
+    y = torch.empty(M, N, dtype=a.dtype, device=dev)
+    s = torch.empty(M, N, dtype=a.dtype, device=dev)
     mean = torch.empty(M, dtype=torch.float32, device=dev)
     rstd = torch.empty(M, dtype=torch.float32, device=dev)
     _count(1)
@@ -296,11 +301,11 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
     """dbias_lin (bf16 [D], optional) receives the column sums of dx = the bias gradient of the Linear that produced x.
     side_run(fn, *keepalive): when given, the small kernel that reduces the CTA partials into dgamma / dbeta / dbias_lin is
     handed to it (ops.WgradStream.run: another stream) together with its private partials buffer."""
-    lib = _lib.load()
+    lib = _lib.load(dy.dtype)
     M, D = dy.shape
     dev = dy.device
-    dx = torch.empty(M, D, dtype=BF16, device=dev)
-    dres = torch.empty(M, D, dtype=BF16, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
+    dx = torch.empty(M, D, dtype=dy.dtype, device=dev)
+    dres = torch.empty(M, D, dtype=dy.dtype, device=dev) if (need_dresidual and p > 0.0) else (dx if need_dresidual else None)
     need_ws = (gamma is not None and (dgamma is not None or dbeta is not None)) or dbias_lin is not None
     defer = need_ws and side_run is not None
     ws = None
@@ -322,9 +327,9 @@ def dropout_add_ln_bwd(dy: Tensor, dsum_extra: Optional[Tensor], sum_: Optional[
 
 @_bracketed
 def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
-    lib = _lib.load()
+    lib = _lib.load(x.dtype)
     M, N = x.shape
-    out = out if out is not None else torch.empty(N, dtype=BF16, device=x.device)
+    out = out if out is not None else torch.empty(N, dtype=x.dtype, device=x.device)
     ws = _ws(lib.pb200_colsum_workspace_bytes(M, N), x.device)
     _count(2)
     fn = lib.pb200_colsum_f32 if out.dtype == torch.float32 else lib.pb200_colsum_bf16   # fp32: main gradient of a bias
@@ -338,8 +343,8 @@ def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) ->
 @_bracketed
 def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int, D: int, L: int, scale: float,
               p: float, seed: int, offset: int) -> Tensor:
-    lib = _lib.load()
-    out = torch.empty(M, D, dtype=BF16, device=src.device)
+    lib = _lib.load(src.dtype)
+    out = torch.empty(M, D, dtype=src.dtype, device=src.device)
     _count(1)
     check(lib.pb200_embed_fwd(ptr(ids), src.data_ptr(), ptr(pos), M, D, L, scale, p, seed, offset,
                               ptr(RNG_OFFSET_BASE), src.shape[0] if ids is not None else 0, out.data_ptr(), stream_ptr()))
@@ -349,8 +354,8 @@ def embed_fwd(ids: Optional[Tensor], src: Tensor, pos: Optional[Tensor], M: int,
 @_bracketed
 def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p: float, seed: int, offset: int,
               padding_idx: int = -1, dtable: Optional[Tensor] = None) -> Optional[Tensor]:
-    lib = _lib.load()
-    dx = torch.empty(M, D, dtype=BF16, device=dy.device) if ids is None else None
+    lib = _lib.load(dy.dtype)
+    dx = torch.empty(M, D, dtype=dy.dtype, device=dy.device) if ids is None else None
     _count(1)
     check(lib.pb200_embed_bwd(dy.data_ptr(), ptr(ids), M, D, scale, p, seed, offset, ptr(RNG_OFFSET_BASE), padding_idx,
                               dtable.shape[0] if dtable is not None else 0, ptr(dx), ptr(dtable), stream_ptr()))
@@ -359,26 +364,26 @@ def embed_bwd(dy: Tensor, ids: Optional[Tensor], M: int, D: int, scale: float, p
 
 @_bracketed
 def glu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
-    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    out = torch.empty(B, Tp, C, dtype=x.dtype, device=x.device)
     _count(1)
-    check(_lib.load().pb200_glu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    check(_lib.load(x.dtype).pb200_glu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
 
 @_bracketed
 def glu_bwd(dy: Tensor, x: Tensor, M: int, C: int) -> Tensor:
-    din = torch.empty(M, 2 * C, dtype=BF16, device=x.device)
+    din = torch.empty(M, 2 * C, dtype=x.dtype, device=x.device)
     _count(1)
-    check(_lib.load().pb200_glu_bwd(dy.data_ptr(), x.data_ptr(), M, C, din.data_ptr(), stream_ptr()))
+    check(_lib.load(x.dtype).pb200_glu_bwd(dy.data_ptr(), x.data_ptr(), M, C, din.data_ptr(), stream_ptr()))
     return din
 
 
 @_bracketed
 def gelu_fwd(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
     """gelu(x [B*T, C]) written into rows [front_pad, front_pad + T) of a zero-padded [B, Tp, C] tensor."""
-    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    out = torch.empty(B, Tp, C, dtype=x.dtype, device=x.device)
     _count(1)
-    check(_lib.load().pb200_gelu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    check(_lib.load(x.dtype).pb200_gelu_fwd(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
 
@@ -388,7 +393,7 @@ def gelu_bwd(dy: Tensor, pre: Tensor) -> Tensor:
     assert dy.is_contiguous() and pre.is_contiguous() and dy.numel() == pre.numel()
     dx = torch.empty_like(dy)
     _count(1)
-    check(_lib.load().pb200_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
+    check(_lib.load(dy.dtype).pb200_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
     return dx
 
 
@@ -398,35 +403,35 @@ def relu_bwd(dy: Tensor, h: Tensor) -> Tensor:
     assert dy.is_contiguous() and h.is_contiguous() and dy.numel() == h.numel()
     dx = torch.empty_like(dy)
     _count(1)
-    check(_lib.load().pb200_relu_bwd(dy.data_ptr(), h.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
+    check(_lib.load(dy.dtype).pb200_relu_bwd(dy.data_ptr(), h.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
     return dx
 
 
 @_bracketed
 def col2im(dcol: Tensor, B: int, Tin: int, Tout: int, C: int, KW: int, stride: int) -> Tensor:
-    dx = torch.empty(B * Tin, C, dtype=BF16, device=dcol.device)
+    dx = torch.empty(B * Tin, C, dtype=dcol.dtype, device=dcol.device)
     _count(1)
-    check(_lib.load().pb200_col2im(dcol.data_ptr(), B, Tin, Tout, C, KW, stride, dx.data_ptr(), stream_ptr()))
+    check(_lib.load(dcol.dtype).pb200_col2im(dcol.data_ptr(), B, Tin, Tout, C, KW, stride, dx.data_ptr(), stream_ptr()))
     return dx
 
 
 @_bracketed
 def pad_rows(x: Tensor, B: int, T: int, C: int, Tp: int, front_pad: int) -> Tensor:
-    out = torch.empty(B, Tp, C, dtype=BF16, device=x.device)
+    out = torch.empty(B, Tp, C, dtype=x.dtype, device=x.device)
     _count(1)
-    check(_lib.load().pb200_pad_rows(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
+    check(_lib.load(x.dtype).pb200_pad_rows(x.data_ptr(), B, T, C, out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
 
 @_bracketed
-def collate_features(rows: Tensor, offsets: Tensor, B: int, Tp: int, front_pad: int = 0) -> Tensor:
+def collate_features(rows: Tensor, offsets: Tensor, B: int, Tp: int, front_pad: int = 0, out_dtype=BF16) -> Tensor:
     """rows: fp16 / fp32 [total_rows, C] on the device (utterances back to back), offsets int64 [B + 1] (device, in rows).
     Returns bf16 [B, Tp, C]: utterance b at rows [front_pad, front_pad + len_b), zeros elsewhere."""
     assert rows.dtype in (torch.float16, torch.float32) and rows.is_contiguous() and offsets.dtype == torch.int64
     C = rows.shape[1]
-    out = torch.empty(B, Tp, C, dtype=BF16, device=rows.device)
+    out = torch.empty(B, Tp, C, dtype=out_dtype, device=rows.device)
     _count(1)
-    check(_lib.load().pb200_collate_features(rows.data_ptr(), int(rows.dtype == torch.float16), offsets.data_ptr(), B, C,
+    check(_lib.load(out_dtype).pb200_collate_features(rows.data_ptr(), int(rows.dtype == torch.float16), offsets.data_ptr(), B, C,
                                              out.data_ptr(), Tp, front_pad, stream_ptr()))
     return out
 
@@ -434,7 +439,7 @@ def collate_features(rows: Tensor, offsets: Tensor, B: int, Tp: int, front_pad: 
 @_bracketed
 def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
     _count(1)
-    check(_lib.load().pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))
+    check(_lib.load(out.dtype).pb200_f32_to_bf16(src.data_ptr(), src.numel(), out.data_ptr(), int(accumulate), stream_ptr()))
     return out
 
 
@@ -452,7 +457,7 @@ def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smooth
     V = vocab if vocab is not None else logits.shape[1]
     assert V <= logits.shape[1]
     _count(1)
-    check(_lib.load().pb200_ls_ce_fwd_bwd(logits.data_ptr(), target.data_ptr(), target.stride(0), B, T, V,
+    check(_lib.load(logits.dtype).pb200_ls_ce_fwd_bwd(logits.data_ptr(), target.data_ptr(), target.stride(0), B, T, V,
                                           logits.stride(0), padding_idx, label_smoothing, grad_scale, int(write_grad),
                                           stats.data_ptr(), ptr(row_loss), stream_ptr()))
 
@@ -467,7 +472,7 @@ CE_CHUNK_COLS = 8192
 def ce_chunk_stats(logits: Tensor, target: Tensor, c0: int, cols: int, padding_idx: int, row_state: Tensor) -> None:
     B, T = target.shape
     _count(1)
-    check(_lib.load().pb200_ce_chunk_stats(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols,
+    check(_lib.load(logits.dtype).pb200_ce_chunk_stats(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols,
                                            padding_idx, row_state.data_ptr(), stream_ptr()))
 
 
@@ -476,7 +481,7 @@ def ce_chunk_finish(row_state: Tensor, target: Tensor, V: int, padding_idx: int,
     B, T = target.shape
     lse = torch.empty(B * T, dtype=torch.float32, device=row_state.device)
     _count(1)
-    check(_lib.load().pb200_ce_chunk_finish(row_state.data_ptr(), target.data_ptr(), target.stride(0), B, T, V, padding_idx,
+    check(_lib.load(None).pb200_ce_chunk_finish(row_state.data_ptr(), target.data_ptr(), target.stride(0), B, T, V, padding_idx,
                                             label_smoothing, stats.data_ptr(), lse.data_ptr(), stream_ptr()))
     return lse
 
@@ -485,7 +490,7 @@ def ce_chunk_finish(row_state: Tensor, target: Tensor, V: int, padding_idx: int,
 def ce_chunk_grad(logits: Tensor, target: Tensor, c0: int, cols: int, V: int, label_smoothing: float, lse: Tensor) -> None:
     B, T = target.shape
     _count(1)
-    check(_lib.load().pb200_ce_chunk_grad(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols, V,
+    check(_lib.load(logits.dtype).pb200_ce_chunk_grad(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols, V,
                                           label_smoothing, lse.data_ptr(), stream_ptr()))
 
 
@@ -496,13 +501,13 @@ _SQNORM_WS = {}
 def grad32_flush(acc32: Tensor, grad: Tensor, ranges: Tensor, max_len: int) -> None:
     """bf16 gradient arena <- rounded fp32 main gradients over `ranges` (int64 [n, 2], device); zeroes the source."""
     _count(1)
-    check(_lib.load().pb200_grad32_flush(acc32.data_ptr(), grad.data_ptr(), ranges.data_ptr(), ranges.shape[0], max_len,
+    check(_lib.load(grad.dtype).pb200_grad32_flush(acc32.data_ptr(), grad.data_ptr(), ranges.data_ptr(), ranges.shape[0], max_len,
                                          stream_ptr()))
 
 
 @_bracketed
 def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
-    lib = _lib.load()
+    lib = _lib.load(grad.dtype)
     ws = _SQNORM_WS.get(grad.device)
     if ws is None:   # persistent, zero-initialised once (the kernel re-arms its ticket)
         ws = _SQNORM_WS[grad.device] = torch.zeros(lib.pb200_grad_sqnorm_workspace_bytes(), dtype=torch.uint8, device=grad.device)
@@ -512,14 +517,17 @@ def grad_sqnorm(grad: Tensor, hyper: Tensor, stats: Tensor) -> None:
 
 
 @_bracketed
-def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor) -> None:
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, hyper: Tensor, stats: Tensor,
+              master: Optional[Tensor] = None) -> None:
+    """master (fp32, same length): the update goes to it and `param` receives its rounded image (MixedPrecisionAdam /
+    FlatFP16Adam); None: in-place update with the 16-bit rounding points of optimization.Adam."""
     _count(1)
-    check(_lib.load().pb200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+    check(_lib.load(param.dtype).pb200_adam_step(param.data_ptr(), ptr(master), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                       param.numel(), hyper.data_ptr(), stats.data_ptr(), stream_ptr()))
 
 
 def fbank_num_frames(num_samples: int) -> int:
-    return int(_lib.load().pb200_fbank_num_frames(num_samples))
+    return int(_lib.load(None).pb200_fbank_num_frames(num_samples))
 
 
 _FBANK_WS = {}
@@ -528,15 +536,15 @@ _FBANK_WS = {}
 @_bracketed
 def fbank_cmvn(pcm: Tensor, sample_offsets: Tensor, frame_offsets: Tensor, batch: int, max_frames: int,
                total_frames: int, pcm_scale: float = 32768.0, cmvn: bool = True, padded_frames: int = 0,
-               front_pad: int = 0, keep_fp32: bool = True):
+               front_pad: int = 0, keep_fp32: bool = True, out_dtype=BF16):
     """pcm fp32 [total_samples]; offsets int64 [batch+1] on device. Returns (feats fp32 [total_frames, 80],
     bf16 padded [batch, padded_frames, 80] or None). keep_fp32=False (needs the padded output and cmvn): the fp32 rows are
     only the kernel's scratch (raw log-mel), the normalised features exist in the bf16 padded layout alone."""
-    lib = _lib.load()
+    lib = _lib.load(out_dtype)
     dev = pcm.device
     assert pcm.dtype == torch.float32 and pcm.is_contiguous()
     feats = torch.empty(total_frames, 80, dtype=torch.float32, device=dev)
-    padded = torch.empty(batch, padded_frames, 80, dtype=BF16, device=dev) if padded_frames > 0 else None
+    padded = torch.empty(batch, padded_frames, 80, dtype=out_dtype, device=dev) if padded_frames > 0 else None
     # statistics + tile counters: zero on first use, left zeroed by every call (see pb200_fbank_workspace_bytes) -> one
     # persistent buffer per (device, stream, batch), no memset in the step
     key = (dev, stream_ptr(), batch)

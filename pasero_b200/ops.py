@@ -314,11 +314,11 @@ class AttentionFn(torch.autograd.Function):
         if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
-        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=dy.dtype, device=dy.device)
         b32 = _sink32(p_in_b)    # fp32 main gradient of the fused bias: filled by the weight-gradient GEMMs themselves
         kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
-            dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+            dkvq = torch.empty(B * Lq, 3 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
             dquery = K.linear_dgrad(dkvq, in_w)
@@ -329,8 +329,8 @@ class AttentionFn(torch.autograd.Function):
                 K.colsum(dkvq[:, D:], out=(b32 if b32 is not None else d_in_b)[D:], accumulate=acc_b or b32 is not None)
             dkey = None
         else:
-            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
-            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            dq = torch.empty(B * Lq, D, dtype=dy.dtype, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dquery = K.linear_dgrad(dq, in_w[2 * D:])
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
@@ -365,11 +365,11 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=No
         ag = ab = al = False
         if need_ln:
             sg, ag = _sink(p_gamma); sb, ab = _sink(p_beta)
-            dgamma = sg if sg is not None else torch.empty(D, dtype=BF16, device=dy.device)
-            dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
+            dgamma = sg if sg is not None else torch.empty(D, dtype=dy.dtype, device=dy.device)
+            dbeta = sb if sb is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if p_beta is not None else None)
         if need_lin and lin_bias is not None:
             sl, al = _sink(lin_bias)
-            dlin = sl if sl is not None else torch.empty(D, dtype=BF16, device=dy.device)
+            dlin = sl if sl is not None else torch.empty(D, dtype=dy.dtype, device=dy.device)
         # every output is an arena sink (nothing is handed back to autograd): the partials' reduction can leave the chain
         side = WgradStream.run if ((dgamma is None or sg is not None) and (dbeta is None or sb is not None)
                                    and (dlin is None or sl is not None)) else None
@@ -379,9 +379,9 @@ def _ln_bwd(dy, s, gamma, mean, rstd, p, seed, offset, params, lin_bias, keep=No
     sg, ag = _sink(p_gamma)
     sb, ab = _sink(p_beta)
     sl, al = _sink(lin_bias)
-    dgamma = sg if sg is not None else torch.empty(D, dtype=BF16, device=dy.device)
-    dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if p_beta is not None else None)
-    dlin = sl if sl is not None else (torch.empty(D, dtype=BF16, device=dy.device) if lin_bias is not None else None)
+    dgamma = sg if sg is not None else torch.empty(D, dtype=dy.dtype, device=dy.device)
+    dbeta = sb if sb is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if p_beta is not None else None)
+    dlin = sl if sl is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if lin_bias is not None else None)
     side = WgradStream.run if (sg is not None and (dbeta is None or sb is not None) and (dlin is None or sl is not None)) else None
     dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, True, dgamma, dbeta,
                                     accumulate=ag or ab, dbias_lin=dlin, accumulate_lin=al, keep_mask=keep, side_run=side)
@@ -451,12 +451,12 @@ class AttnSublayerFn(torch.autograd.Function):
         _ready(p_out_w, p_out_b)
         if not need[2]:   # frozen projections: only the input gradients
             if self_attn:
-                dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+                dkvq = torch.empty(B * Lq, 3 * D, dtype=dy.dtype, device=dy.device)
                 K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                                 dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
                 return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
-            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
-            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            dq = torch.empty(B * Lq, D, dtype=dy.dtype, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dkey = K.linear_dgrad(dkv, in_w[:2 * D]) if need[1] else None
             return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
@@ -466,11 +466,11 @@ class AttnSublayerFn(torch.autograd.Function):
         if w32 is not None:      # fp32 main gradient: always accumulate, nothing to hand back
             sink_w, acc_w = w32, True
         d_in_w = sink_w if sink_w is not None else torch.empty_like(in_w)
-        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=BF16, device=dy.device)
+        d_in_b = sink_b if sink_b is not None else torch.zeros(3 * D, dtype=dy.dtype, device=dy.device)
         b32 = _sink32(p_in_b)    # fp32 main gradient of the fused bias: filled by the weight-gradient GEMMs themselves
         kb = ctx.key_bias   # False: the k rows of the fused bias are not a parameter of the reference model -> no gradient
         if self_attn:
-            dkvq = torch.empty(B * Lq, 3 * D, dtype=BF16, device=dy.device)
+            dkvq = torch.empty(B * Lq, 3 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                             dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
             dx = K.linear_dgrad(dkvq, in_w, residual=dres)
@@ -481,8 +481,8 @@ class AttnSublayerFn(torch.autograd.Function):
                 K.colsum(dkvq[:, D:], out=(b32 if b32 is not None else d_in_b)[D:], accumulate=acc_b or b32 is not None)
             dkey = None
         else:
-            dq = torch.empty(B * Lq, D, dtype=BF16, device=dy.device)
-            dkv = torch.empty(B * Lk, 2 * D, dtype=BF16, device=dy.device)
+            dq = torch.empty(B * Lq, D, dtype=dy.dtype, device=dy.device)
+            dkv = torch.empty(B * Lk, 2 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dx = K.linear_dgrad(dq, in_w[2 * D:], residual=dres)
             dkey = K.linear_dgrad(dkv, in_w[:2 * D])
@@ -553,8 +553,8 @@ class DropoutAddLNFn(torch.autograd.Function):
         p_gamma, p_beta = ctx.params
         sg, ag = _sink(p_gamma)
         sb, ab = _sink(p_beta)
-        dgamma = sg if sg is not None else (torch.empty(D, dtype=BF16, device=dy.device) if gamma is not None else None)
-        dbeta = sb if sb is not None else (torch.empty(D, dtype=BF16, device=dy.device) if (gamma is not None and has_beta) else None)
+        dgamma = sg if sg is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if gamma is not None else None)
+        dbeta = sb if sb is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if (gamma is not None and has_beta) else None)
         dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, has_res, dgamma, dbeta,
                                         accumulate=ag or ab)
         _ready(p_gamma, p_beta)
@@ -610,7 +610,7 @@ class EmbedFn(torch.autograd.Function):
         dtable32 = torch.zeros(rows, D, dtype=torch.float32, device=dy.device)
         K.embed_bwd(dy, ids_flat, M, D, scale, p, seed, offset, padding_idx, dtable32)
         so, acc = _sink(ctx.table)
-        dtable = so if so is not None else torch.empty(rows, D, dtype=BF16, device=dy.device)
+        dtable = so if so is not None else torch.empty(rows, D, dtype=dy.dtype, device=dy.device)
         K.f32_to_bf16(dtable32, dtable, accumulate=acc)
         if ctx.notify_ready:
             _ready(ctx.table)
@@ -677,9 +677,10 @@ class ConvGLUFn(torch.autograd.Function):
         Tp = xp.shape[1]
         Cout = weight.shape[0]
         Tout = 1 + (Tin + 2 * (KW // 2) - KW) // stride
-        pre = torch.empty(B * Tout, Cout, dtype=BF16, device=xp.device)
+        pre = torch.empty(B * Tout, Cout, dtype=xp.dtype, device=xp.device)
         K.gemm_raw(xp.data_ptr(), weight.data_ptr(), pre, Tout, Cout, KW * Cin, lda=stride * Cin, ldb=KW * Cin, ldc=Cout,
-                   batch=B, a_batch_stride=Tp * Cin, b_batch_stride=0, c_batch_stride=Tout * Cout, bias=bias, split_k=1)
+                   batch=B, a_batch_stride=Tp * Cin, b_batch_stride=0, c_batch_stride=Tout * Cout, bias=bias, split_k=1,
+                   elem_dtype=xp.dtype)
         if act == 'glu':
             out = K.glu_fwd(pre, B, Tout, Cout // 2, out_Tp, out_front_pad)
         else:   # GELU keeps all Cout channels (Whisper-style front end, modules.py:803)
@@ -712,7 +713,7 @@ class ConvGLUFn(torch.autograd.Function):
         fuse_b = b32 is not None and w32 is not None   # bias gradient = row sums of the GEMM's A operand (see _wgrad_bias)
         K.gemm_raw(dpre.data_ptr(), xp.data_ptr(), dw, Cout, KW * Cin, Tout, lda=Cout, ldb=stride * Cin, ldc=KW * Cin, batch=B,
                    a_batch_stride=Tout * Cout, b_batch_stride=Tp * Cin, a_mn_major=True, b_mn_major=True, reduce_batch=True,
-                   accumulate=acc_w, a_rowsum=b32 if fuse_b else None)
+                   accumulate=acc_w, a_rowsum=b32 if fuse_b else None, elem_dtype=dpre.dtype)
         so_b, acc_b = _sink(p_b)
         if b32 is not None:
             db = b32 if fuse_b else K.colsum(dpre, out=b32, accumulate=True)
@@ -722,9 +723,9 @@ class ConvGLUFn(torch.autograd.Function):
         dw, db = _ret(dw, so_w), _ret(db, so_b)
         dxp = None
         if need_input_grad:
-            dcol = torch.empty(B * Tout, KW * Cin, dtype=BF16, device=dout.device)
+            dcol = torch.empty(B * Tout, KW * Cin, dtype=dout.dtype, device=dout.device)
             K.gemm_raw(dpre.data_ptr(), weight.data_ptr(), dcol, B * Tout, KW * Cin, Cout, lda=Cout, ldb=KW * Cin,
-                       ldc=KW * Cin, b_mn_major=True, split_k=1)
+                       ldc=KW * Cin, b_mn_major=True, split_k=1, elem_dtype=dpre.dtype)
             dx = K.col2im(dcol, B, Tin, Tout, Cin, KW, stride)            # [B*Tin, Cin]
             front = KW // 2
             dxp = torch.zeros_like(xp)
@@ -746,6 +747,7 @@ class ProjCEFn(torch.autograd.Function):
     the projection GEMM a second time (+1/3 of the projection FLOPs)."""
 
     unit_loss_grad = False   # Trainer sets this when the loss is the root of backward (grad_output == 1)
+    loss_scale = 1.0         # float16 training: the Trainer's current loss scale, folded into d loss / d logits where it is written
 
     @staticmethod
     def forward(ctx, x, table, target, padding_idx, label_smoothing, stats, vocab=None):
@@ -755,7 +757,11 @@ class ProjCEFn(torch.autograd.Function):
         V = vocab if vocab is not None else table.shape[0]
         ctx.table = table
         before = stats[0].clone()
+        ctx.elem_dtype = x.dtype
         if V >= K.CE_CHUNK_MIN_VOCAB:
+            if ProjCEFn.loss_scale != 1.0:
+                raise NotImplementedError('loss scaling (dtype: float16) is not wired into the chunked projection + cross-entropy '
+                                          f'path (vocabularies >= {K.CE_CHUNK_MIN_VOCAB}); train those in bfloat16')
             ctx.chunked = True
             need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]   # (grad mode is off inside forward: ask autograd)
             dx32, dtable = ProjCEFn._chunked(x, table, target, padding_idx, label_smoothing, stats, V, need_grad)
@@ -763,7 +769,8 @@ class ProjCEFn(torch.autograd.Function):
             return (stats[0] - before).float()
         ctx.chunked = False
         logits = K.linear_fwd(x, table, None)
-        K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True, vocab=vocab)
+        K.ls_ce_fwd_bwd(logits, target, padding_idx, label_smoothing, stats, write_grad=True, vocab=vocab,
+                        grad_scale=ProjCEFn.loss_scale)
         ctx.save_for_backward(x, table, logits)
         return (stats[0] - before).float()
 
@@ -773,14 +780,15 @@ class ProjCEFn(torch.autograd.Function):
         fp32 main-gradient arena). Gradients are those of the summed loss (grad_output == 1); backward rescales otherwise."""
         M, D = x.shape
         cols = K.CE_CHUNK_COLS
-        buf = torch.empty(M, cols, dtype=BF16, device=x.device)
+        buf = torch.empty(M, cols, dtype=x.dtype, device=x.device)
         state = torch.empty(4, M, dtype=torch.float32, device=x.device)
         chunks = [(c0, min(cols, V - c0)) for c0 in range(0, V, cols)]
 
         def project(c0, n):
             # rows [c0, c0 + n8) of the table, n8 = n rounded up to 8 (inside the zero-padded table): logits of this chunk
             n8 = (n + 7) // 8 * 8
-            return K.gemm_raw(x.data_ptr(), table[c0:c0 + n8].data_ptr(), buf, M, n8, D, lda=D, ldb=D, ldc=cols, split_k=1), n8
+            return K.gemm_raw(x.data_ptr(), table[c0:c0 + n8].data_ptr(), buf, M, n8, D, lda=D, ldb=D, ldc=cols, split_k=1,
+                              elem_dtype=x.dtype), n8
         for c0, n in chunks:
             project(c0, n)
             K.ce_chunk_stats(buf, target, c0, n, padding_idx, state)
@@ -796,7 +804,7 @@ class ProjCEFn(torch.autograd.Function):
             g = buf[:, :n8]
             # dx += dlogits_c W_c (fp32 accumulation across the chunks), dW_c = dlogits_c^T x
             K.gemm_raw(g.data_ptr(), table[c0:c0 + n8].data_ptr(), dx32, M, D, n8, lda=cols, ldb=D, ldc=D, b_mn_major=True,
-                       accumulate=True)
+                       accumulate=True, elem_dtype=x.dtype)
             if t32 is not None:
                 K.linear_wgrad(g, x, out=t32[c0:c0 + n8], accumulate=True)
             else:
@@ -815,13 +823,13 @@ class ProjCEFn(torch.autograd.Function):
                     dtable = dtable * dloss.to(dtable.dtype)
                 elif float(dloss) != 1.0:
                     raise RuntimeError('ProjCEFn: the table gradient already sits in the gradient arena; scale the loss instead')
-            return dx32.to(BF16), dtable, None, None, None, None, None
+            return dx32.to(ctx.elem_dtype), dtable, None, None, None, None, None
         x, table, dlogits = ctx.saved_tensors
         dx = K.linear_dgrad(dlogits, table)
         if ProjCEFn.unit_loss_grad:
             dtable = _wgrad(dlogits, x, ctx.table)
         else:
-            dtable = K.linear_wgrad(dlogits, x) * dloss.to(BF16)
+            dtable = K.linear_wgrad(dlogits, x) * dloss.to(x.dtype)
             dx = dx * dloss.to(dx.dtype)
         return dx, dtable, None, None, None, None, None
 

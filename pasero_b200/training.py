@@ -65,9 +65,10 @@ class LRScheduler:
 
 
 class ParamArena:
-    """Flat storage for parameters (bf16), gradients (bf16) and Adam moments (fp32); parameters become views."""
+    """Flat storage for parameters and gradients (the model's 16-bit dtype), Adam moments (fp32) and — `master=True`: float16
+    training with MixedPrecisionAdam / FlatFP16Adam semantics — an fp32 master copy of the parameters; parameters become views."""
 
-    def __init__(self, model: torch.nn.Module, device):
+    def __init__(self, model: torch.nn.Module, device, dtype=BF16, master: bool = False):
         self.params, self.names, self.offsets = [], [], []
         seen = set()
         off = 0
@@ -80,8 +81,8 @@ class ParamArena:
             self.offsets.append(off)
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
-        self.param = torch.zeros(off, dtype=BF16, device=device)
-        self.grad = torch.zeros(off, dtype=BF16, device=device)
+        self.param = torch.zeros(off, dtype=dtype, device=device)
+        self.grad = torch.zeros(off, dtype=dtype, device=device)
         # fp32 main gradients of the GEMM weights (>= 2-D parameters): the weight-gradient GEMMs reduce-add into it, it is
         # rounded into `grad` (and zeroed) once per optimizer step, before the allreduce / the optimizer read `grad`
         self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
@@ -97,6 +98,8 @@ class ParamArena:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        # fp32 master parameters (optimization.py:183-191, 222-233): built from the 16-bit weights, updated by Adam, copied back
+        self.master = self.param.float() if master else None
 
     def view(self, flat: Tensor, i: int) -> Tensor:
         p, o = self.params[i], self.offsets[i]
@@ -268,11 +271,20 @@ class Trainer:
         cfg = TrainingConfig.adopt(cfg)      # ours, or the reference's own TrainingConfig (cli/train.py:287)
         self.cfg, self.task, self.model = cfg, task, model
         self.device = torch.device(device or f'cuda:{torch.cuda.current_device()}')
-        self.dtype = BF16
+        self.dtype = torch.float16 if cfg.dtype == 'float16' else BF16
+        # float16 (pasero/training.py:289-306): dynamic loss scaling (GradScaler: init 2**7, x2 every growth_interval clean
+        # steps, / 2 and a skipped update on an inf / nan gradient); Adam on the 16-bit parameters (memory_efficient_fp16,
+        # the reference's default) or on an fp32 master copy (MixedPrecisionAdam / FlatFP16Adam)
+        self.fp16 = self.dtype == torch.float16
+        self.master_weights = self.fp16 and (cfg.flat_fp16 or not cfg.memory_efficient_fp16)
+        self.loss_scale = 2.0 ** 7 if self.fp16 else 1.0
+        self._growth_tracker = 0
+        self.overflows = 0
         self.distributed = data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dp_size = dist.get_world_size() if self.distributed else 1
         cfg.dp_size = self.dp_size
         self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)
+        self.growth_interval = 2 ** 14 // self.update_freq
         if getattr(model, 'find_unused_parameters', False):
             # `*_adapters_by`: a different subset of the adapters is used from step to step. The reference skips Adam
             # entirely for parameters without a gradient (per-parameter step counters, optimization.py:77-86) and DDP
@@ -285,7 +297,7 @@ class Trainer:
         model.to(self.device)
         from . import reference_param_names
         ref_names = reference_param_names(model)     # before the arena: afterwards every parameter shares one storage
-        self.arena = ParamArena(model, self.device)
+        self.arena = ParamArena(model, self.device, self.dtype, master=self.master_weights)
         self.param_names = list(self.arena.names)
         # the reference's names of the TRAINABLE parameters: optimizer state is keyed by them (pasero/training.py:899-906)
         self.reference_names = [r for n in self.arena.names for r in ref_names[n]]
@@ -350,6 +362,7 @@ class Trainer:
         h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, cfg.adam_eps, cfg.weight_decay
         h[5], h[6], h[7], h[8] = bc1, math.sqrt(bc2), cfg.clip_norm, 1.0
         h[9], h[10], h[11], h[12] = 1 - b1, 1 - b2, lr / bc1, cfg.weight_decay * lr
+        h[13], h[14] = 1.0 / self.loss_scale, float(self.master_weights)
         self.hyper.copy_(h, non_blocking=True)
 
     def move_to_device(self, batch: dict) -> dict:
@@ -364,6 +377,9 @@ class Trainer:
         return out
 
     def _forward_backward(self, batch: dict, after_forward=None):
+        # float16: `scaler.scale(loss).backward()` (training.py:399-408) — the scale enters where the gradient is born, in the
+        # loss kernel that writes d loss / d logits, so every downstream gradient is the scaled one
+        ops.ProjCEFn.loss_scale = self.loss_scale
         loss, logs = self.model(**batch)
         if after_forward is not None:
             after_forward()
@@ -372,11 +388,13 @@ class Trainer:
             loss.backward()
         finally:
             ops.ProjCEFn.unit_loss_grad = False
+            ops.ProjCEFn.loss_scale = 1.0
         return logs
 
     def _optimizer_kernels(self) -> None:
         K.grad_sqnorm(self.arena.grad, self.hyper, self.stats)
-        K.adam_step(self.arena.param, self.arena.grad, self.arena.exp_avg, self.arena.exp_avg_sq, self.hyper, self.stats)
+        K.adam_step(self.arena.param, self.arena.grad, self.arena.exp_avg, self.arena.exp_avg_sq, self.hyper, self.stats,
+                    master=self.arena.master)
 
     # ------------------------------------------------------------------ the step
     def train_step(self, batch_iterator: Iterator[dict]) -> dict:
@@ -427,7 +445,32 @@ class Trainer:
             return {}
         return {'loss': v[0], 'nll_loss': v[1], 'num_tokens': int(v[2]), 'num_lines': int(v[3])}
 
+    def _update_loss_scale(self) -> bool:
+        """GradScaler.update() (torch.amp.GradScaler: growth 2, backoff 0.5) on the found_inf flag the norm kernel left in
+        stats[5]; reading it is float16 training's one host synchronisation per step (the scheduler and the step counter only
+        advance on clean steps, pasero/training.py:489-503). Returns True when the update was skipped."""
+        found_inf = bool(self.stats[5].item() != 0)
+        if found_inf:
+            self.loss_scale *= 0.5
+            self._growth_tracker = 0
+            self.overflows += 1
+            if self.loss_scale < 1e-4:
+                raise FloatingPointError('too many overflows: the loss scaling factor has reached its minimum value, '
+                                         'try lowering the learning rate')
+        else:
+            self._growth_tracker += 1
+            if self._growth_tracker == self.growth_interval:
+                self.loss_scale *= 2.0
+                self._growth_tracker = 0
+        return found_inf
+
     def _finish_step(self) -> dict:
+        if self.fp16 and self._update_loss_scale():      # overflow: nothing was updated, the step does not count
+            host = self._stats_ring[self.steps % len(self._stats_ring)]
+            host.copy_(self.stats, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            return LazyLogs(self, host, event, self.scheduler.get_last_lr()[0], overflow=True)
         self.scheduler.step()
         self.optimizer_steps += 1
         self.steps += 1
@@ -439,14 +482,16 @@ class Trainer:
         return LazyLogs(self, host, event, self.scheduler.get_last_lr()[0])
 
     @staticmethod
-    def read_logs(host: Tensor, event, lr: float) -> dict:
+    def read_logs(host: Tensor, event, lr: float, loss_scale: float = 1.0, overflow: bool = False) -> dict:
         """Synchronises on the step's single deferred D2H copy and returns python numbers."""
         event.synchronize()
         s = host.tolist()
         if s[7] > 0:    # counted by the loss kernel (csrc/loss.cu); the reference's F.cross_entropy raises for these
             raise RuntimeError(f'{int(s[7])} target ids outside [0, vocabulary size) in this step')
         logs = {'loss': s[0] / math.log(2), 'nll_loss': s[1] / math.log(2), 'num_tokens': int(s[2]), 'num_lines': int(s[3]),
-                'gnorm': math.sqrt(max(s[4], 0.0)), 'lr': lr, 'loss_scale': 1.0}
+                'gnorm': math.sqrt(max(s[4], 0.0)) if not overflow else float('inf'), 'lr': lr, 'loss_scale': loss_scale}
+        if overflow:
+            logs['overflow'] = True
         return logs
 
     # ------------------------------------------------------------------ CUDA-graph path
@@ -460,6 +505,8 @@ class Trainer:
         key = key + tuple(sorted((k, v) for k, v in batch.items() if isinstance(v, (int, tuple))))
         # anything in `meta` may select code paths (adapters by language / domain): a graph is only replayed for the same meta
         key = key + tuple(sorted((k, str(v)) for k, v in (batch.get('meta') or {}).items() if k != 'step'))
+        if self.fp16:     # the loss scale is a launch argument of the captured loss kernel: one graph per scale value
+            key = key + (('loss_scale', self.loss_scale),)
         self.model.train()
         # data parallel, NCCL: the allreduces stay outside the graph (capturing them hangs on this stack) but are ordered
         # behind external event nodes of the graph, one per bucket, so they overlap the replayed backward
@@ -571,6 +618,13 @@ class Trainer:
                  'weight_decay': self.cfg.weight_decay, 'amsgrad': False, 'params': names}
         return {'state': state, 'param_groups': [group]}
 
+    def scaler_state_dict(self) -> dict:
+        """torch.amp.GradScaler.state_dict() of the reference's scaler ({} when it is disabled: bfloat16)."""
+        if not self.fp16:
+            return {}
+        return {'scale': self.loss_scale, 'growth_factor': 2.0, 'backoff_factor': 0.5, 'growth_interval': self.growth_interval,
+                '_growth_tracker': self._growth_tracker}
+
     def save(self, model_dir: Optional[str] = None) -> None:
         """model_{steps}.bin / optimizer_{steps}.bin / metrics_{steps}.bin + model_last.bin symlink
         (pasero/training.py:736-780, 878-939)."""
@@ -582,7 +636,7 @@ class Trainer:
         torch.save({'args': args, 'model': self.model_state_dict(), 'steps': self.steps},
                    os.path.join(model_dir, f'model_{self.steps}.bin'))
         torch.save({'args': args, 'optimizer': self.optimizer_state_dict(), 'scheduler': self.scheduler.state_dict(),
-                    'scaler': {}, 'steps': self.steps}, os.path.join(model_dir, f'optimizer_{self.steps}.bin'))
+                    'scaler': self.scaler_state_dict(), 'steps': self.steps}, os.path.join(model_dir, f'optimizer_{self.steps}.bin'))
         torch.save({'args': args, 'metrics': dict(self.metrics) if isinstance(self.metrics, dict) else {},
                     'last_valid': 0, 'best_score': None, 'patience': None, 'steps': self.steps},
                    os.path.join(model_dir, f'metrics_{self.steps}.bin'))
@@ -607,6 +661,11 @@ class Trainer:
             self._load_named_state(self.arena.exp_avg_sq, {k: v['exp_avg_sq'] for k, v in state.items()})
             self.optimizer_steps = next(iter(state.values()))['step'] if state else 0
             self.scheduler.load_state_dict(opt['scheduler'])
+            if self.fp16 and opt.get('scaler'):
+                self.loss_scale = float(opt['scaler']['scale'])
+                self._growth_tracker = int(opt['scaler'].get('_growth_tracker', 0))
+        if self.arena.master is not None:       # the master copy follows the loaded 16-bit weights (build_fp32_params)
+            self.arena.master.copy_(self.arena.param)
 
 
 class DevicePrefetcher:
@@ -678,8 +737,8 @@ class LazyLogs(Mapping):
     The pinned host slot is reused `len(ring)` steps later; reading after that raises instead of returning another
     step's numbers."""
 
-    def __init__(self, trainer: 'Trainer', host: Tensor, event, lr: float):
-        self._src, self._data = (host, event, lr), None
+    def __init__(self, trainer: 'Trainer', host: Tensor, event, lr: float, overflow: bool = False):
+        self._src, self._data = (host, event, lr, trainer.loss_scale, overflow), None
         self._trainer, self._step = trainer, trainer.steps
 
     def _load(self) -> dict:

@@ -224,8 +224,9 @@ class TransformerEncoder(nn.Module):
                                   float(p), S, self.padding_idx, learned, self.embed_positions.shift, True).view(B, S, D)
         else:
             x = encoder_input
-            if x.dtype != BF16:
-                x = x.to(BF16)
+            dt = next(self.parameters()).dtype      # the model's 16-bit type (bfloat16, or float16 with `dtype: float16`)
+            if x.dtype != dt:
+                x = x.to(dt)
             if self.in_linear is not None:
                 if padded_layout is not None:
                     raise NotImplementedError('the fused fbank layout feeds the subsampler directly (no in_linear)')

@@ -282,7 +282,10 @@ def test_config_surface():
     with pytest.raises(NotImplementedError):
         TrainingConfig.from_dict({'dtype': 'bfloat16', 'fsdp': True})
     with pytest.raises(NotImplementedError):
-        TrainingConfig.from_dict({'dtype': 'float16'})
+        TrainingConfig.from_dict({'dtype': 'float32'})
+    # the IWSLT2023 recipe's precision options (examples/IWSLT2023/taq-fr-contrastive-1.yaml:37-38)
+    f16 = TrainingConfig.from_dict({'dtype': 'float16', 'memory_efficient_fp16': False, 'flat_fp16': True})
+    assert (f16.dtype, f16.memory_efficient_fp16, f16.flat_fp16) == ('float16', False, True)
     assert cfg.as_dict()['encoder_layers'] == 12
 
 

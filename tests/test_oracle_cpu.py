@@ -250,3 +250,70 @@ def test_lr_schedule():
     assert abs(oo.lr_at(16000, 1e-3, 4000) - 5e-4) < 1e-15
     assert abs(oo.lr_at(50, 1e-3, 0, max_steps=100) - 5e-4) < 1e-15
     assert oo.lr_at(10 ** 9, 1e-3, 4000, min_lr=1e-5) == 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# float16 training: the oracle's loss scaler and master-copy Adam against torch.amp.GradScaler and the reference's own
+# MixedPrecisionAdam / FlatFP16Adam (imported from the reference tree where it is present)
+# --------------------------------------------------------------------------------------------------
+def test_loss_scaler_matches_torch_grad_scaler():
+    from oracle import optim as oo
+    ours = oo.LossScaler(init_scale=2.0 ** 7, growth_interval=3)
+    ref = torch.amp.GradScaler('cpu', init_scale=2.0 ** 7, growth_interval=3)
+    p = torch.nn.Parameter(torch.ones(4))
+    opt = torch.optim.SGD([p], lr=0.0)
+    pattern = [False, False, True, False, False, False, False, True, True, False, False, False, False, False, False]
+    for found_inf in pattern:
+        ref.scale(torch.zeros(()))          # (initialises the scaler's lazy state, as `scaler.scale(loss)` does)
+        p.grad = torch.full((4,), float('inf') if found_inf else 1.0) * ref.get_scale()
+        ref.unscale_(opt)
+        ref.step(opt)
+        ref.update()
+        ours.update(found_inf)
+        assert ours.scale == ref.get_scale(), (ours.scale, ref.get_scale())
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pasero'), reason='the reference tree is not on this box')
+@pytest.mark.parametrize('flat', [False, True])
+def test_master_copy_adam_matches_reference_mixed_precision_adam(flat):
+    """oracle.optim.fp16_train_step(master=...) against optimization.MixedPrecisionAdam / FlatFP16Adam driven the way
+    Trainer.train_step drives them (pasero/training.py:455-487) on a toy float16 model (CPU)."""
+    from oracle import optim as oo
+    from tests.golden import make_golden as mg
+    mg.import_reference()
+    from pasero import optimization as ro
+    torch.manual_seed(0)
+    w0 = (torch.randn(8, 6) * 0.3).half()
+    b0 = (torch.randn(8) * 0.1).half()
+    xs = [torch.randn(5, 6).half() for _ in range(6)]
+    scale, ntok, lr = 128.0, 5, 3e-3
+
+    def loss_fn(w, b, x):
+        return (torch.tanh(x.float() @ w.float().t() + b.float()) ** 2).sum()
+
+    # reference optimizer
+    rw, rb = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(b0.clone())
+    cls = ro.FlatFP16Adam if flat else ro.MixedPrecisionAdam
+    ropt = cls([rw, rb], lr=lr, betas=(0.9, 0.999), weight_decay=0.0)
+    # oracle
+    sd = {'w': w0.clone().requires_grad_(True), 'b': b0.clone().requires_grad_(True)}
+    master = {k: v.detach().float().clone() for k, v in sd.items()}
+    state, scaler = {}, oo.LossScaler(init_scale=scale, growth_interval=10 ** 9)
+    for step, x in enumerate(xs):
+        ropt.zero_grad()
+        (loss_fn(rw, rb, x) * scale).backward()
+        ropt.fp16_to_fp32()                                   # GradScaler.unscale_ (optimization.py:367-370) ...
+        params = ropt.param_groups[0]['params']
+        for p in params:
+            p.grad.mul_(1.0 / scale)                          # ... then the unscaling itself, on the fp32 copies
+            p.grad.mul_(1.0 / ntok)                           # training.py:462-470
+        ro.clip_grad_norm_(params, 1.0)
+        ropt.step()
+        ropt.fp32_to_fp16()
+
+        def fwd(cfg, sd_, enc, length, dec, x=x):
+            return loss_fn(sd_['w'], sd_['b'], x), {'loss': 0.0, 'nll_loss': 0.0, 'num_tokens': ntok, 'num_lines': 1}
+        hp = dict(lr=lr, warmup=0, min_lr=lr, max_steps=1, clip_norm=1.0)     # constant learning rate
+        oo.fp16_train_step(None, sd, [dict(encoder_input=None, encoder_input_length=None, decoder_input=None)], state, step, hp,
+                           fwd, scaler, master=master)
+        assert torch.equal(sd['w'].detach(), rw.detach()) and torch.equal(sd['b'].detach(), rb.detach()), step

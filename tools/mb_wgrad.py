@@ -32,7 +32,7 @@ for (M, N, K) in [(16000, 2048, 512), (16000, 1536, 512), (16000, 1024, 512), (3
 
             def run():
                 i[0] = (i[0] + 1) % 4
-                k.gemm_raw(dys[i[0]].data_ptr(), xs[i[0]].data_ptr(), g32, N, K, M, lda=N, ldb=K, ldc=K, a_mn_major=True,
+                k.gemm_raw(dys[i[0]].data_ptr(), xs[i[0]].data_ptr(), g32, N, K, M, lda=N, ldb=K, ldc=K, a_mn_major=True, elem_dtype=torch.bfloat16,
                            b_mn_major=True, accumulate=True, split_k=sk, cluster_m=cl, a_rowsum=b32 if fused else None)
             try:
                 t = graph_time(run, n=40)
