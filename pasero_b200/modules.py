@@ -62,18 +62,18 @@ class SinusoidalPositionalEmbedding(nn.Module):
         self.register_buffer('_float_tensor', torch.FloatTensor(1))
         self._cache = None
 
-    def table(self, length: int) -> Tensor:
-        """rows shift .. shift+length-1 as a contiguous [length, D] tensor in the model dtype/device"""
-        assert length + self.shift - 1 < self.weight.size(0), (
-            f'input sequence is too long: {length}, positional embedding size: {self.weight.size(0)}')
+    def table(self, length: int, offset: int = 0) -> Tensor:
+        """rows shift+offset .. shift+offset+length-1 as a contiguous [length, D] tensor in the model dtype/device (`offset`:
+        positions already consumed, incremental decoding — modules.py:449-457)"""
+        assert offset + length + self.shift - 1 < self.weight.size(0), (
+            f'input sequence is too long: {offset + length}, positional embedding size: {self.weight.size(0)}')
         ref = self._float_tensor
         if self._cache is None or self._cache.device != ref.device or self._cache.dtype != ref.dtype:
             self._cache = self.weight.to(ref)     # built in fp32, cast to the model dtype (modules.py:447)
-        return self._cache[self.shift:self.shift + length]
+        return self._cache[self.shift + offset:self.shift + offset + length]
 
     def forward(self, length: int, offset: int = 0) -> Tensor:
-        assert offset == 0, 'incremental decoding offsets are outside the training path'
-        return self.table(length).unsqueeze(0).detach()
+        return self.table(length, offset).unsqueeze(0).detach()
 
 
 class LearnedPositionalEmbedding(nn.Module):
@@ -87,14 +87,13 @@ class LearnedPositionalEmbedding(nn.Module):
         nn.init.normal_(self.weight, mean=0, std=embedding_dim ** -0.5)   # utils.embed_init
         self.weight._pb200_bf16_grad = True   # gradient = batch sum written in bf16 (not a GEMM weight gradient)
 
-    def table(self, length: int) -> Tensor:
-        assert length + self.shift - 1 < self.weight.size(0), (
-            f'input sequence is too long: {length}, positional embedding size: {self.weight.size(0)}')
-        return self.weight[self.shift:self.shift + length]
+    def table(self, length: int, offset: int = 0) -> Tensor:
+        assert offset + length + self.shift - 1 < self.weight.size(0), (
+            f'input sequence is too long: {offset + length}, positional embedding size: {self.weight.size(0)}')
+        return self.weight[self.shift + offset:self.shift + offset + length]
 
     def forward(self, length: int, offset: int = 0) -> Tensor:
-        assert offset == 0, 'incremental decoding offsets are outside the training path'
-        return self.table(length).unsqueeze(0)
+        return self.table(length, offset).unsqueeze(0)
 
 
 def positional_embedding(kind: str, num_embeddings: int, embedding_dim: int, shift: int):

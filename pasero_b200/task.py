@@ -263,6 +263,10 @@ class SpeechTranslationTask:
         return self.dictionary.eos_idx
 
     @property
+    def bos_idx(self) -> int:
+        return self.dictionary.bos_idx
+
+    @property
     def decoder_num_embeddings(self) -> int:
         return len(self.dictionary)
 

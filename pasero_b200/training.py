@@ -445,6 +445,54 @@ class Trainer:
             return {}
         return {'loss': v[0], 'nll_loss': v[1], 'num_tokens': int(v[2]), 'num_lines': int(v[3])}
 
+    @torch.no_grad()
+    def inference_step(self, batch: Optional[dict], **decoding_opts) -> list:
+        """Decodes one validation batch between training steps (pasero/training.py:549-611): the teacher-forcing
+        `decoder_input` is cut back to its prompt (BOS + target tags, `prompt_length`), the encoder runs once and
+        pasero_b200.decoding.search (beam search over the incremental CUDA decoder) produces the hypotheses; the best one per
+        sentence is returned as a dict with 'tokens' (LongTensor on the CPU), 'score', 'normalized_score' and 'idx' (the
+        sample's index in its corpus), plus whatever `task.postprocess` adds when the task has one (detokenisation is the
+        reference task's business: this package's task stops at token ids). Data parallel: every rank decodes its own
+        batch (`batch=None`: nothing to decode) and the lists are gathered on all ranks, like utils.gather_list."""
+        from . import decoding
+        hyps = []
+        if batch is not None:
+            batch = self.move_to_device(dict(batch))
+            meta = dict(batch.pop('meta', None) or {})
+            dec = batch['decoder_input']
+            if 'prompt_length' in batch:       # utils.mask_by_len(..., truncate=True): keep the prompt, pad the rest, cut
+                plen = batch['prompt_length'].to(dec.device)
+                keep = torch.arange(dec.size(1), device=dec.device).unsqueeze(0) < plen.unsqueeze(1)
+                dec = dec.masked_fill(~keep, self.model.padding_idx)[:, :int(plen.max())]
+            else:
+                dec = dec[:, :1]
+            was_training = self.model.training
+            self.model.eval()
+            try:
+                enc_kwargs = {k: v for k, v in batch.items() if k in ('encoder_input', 'encoder_input_length', 'padded_layout')}
+                encoder_out, encoder_mask, _ = self.model.encoder(**enc_kwargs, meta=meta)
+                opts = dict(max_output_len=decoding_opts.pop('max_output_len', self.cfg.max_target_len),
+                            beam_size=decoding_opts.pop('beam_size', 5))
+                opts.update(decoding_opts)
+                output = decoding.search(self.model.decoder, encoder_out, encoder_mask, decoder_input=dec, meta=meta, **opts)
+            finally:
+                self.model.train(was_training)
+            indices = batch.get('indices')
+            for i, nbest in enumerate(output):
+                hyp = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in nbest[0].items()}
+                hyp['score'], hyp['normalized_score'] = float(hyp['score']), float(hyp['normalized_score'])
+                if hasattr(self.task, 'postprocess'):
+                    sample_bin = {k: v[i] for k, v in batch.items() if torch.is_tensor(v)}
+                    sample_bin['meta'] = meta
+                    self.task.postprocess(sample_bin, hyp, detokenize=True)
+                hyp['idx'] = int(indices[i]) if indices is not None else i
+                hyps.append(hyp)
+        if self.distributed:
+            gathered = [None] * self.dp_size
+            dist.all_gather_object(gathered, hyps)
+            hyps = [h for part in gathered for h in part]
+        return hyps
+
     def _update_loss_scale(self) -> bool:
         """GradScaler.update() (torch.amp.GradScaler: growth 2, backoff 0.5) on the found_inf flag the norm kernel left in
         stats[5]; reading it is float16 training's one host synchronisation per step (the scheduler and the step counter only

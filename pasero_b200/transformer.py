@@ -258,6 +258,7 @@ class TransformerDecoder(nn.Module):
     def __init__(self, cfg: TransformerConfig, dist_cfg: DistributedConfig, task=None, embed=None):
         super().__init__()
         self.cfg = cfg
+        self.task = task
         self.padding_idx = task.padding_idx
         self.embed_tokens = embed if embed is not None else modules.Embedding(task.decoder_num_embeddings, cfg.embed_dim,
                                                                               self.padding_idx)
@@ -271,6 +272,19 @@ class TransformerDecoder(nn.Module):
         self.layer_norm = nn.LayerNorm(cfg.embed_dim, eps=cfg.norm_eps) if cfg.decoder_prenorm else None
         self.output_projection = None  # tied (cfg.tied_output_projection)
         self.table_shared_with_encoder = False   # set by Transformer when the encoder embeds tokens with the same table
+
+    # what a search loop asks a decoder (pasero/models/transformer.py: Decoder.bos_idx / eos_idx / max_len)
+    @property
+    def eos_idx(self) -> int:
+        return self.task.eos_idx
+
+    @property
+    def bos_idx(self) -> int:
+        return getattr(self.task, 'bos_idx', self.task.eos_idx)
+
+    @property
+    def max_len(self) -> int:
+        return self.cfg.decoder_max_len
 
     def features(self, encoder_out, encoder_mask, decoder_input, return_layers=(), encoder_lengths=None, meta=None):
         _select_adapters(self.layers, self.cfg.decoder_adapters_by if self.cfg.adapters else (), meta)
@@ -291,9 +305,11 @@ class TransformerDecoder(nn.Module):
 
     def forward(self, encoder_out: Tensor, encoder_mask: Tensor, decoder_input: Tensor, prompt_mask=None, state=None,
                 return_layers=(), meta: dict = {}, encoder_lengths=None, **kwargs):
-        """Returns (logits (B, T, V), layer_outputs)"""
+        """Returns (logits (B, T, V), layer_outputs). `state` (a dict, empty at the first call): incremental decoding —
+        `decoder_input` then holds only the newest tokens and the cached keys / values live in `state` (pasero_b200.decoding)."""
         if state is not None:
-            raise NotImplementedError('incremental decoding is outside the training path')
+            from . import decoding
+            return decoding.incremental_forward(self, encoder_out, encoder_mask, decoder_input, state, encoder_lengths, meta)
         x, layer_outputs = self.features(encoder_out, encoder_mask, decoder_input, return_layers or (), encoder_lengths, meta)
         return self.embed_tokens.projection(x), layer_outputs
 

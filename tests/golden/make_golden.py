@@ -416,6 +416,60 @@ def golden_training_curve(pasero, cfg, task, model, out):
     print('training golden: first', rows[0], 'last', rows[-1])
 
 
+DECODE_CASES = [dict(name='beam5', beam_size=5, max_output_len=12, prompt=False, len_penalty=1.0),
+                dict(name='greedy', beam_size=1, max_output_len=12, prompt=False, len_penalty=1.0),
+                dict(name='beam3_prompt', beam_size=3, max_output_len=9, prompt=True, len_penalty=0.7),
+                dict(name='beam4_short', beam_size=4, max_output_len=3, prompt=False, len_penalty=1.0)]
+
+
+def decode_prompts(batch_size: int) -> torch.Tensor:
+    """BOS (+ forced target tags for some sentences), right-padded: the `decoder_input` a validation batch carries after
+    Trainer.inference_step cut it back to `prompt_length`."""
+    rows = [[synth.BOS, 7, 9], [synth.BOS], [synth.BOS, 11], [synth.BOS, 7, 9]]
+    rows = [rows[i % len(rows)] for i in range(batch_size)]
+    width = max(len(r) for r in rows)
+    return torch.tensor([r + [synth.PAD] * (width - len(r)) for r in rows], dtype=torch.long)
+
+
+def golden_decoding(pasero, cfg, task, model, out):
+    """pasero.decoding.beam_search (the unmodified reference, CPU, fp32) on the tiny ST model and the seeded model batch:
+    tokens, scores and per-position scores of every finished hypothesis, for the cases of DECODE_CASES."""
+    import json
+    from pasero import decoding
+    model.eval()
+    batch = synth.model_batch()
+    with torch.no_grad():
+        enc_out, enc_mask, _ = model.encoder(batch['encoder_input'].clone(), batch['encoder_input_length'])
+        cases = {}
+        for case in DECODE_CASES:
+            # (decoder_input=None would reach EnsembleDecoder.bos_idx, which the reference's wrapper lacks: always pass BOS)
+            dec_in = decode_prompts(enc_out.size(0)) if case['prompt'] else torch.full((enc_out.size(0), 1), synth.BOS, dtype=torch.long)
+            res = decoding.beam_search(model.decoder, enc_out, enc_mask, case['max_output_len'], case['beam_size'], {},
+                                       decoder_input=dec_in, return_scores=True, len_penalty=case['len_penalty'])
+            cases[case['name']] = [[{'tokens': [int(t) for t in h['tokens']], 'score': float(h['score']),
+                                     'normalized_score': float(h['normalized_score']),
+                                     'pos_scores': [float(x) for x in h['pos_scores']]} for h in nbest] for nbest in res]
+            print(case['name'], [[h['tokens'] for h in nbest][:2] for nbest in cases[case['name']]][:2])
+    # the search algorithm alone, on the deterministic stand-in decoder (synth.MockDecoder): hypotheses that end at different
+    # steps, sentences that finish early, forced prompts, the length limit
+    mock = {}
+    for seed in range(4):
+        dec = synth.MockDecoder(seed, max_len=32, eos_slope=0.9 if seed < 3 else 0.05)
+        enc, mask = synth.mock_encoder_out(5, seed)
+        for case in DECODE_CASES:
+            dec_in = decode_prompts(5) if case['prompt'] else torch.full((5, 1), synth.BOS, dtype=torch.long)
+            with torch.no_grad():
+                res = decoding.beam_search(dec, enc, mask, case['max_output_len'], case['beam_size'], {}, decoder_input=dec_in,
+                                           return_scores=True, len_penalty=case['len_penalty'])
+            mock[f"{case['name']}_seed{seed}"] = [[{'tokens': [int(t) for t in h['tokens']], 'score': float(h['score']),
+                                                   'normalized_score': float(h['normalized_score']),
+                                                   'pos_scores': [float(x) for x in h['pos_scores']]} for h in nbest] for nbest in res]
+    print('mock lengths', sorted({len(h['tokens']) for r in mock.values() for nb in r for h in nb}),
+          'nbest sizes', sorted({len(nb) for r in mock.values() for nb in r}))
+    with open(os.path.join(out, 'beam_search.json'), 'w') as f:
+        json.dump({'cases': DECODE_CASES, 'results': cases, 'mock': mock}, f)
+
+
 def numpy_file_features():
     """Seeded utterances of the NumpyFile fixture (float32 in, stored as float16 like examples/*/extract-features.py)."""
     rng = np.random.RandomState(31)
@@ -468,6 +522,14 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'options':      # only the option-name list
         reference_option_names(pasero)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'decode':       # only the beam-search fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            cfg, task, model = make_task_and_model(pasero, tmp)
+            golden_decoding(pasero, cfg, task, model, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'numpyfile':    # only the NumpyFile fixture
         golden_numpy_file(pasero, out)
         return
@@ -508,6 +570,7 @@ def main():
         cfg, task, model = make_task_and_model(pasero, tmp)
         golden_batching(pasero, task, out)
         golden_model(pasero, cfg, task, model, out)
+        golden_decoding(pasero, cfg, task, model, out)
         cfg2, task2, model2 = make_task_and_model(pasero, tmp)
         golden_training_curve(pasero, cfg2, task2, model2, out)
         cfg3, task3, model3 = make_whisper_model(pasero, tmp)

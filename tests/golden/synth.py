@@ -397,3 +397,50 @@ def sized_batch(seed: int, frames, dec_lens, vocab: int, text: bool = False) -> 
     return {'encoder_input': x, 'encoder_input_length': torch.tensor(frames), 'decoder_input': dec, 'prompt_mask': pm,
             'prompt_length': torch.ones(B, dtype=torch.int64), 'indices': torch.arange(B),
             'meta': {'source_lang': 'de', 'target_lang': 'en'}}
+
+
+# --------------------------------------------------------------------------------------------------
+# decoding: a deterministic stand-in decoder with the reference's call signature, for pinning the SEARCH algorithm (the model's
+# incremental forward is pinned separately): next-token scores are a seeded function of the last two tokens, the prefix length
+# and a per-sentence key read from the encoder output; EOS gets likelier with length, so hypotheses finish at different steps.
+# --------------------------------------------------------------------------------------------------
+MOCK_VOCAB = 40
+
+
+class MockDecoder(torch.nn.Module):
+    padding_idx, eos_idx, bos_idx = PAD, EOS, BOS
+
+    def __init__(self, seed: int = 0, max_len: int = 32, eos_slope: float = 0.9):
+        super().__init__()
+        rng = np.random.RandomState(100 + seed)
+        self.a = torch.from_numpy(rng.randn(MOCK_VOCAB, MOCK_VOCAB).astype(np.float32) * 1.5)
+        self.b = torch.from_numpy(rng.randn(MOCK_VOCAB, MOCK_VOCAB).astype(np.float32))
+        self.c = torch.from_numpy(rng.randn(MOCK_VOCAB).astype(np.float32))
+        self._max_len, self.eos_slope = max_len, eos_slope
+
+    @property
+    def max_len(self) -> int:
+        return self._max_len
+
+    def forward(self, encoder_out, encoder_mask, decoder_input, state=None, meta=None, return_layers=(), **kwargs):
+        prefix = decoder_input if not state or 'prefix' not in state else torch.cat([state['prefix'], decoder_input], dim=1)
+        if state is not None:
+            state['prefix'] = prefix
+        T = decoder_input.size(1)
+        key = encoder_out[:, 0, 0].float()
+        rows = []
+        for t in range(prefix.size(1) - T, prefix.size(1)):
+            last = prefix[:, t].clamp(min=0)
+            prev = prefix[:, t - 1].clamp(min=0) if t > 0 else last
+            logits = self.a[last] + 0.7 * self.b[prev] + key.unsqueeze(1) * self.c.unsqueeze(0)
+            logits[:, self.eos_idx] += self.eos_slope * (t - 2)
+            logits[:, self.padding_idx] = -20.0
+            rows.append(logits)
+        return torch.stack(rows, dim=1), {}
+
+
+def mock_encoder_out(batch_size: int, seed: int = 0):
+    """(encoder_out (B, 3, 4), encoder_mask (B, 3)): only entry [b, 0, 0], the sentence key, matters to MockDecoder."""
+    rng = np.random.RandomState(200 + seed)
+    enc = torch.from_numpy(rng.randn(batch_size, 3, 4).astype(np.float32))
+    return enc, torch.zeros(batch_size, 3, dtype=torch.bool)
