@@ -183,6 +183,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--dtype', default='bfloat16', choices=['bfloat16', 'float16'],
+                    help='float16: the same step with loss scaling and FlatFP16Adam (fp32 master weights); reported next to the bf16 headline')
     ap.add_argument('--bucket-mb', type=float, default=0.0, help='gradient allreduce bucket size (MB); 0 = the configuration default (25)')
     ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-eager comparator leg (N = 1 only)')
     ap.add_argument('--workload', default='st', choices=['st', 'whisper_small', 'big_adapters'],
@@ -211,7 +213,11 @@ def main():
     assert world == max(1, args.gpus), f'--gpus {args.gpus} but WORLD_SIZE={world}'
     W = max(3, args.warmup)
 
-    cfg = st_config(**({'bucket_bytes': int(args.bucket_mb * 2 ** 20)} if args.bucket_mb > 0 else {}))
+    extra_cfg = {'bucket_bytes': int(args.bucket_mb * 2 ** 20)} if args.bucket_mb > 0 else {}
+    if args.dtype == 'float16':
+        extra_cfg.update(dtype='float16', memory_efficient_fp16=False, flat_fp16=True)
+    cfg = st_config(**extra_cfg)
+    elem_dtype = torch.float16 if args.dtype == 'float16' else torch.bfloat16
     task = SpeechTranslationTask(cfg, Dictionary(tokens=[f't{i}' for i in range(VOCAB - 4)]))
     torch.manual_seed(1234)
     model = build_model(cfg, task)
@@ -229,7 +235,7 @@ def main():
     use_graph = not args.no_graph
 
     def step(pcm_flat, dec):
-        _, padded = frontend.fbank(pcm_flat, plan, cmvn=True, padded_frames=rows, front_pad=front, keep_fp32=False)
+        _, padded = frontend.fbank(pcm_flat, plan, cmvn=True, padded_frames=rows, front_pad=front, keep_fp32=False, dtype=elem_dtype)
         batch = {'encoder_input': padded, 'encoder_input_length': plan.frames_tensor, 'decoder_input': dec,
                  'padded_layout': (F,), 'meta': {}}
         if use_graph:
@@ -314,8 +320,8 @@ def main():
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-            'data': 'synthetic', 'config': workload_config(world),
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.dtype == 'bfloat16' else 'f16', 'data': 'synthetic', 'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches * args.steps if launches else None, 'clocks': clock_info, 'roofline': roofline,
             'cpu_baseline': cpu, 'fbank': fbank, 'families': families, 'gpu_eager': eager,

@@ -180,9 +180,17 @@ class TrainingConfig(DistributedConfig):
     OUT_OF_SCOPE = ('fsdp', 'amp', 'lora_rank', 'moe_', 'checkpoint_activations')
 
     # model-config presets selected by `arch` (pasero/config.py: register_model_config). `whisper_base` :2539-2566.
+    _BIG = dict(embed_dim=1024, encoder_ffn_dim=4096, decoder_ffn_dim=4096, encoder_attention_heads=16, decoder_attention_heads=16)
+    _NLLB_1B3 = dict(_BIG, encoder_layers=24, decoder_layers=24, encoder_ffn_dim=8192, decoder_ffn_dim=8192, encoder_prenorm=True,
+                     decoder_prenorm=True)
     ARCH_PRESETS = {
         'transformer': {},
         'adapter_transformer': dict(adapters=True),
+        # pasero/config.py:2183-2188 (BASELINE config 5) and :2229-2240, 2499-2501 (the IWSLT2023 recipe's NLLB 1.3B body)
+        'transformer_big': dict(_BIG),
+        'adapter_transformer_big': dict(_BIG, adapters=True),
+        'nllb_1b3': dict(_NLLB_1B3),
+        'adapter_nllb_1b3': dict(_NLLB_1B3, adapters=True),
         'whisper_base': dict(encoder_layers=6, decoder_layers=6, embed_dim=512, encoder_ffn_dim=2048, decoder_ffn_dim=2048,
                              encoder_attention_heads=8, decoder_attention_heads=8, encoder_prenorm=True, decoder_prenorm=True,
                              activation_fn='gelu', encoder_positional_encoding='learned', decoder_positional_encoding='learned',

@@ -18,6 +18,8 @@
 //   stats (fp64[8]) : [2] num_tokens (divisor; <=0 -> 1)   [4] out: sum of squares of the scaled grads
 //                     [5] out: 1 when that sum is not finite (an inf / nan gradient: GradScaler's found_inf) — the Adam
 //                         kernel then leaves parameters and moments untouched (GradScaler.step skips the update)
+//                     [6] in: number of micro-batches that failed on some rank (data loading, CUDA OOM; summed over the ranks
+//                         by the caller): the step must not update anything then (pasero/training.py:444-446) -> [5] is raised too
 #include "common.cuh"
 #include "../../include/pasero_b200.h"
 
@@ -75,7 +77,7 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
         double t = 0.0;
         for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(partials)[i];
         stats[4] = t;
-        stats[5] = isfinite(t) ? 0.0 : 1.0;
+        stats[5] = (isfinite(t) && stats[6] == 0.0) ? 0.0 : 1.0;     // [6]: a failed micro-batch on some rank -> no update either
         *ticket = 0;
     }
 }

@@ -14,6 +14,7 @@ Design (B200-first, one process per GPU):
 import math
 import os
 import time
+import traceback
 from collections import defaultdict
 from collections.abc import Mapping
 from typing import Iterator, Optional
@@ -133,6 +134,13 @@ class ParamArena:
                 p.grad = self.view(self.grad, i)
 
 
+# Step scalars (`stats`, fp64[8] on the device): [0] loss [1] nll [2] target tokens [3] lines [4] squared gradient norm (written by
+# the norm kernel after the reduction) [5] found_inf (ditto) [6] failed micro-batches (data-loading error / CUDA OOM on some rank)
+# [7] target ids outside the vocabulary. Slots [0, STATS_SYNCED) are summed over the data-parallel ranks right after the forward
+# pass ([4] and [5] are still zero then): the logs, and the job's status (pasero/training.py:431: utils.gather_dict).
+STATS_SYNCED = 7
+
+
 class GradBuckets:
     """Bucketed allreduce of the gradient arena, overlapped with backward (replaces torch DDP's reducer,
     pasero/training.py:243-250). Buckets are contiguous arena slices of ~bucket_bytes, filled back to front."""
@@ -222,12 +230,12 @@ class GradBuckets:
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM, group=self.group)
                 if stats is not None:
-                    dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(stats[:STATS_SYNCED], op=dist.ReduceOp.SUM, group=self.group)
             torch.cuda.current_stream().wait_stream(self.stream)
         else:
             dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM, group=self.group)
             if stats is not None:
-                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(stats[:STATS_SYNCED], op=dist.ReduceOp.SUM, group=self.group)
         self.pending = [-1] * len(self.buckets)
         self.launch_order = list(range(len(self.buckets)))
 
@@ -238,7 +246,7 @@ class GradBuckets:
         with torch.cuda.stream(self.stream):
             if stats is not None:
                 self.stream.wait_event(stats_event)
-                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(stats[:STATS_SYNCED], op=dist.ReduceOp.SUM, group=self.group)
             for b, event in events:
                 lo, hi = self.buckets[b]
                 self.stream.wait_event(event)
@@ -256,9 +264,9 @@ class GradBuckets:
             if self.cuda:
                 self.stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self.stream):
-                    dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(stats[:STATS_SYNCED], op=dist.ReduceOp.SUM, group=self.group)
             else:
-                dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(stats[:STATS_SYNCED], op=dist.ReduceOp.SUM, group=self.group)
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.stream)
 
@@ -399,21 +407,54 @@ class Trainer:
     # ------------------------------------------------------------------ the step
     def train_step(self, batch_iterator: Iterator[dict]) -> dict:
         """One optimizer update over `update_freq` micro-batches (pasero/training.py:324-517). Returns the step's
-        logs: loss / nll_loss in bits (summed over all ranks' tokens), num_tokens, num_lines, gnorm, lr."""
+        logs: loss / nll_loss in bits (summed over all ranks' tokens), num_tokens, num_lines, gnorm, lr.
+
+        Failure handling (training.py:339-386, 411-421): a micro-batch whose loading raises, or whose forward / backward runs
+        out of GPU memory, is replaced by nothing — this rank's gradients of the step are zeroed, so it still takes part in
+        every collective with a neutral contribution — and counted in stats[6], which is summed over the ranks with the other
+        step scalars. A step with a failure anywhere updates no parameter on any rank (the norm kernel raises the same flag
+        the loss scaler's overflow uses) and its logs carry 'failed': True: the caller stops training, as the reference's
+        main loop does on `status.failed()`."""
         self.model.train()
         self.stats.zero_()
         ops.DirectGrads.active = self.direct
         self.direct.start_step()
+        failed = 0
         for batch_id in range(self.update_freq):
-            batch = next(batch_iterator)
-            batch = self.move_to_device(batch)
-            batch.setdefault('meta', {})
-            batch['meta']['step'] = self.steps
+            batch = None
+            try:
+                batch = next(batch_iterator)
+            except StopIteration:
+                raise
+            except Exception:   # noqa: BLE001  (a data-loading error must not desynchronise the ranks)
+                traceback.print_exc()
             last = batch_id == self.update_freq - 1
             if self.buckets is not None:
-                self.buckets.start_step(sync=last)   # no_sync() on all but the last micro-batch (training.py:407)
-            self._forward_backward(batch)
+                self.buckets.start_step(sync=last and batch is not None)   # no_sync() on all but the last micro-batch (training.py:407)
+            if batch is None:
+                failed += 1
+                continue
+            try:
+                batch = self.move_to_device(batch)
+                batch.setdefault('meta', {})
+                batch['meta']['step'] = self.steps
+                self._forward_backward(batch)
+            except RuntimeError as e:
+                if 'out of memory' not in str(e):
+                    raise
+                traceback.print_exc()
+                torch.cuda.empty_cache()
+                failed += 1
+                if self.buckets is not None:
+                    self.buckets.start_step(sync=False)     # whatever was launched stays launched; the rest goes through finish()
             ops.WgradStream.join()   # per micro-batch: the forked GEMMs' operands are kept referenced until the join
+        if failed:
+            self.arena.grad32.zero_()
+            self.arena.grad.zero_()
+            self.stats[:4] = 0
+            self.stats[6] = failed
+            # (buckets of this step that were already launched carry partial gradients into their allreduce: every rank sees
+            # the failure flag and skips the update, so their content no longer matters — only the order of the collectives)
         if self.buckets is not None:
             self.buckets.finish(self.stats)
         else:
@@ -540,6 +581,8 @@ class Trainer:
                 'gnorm': math.sqrt(max(s[4], 0.0)) if not overflow else float('inf'), 'lr': lr, 'loss_scale': loss_scale}
         if overflow:
             logs['overflow'] = True
+        if s[6] > 0:
+            logs['failed'] = True      # a micro-batch failed on some rank: no parameter was updated (see train_step)
         return logs
 
     # ------------------------------------------------------------------ CUDA-graph path

@@ -49,7 +49,7 @@ def _worker(rank: int, world: int, port: int, q):
                 continue
             arena.view(arena.grad, i).fill_(float(rank + 1))
             buckets.param_ready(i)
-        stats = torch.tensor([10.0 * (rank + 1), 5.0, 100.0 + rank, 4.0, 0, 0, 0, 0], dtype=torch.float64)
+        stats = torch.tensor([10.0 * (rank + 1), 5.0, 100.0 + rank, 4.0, 0, 0, float(rank == 1), 0], dtype=torch.float64)
         launched_before_finish = list(buckets.launch_order)
         buckets.finish(stats)
         expect = float(sum(r + 1 for r in range(world)))
@@ -58,6 +58,7 @@ def _worker(rank: int, world: int, port: int, q):
             want = 0.0 if name == 'unused' else expect
             assert torch.all(g == want), (name, g.unique())
         assert stats[:4].tolist() == [10.0 * 3, 10.0, 201.0, 8.0]
+        assert stats[6].item() == 1.0 and stats[7].item() == 0.0     # rank 1's failed micro-batch is known to every rank
         # buckets complete in reverse-layer order (the last bucket holds the last parameters)
         assert launched_before_finish == sorted(launched_before_finish)
         # graph mode: one allreduce over the whole arena between the step graph and the optimizer (allreduce_all)

@@ -477,3 +477,24 @@ def test_fbank_into_encoder_padded_layout():
         out2, mask2, _ = model.encoder(padded, plan.frames_tensor, padded_layout=(F,))
     assert torch.equal(mask1, mask2)
     assert torch.equal(out1, out2)
+
+
+def test_failed_micro_batch_updates_nothing_and_is_reported():
+    """pasero/training.py:339-386, 411-421: a micro-batch whose loading raises (or that runs out of memory) must not
+    desynchronise or corrupt the step — no parameter moves, the logs say so, and the next step trains normally."""
+    from pasero_b200.training import Trainer
+    cfg, task, model = build()
+    trainer = Trainer(cfg, task, model)
+    batches = synth.train_batches()
+    trainer.train_step(iter([batches[0]]))
+    before = (trainer.arena.param.clone(), trainer.arena.exp_avg.clone(), trainer.arena.exp_avg_sq.clone())
+
+    def broken():
+        raise OSError('corrupt feature file')
+        yield   # pragma: no cover
+    logs = trainer.train_step(broken())
+    assert logs['failed'] and logs['num_tokens'] == 0
+    assert torch.equal(trainer.arena.param, before[0]) and torch.equal(trainer.arena.exp_avg, before[1])
+    assert torch.equal(trainer.arena.exp_avg_sq, before[2])
+    logs = trainer.train_step(iter([batches[1]]))
+    assert 'failed' not in logs and logs['num_tokens'] > 0 and not torch.equal(trainer.arena.param, before[0])

@@ -388,3 +388,95 @@ def test_big_adapter_dims_forward_backward_matches_oracle(train_all):
     else:
         assert all(p.grad is None for n, p in model.named_parameters() if 'adapters' not in n.split('.'))
         check_grads(got, {k: v for k, v in grads_w.items() if '.adapters.' in k}, grads16, label='Transformer-big dims, adapters only')
+
+
+# ---------------------------------------------------------------------------------------------- IWSLT2023 recipe
+IWSLT_RECIPE = """
+arch: adapter_nllb_1b3
+encoder_positional_encoding: sinusoidal
+encoder_embed_norm: False
+encoder_layers: 4                 # (24 in examples/IWSLT2023/taq-fr-contrastive-1.yaml: depth reduced, every width kept)
+decoder_layers: 2                 # (24)
+shift_encoder_layers: 0
+flexible: True
+conv_input_dim: 80
+conv_kernel_sizes: [5]
+input_dim: 768
+seed: 3
+train_params_regex: '(.*\\.in_linear|.*\\.subsample|encoder\\.layers\\.[0-1]\\.|.*\\.adapters|encoder\\.layernorm_embedding)'
+encoder_adapter_layer_ids: [2, 3]
+dropout: 0.3
+attention_dropout: 0.1
+label_smoothing: 0.2
+lr: 0.0005
+warmup: 10000
+init_lr: 1.0e-07
+clip_norm: 0.0
+batch_size: 4000
+virtual_dp_size: 2                # (8)
+max_steps: 300000
+encoder_max_len: 2048
+decoder_max_len: 128
+memory_efficient_fp16: False
+flat_fp16: True
+dtype: float16
+task: speech_translation
+target_lang_code: True
+"""
+
+
+def test_iwslt2023_recipe_float16_partial_freeze_training():
+    """The one shipped ST recipe (examples/IWSLT2023/taq-fr-contrastive-1.yaml) at its real widths — NLLB-1.3B body (d 1024,
+    16 heads, FFN 8192, pre-norm) with adapters in the upper encoder layers, 768-dim wav2vec features through `in_linear`, a
+    single k = 5 convolution, `train_params_regex`, float16 with FlatFP16Adam, gradient accumulation, attention dropout, no
+    clipping — parsed from its own YAML keys and trained for a few steps: exactly the regex-selected parameters are trained and
+    move, the rest stays bit-identical, the loss goes down on a repeated batch and the loss scale behaves."""
+    import re
+    import numpy as np
+    import yaml
+    from pasero_b200 import TrainingConfig, build_model, reference_param_names
+    from pasero_b200.task import Dictionary, SpeechTranslationTask
+    from pasero_b200.training import Trainer
+    opts = yaml.safe_load(IWSLT_RECIPE)
+    cfg = TrainingConfig.from_dict(opts)
+    m = cfg.model_cfg
+    assert (m.embed_dim, m.encoder_ffn_dim, m.encoder_attention_heads, m.encoder_prenorm, m.adapters) == (1024, 8192, 16, True, True)
+    task = SpeechTranslationTask(cfg, Dictionary(tokens=[f't{i}' for i in range(8028)]))
+    torch.manual_seed(3)
+    model = build_model(cfg, task)
+    ref_names = reference_param_names(model)
+    pattern = re.compile(opts['train_params_regex'])
+    trainer = Trainer(cfg, task, model)
+    assert trainer.fp16 and trainer.master_weights and trainer.update_freq == 2 and trainer.arena.master is not None
+    trained = {n for n, p in model.named_parameters() if p.requires_grad}
+    for n, p in model.named_parameters():
+        assert (n in trained) == all(bool(pattern.match(r)) for r in ref_names[n]), n
+    assert any('adapters' in n for n in trained) and any(n.startswith('encoder.in_linear') for n in trained)
+    assert not any(n.startswith('decoder.layers') and 'adapters' not in n for n in trained)
+    frozen_before = {n: p.detach().clone() for n, p in model.named_parameters() if n not in trained}
+    moved_before = {n: p.detach().clone() for n, p in model.named_parameters() if n in trained}
+    master_before = trainer.arena.master.clone()
+    rng = np.random.RandomState(4)
+    frames, dec_lens = [310, 180, 97], [14, 9, 6]
+    batches = []
+    for k in range(2):
+        b = synth.sized_batch(20 + k, frames, dec_lens, 8032)
+        x = torch.zeros(len(frames), max(frames), 768)
+        for i, f in enumerate(frames):
+            x[i, :f] = torch.from_numpy(rng.randn(f, 768).astype(np.float32))
+        b['encoder_input'] = x
+        batches.append(b)
+    losses = []
+    for step in range(6):
+        logs = trainer.train_step(iter(batches))
+        assert 'overflow' not in logs and 'failed' not in logs and logs['loss_scale'] == 128.0
+        assert logs['num_tokens'] == 2 * (sum(dec_lens) - len(dec_lens))
+        losses.append(logs['loss'])
+    assert losses[-1] < losses[0], losses
+    for n, p in model.named_parameters():
+        if n in frozen_before:
+            assert torch.equal(p.detach(), frozen_before[n]), n
+    changed = [n for n in trained if not torch.equal(dict(model.named_parameters())[n].detach(), moved_before[n])]
+    # lr is still ~1e-7 (warm-up over 10 000 steps): every fp32 master weight moves, but not every update reaches half a float16 ulp
+    assert (trainer.arena.master != master_before).float().mean().item() > 0.9
+    assert len(changed) >= 0.5 * len(trained), (len(changed), len(trained))
