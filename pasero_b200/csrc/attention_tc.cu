@@ -363,7 +363,14 @@ struct BwdCfg {
 // item are requested after the current item's first key tile is finished, Q_0 / dO_0 after its second-to-last iteration,
 // so the next item's first S^T / dP^T products start the moment the current item's last chains are issued.
 // Operand tiles are 128 rows; load groups: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1).
-static constexpr int BWD_THREADS = 320;   // 8 softmax / drain warps, 1 MMA warp, 1 TMA warp
+// BWD_SW softmax / drain warps (TMEM lane quarter = warp & 3, column part = warp >> 2), then 1 MMA warp and 1 TMA warp.
+// 16 softmax warps were measured (64 x 8 heads x 250 x 250: 100.4 us against 96.3 us with 8): the elementwise stage between the two
+// groups of MMAs is not what bounds an iteration — the serial chain MMA -> commit -> tcgen05.ld -> exp / dS -> shared-memory
+// stores -> fence -> MMA is, and more warps only add barrier traffic.
+static constexpr int BWD_SW = 8;
+static constexpr int BWD_PARTS = BWD_SW / 4;
+static constexpr int BWD_ST = BWD_SW * 32;      // softmax threads
+static constexpr int BWD_THREADS = BWD_ST + 64;
 
 template <bool CAUSAL, bool DROPOUT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -392,10 +399,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const int total_items = p.H * p.B * pairs;
     const bool part = pairs > 1;
 
-    if (warp == 8) {
+    if (warp == BWD_SW) {
         if (lane == 0) {
             ptx::prefetch_tmap(&tmq); ptx::prefetch_tmap(&tmk); ptx::prefetch_tmap(&tmv); ptx::prefetch_tmap(&tmdo);
-            ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 256); ptx::mbar_init(bar_acc, 1);
+            ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, BWD_ST); ptx::mbar_init(bar_acc, 1);
             for (int i = 0; i < 4; ++i) { ptx::mbar_init(&bar_ld[i], 1); ptx::mbar_init(&bar_free[i], 1); }
             ptx::fence_barrier_init();
         }
@@ -425,7 +432,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         return w;
     };
 
-    if (warp == 9) {
+    if (warp == BWD_SW + 1) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             const uint32_t qb = (uint32_t)p.q_tma_rows * 128u, kb = (uint32_t)p.kv_tma_rows * 128u;   // bytes per tile box
@@ -458,7 +465,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             }
             (void)n2; (void)n3;
         }
-    } else if (warp == 8) {
+    } else if (warp == BWD_SW) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc_cd = ptx::make_idesc_bf16(128, 64, false, true);
@@ -537,8 +544,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         }
     } else {
         // ===================== softmax / drain warps =====================
-        // warps w and w + 4 own the same 32 key rows (TMEM lanes) and split the query columns / output columns
-        const int quarter = warp & 3, half = warp >> 2;
+        // warps w, w + 4, ... own the same 32 key rows (TMEM lanes) and split the query columns / output columns
+        const int quarter = warp & 3, part_id = warp >> 2;
         const int t = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
@@ -549,8 +556,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
             const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
             const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
-            ptx::bar_sync(1, 256);     // everybody is done with the previous item's lse / delta
-            {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
+            ptx::bar_sync(1, BWD_ST);     // everybody is done with the previous item's lse / delta
+            if (threadIdx.x < 256) {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
                 const int r = threadIdx.x;   // 0..255: query q0 + r
                 float l2 = INFINITY, dl = 0.f;
                 if (r < Lq_blk) {
@@ -570,7 +577,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
                 sLse[r] = l2; sDelta[r] = dl;
             }
-            ptx::bar_sync(1, 256);
+            ptx::bar_sync(1, BWD_ST);
 
             for (int j = 0; j < nj; ++j) {
                 const int key = 128 * j + t;            // block-local key of this thread
@@ -581,7 +588,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                     ptx::mbar_wait(bar_s, it & 1);
                     ptx::tc_fence_after();
 #pragma unroll 1
-                    for (int c = half; c < nch; c += 2) {
+                    for (int c = part_id; c < nch; c += BWD_PARTS) {
                         uint32_t s[32], dp[32];
                         ptx::tmem_ld_32x32(t_s + lane_base + c * 32, s);
                         ptx::tmem_ld_32x32(t_dp + lane_base + c * 32, dp);
@@ -638,16 +645,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                     if (i == ni - 1) {   // dV_j and dK_j are complete once this iteration's MMAs retire
                         ptx::mbar_wait(bar_acc, it & 1);
                         ptx::tc_fence_after();
-                        // half 0 drains dV, half 1 drains dK (64 columns each)
+                        // the column parts share the drain: dV then dK, 64 columns each, in slices of 128 / BWD_PARTS columns
                         // a single block pair writes the gradients themselves, otherwise this pair's partial sums
                         // (dk_part / dv_part [n_qb][B*Lk][H*64], added up by attn_reduce_kernel)
+                        constexpr int SLICE = 128 / BWD_PARTS;            // 64 (8 warps) or 32 (16 warps) columns per warp
+                        const int col_all = part_id * SLICE;              // position inside [dV | dK]
+                        const bool is_dk = col_all >= 64;
+                        const int col = col_all & 63;
                         const long long krow = (long long)b * p.Lk + k0 + key;
-                        bf16* dst = !part ? (half == 0 ? p.dv + krow * p.lddv + h * 64 : p.dk + krow * p.lddk + h * 64)
-                                          : (half == 0 ? p.dv_part : p.dk_part) + ((long long)qi * p.B * p.Lk + krow) * (p.H * 64) + h * 64;
-                        const float mul = half == 0 ? 1.0f : p.scale;
-                        const uint32_t src = (half == 0 ? t_dv : t_dk) + lane_base;
+                        bf16* dst = (!part ? (!is_dk ? p.dv + krow * p.lddv + h * 64 : p.dk + krow * p.lddk + h * 64)
+                                           : (!is_dk ? p.dv_part : p.dk_part) + ((long long)qi * p.B * p.Lk + krow) * (p.H * 64) + h * 64) + col;
+                        const float mul = !is_dk ? 1.0f : p.scale;
+                        const uint32_t src = (!is_dk ? t_dv : t_dk) + lane_base + col;
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
+                        for (int hh = 0; hh < SLICE / 32; ++hh) {
                             uint32_t v[32];
                             ptx::tmem_ld_32x32(src + hh * 32, v);
                             ptx::tmem_ld_wait();
@@ -670,12 +681,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             // dQ: every (j, i) chain has retired (the last bar_acc wait above covers all earlier MMAs); each warp drains
             // 32 of the 64 columns of its rows. The next item's first dQ MMA is issued behind its first bar_p, i.e. after
             // this drain in every softmax thread's program order.
-            for (int i = 0; i < ni; ++i) {
+            // the (query chunk, 32-column slice) pairs are dealt round-robin to the column parts
+            for (int u = part_id; u < 2 * ni; u += BWD_PARTS) {
+                const int i = u >> 1, ch = u & 1;
                 const int qrow = 128 * i + t;           // block-local query
                 const long long grow = (long long)b * p.Lq + q0 + qrow;
-                bf16* dst = (!part ? p.dq + grow * p.lddq : p.dq_part + ((long long)kj * p.B * p.Lq + grow) * (p.H * 64)) + h * 64 + half * 32;
+                bf16* dst = (!part ? p.dq + grow * p.lddq : p.dq_part + ((long long)kj * p.B * p.Lq + grow) * (p.H * 64)) + h * 64 + ch * 32;
                 uint32_t v[32];
-                ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + half * 32, v);
+                ptx::tmem_ld_32x32(t_dq + 64 * i + lane_base + ch * 32, v);
                 ptx::tmem_ld_wait();
                 if (qrow < Lq_blk) {
 #pragma unroll
@@ -693,7 +706,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         }
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == BWD_SW) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
     }
