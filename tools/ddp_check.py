@@ -19,9 +19,11 @@ def main():
     from pasero_b200.training import Trainer
     batches = synth.train_batches()
     steps = 4
+    # `float16` as the first argument: the same check with dtype float16 + FlatFP16Adam (loss scaling, fp32 master weights)
+    extra = dict(dtype='float16', memory_efficient_fp16=False, flat_fp16=True) if 'float16' in sys.argv[1:] else {}
     results = {}
     for mode in ('eager', 'graph'):
-        cfg, task, model = build(seed=1, bucket_bytes=64 * 1024)
+        cfg, task, model = build(seed=1, bucket_bytes=64 * 1024, **extra)
         trainer = Trainer(cfg, task, model)
         assert trainer.distributed and trainer.dp_size == world and len(trainer.buckets.buckets) > 3
         logs_all = []
@@ -34,7 +36,7 @@ def main():
             logs_all.append(dict(logs.items()))
         results[mode] = (trainer.arena.param.clone(), logs_all, trainer.arena.grad.float().clone())
     # reference: one process, the ranks' batches as micro-batches
-    cfg, task, model = build(seed=1, virtual_dp_size=world)
+    cfg, task, model = build(seed=1, virtual_dp_size=world, **extra)
     ref = Trainer(cfg, task, model, data_parallel=False)
     ref.update_freq = world
     ref_logs = []
@@ -64,7 +66,7 @@ def main():
     dist.broadcast(p0, 0)
     assert torch.equal(p, p0), 'ranks diverged'
     if rank == 0:
-        print('DDP CHECK', 'OK' if ok else 'FAILED')
+        print('DDP CHECK', 'float16' if extra else 'bfloat16', 'OK' if ok else 'FAILED')
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
