@@ -352,7 +352,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 struct BwdCfg {
     static constexpr int T = 256 * 128;                 // one [256 x 64] bf16 operand
     static constexpr int PT = 128 * 256;                // one [128 x 128] bf16 tile (two 64-column blocks)
-    static constexpr int SMEM_BYTES = 4 * T + 2 * PT + 2 * 256 * 4 + 1024 /*align*/ + 128 /*barriers*/;
+    static constexpr int SMEM_BYTES = 4 * T + 2 * PT + 4 * 256 * 4 /* lse, delta: two items */ + 1024 /*align*/ + 128 /*barriers*/;
     // TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ chunk i [384 + 64 i, ...)
 };
 
@@ -387,8 +387,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     uint8_t* sPT = sV + BwdCfg::T;
     uint8_t* sdST = sPT + BwdCfg::PT;
     float* sLse = reinterpret_cast<float*>(sdST + BwdCfg::PT);
-    float* sDelta = sLse + 256;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+    float* sDelta = sLse + 512;       // [2][256] each: the current item's values and the next item's
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 512);
     uint64_t* bar_s = bars, *bar_p = bars + 1, *bar_acc = bars + 2;
     uint64_t* bar_ld = bars + 3;     // [4] operand group landed: (K_0, Q_0), (V_0, dO_0), (Q_1, dO_1), (K_1, V_1)
     uint64_t* bar_free = bars + 7;   // [4] buffers reusable: (K_0, V_0), (Q_0, dO_0), (Q_1, dO_1), (K_1, V_1)
@@ -466,47 +466,69 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             (void)n2; (void)n3;
         }
     } else if (warp == BWD_SW) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, warp-uniform; one elected lane issues) =====================
+        {
+            const bool leader = ptx::elect_one();
             const uint32_t idesc_cd = ptx::make_idesc_bf16(128, 64, false, true);
             const uint32_t idesc_e = ptx::make_idesc_bf16(128, 64, true, true);
             uint32_t it = 0, n = 0, n2 = 0, n3 = 0;   // iterations / items / uses of load groups 2 and 3 so far (barrier phases)
+#ifdef PB_ATTN_TIMING
+            long long tm[16][3]; const long long tm0 = clock64();
+#endif
+            // S^T = K_j Q_i^T and dP^T = V_j dO_i^T of iteration (j, i). Independent chains are interleaved step by step: consecutive
+            // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
+            auto issue_scores = [&](const Item& w, int j, int i, bool first_of_item, uint32_t lpar) {
+                const int nq = min(128, w.q_box - 128 * i);     // query columns of this chunk inside the box
+                const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
+                const uint64_t kd = kdesc(sK + j * 16384, 0), qd = kdesc(sQ + i * 16384, 0);
+                const uint64_t vd = kdesc(sV + j * 16384, 0), dod = kdesc(sdO + i * 16384, 0);
+                if (first_of_item) {
+                    ptx::mbar_wait(&bar_ld[0], lpar);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (leader) ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                    ptx::mbar_wait(&bar_ld[1], lpar);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (leader) ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                } else {
+                    if (j == 0 && i == 1) { ptx::mbar_wait(&bar_ld[2], n2 & 1); ++n2; ptx::tc_fence_after(); }   // Q_1, dO_1
+                    if (j == 1 && i == 0) { ptx::mbar_wait(&bar_ld[3], n3 & 1); ++n3; ptx::tc_fence_after(); }   // K_1, V_1
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (leader) ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
+                        if (leader) ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
+                    }
+                }
+                if (leader) ptx::umma_commit(bar_s);
+            };
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
                 const Item w = decode(item);
                 const uint32_t lpar = n & 1;
-                int local = 0;
+                issue_scores(w, 0, 0, true, lpar);
                 for (int j = 0; j < w.nj; ++j) {
                     const int kc = min(128, w.kv_box - 128 * j);       // key rows of this tile inside the TMA box
-                    for (int i = 0; i < w.ni; ++i, ++it, ++local) {
-                        const int nq = min(128, w.q_box - 128 * i);     // query columns of this chunk inside the box
-                        const uint32_t idesc_ab = ptx::make_idesc_bf16(128, nq, false, false);
-                        // S^T = K_j Q_i^T and dP^T = V_j dO_i^T. Independent chains are interleaved step by step: consecutive
-                        // tcgen05.mma into the same accumulator serialise on its latency when N is small (measured).
-                        const uint64_t kd = kdesc(sK + j * 16384, 0), qd = kdesc(sQ + i * 16384, 0);
-                        const uint64_t vd = kdesc(sV + j * 16384, 0), dod = kdesc(sdO + i * 16384, 0);
-                        if (local == 0) {
-                            ptx::mbar_wait(&bar_ld[0], lpar);
-                            ptx::tc_fence_after();
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
-                            ptx::mbar_wait(&bar_ld[1], lpar);
-                            ptx::tc_fence_after();
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
-                        } else {
-                            if (j == 0 && i == 1) { ptx::mbar_wait(&bar_ld[2], n2 & 1); ++n2; ptx::tc_fence_after(); }   // Q_1, dO_1
-                            if (j == 1 && i == 0) { ptx::mbar_wait(&bar_ld[3], n3 & 1); ++n3; ptx::tc_fence_after(); }   // K_1, V_1
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                ptx::umma_bf16_lh(t_s, lo32(kd) + 2 * k, hi32(kd), lo32(qd) + 2 * k, hi32(qd), idesc_ab, k > 0 ? 1u : 0u);
-                                ptx::umma_bf16_lh(t_dp, lo32(vd) + 2 * k, hi32(vd), lo32(dod) + 2 * k, hi32(dod), idesc_ab, k > 0 ? 1u : 0u);
-                            }
-                        }
-                        ptx::umma_commit(bar_s);
-                        ptx::mbar_wait(bar_p, it & 1);
+                    for (int i = 0; i < w.ni; ++i, ++it) {
+                        const int nq = min(128, w.q_box - 128 * i);
+                        const bool last = (j == w.nj - 1 && i == w.ni - 1);
+#ifdef PB_ATTN_TIMING
+                        if (it < 16) tm[it][0] = clock64() - tm0;
+#endif
+                        ptx::mbar_wait(bar_p, it & 1);     // P^T / dS^T of this iteration are in shared memory; S^T / dP^T have been read
                         ptx::tc_fence_after();
+#ifdef PB_ATTN_TIMING
+                        if (it < 16) tm[it][1] = clock64() - tm0;
+#endif
+                        // The NEXT iteration's scores go first: the softmax warps then work on them while this iteration's three
+                        // gradient chains are still being issued and executed (one thread issues ~75 cycles per MMA: the 24 of them
+                        // were 1.8 k of every iteration's 5.6 k cycles, in-kernel timeline). Not across items: the next item's
+                        // operand loads wait for buffers that this item's last gradient chains release.
+                        if (!last) {
+                            const int jn = (i + 1 < w.ni) ? j : j + 1, in = (i + 1 < w.ni) ? i + 1 : 0;
+                            issue_scores(w, jn, in, false, lpar);
+                        }
                         const int qsteps = nq >> 4, ksteps = kc >> 4;
                         const uint64_t ptd = kdesc(sPT, 0), dstd = kdesc(sdST, 0), dst_mn = mndesc(sdST, 0, 16384);
                         const uint64_t do_mn = mndesc(sdO + i * 16384, 0, 8192), q_mn = mndesc(sQ + i * 16384, 0, 8192);
@@ -517,23 +539,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                         for (int kk = 0; kk < 8; ++kk) {   // the three chains interleaved
                             if (kk < qsteps) {
                                 // dV_j += P^T dO_i ; dK_j += dS^T Q_i
-                                ptx::umma_bf16_lh(t_dv, lo32(ptd) + kstep16(kk), hi32(ptd), lo32(do_mn) + 128 * kk, hi32(do_mn), idesc_cd,
+                                if (leader) ptx::umma_bf16_lh(t_dv, lo32(ptd) + kstep16(kk), hi32(ptd), lo32(do_mn) + 128 * kk, hi32(do_mn), idesc_cd,
                                                   kk > 0 ? 1u : acc_i);
-                                ptx::umma_bf16_lh(t_dk, lo32(dstd) + kstep16(kk), hi32(dstd), lo32(q_mn) + 128 * kk, hi32(q_mn), idesc_cd,
+                                if (leader) ptx::umma_bf16_lh(t_dk, lo32(dstd) + kstep16(kk), hi32(dstd), lo32(q_mn) + 128 * kk, hi32(q_mn), idesc_cd,
                                                   kk > 0 ? 1u : acc_i);
                             }
                             if (kk < ksteps)   // dQ_i += dS K_j   (A = dS^T read MN-major)
-                                ptx::umma_bf16_lh(t_dqi, lo32(dst_mn) + 128 * kk, hi32(dst_mn), lo32(k_mn) + 128 * kk, hi32(k_mn), idesc_e,
+                                if (leader) ptx::umma_bf16_lh(t_dqi, lo32(dst_mn) + 128 * kk, hi32(dst_mn), lo32(k_mn) + 128 * kk, hi32(k_mn), idesc_e,
                                                   kk > 0 ? 1u : acc_j);
                         }
-                        ptx::umma_commit(bar_acc);
+                        if (leader) ptx::umma_commit(bar_acc);
+#ifdef PB_ATTN_TIMING
+                        if (it < 16) tm[it][2] = clock64() - tm0;
+#endif
                         // operand buffers whose last reader has just been issued go back to the TMA warp (the commit arrives
                         // when these MMAs have retired); buffers this item never used are released with the last iteration
-                        const bool last = (j == w.nj - 1 && i == w.ni - 1);
-                        if (j == 0 && i == w.ni - 1) ptx::umma_commit(&bar_free[0]);                 // K_0, V_0
-                        if (j == w.nj - 1 && i == 0) ptx::umma_commit(&bar_free[1]);                 // Q_0, dO_0
-                        if ((w.ni > 1 && j == w.nj - 1 && i == 1) || (w.ni == 1 && last)) ptx::umma_commit(&bar_free[2]);   // Q_1, dO_1
-                        if ((w.nj > 1 && j == 1 && i == w.ni - 1) || (w.nj == 1 && last)) ptx::umma_commit(&bar_free[3]);   // K_1, V_1
+                        if (leader && j == 0 && i == w.ni - 1) ptx::umma_commit(&bar_free[0]);                 // K_0, V_0
+                        if (leader && j == w.nj - 1 && i == 0) ptx::umma_commit(&bar_free[1]);                 // Q_0, dO_0
+                        if (leader && ((w.ni > 1 && j == w.nj - 1 && i == 1) || (w.ni == 1 && last))) ptx::umma_commit(&bar_free[2]);   // Q_1, dO_1
+                        if (leader && ((w.nj > 1 && j == 1 && i == w.ni - 1) || (w.nj == 1 && last))) ptx::umma_commit(&bar_free[3]);   // K_1, V_1
                     }
                 }
             }
@@ -541,6 +565,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             // landed in this CTA's shared memory before the CTA may exit and the memory is handed to another block
             if (n > 0)
                 for (int g = 0; g < 4; ++g) ptx::mbar_wait(&bar_free[g], (n - 1) & 1);
+#ifdef PB_ATTN_TIMING
+            if (blockIdx.x == 0 && leader)
+                for (uint32_t i = 0; i < it && i < 16; ++i)
+                    printf("mma it %u: S/dP issued+commit %lld  P ready %lld  dV/dK/dQ issued+commit %lld\n", i, tm[i][0], tm[i][1], tm[i][2]);
+#endif
         }
     } else {
         // ===================== softmax / drain warps =====================
@@ -550,20 +579,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
         uint32_t it = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const Item w = decode(item);
-            const int h = w.h, b = w.b, q0 = w.q0, k0 = w.k0, qi = w.qi, kj = w.kj, ni = w.ni, nj = w.nj;
-            const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
-            const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
-            const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
-            ptx::bar_sync(1, BWD_ST);     // everybody is done with the previous item's lse / delta
-            if (threadIdx.x < 256) {   // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread, while the loads fly
+#ifdef PB_ATTN_TIMING
+        long long ts[16][4]; const long long ts0 = clock64();
+#endif
+        // log-sum-exp (log2 units) and delta = rowsum(dO o O) of one query row per thread for item `w`, into lse / delta buffer
+        // `which`. Called for the NEXT item right after the current item's last softmax stage, so that the global-load latency
+        // sits under the last gradient MMAs instead of between two items (it was ~5 k of the ~19 k idle cycles per item).
+        auto item_prologue = [&](const Item& w, int which) {
+            if (threadIdx.x < 256) {
                 const int r = threadIdx.x;   // 0..255: query q0 + r
+                const int Lq_rows = min(256, p.Lq - w.q0);
                 float l2 = INFINITY, dl = 0.f;
-                if (r < Lq_blk) {
-                    l2 = p.lse_in[((long long)b * p.H + h) * p.Lq + q0 + r] * LOG2E_F;
-                    const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.Lq + q0 + r) * p.ldo + h * 64);
-                    const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + q0 + r) * p.lddo + h * 64);
+                if (r < Lq_rows) {
+                    l2 = p.lse_in[((long long)w.b * p.H + w.h) * p.Lq + w.q0 + r] * LOG2E_F;
+                    const uint4* po = reinterpret_cast<const uint4*>(p.o_in + ((long long)w.b * p.Lq + w.q0 + r) * p.ldo + w.h * 64);
+                    const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)w.b * p.Lq + w.q0 + r) * p.lddo + w.h * 64);
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const uint4 a = __ldg(po + g), d = __ldg(pd + g);
@@ -575,18 +605,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                         }
                     }
                 }
-                sLse[r] = l2; sDelta[r] = dl;
+                sLse[which * 256 + r] = l2; sDelta[which * 256 + r] = dl;
             }
-            ptx::bar_sync(1, BWD_ST);
+        };
+        int buf = 0;
+        if ((int)blockIdx.x < total_items) item_prologue(decode(blockIdx.x), 0);
+        ptx::bar_sync(1, BWD_ST);
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, buf ^= 1) {
+            const Item w = decode(item);
+            const int h = w.h, b = w.b, q0 = w.q0, k0 = w.k0, qi = w.qi, kj = w.kj, ni = w.ni, nj = w.nj;
+            const int Lq_blk = min(256, p.Lq - q0), Lk_blk = min(256, p.Lk - k0);   // rows of this block that exist
+            const int kvlen = (p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk) - k0;   // block-local: keys [0, kvlen) are unmasked
+            const int coff = p.Lk - p.Lq + q0 - k0;                               // causal: local key j visible to local query i iff j <= i + coff
+            // lse / delta of this item were put into buffer `buf` while the previous item was finishing (or before the loop)
+            const float* cLse = sLse + buf * 256;
+            const float* cDelta = sDelta + buf * 256;
+            const int next_item = item + gridDim.x;
+            int local = 0;
 
             for (int j = 0; j < nj; ++j) {
                 const int key = 128 * j + t;            // block-local key of this thread
                 const bool rowok = key < kvlen;
-                for (int i = 0; i < ni; ++i, ++it) {
+                for (int i = 0; i < ni; ++i, ++it, ++local) {
                     const int nq = min(128, w.q_box - 128 * i);
                     const int nch = (nq + 31) >> 5;
+                    // P^T / dS^T of the previous iteration may still be read by its gradient MMAs (issued AFTER this iteration's
+                    // score MMAs): the first shared-memory store of this iteration waits for them, the arithmetic does not
+                    bool wait_prev = local > 0;
+#ifdef PB_ATTN_TIMING
+                    if (it < 16) ts[it][0] = clock64() - ts0;
+#endif
                     ptx::mbar_wait(bar_s, it & 1);
                     ptx::tc_fence_after();
+#ifdef PB_ATTN_TIMING
+                    if (it < 16) ts[it][1] = clock64() - ts0;
+#endif
 #pragma unroll 1
                     for (int c = part_id; c < nch; c += BWD_PARTS) {
                         uint32_t s[32], dp[32];
@@ -594,8 +647,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                         ptx::tmem_ld_32x32(t_dp + lane_base + c * 32, dp);
                         ptx::tmem_ld_wait();
                         const int qb = 128 * i + c * 32;
-                        const float4* l4 = reinterpret_cast<const float4*>(sLse + qb);
-                        const float4* d4 = reinterpret_cast<const float4*>(sDelta + qb);
+                        const float4* l4 = reinterpret_cast<const float4*>(cLse + qb);
+                        const float4* d4 = reinterpret_cast<const float4*>(cDelta + qb);
                         // keep bits of (query qb + e, this thread's key): lane e fetches query qb + e's word of this warp's 32
                         // keys (the warp's keys share one word: key = k0 + 128 j + 32 quarter + lane), broadcast by shuffle below
                         uint32_t mword = 0xffffffffu;
@@ -604,6 +657,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                             const int word = (k0 + 128 * j + quarter * 32) >> 5;
                             mword = (qrow < p.Lq && word < p.mask_ld) ? p.mask[(((long long)b * p.H + h) * p.Lq + qrow) * p.mask_ld + word] : 0u;
                         }
+                        uint4 pw4[4], dw4[4];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {   // 8 queries = one 16-byte chunk of P^T and of dS^T
                             const float4 la = l4[2 * g], lb = l4[2 * g + 1], da = d4[2 * g], db = d4[2 * g + 1];
@@ -633,15 +687,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                             dw.x = pack_bf16x2(ds[0], ds[1]); dw.y = pack_bf16x2(ds[2], ds[3]);
                             dw.z = pack_bf16x2(ds[4], ds[5]); dw.w = pack_bf16x2(ds[6], ds[7]);
                             if (!rowok) { pw = make_uint4(0, 0, 0, 0); dw = make_uint4(0, 0, 0, 0); }   // masked / unloaded key row
+                            pw4[g] = pw; dw4[g] = dw;
+                        }
+                        if (wait_prev) {
+                            ptx::mbar_wait(bar_acc, (it - 1) & 1);
+                            wait_prev = false;
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
                             const int c8 = c * 4 + g;
                             const int off = (c8 >> 3) * 16384 + t * 128 + (((c8 & 7) ^ (t & 7)) << 4);
-                            *reinterpret_cast<uint4*>(sPT + off) = pw;
-                            *reinterpret_cast<uint4*>(sdST + off) = dw;
+                            *reinterpret_cast<uint4*>(sPT + off) = pw4[g];
+                            *reinterpret_cast<uint4*>(sdST + off) = dw4[g];
                         }
                     }
+                    // every thread observes every phase of bar_acc, also the ones without a chunk in this iteration: a thread that
+                    // skipped one would find the NEXT wait on it (parity of two phases later) already satisfied
+                    if (wait_prev) ptx::mbar_wait(bar_acc, (it - 1) & 1);
+#ifdef PB_ATTN_TIMING
+                    if (it < 16) ts[it][2] = clock64() - ts0;
+#endif
                     ptx::fence_proxy_async();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(bar_p);
+#ifdef PB_ATTN_TIMING
+                    if (it < 16) ts[it][3] = clock64() - ts0;
+#endif
+                    if (j == nj - 1 && i == ni - 1 && next_item < total_items) item_prologue(decode(next_item), buf ^ 1);
                     if (i == ni - 1) {   // dV_j and dK_j are complete once this iteration's MMAs retire
                         ptx::mbar_wait(bar_acc, it & 1);
                         ptx::tc_fence_after();
@@ -703,7 +775,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
                 }
             }
             ptx::tc_fence_before();
+            ptx::bar_sync(1, BWD_ST);     // the next item's lse / delta (written above by every thread) are visible
         }
+#ifdef PB_ATTN_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (uint32_t i = 0; i < it && i < 16; ++i)
+                printf("softmax it %u: reach wait %lld  S ready %lld  math done %lld  arrived %lld\n", i, ts[i][0], ts[i][1], ts[i][2], ts[i][3]);
+#endif
     }
     __syncthreads();
     if (warp == BWD_SW) {
@@ -924,7 +1002,7 @@ int attn_bwd_tc(const pb200_attn_params* q, cudaStream_t stream) {
 
 }  // namespace pb200
 
-#ifdef PB_ATTN_TIMING
+#if defined(PB_ATTN_TIMING) && !defined(PB200_HALF)   // (debug export, not in the header: only the bfloat16 build defines it)
 extern "C" int pb200_debug_attn_timing(long long* host_out, int n_ctas) {
     if (n_ctas > 4096) n_ctas = 4096;
     cudaDeviceSynchronize();

@@ -127,6 +127,21 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
+// true in exactly one (elected) lane of the converged warp. The MMA-issuing warps run their whole control flow warp-uniformly and
+// guard only the tcgen05 instructions themselves with it: descriptors, TMEM addresses and loop counters then live in uniform
+// registers. Behind an `if (lane == 0)` the same values sit in vector registers of divergent code and every tcgen05.mma is
+// preceded by R2UR moves inside an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~90 cycles per issue, measured in attention backward).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }

@@ -466,17 +466,22 @@ def test_iwslt2023_recipe_float16_partial_freeze_training():
             x[i, :f] = torch.from_numpy(rng.randn(f, 768).astype(np.float32))
         b['encoder_input'] = x
         batches.append(b)
-    losses = []
-    for step in range(6):
+    # the training loss of a repeated batch is noisy (dropout 0.3 + attention dropout) and the recipe's lr is ~1e-7 during
+    # these steps: "the loss goes down" is checked on the dropout-free validation loss of the same batches, with the
+    # warm-up (and only the warm-up) shortened so that the recipe's peak lr is reached inside the test
+    trainer.scheduler.warmup = 4
+    valid_before = sum(trainer.valid_step(dict(b))['loss'] for b in batches)
+    for step in range(8):
         logs = trainer.train_step(iter(batches))
         assert 'overflow' not in logs and 'failed' not in logs and logs['loss_scale'] == 128.0
         assert logs['num_tokens'] == 2 * (sum(dec_lens) - len(dec_lens))
-        losses.append(logs['loss'])
-    assert losses[-1] < losses[0], losses
+        assert np.isfinite(logs['loss'])
+    valid_after = sum(trainer.valid_step(dict(b))['loss'] for b in batches)
+    assert valid_after < 0.98 * valid_before, (valid_before, valid_after)
     for n, p in model.named_parameters():
         if n in frozen_before:
             assert torch.equal(p.detach(), frozen_before[n]), n
     changed = [n for n in trained if not torch.equal(dict(model.named_parameters())[n].detach(), moved_before[n])]
-    # lr is still ~1e-7 (warm-up over 10 000 steps): every fp32 master weight moves, but not every update reaches half a float16 ulp
+    # every fp32 master weight moves; not every update has to reach half a float16 ulp
     assert (trainer.arena.master != master_before).float().mean().item() > 0.9
     assert len(changed) >= 0.5 * len(trained), (len(changed), len(trained))
