@@ -141,13 +141,14 @@ def relu_bits_supported(N: int, bias: Optional[Tensor]) -> bool:
 
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: int = 0,
                residual: Optional[Tensor] = None, out_dtype=None, tile_n: int = 0, cluster_m: int = 0,
-               relu_bits_out: Optional[Tensor] = None) -> Tensor:
+               relu_bits_out: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) (+ residual). relu_bits_out (int32 [N / 32, M], with act == 1): sign map
     of y for linear_dgrad(..., relu_bits=...)."""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and x.dtype in ELEM_DTYPES and w.dtype == x.dtype and x.is_contiguous() and w.is_contiguous()
-    y = torch.empty(M, N, dtype=out_dtype or x.dtype, device=x.device)
+    y = out if out is not None else torch.empty(M, N, dtype=out_dtype or x.dtype, device=x.device)
+    assert y.shape == (M, N) and y.is_contiguous()
     return gemm_raw(x.data_ptr(), w.data_ptr(), y, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, act=act,
                     residual=residual, split_k=1, tile_n=tile_n, cluster_m=cluster_m, relu_bits_out=relu_bits_out, elem_dtype=x.dtype)
 
