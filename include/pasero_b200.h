@@ -239,14 +239,15 @@ int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t target_stri
  *   pass 1, per chunk: pb200_ce_chunk_stats folds the chunk's logits (bf16 [B*T, chunk_cols], row stride ld) into row_state
  *           (fp32 [4][B*T]: running max, sum exp, sum of logits, target logit; chunk_begin == 0 initialises it);
  *   pb200_ce_chunk_finish: row_state -> stats ([0] loss, [1] nll, [2] tokens, [7] bad targets) and lse fp32 [B*T];
- *   pass 2, per chunk: pb200_ce_chunk_grad overwrites the recomputed chunk with d loss / d logits (the caller runs the
- *           chunk's dgrad / wgrad GEMMs on it). */
+ *   pass 2, per chunk: pb200_ce_chunk_grad overwrites the recomputed chunk with grad_scale * d loss / d logits (the caller
+ *           runs the chunk's dgrad / wgrad GEMMs on it; grad_scale: the loss scale of float16 training, 1 otherwise). */
 int pb200_ce_chunk_stats(const void* logits, int64_t ld, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
                          int64_t chunk_begin, int64_t chunk_cols, int64_t padding_idx, float* row_state, void* stream);
 int pb200_ce_chunk_finish(const float* row_state, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T, int64_t V,
                           int64_t padding_idx, float label_smoothing, double* stats, float* lse, void* stream);
 int pb200_ce_chunk_grad(void* logits, int64_t ld, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
-                        int64_t chunk_begin, int64_t chunk_cols, int64_t V, float label_smoothing, const float* lse, void* stream);
+                        int64_t chunk_begin, int64_t chunk_cols, int64_t V, float label_smoothing, float grad_scale,
+                        const float* lse, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer over the flat arenas (pasero/training.py:455-487; pasero/optimization.py:56-149, 390-427).

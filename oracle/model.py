@@ -9,6 +9,7 @@ PARITY PIN: tests/golden/st_tiny_*.pt were produced by tests/golden/make_golden.
 reference (imported from /root/reference) on seeded inputs; tests/test_oracle_cpu.py checks this file
 against those vectors (loss, logs, encoder output, logits and every parameter gradient).
 """
+import dataclasses
 import math
 from dataclasses import dataclass, field
 from typing import Optional
@@ -246,9 +247,22 @@ def compute_loss(cfg: STConfig, logits: Tensor, target: Tensor):
     return loss, logs
 
 
+def adapters_in_use(cfg: STConfig, side: str, meta: Optional[dict]):
+    """AdapterTransformer{Encoder,Decoder}.forward (pasero/models/adapters.py:186-197, 219-229): with `{side}_adapters_by`
+    (cfg.extra) the adapters of a batch are named after its language(s) / domain, `lang:<value>` or `domain:<value>`."""
+    by = cfg.extra.get(f'{side}_adapters_by') or ()
+    if not by:
+        return cfg.extra.get(f'{side}_adapters', ('default',))
+    return tuple(f"{'domain:' if key == 'domain' else 'lang:'}{meta[key]}" for key in by)
+
+
 def forward(cfg: STConfig, sd, encoder_input: Tensor, encoder_input_length: Tensor, decoder_input: Tensor,
-            layer_outputs: Optional[dict] = None):
+            layer_outputs: Optional[dict] = None, meta: Optional[dict] = None):
     """Transformer.forward, pasero/models/transformer.py:227-283: shift (target = dec[:, 1:], input = dec[:, :-1])."""
+    if cfg.extra.get('encoder_adapters_by') or cfg.extra.get('decoder_adapters_by'):
+        cfg = dataclasses.replace(cfg, extra={**cfg.extra, 'encoder_adapters_by': (), 'decoder_adapters_by': (),
+                                              'encoder_adapters': adapters_in_use(cfg, 'encoder', meta),
+                                              'decoder_adapters': adapters_in_use(cfg, 'decoder', meta)})
     target = decoder_input[:, 1:]
     dec_in = decoder_input[:, :-1]
     enc, mask = encode(cfg, sd, encoder_input, encoder_input_length, layer_outputs)

@@ -74,7 +74,10 @@ def train_step(cfg, sd: dict, batches: list, opt_state: dict, step: int, hp: dic
         sd[k].grad = None
     logs = {'loss': 0.0, 'nll_loss': 0.0, 'num_tokens': 0, 'num_lines': 0}
     for batch in batches:
-        loss, blogs = forward_fn(cfg, sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'])
+        # (`*_adapters_by`: the batch's meta selects the adapters, pasero/models/adapters.py:186-197; parameters of the
+        # others keep grad None and are skipped by clip_grad_norm_ and Adam below, like in the reference)
+        kw = {'meta': batch['meta']} if getattr(cfg, 'extra', {}).get('encoder_adapters_by') or getattr(cfg, 'extra', {}).get('decoder_adapters_by') else {}
+        loss, blogs = forward_fn(cfg, sd, batch['encoder_input'], batch['encoder_input_length'], batch['decoder_input'], **kw)
         loss.backward()
         for k, v in blogs.items():
             logs[k] += v

@@ -90,7 +90,7 @@ PROTOTYPES = {
                                       c_int32, _P, _P, _P]),
     'pb200_ce_chunk_stats': (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     'pb200_ce_chunk_finish': (c_int32, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
-    'pb200_ce_chunk_grad': (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
+    'pb200_ce_chunk_grad': (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float, _P, _P]),
     'pb200_grad32_flush': (c_int32, [_P, _P, _P, c_int32, c_int64, _P]),
     'pb200_grad_sqnorm_workspace_bytes': (c_size_t, []),
     'pb200_grad_sqnorm': (c_int32, [_P, c_int64, _P, _P, _P, c_size_t, _P]),

@@ -207,7 +207,7 @@ __global__ void ce_chunk_finish_kernel(const float* __restrict__ state, const lo
 // chunk of logits -> chunk of d loss / d logits, in place
 __global__ void __launch_bounds__(CE_THREADS)
 ce_chunk_grad_kernel(bf16* __restrict__ logits, long long ld, const long long* __restrict__ target, long long target_stride0,
-                     int T, int c0, int vc, int V, float eps, const float* __restrict__ lse) {
+                     int T, int c0, int vc, int V, float eps, float grad_scale, const float* __restrict__ lse) {
     const long long row = blockIdx.x;
     const long long tgt = target[(row / T) * target_stride0 + (row % T)];
     bf16* x = logits + row * ld;
@@ -228,7 +228,7 @@ ce_chunk_grad_kernel(bf16* __restrict__ logits, long long ld, const long long* _
             if (c0 + c + 1 == tgt) g1 -= hot;
             if (c >= vc) g0 = 0.f;
             if (c + 1 >= vc) g1 = 0.f;
-            o[j] = pack_bf16x2(g0, g1);
+            o[j] = pack_bf16x2(g0 * grad_scale, g1 * grad_scale);
         }
         reinterpret_cast<uint4*>(x)[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -276,13 +276,13 @@ extern "C" int pb200_ce_chunk_finish(const float* row_state, const int64_t* targ
 }
 
 extern "C" int pb200_ce_chunk_grad(void* logits, int64_t ld, const int64_t* target, int64_t target_stride0, int64_t B, int64_t T,
-                                   int64_t chunk_begin, int64_t chunk_cols, int64_t V, float label_smoothing, const float* lse,
-                                   void* stream_) {
+                                   int64_t chunk_begin, int64_t chunk_cols, int64_t V, float label_smoothing, float grad_scale,
+                                   const float* lse, void* stream_) {
     if (B * T == 0 || chunk_cols == 0) return 0;
     PB_CHECK(ld % 8 == 0 && ld >= (chunk_cols + 7) / 8 * 8 && lse, "ce_chunk_grad: ld must be a multiple of 8 covering the chunk");
     ce_chunk_grad_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
         (bf16*)logits, ld, (const long long*)target, target_stride0, (int)T, (int)chunk_begin, (int)chunk_cols, (int)V,
-        label_smoothing, lse);
+        label_smoothing, grad_scale, lse);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -488,11 +488,12 @@ def ce_chunk_finish(row_state: Tensor, target: Tensor, V: int, padding_idx: int,
 
 
 @_bracketed
-def ce_chunk_grad(logits: Tensor, target: Tensor, c0: int, cols: int, V: int, label_smoothing: float, lse: Tensor) -> None:
+def ce_chunk_grad(logits: Tensor, target: Tensor, c0: int, cols: int, V: int, label_smoothing: float, lse: Tensor,
+                  grad_scale: float = 1.0) -> None:
     B, T = target.shape
     _count(1)
     check(_lib.load(logits.dtype).pb200_ce_chunk_grad(logits.data_ptr(), logits.stride(0), target.data_ptr(), target.stride(0), B, T, c0, cols, V,
-                                          label_smoothing, lse.data_ptr(), stream_ptr()))
+                                          label_smoothing, grad_scale, lse.data_ptr(), stream_ptr()))
 
 
 _SQNORM_WS = {}

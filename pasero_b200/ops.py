@@ -759,9 +759,6 @@ class ProjCEFn(torch.autograd.Function):
         before = stats[0].clone()
         ctx.elem_dtype = x.dtype
         if V >= K.CE_CHUNK_MIN_VOCAB:
-            if ProjCEFn.loss_scale != 1.0:
-                raise NotImplementedError('loss scaling (dtype: float16) is not wired into the chunked projection + cross-entropy '
-                                          f'path (vocabularies >= {K.CE_CHUNK_MIN_VOCAB}); train those in bfloat16')
             ctx.chunked = True
             need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]   # (grad mode is off inside forward: ask autograd)
             dx32, dtable = ProjCEFn._chunked(x, table, target, padding_idx, label_smoothing, stats, V, need_grad)
@@ -777,7 +774,8 @@ class ProjCEFn(torch.autograd.Function):
     @staticmethod
     def _chunked(x, table, target, padding_idx, eps, stats, V, need_grad):
         """Both passes. Returns (dx fp32 [M, D] or None, dtable bf16 [rows, D] or None when it went into the Trainer's
-        fp32 main-gradient arena). Gradients are those of the summed loss (grad_output == 1); backward rescales otherwise."""
+        fp32 main-gradient arena). Gradients are those of the summed loss (grad_output == 1) times ProjCEFn.loss_scale (float16
+        training: the scale enters where d loss / d logits is written, like in the one-pass kernel); backward rescales otherwise."""
         M, D = x.shape
         cols = K.CE_CHUNK_COLS
         buf = torch.empty(M, cols, dtype=x.dtype, device=x.device)
@@ -800,7 +798,7 @@ class ProjCEFn(torch.autograd.Function):
         dtable = None if t32 is not None else torch.zeros_like(table)
         for c0, n in chunks:
             _, n8 = project(c0, n)
-            K.ce_chunk_grad(buf, target, c0, n, V, eps, lse)
+            K.ce_chunk_grad(buf, target, c0, n, V, eps, lse, grad_scale=ProjCEFn.loss_scale)
             g = buf[:, :n8]
             # dx += dlogits_c W_c (fp32 accumulation across the chunks), dW_c = dlogits_c^T x
             K.gemm_raw(g.data_ptr(), table[c0:c0 + n8].data_ptr(), dx32, M, D, n8, lda=cols, ldb=D, ldc=D, b_mn_major=True,

@@ -13,6 +13,7 @@ Design (B200-first, one process per GPU):
 """
 import math
 import os
+import re
 import time
 import traceback
 from collections import defaultdict
@@ -65,22 +66,80 @@ class LRScheduler:
         self.last_epoch = state['last_epoch']
 
 
+_ADAPTER_NAME = re.compile(r'^(encoder|decoder)\.layers\.\d+\.adapters\.([^.]+)\.')
+
+
+def adapter_group(name: str):
+    """('encoder' | 'decoder', adapter name) for an adapter parameter, None for every other parameter: the unit that is used
+    or unused as a whole in a step under `*_adapters_by` (pasero/models/adapters.py:186-197, 219-229 select one adapter name
+    per side for all layers)."""
+    m = _ADAPTER_NAME.match(name)
+    return (m.group(1), m.group(2)) if m else None
+
+
+def groups_in_use(keys: list, local, distributed: bool, host_group=None) -> list:
+    """The adapter groups that received a gradient on ANY rank in this step, in arena order (`local`: this rank's). The
+    union is formed on the host (CPU tensor over gloo): the GPU is not synchronised and every rank gets the same answer,
+    which DDP's find_unused_parameters obtains from an allreduced usage bitmap (pasero/training.py:236-250)."""
+    flags = torch.tensor([int(g in local) for g in keys], dtype=torch.int32)
+    if distributed and len(keys) > 0:
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=host_group)
+    return [g for g, f in zip(keys, flags.tolist()) if f]
+
+
+class PinnedRing:
+    """Pinned host staging buffers for small per-step H2D copies. An asynchronous copy reads pinned memory when it EXECUTES,
+    not when it is enqueued, and the host runs several steps ahead of the GPU (deferred logs): a single staging buffer would
+    hand step t the scalars of step t + k. Each slot is reused only after the copy enqueued from it has completed."""
+
+    def __init__(self, shape, dtype, slots: int = 8):
+        self.slots = [torch.zeros(shape, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+
+    def acquire(self) -> Tensor:
+        if self.events[self.i] is not None:
+            self.events[self.i].synchronize()
+        return self.slots[self.i]
+
+    def release(self) -> None:
+        """Call after the copies out of the acquired slot were enqueued on the current stream."""
+        event = torch.cuda.Event()
+        event.record()
+        self.events[self.i] = event
+        self.i = (self.i + 1) % len(self.slots)
+
+
 class ParamArena:
     """Flat storage for parameters and gradients (the model's 16-bit dtype), Adam moments (fp32) and — `master=True`: float16
     training with MixedPrecisionAdam / FlatFP16Adam semantics — an fp32 master copy of the parameters; parameters become views."""
 
-    def __init__(self, model: torch.nn.Module, device, dtype=BF16, master: bool = False):
+    def __init__(self, model: torch.nn.Module, device, dtype=BF16, master: bool = False, group_key=None):
+        """`group_key(name)` (optional): a hashable group for parameters that are only used in some steps (per-language /
+        per-domain adapters), None for the always-used rest. Groups are laid out contiguously — the always-used parameters
+        first, then one range per group (`group_ranges`) — so that the optimizer can step or skip a whole group with one launch."""
         self.params, self.names, self.offsets = [], [], []
         seen = set()
-        off = 0
+        entries = []
         for name, p in model.named_parameters():
             if not p.requires_grad or id(p) in seen:
                 continue
             seen.add(id(p))
+            entries.append((name, p, group_key(name) if group_key is not None else None))
+        order = {None: 0}
+        for _, _, g in entries:
+            order.setdefault(g, len(order))
+        entries.sort(key=lambda e: order[e[2]])       # stable: model order inside a group
+        off = 0
+        self.group_ranges = {}
+        for name, p, g in entries:
             self.params.append(p)
             self.names.append(name)
             self.offsets.append(off)
+            lo, _ = self.group_ranges.get(g, (off, off))
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            self.group_ranges[g] = (lo, off)
+        self.param_group = [g for _, _, g in entries]
         self.numel = off
         self.param = torch.zeros(off, dtype=dtype, device=device)
         self.grad = torch.zeros(off, dtype=dtype, device=device)
@@ -180,12 +239,17 @@ class GradBuckets:
         # (`reduce_behind_events`), so they run next to the rest of the replayed backward
         self.capture_events = None
         self.use_autograd_hooks = True   # set False when DirectGrads reports readiness itself (the hooks still fire)
+        # True when some parameters are unused in some steps (`*_adapters_by`): which buckets complete during backward then
+        # differs from rank to rank, and collectives must be issued in ONE order everywhere — every bucket waits for finish(),
+        # which launches them by index (torch DDP's find_unused_parameters answers the same question with an extra
+        # allreduce of a usage bitmap, pasero/training.py:236-250)
+        self.ordered = False
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(lambda param, i=i: self.param_ready(i) if self.use_autograd_hooks else None)
 
     def param_ready(self, i: int) -> None:
         """Parameter i's gradient for this micro-batch is complete; launch its bucket when it is the last one."""
-        if not self.enabled:
+        if not self.enabled or self.ordered:
             return
         b = self.param_bucket[i]
         if self.pending[b] < 0:
@@ -293,22 +357,32 @@ class Trainer:
         cfg.dp_size = self.dp_size
         self.update_freq = max(1, cfg.virtual_dp_size // self.dp_size)
         self.growth_interval = 2 ** 14 // self.update_freq
-        if getattr(model, 'find_unused_parameters', False):
-            # `*_adapters_by`: a different subset of the adapters is used from step to step. The reference skips Adam
-            # entirely for parameters without a gradient (per-parameter step counters, optimization.py:77-86) and DDP
-            # leaves globally unused gradients untouched; the flat-arena optimizer here updates every element every
-            # step, which would decay the idle adapters' moments and re-apply stale gradients. Refuse rather than
-            # silently train something else (the model itself runs: forward / backward parity is tested).
-            raise NotImplementedError('pasero_b200.Trainer does not cover encoder/decoder_adapters_by (parameters unused in '
-                                      'some steps); train with one adapter set per run (encoder_adapters / decoder_adapters)')
+        # `*_adapters_by` (pasero/models/adapters.py:74-105, 186-229): which adapters run depends on the batch's language /
+        # domain, so their parameters are unused in some steps. The reference's Adam keeps a step counter PER PARAMETER and
+        # skips parameters without a gradient (optimization.py:72-74, 112), DDP (find_unused_parameters) leaves globally
+        # unused gradients alone and clip_grad_norm_ only sees existing gradients. Here: the arena lays every adapter set
+        # ("group": side + adapter name) out contiguously, the 16-bit gradient arena is zeroed at the start of the step,
+        # every rank issues the gradient buckets in index order, the union over the ranks of the groups that received a
+        # gradient is formed on the HOST (a gloo allreduce of a bitmap: no GPU synchronisation) and Adam is launched per
+        # used group with that group's own step count / bias corrections; unused groups are not touched at all.
+        self.grouped = bool(getattr(model, 'find_unused_parameters', False))
         model.to(self.dtype)
         model.to(self.device)
         from . import reference_param_names
         ref_names = reference_param_names(model)     # before the arena: afterwards every parameter shares one storage
-        self.arena = ParamArena(model, self.device, self.dtype, master=self.master_weights)
+        self.arena = ParamArena(model, self.device, self.dtype, master=self.master_weights,
+                                group_key=adapter_group if self.grouped else None)
+        self.group_keys = [g for g in self.arena.group_ranges if g is not None]
+        self.group_steps = {g: 0 for g in self.group_keys}      # Adam's state['step'] of each group's parameters
+        self._group_of = {id(p): g for p, g in zip(self.arena.params, self.arena.param_group)}
+        self._stepped_groups = ()
+        self.host_group = None
+        if self.grouped and self.distributed and dist.get_backend() != 'gloo':
+            self.host_group = dist.new_group(backend='gloo')    # host-side bitmap of the groups in use, see above
         self.param_names = list(self.arena.names)
         # the reference's names of the TRAINABLE parameters: optimizer state is keyed by them (pasero/training.py:899-906)
         self.reference_names = [r for n in self.arena.names for r in ref_names[n]]
+        self._reference_group = {r: g for n, g in zip(self.arena.names, self.arena.param_group) for r in ref_names[n]}
         if self.distributed:  # identical initial weights on every rank (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.arena.param, src=0)
         # a communicator of its own for the gradient buckets, on HIGH-PRIORITY streams: the step's persistent GEMM kernels follow
@@ -325,6 +399,8 @@ class Trainer:
             except Exception:   # noqa: BLE001  (another backend / an old torch): the default group does the job
                 group = None
         self.buckets = GradBuckets(self.arena, cfg.bucket_bytes, group) if self.distributed else None
+        if self.buckets is not None:
+            self.buckets.ordered = self.grouped
         # parameter gradients go straight into the arena (no AccumulateGrad adds, no per-step memset)
         index = {id(p): i for i, p in enumerate(self.arena.params)}
         on_ready = (lambda p: self.buckets.param_ready(index[id(p)])) if self.buckets is not None else None
@@ -343,8 +419,10 @@ class Trainer:
         self.optimizer_steps = 0     # Adam's state['step']
         self.steps = 0
         self.metrics = metrics if metrics is not None else defaultdict(list)
-        self.hyper = torch.zeros(16, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        # row 0: the step scalars every kernel reads; rows 1..: the same with each adapter group's own Adam step count
+        self._hyper_all = torch.zeros(1 + len(self.group_keys), 16, dtype=torch.float32, device=self.device)
+        self.hyper = self._hyper_all[0]
+        self._hyper_ring = PinnedRing((1 + len(self.group_keys), 16), torch.float32)
         self.stats = model.stats_buffer(self.device)
         # ring of pinned host buffers: the logs of a step can be read after later steps were enqueued (pipelined loops)
         self._stats_ring = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(4)]
@@ -360,18 +438,22 @@ class Trainer:
         self.saved = True
 
     # ------------------------------------------------------------------ step pieces
-    def _write_hyper(self) -> None:
+    def _hyper_row(self, h: Tensor, t: int) -> None:
+        """The step scalars of csrc/optim.cu for Adam step count `t`, computed in fp64 like the reference's Python floats."""
         cfg = self.cfg
         lr = self.scheduler.get_last_lr()[0]
         b1, b2 = cfg.adam_betas
-        t = self.optimizer_steps + 1
         bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
-        h = self._hyper_host
         h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, cfg.adam_eps, cfg.weight_decay
         h[5], h[6], h[7], h[8] = bc1, math.sqrt(bc2), cfg.clip_norm, 1.0
         h[9], h[10], h[11], h[12] = 1 - b1, 1 - b2, lr / bc1, cfg.weight_decay * lr
         h[13], h[14] = 1.0 / self.loss_scale, float(self.master_weights)
-        self.hyper.copy_(h, non_blocking=True)
+
+    def _write_hyper(self) -> None:
+        h = self._hyper_ring.acquire()
+        self._hyper_row(h[0], self.optimizer_steps + 1)
+        self.hyper.copy_(h[0], non_blocking=True)
+        self._hyper_ring.release()
 
     def move_to_device(self, batch: dict) -> dict:
         """utils.move_to_device(batch, 'cuda', dtype) (pasero/utils.py:691-702): float tensors are cast to bf16."""
@@ -399,10 +481,36 @@ class Trainer:
             ops.ProjCEFn.loss_scale = 1.0
         return logs
 
-    def _optimizer_kernels(self) -> None:
+    def _groups_in_use(self, local) -> list:
+        return groups_in_use(self.group_keys, local, self.distributed, self.host_group)
+
+    def _optimizer_kernels(self, local_groups=None) -> None:
         K.grad_sqnorm(self.arena.grad, self.hyper, self.stats)
-        K.adam_step(self.arena.param, self.arena.grad, self.arena.exp_avg, self.arena.exp_avg_sq, self.hyper, self.stats,
-                    master=self.arena.master)
+        a = self.arena
+        if not self.grouped:
+            K.adam_step(a.param, a.grad, a.exp_avg, a.exp_avg_sq, self.hyper, self.stats, master=a.master)
+            return
+        # per-group Adam (see __init__): the always-used parameters with the global step count, then every adapter group
+        # some rank used, with its own; a group nobody used keeps parameters, moments and step count as they are
+        if local_groups is None:
+            local_groups = {self._group_of[i] for i in self.direct.written if i in self._group_of}
+        used = self._groups_in_use(local_groups)
+        launches = []
+        base = a.group_ranges.get(None)
+        if base is not None and base[1] > base[0]:
+            launches.append((0, base))
+        if used:
+            h = self._hyper_ring.acquire()
+            for g in used:
+                row = 1 + self.group_keys.index(g)
+                self._hyper_row(h[row], self.group_steps[g] + 1)
+                launches.append((row, a.group_ranges[g]))
+            self._hyper_all[1:].copy_(h[1:], non_blocking=True)
+            self._hyper_ring.release()
+        for row, (lo, hi) in launches:
+            K.adam_step(a.param[lo:hi], a.grad[lo:hi], a.exp_avg[lo:hi], a.exp_avg_sq[lo:hi], self._hyper_all[row], self.stats,
+                        master=a.master[lo:hi] if a.master is not None else None)
+        self._stepped_groups = tuple(used)
 
     # ------------------------------------------------------------------ the step
     def train_step(self, batch_iterator: Iterator[dict]) -> dict:
@@ -417,6 +525,8 @@ class Trainer:
         main loop does on `status.failed()`."""
         self.model.train()
         self.stats.zero_()
+        if self.grouped:
+            self.arena.grad.zero_()      # gradients of the adapters this step does not use must read as zero (see __init__)
         ops.DirectGrads.active = self.direct
         self.direct.start_step()
         failed = 0
@@ -562,6 +672,9 @@ class Trainer:
             return LazyLogs(self, host, event, self.scheduler.get_last_lr()[0], overflow=True)
         self.scheduler.step()
         self.optimizer_steps += 1
+        for g in self._stepped_groups:
+            self.group_steps[g] += 1
+        self._stepped_groups = ()
         self.steps += 1
         self.saved = False
         host = self._stats_ring[self.steps % len(self._stats_ring)]
@@ -639,8 +752,10 @@ class Trainer:
             finally:
                 if self.buckets is not None:
                     self.buckets.capture_events = None
-            self._graphs[key] = (graph, static, events, stats_event)
-        graph, static, events, stats_event = self._graphs[key]
+            # (a replay runs no Python: the adapter groups this batch shape + meta writes gradients for are noted now)
+            groups = {self._group_of[i] for i in self.direct.written if i in self._group_of} if self.grouped else None
+            self._graphs[key] = (graph, static, events, stats_event, groups)
+        graph, static, events, stats_event, groups = self._graphs[key]
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
         self._write_hyper()
@@ -650,11 +765,13 @@ class Trainer:
             self.buckets.reduce_behind_events(events, self.stats, stats_event)
         elif self.buckets is not None:
             self.buckets.allreduce_all(self.stats)
-        self._optimizer_kernels()
+        self._optimizer_kernels(groups)
         return self._finish_step()
 
     def _graph_body(self, static: dict, extras: dict, after_forward=None) -> None:
         self.stats.zero_()
+        if self.grouped:
+            self.arena.grad.zero_()
         ops.DirectGrads.active = self.direct
         self.direct.start_step()
         batch = dict(static)
@@ -704,7 +821,12 @@ class Trainer:
         optimizer state by parameter *name* (pasero/training.py:899-906)."""
         m, v = self._named_state(self.arena.exp_avg), self._named_state(self.arena.exp_avg_sq)
         names = list(m)
-        state = {k: {'step': self.optimizer_steps, 'exp_avg': m[k], 'exp_avg_sq': v[k]} for k in names}
+
+        def steps_of(name):     # adapter groups (`*_adapters_by`) count their own steps, like the reference's per-parameter state
+            g = self._reference_group.get(name)
+            return self.optimizer_steps if g is None else self.group_steps[g]
+        # (a parameter that never received a gradient has no optimizer state in the reference: optimization.py:72-74)
+        state = {k: {'step': steps_of(k), 'exp_avg': m[k], 'exp_avg_sq': v[k]} for k in names if steps_of(k) > 0 or not self.grouped}
         group = {'lr': self.scheduler.get_last_lr()[0], 'betas': tuple(self.cfg.adam_betas), 'eps': self.cfg.adam_eps,
                  'weight_decay': self.cfg.weight_decay, 'amsgrad': False, 'params': names}
         return {'state': state, 'param_groups': [group]}
@@ -750,7 +872,17 @@ class Trainer:
             state = opt['optimizer']['state']
             self._load_named_state(self.arena.exp_avg, {k: v['exp_avg'] for k, v in state.items()})
             self._load_named_state(self.arena.exp_avg_sq, {k: v['exp_avg_sq'] for k, v in state.items()})
-            self.optimizer_steps = next(iter(state.values()))['step'] if state else 0
+            base = [v['step'] for k, v in state.items() if self._reference_group.get(k) is None]
+            self.optimizer_steps = int(base[0]) if base else max((int(v['step']) for v in state.values()), default=0)
+            for g in self.group_keys:
+                steps = [int(v['step']) for k, v in state.items() if self._reference_group.get(k) == g]
+                self.group_steps[g] = steps[0] if steps else 0
+            if self.grouped:     # groups without an entry were never stepped: their moments are zero
+                absent = [g for g in self.group_keys if self.group_steps[g] == 0]
+                for g in absent:
+                    lo, hi = self.arena.group_ranges[g]
+                    self.arena.exp_avg[lo:hi].zero_()
+                    self.arena.exp_avg_sq[lo:hi].zero_()
             self.scheduler.load_state_dict(opt['scheduler'])
             if self.fp16 and opt.get('scaler'):
                 self.loss_scale = float(opt['scaler']['scale'])

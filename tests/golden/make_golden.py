@@ -40,7 +40,7 @@ def import_reference():
     return pasero
 
 
-def make_task_and_model(pasero, tmp, extra=(), adapters=False):
+def make_task_and_model(pasero, tmp, extra=(), adapters=False, by_langs=False):
     from pasero.config import TrainingConfig, get_task_class, get_architecture
     dict_path = os.path.join(tmp, 'dict.txt')
     with open(dict_path, 'w') as f:
@@ -54,11 +54,16 @@ def make_task_and_model(pasero, tmp, extra=(), adapters=False):
             '--encoder-attention-heads', str(t['heads']), '--decoder-attention-heads', str(t['heads']),
             '--input-dim', '80', '--conv-input-dim', '80', '--conv-channels', str(t['conv_channels']),
             '--conv-kernel-sizes', '5', '5', '--data-dir', tmp, '--dict', 'dict.txt', '--tokenizer-path', 'bpecodes',
-            '--source-lang', 'de', '--target-lang', 'en', '--model-dir', os.path.join(tmp, 'model'),
+            '--model-dir', os.path.join(tmp, 'model'),
             '--encoder-max-len', '3000', '--batch-size', '64000', '--dropout', '0', '--label-smoothing', '0.1',
             '--metrics', '--early-stopping-metric', 'nll_loss', '--max-steps', '1000', '--valid-interval', '1000',
             '--dataset-type', 'simple', '--dtype', 'float32', '--lr', str(synth.TRAIN['lr']),
-            '--warmup', str(synth.TRAIN['warmup']), '--seed', '1234'] + list(extra)
+            '--warmup', str(synth.TRAIN['warmup']), '--seed', '1234']
+    if by_langs:
+        args += ['--source-langs', *synth.BY_LANGS['encoder'], '--target-langs', *synth.BY_LANGS['decoder']]
+    else:
+        args += ['--source-lang', 'de', '--target-lang', 'en']
+    args += list(extra)       # (later occurrences of an option win)
     cfg = TrainingConfig(*args)
     task = get_task_class(cfg.task)(cfg.data_dir, cfg.task_cfg)
     task.setup_for_model(cfg.model_cfg)
@@ -66,8 +71,9 @@ def make_task_and_model(pasero, tmp, extra=(), adapters=False):
     torch.manual_seed(1234)
     model = get_architecture(cfg.model_cfg)(cfg.model_cfg, cfg, task)
     # seeded, reference-independent weights (bf16-representable), so the fixtures need not carry them
-    sd = synth.adapter_state_dict() if adapters else synth.tiny_state_dict()
-    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == (synth.adapter_param_shapes() if adapters else synth.tiny_param_shapes())
+    sd = synth.by_adapter_state_dict() if by_langs else synth.adapter_state_dict() if adapters else synth.tiny_state_dict()
+    assert {k: tuple(v.shape) for k, v in model.named_parameters()} == (synth.by_adapter_param_shapes() if by_langs else
+                                                                        synth.adapter_param_shapes() if adapters else synth.tiny_param_shapes())
     missing = model.load_state_dict(sd, strict=False)
     assert all('_float_tensor' in k for k in missing.missing_keys) and not missing.unexpected_keys, missing
     return cfg, task, model
@@ -416,6 +422,60 @@ def golden_training_curve(pasero, cfg, task, model, out):
     print('training golden: first', rows[0], 'last', rows[-1])
 
 
+def golden_training_adapters_by(pasero, tmp, out):
+    """`--encoder-adapters-by source_lang --decoder-adapters-by target_lang` through the reference's Trainer.train_step (CPU,
+    fp32): the language pair changes from step to step (synth.BY_SCHEDULE), so every step leaves some adapter sets without a
+    gradient. Recorded: per-step logs, which parameters each step changed, the optimizer's per-parameter step counts and
+    moments at the end."""
+    from pasero.training import Trainer
+    from pasero import utils
+    bt = synth.BY_TRAIN
+    cfg, task, model = make_task_and_model(pasero, tmp, ('--arch', 'adapter_transformer', '--encoder-adapter-dim', str(synth.ADAPTER_DIM),
+                                                         '--decoder-adapter-dim', str(synth.ADAPTER_DIM),
+                                                         '--encoder-adapters-by', 'source_lang', '--decoder-adapters-by', 'target_lang',
+                                                         '--lr', str(bt['lr']), '--warmup', str(bt['warmup']),
+                                                         '--model-dir', os.path.join(tmp, 'model_by')), by_langs=True)
+    assert model.find_unused_parameters
+    os.makedirs(cfg.model_dir, exist_ok=True)
+    metrics = utils.Metrics()
+    current = {}
+    orig_update = metrics.update
+
+    def update(name, value, *a, **kw):
+        current[name] = value
+        return orig_update(name, value, *a, **kw)
+    metrics.update = update
+    trainer = Trainer(cfg, task, model, metrics, None)
+    rows, changed = [], []
+    for step in range(bt['steps']):
+        b = synth.by_train_batch(step)
+        before = {k: v.detach().clone() for k, v in model.named_parameters() if v.requires_grad}
+        current.clear()
+        trainer.train_step(iter([{k: (v.clone() if torch.is_tensor(v) else dict(v)) for k, v in b.items()}]))
+        rows.append({k: float(current[k]) for k in ('loss', 'nll_loss', 'num_tokens', 'num_lines', 'gnorm', 'lr')})
+        changed.append(sorted({adapter_set(k) for k, v in model.named_parameters()
+                               if v.requires_grad and not torch.equal(before[k], v.detach())}))
+    opt = {n: trainer.optimizer.state[p] for n, p in model.named_parameters() if p in trainer.optimizer.state and trainer.optimizer.state[p]}
+    trainer.save()
+    ck = torch.load(os.path.join(cfg.model_dir, f"optimizer_{bt['steps']}.bin"), map_location='cpu', weights_only=False)
+    torch.save({
+        'train': bt, 'schedule': synth.BY_SCHEDULE, 'curve': rows, 'changed': changed,
+        'optimizer_steps': {n: int(s['step']) for n, s in opt.items()},
+        'optimizer_checkpoint_steps': {str(k): int(v['step']) for k, v in ck['optimizer']['state'].items()},
+        'exp_avg': {n: synth.summarize_grad(s['exp_avg']) for n, s in opt.items()},
+        'params_final': {k: synth.summarize_grad(v.detach()) for k, v in model.named_parameters() if v.requires_grad},
+        'trainable': [k for k, v in model.named_parameters() if v.requires_grad],
+    }, os.path.join(out, 'st_adapters_by_train.pt'))
+    print('adapters_by training golden: first', rows[0], 'last', rows[-1])
+    print('  changed per step:', changed[:8])
+    print('  step counts:', sorted({(adapter_set(n), s) for n, s in ((n, int(s['step'])) for n, s in opt.items())}))
+
+
+def adapter_set(name: str) -> str:
+    parts = name.split('.')
+    return f"{parts[0]}/{parts[parts.index('adapters') + 1]}" if 'adapters' in parts else 'base'
+
+
 DECODE_CASES = [dict(name='beam5', beam_size=5, max_output_len=12, prompt=False, len_penalty=1.0),
                 dict(name='greedy', beam_size=1, max_output_len=12, prompt=False, len_penalty=1.0),
                 dict(name='beam3_prompt', beam_size=3, max_output_len=9, prompt=True, len_penalty=0.7),
@@ -555,6 +615,13 @@ def main():
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'adapters_by':  # only the per-language adapter training fixture
+        tmp = tempfile.mkdtemp()
+        try:
+            golden_training_adapters_by(pasero, tmp, out)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'whisper':      # only the Whisper-style fixture
         tmp = tempfile.mkdtemp()
         try:
@@ -576,6 +643,7 @@ def main():
         cfg3, task3, model3 = make_whisper_model(pasero, tmp)
         golden_model_whisper(pasero, cfg3, task3, model3, out)
         golden_model_adapters(pasero, tmp, out)
+        golden_training_adapters_by(pasero, tmp, out)
         golden_model_text(pasero, tmp, out)
         golden_preprocess_tags(pasero, tmp, out)
         golden_numpy_file(pasero, out)

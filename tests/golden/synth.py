@@ -237,6 +237,64 @@ def adapter_state_dict() -> dict:
     return sd
 
 
+# ---- per-language adapters (`--encoder-adapters-by source_lang --decoder-adapters-by target_lang`, adapters.py:74-105,
+# 186-229): one adapter set per source language in the encoder and per target language in the decoder; a batch only uses (and
+# only trains) the sets of its own language pair, so every step leaves some parameters without a gradient
+BY_LANGS = {'encoder': ('de', 'it'), 'decoder': ('en', 'fr')}
+# language pair of each training step (cycled): 'fr' first appears at step 3, 'it' at step 2, and (it, fr) only once per cycle,
+# so the adapter sets' Adam step counts drift apart
+BY_SCHEDULE = [('de', 'en'), ('de', 'en'), ('it', 'en'), ('de', 'fr'), ('de', 'en'), ('it', 'fr'), ('de', 'en'), ('it', 'en')]
+BY_TRAIN = dict(lr=1e-3, warmup=10, steps=40)
+
+
+def by_adapter_param_shapes() -> dict:
+    t = TINY
+    d = t['embed_dim']
+    shapes = dict(tiny_param_shapes())
+    for side, n in (('encoder', t['encoder_layers']), ('decoder', t['decoder_layers'])):
+        for i in range(n):
+            for lang in BY_LANGS[side]:
+                p = f'{side}.layers.{i}.adapters.lang:{lang}'
+                shapes[p + '.down.weight'] = (ADAPTER_DIM, d)
+                shapes[p + '.down.bias'] = (ADAPTER_DIM,)
+                shapes[p + '.up.weight'] = (d, ADAPTER_DIM)
+                shapes[p + '.up.bias'] = (d,)
+                shapes[p + '.layer_norm.weight'] = (d,)
+                shapes[p + '.layer_norm.bias'] = (d,)
+    return shapes
+
+
+def by_adapter_state_dict() -> dict:
+    sd = dict(tiny_state_dict())
+    rng = np.random.RandomState(56)
+    for name, shape in by_adapter_param_shapes().items():
+        if name in sd:
+            continue
+        if 'layer_norm' in name:
+            w = (1.0 + 0.1 * rng.randn(*shape)) if name.endswith('weight') else 0.05 * rng.randn(*shape)
+        elif name.endswith('bias'):
+            w = 0.02 * rng.randn(*shape)
+        else:
+            w = rng.randn(*shape) * shape[1] ** -0.5
+        sd[name] = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+    return sd
+
+
+_TRAIN_BATCHES = None
+
+
+def by_train_batch(step: int) -> dict:
+    """The batch of training step `step`: the seeded batches of train_batches(), tagged with the step's language pair."""
+    global _TRAIN_BATCHES
+    if _TRAIN_BATCHES is None:
+        _TRAIN_BATCHES = train_batches()
+    batches = _TRAIN_BATCHES
+    b = dict(batches[step % len(batches)])
+    src, tgt = BY_SCHEDULE[step % len(BY_SCHEDULE)]
+    b['meta'] = {'source_lang': src, 'target_lang': tgt}
+    return b
+
+
 # ---- text-input variant (BASELINE configs 1 / 5 family: `--task translation`, token-id encoder sharing its embedding
 # table with the decoder and the output projection; pasero/models/transformer.py:610-752)
 def text_param_shapes() -> dict:

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pasero_b200.training import GradBuckets, ParamArena
+from pasero_b200.training import GradBuckets, ParamArena, adapter_group, groups_in_use
 
 
 def _free_port() -> int:
@@ -89,6 +89,93 @@ def _worker(rank: int, world: int, port: int, q):
         q.put((rank, repr(e)))
     finally:
         dist.destroy_process_group()
+
+
+class Adapter(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.down = torch.nn.Linear(32, 8)
+        self.up = torch.nn.Linear(8, 32)
+
+
+class Layer(torch.nn.Module):
+    def __init__(self, names):
+        super().__init__()
+        self.fc = torch.nn.Linear(32, 32)
+        self.adapters = torch.nn.ModuleDict({n: Adapter() for n in names})
+
+
+class ByLang(torch.nn.Module):
+    """Parameter names of an AdapterTransformer with `encoder_adapters_by: source_lang`, `decoder_adapters_by: target_lang`."""
+    def __init__(self):
+        super().__init__()
+        self.encoder = torch.nn.Module()
+        self.encoder.layers = torch.nn.ModuleList([Layer(['lang:de', 'lang:it']) for _ in range(2)])
+        self.decoder = torch.nn.Module()
+        self.decoder.layers = torch.nn.ModuleList([Layer(['lang:en', 'lang:fr']) for _ in range(2)])
+
+
+def _worker_by(rank: int, world: int, port: int, q):
+    """`*_adapters_by`: rank 0 trains a (de, en) batch, rank 1 an (it, en) batch. Buckets are issued in index order on every
+    rank (their completion order during backward differs), gradients of adapters a rank did not use enter the sum as zeros,
+    and the union of the groups in use is the same on both ranks."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = ByLang().to(torch.bfloat16)
+        arena = ParamArena(model, 'cpu', group_key=adapter_group)
+        keys = [g for g in arena.group_ranges if g is not None]
+        assert keys == [('encoder', 'lang:de'), ('encoder', 'lang:it'), ('decoder', 'lang:en'), ('decoder', 'lang:fr')]
+        # layout: the always-used parameters first, then one contiguous range per group, covering the arena
+        spans = [arena.group_ranges[None]] + [arena.group_ranges[g] for g in keys]
+        assert spans[0][0] == 0 and spans[-1][1] == arena.numel and all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+        for i, name in enumerate(arena.names):
+            lo, hi = arena.group_ranges[adapter_group(name)]
+            assert lo <= arena.offsets[i] < hi and arena.param_group[i] == adapter_group(name)
+        buckets = GradBuckets(arena, bucket_bytes=2 * 1024)
+        buckets.ordered = True
+        assert len(buckets.buckets) >= 4
+        mine = {('encoder', 'lang:de' if rank == 0 else 'lang:it'), ('decoder', 'lang:en')}
+        arena.grad.zero_()          # what the Trainer does at the start of a step in this mode
+        buckets.start_step(sync=True)
+        order = reversed(range(len(arena.params))) if rank == 0 else range(len(arena.params))    # different completion orders
+        for i in order:
+            g = arena.param_group[i]
+            if g is None or g in mine:
+                arena.view(arena.grad, i).fill_(float(rank + 1))
+                buckets.param_ready(i)
+        assert buckets.launch_order == []            # nothing before finish()
+        buckets.finish(None)
+        assert buckets.launch_order == list(range(len(buckets.buckets)))
+        want = {None: 3.0, ('encoder', 'lang:de'): 1.0, ('encoder', 'lang:it'): 2.0, ('decoder', 'lang:en'): 3.0, ('decoder', 'lang:fr'): 0.0}
+        for i, name in enumerate(arena.names):
+            g = arena.view(arena.grad, i).float()
+            assert torch.all(g == want[arena.param_group[i]]), (name, g.unique())
+        used = groups_in_use(keys, mine, True)
+        assert used == [('encoder', 'lang:de'), ('encoder', 'lang:it'), ('decoder', 'lang:en')], used
+        q.put((rank, 'ok'))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(worker):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: 'ok', 1: 'ok'}, results
+
+
+def test_adapters_by_world2_gloo():
+    _run(_worker_by)
 
 
 def test_bucketed_allreduce_world2_gloo():

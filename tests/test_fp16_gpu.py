@@ -67,6 +67,84 @@ def test_loss_scale_enters_the_loss_gradient():
     tk._close(gs, 128.0 * x.grad, 128e-3, 1e-2, 'scaled d loss / d logits')
 
 
+@pytest.mark.parametrize('V,D,M,cols', [(40003, 256, 96, 8192), (1003, 128, 77, 256)])
+def test_loss_scale_enters_the_chunked_projection_ce(V, D, M, cols):
+    """float16 + a vocabulary of chunked size (the NLLB dictionary of the IWSLT2023 recipe: 256 k entries): the loss scale is
+    applied where the chunk's d loss / d logits is written (pb200_ce_chunk_grad), so dx and the table gradient are the scaled
+    gradients of fp32 PyTorch, and the loss itself is unscaled."""
+    import torch.nn.functional as F
+    from pasero_b200 import kernels as K, modules, ops
+    saved = (K.CE_CHUNK_MIN_VOCAB, K.CE_CHUNK_COLS, ops.ProjCEFn.loss_scale)
+    emb = modules.Embedding(V, D, 1).to(F16).cuda()
+    g = torch.Generator(device='cuda').manual_seed(6)
+    x0 = (torch.randn(M, D, generator=g, device='cuda') * 2).to(F16)
+    target = torch.randint(4, V, (1, M), generator=g, device='cuda')
+    target[0, -3:] = 1
+    scale = 128.0
+    try:
+        K.CE_CHUNK_MIN_VOCAB, K.CE_CHUNK_COLS = 1, cols
+        ops.ProjCEFn.loss_scale = scale
+        x = x0.clone().requires_grad_(True)
+        stats = torch.zeros(8, dtype=torch.float64, device='cuda')
+        loss = ops.ProjCEFn.apply(x, emb.weight, target, 1, 0.1, stats, V)
+        loss.backward()
+    finally:
+        K.CE_CHUNK_MIN_VOCAB, K.CE_CHUNK_COLS, ops.ProjCEFn.loss_scale = saved
+    xr = x0.float().requires_grad_(True)
+    wr = emb.weight.detach().float()[:V].requires_grad_(True)
+    ref = F.cross_entropy(xr @ wr.T, target.reshape(-1), ignore_index=1, reduction='sum', label_smoothing=0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) / ref.item() < 5e-3
+    assert x.grad.dtype == F16 and torch.isfinite(x.grad).all() and torch.isfinite(emb.weight.grad).all()
+    tk._close(x.grad.float(), scale * xr.grad, 2e-2 * scale * xr.grad.abs().max().item(), 2e-2, 'scaled dx')
+    tk._close(emb.weight.grad.float()[:V], scale * wr.grad, 2e-2 * scale * wr.grad.abs().max().item(), 3e-2, 'scaled dtable')
+
+
+def test_trainer_float16_large_vocabulary():
+    """dtype float16 + FlatFP16Adam on a model whose vocabulary takes the chunked projection + CE path (V >= 32 768): the
+    combination the IWSLT2023 recipe trains with its real NLLB dictionary. Loss per step within 1 % of the oracle's float16
+    step with master weights, same loss-scale trajectory, no overflow."""
+    from oracle import model as om
+    from oracle import optim as oo
+    from pasero_b200 import TrainingConfig, build_model, kernels as K
+    from pasero_b200.task import Dictionary, SpeechTranslationTask
+    from pasero_b200.training import Trainer
+    import numpy as np
+    V = 33000
+    assert V >= K.CE_CHUNK_MIN_VOCAB
+    t = synth.TINY
+    cfg = tiny_training_cfg(dtype='float16', memory_efficient_fp16=False, flat_fp16=True, seed=1)
+    task = SpeechTranslationTask(cfg, Dictionary(tokens=[f'tok{i}' for i in range(V - 4)]))
+    torch.manual_seed(7)
+    model = build_model(cfg, task)
+    sd0 = {k: v.detach().clone().half().float() for k, v in model.state_dict().items() if v.is_floating_point() and '_float_tensor' not in k}
+    model.load_state_dict(sd0, strict=False)
+    trainer = Trainer(cfg, task, model)
+    rng = np.random.RandomState(8)
+    batches = []
+    for b in synth.train_batches()[:4]:
+        b = dict(b)
+        dec = b['decoder_input'].clone()
+        body = dec >= 4
+        dec[body] = torch.from_numpy(rng.randint(4, V, int(body.sum())))
+        b['decoder_input'] = dec
+        batches.append(b)
+    import dataclasses
+    ocfg = dataclasses.replace(tiny_cfg(), vocab_size=V)
+    sd = {k: v.clone().to(F16).requires_grad_(True) for k, v in sd0.items()}
+    hp = dict(lr=synth.TRAIN['lr'], warmup=synth.TRAIN['warmup'], max_steps=1000, clip_norm=1.0)
+    scaler, ostate = oo.LossScaler(), {}
+    master = {k: v.detach().float().clone() for k, v in sd.items()}
+    for step in range(6):
+        ob = {k: (v.to(F16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in batches[step % 4].items()}
+        want = oo.fp16_train_step(ocfg, sd, [ob], ostate, step, hp, om.forward, scaler, master=master)
+        logs = trainer.train_step(iter([batches[step % 4]]))
+        assert 'overflow' not in logs and logs['num_tokens'] == want['num_tokens']
+        assert abs(logs['loss'] - want['loss']) / want['loss'] < 1e-2, (step, logs['loss'], want['loss'])
+        assert abs(logs['gnorm'] - want['gnorm']) / want['gnorm'] < 5e-2, (step, logs['gnorm'], want['gnorm'])
+        assert trainer.loss_scale == scaler.scale
+
+
 @pytest.mark.parametrize('master', [False, True])
 def test_adam_float16_variants_and_skipped_step(master):
     """optimization.Adam on float16 parameters (16-bit rounding points: unscale, normalise, clip) and the fp32 master copy of

@@ -192,6 +192,47 @@ def test_adapter_variant_matches_reference():
     assert all(sd[k].grad is None for k in sd if k not in gold['trainable'])
 
 
+def by_cfg() -> om.STConfig:
+    return tiny_cfg(extra={'encoder_adapters_by': ('source_lang',), 'decoder_adapters_by': ('target_lang',)})
+
+
+def adapter_set(name: str) -> str:
+    parts = name.split('.')
+    return f"{parts[0]}/{parts[parts.index('adapters') + 1]}" if 'adapters' in parts else 'base'
+
+
+def test_adapters_by_training_matches_reference():
+    """`--encoder-adapters-by source_lang --decoder-adapters-by target_lang` (pasero/models/adapters.py:74-105, 186-229)
+    through 40 optimizer steps whose language pair changes from step to step: the adapter sets a step does not use keep
+    parameters, Adam moments and their per-parameter step count (optimization.py:72-74, 112), the others follow the
+    reference's own run (CPU, fp32) — logs of every step, which sets changed, final step counts, moments and parameters."""
+    gold = torch.load(os.path.join(GOLD, 'st_adapters_by_train.pt'), weights_only=False)
+    cfg = by_cfg()
+    sd = {k: v.clone().requires_grad_(k in gold['trainable']) for k, v in synth.by_adapter_state_dict().items()}
+    hp = dict(lr=gold['train']['lr'], warmup=gold['train']['warmup'], max_steps=1000, clip_norm=1.0)
+    state = {}
+    for step in range(gold['train']['steps']):
+        before = {k: sd[k].detach().clone() for k in gold['trainable']}
+        logs = oo.train_step(cfg, sd, [synth.by_train_batch(step)], state, step, hp, om.forward)
+        want = gold['curve'][step]
+        assert logs['num_tokens'] == want['num_tokens'] and abs(logs['lr'] - want['lr']) < 1e-12
+        assert abs(logs['loss'] - want['loss']) / want['loss'] < 1e-4, step
+        assert abs(logs['gnorm'] - want['gnorm']) / want['gnorm'] < 1e-3, step
+        changed = sorted({adapter_set(k) for k in gold['trainable'] if not torch.equal(before[k], sd[k].detach())})
+        assert changed == gold['changed'][step], (step, changed, gold['changed'][step])
+    assert {k: v['step'] for k, v in state.items()} == gold['optimizer_steps']
+    # The reference's checkpoint labels optimizer state by zipping ALL trainable names with the state entries in the order
+    # they were created (pasero/training.py:903) — with adapters that are first used at different steps the labels end up on
+    # the wrong parameters (same multiset of step counts, different owners). Recorded here as a known defect of the reference;
+    # pasero_b200 writes each entry under the name of the parameter it belongs to (tests/test_parity_gpu.py).
+    assert sorted(gold['optimizer_checkpoint_steps'].values()) == sorted(gold['optimizer_steps'].values())
+    assert gold['optimizer_checkpoint_steps'] != gold['optimizer_steps']
+    for name, d in gold['exp_avg'].items():
+        _check_digest(name, state[name]['exp_avg'], d, rtol=2e-3, atol=1e-6)
+    for name, d in gold['params_final'].items():
+        _check_digest(name, sd[name], d, rtol=1e-4, atol=2e-5)
+
+
 def test_text_encoder_variant_matches_reference():
     """Token-id encoder with shared embeddings (`--task translation`): BASELINE configs 1 / 5 family."""
     gold = torch.load(os.path.join(GOLD, 'st_text_model.pt'), weights_only=False)

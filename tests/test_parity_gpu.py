@@ -249,6 +249,125 @@ def test_adapter_variant_matches_reference_and_trains_only_adapters():
     assert trainer.arena.numel < sum(p.numel() for p in model2.parameters()) // 4     # the arenas hold the adapters only
 
 
+def by_training_cfg(**kw):
+    bt = synth.BY_TRAIN
+    return tiny_training_cfg(arch='adapter_transformer', encoder_adapter_dim=synth.ADAPTER_DIM, decoder_adapter_dim=synth.ADAPTER_DIM,
+                             encoder_adapters_by=['source_lang'], decoder_adapters_by=['target_lang'],
+                             source_langs=list(synth.BY_LANGS['encoder']), target_langs=list(synth.BY_LANGS['decoder']),
+                             lr=bt['lr'], warmup=bt['warmup'], **kw)
+
+
+def by_build(**kw):
+    from pasero_b200 import build_model
+    cfg = by_training_cfg(**kw)
+    task = tiny_task(cfg)
+    model = build_model(cfg, task)
+    missing = model.load_state_dict(synth.by_adapter_state_dict(), strict=False)
+    assert not missing.unexpected_keys and all('_float_tensor' in k for k in missing.missing_keys), missing
+    return cfg, task, model
+
+
+def group_label(g) -> str:
+    return f'{g[0]}/{g[1]}'
+
+
+@pytest.mark.parametrize('graphed', [False, True])
+def test_adapters_by_training_matches_oracle_and_reference(graphed, tmp_path):
+    """`encoder_adapters_by: source_lang`, `decoder_adapters_by: target_lang` (pasero/models/adapters.py:74-105, 186-229):
+    40 steps whose language pair changes from step to step. Against the golden run of the unmodified reference: which adapter
+    sets each step changes and every set's final Adam step count (per-parameter `state['step']`, optimization.py:72-112).
+    Sets a step does not use must keep parameters AND both moments bit-identical. Loss per step within 1 % of the oracle run
+    with the reference's bf16 semantics. Then the checkpoint: per-name step counts, and a bit-identical resume."""
+    from oracle import model as om
+    from oracle import optim as oo
+    from pasero_b200.training import Trainer
+    from tests.test_oracle_cpu import by_cfg
+    gold = torch.load(os.path.join(GOLD, 'st_adapters_by_train.pt'), weights_only=False)
+    cfg, task, model = by_build(seed=1, model_dir=str(tmp_path))
+    assert model.find_unused_parameters and sorted(k for k, p in model.named_parameters() if p.requires_grad) == sorted(gold['trainable'])
+    trainer = Trainer(cfg, task, model)
+    a = trainer.arena
+    assert sorted(group_label(g) for g in trainer.group_keys) == sorted({s for c in gold['changed'] for s in c})
+    # oracle, bf16 semantics (bf16 parameters, fp32 moments, parameter rounded back every step)
+    sd = {k: (v.clone().to(BF16).requires_grad_(True) if k in gold['trainable'] else v.clone().to(BF16))
+          for k, v in synth.by_adapter_state_dict().items()}
+    hp = dict(lr=gold['train']['lr'], warmup=gold['train']['warmup'], max_steps=1000, clip_norm=1.0)
+    ostate = {}
+    steps = gold['train']['steps']
+    for step in range(steps):
+        batch = synth.by_train_batch(step)
+        obatch = {k: (v.to(BF16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in batch.items()}
+        want = oo.train_step(by_cfg(), sd, [obatch], ostate, step, hp, om.forward)
+        before = [t.clone() for t in (a.param, a.exp_avg, a.exp_avg_sq)]
+        if graphed:
+            logs = trainer.train_step_graphed(trainer.move_to_device(batch))
+        else:
+            logs = trainer.train_step(iter([batch]))
+        assert logs['num_tokens'] == gold['curve'][step]['num_tokens']
+        assert abs(logs['lr'] - gold['curve'][step]['lr']) < 1e-12
+        assert abs(logs['loss'] - want['loss']) / want['loss'] < 1e-2, (step, logs['loss'], want['loss'])
+        assert abs(logs['gnorm'] - want['gnorm']) / want['gnorm'] < 5e-2, (step, logs['gnorm'], want['gnorm'])
+        src, tgt = synth.BY_SCHEDULE[step % len(synth.BY_SCHEDULE)]
+        in_use = {('encoder', f'lang:{src}'), ('decoder', f'lang:{tgt}')}
+        changed = []
+        for g in trainer.group_keys:
+            lo, hi = a.group_ranges[g]
+            same = [torch.equal(b[lo:hi], t[lo:hi]) for b, t in zip(before, (a.param, a.exp_avg, a.exp_avg_sq))]
+            if g in in_use:
+                assert not same[1] and not same[2], (step, g)       # moments always move (lr(0) = 0 only freezes the parameters)
+                if not same[0]:
+                    changed.append(group_label(g))
+            else:
+                assert all(same), (step, g, same)
+        assert sorted(changed) == gold['changed'][step], (step, changed, gold['changed'][step])
+    want_steps = {}
+    for name, n in gold['optimizer_steps'].items():
+        parts = name.split('.')
+        want_steps[(parts[0], parts[parts.index('adapters') + 1])] = n
+    assert trainer.group_steps == want_steps
+    # checkpoint: every entry under its own parameter's name, with that parameter's step count
+    trainer.save()
+    opt = torch.load(tmp_path / f'optimizer_{steps}.bin', weights_only=False)
+    assert {k: v['step'] for k, v in opt['optimizer']['state'].items()} == gold['optimizer_steps']
+    nxt = synth.by_train_batch(steps)
+    ref_logs = dict(trainer.train_step(iter([nxt])))
+    cfg2, task2, model2 = by_build(seed=1, model_dir=str(tmp_path))
+    t2 = Trainer(cfg2, task2, model2)
+    t2.load(str(tmp_path))
+    assert t2.group_steps == want_steps and t2.steps == steps
+    logs2 = t2.train_step(iter([nxt]))
+    assert abs(logs2['loss'] - ref_logs['loss']) < 1e-9 * max(1.0, abs(ref_logs['loss']))
+    assert torch.equal(t2.arena.param, trainer.arena.param) and torch.equal(t2.arena.exp_avg, trainer.arena.exp_avg)
+
+
+def test_adapters_by_with_trainable_base_and_accumulation():
+    """`train_all_params` + `*_adapters_by` + gradient accumulation over two language pairs: the base parameters step every
+    time (global step count), the adapter sets only when one of the step's micro-batches used them; eager == oracle."""
+    from oracle import model as om
+    from oracle import optim as oo
+    from pasero_b200.training import Trainer
+    from tests.test_oracle_cpu import by_cfg
+    cfg, task, model = by_build(seed=1, train_all_params=True, virtual_dp_size=2)
+    trainer = Trainer(cfg, task, model)
+    assert trainer.update_freq == 2 and trainer.arena.group_ranges[None][1] > 0
+    sd = {k: v.clone().to(BF16).requires_grad_(True) for k, v in synth.by_adapter_state_dict().items()}
+    hp = dict(lr=synth.BY_TRAIN['lr'], warmup=synth.BY_TRAIN['warmup'], max_steps=1000, clip_norm=1.0)
+    ostate = {}
+    for step in range(12):
+        pair = [synth.by_train_batch(2 * step), synth.by_train_batch(2 * step + 1)]
+        opair = [{k: (v.to(BF16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in b.items()} for b in pair]
+        want = oo.train_step(by_cfg(), sd, opair, ostate, step, hp, om.forward)
+        logs = trainer.train_step(iter(pair))
+        assert logs['num_tokens'] == want['num_tokens']
+        assert abs(logs['loss'] - want['loss']) / want['loss'] < 1e-2, (step, logs['loss'], want['loss'])
+        assert abs(logs['gnorm'] - want['gnorm']) / want['gnorm'] < 5e-2, (step, logs['gnorm'], want['gnorm'])
+    assert trainer.optimizer_steps == 12
+    for g, n in trainer.group_steps.items():
+        name = f'{g[0]}.layers.0.adapters.{g[1]}.down.weight'
+        assert ostate[name]['step'] == n, (g, n, ostate[name]['step'])
+    assert len(set(trainer.group_steps.values())) > 1
+
+
 def test_text_encoder_variant_matches_reference():
     """Token-id encoder sharing its embedding table with the decoder and the output projection (`--task translation`,
     BASELINE configs 1 / 5 family): activations, loss and gradients against the reference's golden vectors, and two

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 
 from tests.golden import synth
-from tests.test_parity_gpu import build
+from tests.test_parity_gpu import build, by_build
 
 
 def main():
@@ -19,11 +19,20 @@ def main():
     from pasero_b200.training import Trainer
     batches = synth.train_batches()
     steps = 4
+    # `adapters_by`: per-language adapters (encoder_adapters_by / decoder_adapters_by): the ranks of one step train different
+    # language pairs, i.e. different adapter sets, and some sets are used by no rank at all
+    by = 'adapters_by' in sys.argv[1:]
+    if by:
+        steps = 6
+        batches = [synth.by_train_batch(i) for i in range(steps * world)]
+        build_fn = by_build
+    else:
+        build_fn = build
     # `float16` as the first argument: the same check with dtype float16 + FlatFP16Adam (loss scaling, fp32 master weights)
     extra = dict(dtype='float16', memory_efficient_fp16=False, flat_fp16=True) if 'float16' in sys.argv[1:] else {}
     results = {}
     for mode in ('eager', 'graph'):
-        cfg, task, model = build(seed=1, bucket_bytes=64 * 1024, **extra)
+        cfg, task, model = build_fn(seed=1, bucket_bytes=(4 if by else 64) * 1024, **extra)
         trainer = Trainer(cfg, task, model)
         assert trainer.distributed and trainer.dp_size == world and len(trainer.buckets.buckets) > 3
         logs_all = []
@@ -34,9 +43,9 @@ def main():
             else:
                 logs = trainer.train_step(iter([b]))
             logs_all.append(dict(logs.items()))
-        results[mode] = (trainer.arena.param.clone(), logs_all, trainer.arena.grad.float().clone())
+        results[mode] = (trainer.arena.param.clone(), logs_all, trainer.arena.grad.float().clone(), dict(trainer.group_steps))
     # reference: one process, the ranks' batches as micro-batches
-    cfg, task, model = build(seed=1, virtual_dp_size=world, **extra)
+    cfg, task, model = build_fn(seed=1, virtual_dp_size=world, **extra)
     ref = Trainer(cfg, task, model, data_parallel=False)
     ref.update_freq = world
     ref_logs = []
@@ -45,7 +54,8 @@ def main():
         ref_logs.append(dict(ref.train_step(iter(mb)).items()))
     ok = True
     ref_grad = ref.arena.grad.float()
-    for mode, (param, logs_all, grad) in results.items():
+    for mode, (param, logs_all, grad, group_steps) in results.items():
+        assert group_steps == ref.group_steps, (mode, group_steps, ref.group_steps)
         # the reduced gradients of the last step themselves (the parameters barely move at this learning rate)
         gdiff = ((grad - ref_grad).abs().max() / ref_grad.abs().max()).item()
         diff = (param.float() - ref.arena.param.float()).abs().max().item()
@@ -66,7 +76,7 @@ def main():
     dist.broadcast(p0, 0)
     assert torch.equal(p, p0), 'ranks diverged'
     if rank == 0:
-        print('DDP CHECK', 'float16' if extra else 'bfloat16', 'OK' if ok else 'FAILED')
+        print('DDP CHECK', 'float16' if extra else 'bfloat16', 'adapters_by ' + str(ref.group_steps) if by else '', 'OK' if ok else 'FAILED')
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
