@@ -107,6 +107,19 @@ class WgradStream:
         cls._forked = side
 
     @classmethod
+    def run_behind(cls, fn):
+        """Runs fn() on the side stream BEHIND everything forked so far and everything already on the current stream, without
+        making the current stream wait (the gradient-bucket flush: it needs the bucket's weight-gradient GEMMs, which are all
+        on the side stream already, not the other way round — a join here would stall the dependent chain of backward until
+        the side stream has drained, once per bucket). Returns the stream fn ran on: the side stream, or the current stream
+        when the second stream is disabled."""
+        if not cls.enabled:
+            fn()
+            return torch.cuda.current_stream()
+        cls.run(fn)
+        return cls._forked
+
+    @classmethod
     def join(cls) -> None:
         """The current stream waits for every forked GEMM (call before anything reads the fp32 main gradients)."""
         if cls._forked is not None:

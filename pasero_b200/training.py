@@ -187,6 +187,14 @@ class ParamArena:
         if ranges[1] > 0:
             K.grad32_flush(self.grad32, self.grad, ranges[0], ranges[1])
 
+    def flush32_behind(self, ranges: tuple):
+        """The same for one gradient bucket in the middle of backward, on the weight-gradient stream: ordered behind the
+        bucket's GEMMs (already queued there) and behind the current stream's work so far, while the current stream carries on
+        with the rest of backward. Returns the stream on which the bucket's 16-bit gradients are final."""
+        if not self.grad.is_cuda:
+            return None
+        return ops.WgradStream.run_behind(lambda: K.grad32_flush(self.grad32, self.grad, ranges[0], ranges[1]) if ranges[1] > 0 else None)
+
     def rebind_grads(self) -> None:
         for i, p in enumerate(self.params):
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + self.offsets[i] * 2:
@@ -260,14 +268,17 @@ class GradBuckets:
 
     def _launch(self, b: int) -> None:
         lo, hi = self.buckets[b]
-        if self.pre_launch is not None:
-            self.pre_launch(b)
+        # pre_launch may finish the bucket on another stream (the fp32 -> 16-bit flush behind the weight-gradient GEMMs): that
+        # stream, not the current one, is what the allreduce has to wait for
+        final = self.pre_launch(b) if self.pre_launch is not None else None
+        if final is None and self.cuda:
+            final = torch.cuda.current_stream()
         if self.capture_events is not None:
             event = torch.cuda.Event(external=True)
-            event.record()
+            event.record(final)
             self.capture_events.append((b, event))
         elif self.cuda:
-            self.stream.wait_stream(torch.cuda.current_stream())
+            self.stream.wait_stream(final)
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         else:
@@ -287,8 +298,9 @@ class GradBuckets:
         if self.pre_all is not None:
             self.pre_all()
         elif self.pre_launch is not None:
-            for b in range(len(self.buckets)):
-                self.pre_launch(b)
+            finals = {self.pre_launch(b) for b in range(len(self.buckets))} - {None}
+            for s in finals:
+                torch.cuda.current_stream().wait_stream(s)
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
@@ -413,7 +425,7 @@ class Trainer:
         if self.buckets is not None:
             self.buckets.use_autograd_hooks = False
             bucket_ranges = [self.arena.ranges32(lo, hi) for lo, hi in self.buckets.buckets]
-            self.buckets.pre_launch = lambda b: self.arena.flush32(bucket_ranges[b])
+            self.buckets.pre_launch = lambda b: self.arena.flush32_behind(bucket_ranges[b])
             self.buckets.pre_all = lambda: self.arena.flush32(self._ranges32_all)
         self.scheduler = LRScheduler(cfg)
         self.optimizer_steps = 0     # Adam's state['step']
@@ -567,6 +579,7 @@ class Trainer:
             # the failure flag and skips the update, so their content no longer matters — only the order of the collectives)
         if self.buckets is not None:
             self.buckets.finish(self.stats)
+            ops.WgradStream.join()      # (finish() may have flushed its buckets on the weight-gradient stream)
         else:
             self.arena.flush32(self._ranges32_all)
         self._write_hyper()
@@ -749,6 +762,7 @@ class Trainer:
                     self._graph_body(static, extras, after_forward=stats_event.record if overlap else None)
                     if overlap:
                         self.buckets.finish(None)
+                        ops.WgradStream.join()      # finish() flushed the remaining buckets on the weight-gradient stream
             finally:
                 if self.buckets is not None:
                     self.buckets.capture_events = None

@@ -98,6 +98,14 @@ def test_collate_bit_exact_with_reference():
     for k in ('decoder_input', 'prompt_mask', 'prompt_length', 'indices', 'encoder_input_length'):
         assert np.array_equal(col[k].numpy(), g['collate_' + k]), k
     assert np.array_equal(col['encoder_input'].double().sum(dim=(1, 2)).numpy(), g['collate_encoder_input_sum'])
+    # ... and element-wise: row i is sample i's feature matrix followed by zeros up to the batch's longest utterance
+    # (utils.tokens_as_tensor, pasero/utils.py:709-736), in the order the golden `indices` fix
+    assert col['encoder_input'].shape == (len(small), max(len(s['encoder_input']) for s in small), 80)
+    for i, sample in enumerate(small):
+        n = len(sample['encoder_input'])
+        assert col['indices'][i] == sample['index'] and col['encoder_input_length'][i] == n
+        assert np.array_equal(col['encoder_input'][i, :n].numpy(), np.asarray(sample['encoder_input'], dtype=np.float32))
+        assert not col['encoder_input'][i, n:].any()
     assert task.collate([], 1, torch.float32) is None
 
 

@@ -251,10 +251,12 @@ def test_adapter_variant_matches_reference_and_trains_only_adapters():
 
 def by_training_cfg(**kw):
     bt = synth.BY_TRAIN
-    return tiny_training_cfg(arch='adapter_transformer', encoder_adapter_dim=synth.ADAPTER_DIM, decoder_adapter_dim=synth.ADAPTER_DIM,
-                             encoder_adapters_by=['source_lang'], decoder_adapters_by=['target_lang'],
-                             source_langs=list(synth.BY_LANGS['encoder']), target_langs=list(synth.BY_LANGS['decoder']),
-                             lr=bt['lr'], warmup=bt['warmup'], **kw)
+    opts = dict(arch='adapter_transformer', encoder_adapter_dim=synth.ADAPTER_DIM, decoder_adapter_dim=synth.ADAPTER_DIM,
+                encoder_adapters_by=['source_lang'], decoder_adapters_by=['target_lang'],
+                source_langs=list(synth.BY_LANGS['encoder']), target_langs=list(synth.BY_LANGS['decoder']),
+                lr=bt['lr'], warmup=bt['warmup'])
+    opts.update(kw)
+    return tiny_training_cfg(**opts)
 
 
 def by_build(**kw):

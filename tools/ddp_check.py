@@ -25,7 +25,9 @@ def main():
     if by:
         steps = 6
         batches = [synth.by_train_batch(i) for i in range(steps * world)]
-        build_fn = by_build
+
+        def build_fn(**kw):     # the base check's learning rate: the parameters barely move, so the last step's reduced
+            return by_build(lr=synth.TRAIN['lr'], warmup=synth.TRAIN['warmup'], **kw)    # gradients stay comparable
     else:
         build_fn = build
     # `float16` as the first argument: the same check with dtype float16 + FlatFP16Adam (loss scaling, fp32 master weights)
