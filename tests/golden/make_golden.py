@@ -341,6 +341,26 @@ def golden_batching(pasero, task, out):
     print('batching goldens:', combos)
 
 
+def golden_batching_by(pasero, task, out):
+    """TrainingDataset.buffered_batching with `batch_by` (pasero/datasets.py:708-730; set by cli/train.py:275 from the model's
+    `batch_by` when adapters are selected per language): every batch holds one (source, target) language pair, and the
+    collated batch keeps exactly the meta entries its samples share (tasks/task.py:531-571)."""
+    from pasero import datasets
+    samples = synth.batching_samples_by_lang()
+    ds = types.SimpleNamespace(batch_by={'source_lang', 'target_lang'}, task=task, shuffle=True, batch_size=4000)
+    np.random.seed(synth.BATCHING_SEED)
+    batches = datasets.TrainingDataset.buffered_batching(ds, list(samples))
+    langs = [{(s['meta']['source_lang'], s['meta']['target_lang']) for s in b} for b in batches]
+    assert all(len(x) == 1 for x in langs)
+    col = task.collate(batches[0], padding_idx=task.padding_idx, dtype=torch.float32, model_type='encoder_decoder')
+    assert 'uid' not in col['meta'] and set(col['meta']) == {'source_lang', 'target_lang'}, col['meta']
+    np.savez_compressed(os.path.join(out, 'batching_by.npz'),
+                        flat=np.array([s['meta']['uid'] for b in batches for s in b], dtype=np.int64),
+                        index=np.array([s['index'] for b in batches for s in b], dtype=np.int64),
+                        sizes=np.array([len(b) for b in batches], dtype=np.int64))
+    print('batching-by-language golden:', len(batches), 'batches,', sorted({next(iter(x)) for x in langs}))
+
+
 def golden_model(pasero, cfg, task, model, out):
     model.train()
     batch = synth.model_batch()
@@ -615,9 +635,11 @@ def main():
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         return
-    if len(sys.argv) > 1 and sys.argv[1] == 'adapters_by':  # only the per-language adapter training fixture
+    if len(sys.argv) > 1 and sys.argv[1] == 'adapters_by':  # only the per-language adapter fixtures (batching + training)
         tmp = tempfile.mkdtemp()
         try:
+            cfg, task, model = make_task_and_model(pasero, tmp)
+            golden_batching_by(pasero, task, out)
             golden_training_adapters_by(pasero, tmp, out)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
@@ -636,6 +658,7 @@ def main():
     try:
         cfg, task, model = make_task_and_model(pasero, tmp)
         golden_batching(pasero, task, out)
+        golden_batching_by(pasero, task, out)
         golden_model(pasero, cfg, task, model, out)
         golden_decoding(pasero, cfg, task, model, out)
         cfg2, task2, model2 = make_task_and_model(pasero, tmp)

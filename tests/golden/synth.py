@@ -11,6 +11,7 @@ TINY = dict(vocab_size=200, encoder_layers=2, decoder_layers=2, embed_dim=128, f
 TRAIN = dict(lr=2e-4, warmup=50, steps=200, clip_norm=1.0, label_smoothing=0.1)
 FBANK_CASES = {'noise': 8000, 'tone': 12000, 'single_frame': 400}
 BATCHING_SEED = 7
+BY_LANGS = {'encoder': ('de', 'it'), 'decoder': ('en', 'fr')}      # per-language adapter fixtures, see below
 PAD, EOS, BOS = 1, 2, 2
 
 
@@ -43,6 +44,16 @@ def batching_samples(n: int = 5000, real_features: int = 64) -> list:
         samples.append({'encoder_input': feats, 'decoder_input': dec, 'prompt_mask': pm,
                         'meta': {'source_lang': 'de', 'target_lang': 'en'}})
     return samples
+
+
+def batching_samples_by_lang(n: int = 1200) -> list:
+    """The first n samples of the batching parity set, spread over 2 source x 2 target languages (a fixed function of the
+    sample number) and tagged with a 'uid' (the `index` field the batcher writes is local to a language group)."""
+    out = []
+    for i, s in enumerate(batching_samples(n, real_features=0)):
+        src, tgt = BY_LANGS['encoder'][(i // 3) % 2], BY_LANGS['decoder'][(i // 7) % 2]
+        out.append({**s, 'meta': {'source_lang': src, 'target_lang': tgt, 'uid': i}})
+    return out
 
 
 def _batch(rng, frames, dec_lens) -> dict:
@@ -240,7 +251,6 @@ def adapter_state_dict() -> dict:
 # ---- per-language adapters (`--encoder-adapters-by source_lang --decoder-adapters-by target_lang`, adapters.py:74-105,
 # 186-229): one adapter set per source language in the encoder and per target language in the decoder; a batch only uses (and
 # only trains) the sets of its own language pair, so every step leaves some parameters without a gradient
-BY_LANGS = {'encoder': ('de', 'it'), 'decoder': ('en', 'fr')}
 # language pair of each training step (cycled): 'fr' first appears at step 3, 'it' at step 2, and (it, fr) only once per cycle,
 # so the adapter sets' Adam step counts drift apart
 BY_SCHEDULE = [('de', 'en'), ('de', 'en'), ('it', 'en'), ('de', 'fr'), ('de', 'en'), ('it', 'fr'), ('de', 'en'), ('it', 'en')]

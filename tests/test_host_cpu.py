@@ -89,6 +89,22 @@ def test_bucketing_bit_exact_with_reference(bs, mult, lines):
     assert np.array_equal(np.array([len(b) for b in batches]), g[key + '_sizes'])
 
 
+def test_batch_by_language_bit_exact_with_reference():
+    """`batch_by` (what `*_adapters_by` models ask the batcher for, cli/train.py:275): batches of one language pair each, in the
+    reference's order; the collated batch carries the shared meta entries (the adapters are selected from them) and only those."""
+    g = np.load(os.path.join(GOLD, 'batching_by.npz'))
+    task = tiny_task()
+    np.random.seed(synth.BATCHING_SEED)
+    batches = task.buffered_batching(list(synth.batching_samples_by_lang()), batch_by=('source_lang', 'target_lang'), batch_size=4000)
+    assert np.array_equal(np.array([s['meta']['uid'] for b in batches for s in b]), g['flat'])
+    assert np.array_equal(np.array([s['index'] for b in batches for s in b]), g['index'])
+    assert np.array_equal(np.array([len(b) for b in batches]), g['sizes'])
+    for b in batches[:20]:
+        col = task.collate(b, padding_idx=task.padding_idx, dtype=torch.float32)
+        shared = {k: v for k, v in b[0]['meta'].items() if all(s['meta'].get(k) == v for s in b)}
+        assert col['meta'] == shared and {'source_lang', 'target_lang'} <= set(shared) and (len(b) == 1 or 'uid' not in shared)
+
+
 def test_collate_bit_exact_with_reference():
     g = np.load(os.path.join(GOLD, 'batching.npz'))
     task = tiny_task()
