@@ -113,6 +113,32 @@ def test_registry_binding_builds_and_exchanges_checkpoints(pasero, tmp_path, arc
     assert not result.missing_keys and not result.unexpected_keys
 
 
+def test_registry_binding_per_language_adapters(pasero, tmp_path):
+    """`--encoder-adapters-by source_lang --decoder-adapters-by target_lang` through the reference's registry and its own task
+    object (whose corpora define the languages, models/adapters.py:74-105): the same adapter sets under the same keys, the same
+    `batch_by` / `find_unused_parameters` the reference's `AdapterTransformer` hands to cli/train.py:275 and to DDP, and the
+    adapters of the batch's language pair selected from `meta` (adapters.py:186-197, 219-229)."""
+    from pasero_b200.training import adapter_group
+    from pasero_b200.transformer import _select_adapters
+    tmp = str(tmp_path)
+    extra = ('--source-langs', 'de', 'it', '--target-langs', 'en', 'fr', '--encoder-adapters-by', 'source_lang',
+             '--decoder-adapters-by', 'target_lang', '--encoder-adapter-dim', '16', '--decoder-adapter-dim', '16')
+    cfg_r, task_r, ref_model = build_through_registry(tmp, 'adapter_transformer', extra)
+    cfg_o, task_o, our_model = build_through_registry(tmp, 'adapter_transformer_b200', extra)
+    assert shapes(our_model.state_dict()) == shapes(ref_model.state_dict())
+    assert our_model.find_unused_parameters is True and ref_model.find_unused_parameters is True
+    assert sorted(our_model.batch_by) == sorted(ref_model.batch_by) == ['source_lang', 'target_lang']
+    trainable = {n for n, p in our_model.named_parameters() if p.requires_grad}
+    assert trainable == {n for n, p in ref_model.named_parameters() if p.requires_grad}
+    assert {adapter_group(n) for n in trainable} == {('encoder', 'lang:de'), ('encoder', 'lang:it'), ('decoder', 'lang:en'),
+                                                     ('decoder', 'lang:fr')}
+    meta = {'source_lang': 'it', 'target_lang': 'fr'}
+    _select_adapters(our_model.encoder.layers, our_model.cfg.encoder_adapters_by, meta)
+    _select_adapters(our_model.decoder.layers, our_model.cfg.decoder_adapters_by, meta)
+    assert all(tuple(layer.adapters_in_use) == ('lang:it',) for layer in our_model.encoder.layers)
+    assert all(tuple(layer.adapters_in_use) == ('lang:fr',) for layer in our_model.decoder.layers)
+
+
 def test_reference_training_config_is_adopted(pasero, tmp_path):
     """`Trainer(cfg, ...)` receives the reference's own TrainingConfig at cli/train.py:287."""
     from pasero.config import TrainingConfig as RefTrainingConfig
