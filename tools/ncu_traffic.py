@@ -26,6 +26,8 @@ for r in rows[h + 1:]:
 def family(name: str) -> str:
     if 'gemm_kernel' in name or 'splitk' in name:
         return 'gemm'
+    if 'gemm_ln' in name:
+        return 'linear_ln_fused'
     if 'attn' in name:
         return 'attention'
     if 'ln_' in name or 'dropout_add' in name or 'reduce_partials' in name:
