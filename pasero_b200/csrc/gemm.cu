@@ -861,8 +861,13 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     } else {
         memset(&tc, 0, sizeof(tc));
     }
-    if (!a_mn) rc = make_tmap(&ta, q->a, q->m, q->k, q->lda, Zall, q->a_batch_stride, BK, BM);
-    else rc = make_tmap(&ta, q->a, q->k, q->m, q->lda, Zall, q->a_batch_stride, 64, BK);
+    // An operand shared by all batches (batch stride 0: the conv weight of the batched implicit GEMM) is described as ONE matrix:
+    // a map with Zall slices would claim Zall x its size, i.e. memory past the end of the allocation (never addressed by the
+    // kernel, which passes slice 0 for such an operand, but the extent a descriptor claims should be memory that exists).
+    const long long Za = (Zall > 1 && q->a_batch_stride != 0) ? Zall : 1;
+    const long long Zb = (Zall > 1 && q->b_batch_stride != 0) ? Zall : 1;
+    if (!a_mn) rc = make_tmap(&ta, q->a, q->m, q->k, q->lda, Za, q->a_batch_stride, BK, BM);
+    else rc = make_tmap(&ta, q->a, q->k, q->m, q->lda, Za, q->a_batch_stride, 64, BK);
     if (rc) return rc;
     // cluster size along M (B-tile multicast); 2 keeps every SM usable (4-CTA clusters strand SMs on this part)
     int cl = q->cluster_m > 0 ? q->cluster_m : 2;
@@ -873,8 +878,8 @@ extern "C" int pb200_gemm_bf16(const pb200_gemm_params* q, void* stream_) {
     if (cl == 4 && b_mn && bn == 128) cl = 2;
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     if (epi == 7 && cl == 4) cl = 2;
-    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zall, q->b_batch_stride, BK, bn == 512 ? 128 : bn / cl);
-    else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zall, q->b_batch_stride, 64, BK);
+    if (!b_mn) rc = make_tmap(&tb, q->b, q->n, q->k, q->ldb, Zb, q->b_batch_stride, BK, bn == 512 ? 128 : bn / cl);
+    else rc = make_tmap(&tb, q->b, q->k, q->n, q->ldb, Zb, q->b_batch_stride, 64, BK);
     if (rc) return rc;
 
     GemmDev d;

@@ -418,6 +418,32 @@ def _linear_dropout_add_ln(a: Tensor, w: Tensor, b: Optional[Tensor], residual: 
     return out, s, mean, rstd, keep
 
 
+class GradCell:
+    """Running sum of the gradients that several autograd nodes owe ONE tensor — the encoder output, read by the
+    cross-attention of every decoder layer. Autograd would add the nodes' contributions with one elementwise kernel per extra
+    consumer (five [B*S, D] adds per step for six decoder layers); instead each node's key / value dgrad GEMM takes the running
+    sum as its residual operand (added in the GEMM epilogue), the nodes return None for that input, and the last one to run
+    hands autograd the total. Counting down `remaining` makes the result independent of the order the engine picks."""
+
+    def __init__(self, consumers: int):
+        self.remaining, self.acc = consumers, None
+
+    def contribute(self, fn):
+        """fn(residual or None) -> this node's gradient plus the residual. Returns the total for the last node, else None."""
+        self.acc = fn(self.acc)
+        self.remaining -= 1
+        if self.remaining > 0:
+            return None
+        total, self.acc = self.acc, None
+        return total
+
+
+def _dkey(dkv: Tensor, w_kv: Tensor, cell: Optional[GradCell]):
+    if cell is None:
+        return K.linear_dgrad(dkv, w_kv)
+    return cell.contribute(lambda acc: K.linear_dgrad(dkv, w_kv, residual=acc))
+
+
 class AttnSublayerFn(torch.autograd.Function):
     """Post-norm attention sub-block in one autograd node: LN(x + dropout(MHA(x, key))) (pasero/models/transformer.py
     :1021-1054, 1246-1289). Compared with AttentionFn followed by DropoutAddLNFn, the backward gets the out-projection
@@ -425,9 +451,11 @@ class AttnSublayerFn(torch.autograd.Function):
     dgrad GEMM (no column-sum pass over dy, no separate add kernel)."""
 
     @staticmethod
-    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps, key_bias=True, attn_p=0.0):
+    def forward(ctx, x, key, in_w, in_b, out_w, out_b, gamma, beta, kv_len, B, Lq, Lk, H, causal, scale, p, eps, key_bias=True, attn_p=0.0,
+                key_grad_cell=None):
         D = H * 64
         ctx.key_bias = key_bias
+        ctx.key_grad_cell = key_grad_cell
         x = _c(x)
         self_attn = key is None
         if self_attn:
@@ -467,12 +495,12 @@ class AttnSublayerFn(torch.autograd.Function):
                 dkvq = torch.empty(B * Lq, 3 * D, dtype=dy.dtype, device=dy.device)
                 K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale,
                                 dkvq[:, 2 * D:], dkvq[:, :D], dkvq[:, D:2 * D], dropout=ctx.drop)
-                return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
+                return (K.linear_dgrad(dkvq, in_w, residual=dres), None, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 12
             dq = torch.empty(B * Lq, D, dtype=dy.dtype, device=dy.device)
             dkv = torch.empty(B * Lk, 2 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
-            dkey = K.linear_dgrad(dkv, in_w[:2 * D]) if need[1] else None
-            return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 11
+            dkey = _dkey(dkv, in_w[:2 * D], ctx.key_grad_cell) if need[1] else None
+            return (K.linear_dgrad(dq, in_w[2 * D:], residual=dres), dkey, None, None, d_out_w, d_out_b, dgamma, dbeta) + (None,) * 12
         sink_w, acc_w = _sink(p_in_w)
         sink_b, acc_b = _sink(p_in_b)
         w32 = _sink32(p_in_w)
@@ -498,7 +526,7 @@ class AttnSublayerFn(torch.autograd.Function):
             dkv = torch.empty(B * Lk, 2 * D, dtype=dy.dtype, device=dy.device)
             K.attention_bwd(d_o, q2, k2, v2, o, lse, B, H, Lq, Lk, kv_len, causal, scale, dq, dkv[:, :D], dkv[:, D:], dropout=ctx.drop)
             dx = K.linear_dgrad(dq, in_w[2 * D:], residual=dres)
-            dkey = K.linear_dgrad(dkv, in_w[:2 * D])
+            dkey = _dkey(dkv, in_w[:2 * D], ctx.key_grad_cell) if need[1] else None
             if kb:
                 _wgrad_bias(dkv, key_c, d_in_w[:2 * D], acc_w, b32[:2 * D] if b32 is not None else None, d_in_b[:2 * D], acc_b)
             else:
@@ -506,8 +534,7 @@ class AttnSublayerFn(torch.autograd.Function):
                 K.colsum(dkv[:, D:], out=(b32 if b32 is not None else d_in_b)[D:2 * D], accumulate=acc_b or b32 is not None)
             _wgrad_bias(dq, x, d_in_w[2 * D:], acc_w, b32[2 * D:] if b32 is not None else None, d_in_b[2 * D:], acc_b)
         _ready(p_in_w, p_in_b)
-        return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta,
-                None, None, None, None, None, None, None, None, None, None, None)
+        return (dx, dkey, _ret(d_in_w, sink_w), _ret(d_in_b, sink_b), d_out_w, d_out_b, dgamma, dbeta) + (None,) * 12
 
 
 class FFNSublayerFn(torch.autograd.Function):
@@ -864,14 +891,16 @@ def dropout_add_ln(x: Tensor, residual: Optional[Tensor], gamma, beta, p: float,
     return DropoutAddLNFn.apply(x.reshape(-1, shape[-1]), r2, gamma, beta, float(p), float(eps)).view(shape)
 
 
-def attn_sublayer(x: Tensor, key: Optional[Tensor], attn, ln, kv_len, causal: bool, p: float, eps: float) -> Tensor:
-    """LN(x + dropout(attn(x, key, key))) for a `modules.MultiheadAttention` + nn.LayerNorm pair (post-norm)."""
+def attn_sublayer(x: Tensor, key: Optional[Tensor], attn, ln, kv_len, causal: bool, p: float, eps: float,
+                  key_grad_cell: Optional[GradCell] = None) -> Tensor:
+    """LN(x + dropout(attn(x, key, key))) for a `modules.MultiheadAttention` + nn.LayerNorm pair (post-norm).
+    key_grad_cell: shared by every call that reads the same `key` tensor (see GradCell)."""
     B, T, D = x.shape
     S = T if key is None else key.shape[1]
     out = AttnSublayerFn.apply(x.reshape(B * T, D), None if key is None else key.reshape(B * S, D), attn.in_proj_weight,
                                attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias, ln.weight, ln.bias, kv_len,
                                B, T, S, attn.num_heads, causal, attention_scale(attn.head_dim, attn.scaled), float(p), float(eps),
-                               attn.key_bias, float(attn.dropout) if attn.training else 0.0)
+                               attn.key_bias, float(attn.dropout) if attn.training else 0.0, key_grad_cell)
     return out.view(B, T, D)
 
 

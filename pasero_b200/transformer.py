@@ -4,6 +4,7 @@ re-built on the sm_100a kernels. Same constructor contract `(cfg, dist_cfg, task
 state_dict keys, so it drops in behind the reference's model registry for this path.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -135,16 +136,22 @@ class TransformerDecoderLayer(nn.Module, _AdapterMixin):
             return ops.dropout_add_ln(x, residual, None, None, p, eps)
         return ops.dropout_add_ln(x, residual, ln.weight, ln.bias, p, eps)
 
+    @property
+    def fused_sublayers(self) -> bool:
+        """Post-norm + ReLU: every sub-block is one autograd node (ops.AttnSublayerFn / FFNSublayerFn)."""
+        return not self.prenorm and self.cfg.activation_fn == 'relu'
+
     def forward(self, x: Tensor, encoder_out: Tensor, encoder_mask: Optional[Tensor], padding_mask: Optional[Tensor], /,
-                return_layers=(), state=None, encoder_lengths: Optional[Tensor] = None, **kwargs):
+                return_layers=(), state=None, encoder_lengths: Optional[Tensor] = None, encoder_grad_cell=None, **kwargs):
         if state is not None:
             raise NotImplementedError('incremental decoding is outside the training path')
         p = self.dropout_p if self.training else 0.0
         eps = self.cfg.norm_eps
-        if not self.prenorm and self.cfg.activation_fn == 'relu':
+        if self.fused_sublayers:
             x = ops.attn_sublayer(x, None, self.self_attn, self.self_attn_layer_norm, None, True, p, eps)
             enc_len = encoder_lengths if encoder_lengths is not None else self.encoder_attn.key_lengths_of(encoder_mask)
-            x = ops.attn_sublayer(x, encoder_out, self.encoder_attn, self.encoder_attn_layer_norm, enc_len, False, p, eps)
+            x = ops.attn_sublayer(x, encoder_out, self.encoder_attn, self.encoder_attn_layer_norm, enc_len, False, p, eps,
+                                  key_grad_cell=encoder_grad_cell)
             x = ops.ffn_sublayer(x, self.fc1, self.fc2, self.final_layer_norm, p, eps)
             return self.apply_adapters(x), ({self.name: x} if self.name in return_layers else {})
         x = self._block(x, self.self_attn_layer_norm, lambda h: self.self_attn(h, h, h)[0], p, eps)
@@ -296,8 +303,14 @@ class TransformerDecoder(nn.Module):
         x = ops.EmbedFn.apply(self.embed_tokens.weight, decoder_input, pos, float(self.embed_scale), float(p), T,
                               self.padding_idx, learned, self.embed_positions.shift, not self.table_shared_with_encoder).view(B, T, D)
         layer_outputs = {}
+        # every layer's cross-attention reads the encoder output: their gradients for it are summed in the dgrad GEMMs' epilogues
+        # (ops.GradCell) instead of by one autograd add kernel per extra layer
+        fused = sum(1 for layer in self.layers if layer.fused_sublayers)
+        cell = ops.GradCell(fused) if (fused > 1 and torch.is_grad_enabled() and encoder_out.requires_grad and
+                                       os.environ.get('PB200_GRAD_CELL', '1') != '0') else None
         for layer in self.layers:
-            x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths)
+            x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths,
+                           encoder_grad_cell=cell)
             layer_outputs.update(out)
         if self.layer_norm is not None:
             x = ops.dropout_add_ln(x, None, self.layer_norm.weight, self.layer_norm.bias, 0.0, self.cfg.norm_eps)

@@ -148,6 +148,34 @@ def test_gemm_conv_view():
     _close(dx.view(B, T, C), xr.grad.transpose(1, 2), 5e-2, 2e-2, 'conv dgrad')
 
 
+def test_gemm_shared_operand_at_the_end_of_a_mapping():
+    """Regression: the weight of a batched implicit-GEMM convolution is shared by all batches (batch stride 0). Its TMA
+    descriptor once claimed `batch` slices of the weight's size, i.e. memory past the end of the weight, and the launch died
+    with an illegal memory access whenever that range was not mapped (found by running the test files in another order: the
+    Whisper-style conv front end after four Trainers had come and gone). The weight here fills a 10 MiB device allocation
+    of its own (the caching allocator gives requests above 10 MiB their own segment), after everything cached was released,
+    so what follows it in the address space is most likely unmapped."""
+    import gc
+    k = _k()
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    B, T, C, N, KW = 4, 93, 128, 8192, 5          # weight: 8192 x 640 x 2 B = 10 MiB exactly
+    w2 = _rand(N, KW * C, scale=(C * KW) ** -0.5, seed=2)
+    assert w2.numel() * 2 == 10 * 2 ** 20
+    x = _rand(B, T, C, seed=1)
+    Tout = 1 + (T + 2 * (KW // 2) - KW) // 2
+    Tp = T + 4 + (T % 2)
+    xp = k.pad_rows(x, B, T, C, Tp, 2)
+    y = torch.empty(B, Tout, N, dtype=DTYPE, device='cuda')
+    k.gemm_raw(xp.data_ptr(), w2.data_ptr(), y, Tout, N, KW * C, lda=2 * C, ldb=KW * C, ldc=N, batch=B,
+               a_batch_stride=Tp * C, b_batch_stride=0, c_batch_stride=Tout * N, split_k=1)
+    torch.cuda.synchronize()
+    w = w2.view(N, KW, C).permute(0, 2, 1).float()
+    ref = F.conv1d(x.float().transpose(1, 2), w, None, stride=2, padding=2).transpose(1, 2)
+    _close(y, ref, 3e-2, 1e-2, 'conv fwd, weight in its own mapping')
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, kv_len, causal, scale):
     B, H, Lq, Lk = q.shape[0], q.shape[1], q.shape[2], k.shape[2]
