@@ -303,11 +303,13 @@ class TransformerDecoder(nn.Module):
         x = ops.EmbedFn.apply(self.embed_tokens.weight, decoder_input, pos, float(self.embed_scale), float(p), T,
                               self.padding_idx, learned, self.embed_positions.shift, not self.table_shared_with_encoder).view(B, T, D)
         layer_outputs = {}
-        # every layer's cross-attention reads the encoder output: their gradients for it are summed in the dgrad GEMMs' epilogues
-        # (ops.GradCell) instead of by one autograd add kernel per extra layer
+        # every layer's cross-attention reads the encoder output: PB200_GRAD_CELL=1 sums their gradients for it in the dgrad
+        # GEMMs' epilogues (ops.GradCell) instead of by one autograd add kernel per extra layer. Off by default: measured on
+        # config 2 the five saved adds (~55 us) are paid back by the slower residual epilogue of five 16 000 x 512 x 1 024 GEMMs
+        # (step 8.77 -> 8.71 - 8.73 ms, inside the run-to-run noise; GEMM family 5.28 -> 5.44 ms)
         fused = sum(1 for layer in self.layers if layer.fused_sublayers)
         cell = ops.GradCell(fused) if (fused > 1 and torch.is_grad_enabled() and encoder_out.requires_grad and
-                                       os.environ.get('PB200_GRAD_CELL', '1') != '0') else None
+                                       os.environ.get('PB200_GRAD_CELL', '0') == '1') else None
         for layer in self.layers:
             x, out = layer(x, encoder_out, encoder_mask, None, return_layers=return_layers, encoder_lengths=encoder_lengths,
                            encoder_grad_cell=cell)

@@ -100,6 +100,34 @@ def test_forward_backward_matches_reference_and_oracle():
             assert rel_to_max(grads[k].reshape(grads[k].shape[0], -1)[:4], d['rows']) < 0.3, k
 
 
+def test_encoder_output_gradient_cell_matches_autograd_sum(monkeypatch):
+    """PB200_GRAD_CELL=1: the decoder layers' gradients for the encoder output are summed in the epilogues of their key / value
+    dgrad GEMMs (ops.GradCell; one rounding of the total) instead of by autograd's add kernels (the default; a rounding per add):
+    same encoder gradients up to that rounding, and the cell really replaces the adds (every layer but the last returns None)."""
+    from pasero_b200 import ops
+    results = {}
+    calls = []
+    orig = ops.GradCell.contribute
+
+    def contribute(self, fn):
+        out = orig(self, fn)
+        calls.append(out is not None)
+        return out
+    monkeypatch.setattr(ops.GradCell, 'contribute', contribute)
+    for flag in ('1', '0'):
+        monkeypatch.setenv('PB200_GRAD_CELL', flag)
+        cfg, task, model = build()
+        model.to(BF16).cuda().train()
+        loss, _ = model(**to_cuda(synth.model_batch()))
+        model.zero_grad()
+        loss.backward()
+        results[flag] = {n: p.grad.float().clone() for n, p in model.named_parameters() if n.startswith('encoder.') and p.grad is not None}
+    assert calls == [False] * (synth.TINY['decoder_layers'] - 1) + [True]      # only the run with the cell got here
+    assert results['1'].keys() == results['0'].keys() and len(results['1']) > 10
+    for n, g in results['1'].items():
+        assert rel_to_max(g, results['0'][n]) < 2e-2, n
+
+
 def oracle_bf16_curve(steps: int) -> list:
     """The oracle's train step with the reference's bf16 semantics, on CPU (a few seconds for the tiny model)."""
     from oracle import model as om
