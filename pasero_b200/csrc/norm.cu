@@ -271,6 +271,158 @@ dropout_add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
     }
 }
 
+// The shape the training step launches 42 times: LayerNorm present, D == NCH * 256 (every lane's chunks are in range), the
+// dropout keep bits stored by forward (or no dropout), no extra gradient operand, all three column sums wanted. Same
+// arithmetic and the same partial layout as the general kernel above; what it sheds is instruction issue, which is what
+// bounds the general kernel (ncu: issue slots 69 % busy at 16 warps per SM, DRAM 21 %): operand options are compile-time, the
+// element offset is carried instead of recomputed per chunk, packed pairs are split by bit operations, the normalised input
+// is one FFMA, 1 / D is a constant and the row statistics are folded into the two gradient FFMAs: 376 SASS instructions per
+// row of 512 against 736 (cuobjdump -sass; an alternating pair of row buffers, which would also save the 20 register copies
+// per row, does not fit the 128-register cap of two CTAs per SM without spilling).
+template <int NCH>
+struct LnbRow {
+    uint4 d[NCH], s[NCH];
+    uint32_t k[NCH];
+    float mu, rs;
+};
+
+// a packed pair as two fp32 values by bit operations on the word (no 16-bit sub-register traffic)
+__device__ __forceinline__ float2 unpack2(uint32_t w) { return make_float2(elem_lo_f(w), elem_hi_f(w)); }
+
+template <int NCH, bool DROP, bool LIN>
+__global__ void __launch_bounds__(LNB_WARPS * 32, NCH <= 2 ? 2 : 1)
+ln_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ sum, const bf16* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, int M, float keep_scale,
+                   bf16* __restrict__ dresidual, bf16* __restrict__ dx, float* __restrict__ partial,
+                   const uint8_t* __restrict__ keep_in) {
+    constexpr int D = NCH * 256;
+    constexpr float inv_D = 1.0f / (float)D;
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // gamma as fp32 in shared memory, laid out so that a lane's four columns are one conflict-free 128-bit load: 16 more
+    // registers per lane would not fit beside the 48 column accumulators and the two row buffers under the 128-register cap
+    __shared__ float4 gs4[NCH * 2 * 32];
+    if (threadIdx.x < NCH * 64) {
+        const int q = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const uint2 gv = __ldg(reinterpret_cast<const uint2*>(gamma + (q >> 1) * 256 + l * 8 + (q & 1) * 4));
+        const float2 g01 = unpack2(gv.x), g23 = unpack2(gv.y);
+        gs4[threadIdx.x] = make_float4(g01.x, g01.y, g23.x, g23.y);
+    }
+    __syncthreads();
+    const uint32_t gs_lane = (uint32_t)__cvta_generic_to_shared(gs4 + lane);
+    auto gamma4 = [&](int q) {      // asm volatile: re-read where it is used instead of being hoisted into (spilled) registers
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(gs_lane + q * 512));
+        return v;
+    };
+    float dg[NCH][8], db[NCH][8], dl[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; dl[c][j] = 0.f; }
+    const int stride = gridDim.x * LNB_WARPS;
+    const long long step = (long long)stride * D;
+    int row = blockIdx.x * LNB_WARPS + warp;
+    long long e = (long long)row * D + lane * 8;      // element offset of this lane's first chunk in the current row
+
+    auto load = [&](LnbRow<NCH>& R, int r, long long er) {
+        if (r < M) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                R.d[c] = __ldg(reinterpret_cast<const uint4*>(dy + er) + c * 32);
+                R.s[c] = __ldg(reinterpret_cast<const uint4*>(sum + er) + c * 32);
+                if (DROP) R.k[c] = (uint32_t)__ldg(keep_in + (er >> 3) + c * 32);
+            }
+            R.mu = __ldg(mean + r); R.rs = __ldg(rstd + r);
+        }
+    };
+    auto process = [&](const LnbRow<NCH>& R, long long er) {
+        const float rs = R.rs, nmr = -R.mu * rs;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t dw[4] = {R.d[c].x, R.d[c].y, R.d[c].z, R.d[c].w};
+            const uint32_t sw[4] = {R.s[c].x, R.s[c].y, R.s[c].z, R.s[c].w};
+            const float4 ga = gamma4(2 * c), gb = gamma4(2 * c + 1);
+            const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 d = unpack2(dw[j]);
+                const float2 sx = unpack2(sw[j]);
+                const float x0 = fmaf(sx.x, rs, nmr), x1 = fmaf(sx.y, rs, nmr);
+                dg[c][2 * j] = fmaf(d.x, x0, dg[c][2 * j]); dg[c][2 * j + 1] = fmaf(d.y, x1, dg[c][2 * j + 1]);
+                db[c][2 * j] += d.x; db[c][2 * j + 1] += d.y;
+                const float g0 = d.x * gm[2 * j], g1 = d.y * gm[2 * j + 1];
+                s1a += g0; s1b += g1;
+                s2a = fmaf(g0, x0, s2a); s2b = fmaf(g1, x1, s2b);
+            }
+        }
+        const float a = warp_sum(s1a + s1b) * (inv_D * rs);     // rs * mean(g)
+        const float b = warp_sum(s2a + s2b) * (inv_D * rs);     // rs * mean(g * xhat)
+        const float nb = -b * rs, c0 = -(a + nmr * b);          // -xhat * b - a = s * nb + c0
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t dw[4] = {R.d[c].x, R.d[c].y, R.d[c].z, R.d[c].w};
+            const uint32_t sw[4] = {R.s[c].x, R.s[c].y, R.s[c].z, R.s[c].w};
+            const float4 ga = gamma4(2 * c), gb = gamma4(2 * c + 1);
+            const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {    // rs * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma
+                const float2 d = unpack2(dw[j]);
+                const float2 sx = unpack2(sw[j]);
+                ow[j] = pack_bf16x2(fmaf(d.x * gm[2 * j], rs, fmaf(sx.x, nb, c0)),
+                                    fmaf(d.y * gm[2 * j + 1], rs, fmaf(sx.y, nb, c0)));
+            }
+            if (DROP) {
+                *(reinterpret_cast<uint4*>(dresidual + er) + c * 32) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                const uint32_t keep = R.k[c];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 r = unpack2(ow[j]);      // the gradient reaching dropout is 16-bit
+                    ow[j] = pack_bf16x2(((keep >> (2 * j)) & 1) ? r.x * keep_scale : 0.f,
+                                        ((keep >> (2 * j + 1)) & 1) ? r.y * keep_scale : 0.f);
+                }
+            }
+            *(reinterpret_cast<uint4*>(dx + er) + c * 32) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (LIN) {                                          // column sums of dx exactly as stored
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 r = unpack2(ow[j]);
+                    dl[c][2 * j] += r.x; dl[c][2 * j + 1] += r.y;
+                }
+            }
+        }
+    };
+
+    LnbRow<NCH> N;
+    load(N, row, e);
+    for (; row < M; row += stride, e += step) {
+        const LnbRow<NCH> C = N;
+        load(N, row + stride, e + step);
+        process(C, e);
+    }
+    // CTA-level sum, as in the general kernel (128-bit shared stores)
+    extern __shared__ float red[];   // [LNB_WARPS][3][D]
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        float4* r0 = reinterpret_cast<float4*>(red + (warp * 3 + 0) * D + c * 256 + lane * 8);
+        float4* r1 = reinterpret_cast<float4*>(red + (warp * 3 + 1) * D + c * 256 + lane * 8);
+        float4* r2 = reinterpret_cast<float4*>(red + (warp * 3 + 2) * D + c * 256 + lane * 8);
+        r0[0] = make_float4(dg[c][0], dg[c][1], dg[c][2], dg[c][3]); r0[1] = make_float4(dg[c][4], dg[c][5], dg[c][6], dg[c][7]);
+        r1[0] = make_float4(db[c][0], db[c][1], db[c][2], db[c][3]); r1[1] = make_float4(db[c][4], db[c][5], db[c][6], db[c][7]);
+        r2[0] = make_float4(dl[c][0], dl[c][1], dl[c][2], dl[c][3]); r2[1] = make_float4(dl[c][4], dl[c][5], dl[c][6], dl[c][7]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < LNB_WARPS; ++w) acc += red[w * 3 * D + i];
+        partial[(long long)blockIdx.x * 3 * D + i] = acc;
+    }
+}
+
 // out[n] (bf16 or fp32) = (accumulate ? out[n] : 0) + sum_p partial[p * stride + n]
 // block = 32 columns x 8 partial-row lanes: coalesced 128-byte reads, tree-free smem reduce over the 8 lanes.
 __device__ __forceinline__ float out_load(const bf16* p) { return bf16_to_f(*p); }
@@ -434,6 +586,34 @@ extern "C" int pb200_dropout_add_ln_bwd(const void* dy, const void* dsum_extra, 
         partial = reinterpret_cast<float*>(workspace);
     }
     const int nch = (int)((D + 255) / 256);
+    // the training step's shape: see ln_bwd_fast_kernel
+    const bool drop = p > 0.f;
+    if (gamma && sum && mean && rstd && !dsum_extra && partial && dx && D == 256LL * nch && nch >= 2 &&
+        (drop ? (keep_mask && dresidual && dresidual != dx) : (!dresidual || dresidual == dx))) {
+        const bool lin = dbias_lin != nullptr;
+        const float keep_scale = drop ? 1.0f / (1.0f - p) : 1.0f;
+#define PB_LN_FAST(N_, DROP_, LIN_)                                                                                    \
+        do {                                                                                                           \
+            PB_CUDA(cudaFuncSetAttribute(ln_bwd_fast_kernel<N_, DROP_, LIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         LNB_WARPS * 3 * N_ * 256 * 4));                                               \
+            PB_CUDA(launch_pdl(ln_bwd_fast_kernel<N_, DROP_, LIN_>, dim3(grid), dim3(LNB_WARPS * 32),                  \
+                               (size_t)(LNB_WARPS * 3 * N_ * 256 * 4), stream, (const bf16*)dy, (const bf16*)sum,      \
+                               (const bf16*)gamma, mean, rstd, (int)M, keep_scale, (bf16*)dresidual, (bf16*)dx, partial, \
+                               (const uint8_t*)keep_mask));                                                            \
+        } while (0)
+#define PB_LN_FAST2(N_)                                                                                                \
+        do {                                                                                                           \
+            if (drop) { if (lin) PB_LN_FAST(N_, true, true); else PB_LN_FAST(N_, true, false); }                       \
+            else { if (lin) PB_LN_FAST(N_, false, true); else PB_LN_FAST(N_, false, false); }                          \
+        } while (0)
+        switch (nch) { case 2: PB_LN_FAST2(2); break; case 3: PB_LN_FAST2(3); break; default: PB_LN_FAST2(4); }
+#undef PB_LN_FAST2
+#undef PB_LN_FAST
+        PB_LAUNCH_CHECK();
+        if (!(accumulate & 4))
+            return pb200_ln_bwd_reduce(workspace, M, D, dgamma, dbeta, dbias_lin, accumulate, stream_);
+        return 0;
+    }
 #define PB_LN_BWD(N_)                                                                                        \
     PB_CUDA(cudaFuncSetAttribute(dropout_add_ln_bwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                  LNB_WARPS * 3 * N_ * 256 * 4));                                                \

@@ -42,8 +42,7 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
     const float inv_scale = hyper[13] != 0.f ? hyper[13] : 1.0f;    // (0 = not set: no loss scaling)
     const bool f32g = hyper[14] != 0.f;
     float acc = 0.f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(grad) + i);
+    auto add = [&](const uint4& v) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -58,7 +57,17 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
             }
             acc += a * a + b * b;
         }
+    };
+    // four 16-byte loads in flight per thread: with one, the 4 x 256-thread CTAs an SM holds keep 16 KB outstanding, which at
+    // HBM latency is a third of the bandwidth (the arena is read once, nothing else hides the latency)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint4* g4 = reinterpret_cast<const uint4*>(grad);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n8; i += 4 * stride) {
+        const uint4 v0 = __ldg(g4 + i), v1 = __ldg(g4 + i + stride), v2 = __ldg(g4 + i + 2 * stride), v3 = __ldg(g4 + i + 3 * stride);
+        add(v0); add(v1); add(v2); add(v3);
     }
+    for (; i < n8; i += stride) add(__ldg(g4 + i));
     __shared__ double red[8];
     __shared__ bool is_last;
     double d = warp_sum_d((double)acc);

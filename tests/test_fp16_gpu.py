@@ -31,7 +31,7 @@ def float16_operands(monkeypatch):
 # ---- the kernel tests, float16 build -------------------------------------------------------------------------------------
 from tests.test_kernels_gpu import (test_gemm_forward, test_gemm_tile512, test_gemm_epilogues, test_gemm_dgrad_wgrad,  # noqa: E402,F401
                                     test_wgrad_fused_bias_grad, test_gemm_conv_view, test_attention, test_attention_dropout,
-                                    test_dropout_add_ln, test_linear_dropout_add_ln_fused,
+                                    test_dropout_add_ln, test_ln_bwd_training_shape_kernel, test_linear_dropout_add_ln_fused,
                                     test_sublayers_fused_linear_ln_matches_two_kernel_path, test_dropout_mask_consistency,
                                     test_colsum, test_embed, test_glu, test_gelu_padded_layout, test_ls_ce, test_adam_and_clip,
                                     test_projection_ce_chunked)

@@ -305,6 +305,56 @@ def test_dropout_add_ln(M, D):
     _close(dl2, 2 * dx.float().sum(0), 0.1 * math.sqrt(M / 100), 3e-2, 'ln dbias_lin accumulate')
 
 
+@pytest.mark.parametrize('M,D,p', [(16000, 512, 0.1), (3072, 512, 0.1), (1237, 512, 0.0), (531, 768, 0.1), (700, 1024, 0.25),
+                                   (7, 512, 0.1)])
+@pytest.mark.parametrize('lin', [True, False])
+def test_ln_bwd_training_shape_kernel(M, D, p, lin):
+    """csrc/norm.cu has a second backward kernel for the shape the training step launches (LayerNorm present, D a multiple of
+    256, stored keep bits or no dropout, no extra gradient operand): against an fp32 torch restatement applied to the kernel's
+    own keep bits, and against the general kernel (selected by passing an all-zero extra gradient operand) on the same inputs."""
+    k = _k()
+    x, r = _rand(M, D, seed=11), _rand(M, D, seed=12)
+    g, b = (1 + 0.1 * _rand(D, seed=13).float()).to(DTYPE), _rand(D, scale=0.1, seed=14)
+    keep = torch.zeros(M * D // 8, dtype=torch.uint8, device='cuda') if p > 0 else None
+    y, s, mean, rstd = k.dropout_add_ln_fwd(x, r, g, b, 1e-5, p, 4242, 3, keep_out=keep)
+    dy = _rand(M, D, seed=15)
+
+    def run(extra):
+        dg, db = torch.empty(D, dtype=DTYPE, device='cuda'), torch.empty(D, dtype=DTYPE, device='cuda')
+        dl = torch.empty(D, dtype=DTYPE, device='cuda') if lin else None
+        dx, dres = k.dropout_add_ln_bwd(dy, extra, s, g, mean, rstd, p, 4242, 3, True, dg, db, dbias_lin=dl, keep_mask=keep)
+        return dx, dres, dg, db, dl
+
+    dx, dres, dg, db, dl = run(None)
+    dx0, dres0, dg0, db0, dl0 = run(torch.zeros_like(dy))
+    # fp32 restatement
+    xs = s.float().requires_grad_(True)
+    gr, br = g.float().requires_grad_(True), b.float().requires_grad_(True)
+    F.layer_norm(xs, (D,), gr, br, 1e-5).backward(dy.float())
+    _close(dres, xs.grad, 2e-2, 2e-2, 'training-shape ln dres')
+    _close(dg, gr.grad, 0.05 * math.sqrt(max(M, 100) / 100), 2e-2, 'training-shape ln dgamma')
+    _close(db, br.grad, 0.05 * math.sqrt(max(M, 100) / 100), 2e-2, 'training-shape ln dbeta')
+    if p > 0:
+        bits = ((keep.view(M, D // 8, 1).int() >> torch.arange(8, device='cuda').view(1, 1, 8)) & 1).view(M, D).bool()
+        ref_dx = torch.where(bits, (dres.float() * (1 / (1 - p))).to(DTYPE), torch.zeros_like(dres))
+        assert torch.equal(dx, ref_dx)          # dropout' applied to the 16-bit gradient exactly as stored
+    else:
+        assert dres is dx
+    if lin:
+        _close(dl, dx.float().sum(0), 0.05 * math.sqrt(max(M, 100) / 100), 2e-2, 'training-shape ln dbias_lin')
+    # the general kernel: same values up to the last 16-bit rounding (the two evaluate rs * (g - mean g - xhat mean(g xhat))
+    # with differently associated fp32 operations)
+    ulp = 2 ** -7 if DTYPE == torch.bfloat16 else 2 ** -10
+    for name, a_, b_ in (('dres', dres, dres0), ('dx', dx, dx0)):
+        d = (a_.float() - b_.float()).abs()
+        assert (d <= 2 * ulp * b_.float().abs() + 1e-6).all(), (name, d.max().item())
+        assert (d > 0).float().mean().item() < 0.05, name
+    _close(dg, dg0.float(), 0.02 * math.sqrt(max(M, 100) / 100), 1e-2, 'dgamma vs general kernel')
+    _close(db, db0.float(), 0.02 * math.sqrt(max(M, 100) / 100), 1e-2, 'dbeta vs general kernel')
+    if lin:
+        _close(dl, dl0.float(), 0.02 * math.sqrt(max(M, 100) / 100), 1e-2, 'dbias_lin vs general kernel')
+
+
 @pytest.mark.parametrize('M,K,p', [(16000, 512, 0.0), (16000, 2048, 0.1), (8192, 512, 0.1), (8300, 1024, 0.25)])
 def test_linear_dropout_add_ln_fused(M, K, p):
     """csrc/gemm_ln.cu against the two-kernel path it replaces (GEMM, then dropout + residual + LayerNorm) and against an
