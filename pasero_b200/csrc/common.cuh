@@ -117,13 +117,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     bf162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
-    bf162 h = *reinterpret_cast<bf162*>(&v);
-    return __bfloat1622float2(h);
-}
 // the low / high element of a packed pair as fp32 (a bfloat16 is the top half of an fp32)
 __device__ __forceinline__ float elem_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float elem_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// by bit operations on the word: __bfloat1622float2 goes through 16-bit sub-registers (a PRMT per pair on top of the shifts)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) { return make_float2(elem_lo_f(v), elem_hi_f(v)); }
 #endif
 
 __device__ __forceinline__ float warp_sum(float v) {
