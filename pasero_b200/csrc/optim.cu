@@ -81,10 +81,18 @@ grad_sqnorm_kernel(const bf16* __restrict__ grad, long long n8, const float* __r
         is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(partials)[i];
+    if (!is_last) return;
+    // the last CTA adds the partials: every thread its share (a fixed order, so replicas stay bit-identical), then the block;
+    // one thread walking all of them is a chain of dependent L2 round trips as long as the rest of the kernel
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += reinterpret_cast<volatile double*>(partials)[i];
+    t = warp_sum_d(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
         stats[4] = t;
         stats[5] = (isfinite(t) && stats[6] == 0.0) ? 0.0 : 1.0;     // [6]: a failed micro-batch on some rank -> no update either
         *ticket = 0;

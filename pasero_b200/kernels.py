@@ -447,7 +447,13 @@ def f32_to_bf16(src: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 # loss, optimizer, frontend
 # --------------------------------------------------------------------------------------------------
-@_bracketed
+def _ce_bytes(logits, target, *args, **kwargs):
+    # label-smoothed CE in one pass: the bf16 logits are read once and overwritten with their gradient
+    vocab = kwargs.get('vocab') or (args[6] if len(args) > 6 and args[6] else logits.shape[1])
+    return 'byte', 2.0 * logits.shape[0] * vocab * 2
+
+
+@_bracketed(work=_ce_bytes)
 def ls_ce_fwd_bwd(logits: Tensor, target: Tensor, padding_idx: int, label_smoothing: float, stats: Tensor,
                   write_grad: bool = True, grad_scale: float = 1.0, row_loss: Optional[Tensor] = None,
                   vocab: Optional[int] = None) -> None:
