@@ -300,6 +300,26 @@ ln_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ sum, co
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = gridDim.x * LNB_WARPS;
+    const long long step = (long long)stride * D;
+    int row = blockIdx.x * LNB_WARPS + warp;
+    long long e = (long long)row * D + lane * 8;      // element offset of this lane's first chunk in the current row
+
+    auto load = [&](LnbRow<NCH>& R, int r, long long er) {
+        if (r < M) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                R.d[c] = __ldg(reinterpret_cast<const uint4*>(dy + er) + c * 32);
+                R.s[c] = __ldg(reinterpret_cast<const uint4*>(sum + er) + c * 32);
+                if (DROP) R.k[c] = (uint32_t)__ldg(keep_in + (er >> 3) + c * 32);
+            }
+            R.mu = __ldg(mean + r); R.rs = __ldg(rstd + r);
+        }
+    };
+    // the first row is requested before gamma is staged (a warp handles ~7 rows of a 16 000-row launch: a second exposed
+    // round trip to HBM at the start is a tenth of the kernel)
+    LnbRow<NCH> N;
+    load(N, row, e);
     // gamma as fp32 in shared memory, laid out so that a lane's four columns are one conflict-free 128-bit load: 16 more
     // registers per lane would not fit beside the 48 column accumulators and the two row buffers under the 128-register cap
     __shared__ float4 gs4[NCH * 2 * 32];
@@ -321,22 +341,6 @@ ln_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ sum, co
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; dl[c][j] = 0.f; }
-    const int stride = gridDim.x * LNB_WARPS;
-    const long long step = (long long)stride * D;
-    int row = blockIdx.x * LNB_WARPS + warp;
-    long long e = (long long)row * D + lane * 8;      // element offset of this lane's first chunk in the current row
-
-    auto load = [&](LnbRow<NCH>& R, int r, long long er) {
-        if (r < M) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                R.d[c] = __ldg(reinterpret_cast<const uint4*>(dy + er) + c * 32);
-                R.s[c] = __ldg(reinterpret_cast<const uint4*>(sum + er) + c * 32);
-                if (DROP) R.k[c] = (uint32_t)__ldg(keep_in + (er >> 3) + c * 32);
-            }
-            R.mu = __ldg(mean + r); R.rs = __ldg(rstd + r);
-        }
-    };
     auto process = [&](const LnbRow<NCH>& R, long long er) {
         const float rs = R.rs, nmr = -R.mu * rs;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
@@ -396,8 +400,6 @@ ln_bwd_fast_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ sum, co
         }
     };
 
-    LnbRow<NCH> N;
-    load(N, row, e);
     for (; row < M; row += stride, e += step) {
         const LnbRow<NCH> C = N;
         load(N, row + stride, e + step);
