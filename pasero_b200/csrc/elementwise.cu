@@ -16,6 +16,8 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const bf16* 
                                  const bf16* __restrict__ pos, long long M, int D, int L, float scale, float p,
                                  uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
                                  long long num_embeddings, bf16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
@@ -63,6 +65,8 @@ __global__ void embed_bwd_kernel(const bf16* __restrict__ dy, const long long* _
                                  float scale, float p, uint64_t seed, uint64_t offset, const long long* __restrict__ offset_base,
                                  long long padding_idx, long long num_embeddings, bf16* __restrict__ dx,
                                  float* __restrict__ dtable) {
+    pdl_trigger();
+    pdl_wait();
     if (offset_base) offset += (uint64_t)(*offset_base) << 12;
     const Philox rng(seed);
     const uint32_t thresh = dropout_thresh16(p);
@@ -110,6 +114,8 @@ __global__ void embed_bwd_kernel(const bf16* __restrict__ dy, const long long* _
 // remaining rows are written as zeros (the next conv's implicit padding).
 __global__ void glu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C, bf16* __restrict__ out, int Tp,
                                int front_pad) {
+    pdl_trigger();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long total = (long long)B * Tp * c8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -141,6 +147,8 @@ __global__ void glu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C,
 // d(value) = dy * sigmoid(g); d(gate) = dy * a * sigmoid(g) * (1 - sigmoid(g)); dy is [B*T, C] contiguous
 __global__ void glu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ in, long long M, int C,
                                bf16* __restrict__ din) {
+    pdl_trigger();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long total = M * c8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -172,6 +180,8 @@ __global__ void glu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
 // with B = 1, Tp = T, the FFN activation.
 __global__ void gelu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C, bf16* __restrict__ out, int Tp,
                                 int front_pad) {
+    pdl_trigger();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long total = (long long)B * Tp * c8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -199,6 +209,8 @@ __global__ void gelu_fwd_kernel(const bf16* __restrict__ in, int B, int T, int C
 
 // dx = dy where the ReLU output h > 0, else 0 (backward of a stand-alone ReLU, e.g. the encoder's in_linear)
 __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h, long long n8, bf16* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy) + i);
         const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h) + i);
@@ -217,6 +229,8 @@ __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 // GELU (erf) elementwise fwd/bwd for the Whisper-style conv front end and FFN backward
 __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, long long n8,
                                 bf16* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
          i += (long long)gridDim.x * blockDim.x) {
         const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy) + i);
@@ -239,6 +253,8 @@ __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 //   dx[b, s, c] = sum_{tap : (s + pad - tap) % stride == 0, t = (s + pad - tap)/stride in [0,Tout)} dcol[b,t,tap,c]
 __global__ void col2im_kernel(const bf16* __restrict__ dcol, int B, int Tin, int Tout, int C, int KW, int stride,
                               bf16* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     const int c8 = C >> 3;
     const int pad = KW / 2;
     const long long total = (long long)B * Tin * c8;
@@ -272,6 +288,8 @@ __global__ void col2im_kernel(const bf16* __restrict__ dcol, int B, int Tin, int
 // [B, T, C] bf16 -> zero-padded [B, Tp, C] bf16 (front_pad zero rows, zeros after T)
 __global__ void pad_rows_kernel(const bf16* __restrict__ in, int B, int T, int C, bf16* __restrict__ out, int Tp,
                                 int front_pad) {
+    pdl_trigger();
+    pdl_wait();
     const int c8 = C >> 3;
     const long long total = (long long)B * Tp * c8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -313,9 +331,9 @@ extern "C" int pb200_embed_fwd(const int64_t* ids, const void* src, const void* 
     if (M == 0) return 0;
     PB_CHECK(D % 8 == 0, "embed: D must be a multiple of 8");
     PB_CHECK(L > 0, "embed: L must be positive");
-    embed_fwd_kernel<<<ew_grid(M * (D / 8)), 256, 0, (cudaStream_t)stream_>>>(
-        (const long long*)ids, (const bf16*)src, (const bf16*)pos, M, (int)D, (int)L, scale, p, seed, offset,
-        (const long long*)offset_base, num_embeddings, (bf16*)out);
+    PB_CUDA(launch_pdl(embed_fwd_kernel, dim3(ew_grid(M * (D / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const long long*)ids, (const bf16*)src, (const bf16*)pos, M, (int)D, (int)L, scale, p, seed, offset,
+                       (const long long*)offset_base, num_embeddings, (bf16*)out));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -327,9 +345,9 @@ extern "C" int pb200_embed_bwd(const void* dy, const int64_t* ids, int64_t M, in
     PB_CHECK(D % 8 == 0, "embed: D must be a multiple of 8");
     PB_CHECK((ids != nullptr) == (dtable != nullptr), "embed_bwd: ids and dtable go together");
     PB_CHECK(ids != nullptr || dx != nullptr, "embed_bwd: dx required without ids");
-    embed_bwd_kernel<<<ew_grid(M * (D / 8)), 256, 0, (cudaStream_t)stream_>>>(
-        (const bf16*)dy, (const long long*)ids, M, (int)D, scale, p, seed, offset, (const long long*)offset_base, padding_idx,
-        num_embeddings, (bf16*)dx, dtable);
+    PB_CUDA(launch_pdl(embed_bwd_kernel, dim3(ew_grid(M * (D / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)dy, (const long long*)ids, M, (int)D, scale, p, seed, offset,
+                       (const long long*)offset_base, padding_idx, num_embeddings, (bf16*)dx, dtable));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -338,8 +356,8 @@ extern "C" int pb200_glu_fwd(const void* in, int32_t B, int32_t T, int32_t C, vo
                              void* stream_) {
     if (B == 0) return 0;
     PB_CHECK(C % 8 == 0 && Tp >= T + front_pad, "glu: bad shape");
-    glu_fwd_kernel<<<ew_grid((long long)B * Tp * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)in, B, T, C,
-                                                                                          (bf16*)out, Tp, front_pad);
+    PB_CUDA(launch_pdl(glu_fwd_kernel, dim3(ew_grid((long long)B * Tp * (C / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)in, B, T, C, (bf16*)out, Tp, front_pad));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -347,8 +365,8 @@ extern "C" int pb200_glu_fwd(const void* in, int32_t B, int32_t T, int32_t C, vo
 extern "C" int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t C, void* din, void* stream_) {
     if (M == 0) return 0;
     PB_CHECK(C % 8 == 0, "glu: C must be a multiple of 8");
-    glu_bwd_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)in, M, C,
-                                                                          (bf16*)din);
+    PB_CUDA(launch_pdl(glu_bwd_kernel, dim3(ew_grid(M * (C / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)dy, (const bf16*)in, M, C, (bf16*)din));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -356,7 +374,8 @@ extern "C" int pb200_glu_bwd(const void* dy, const void* in, int64_t M, int32_t 
 extern "C" int pb200_relu_bwd(const void* dy, const void* h, int64_t n, void* dx, void* stream_) {
     if (n == 0) return 0;
     PB_CHECK(n % 8 == 0, "relu_bwd: n must be a multiple of 8");
-    relu_bwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)h, n / 8, (bf16*)dx);
+    PB_CUDA(launch_pdl(relu_bwd_kernel, dim3(ew_grid(n / 8)), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)dy, (const bf16*)h, n / 8, (bf16*)dx));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -365,8 +384,8 @@ extern "C" int pb200_gelu_fwd(const void* in, int32_t B, int32_t T, int32_t C, v
                               void* stream_) {
     if (B == 0 || T == 0) return 0;
     PB_CHECK(C % 8 == 0 && Tp >= T + front_pad, "gelu_fwd: bad shape");
-    gelu_fwd_kernel<<<ew_grid((long long)B * Tp * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)in, B, T, C,
-                                                                                           (bf16*)out, Tp, front_pad);
+    PB_CUDA(launch_pdl(gelu_fwd_kernel, dim3(ew_grid((long long)B * Tp * (C / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)in, B, T, C, (bf16*)out, Tp, front_pad));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -374,7 +393,8 @@ extern "C" int pb200_gelu_fwd(const void* in, int32_t B, int32_t T, int32_t C, v
 extern "C" int pb200_gelu_bwd(const void* dy, const void* pre, int64_t n, void* dx, void* stream_) {
     if (n == 0) return 0;
     PB_CHECK(n % 8 == 0, "gelu_bwd: n must be a multiple of 8");
-    gelu_bwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dy, (const bf16*)pre, n / 8, (bf16*)dx);
+    PB_CUDA(launch_pdl(gelu_bwd_kernel, dim3(ew_grid(n / 8)), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)dy, (const bf16*)pre, n / 8, (bf16*)dx));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -383,8 +403,8 @@ extern "C" int pb200_col2im(const void* dcol, int32_t B, int32_t Tin, int32_t To
                             int32_t stride, void* dx, void* stream_) {
     if (B == 0) return 0;
     PB_CHECK(C % 8 == 0 && stride >= 1 && KW >= 1, "col2im: bad shape");
-    col2im_kernel<<<ew_grid((long long)B * Tin * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)dcol, B, Tin, Tout,
-                                                                                          C, KW, stride, (bf16*)dx);
+    PB_CUDA(launch_pdl(col2im_kernel, dim3(ew_grid((long long)B * Tin * (C / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)dcol, B, Tin, Tout, C, KW, stride, (bf16*)dx));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -393,8 +413,8 @@ extern "C" int pb200_pad_rows(const void* in, int32_t B, int32_t T, int32_t C, v
                               void* stream_) {
     if (B == 0) return 0;
     PB_CHECK(C % 8 == 0 && Tp >= T + front_pad, "pad_rows: bad shape");
-    pad_rows_kernel<<<ew_grid((long long)B * Tp * (C / 8)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)in, B, T, C,
-                                                                                           (bf16*)out, Tp, front_pad);
+    PB_CUDA(launch_pdl(pad_rows_kernel, dim3(ew_grid((long long)B * Tp * (C / 8))), dim3(256), 0, (cudaStream_t)stream_,
+                       (const bf16*)in, B, T, C, (bf16*)out, Tp, front_pad));
     PB_LAUNCH_CHECK();
     return 0;
 }

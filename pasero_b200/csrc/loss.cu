@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(CE_THREADS)
 ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, long long target_stride0,
              int T, int V, long long ld, long long padding_idx, float eps, float grad_scale, int write_grad,
              double* __restrict__ stats, float* __restrict__ row_loss) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[CE_THREADS / 32];
     const long long row = blockIdx.x;
     // targets may be a strided [B, T] view (decoder_input[:, 1:]); row = b * T + t
@@ -131,6 +133,8 @@ ls_ce_kernel(bf16* __restrict__ logits, const long long* __restrict__ target, lo
 __global__ void __launch_bounds__(CE_THREADS)
 ce_chunk_stats_kernel(const bf16* __restrict__ logits, long long ld, const long long* __restrict__ target,
                       long long target_stride0, int T, int c0, int vc, long long padding_idx, float* __restrict__ state, int M) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[CE_THREADS / 32];
     const long long row = blockIdx.x;
     const long long tgt = target[(row / T) * target_stride0 + (row % T)];
@@ -208,6 +212,8 @@ __global__ void ce_chunk_finish_kernel(const float* __restrict__ state, const lo
 __global__ void __launch_bounds__(CE_THREADS)
 ce_chunk_grad_kernel(bf16* __restrict__ logits, long long ld, const long long* __restrict__ target, long long target_stride0,
                      int T, int c0, int vc, int V, float eps, float grad_scale, const float* __restrict__ lse) {
+    pdl_trigger();
+    pdl_wait();
     const long long row = blockIdx.x;
     const long long tgt = target[(row / T) * target_stride0 + (row % T)];
     bf16* x = logits + row * ld;
@@ -245,9 +251,9 @@ extern "C" int pb200_ls_ce_fwd_bwd(void* logits, const int64_t* target, int64_t 
     PB_CHECK(ld % 8 == 0 && ld >= (V + 7) / 8 * 8, "cross-entropy: ld (%lld) must be a multiple of 8 covering V (%lld) rounded up to 8",
              (long long)ld, (long long)V);
     PB_CHECK(stats != nullptr, "cross-entropy: stats buffer required");
-    ls_ce_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
-        (bf16*)logits, (const long long*)target, target_stride0, (int)T, (int)V, ld, padding_idx, label_smoothing,
-        grad_scale, write_grad, stats, row_loss);
+    PB_CUDA(launch_pdl(ls_ce_kernel, dim3((unsigned)(B * T)), dim3(CE_THREADS), 0, (cudaStream_t)stream_,
+                       (bf16*)logits, (const long long*)target, target_stride0, (int)T, (int)V, ld, padding_idx,
+                       label_smoothing, grad_scale, write_grad, stats, row_loss));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -257,9 +263,9 @@ extern "C" int pb200_ce_chunk_stats(const void* logits, int64_t ld, const int64_
                                     void* stream_) {
     if (B * T == 0 || chunk_cols == 0) return 0;
     PB_CHECK(ld % 8 == 0 && ld >= (chunk_cols + 7) / 8 * 8 && row_state, "ce_chunk_stats: ld must be a multiple of 8 covering the chunk");
-    ce_chunk_stats_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
-        (const bf16*)logits, ld, (const long long*)target, target_stride0, (int)T, (int)chunk_begin, (int)chunk_cols, padding_idx,
-        row_state, (int)(B * T));
+    PB_CUDA(launch_pdl(ce_chunk_stats_kernel, dim3((unsigned)(B * T)), dim3(CE_THREADS), 0, (cudaStream_t)stream_,
+                       (const bf16*)logits, ld, (const long long*)target, target_stride0, (int)T, (int)chunk_begin,
+                       (int)chunk_cols, padding_idx, row_state, (int)(B * T)));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -280,9 +286,9 @@ extern "C" int pb200_ce_chunk_grad(void* logits, int64_t ld, const int64_t* targ
                                    const float* lse, void* stream_) {
     if (B * T == 0 || chunk_cols == 0) return 0;
     PB_CHECK(ld % 8 == 0 && ld >= (chunk_cols + 7) / 8 * 8 && lse, "ce_chunk_grad: ld must be a multiple of 8 covering the chunk");
-    ce_chunk_grad_kernel<<<(unsigned)(B * T), CE_THREADS, 0, (cudaStream_t)stream_>>>(
-        (bf16*)logits, ld, (const long long*)target, target_stride0, (int)T, (int)chunk_begin, (int)chunk_cols, (int)V,
-        label_smoothing, grad_scale, lse);
+    PB_CUDA(launch_pdl(ce_chunk_grad_kernel, dim3((unsigned)(B * T)), dim3(CE_THREADS), 0, (cudaStream_t)stream_,
+                       (bf16*)logits, ld, (const long long*)target, target_stride0, (int)T, (int)chunk_begin,
+                       (int)chunk_cols, (int)V, label_smoothing, grad_scale, lse));
     PB_LAUNCH_CHECK();
     return 0;
 }
