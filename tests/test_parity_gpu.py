@@ -647,3 +647,27 @@ def test_failed_micro_batch_updates_nothing_and_is_reported():
     assert torch.equal(trainer.arena.exp_avg_sq, before[2])
     logs = trainer.train_step(iter([batches[1]]))
     assert 'failed' not in logs and logs['num_tokens'] > 0 and not torch.equal(trainer.arena.param, before[0])
+
+
+def test_pdl_switch():
+    """PB200_PDL=0 (kernels launched without the programmatic-dependent-launch attribute: csrc/common.cuh launch_pdl) must not
+    change a result: the same forward + backward in two child processes, with and without it. The forward pass has no
+    order-dependent accumulation, so the loss is identical; weight gradients are reduce-added by split-K CTAs in whatever order
+    they finish, hence a tolerance of 1e-3 of each tensor's largest entry for them."""
+    import json
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_pdl_probe.py')
+    outs = []
+    for pdl in ('1', '0'):
+        env = dict(os.environ, PB200_PDL=pdl)
+        res = subprocess.run([sys.executable, probe], env=env, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
+    on, off = outs
+    assert on['loss'] == off['loss'] and on['nll_loss'] == off['nll_loss']
+    assert on['grads'].keys() == off['grads'].keys() and len(on['grads']) > 20
+    for name, (s_on, m_on) in on['grads'].items():
+        s_off, m_off = off['grads'][name]
+        assert abs(m_on - m_off) <= 1e-3 * max(m_on, 1e-6), name
+        assert abs(s_on - s_off) <= 1e-3 * max(s_on, 1e-6), name
