@@ -578,15 +578,19 @@ class DropoutAddLNFn(torch.autograd.Function):
         x = _c(x)
         residual = _c(residual) if residual is not None else None
         seed, offset = DropoutState.next() if p > 0 else (0, 0)
-        y, s, mean, rstd = K.dropout_add_ln_fwd(x, residual, gamma, beta, eps, p, seed, offset)
-        ctx.save_for_backward(s if gamma is not None else None, gamma, mean, rstd)
+        # with LayerNorm the keep bits are stored (one byte per 8 elements): backward then reads them instead of redoing the
+        # Philox rounds, which is also what selects csrc/norm.cu's training-shape backward kernel
+        keep = (torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device)
+                if p > 0 and gamma is not None and x.shape[1] % 8 == 0 else None)
+        y, s, mean, rstd = K.dropout_add_ln_fwd(x, residual, gamma, beta, eps, p, seed, offset, keep_out=keep)
+        ctx.save_for_backward(s if gamma is not None else None, gamma, mean, rstd, keep)
         ctx.cfg = (p, seed, offset, residual is not None, beta is not None)
         ctx.params = (gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        s, gamma, mean, rstd = ctx.saved_tensors
+        s, gamma, mean, rstd, keep = ctx.saved_tensors
         p, seed, offset, has_res, has_beta = ctx.cfg
         dy = _c(dy)
         D = dy.shape[1]
@@ -596,7 +600,7 @@ class DropoutAddLNFn(torch.autograd.Function):
         dgamma = sg if sg is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if gamma is not None else None)
         dbeta = sb if sb is not None else (torch.empty(D, dtype=dy.dtype, device=dy.device) if (gamma is not None and has_beta) else None)
         dx, dres = K.dropout_add_ln_bwd(dy, None, s, gamma, mean, rstd, p, seed, offset, has_res, dgamma, dbeta,
-                                        accumulate=ag or ab)
+                                        accumulate=ag or ab, keep_mask=keep)
         _ready(p_gamma, p_beta)
         return dx, dres, _ret(dgamma, sg), _ret(dbeta, sb), None, None
 
