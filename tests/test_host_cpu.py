@@ -330,3 +330,23 @@ def test_config_argv_surface_and_unknown_options(tmp_path):
         TrainingConfig.from_dict({'not_an_option': 1})
     with pytest.raises(NotImplementedError):
         TrainingConfig.from_dict({'fsdp': True})
+
+
+def test_roofline_work_accounting():
+    """The algorithmic FLOPs / bytes bench.py divides the in-situ kernel times by (pasero_b200/kernels.py: _attn_flops,
+    _ln_bytes, _ce_bytes) against the figures DESIGN.md section 4 states, at the config-2 shapes."""
+    from pasero_b200 import kernels as K
+    B, H, Lq, Lk = 64, 8, 250, 250
+    q = torch.empty(B * Lq, H * 64)
+    # forward: 4 B H Lq Lk 64 FLOPs; backward 2.5 x; a causal mask halves it
+    assert K._attn_flops(1.0)(q, q, q, B, H, Lq, Lk, None, False, 0.125) == ('flop', 4.0 * B * H * Lq * Lk * 64)
+    assert K._attn_flops(1.0)(q, q, q, B, H, 48, 48, None, True, 0.125) == ('flop', 2.0 * B * H * 48 * 48 * 64)
+    bwd = K._attn_flops(2.5)(q, q, q, q, q, q, B, H, Lq, Lk, None, False, 0.125, q, q, q)
+    assert bwd == ('flop', 10.0 * B * H * Lq * Lk * 64)
+    x = torch.empty(16000, 512)
+    assert K._ln_bytes(x) == ('byte', 4.0 * 16000 * 512 * 2)            # four [M, D] 16-bit streams
+    logits, target = torch.empty(3072, 8032), torch.empty(64, 48, dtype=torch.int64)
+    assert K._ce_bytes(logits, target, 1, 0.1, None) == ('byte', 2.0 * 3072 * 8032 * 2)     # read once, gradient written over it
+    padded = torch.empty(3072, 8040)
+    assert K._ce_bytes(padded, target, 1, 0.1, None, vocab=8032) == ('byte', 2.0 * 3072 * 8032 * 2)
+    assert K._ce_bytes(padded, target, 1, 0.1, None, True, 1.0, None, 8032) == ('byte', 2.0 * 3072 * 8032 * 2)
