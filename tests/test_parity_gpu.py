@@ -652,7 +652,7 @@ def test_failed_micro_batch_updates_nothing_and_is_reported():
 def test_pdl_switch():
     """PB200_PDL=0 (kernels launched without the programmatic-dependent-launch attribute: csrc/common.cuh launch_pdl) must not
     change a result: the same forward + backward in two child processes, with and without it. The forward pass has no
-    order-dependent accumulation, so the loss is identical; weight gradients are reduce-added by split-K CTAs in whatever order
+    order-dependent accumulation beyond the fp64 sums of the step scalars, so the loss agrees to 1e-6; weight gradients are reduce-added by split-K CTAs in whatever order
     they finish, hence a tolerance of 1e-3 of each tensor's largest entry for them."""
     import json
     import subprocess
@@ -665,7 +665,8 @@ def test_pdl_switch():
         assert res.returncode == 0, res.stderr[-2000:]
         outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
     on, off = outs
-    assert on['loss'] == off['loss'] and on['nll_loss'] == off['nll_loss']
+    # (the step scalars are fp64 atomic sums over the target rows: their order, and so the last bits, may differ)
+    assert abs(on['loss'] - off['loss']) <= 1e-6 * abs(on['loss']) and abs(on['nll_loss'] - off['nll_loss']) <= 1e-6 * abs(on['nll_loss'])
     assert on['grads'].keys() == off['grads'].keys() and len(on['grads']) > 20
     for name, (s_on, m_on) in on['grads'].items():
         s_off, m_off = off['grads'][name]
